@@ -1,0 +1,304 @@
+/*
+ * glc_b200.h -- C-ABI of the B200-native node-ODE evolver for Galacticus.
+ *
+ * This is the drop-in boundary for ONE path of the reference: the per-node ODE
+ * integration performed by mergerTreeNodeEvolverStandard
+ *   (source/merger_trees/node_evolver/standard.F90:385-755, "standardEvolve")
+ * including its RHS (standardODEs :831-946, standardDerivativesCompute :1019-1061),
+ * post-step hook (:1160-1185), the GSL driver chain below it
+ *   (source/numerical/ODE_solver/solver.F90:492-636,
+ *    source/external/gslODEInitVal2/driver2.c:148-250, cscal2.c:93-169,
+ *    libgsl-2.6 rkck.c / evolve.c)
+ * and the standard-component rate functions reached from nodeOperatorMulti
+ *   (source/nodes/operators/multi.F90:313-332).
+ *
+ * All entry points are extern "C", take plain pointers/sizes and are callable from
+ * Fortran through ISO_C_BINDING (see INTEGRATION.md for the bind(C) interface block
+ * and the mergerTreeNodeEvolverB200 shim a maintainer would add).  No torch types.
+ *
+ * Units follow Galacticus: Msun, Mpc, km/s, Gyr.
+ */
+#ifndef GLC_B200_H
+#define GLC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLC_ABI_VERSION 1
+
+/* ---------------------------------------------------------------------------------
+ * Node record.  One row of GLC_NPROP doubles per node, node-major ("what
+ * treeNode%serializeValues would write", python/Galacticus/Build/Components/
+ * TreeNodes/ODESolver.py:95-138, extended by the analytic / non-evolved properties
+ * the RHS reads).  Component class order and property order follow the generated
+ * serialization (alphabetical component classes, XML property order).
+ * ------------------------------------------------------------------------------- */
+enum glc_prop {
+    /* --- numerically integrated properties (the ODE state vector y) ------------- */
+    /* blackHole/standard  objects/nodes/components/black_hole/standard/_class.F90:42 */
+    GLC_P_BH_MASS = 0,
+    GLC_P_BH_SPIN,
+    /* disk/standard       objects/nodes/components/disk/standard/_class.F90:42-130 */
+    GLC_P_DISK_MASS_STELLAR,
+    GLC_P_DISK_ABUND_STELLAR, /* abundancesStellar (single "metals" scalar)  */
+    GLC_P_DISK_MASS_GAS,
+    GLC_P_DISK_ABUND_GAS,
+    GLC_P_DISK_ANGMOM,
+    /* hotHalo/standard    objects/nodes/components/hot_halo/standard/_class.F90:50-180 */
+    GLC_P_HH_MASS,
+    GLC_P_HH_ABUND,
+    GLC_P_HH_ANGMOM,
+    GLC_P_HH_OUTFLOWED_MASS,
+    GLC_P_HH_OUTFLOWED_ANGMOM,
+    GLC_P_HH_OUTFLOWED_ABUND,
+    GLC_P_HH_UNACCRETED_MASS,
+    GLC_P_HH_UNACCRETED_ABUND,
+    GLC_P_HH_OUTER_RADIUS,
+    GLC_P_HH_STRIPPED_MASS,
+    GLC_P_HH_STRIPPED_ABUND,
+    /* satellite/standard  objects/nodes/components/satellite/standard.F90:33 */
+    GLC_P_SAT_BOUND_MASS,
+    /* spheroid/standard   objects/nodes/components/spheroid/standard/_class.F90:44 */
+    GLC_P_SPH_MASS_STELLAR,
+    GLC_P_SPH_ABUND_STELLAR,
+    GLC_P_SPH_MASS_GAS,
+    GLC_P_SPH_ABUND_GAS,
+    GLC_P_SPH_ANGMOM,
+    GLC_NY, /* = 24: size of the ODE state */
+
+    /* --- analytic / non-evolved properties read (and some written) by the path --- */
+    GLC_P_TIME = GLC_NY,     /* basic%time(): in = start, out = time reached            */
+    GLC_P_TIME_STEP,         /* node%timeStep(): in = step guess (<=0: none), out = last */
+    GLC_P_MASS_TARGET,       /* basic mass at GLC_P_TIME_TARGET (massDMOTarget meta-property,
+                                nodes/operators/physics/dark_matter_only_mass/interpolate.F90:216-238) */
+    GLC_P_MASS_RATE,         /* basic%accretionRate()                                   */
+    GLC_P_TIME_TARGET,       /* parent%basic%time()                                     */
+    GLC_P_DMSCALE_TARGET,    /* darkMatterProfile%scale() target (…/dark_matter_profile_scale/interpolate.F90) */
+    GLC_P_DMSCALE_RATE,
+    GLC_P_SPIN_TARGET,       /* spin%angularMomentum() target (…/halo_angular_momentum_interpolate.F90) */
+    GLC_P_SPIN_RATE,
+    GLC_P_TIME_LAST_ISOLATED,/* basic%timeLastIsolated(); <=0 -> use time               */
+    GLC_P_DISK_RADIUS,       /* disk%radius()   (in = warm start, out = solved)         */
+    GLC_P_DISK_VELOCITY,
+    GLC_P_SPH_RADIUS,
+    GLC_P_SPH_VELOCITY,
+    GLC_P_BASIC_MASS,        /* out: basic%mass() at the time reached                   */
+    GLC_NPROP
+};
+
+/* component-existence / status bits (int32 per node) */
+enum glc_flag {
+    GLC_F_HAS_HOTHALO  = 1 << 0,
+    GLC_F_HAS_DISK     = 1 << 1,
+    GLC_F_HAS_SPHEROID = 1 << 2,
+    GLC_F_HAS_BH       = 1 << 3,
+    GLC_F_IS_SATELLITE = 1 << 4
+};
+
+/* per-node status: errorStatus* of source/error/_module.F90 as used at
+ * node_evolver/standard.F90:392-393,697-720 */
+enum glc_status {
+    GLC_STATUS_SUCCESS   = 0,
+    GLC_STATUS_FAIL      = 1,
+    GLC_STATUS_UNDERFLOW = 2, /* errorStatusUnderflow: 8 trials exhausted (standard.F90:707-722) */
+    GLC_STATUS_NONFINITE = 3  /* device flagged NaN/Inf where the reference would trap (-ffpe-trap) */
+};
+
+/* interrupt codes = which functionInterrupt the host must call
+ * (python/Galacticus/Build/Components/Properties/Evolve.py:486-493; black_holes/seed.F90:179-180) */
+enum glc_interrupt {
+    GLC_INT_NONE = 0,
+    GLC_INT_HOTHALO_CREATE,  /* hotHaloCreateByInterrupt  */
+    GLC_INT_DISK_CREATE,     /* diskCreateByInterrupt     */
+    GLC_INT_SPHEROID_CREATE, /* spheroidCreateByInterrupt */
+    GLC_INT_BH_CREATE        /* blackHoleCreate           */
+};
+
+enum glc_model {
+    GLC_MODEL_BOX = 0,      /* testSuite/parameters/reproducibility/{closedBox,leakyBox}.xml physics */
+    GLC_MODEL_STANDARD = 1  /* parameters/quickTest.xml operator set                                  */
+};
+
+/* ---------------------------------------------------------------------------------
+ * Parameters: flat POD filled once by the Fortran shim from the already-constructed
+ * objects.  Field names follow the XML parameter names.
+ * ------------------------------------------------------------------------------- */
+typedef struct glc_params {
+    int32_t abi_version; /* GLC_ABI_VERSION */
+    int32_t model;       /* enum glc_model  */
+    /* mergerTreeNodeEvolverStandard, node_evolver/standard.F90:166-253 */
+    double odeToleranceAbsolute;
+    double odeToleranceRelative;
+    int32_t reuseODEStepSize;
+    int32_t enforceNonNegativity;
+    int32_t resolveInterruptsOnDevice; /* 1: component-creation interrupts are applied in the
+                                          kernel and the segment restarted (equivalent to the
+                                          host loop evolver/standard.F90:425-476); 0: return to host */
+    int32_t pad0;
+    /* cosmologyParameters */
+    double OmegaMatter, OmegaBaryon, HubbleConstant;
+    /* stellarPopulation standard / instantaneous (stellar_populations/properties/instantaneous.F90) */
+    double recycledFraction, metalYield;
+    /* box model: starFormationRateDisks=timescale(fixed), stellarFeedbackOutflows=fixed */
+    double box_timescaleStarFormation;
+    double box_fractionOutflow;
+    /* accretionHalo simple */
+    double timeReionization, velocitySuppressionReionization;
+    /* hot halo */
+    double hotHaloBeta;                /* hotHaloMassDistribution betaProfile [beta] */
+    double coreRadiusOverVirialRadius; /* hotHaloMassDistributionCoreRadius virialFraction */
+    double hotHaloScaleMassRelative, hotHaloScaleRadiusRelative; /* hot_halo/standard/_class.F90:226-227 */
+    double outflowStrippingEfficiency; /* hotHaloOutflowStripping standard [efficiency] */
+    double reincorporationMultiplier;  /* hotHaloOutflowReincorporation haloDynamicalTime [multiplier] */
+    double fractionLossAngularMomentum;/* coolingInfallTorque fixed */
+    double coolingVelocityCutOff;      /* coolingRate whiteFrenk1991 [velocityCutOff] */
+    double coolingDegreesOfFreedom;    /* coolingTime simple [degreesOfFreedom] */
+    double rateMaximumExpulsion;       /* nodeOperator CGMCoolingHeating */
+    int32_t excessHeatDrivesOutflow;
+    int32_t allowNegativeCGMMass;      /* nodeOperator CGMAccretion */
+    /* star formation: krumholz2009 + intgrtdSurfaceDensity */
+    double frequencyStarFormation, clumpingFactorMolecularComplex;
+    double sfrIntegrationTolerance;    /* starFormationRateDisks intgrtdSurfaceDensity [tolerance] */
+    /* star formation spheroids: timescale dynamicalTime */
+    double sfSpheroidEfficiency, sfSpheroidExponentVelocity, sfSpheroidTimescaleMinimum;
+    /* stellar feedback (power law inside rate limit) */
+    double fbDiskVelocityCharacteristic, fbDiskExponent;
+    double fbSpheroidVelocityCharacteristic, fbSpheroidExponent;
+    double fbTimescaleOutflowFractionalMinimum;
+    /* disk / spheroid components */
+    double diskToleranceAbsoluteMass, spheroidToleranceAbsoluteMass;
+    double spheroidRatioAngularMomentumScaleRadius, spheroidEfficiencyEnergeticOutflow;
+    /* galactic structure */
+    double structureSolutionTolerance; /* galacticStructureSolverEquilibrium [solutionTolerance] */
+    double adiabaticA, adiabaticOmega;  /* darkMatterProfile adiabaticGnedin2004 */
+    int32_t includeBaryonGravity;
+    int32_t adiabaticContraction;       /* 1: adiabaticGnedin2004, 0: darkMatterOnly */
+    /* bar instability efstathiou1982 */
+    double barStabilityThresholdGaseous, barStabilityThresholdStellar;
+    /* black holes */
+    double bhSeedMass, bhSeedSpin;
+    double bondiHoyleAccretionEnhancementSpheroid, bondiHoyleAccretionEnhancementHotHalo;
+    double bondiHoyleAccretionTemperatureSpheroid;
+    int32_t bondiHoyleAccretionHotModeOnly;
+    int32_t pad1;
+    double bhEfficiencyWind, bhEfficiencyRadioMode;
+    double accretionRateThinDiskMaximum, accretionRateThinDiskMinimum;
+    double adafEfficiencyRadiation, adafAdiabaticIndex;
+    /* operator enable mask (bit i = operator i of enum glc_operator); lets a host run
+       reduced operator sets exactly as a reduced <nodeOperator value="multi"> would */
+    uint32_t operatorMask;
+    uint32_t pad2;
+} glc_params;
+
+enum glc_operator {
+    GLC_OP_STAR_FORMATION_DISKS      = 1u << 0,
+    GLC_OP_STAR_FORMATION_SPHEROIDS  = 1u << 1,
+    GLC_OP_STELLAR_FEEDBACK_DISKS    = 1u << 2,
+    GLC_OP_STELLAR_FEEDBACK_SPHEROIDS= 1u << 3,
+    GLC_OP_BAR_INSTABILITY           = 1u << 4,
+    GLC_OP_BLACK_HOLES_SEED          = 1u << 5,
+    GLC_OP_BLACK_HOLES_ACCRETION     = 1u << 6,
+    GLC_OP_BLACK_HOLES_WINDS         = 1u << 7,
+    GLC_OP_CGM_ACCRETION             = 1u << 8,
+    GLC_OP_CGM_OUTFLOW_REINCORPORATION = 1u << 9,
+    GLC_OP_CGM_COOLING_HEATING       = 1u << 10,
+    GLC_OP_CGM_OUTER_RADIUS          = 1u << 11,
+    GLC_OP_SATELLITE_MASS_LOSS       = 1u << 12,
+    GLC_OP_ALL                       = 0x1fffu
+};
+
+/* ---------------------------------------------------------------------------------
+ * Tables (read-only inputs uploaded once).
+ * ------------------------------------------------------------------------------- */
+enum glc_table {
+    /* cooling function: CIE table, format of cooling/cooling_function/CIE_file.F90:30-134.
+       x0 = metallicities[n0] (linear, Solar units; first may be 0), x1 = temperatures[n1] (K),
+       values[n0][n1] = Lambda (erg cm^3 s^-1, i.e. cooling function / n_H^2). */
+    GLC_TABLE_COOLING_FUNCTION = 0,
+    /* electron density / n_H on the same kind of grid (chemical/state/CIE_file.F90) */
+    GLC_TABLE_ELECTRON_FRACTION = 1,
+    /* halo mean density table, linear in ln t (dark_matter_halos/scales/
+       virial_density_contrast.F90:356-417): x0 = times[n0] (Gyr, log-uniform), n1 = 2:
+       values[n0][0] = mean virial density (Msun/Mpc^3), values[n0][1] = its growth rate
+       d rho / dt  (:419-459). */
+    GLC_TABLE_HALO_MEAN_DENSITY = 2,
+    GLC_NTABLES
+};
+
+typedef struct glc_counters {
+    uint64_t steps_accepted; /* successful iterations of driver2.c:190 loop (the metric's "node-ODE steps") */
+    uint64_t steps_rejected; /* HADJ_DEC retries inside gsl_odeiv2_evolve_apply */
+    uint64_t rhs_evaluations;
+    uint64_t segments;       /* calls of standardEvolve (one per interrupt-delimited segment) */
+    uint64_t trials_failed;  /* trialCount increments (standard.F90:686-692) */
+    uint64_t nodes;
+} glc_counters;
+
+typedef struct glc_evolver glc_evolver; /* opaque; owns device arena, tables, stream */
+
+/* life cycle.  Return 0 on success, negative glc error code otherwise; never abort. */
+int glc_evolver_create(glc_evolver **out, int32_t device_ordinal);
+int glc_evolver_destroy(glc_evolver *ev);
+const char *glc_last_error(const glc_evolver *ev);
+int glc_abi_version(void);
+
+/* replaces: parameter hand-off done by the objectBuilder / constructor of
+ * mergerTreeNodeEvolverStandard (standard.F90:146-354) and of every physics class */
+int glc_evolver_set_params(glc_evolver *ev, const glc_params *params);
+/* fills *params with the defaults of parameters/quickTest.xml (model STANDARD) or
+ * testSuite/parameters/reproducibility/closedBox.xml (model BOX) */
+int glc_params_default(glc_params *params, int32_t model);
+
+/* replaces: the read of the tabulated inputs (CIE_file.F90:535-663 etc.) */
+int glc_evolver_set_table(glc_evolver *ev, int32_t table_id, int32_t n0, int32_t n1,
+                          const double *x0, const double *x1, const double *values);
+
+/*
+ * glc_evolve_batch -- batched mergerTreeNodeEvolver%evolve.
+ * replaces: n calls of standardEvolve(self,tree,node,timeEnd,interrupted,functionInterrupt,...)
+ *           (node_evolver/standard.F90:385) issued by evolver/standard.F90:452.
+ *   props      [n][GLC_NPROP] host, in/out   node records
+ *   flags      [n]            host, in/out   component bits (creation interrupts set bits)
+ *   time_end   [n]            host, in       timeEnd per node
+ *   status     [n]            host, out      enum glc_status
+ *   interrupt  [n]            host, out      enum glc_interrupt (GLC_INT_NONE if time_end reached)
+ *   counters                  host, out      accumulated over the batch (may be NULL)
+ */
+int glc_evolve_batch(glc_evolver *ev, int64_t n, double *props, int32_t *flags,
+                     const double *time_end, int32_t *status, int32_t *interrupt,
+                     glc_counters *counters);
+
+/*
+ * Device-resident variant: the arena is SoA in HBM, [GLC_NPROP][capacity] doubles.
+ * glc_arena_* move node records between host (node-major) and the arena;
+ * glc_evolve_arena runs the hot path on records already resident in HBM.
+ */
+int glc_arena_reserve(glc_evolver *ev, int64_t capacity);
+int glc_arena_upload(glc_evolver *ev, int64_t n, const double *props, const int32_t *flags,
+                     const double *time_end);
+int glc_arena_download(glc_evolver *ev, int64_t n, double *props, int32_t *flags, int32_t *status,
+                       int32_t *interrupt);
+int glc_evolve_arena(glc_evolver *ev, int64_t n, glc_counters *counters);
+/* duration (ms, CUDA events on the evolver's stream) of the last glc_evolve_arena kernel */
+float glc_last_kernel_ms(const glc_evolver *ev);
+/* raw device pointers for zero-copy interop (e.g. torch.distributed/NCCL reductions) */
+void *glc_arena_device_props(glc_evolver *ev);
+void *glc_evolver_stream(glc_evolver *ev);
+
+/* one evaluation of the RHS (standardODEs) for each node, for unit-level parity tests:
+ *   dydt [n][GLC_NY] host out; props/flags are not modified except radii warm starts. */
+int glc_rhs_batch(glc_evolver *ev, int64_t n, double *props, const int32_t *flags,
+                  double *dydt, int32_t *interrupt);
+
+/* histogram accumulation on device for the end-of-run reduction
+ * (mirrors output/analyses/volume_function_1d.F90:986-987): bins a property of the arena */
+int glc_histogram_accumulate(glc_evolver *ev, int64_t n, int32_t prop, double log10_min,
+                             double log10_max, int32_t n_bins, double *device_hist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLC_B200_H */
