@@ -1,0 +1,100 @@
+// glc_common.cuh -- device-side types shared by the kernels of libglcb200.
+//
+// Data layout in HBM:
+//   arena props : double [GLC_NPROP][capacity]   SoA, one column per node
+//   arena flags : int32  [capacity]
+//   workspace   : double [WS_NVEC][GLC_NY][nslots]  per-resident-thread RK stage vectors;
+//                 slot = global thread id, so every access is a coalesced 256-B line per warp
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/glc_b200.h"
+
+namespace glc {
+
+// ---- physical constants: source/numerical/constants/*.F90 with GSL-2.6 MKSA values ----
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kGravitationalConstant = 6.673e-11;  // GSL_CONST_MKSA_GRAVITATIONAL_CONSTANT
+constexpr double kParsec = 3.08567758135e16;          // GSL_CONST_MKSA_PARSEC
+constexpr double kMassSolar = 1.98892e30;             // GSL_CONST_MKSA_SOLAR_MASS
+constexpr double kBoltzmann = 1.3806504e-23;          // GSL_CONST_MKSA_BOLTZMANN
+constexpr double kAtomicMassUnit = 1.660538782e-27;   // GSL_CONST_MKSA_UNIFIED_ATOMIC_MASS
+constexpr double kSpeedLight = 2.99792458e8;          // GSL_CONST_MKSA_SPEED_OF_LIGHT
+constexpr double kThomsonCrossSection = 6.65245893699e-29;
+constexpr double kKilo = 1.0e3, kMega = 1.0e6, kGiga = 1.0e9, kHecto = 1.0e2, kErgs = 1.0e-7;
+constexpr double kMegaParsec = kMega * kParsec;
+constexpr double kYear = 3.15581497635456e7;
+constexpr double kGigaYear = kGiga * kYear;
+constexpr double kGInternal = kGravitationalConstant * kMassSolar / (kKilo * kKilo) / kMegaParsec;
+constexpr double kMpcPerKmPerSToGyr = kMegaParsec / kKilo / kGigaYear;
+constexpr double kHydrogenByMassSolar = 0.7070, kHeliumByMassSolar = 0.2740;
+constexpr double kMetallicitySolar = 0.0188;
+constexpr double kHydrogenByMassPrimordial = 0.7514, kHeliumByMassPrimordial = 0.2486;
+constexpr double kAtomicMassHydrogen = 1.0078250322, kAtomicMassHelium = 4.0026032545;
+constexpr double kMassHydrogenAtom = kAtomicMassHydrogen * kAtomicMassUnit;
+constexpr double kMeanAtomicMassPrimordial =
+    1.0 / (2.0 * kHydrogenByMassPrimordial / kAtomicMassHydrogen +
+           3.0 * kHeliumByMassPrimordial / kAtomicMassHelium);
+constexpr double kFeedbackEnergyInputAtInfinityCanonical = 4.517e5;
+
+// GSL status codes on the path
+constexpr int kGslSuccess = 0, kGslFailure = -1, kGslContinue = -2;
+
+constexpr int NY = GLC_NY;
+constexpr int NPROP = GLC_NPROP;
+
+// workspace vector ids
+enum : int { WS_YA = 0, WS_YB, WS_KA, WS_KB, WS_K2, WS_K3, WS_K4, WS_K5, WS_K6, WS_SCALE, WS_NVEC };
+
+struct DeviceTable2D {
+    int n0, n1;
+    const double *x0, *x1, *v;  // device pointers; v[n0][n1]
+};
+
+struct DeviceTables {
+    // CIE tables pre-processed as cieFileReadFile does (CIE_file.F90:627-659)
+    DeviceTable2D cooling;   // x0 = ln Z (or -999), x1 = ln T, v = ln Lambda when cooling_log
+    int cooling_log, cooling_first_z_zero;
+    double cooling_first_nonzero_z, cooling_z_min, cooling_z_max, cooling_t_min, cooling_t_max;
+    DeviceTable2D electron;
+    int electron_log, electron_first_z_zero;
+    double electron_first_nonzero_z, electron_z_min, electron_z_max, electron_t_min, electron_t_max;
+    // halo mean density, uniform in ln t
+    DeviceTable2D density;   // x0 = ln t, v[n0][2] = {rho_mean, d rho_mean/dt}
+    double density_lnt0, density_inv_dlnt;
+};
+
+struct KernelArgs {
+    double *props;        // [NPROP][cap]
+    int32_t *flags;       // [cap]
+    const double *time_end;  // [cap]
+    int32_t *status;      // [cap]
+    int32_t *interrupt;   // [cap]
+    int64_t cap;
+    int n;
+    double *ws;           // [WS_NVEC][NY][nslots]
+    int64_t nslots;
+    int *work_counter;
+    unsigned long long *counters;  // 6 x u64, layout of glc_counters
+};
+
+// Per-node context kept in registers while a node is resident in a thread.
+struct NodeCtx {
+    int flags;
+    // linear-in-time interpolants of the analytically solved properties
+    double massTarget, massRate, timeTarget;
+    double scaleTarget, scaleRate, spinTarget, spinRate;
+    double timeLastIsolated;
+    // their current values (refreshed by solve_analytics at every RHS call)
+    double basicMass, dmScale, spinJ;
+    // structure-solver state (warm start in, solution out)
+    double diskRadius, diskVelocity, sphRadius, sphVelocity;
+};
+
+// single translation unit (glc_api.cu): defined here
+__constant__ glc_params c_params;
+__constant__ DeviceTables c_tables;
+
+}  // namespace glc

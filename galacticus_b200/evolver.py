@@ -1,0 +1,160 @@
+"""Host-side handle on the C-ABI shared library ``libglcb200.so``.
+
+This is a thin ctypes binding used by tests and ``bench.py``; the production host is the
+Fortran shim shown in INTEGRATION.md (or the C++ mirror in ``csrc/host``), which binds the same
+``extern "C"`` entry points.  There is NO CPU fallback: if the CUDA extension is missing or no
+GPU is visible, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libglcb200.so")
+_LIB = None
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+class GlcError(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """Load libglcb200.so (built in-tree by build.sh / __graft_entry__.build())."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise GlcError(
+            f"{LIB_PATH} is missing: build it with ./build.sh (nvcc, sm_100a). "
+            "galacticus_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.glc_abi_version.restype = C.c_int
+    L.glc_last_error.restype = C.c_char_p
+    L.glc_last_error.argtypes = [vp]
+    L.glc_evolver_create.argtypes = [C.POINTER(vp), C.c_int32]
+    L.glc_evolver_destroy.argtypes = [vp]
+    L.glc_evolver_set_params.argtypes = [vp, C.POINTER(abi.glc_params)]
+    L.glc_params_default.argtypes = [C.POINTER(abi.glc_params), C.c_int32]
+    L.glc_evolver_set_table.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, _dp, vp, _dp]
+    L.glc_evolve_batch.argtypes = [vp, C.c_int64, _dp, _ip, _dp, _ip, _ip, C.POINTER(abi.glc_counters)]
+    L.glc_arena_reserve.argtypes = [vp, C.c_int64]
+    L.glc_arena_upload.argtypes = [vp, C.c_int64, _dp, _ip, _dp]
+    L.glc_arena_download.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+    L.glc_evolve_arena.argtypes = [vp, C.c_int64, C.POINTER(abi.glc_counters)]
+    L.glc_last_kernel_ms.restype = C.c_float
+    L.glc_last_kernel_ms.argtypes = [vp]
+    L.glc_arena_device_props.restype = vp
+    L.glc_arena_device_props.argtypes = [vp]
+    L.glc_evolver_stream.restype = vp
+    L.glc_evolver_stream.argtypes = [vp]
+    L.glc_rhs_batch.argtypes = [vp, C.c_int64, _dp, _ip, _dp, _ip]
+    L.glc_histogram_accumulate.argtypes = [vp, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int32, vp]
+    if L.glc_abi_version() != abi.GLC_ABI_VERSION:
+        raise GlcError("libglcb200.so ABI version does not match include/glc_b200.h")
+    _LIB = L
+    return L
+
+
+def params_default(model: int) -> abi.glc_params:
+    p = abi.glc_params()
+    rc = load_library().glc_params_default(C.byref(p), model)
+    if rc != 0:
+        raise GlcError(f"glc_params_default failed ({rc})")
+    return p
+
+
+class Evolver:
+    """Batched ``mergerTreeNodeEvolver`` on one GPU (mirrors
+    source/merger_trees/node_evolver/_class.F90:34-82, batched)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.glc_evolver_create(C.byref(self.h), device)
+        if rc != 0:
+            raise GlcError(f"glc_evolver_create(device={device}) failed ({rc}): no usable CUDA device? "
+                           "galacticus_b200 has no CPU fallback.")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.glc_evolver_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.L.glc_last_error(self.h)
+            raise GlcError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def set_params(self, p: abi.glc_params) -> None:
+        self.params = p
+        self._check(self.L.glc_evolver_set_params(self.h, C.byref(p)), "glc_evolver_set_params")
+
+    def set_table(self, table_id: int, x0, x1, values) -> None:
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        values = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
+        n0 = x0.size
+        if x1 is None:
+            n1 = values.size // n0
+            x1p = None
+        else:
+            x1 = np.ascontiguousarray(x1, dtype=np.float64)
+            n1 = x1.size
+            x1p = x1.ctypes.data_as(C.c_void_p)
+        assert values.size == n0 * n1
+        self._check(self.L.glc_evolver_set_table(self.h, table_id, n0, n1, x0, x1p, values), "glc_evolver_set_table")
+
+    def evolve_batch(self, props, flags, time_end):
+        """In-place on host arrays; returns (status, interrupt, counters)."""
+        n = props.shape[0]
+        assert props.shape == (n, abi.NPROP) and props.dtype == np.float64 and props.flags.c_contiguous
+        status = np.zeros(n, dtype=np.int32)
+        interrupt = np.zeros(n, dtype=np.int32)
+        c = abi.glc_counters()
+        te = np.ascontiguousarray(time_end, dtype=np.float64)
+        self._check(self.L.glc_evolve_batch(self.h, n, props, flags, te, status, interrupt, C.byref(c)), "glc_evolve_batch")
+        return status, interrupt, abi.counters_dict(c)
+
+    # ---- device-resident path
+    def arena_upload(self, props, flags, time_end):
+        n = props.shape[0]
+        te = np.ascontiguousarray(time_end, dtype=np.float64)
+        self._check(self.L.glc_arena_upload(self.h, n, props, flags, te), "glc_arena_upload")
+
+    def evolve_arena(self, n: int):
+        c = abi.glc_counters()
+        self._check(self.L.glc_evolve_arena(self.h, n, C.byref(c)), "glc_evolve_arena")
+        return abi.counters_dict(c), float(self.L.glc_last_kernel_ms(self.h))
+
+    def arena_download(self, n: int):
+        props = np.zeros((n, abi.NPROP), dtype=np.float64)
+        flags = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        interrupt = np.zeros(n, dtype=np.int32)
+        vp = C.c_void_p
+        self._check(self.L.glc_arena_download(self.h, n, props.ctypes.data_as(vp), flags.ctypes.data_as(vp),
+                                              status.ctypes.data_as(vp), interrupt.ctypes.data_as(vp)),
+                    "glc_arena_download")
+        return props, flags, status, interrupt
+
+    def rhs_batch(self, props, flags):
+        n = props.shape[0]
+        dydt = np.zeros((n, abi.NY), dtype=np.float64)
+        interrupt = np.zeros(n, dtype=np.int32)
+        p = props.copy()
+        self._check(self.L.glc_rhs_batch(self.h, n, p, flags, dydt, interrupt), "glc_rhs_batch")
+        return dydt, interrupt, p
