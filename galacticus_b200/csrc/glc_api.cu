@@ -114,7 +114,12 @@ __global__ void rhs_kernel(KernelArgs A, double *dydt) {
     ctx.sphRadius = AR(GLC_P_SPH_RADIUS);
     ctx.sphVelocity = AR(GLC_P_SPH_VELOCITY);
     ctx.basicMass = AR(GLC_P_BASIC_MASS);
+    ctx.dmScale = AR(GLC_P_DMSCALE);
+    ctx.spinJ = AR(GLC_P_SPIN);
+    ctx.massBaryonicSubhalos = AR(GLC_P_MASS_BARYONIC_SUBHALOS);
+    ctx.numericsFailed = 0;
     const double time = AR(GLC_P_TIME);
+    ctx.timeNode = time;
     Model::solve_analytics(ctx, time);
     const int code = Model::rates(ctx, time, y, rate);
     const uint32_t mask = Model::active_mask(ctx.flags);
@@ -336,6 +341,11 @@ int glc_evolver_set_table(glc_evolver *ev, int32_t id, int32_t n0, int32_t n1, c
         ev->tables.density = d;
         ev->tables.density_lnt0 = lnt[0];
         ev->tables.density_inv_dlnt = (double)(n0 - 1) / (lnt[n0 - 1] - lnt[0]);
+    } else if (id == GLC_TABLE_DISK_ROTATION_CURVE) {
+        if (n1 != 1) return -1;
+        ev->tables.diskrc = d;
+        ev->tables.diskrc_lnx0 = std::log(hx0[0]);
+        ev->tables.diskrc_inv_dlnx = (double)(n0 - 1) / (std::log(hx0[n0 - 1]) - std::log(hx0[0]));
     }
     return 0;
 }

@@ -64,6 +64,9 @@ struct DeviceTables {
     // halo mean density, uniform in ln t
     DeviceTable2D density;   // x0 = ln t, v[n0][2] = {rho_mean, d rho_mean/dt}
     double density_lnt0, density_inv_dlnt;
+    // exponential-disk rotation-curve factor, uniform in ln(half-radius)
+    DeviceTable2D diskrc;
+    double diskrc_lnx0, diskrc_inv_dlnx;
 };
 
 struct KernelArgs {
@@ -91,6 +94,9 @@ struct NodeCtx {
     double basicMass, dmScale, spinJ;
     // structure-solver state (warm start in, solution out)
     double diskRadius, diskVelocity, sphRadius, sphVelocity;
+    double timeNode;              // basic%time() of the node outside the ODE solve (scale-set, pre/post-evolve hooks)
+    double massBaryonicSubhalos;  // frozen input, see GLC_P_MASS_BARYONIC_SUBHALOS
+    int numericsFailed;           // a nested solver (Brent/QAG) failed where the reference would abort
 };
 
 // single translation unit (glc_api.cu): defined here

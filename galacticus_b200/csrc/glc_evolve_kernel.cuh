@@ -42,7 +42,7 @@ constexpr int kTrialCountMaximum = 8;  // standard.F90:135
 constexpr int kSegmentGuard = 64;
 
 __device__ __forceinline__ bool prop_is_non_negative(int prop) {
-    return prop != GLC_P_BH_SPIN && prop != GLC_P_SAT_BOUND_MASS && prop != GLC_P_BH_MASS;
+    return prop != GLC_P_SAT_BOUND_MASS;  // isNonNegative attributes of the component definitions
 }
 
 template <class Model>
@@ -100,7 +100,12 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
             ctx.sphRadius = AR(GLC_P_SPH_RADIUS, node);
             ctx.sphVelocity = AR(GLC_P_SPH_VELOCITY, node);
             ctx.basicMass = AR(GLC_P_BASIC_MASS, node);
+            ctx.dmScale = AR(GLC_P_DMSCALE, node);
+            ctx.spinJ = AR(GLC_P_SPIN, node);
+            ctx.massBaryonicSubhalos = AR(GLC_P_MASS_BARYONIC_SUBHALOS, node);
+            ctx.numericsFailed = 0;
             timeStartSaved = AR(GLC_P_TIME, node);
+            ctx.timeNode = timeStartSaved;
             timeStepIn = AR(GLC_P_TIME_STEP, node);
             nSeg++;
             segmentsThisNode++;
@@ -351,7 +356,9 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
                 timeOut = tEnd;
                 timeStepOut = (timeStartSaved != tEnd && mask != 0u) ? h : -1.0;
             }
+            ctx.timeNode = timeOut;
             Model::post_evolve(ctx, y);
+            if (ctx.numericsFailed) nodeStatus = GLC_STATUS_NONFINITE;
             int code = interrupted ? interruptCode : GLC_INT_NONE;
             if (interrupted && c_params.resolveInterruptsOnDevice) {
                 // functionInterrupt: <class>CreateByInterrupt / blackHoleCreate
@@ -374,6 +381,8 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
             AR(GLC_P_SPH_RADIUS, node) = ctx.sphRadius;
             AR(GLC_P_SPH_VELOCITY, node) = ctx.sphVelocity;
             AR(GLC_P_BASIC_MASS, node) = ctx.basicMass;
+            AR(GLC_P_DMSCALE, node) = ctx.dmScale;
+            AR(GLC_P_SPIN, node) = ctx.spinJ;
             A.flags[node] = ctx.flags;
             if (interrupted && code == GLC_INT_NONE && timeOut < tEnd) {
                 if (segmentsThisNode < kSegmentGuard) {

@@ -1,14 +1,952 @@
-// placeholder (replaced by the full standard model)
+// glc_model_standard.cuh -- device rate functions for the operator set of parameters/quickTest.xml:
+// the RHS evaluated by standardDerivativesCompute (source/merger_trees/node_evolver/standard.F90:1019-1061)
+// through nodeOperatorMulti (source/nodes/operators/multi.F90:313-332), and the scale-set / pre-evolve /
+// post-step / post-evolve hooks of the standard components.  Citations are relative to
+// /root/reference/source.
+//
+// GPU layout of the computation: one thread = one node.  Everything a reference
+// "Calculations_Reset" memoises per RHS call (halo scales, beta-profile normalisation, cooling
+// function at (T_vir, Z_hot), Krumholz factors, disk SFR) is computed once per call into a small
+// register-resident struct (Work) and re-used by the operators, which are fused into one pass that
+// accumulates directly into the rate vector.  Table look-ups go through the read-only path; the
+// nested adaptive numerics (structure fixed point, Brent, QAG) are single-call-site state machines
+// (glc_numerics.cuh).
+//
+// Documented deviations from quickTest.xml ("out of scope / next"):
+// hotHaloRamPressureStripping=virialRadius; black-hole operators gated off by operatorMask; direct
+// solve for the first-guess radius; per-solve reset of the oscillation history; beta = 2/3.
 #pragma once
-#include "glc_model_box.cuh"
+
+#include "glc_common.cuh"
+#include "glc_numerics.cuh"
+
 namespace glc {
-struct ModelStandard {
-    static __device__ __forceinline__ uint32_t active_mask(int) { return 0; }
-    static __device__ __forceinline__ void solve_analytics(NodeCtx &, double) {}
-    static __device__ __forceinline__ void scales(const NodeCtx &, const double (&)[NY], double (&)[NY]) {}
-    static __device__ __forceinline__ int rates(NodeCtx &, double, const double (&)[NY], double (&)[NY]) { return 0; }
-    static __device__ __forceinline__ int post_step(NodeCtx &, double (&)[NY]) { return 0; }
-    static __device__ __forceinline__ void pre_evolve(NodeCtx &, double (&)[NY]) {}
-    static __device__ __forceinline__ void post_evolve(NodeCtx &, double (&)[NY]) {}
+
+struct Work {
+    // halo scales
+    double rhoMean, rvir, vvir, tdyn, tvir, dlnrhoDt;
+    // hot-halo beta profile
+    double hhRouter, hhRcore, hhRho0;
+    bool hhValid;
+    // cooling: t_cool(rho) = coolA / rho for the node's (T_vir, Z_hot)
+    double coolA, coolTavail, rcool;
+    bool coolReady;
+    bool plausible, solvable;
 };
+
+__device__ __forceinline__ double mass_to_fraction(double ab, double mass) {
+    // Abundances_Mass_To_Mass_Fraction, objects/abundances.F90:811-828
+    return (ab > mass) ? 1.0 : ((ab <= 0.0) ? 0.0 : ab / mass);
 }
+__device__ __forceinline__ double hydrogen_mass_fraction(double z) {
+    // objects/abundances.F90:830-850
+    double x = z / kMetallicitySolar * (kHydrogenByMassSolar - kHydrogenByMassPrimordial) + kHydrogenByMassPrimordial;
+    return fmin(fmax(x, 0.7), kHydrogenByMassPrimordial);
+}
+__device__ __forceinline__ double hydrogen_number_fraction(double z) {
+    const double nh = hydrogen_mass_fraction(z) / kAtomicMassHydrogen;
+    const double nhe = fmin(z / kMetallicitySolar * (kHeliumByMassSolar - kHeliumByMassPrimordial) + kHeliumByMassPrimordial,
+                            kHeliumByMassPrimordial) / kAtomicMassHelium;
+    return nh / (nh + nhe);
+}
+
+// ------------------------------------------------------------------ CIE tables (CIE_file.F90:665-735)
+__device__ __forceinline__ int locate(const double *__restrict__ x, int n, double v) {
+    int lo = 0, hi = n - 1;
+    while (hi > lo + 1) {
+        const int mid = (hi + lo) >> 1;
+        if (__ldg(x + mid) > v)
+            hi = mid;
+        else
+            lo = mid;
+    }
+    return lo + 1;
+}
+
+struct CieFactors {
+    int iT, iZ;
+    double hT, hZ;
+};
+
+__device__ __forceinline__ CieFactors cie_factors(const DeviceTable2D &t, bool isLog, bool firstZero,
+                                                  double firstNonzero, double temperature, double metallicity) {
+    CieFactors f;
+    double tu = isLog ? log(temperature) : temperature;
+    int i = min(max(locate(t.x1, t.n1, tu), 1), t.n1 - 1);
+    f.iT = i;
+    f.hT = (tu - __ldg(t.x1 + i - 1)) / (__ldg(t.x1 + i) - __ldg(t.x1 + i - 1));
+    double zu = fmax(metallicity, 0.0);
+    if (firstZero && zu < firstNonzero) {
+        f.iZ = 1;
+        f.hZ = zu / firstNonzero;
+    } else {
+        if (isLog) zu = log(zu);
+        i = min(max(locate(t.x0, t.n0, zu), 1), t.n0 - 1);
+        f.iZ = i;
+        f.hZ = (zu - __ldg(t.x0 + i - 1)) / (__ldg(t.x0 + i) - __ldg(t.x0 + i - 1));
+    }
+    return f;
+}
+__device__ __forceinline__ double cie_interpolate(const DeviceTable2D &t, bool isLog, const CieFactors &f) {
+    const double *a = t.v + (size_t)(f.iZ - 1) * t.n1 + (f.iT - 1);
+    const double *b = a + t.n1;
+    const double r = __ldg(a) * (1.0 - f.hT) * (1.0 - f.hZ) + __ldg(b) * (1.0 - f.hT) * f.hZ +
+                     __ldg(a + 1) * f.hT * (1.0 - f.hZ) + __ldg(b + 1) * f.hT * f.hZ;
+    return isLog ? exp(r) : r;
+}
+
+struct ModelStandard {
+    // ---------------------------------------------------------------- small accessors
+    static __device__ __forceinline__ bool has(const NodeCtx &c, int f) { return (c.flags & f) != 0; }
+
+    static __device__ __forceinline__ uint32_t active_mask(int flags) {
+        uint32_t m = 1u << GLC_P_SAT_BOUND_MASS;
+        if (flags & GLC_F_HAS_BH) m |= (1u << GLC_P_BH_MASS) | (1u << GLC_P_BH_SPIN);
+        if (flags & GLC_F_HAS_DISK) m |= 0x1fu << GLC_P_DISK_MASS_STELLAR;
+        if (flags & GLC_F_HAS_HOTHALO) m |= 0x7ffu << GLC_P_HH_MASS;
+        if (flags & GLC_F_HAS_SPHEROID) m |= 0x1fu << GLC_P_SPH_MASS_STELLAR;
+        return m;
+    }
+
+    static __device__ __forceinline__ void solve_analytics(NodeCtx &c, double time) {
+        // {dmo,dmpScale,haloAngMom}Interpolate...SolveAnalytics (dark_matter_only_mass/interpolate.F90:217-239,
+        // dark_matter_profile_scale/interpolate.F90:153-178, halo_angular_momentum_interpolate.F90:147-192)
+        if (c.massRate != 0.0) c.basicMass = c.massTarget + c.massRate * (time - c.timeTarget);
+        c.dmScale = c.scaleTarget + (time - c.timeTarget) * c.scaleRate;
+        c.spinJ = c.spinTarget + (time - c.timeTarget) * c.spinRate;
+    }
+
+    // ---------------------------------------------------------------- halo scales
+    static __device__ __forceinline__ void halo_scales(const NodeCtx &c, double timeNow, Work &w) {
+        // dark_matter_halos/scales/virial_density_contrast.F90:195-417
+        double time = c.timeLastIsolated;
+        if (!has(c, GLC_F_IS_SATELLITE) || time <= 0.0) time = timeNow;
+        const DeviceTable2D &t = c_tables.density;
+        const double lnt = log(time);
+        const double x = (lnt - c_tables.density_lnt0) * c_tables.density_inv_dlnt;
+        int i = (int)x;
+        if (lnt < c_tables.density_lnt0) i = 0;
+        i = max(min(i, t.n0 - 2), 0);
+        const double h = x - (double)i;
+        w.rhoMean = __ldg(t.v + 2 * i) * (1.0 - h) + __ldg(t.v + 2 * (i + 1)) * h;
+        w.dlnrhoDt = __ldg(t.v + 2 * i + 1) * (1.0 - h) + __ldg(t.v + 2 * (i + 1) + 1) * h;
+        w.rvir = cbrt(3.0 * c.basicMass / 4.0 / kPi / w.rhoMean);
+        w.vvir = sqrt(kGInternal * c.basicMass / w.rvir);
+        w.tdyn = w.rvir / w.vvir * kMpcPerKmPerSToGyr;
+        w.tvir = 0.5 * kAtomicMassUnit * kMeanAtomicMassPrimordial * ((kKilo * w.vvir) * (kKilo * w.vvir)) / kBoltzmann;
+    }
+
+    // ---------------------------------------------------------------- hot halo beta profile (beta = 2/3)
+    static __device__ __forceinline__ double hh_outer_radius(const Work &w, const double (&y)[NY]) {
+        // Node_Component_Hot_Halo_Standard_Outer_Radius, hot_halo/standard/_class.F90:430-450
+        return fmax(fmin(y[GLC_P_HH_OUTER_RADIUS], w.rvir), c_params.hotHaloScaleRadiusRelative * w.rvir);
+    }
+    static __device__ __forceinline__ void hh_profile(const NodeCtx &c, const double (&y)[NY], Work &w) {
+        // hot_halo/mass_distribution/beta_profile.F90:140-215; mass_distributions/spherical/beta_profile.F90:190-301
+        const bool hh = has(c, GLC_F_HAS_HOTHALO);
+        w.hhRouter = hh ? hh_outer_radius(w, y) : 0.0;
+        const double mass = hh ? y[GLC_P_HH_MASS] : 0.0;
+        w.hhRcore = c_params.coreRadiusOverVirialRadius * w.rvir;
+        w.hhValid = !(w.hhRouter <= 0.0 || mass <= 0.0);
+        w.hhRho0 = 0.0;
+        if (!w.hhValid) return;
+        const double r = w.hhRouter / w.hhRcore;
+        const double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - atan(r));
+        w.hhRho0 = mass / 4.0 / kPi / (w.hhRcore * w.hhRcore * w.hhRcore) * nf;
+    }
+    static __device__ __forceinline__ double hh_density(const Work &w, double radius) {
+        if (!w.hhValid || radius > w.hhRouter) return 0.0;
+        const double x = radius / w.hhRcore;
+        return w.hhRho0 / pow(1.0 + x * x, 1.5 * c_params.hotHaloBeta);
+    }
+    static __device__ __forceinline__ double hh_mass_enclosed(const Work &w, double radius) {
+        if (!w.hhValid) return 0.0;
+        if (radius > w.hhRouter) radius = w.hhRouter;
+        const double x = radius / w.hhRcore;
+        const double rc3 = w.hhRcore * w.hhRcore * w.hhRcore;
+        if (x < 1.0e-6)
+            return 4.0 * kPi * w.hhRho0 * rc3 * (x * x * x) * (1.0 / 3.0 + x * x * (-1.0 / 5.0 + x * x * (1.0 / 7.0)));
+        return 4.0 * kPi * w.hhRho0 * (x - atan(x)) * rc3;
+    }
+
+    // ---------------------------------------------------------------- cooling
+    // coolingTimeSimple (cooling/cooling_time/simple.F90:128-179) with the CIE tables evaluated once at
+    // (T_vir, Z_hot) -- the reference memoises the same way (CIE_file.F90:300-312): only n_H varies
+    // along the cooling-radius root find, so t_cool(rho) = coolA / rho.
+    static __device__ __forceinline__ void cooling_prepare(const double (&y)[NY], Work &w, double &logSlopeT) {
+        const double z = mass_to_fraction(y[GLC_P_HH_ABUND], y[GLC_P_HH_MASS]);
+        const DeviceTable2D &tc = c_tables.cooling;
+        const DeviceTable2D &te = c_tables.electron;
+        double tu = w.tvir, zu = z / kMetallicitySolar;
+        bool outsideT = false;
+        if (tu < c_tables.cooling_t_min) {
+            tu = c_tables.cooling_t_min;
+            outsideT = true;
+        }
+        if (tu > c_tables.cooling_t_max) {
+            tu = c_tables.cooling_t_max;
+            outsideT = true;
+        }
+        zu = fmin(fmax(zu, c_tables.cooling_z_min), c_tables.cooling_z_max);
+        const CieFactors f = cie_factors(tc, c_tables.cooling_log, c_tables.cooling_first_z_zero,
+                                         c_tables.cooling_first_nonzero_z, tu, zu);
+        const double lambda = cie_interpolate(tc, c_tables.cooling_log, f);
+        if (outsideT)
+            logSlopeT = 0.0;
+        else {
+            // cieFileCoolingFunctionTemperatureLogSlope :410-512
+            const double *a = tc.v + (size_t)(f.iZ - 1) * tc.n1 + (f.iT - 1);
+            const double *b = a + tc.n1;
+            double s = ((__ldg(a + 1) - __ldg(a)) * (1.0 - f.hZ) + (__ldg(b + 1) - __ldg(b)) * f.hZ) /
+                       (__ldg(tc.x1 + f.iT) - __ldg(tc.x1 + f.iT - 1));
+            if (!c_tables.cooling_log) s = s * w.tvir / lambda;
+            logSlopeT = s;
+        }
+        double te_t = fmin(fmax(w.tvir, c_tables.electron_t_min), c_tables.electron_t_max);
+        double te_z = fmin(fmax(z / kMetallicitySolar, c_tables.electron_z_min), c_tables.electron_z_max);
+        const CieFactors fe = cie_factors(te, c_tables.electron_log, c_tables.electron_first_z_zero,
+                                          c_tables.electron_first_nonzero_z, te_t, te_z);
+        const double efrac = cie_interpolate(te, c_tables.electron_log, fe);
+        // n_H = rho * c1 ; n_all = n_H (1/f_H + e) ; t_cool = dof/2 k T n_all / ergs / (Lambda n_H^2) / Gyr
+        const double c1 = hydrogen_mass_fraction(z) * kMassSolar / kMassHydrogenAtom / (kHecto * kHecto * kHecto) /
+                          (kMegaParsec * kMegaParsec * kMegaParsec);
+        const double nall = 1.0 / hydrogen_number_fraction(z) + efrac;
+        w.coolA = (lambda > 0.0)
+                      ? c_params.coolingDegreesOfFreedom / 2.0 * kBoltzmann * w.tvir * nall / kErgs / lambda / kGigaYear / c1
+                      : -1.0;
+        w.coolTavail = w.tdyn;  // whiteFrenk1991TimeAvailable, ageFactor = 0 (time_available/White-Frenk.F90:144-146)
+        w.coolReady = true;
+    }
+    static __device__ __forceinline__ double cooling_time(const Work &w, double density) {
+        const double timeLarge = 1.0e10;
+        return (w.coolA > 0.0 && density > 0.0) ? w.coolA / density : timeLarge;
+    }
+    static __device__ __forceinline__ double cooling_radius(const double (&y)[NY], Work &w, int &bad) {
+        // coolingRadiusSimple::radius, cooling/cooling_radius/simple.F90:313-387
+        const double router = w.hhRouter;
+        const double rootOuter = cooling_time(w, hh_density(w, router)) - w.coolTavail;
+        if (rootOuter < 0.0) return router;
+        const double rootZero = cooling_time(w, hh_density(w, 0.0)) - w.coolTavail;
+        if (rootZero > 0.0) return 0.0;
+        const RootOptions o{0.0, 1.0e-6, EXPAND_NONE, 0.0, 0.0, SIGN_NONE, SIGN_NONE};
+        int st;
+        const double r = root_find([&](double radius) { return cooling_time(w, hh_density(w, radius)) - w.coolTavail; },
+                                   o, 0.0, router, true, rootZero, rootOuter, st);
+        if (st != 0) bad = 1;
+        return r;
+    }
+
+    // ---------------------------------------------------------------- galactic structure
+    static __device__ __forceinline__ double disk_mass(const double (&y)[NY]) {
+        return fmax(0.0, y[GLC_P_DISK_MASS_STELLAR]) + fmax(0.0, y[GLC_P_DISK_MASS_GAS]);
+    }
+    static __device__ __forceinline__ double sph_mass(const double (&y)[NY]) {
+        return fmax(0.0, y[GLC_P_SPH_MASS_STELLAR]) + fmax(0.0, y[GLC_P_SPH_MASS_GAS]);
+    }
+    static __device__ __forceinline__ double disk_bessel_factor(double halfRadius) {
+        // exponentialDiskBesselFactorRotationCurve, mass_distributions/cylindrical/exponential_disk.F90:675-733
+        const double ln2 = 0.69314718055994530942, euler = 0.57721566490153286061;
+        if (halfRadius <= 0.0) return 0.0;
+        if (halfRadius < 1.0e-3) return (ln2 - euler - 0.5 - log(halfRadius)) * halfRadius * halfRadius;
+        const DeviceTable2D &t = c_tables.diskrc;
+        const double x = (log(halfRadius) - c_tables.diskrc_lnx0) * c_tables.diskrc_inv_dlnx;
+        const int i = max(min((int)x, t.n0 - 2), 0);
+        const double h = x - (double)i;
+        return __ldg(t.v + i) * (1.0 - h) + __ldg(t.v + i + 1) * h;
+    }
+    static __device__ __forceinline__ double baryonic_vc2(const NodeCtx &c, const double (&y)[NY], const Work &w,
+                                                          double radius) {
+        // rotation curve of massType=massTypeBaryonic: disk + spheroid + hot halo (gas + stars)
+        double v2 = 0.0;
+        if (!(radius > 0.0)) return 0.0;
+        if (has(c, GLC_F_HAS_DISK) && c.diskRadius > 0.0) {
+            const double rd = c.diskRadius, m = disk_mass(y), r = radius / rd;
+            if (r > 30.0)
+                v2 += kGInternal * m / radius;  // exponential_disk.F90:532-535
+            else
+                v2 += kGInternal * 2.0 * (m / rd) * disk_bessel_factor(0.5 * r);
+        }
+        if (has(c, GLC_F_HAS_SPHEROID) && c.sphRadius > 0.0) {
+            const double a = c.sphRadius, m = sph_mass(y);
+            v2 += kGInternal * m * radius / ((radius + a) * (radius + a));  // Hernquist
+        }
+        if (has(c, GLC_F_HAS_HOTHALO)) v2 += kGInternal * hh_mass_enclosed(w, radius) / radius;
+        return v2;
+    }
+    static __device__ __forceinline__ double nfw_mass_scale_free(double x) {
+        // massEnclosedScaleFree, mass_distributions/spherical/NFW.F90:550-571
+        if (x == 1.0) return log(2.0) - 0.5;
+        if (x >= 1.0e-6) return log(1.0 + x) - x / (1.0 + x);
+        return x * x * (0.5 + x * (-2.0 / 3.0 + x * (0.75 + x * (-0.8))));
+    }
+    // NFW M(<r) = nfwNorm * m(r/rs), nfwNorm = M_vir / m(c)  (NFW.F90:254-255,444-464)
+    static __device__ __forceinline__ double nfw_norm(const NodeCtx &c, const Work &w) {
+        const double conc = w.rvir / c.dmScale;
+        return c.basicMass / (log(1.0 + conc) - conc / (1.0 + conc));
+    }
+    static __device__ __forceinline__ double ac_orbital_mean(const Work &w, double radius) {
+        // sphericalAdiabaticGnedin2004RadiusOrbitalMean, adiabatic_Gnedin2004.F90:664-687
+        return c_params.adiabaticA * w.rvir * fast_exponentiate(1.0e-3, 1.0, c_params.adiabaticOmega, 1.0e4, radius / w.rvir);
+    }
+    static __device__ __forceinline__ double baryonic_mass_self(const NodeCtx &c, const double (&y)[NY]) {
+        double m = 0.0;
+        if (has(c, GLC_F_HAS_DISK)) m += disk_mass(y);
+        if (has(c, GLC_F_HAS_SPHEROID)) m += sph_mass(y);
+        if (has(c, GLC_F_HAS_HOTHALO)) m += fmax(0.0, y[GLC_P_HH_MASS]) + fmax(0.0, y[GLC_P_HH_OUTFLOWED_MASS]);
+        return m;
+    }
+    static __device__ __forceinline__ double dark_matter_mass_enclosed(const NodeCtx &c, const double (&y)[NY],
+                                                                       const Work &w, double nfwNorm, double radius,
+                                                                       int &bad) {
+        // adiabaticGnedin2004 over NFW: mass_distributions/spherical/adiabatic_Gnedin2004.F90:410-530,707-727;
+        // dark_matter_profiles/adiabatic_Gnedin2004.F90:302-364
+        const double rs = c.dmScale;
+        const double fDm = 1.0 - c_params.OmegaBaryon / c_params.OmegaMatter;
+        if (!c_params.adiabaticContraction) return nfwNorm * nfw_mass_scale_free(radius / rs);
+        if (radius <= 0.0) return 0.0;
+        double rInit;
+        if (radius >= w.rvir)
+            rInit = radius;
+        else {
+            const double mSelfRaw = baryonic_mass_self(c, y);
+            const double mSelf = fmax(mSelfRaw, 0.0);
+            const double mTot = fmax(mSelfRaw + c.massBaryonicSubhalos, 0.0);
+            const double fd = fmin(fDm + (mTot - mSelf) / c.basicMass, 1.0);
+            const double fi = fmin(fDm + mTot / c.basicMass, 1.0);
+            const double rmean = ac_orbital_mean(w, radius);
+            const double bterm = baryonic_vc2(c, y, w, rmean) * rmean * radius / kGInternal;
+            auto solver = [&](double ri) {
+                return nfwNorm * nfw_mass_scale_free(ac_orbital_mean(w, ri) / rs) * (fi * ri - fd * radius) - bterm;
+            };
+            const double menc = nfwNorm * nfw_mass_scale_free(rmean / rs);
+            double rup = radius;
+            if (menc > 0.0) rup = fmax((bterm / menc + fd * radius) / fi, radius);
+            // the reference first tests solver(r_vir) < 0 (:463-466)
+            const RootOptions o{0.0, 1.0e-2, EXPAND_MULTIPLICATIVE, 1.1, 0.9, SIGN_POSITIVE, SIGN_NEGATIVE};
+            int st = 0;
+            const double fVir = solver(w.rvir);
+            if (fVir < 0.0)
+                rInit = w.rvir;
+            else {
+                rInit = root_find(solver, o, radius, rup, false, 0.0, 0.0, st);
+                if (st != 0) bad = 1;
+            }
+        }
+        return fDm * nfwNorm * nfw_mass_scale_free(rInit / rs);
+    }
+    static __device__ __forceinline__ double nfw_radius_from_j(const NodeCtx &c, const Work &w, double nfwNorm, double j) {
+        // stands in for nfwRadiusFromSpecificAngularMomentum (NFW.F90:589-625): solve j = sqrt(G M(<r) r)
+        if (!(j > 0.0)) return 0.0;
+        const double lnj = log(j), rs = c.dmScale;
+        const RootOptions o{1.0e-12, 0.0, EXPAND_ADDITIVE, 2.0, -2.0, SIGN_POSITIVE, SIGN_NEGATIVE};
+        int st;
+        const double lnr = root_find(
+            [&](double lr) {
+                const double r = exp(lr);
+                return 0.5 * log(kGInternal * nfwNorm * nfw_mass_scale_free(r / rs) * r) - lnj;
+            },
+            o, log(w.rvir) - 4.0, log(w.rvir), false, 0.0, 0.0, st);
+        return (st != 0) ? w.rvir : exp(lnr);
+    }
+    static __device__ __forceinline__ void plausibility(const NodeCtx &c, const double (&y)[NY], double time, Work &w) {
+        // basic/standard/_class.F90:105-123; disk/standard/_class.F90:999-1049; spheroid/standard/_class.F90:1249-1296
+        w.plausible = true;
+        w.solvable = true;
+        if (c.basicMass <= 0.0 || time <= 0.0) {
+            w.plausible = false;
+            w.solvable = false;
+            return;
+        }
+        const double s0 = w.rvir * w.vvir;
+        if (has(c, GLC_F_HAS_DISK)) {
+            const double m = y[GLC_P_DISK_MASS_STELLAR] + y[GLC_P_DISK_MASS_GAS], j = y[GLC_P_DISK_ANGMOM];
+            if (m >= 0.0 && j > 0.0 && (j > 1.0e1 * m * s0 || j < 1.0e-6 * m * s0)) w.plausible = false;
+        }
+        if (w.plausible && has(c, GLC_F_HAS_SPHEROID)) {
+            const double m = y[GLC_P_SPH_MASS_STELLAR] + y[GLC_P_SPH_MASS_GAS], j = y[GLC_P_SPH_ANGMOM];
+            if (m >= 0.0 && j > 0.0 && (j > 1.0e1 * m * s0 || j < 1.0e-6 * m * s0)) w.plausible = false;
+        }
+    }
+    static __device__ __forceinline__ double component_j(const double (&y)[NY], int comp) {
+        // disk/standard/_class.F90:1112-1177 (ratio 1/2 for the exponential disk :345-356);
+        // spheroid/standard/_class.F90:1359-1407
+        const double j = comp == 0 ? y[GLC_P_DISK_ANGMOM] : y[GLC_P_SPH_ANGMOM];
+        const double m = comp == 0 ? y[GLC_P_DISK_MASS_GAS] + y[GLC_P_DISK_MASS_STELLAR]
+                                   : y[GLC_P_SPH_MASS_GAS] + y[GLC_P_SPH_MASS_STELLAR];
+        if (!(j >= 0.0)) return 0.0;
+        const double ratio = comp == 0 ? 0.5 : c_params.spheroidRatioAngularMomentumScaleRadius;
+        return ratio * ((m > 0.0) ? j / m : 0.0);
+    }
+    // galacticStructureSolverEquilibrium::solve, galactic_structure/radius_solver/equilibrium.F90:243-506
+    static __device__ __forceinline__ void structure_solve(NodeCtx &c, const double (&y)[NY], double time, Work &w,
+                                                           int &bad) {
+        plausibility(c, y, time, w);
+        if (!w.plausible) return;
+        const double tolerance = c_params.structureSolutionTolerance;
+        const double nfwNorm = nfw_norm(c, w);
+        double hist00 = -1.0, hist01 = -1.0, hist10 = -1.0, hist11 = -1.0;
+        double fit = 2.0 * tolerance;
+        int count = 0;
+        while (count <= 1 || (fit > tolerance && count < 100)) {
+            int active = 0;
+            count++;
+            if (count > 1) fit = 0.0;
+#pragma unroll 1
+            for (int comp = 0; comp < 2; comp++) {
+                if (!has(c, comp == 0 ? GLC_F_HAS_DISK : GLC_F_HAS_SPHEROID)) continue;
+                const double j = component_j(y, comp);
+                double radius, velocity;
+                active++;
+                if (count == 1) {
+                    radius = comp == 0 ? c.diskRadius : c.sphRadius;
+                    if (radius <= 0.0) {
+                        const double radiusLarge = 1.0e10;
+                        const double jmax = sqrt(kGInternal * nfwNorm * nfw_mass_scale_free(radiusLarge / c.dmScale) / radiusLarge) * radiusLarge;
+                        radius = (jmax < j) ? w.rvir : nfw_radius_from_j(c, w, nfwNorm, j);
+                        velocity = (radius > 0.0) ? sqrt(kGInternal * nfwNorm * nfw_mass_scale_free(radius / c.dmScale) / radius) : 0.0;
+                    } else
+                        velocity = comp == 0 ? c.diskVelocity : c.sphVelocity;
+                } else {
+                    if (j <= 0.0) continue;
+                    radius = comp == 0 ? c.diskRadius : c.sphRadius;
+                    const double mdm = dark_matter_mass_enclosed(c, y, w, nfwNorm, radius, bad);
+                    const double vdm2 = kGInternal * mdm / radius;
+                    const double vb2 = c_params.includeBaryonGravity ? baryonic_vc2(c, y, w, radius) : 0.0;
+                    velocity = sqrt(vdm2 + vb2);
+                    const double radiusNew = (radius > 0.0) ? sqrt(j / velocity * radius) : j / velocity;
+                    double &h0 = comp == 0 ? hist00 : hist10;
+                    double &h1 = comp == 0 ? hist01 : hist11;
+                    if (count > 10 && h0 >= 0.0 && h1 >= 0.0 && (h1 - h0) * (h0 - radius) < 0.0) {
+                        switch (count % 4) {
+                            case 0: radius = sqrt(radius * h0); break;
+                            case 1: radius = 0.5 * (radius + h0); break;
+                            case 2: radius = sqrt(h0 * h1); break;
+                            default: radius = 0.5 * (h0 + h1); break;
+                        }
+                        h0 = h1 = -1.0;
+                    }
+                    h1 = h0;
+                    h0 = radius;
+                    if (radius > 0.0 && radiusNew > 0.0) fit += fabs(log(radiusNew / radius));
+                    radius = radiusNew;
+                    if (!(radius > 0.0)) bad = 1;
+                }
+                if (comp == 0) {
+                    c.diskRadius = fmax(radius, 0.0);
+                    c.diskVelocity = velocity;
+                } else {
+                    c.sphRadius = fmax(radius, 0.0);
+                    c.sphVelocity = velocity;
+                }
+            }
+            if (active == 0) {
+                fit = 0.0;
+                break;
+            }
+            fit /= (double)active;
+        }
+    }
+
+    // ---------------------------------------------------------------- star formation in disks
+    static __device__ __forceinline__ double kmt_fh2_fast(double s) {
+        return (s < 2.0) ? 1.0 - 0.75 * s / (1.0 + 0.25 * s) : 0.0;  // Krumholz2009.F90:462-476
+    }
+    struct Kmt {
+        double xh, zsolar, sigmaNorm, sNorm, sigmaTrunc, sigma0, rdisk;  // sigma0 = M_gas/(2 pi Rd^2)
+    };
+    static __device__ __forceinline__ double kmt_rate(const Kmt &k, double radius) {
+        // krumholz2009Rate :360-414 with the exponential-disk surface density (exponential_disk.F90:484-499)
+        const double sg = k.sigma0 * exp(-radius / k.rdisk);
+        const double sgd = k.xh * sg / 85.0e12;
+        if (sg <= 1.0e-100) return 0.0;
+        const double s = k.sNorm / (k.sigmaNorm * sg);
+        const double fh2 = (s > 10.0) ? kmt_fh2_fast(s)
+                                      : linear_table_eval([](double t) { return kmt_fh2_fast(t); }, 0.0, 10.0, 1000, s, true);
+        double factor;
+        if (sgd <= 0.0)
+            factor = 0.0;
+        else
+            factor = fast_exponentiate(1.0, 1000.0, 0.33, 100.0, (sgd < 1.0) ? 1.0 / sgd : sgd);
+        return c_params.frequencyStarFormation * sg * factor * fh2;
+    }
+    // starFormationRateDisksIntgrtdSurfaceDensity::rate (rates/disks/integrated_surface_density.F90:131-190)
+    // with krumholz2009Intervals (rate_surface_density/disks/Krumholz2009.F90:478-587)
+    static __device__ __forceinline__ double sfr_disk(const NodeCtx &c, const double (&y)[NY], int &bad) {
+        const double mgas = y[GLC_P_DISK_MASS_GAS], rdisk = c.diskRadius;
+        if (mgas <= 0.0 || rdisk <= 0.0) return 0.0;
+        Kmt k;
+        const double z = mass_to_fraction(y[GLC_P_DISK_ABUND_GAS], mgas);
+        k.xh = hydrogen_mass_fraction(z);
+        k.zsolar = z / kMetallicitySolar;
+        k.rdisk = rdisk;
+        k.sigma0 = fmax(0.0, mgas) / (2.0 * kPi * rdisk * rdisk);
+        if (!(k.zsolar > 0.0)) return 0.0;
+        const double chi = 0.77 * (1.0 + 3.1 * pow(k.zsolar, 0.365));
+        k.sigmaNorm = k.xh * c_params.clumpingFactorMolecularComplex / (kMega * kMega);
+        k.sNorm = log(1.0 + 0.6 * chi + 0.01 * chi * chi) / (0.04 * k.zsolar);
+        if (!(k.sigmaNorm > 0.0)) return 0.0;
+        k.sigmaTrunc = k.sNorm / k.sigmaNorm / c_params.krumholzSTruncation;
+        const double rIn = 0.0, rOut = 10.0 * rdisk;
+        auto sigma = [&](double r) { return k.sigma0 * exp(-r / k.rdisk); };
+        double sg = sigma(rIn);
+        const double sgdIn = k.xh * sg / 85.0e12;
+        if (sg <= k.sigmaTrunc) return 0.0;
+        sg = sigma(rOut);
+        double sgd = k.xh * sg / 85.0e12;
+        double rMax = rOut;
+        const RootOptions o{0.0, 1.0e-4, EXPAND_MULTIPLICATIVE, 2.0, 0.5, SIGN_NEGATIVE, SIGN_POSITIVE};
+        int st;
+        if (sg <= k.sigmaTrunc) {
+            rMax = root_find([&](double r) { return sigma(r) - k.sigmaTrunc; }, o, rIn, rOut, false, 0.0, 0.0, st);
+            if (st != 0) bad = 1;
+            sgd = k.xh * sigma(rMax) / 85.0e12;
+        }
+        double lo[2], hi[2];
+        int nIv;
+        if (sgdIn <= 1.0 || sgd >= 1.0) {
+            lo[0] = rIn;
+            hi[0] = rMax;
+            nIv = 1;
+        } else {
+            const double rCrit =
+                root_find([&](double r) { return k.xh * sigma(r) / 85.0e12 - 1.0; }, o, rIn, rMax, false, 0.0, 0.0, st);
+            if (st != 0) bad = 1;
+            lo[0] = rIn;
+            hi[0] = rCrit;
+            lo[1] = rCrit;
+            hi[1] = rMax;
+            nIv = 2;
+        }
+        double total = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < nIv; i++) {
+            total += qag15([&](double r) { return r * kmt_rate(k, r); }, lo[i], hi[i], 1.0e-12,
+                           c_params.sfrIntegrationTolerance, st);
+            if (st == 11) bad = 1;
+        }
+        return 2.0 * kPi * total;
+    }
+    static __device__ __forceinline__ double sfr_spheroid(const NodeCtx &c, const double (&y)[NY]) {
+        // rates/spheroids/timescale.F90:109-130 + timescales/dynamical_time.F90:121-189
+        const double v = c.sphVelocity, r = c.sphRadius;
+        if (v <= 0.0 || c_params.sfSpheroidEfficiency == 0.0) return 0.0;
+        const double tau = fmax(kMpcPerKmPerSToGyr * r / v * pow(v / 200.0, c_params.sfSpheroidExponentVelocity) /
+                                    c_params.sfSpheroidEfficiency,
+                                c_params.sfSpheroidTimescaleMinimum);
+        return (tau > 0.0) ? y[GLC_P_SPH_MASS_GAS] / tau : 0.0;
+    }
+
+    // ---------------------------------------------------------------- scales (scaleSetTask hooks)
+    static __device__ __forceinline__ void scales(const NodeCtx &c, const double (&y)[NY], double (&s)[NY]) {
+        Work w;
+        halo_scales(c, c.timeNode, w);
+        s[GLC_P_SAT_BOUND_MASS] = 1.0e-6 * c.basicMass;  // satellite/standard.F90:209-232
+        if (c.flags & (GLC_F_HAS_DISK | GLC_F_HAS_SPHEROID)) {
+            // disk/standard/_class.F90:735-824 and spheroid/standard/_class.F90:804-897
+            const bool hd = has(c, GLC_F_HAS_DISK), hs = has(c, GLC_F_HAS_SPHEROID);
+            const double jd = hd ? y[GLC_P_DISK_ANGMOM] : 0.0, js = hs ? y[GLC_P_SPH_ANGMOM] : 0.0;
+            const double mgd = hd ? y[GLC_P_DISK_MASS_GAS] : 0.0, msd = hd ? y[GLC_P_DISK_MASS_STELLAR] : 0.0;
+            const double mgs = hs ? y[GLC_P_SPH_MASS_GAS] : 0.0, mss = hs ? y[GLC_P_SPH_MASS_STELLAR] : 0.0;
+            const double zgd = hd ? y[GLC_P_DISK_ABUND_GAS] : 0.0, zsd = hd ? y[GLC_P_DISK_ABUND_STELLAR] : 0.0;
+            const double zgs = hs ? y[GLC_P_SPH_ABUND_GAS] : 0.0, zss = hs ? y[GLC_P_SPH_ABUND_STELLAR] : 0.0;
+            const double sj = fmax(fabs(jd) + fabs(js), 0.1);
+            const double sm = fmax(fabs(mgd) + fabs(mgs) + fabs(msd) + fabs(mss), 1.0);
+            const double sz = fmax(fabs(zgd) + fabs(zsd) + fabs(zgs) + fabs(zss), fmax(sm * 1.0e-4, 1.0));
+            if (hd) {
+                s[GLC_P_DISK_ANGMOM] = sj;
+                s[GLC_P_DISK_MASS_GAS] = s[GLC_P_DISK_MASS_STELLAR] = sm;
+                s[GLC_P_DISK_ABUND_GAS] = s[GLC_P_DISK_ABUND_STELLAR] = sz;
+            }
+            if (hs) {
+                s[GLC_P_SPH_ANGMOM] = sj;
+                s[GLC_P_SPH_MASS_GAS] = s[GLC_P_SPH_MASS_STELLAR] = sm;
+                s[GLC_P_SPH_ABUND_GAS] = s[GLC_P_SPH_ABUND_STELLAR] = sz;
+            }
+        }
+        if (has(c, GLC_F_HAS_HOTHALO)) {
+            // hot_halo/standard/_class.F90:804-850
+            const double sm = c.basicMass * c_params.hotHaloScaleMassRelative;
+            const double sj = c.basicMass * w.rvir * w.vvir * c_params.hotHaloScaleMassRelative;
+            s[GLC_P_HH_MASS] = s[GLC_P_HH_OUTFLOWED_MASS] = s[GLC_P_HH_UNACCRETED_MASS] = sm;
+            s[GLC_P_HH_ABUND] = s[GLC_P_HH_UNACCRETED_ABUND] = s[GLC_P_HH_OUTFLOWED_ABUND] = sm;
+            s[GLC_P_HH_ANGMOM] = s[GLC_P_HH_OUTFLOWED_ANGMOM] = sj;
+            s[GLC_P_HH_OUTER_RADIUS] = w.rvir * c_params.hotHaloScaleRadiusRelative;
+            const double ss = has(c, GLC_F_IS_SATELLITE) ? sm : 1.0;
+            s[GLC_P_HH_STRIPPED_MASS] = s[GLC_P_HH_STRIPPED_ABUND] = ss;
+        }
+        if (has(c, GLC_F_HAS_BH)) s[GLC_P_BH_MASS] = s[GLC_P_BH_SPIN] = 1.0;
+    }
+
+    static __device__ __forceinline__ void pre_evolve(NodeCtx &c, double (&y)[NY]) {
+        // Node_Component_Hot_Halo_Standard_Pre_Evolve -> Initializor (hot_halo/standard/_class.F90:725-747,871-891)
+        if (has(c, GLC_F_HAS_HOTHALO) && !has(c, GLC_F_HH_INITIALIZED)) {
+            Work w;
+            solve_analytics(c, c.timeNode);
+            halo_scales(c, c.timeNode, w);
+            y[GLC_P_HH_OUTER_RADIUS] = w.rvir;
+            c.flags |= GLC_F_HH_INITIALIZED;
+        }
+    }
+
+    // ---------------------------------------------------------------- the RHS
+    // rate accumulation with the semantics of the generated <prop>Rate functions
+    // (python/Galacticus/Build/Components/Properties/Evolve.py:202-493)
+    struct Acc {
+        int flags, interrupt;
+        __device__ __forceinline__ void add(double &slot, int compFlag, double v) const {
+            if (flags & compFlag) slot += v;
+        }
+        __device__ __forceinline__ void addCreate(double &slot, int compFlag, int code, double v) {
+            if (flags & compFlag)
+                slot += v;
+            else if (v != 0.0)
+                interrupt = code;
+        }
+    };
+
+    static __device__ __forceinline__ void hh_outflowing(Acc &a, const NodeCtx &c, const Work &w, double (&rate)[NY],
+                                                         double mass, double angmom, double abund) {
+        // hot_halo/standard/_class.F90:598-722 with hotHaloOutflowStrippingStandard (outflow_stripping/standard.F90:133-173)
+        if (!has(c, GLC_F_HAS_HOTHALO)) return;
+        double fs = 0.0;
+        if (has(c, GLC_F_IS_SATELLITE)) {
+            const double mo = hh_mass_enclosed(w, w.hhRouter), mv = hh_mass_enclosed(w, w.rvir);
+            fs = (mv > 0.0) ? c_params.outflowStrippingEfficiency * (1.0 - mo / mv) : c_params.outflowStrippingEfficiency;
+        }
+        rate[GLC_P_HH_STRIPPED_MASS] += mass * fs;
+        rate[GLC_P_HH_OUTFLOWED_MASS] += mass * (1.0 - fs);
+        rate[GLC_P_HH_OUTFLOWED_ANGMOM] += angmom * (1.0 - fs) / (1.0 - c_params.fractionLossAngularMomentum);
+        rate[GLC_P_HH_OUTFLOWED_ABUND] += abund * (1.0 - fs);
+        (void)a;
+    }
+
+    template <bool IS_DISK>
+    static __device__ __forceinline__ void star_formation_and_feedback(Acc &a, const NodeCtx &c, const Work &w,
+                                                                       const double (&y)[NY], double (&rate)[NY],
+                                                                       double psi, bool doSf, bool doFb) {
+        constexpr int pm = IS_DISK ? GLC_P_DISK_MASS_GAS : GLC_P_SPH_MASS_GAS;
+        constexpr int pa = IS_DISK ? GLC_P_DISK_ABUND_GAS : GLC_P_SPH_ABUND_GAS;
+        constexpr int ps = IS_DISK ? GLC_P_DISK_MASS_STELLAR : GLC_P_SPH_MASS_STELLAR;
+        constexpr int pz = IS_DISK ? GLC_P_DISK_ABUND_STELLAR : GLC_P_SPH_ABUND_STELLAR;
+        constexpr int pj = IS_DISK ? GLC_P_DISK_ANGMOM : GLC_P_SPH_ANGMOM;
+        const double massGas = y[pm];
+        const double z = mass_to_fraction(y[pa], massGas);
+        if (doSf) {
+            // instantaneousRates, stellar_populations/properties/instantaneous.F90:173-182
+            const double rateStellar = (1.0 - c_params.recycledFraction) * psi;
+            const double rateZStellar = z * rateStellar;
+            rate[ps] += rateStellar;
+            rate[pm] += -rateStellar;
+            rate[pz] += rateZStellar;
+            rate[pa] += -rateZStellar + c_params.metalYield * psi;
+        }
+        if (doFb) {
+            // stellar_feedback/{disks,spheroids}.F90:116-206; outflows/power_law/_class.F90:118-164;
+            // outflows/rate_limit.F90:111-170
+            const double radius = IS_DISK ? c.diskRadius : c.sphRadius;
+            const double velocity = IS_DISK ? c.diskVelocity : c.sphVelocity;
+            const double vchar = IS_DISK ? c_params.fbDiskVelocityCharacteristic : c_params.fbSpheroidVelocityCharacteristic;
+            const double expo = IS_DISK ? c_params.fbDiskExponent : c_params.fbSpheroidExponent;
+            const double energy = kFeedbackEnergyInputAtInfinityCanonical * psi;
+            double outflow = (velocity <= 0.0) ? 0.0 : pow(vchar / velocity, expo) * energy / kFeedbackEnergyInputAtInfinityCanonical;
+            const double tdyn = (velocity <= 0.0 || radius <= 0.0) ? 1.0 : kMpcPerKmPerSToGyr * radius / velocity;
+            const double outflowMax = fmax(massGas / tdyn / c_params.fbTimescaleOutflowFractionalMinimum, 0.0);
+            if (outflow > outflowMax) outflow = outflow * outflowMax / outflow;
+            if (outflow > 0.0) {
+                const double massComp = massGas + y[ps];
+                const double jOut = (massComp > 0.0) ? y[pj] * (outflow / massComp) : 0.0;
+                const double zOut = (massGas > 0.0) ? z * outflow : 0.0;
+                hh_outflowing(a, c, w, rate, outflow, jOut, zOut);
+                rate[pm] += -outflow;
+                rate[pj] += -jOut;
+                rate[pa] += -zOut;
+            }
+        }
+    }
+
+    static __device__ __forceinline__ int rates(NodeCtx &c, double time, const double (&y)[NY], double (&rate)[NY]) {
+        Work w;
+        Acc a{c.flags, GLC_INT_NONE};
+        int bad = 0;
+        const uint32_t ops = c_params.operatorMask;
+        const bool hh = has(c, GLC_F_HAS_HOTHALO), hd = has(c, GLC_F_HAS_DISK), hs = has(c, GLC_F_HAS_SPHEROID);
+        const bool sat = has(c, GLC_F_IS_SATELLITE);
+        halo_scales(c, time, w);
+        hh_profile(c, y, w);
+        // <eventHook preDerivative>: galactic structure solve (standard.F90:1045)
+        structure_solve(c, y, time, w, bad);
+        if (!w.solvable) return GLC_INT_NONE;
+
+        // satelliteMassLoss (satellite/mass_loss/_class.F90:230-257; darkMatterHaloMassLossRate "zero")
+        if (ops & GLC_OP_SATELLITE_MASS_LOSS) rate[GLC_P_SAT_BOUND_MASS] += sat ? 0.0 : c.massRate;
+
+        // star formation + stellar feedback, disks (star_formation/disks.F90:200-284, stellar_feedback/disks.F90:116-206)
+        if (hd && (ops & (GLC_OP_STAR_FORMATION_DISKS | GLC_OP_STELLAR_FEEDBACK_DISKS)) &&
+            !(y[GLC_P_DISK_ANGMOM] < 0.0 || c.diskRadius < 0.0 || y[GLC_P_DISK_MASS_GAS] < 0.0)) {
+            const double psi = sfr_disk(c, y, bad);
+            star_formation_and_feedback<true>(a, c, w, y, rate, psi, (ops & GLC_OP_STAR_FORMATION_DISKS) != 0,
+                                              (ops & GLC_OP_STELLAR_FEEDBACK_DISKS) != 0);
+        }
+        // spheroids (star_formation/spheroids.F90:152-240, stellar_feedback/spheroids.F90:116-208)
+        if (hs && (ops & (GLC_OP_STAR_FORMATION_SPHEROIDS | GLC_OP_STELLAR_FEEDBACK_SPHEROIDS)) &&
+            !(y[GLC_P_SPH_ANGMOM] < 1.0e-20 || c.sphRadius < 1.0e-12 || y[GLC_P_SPH_MASS_GAS] < 1.0e-6)) {
+            const double psi = sfr_spheroid(c, y);
+            star_formation_and_feedback<false>(a, c, w, y, rate, psi, (ops & GLC_OP_STAR_FORMATION_SPHEROIDS) != 0,
+                                               (ops & GLC_OP_STELLAR_FEEDBACK_SPHEROIDS) != 0);
+        }
+
+        // barInstability (bar_instability.F90:145-249; galactic_dynamics/bar_instability/Efstathiou1982.F90:153-258)
+        if ((ops & GLC_OP_BAR_INSTABILITY) && hd &&
+            !(y[GLC_P_DISK_ANGMOM] < 0.0 || c.diskRadius < 0.0 || y[GLC_P_DISK_MASS_GAS] < 0.0)) {
+            double timescale = -1.0;
+            if (w.plausible && y[GLC_P_DISK_ANGMOM] > 0.0 && c.diskVelocity > 0.0 && c.diskRadius > 0.0) {
+                const double stabilityIsolated = 0.6221297315, boost = 1.1800237580;
+                const double md = y[GLC_P_DISK_MASS_GAS] + y[GLC_P_DISK_MASS_STELLAR];
+                const double fgas = y[GLC_P_DISK_MASS_GAS] / md;
+                const double thr = c_params.barStabilityThresholdStellar * (1.0 - fgas) + c_params.barStabilityThresholdGaseous * fgas;
+                double est = DBL_MAX;
+                if (md >= 0.0) {
+                    const double vself = sqrt(kGInternal * md / c.diskRadius);
+                    if (vself > 0.0) est = fmax(stabilityIsolated, boost * c.diskVelocity / vself);
+                }
+                if (est < thr) {
+                    const double tdyn = kMpcPerKmPerSToGyr * c.diskRadius / fmin(c.diskVelocity, kSpeedLight / kKilo);
+                    const double aa = thr - stabilityIsolated, bb = thr - est;
+                    const double tdim = (aa > 1.0e10 * bb) ? 1.0e10 : (aa / bb) * (aa / bb);
+                    timescale = fmax(tdyn, 1.0e-9) * tdim;
+                }
+            }
+            if (!(timescale < 0.0)) {
+                double tr = fmax(0.0, y[GLC_P_DISK_MASS_GAS]) / timescale;
+                rate[GLC_P_DISK_MASS_GAS] += -tr;
+                a.addCreate(rate[GLC_P_SPH_MASS_GAS], GLC_F_HAS_SPHEROID, GLC_INT_SPHEROID_CREATE, tr);
+                tr = fmax(0.0, y[GLC_P_DISK_MASS_STELLAR]) / timescale;
+                rate[GLC_P_DISK_MASS_STELLAR] += -tr;
+                a.addCreate(rate[GLC_P_SPH_MASS_STELLAR], GLC_F_HAS_SPHEROID, GLC_INT_SPHEROID_CREATE, tr);
+                tr = fmax(0.0, y[GLC_P_DISK_ANGMOM]) / timescale;
+                rate[GLC_P_DISK_ANGMOM] += -(1.0 - 1.0) * tr;  // fractionAngularMomentumRetainedDisk = 1
+                a.addCreate(rate[GLC_P_SPH_ANGMOM], GLC_F_HAS_SPHEROID, GLC_INT_SPHEROID_CREATE, 1.0 * tr);
+                tr = fmax(0.0, y[GLC_P_DISK_ABUND_GAS]) / timescale;
+                rate[GLC_P_DISK_ABUND_GAS] += -tr;
+                a.addCreate(rate[GLC_P_SPH_ABUND_GAS], GLC_F_HAS_SPHEROID, GLC_INT_SPHEROID_CREATE, tr);
+                tr = fmax(0.0, y[GLC_P_DISK_ABUND_STELLAR]) / timescale;
+                rate[GLC_P_DISK_ABUND_STELLAR] += -tr;
+                a.addCreate(rate[GLC_P_SPH_ABUND_STELLAR], GLC_F_HAS_SPHEROID, GLC_INT_SPHEROID_CREATE, tr);
+            }
+        }
+
+        // CGMAccretion (circumgalactic_medium/accretion.F90:517-593; accretion/halo/simple.F90:281-378,592-613)
+        if (ops & GLC_OP_CGM_ACCRETION) {
+            double rateHot = 0.0, rateFailed = 0.0, rateJ = 0.0;
+            const double fb = c_params.OmegaBaryon / c_params.OmegaMatter;
+            if (!sat) {
+                const double failed = (time > c_params.timeReionization && w.vvir < c_params.velocitySuppressionReionization) ? 1.0 : 0.0;
+                const double unaccreted = hh ? y[GLC_P_HH_UNACCRETED_MASS] : 0.0;
+                const double growth = c.massRate / c.basicMass;
+                rateHot = fb * c.massRate * (1.0 - failed) + unaccreted * growth * (1.0 - failed);
+                rateFailed = fb * c.massRate * failed - unaccreted * growth * (1.0 - failed);
+            }
+            if (c.massRate != 0.0) rateJ = c.spinRate * rateHot / c.massRate;
+            const bool hotPositive = hh && y[GLC_P_HH_MASS] > 0.0;
+            if (rateHot > 0.0 || hotPositive || c_params.allowNegativeCGMMass)
+                a.addCreate(rate[GLC_P_HH_MASS], GLC_F_HAS_HOTHALO, GLC_INT_HOTHALO_CREATE, rateHot);
+            if (rateFailed > 0.0 || hotPositive || c_params.allowNegativeCGMMass)
+                a.addCreate(rate[GLC_P_HH_UNACCRETED_MASS], GLC_F_HAS_HOTHALO, GLC_INT_HOTHALO_CREATE, rateFailed);
+            a.addCreate(rate[GLC_P_HH_ANGMOM], GLC_F_HAS_HOTHALO, GLC_INT_HOTHALO_CREATE, rateJ);
+        }
+
+        // CGMOutflowReincorporation (outflow_reincorporation.F90:272-349; halo_dynamical_time.F90:113-128)
+        const double massReturnRate = hh ? y[GLC_P_HH_OUTFLOWED_MASS] * c_params.reincorporationMultiplier / w.tdyn : 0.0;
+        if ((ops & GLC_OP_CGM_OUTFLOW_REINCORPORATION) && hh && y[GLC_P_HH_OUTFLOWED_MASS] > 0.0) {
+            const double mo = y[GLC_P_HH_OUTFLOWED_MASS];
+            const double rj = y[GLC_P_HH_OUTFLOWED_ANGMOM] * (massReturnRate / mo);
+            const double rz = y[GLC_P_HH_OUTFLOWED_ABUND] * (massReturnRate / mo);
+            rate[GLC_P_HH_OUTFLOWED_MASS] += -massReturnRate;
+            rate[GLC_P_HH_OUTFLOWED_ANGMOM] += -rj;
+            rate[GLC_P_HH_OUTFLOWED_ABUND] += -rz;
+            rate[GLC_P_HH_MASS] += massReturnRate;
+            rate[GLC_P_HH_ANGMOM] += rj;
+            rate[GLC_P_HH_ABUND] += rz;
+        }
+
+        // CGMCoolingHeating (cooling_heating.F90:216-381; component=disk, coolingFrom=currentNode)
+        if ((ops & GLC_OP_CGM_COOLING_HEATING) && hh && y[GLC_P_HH_MASS] > 0.0 &&
+            !(y[GLC_P_HH_ANGMOM] <= 0.0 || w.hhRouter <= 0.0)) {
+            // coolingRateWhiteFrenk1991::rate, cooling/cooling_rate/White-Frenk.F90:131-185
+            double cool = 0.0, rinfall = 0.0;
+            if (!(w.vvir > c_params.coolingVelocityCutOff)) {
+                double logSlopeT;
+                cooling_prepare(y, w, logSlopeT);
+                rinfall = cooling_radius(y, w, bad);
+                if (rinfall >= w.hhRouter)
+                    cool = y[GLC_P_HH_MASS] / w.tdyn;
+                else {
+                    // coolingRadiusSimple::radiusGrowthRate :229-311 (isothermal: temperature slope 0)
+                    const double x = rinfall / w.hhRcore;
+                    const double densityLogSlope = -3.0 * c_params.hotHaloBeta * x * x / (x * x + 1.0);
+                    double growth = 0.0;
+                    if (rinfall > 0.0) {
+                        const double slope = densityLogSlope * (1.0 - 2.0) + 0.0 * (-logSlopeT);
+                        if (slope != 0.0) growth = rinfall / w.coolTavail * 1.0 / slope;
+                    }
+                    cool = 4.0 * kPi * rinfall * rinfall * hh_density(w, rinfall) * growth;
+                }
+            }
+            const double heat = 0.0 / (w.vvir * w.vvir);  // circumgalacticMediumHeatingAGNFeedback: no black holes yet
+            if (heat > cool) {
+                if (c_params.excessHeatDrivesOutflow) {
+                    const double out = fmin(heat - cool, c_params.rateMaximumExpulsion * y[GLC_P_HH_MASS] / w.tdyn);
+                    const double rz = y[GLC_P_HH_ABUND] * (out / y[GLC_P_HH_MASS]);
+                    const double rj = y[GLC_P_HH_ANGMOM] * (out / y[GLC_P_HH_MASS]);
+                    rate[GLC_P_HH_MASS] += -out;
+                    rate[GLC_P_HH_ABUND] += -rz;
+                    rate[GLC_P_HH_ANGMOM] += -rj;
+                    if (sat) {
+                        rate[GLC_P_HH_STRIPPED_MASS] += out;
+                        rate[GLC_P_HH_STRIPPED_ABUND] += rz;
+                    }
+                }
+            } else if (cool > heat) {
+                cool = fmax(0.0, cool - heat);
+                // coolingSpecificAngularMomentumConstantRotation (hotGas, hotGas), constant_rotation.F90:198-286
+                double jSpecific = 0.0;
+                if (rinfall > 0.0) {
+                    const double x = w.hhRouter / w.hhRcore;
+                    const double m2 = (x < 1.0e-6) ? x * x * x * (1.0 / 3.0 - x * x / 5.0) : x - atan(x);
+                    const double m3 = (x < 1.0e-6) ? x * x * x * x * (1.0 / 4.0 - x * x / 6.0) : 0.5 * (x * x - log(1.0 + x * x));
+                    const double rc = w.hhRcore;
+                    const double norm = (m2 * w.hhRho0 * (rc * rc * rc)) / (m3 * w.hhRho0 * (rc * rc * rc * rc));
+                    jSpecific = norm * (y[GLC_P_HH_ANGMOM] / y[GLC_P_HH_MASS]) * rinfall;
+                }
+                const double rj = cool * jSpecific;
+                const double rz = cool * y[GLC_P_HH_ABUND] / y[GLC_P_HH_MASS];
+                rate[GLC_P_HH_MASS] += -cool;
+                rate[GLC_P_HH_ANGMOM] += -rj;
+                rate[GLC_P_HH_ABUND] += -rz;
+                a.addCreate(rate[GLC_P_DISK_MASS_GAS], GLC_F_HAS_DISK, GLC_INT_DISK_CREATE, cool);
+                a.addCreate(rate[GLC_P_DISK_ABUND_GAS], GLC_F_HAS_DISK, GLC_INT_DISK_CREATE, rz);
+                a.addCreate(rate[GLC_P_DISK_ANGMOM], GLC_F_HAS_DISK, GLC_INT_DISK_CREATE,
+                            rj * (1.0 - c_params.fractionLossAngularMomentum));
+            }
+        }
+
+        // CGMOuterRadiusRamPressureStripping (outer_radius/ram_pressure_stripping.F90:151-313) with
+        // hotHaloRamPressureStripping=virialRadius
+        if ((ops & GLC_OP_CGM_OUTER_RADIUS) && hh) {
+            const double router = w.hhRouter;
+            if (router < w.rvir) {
+                const double rho = hh_density(w, router);
+                if (router > 0.0 && rho > 0.0) {
+                    const double rhoMin = c_params.OmegaBaryon / c_params.OmegaMatter * c.basicMass / (w.rvir * w.rvir * w.rvir) / 4.0 / kPi;
+                    rate[GLC_P_HH_OUTER_RADIUS] += massReturnRate / 4.0 / kPi / (router * router) / fmax(rho, rhoMin);
+                } else if (massReturnRate > 0.0) {
+                    rate[GLC_P_HH_OUTER_RADIUS] += massReturnRate / c.basicMass * w.rvir;
+                }
+            }
+            if (!sat) {
+                // virialDensityContrastDefinitionVirialRadiusGrowthRate :338-354
+                rate[GLC_P_HH_OUTER_RADIUS] += (1.0 / 3.0) * w.rvir * (c.massRate / c.basicMass - w.dlnrhoDt);
+            }
+        }
+        if (bad) c.numericsFailed = 1;
+        return a.interrupt;
+    }
+
+    // ---------------------------------------------------------------- post-step clamps
+    static __device__ __forceinline__ int post_step(NodeCtx &c, double (&y)[NY]) {
+        int status = kGslSuccess;
+        // Node_Component_Disk_Standard_Post_Step, disk/standard/_class.F90:473-677
+        if (has(c, GLC_F_HAS_DISK)) {
+            if (y[GLC_P_DISK_MASS_GAS] < 0.0) {
+                const double m = y[GLC_P_DISK_MASS_GAS] + y[GLC_P_DISK_MASS_STELLAR];
+                double j;
+                if (m == 0.0) {
+                    j = 0.0;
+                    y[GLC_P_DISK_MASS_STELLAR] = 0.0;
+                    y[GLC_P_DISK_ABUND_STELLAR] = 0.0;
+                } else {
+                    j = y[GLC_P_DISK_ANGMOM] / m;
+                    if (j < 0.0) j = c.diskRadius * c.diskVelocity;
+                }
+                y[GLC_P_DISK_MASS_GAS] = 0.0;
+                y[GLC_P_DISK_ABUND_GAS] = 0.0;
+                y[GLC_P_DISK_ANGMOM] = j * y[GLC_P_DISK_MASS_STELLAR];
+                status = kGslContinue;
+            }
+            if (y[GLC_P_DISK_MASS_STELLAR] < 0.0) {
+                const double m = y[GLC_P_DISK_MASS_GAS] + y[GLC_P_DISK_MASS_STELLAR];
+                double j;
+                if (m == 0.0) {
+                    j = 0.0;
+                    y[GLC_P_DISK_MASS_GAS] = 0.0;
+                    y[GLC_P_DISK_ABUND_GAS] = 0.0;
+                } else {
+                    j = y[GLC_P_DISK_ANGMOM] / m;
+                    if (j < 0.0) j = c.diskRadius * c.diskVelocity;
+                }
+                y[GLC_P_DISK_MASS_STELLAR] = 0.0;
+                y[GLC_P_DISK_ABUND_STELLAR] = 0.0;
+                y[GLC_P_DISK_ANGMOM] = j * y[GLC_P_DISK_MASS_GAS];
+                status = kGslContinue;
+            }
+            if (y[GLC_P_DISK_ANGMOM] < 0.0) {
+                if (y[GLC_P_DISK_MASS_STELLAR] + y[GLC_P_DISK_MASS_GAS] <= 0.0) y[GLC_P_DISK_ANGMOM] = 0.0;
+                status = kGslContinue;
+            }
+        }
+        // Node_Component_Hot_Halo_Standard_Post_Step, hot_halo/standard/_class.F90:455-530
+        if (has(c, GLC_F_HAS_HOTHALO) && y[GLC_P_HH_MASS] < 0.0) {
+            y[GLC_P_HH_MASS] = 0.0;
+            status = kGslContinue;
+        }
+        // Node_Component_Spheroid_Standard_Post_Step, spheroid/standard/_class.F90:464-636
+        if (has(c, GLC_F_HAS_SPHEROID)) {
+            if (y[GLC_P_SPH_MASS_GAS] < 0.0) {
+                const double m = y[GLC_P_SPH_MASS_GAS] + y[GLC_P_SPH_MASS_STELLAR];
+                double j;
+                if (m == 0.0) {
+                    j = 0.0;
+                    y[GLC_P_SPH_MASS_STELLAR] = 0.0;
+                    y[GLC_P_SPH_ABUND_STELLAR] = 0.0;
+                } else
+                    j = y[GLC_P_SPH_ANGMOM] / m;
+                y[GLC_P_SPH_MASS_GAS] = 0.0;
+                y[GLC_P_SPH_ABUND_GAS] = 0.0;
+                y[GLC_P_SPH_ANGMOM] = j * y[GLC_P_SPH_MASS_STELLAR];
+                status = kGslContinue;
+            }
+            if (y[GLC_P_SPH_MASS_STELLAR] < 0.0) {
+                const double m = y[GLC_P_SPH_MASS_GAS] + y[GLC_P_SPH_MASS_STELLAR];
+                double j;
+                if (m == 0.0) {
+                    j = 0.0;
+                    y[GLC_P_SPH_MASS_GAS] = 0.0;
+                    y[GLC_P_SPH_ABUND_GAS] = 0.0;
+                } else
+                    j = y[GLC_P_SPH_ANGMOM] / m;
+                y[GLC_P_SPH_MASS_STELLAR] = 0.0;
+                y[GLC_P_SPH_ABUND_STELLAR] = 0.0;
+                y[GLC_P_SPH_ANGMOM] = j * y[GLC_P_SPH_MASS_GAS];
+                status = kGslContinue;
+            }
+            if (y[GLC_P_SPH_ANGMOM] < 0.0) {
+                const double j = c.sphRadius * c.sphVelocity / c_params.spheroidRatioAngularMomentumScaleRadius;
+                y[GLC_P_SPH_ANGMOM] = j * (y[GLC_P_SPH_MASS_GAS] + y[GLC_P_SPH_MASS_STELLAR]);
+                status = kGslContinue;
+            }
+        }
+        return status;
+    }
+
+    static __device__ __forceinline__ void post_evolve(NodeCtx &c, double (&y)[NY]) {
+        // <eventHook postEvolve>: structure solve at the final state (equilibrium.F90:172,197-217)
+        Work w;
+        int bad = 0;
+        halo_scales(c, c.timeNode, w);
+        hh_profile(c, y, w);
+        structure_solve(c, y, c.timeNode, w, bad);
+        if (bad) c.numericsFailed = 1;
+    }
+};
+
+}  // namespace glc

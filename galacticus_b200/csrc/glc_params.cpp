@@ -50,7 +50,8 @@ extern "C" int glc_params_default(glc_params *P, int32_t model) {
     P->allowNegativeCGMMass = 1;
     P->frequencyStarFormation = 0.385;
     P->clumpingFactorMolecularComplex = 5.0;
-    P->sfrIntegrationTolerance = 1.0e-3;    // star_formation/rates/disks/integrated_surface_density.F90:81-82
+    P->sfrIntegrationTolerance = 1.0e-3;
+    P->krumholzSTruncation = 2.0 - 2.0e-10;  /* exact root of f_H2(s) = 1e-10 for the fast fit; host may refine */    // star_formation/rates/disks/integrated_surface_density.F90:81-82
     P->sfSpheroidEfficiency = 0.04;
     P->sfSpheroidExponentVelocity = 2.0;
     P->sfSpheroidTimescaleMinimum = 0.001;

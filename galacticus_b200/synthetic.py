@@ -1,0 +1,217 @@
+"""Synthetic tabulated inputs and merger trees of the same SHAPE as the reference's datasets.
+
+The external datasets the reference reads (Cloudy CIE cooling/chemical-state tables,
+``atomic_CIE_Cloudy.F90:63``) are not available offline; BASELINE.json's north_star prescribes
+synthetic tables of the same shape, fed identically to the CPU checker and to the CUDA path.  Everything
+here is host-side input generation: it never evaluates the hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import abi
+
+P = abi.P
+
+# numerical constants as in source/numerical/constants (GSL 2.6 MKSA values)
+G_INTERNAL = 6.673e-11 * 1.98892e30 / 1.0e6 / (1.0e6 * 3.08567758135e16)
+MPC_PER_KMS_TO_GYR = (1.0e6 * 3.08567758135e16) / 1.0e3 / (1.0e9 * 3.15581497635456e7)
+
+
+# ------------------------------------------------------------------ cosmology (matterLambda)
+class Cosmology:
+    """Flat matter+Lambda cosmology (cosmologyFunctionsMatterLambda) in closed form."""
+
+    def __init__(self, params: abi.glc_params):
+        self.Om = params.OmegaMatter
+        self.OL = 1.0 - self.Om
+        self.Ob = params.OmegaBaryon
+        self.H0 = params.HubbleConstant / MPC_PER_KMS_TO_GYR  # 1/Gyr
+        self.rho_crit0 = 3.0 * params.HubbleConstant**2 / (8.0 * np.pi * G_INTERNAL)  # Msun/Mpc^3
+
+    def expansion_factor(self, t):
+        return (self.Om / self.OL) ** (1.0 / 3.0) * np.sinh(1.5 * np.sqrt(self.OL) * self.H0 * t) ** (2.0 / 3.0)
+
+    def time_of_redshift(self, z):
+        a = 1.0 / (1.0 + z)
+        return np.arcsinh(np.sqrt(self.OL / self.Om) * a**1.5) / (1.5 * np.sqrt(self.OL) * self.H0)
+
+    def hubble(self, a):
+        return self.H0 * np.sqrt(self.Om / a**3 + self.OL)
+
+    def virial_mean_density(self, t):
+        """Stand-in for virialDensityContrastSphericalCollapse...: Bryan & Norman (1998) fit."""
+        a = self.expansion_factor(t)
+        e2 = self.Om / a**3 + self.OL
+        om_a = self.Om / a**3 / e2
+        x = om_a - 1.0
+        delta_mean = (18.0 * np.pi**2 + 82.0 * x - 39.0 * x**2) / om_a
+        return delta_mean * self.Om * self.rho_crit0 / a**3
+
+
+def halo_mean_density_table(params, t_min=0.01, t_max=30.0, per_decade=100):
+    """GLC_TABLE_HALO_MEAN_DENSITY: log-uniform in time, 100 points per decade
+    (dark_matter_halos/scales/virial_density_contrast.F90:386-414)."""
+    cosmo = Cosmology(params)
+    n = int(np.ceil(np.log10(t_max / t_min) * per_decade)) + 1
+    t = t_min * 10.0 ** (np.arange(n) / per_decade)
+    rho = cosmo.virial_mean_density(t)
+    eps = 1.0e-5
+    dln = (np.log(cosmo.virial_mean_density(t * (1 + eps))) - np.log(cosmo.virial_mean_density(t * (1 - eps)))) / (2 * eps * t)
+    return t, None, np.stack([rho, dln], axis=1)
+
+
+# ------------------------------------------------------------------ CIE tables
+def cie_grids():
+    temperatures = 10.0 ** np.arange(2.0, 9.0001, 0.1)
+    metallicities = np.array([0.0, 1.0e-3, 1.0e-2, 1.0e-1, 0.3, 1.0, 3.0, 10.0, 30.0])  # Solar units
+    return metallicities, temperatures
+
+
+def cooling_function_table():
+    """GLC_TABLE_COOLING_FUNCTION with the layout of CIE_file.F90:30-134 (Lambda/n_H^2, erg cm^3/s)."""
+    Z, T = cie_grids()
+    lgT = np.log10(T)
+    cutoff = 1.0 / (1.0 + (1.2e4 / T) ** 8) + 1.0e-12
+    prim = (2.5e-27 * np.sqrt(T) + 7.0e-23 * np.exp(-(((lgT - 4.3) / 0.25) ** 2))
+            + 2.0e-23 * np.exp(-(((lgT - 5.0) / 0.3) ** 2))) * cutoff
+    metal = 1.2e-22 * np.exp(-(((lgT - 5.4) / 0.6) ** 2)) * cutoff
+    table = prim[None, :] + Z[:, None] * metal[None, :]
+    return Z, T, table
+
+
+def electron_fraction_table():
+    """GLC_TABLE_ELECTRON_FRACTION: n_e / n_H on the same grid (chemical/state/CIE_file.F90)."""
+    Z, T = cie_grids()
+    ion = 1.0 / (1.0 + (1.5e4 / T) ** 6)
+    table = (1.17 * ion[None, :] + 1.0e-4) + 0.01 * Z[:, None] * ion[None, :]
+    return Z, T, table
+
+
+def disk_rotation_curve_table(per_decade=100, x_min=1.0e-6, x_max=1.0e2):
+    """GLC_TABLE_DISK_ROTATION_CURVE: x^2 [I0 K0 - I1 K1](x) on the reference's lattice
+    (exponential_disk.F90:112-113,686: rotationCurveHalfRadiusMinimumDefault=1e-6, 100 points/decade)."""
+    from scipy import special
+
+    n = int(round(np.log10(x_max / x_min) * per_decade)) + 1
+    x = x_min * 10.0 ** (np.arange(n) / per_decade)
+    f = x**2 * (special.i0e(x) * special.k0e(x) - special.i1e(x) * special.k1e(x))
+    return x, None, f
+
+
+def standard_tables(params):
+    return {
+        abi.GLC_TABLE_COOLING_FUNCTION: cooling_function_table(),
+        abi.GLC_TABLE_ELECTRON_FRACTION: electron_fraction_table(),
+        abi.GLC_TABLE_HALO_MEAN_DENSITY: halo_mean_density_table(params),
+        abi.GLC_TABLE_DISK_ROTATION_CURVE: disk_rotation_curve_table(),
+    }
+
+
+def finalize_params(params):
+    """Fill host-computed constants: timeReionization from redshiftReionization=10.5
+    (parameters/quickTest.xml:101-104)."""
+    if params.model == abi.GLC_MODEL_STANDARD:
+        params.timeReionization = float(Cosmology(params).time_of_redshift(10.5))
+    return params
+
+
+def install(target, params):
+    """Give parameters and tables to any object exposing set_params/set_table (e.g. an Evolver)."""
+    finalize_params(params)
+    target.set_params(params)
+    if params.model == abi.GLC_MODEL_STANDARD:
+        for tid, (x0, x1, v) in standard_tables(params).items():
+            target.set_table(tid, x0, x1, v)
+
+
+# ------------------------------------------------------------------ halo helpers (inputs only)
+def virial_radius(params, mass, t):
+    rho = Cosmology(params).virial_mean_density(t)
+    return np.cbrt(3.0 * mass / (4.0 * np.pi * rho))
+
+
+def standard_nodes(params, n, seed=219, fresh_fraction=0.3, satellite_fraction=0.2):
+    """Seeded node records spanning the quickTest mass range (1e10..1e13 Msun) at 1..13 Gyr."""
+    rng = np.random.default_rng(seed)
+    cosmo = Cosmology(params)
+    props = np.zeros((n, abi.NPROP))
+    flags = np.zeros(n, dtype=np.int32)
+    t0 = rng.uniform(0.8, 12.5, n)
+    dt = rng.uniform(0.05, 0.8, n)
+    mass = 10.0 ** rng.uniform(10.0, 13.0, n)
+    growth = rng.uniform(0.0, 0.4, n) * mass / 1.0  # Msun/Gyr
+    sat = rng.random(n) < satellite_fraction
+    growth[sat] = 0.0
+    rvir = virial_radius(params, mass, t0)
+    vvir = np.sqrt(G_INTERNAL * mass / rvir)
+    conc = rng.uniform(4.0, 15.0, n)
+    lam = 0.04326 * np.exp(rng.normal(0.0, 0.5, n))
+    jhalo = np.sqrt(2.0) * lam * mass * rvir * vvir
+    fb = params.OmegaBaryon / params.OmegaMatter
+
+    props[:, P["TIME"]] = t0
+    props[:, P["TIME_STEP"]] = np.where(rng.random(n) < 0.5, -1.0, rng.uniform(1e-3, 0.3, n))
+    props[:, P["TIME_TARGET"]] = t0 + dt * rng.uniform(1.0, 1.5, n)
+    props[:, P["MASS_RATE"]] = growth
+    props[:, P["MASS_TARGET"]] = mass + growth * (props[:, P["TIME_TARGET"]] - t0)
+    props[:, P["BASIC_MASS"]] = mass
+    props[:, P["DMSCALE"]] = rvir / conc
+    props[:, P["DMSCALE_RATE"]] = np.where(sat, 0.0, rng.uniform(-0.1, 0.1, n) * rvir / conc)
+    props[:, P["DMSCALE_TARGET"]] = props[:, P["DMSCALE"]] + props[:, P["DMSCALE_RATE"]] * (props[:, P["TIME_TARGET"]] - t0)
+    props[:, P["SPIN"]] = jhalo
+    props[:, P["SPIN_RATE"]] = np.where(sat, 0.0, rng.uniform(0.0, 0.3, n) * jhalo)
+    props[:, P["SPIN_TARGET"]] = jhalo + props[:, P["SPIN_RATE"]] * (props[:, P["TIME_TARGET"]] - t0)
+    props[:, P["TIME_LAST_ISOLATED"]] = np.where(sat, t0 * rng.uniform(0.6, 1.0, n), 0.0)
+    props[:, P["SAT_BOUND_MASS"]] = mass
+    props[:, P["MASS_BARYONIC_SUBHALOS"]] = np.where(rng.random(n) < 0.3, fb * mass * rng.uniform(0, 0.2, n), 0.0)
+
+    # hot halo
+    has_hh = rng.random(n) < 0.95
+    mhh = fb * mass * rng.uniform(0.05, 1.0, n)
+    zhh = rng.uniform(0.0, 0.02, n) * (rng.random(n) < 0.8)
+    props[:, P["HH_MASS"]] = np.where(has_hh, mhh, 0.0)
+    props[:, P["HH_ABUND"]] = np.where(has_hh, mhh * zhh, 0.0)
+    props[:, P["HH_ANGMOM"]] = np.where(has_hh, jhalo * mhh / mass, 0.0)
+    mout = np.where(rng.random(n) < 0.5, mhh * rng.uniform(0, 0.5, n), 0.0)
+    props[:, P["HH_OUTFLOWED_MASS"]] = np.where(has_hh, mout, 0.0)
+    props[:, P["HH_OUTFLOWED_ABUND"]] = np.where(has_hh, mout * zhh, 0.0)
+    props[:, P["HH_OUTFLOWED_ANGMOM"]] = np.where(has_hh, jhalo * mout / mass, 0.0)
+    props[:, P["HH_UNACCRETED_MASS"]] = np.where(has_hh & (rng.random(n) < 0.3), fb * mass * 0.1, 0.0)
+    init = has_hh & (rng.random(n) > fresh_fraction)
+    props[:, P["HH_OUTER_RADIUS"]] = np.where(init, rvir * rng.uniform(0.3, 1.0, n), 0.0)
+    flags[has_hh] |= abi.GLC_F_HAS_HOTHALO
+    flags[init] |= abi.GLC_F_HH_INITIALIZED
+    flags[sat] |= abi.GLC_F_IS_SATELLITE
+
+    # disk
+    has_d = has_hh & (rng.random(n) < 0.7)
+    md = fb * mass * 10.0 ** rng.uniform(-3.0, -0.5, n)
+    fgas = rng.uniform(0.05, 1.0, n)
+    zd = rng.uniform(1.0e-4, 0.03, n)
+    rd = rvir * lam / np.sqrt(2.0) * rng.uniform(0.5, 1.5, n)
+    props[:, P["DISK_MASS_GAS"]] = np.where(has_d, md * fgas, 0.0)
+    props[:, P["DISK_MASS_STELLAR"]] = np.where(has_d, md * (1 - fgas), 0.0)
+    props[:, P["DISK_ABUND_GAS"]] = np.where(has_d, md * fgas * zd, 0.0)
+    props[:, P["DISK_ABUND_STELLAR"]] = np.where(has_d, md * (1 - fgas) * zd * 0.7, 0.0)
+    props[:, P["DISK_ANGMOM"]] = np.where(has_d, 2.0 * md * rd * vvir * rng.uniform(0.8, 1.3, n), 0.0)
+    warm = has_d & (rng.random(n) > fresh_fraction)
+    props[:, P["DISK_RADIUS"]] = np.where(warm, rd, 0.0)
+    props[:, P["DISK_VELOCITY"]] = np.where(warm, vvir * rng.uniform(0.8, 1.5, n), 0.0)
+    flags[has_d] |= abi.GLC_F_HAS_DISK
+
+    # spheroid
+    has_s = has_d & (rng.random(n) < 0.4)
+    ms = md * 10.0 ** rng.uniform(-2.0, 0.5, n)
+    fgs = rng.uniform(0.0, 0.5, n)
+    rs = rd * rng.uniform(0.1, 0.6, n)
+    props[:, P["SPH_MASS_GAS"]] = np.where(has_s, ms * fgs, 0.0)
+    props[:, P["SPH_MASS_STELLAR"]] = np.where(has_s, ms * (1 - fgs), 0.0)
+    props[:, P["SPH_ABUND_GAS"]] = np.where(has_s, ms * fgs * zd, 0.0)
+    props[:, P["SPH_ABUND_STELLAR"]] = np.where(has_s, ms * (1 - fgs) * zd, 0.0)
+    props[:, P["SPH_ANGMOM"]] = np.where(has_s, ms * rs * vvir * 2.0 * rng.uniform(0.8, 1.3, n), 0.0)
+    warm_s = has_s & (rng.random(n) > fresh_fraction)
+    props[:, P["SPH_RADIUS"]] = np.where(warm_s, rs, 0.0)
+    props[:, P["SPH_VELOCITY"]] = np.where(warm_s, vvir * rng.uniform(0.8, 1.8, n), 0.0)
+    flags[has_s] |= abi.GLC_F_HAS_SPHEROID
+    return props, flags, t0 + dt

@@ -85,7 +85,11 @@ enum glc_prop {
     GLC_P_DISK_VELOCITY,
     GLC_P_SPH_RADIUS,
     GLC_P_SPH_VELOCITY,
-    GLC_P_BASIC_MASS,        /* out: basic%mass() at the time reached                   */
+    GLC_P_BASIC_MASS,        /* basic%mass(): in = value at GLC_P_TIME, out = value at the time reached */
+    GLC_P_DMSCALE,           /* darkMatterProfile%scale() current value (same convention)  */
+    GLC_P_SPIN,              /* spin%angularMomentum() current value (same convention)     */
+    GLC_P_MASS_BARYONIC_SUBHALOS, /* in: sum of massBaryonic() over all sub-satellites, frozen for the
+                                call (dark_matter_profiles/adiabatic_Gnedin2004.F90:327-347)   */
     GLC_NPROP
 };
 
@@ -95,7 +99,9 @@ enum glc_flag {
     GLC_F_HAS_DISK     = 1 << 1,
     GLC_F_HAS_SPHEROID = 1 << 2,
     GLC_F_HAS_BH       = 1 << 3,
-    GLC_F_IS_SATELLITE = 1 << 4
+    GLC_F_IS_SATELLITE = 1 << 4,
+    GLC_F_HH_INITIALIZED = 1 << 5 /* hotHalo%isInitialized(): outerRadius has been set to the virial
+                                     radius by the pre-evolve task (hot_halo/standard/_class.F90:871-891) */
 };
 
 /* per-node status: errorStatus* of source/error/_module.F90 as used at
@@ -162,6 +168,9 @@ typedef struct glc_params {
     /* star formation: krumholz2009 + intgrtdSurfaceDensity */
     double frequencyStarFormation, clumpingFactorMolecularComplex;
     double sfrIntegrationTolerance;    /* starFormationRateDisks intgrtdSurfaceDensity [tolerance] */
+    double krumholzSTruncation;        /* s at which f_H2 drops to 1e-10: a constructor-time constant of
+                                          starFormationRateSurfaceDensityDisksKrumholz2009
+                                          (Krumholz2009.F90:236-241), computed by the host */
     /* star formation spheroids: timescale dynamicalTime */
     double sfSpheroidEfficiency, sfSpheroidExponentVelocity, sfSpheroidTimescaleMinimum;
     /* stellar feedback (power law inside rate limit) */
@@ -222,9 +231,13 @@ enum glc_table {
     GLC_TABLE_ELECTRON_FRACTION = 1,
     /* halo mean density table, linear in ln t (dark_matter_halos/scales/
        virial_density_contrast.F90:356-417): x0 = times[n0] (Gyr, log-uniform), n1 = 2:
-       values[n0][0] = mean virial density (Msun/Mpc^3), values[n0][1] = its growth rate
-       d rho / dt  (:419-459). */
+       values[n0][0] = mean virial density (Msun/Mpc^3), values[n0][1] = its logarithmic
+       growth rate d ln rho / dt = (d Delta/dt)/Delta - 3 H  (1/Gyr)  (:419-459). */
     GLC_TABLE_HALO_MEAN_DENSITY = 2,
+    /* exponential-disk rotation-curve factor x^2 [I0(x)K0(x) - I1(x)K1(x)] tabulated on a log-uniform
+       lattice of half-radii x = R/2R_d, 100 points per decade (table1DLogarithmicLinear,
+       mass_distributions/cylindrical/exponential_disk.F90:675-733): x0 = half-radii[n0], n1 = 1. */
+    GLC_TABLE_DISK_ROTATION_CURVE = 3,
     GLC_NTABLES
 };
 

@@ -125,6 +125,7 @@ void orc_params_default(glc_params *P, int model) {
     P->frequencyStarFormation = 0.385;
     P->clumpingFactorMolecularComplex = 5.0;
     P->sfrIntegrationTolerance = 1.0e-3;
+    P->krumholzSTruncation = 2.0 - 2.0e-10;  /* exact root of f_H2(s) = 1e-10 for the fast fit; host may refine */
     P->sfSpheroidEfficiency = 0.04;
     P->sfSpheroidExponentVelocity = 2.0;
     P->sfSpheroidTimescaleMinimum = 0.001;

@@ -66,9 +66,9 @@ static void standard_post_step(double time, double *y, int *status, void *vctx) 
 }
 
 static int is_non_negative_prop(int prop) {
-    /* isNonNegative="true" attributes of the component definitions; BH spin and
-       satellite bound mass are not flagged */
-    return prop != GLC_P_BH_SPIN && prop != GLC_P_SAT_BOUND_MASS && prop != GLC_P_BH_MASS;
+    /* isNonNegative="true" attributes of the component definitions; only the satellite
+       bound mass (satellite/standard.F90:46-49) is not flagged */
+    return prop != GLC_P_SAT_BOUND_MASS;
 }
 
 int orc_evolve_node_segment(const glc_params *P, const orc_tables *T, double *props, int *flags,

@@ -75,4 +75,33 @@ def smoke_case(model_name):
         p.box_fractionOutflow = 1.0
         props, flags, t_end = box_nodes(512, seed=11, leaky=True)
         return props, flags, t_end, p, {}
+    if model_name == "standard":
+        from galacticus_b200 import synthetic
+
+        p = standard_params()
+        props, flags, t_end = synthetic.standard_nodes(p, 512, seed=17)
+        return props, flags, t_end, p, synthetic.standard_tables(p)
     raise NotImplementedError(model_name)
+
+
+def standard_params(orc_or_none=None, with_black_holes=False):
+    """quickTest.xml operator set (black-hole operators gated until they are restated)."""
+    from galacticus_b200 import synthetic
+
+    if orc_or_none is not None:
+        p = orc_or_none.params_default(abi.GLC_MODEL_STANDARD)
+    else:
+        from galacticus_b200.evolver import params_default
+
+        p = params_default(abi.GLC_MODEL_STANDARD)
+    if not with_black_holes:
+        p.operatorMask = abi.GLC_OP_ALL & ~(abi.GLC_OP_BLACK_HOLES_SEED | abi.GLC_OP_BLACK_HOLES_ACCRETION
+                                            | abi.GLC_OP_BLACK_HOLES_WINDS)
+    return synthetic.finalize_params(p)
+
+
+def y_scale(props):
+    """Per-node magnitude used as the absolute floor of the 1e-6 comparison (the ODE's own scales)."""
+    m = np.abs(props[:, [P["HH_MASS"], P["DISK_MASS_GAS"], P["DISK_MASS_STELLAR"], P["SPH_MASS_GAS"],
+                         P["SPH_MASS_STELLAR"], P["HH_OUTFLOWED_MASS"]]]).sum(axis=1)
+    return np.maximum(m, 1.0)

@@ -1,0 +1,138 @@
+"""CUDA path vs the CPU oracle on the quickTest operator set (through the C-ABI)."""
+import numpy as np
+import pytest
+
+from galacticus_b200 import abi, synthetic
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+P = abi.P
+RTOL = 1.0e-6  # north_star tolerance on per-galaxy properties
+
+
+def make(orc, **kw):
+    from galacticus_b200.evolver import Evolver
+
+    p = cases.standard_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    ev = Evolver(0)
+    synthetic.install(ev, p)
+    o = orc.Oracle()
+    synthetic.install(o, p)
+    return ev, o, p
+
+
+def compare(pg, po, fg, fo, sg, so, ig, io, what):
+    np.testing.assert_array_equal(sg, so, err_msg=f"{what}: status")
+    np.testing.assert_array_equal(ig, io, err_msg=f"{what}: interrupt")
+    np.testing.assert_array_equal(fg, fo, err_msg=f"{what}: flags")
+    np.testing.assert_array_equal(pg[:, P["TIME"]], po[:, P["TIME"]], err_msg=f"{what}: time")
+    scale = cases.y_scale(po)[:, None]
+    # masses/abundances: relative 1e-6 with the ODE absolute scale (1e-6 of the node's baryons) as floor
+    cases.assert_close(pg[:, :abi.NY], po[:, :abi.NY], RTOL, scale=scale * 1e3, what=f"{what}: y")
+    for k in ("DISK_RADIUS", "DISK_VELOCITY", "SPH_RADIUS", "SPH_VELOCITY", "BASIC_MASS", "DMSCALE", "SPIN"):
+        cases.assert_close(pg[:, P[k]], po[:, P[k]], RTOL, what=f"{what}: {k}")
+
+
+def test_rhs_parity(oracle_lib):
+    """One evaluation of standardODEs per node: every operator, no time stepping."""
+    ev, o, p = make(oracle_lib)
+    props, flags, _ = synthetic.standard_nodes(p, 2000, seed=5)
+    dg, ig, pg = ev.rhs_batch(props, flags)
+    do = np.zeros_like(dg)
+    io = np.zeros_like(ig)
+    po = props.copy()
+    for i in range(props.shape[0]):
+        do[i], io[i], po[i] = o.rhs(props[i], flags[i])
+    np.testing.assert_array_equal(ig, io)
+    scale = np.abs(do).max(axis=1, keepdims=True)
+    cases.assert_close(dg, do, RTOL, scale=scale * 1e-3, what="dydt")
+    for k in ("DISK_RADIUS", "DISK_VELOCITY", "SPH_RADIUS", "SPH_VELOCITY"):
+        cases.assert_close(pg[:, P[k]], po[:, P[k]], RTOL, what=k)
+
+
+@pytest.mark.parametrize("n", [1, 37, 3000])
+def test_evolve_parity(oracle_lib, n):
+    ev, o, p = make(oracle_lib)
+    props, flags, t_end = synthetic.standard_nodes(p, n, seed=100 + n)
+    pg, fg = props.copy(), flags.copy()
+    po, fo = props.copy(), flags.copy()
+    sg, ig, cg = ev.evolve_batch(pg, fg, t_end)
+    so, io, co = o.evolve_batch(po, fo, t_end, n_threads=8)
+    compare(pg, po, fg, fo, sg, so, ig, io, f"n={n}")
+    # integer bookkeeping: same number of segments (component creations) and same step counts
+    assert cg["segments"] == co["segments"]
+    assert cg["steps_accepted"] == co["steps_accepted"]
+    assert cg["steps_rejected"] == co["steps_rejected"]
+    assert cg["rhs_evaluations"] == co["rhs_evaluations"]
+
+
+def test_interrupts_returned_to_host(oracle_lib):
+    """resolveInterruptsOnDevice=0: component-creation interrupts come back to the host loop
+    (evolver/standard.F90:425-476); the host applies them and re-submits; the result equals the on-device path."""
+    ev, o, p = make(oracle_lib, resolveInterruptsOnDevice=0)
+    ev2, _, _ = make(oracle_lib)
+    props, flags, t_end = synthetic.standard_nodes(p, 1500, seed=9, fresh_fraction=0.6)
+    # strip some components so that creation interrupts fire
+    flags[::3] &= ~(abi.GLC_F_HAS_DISK | abi.GLC_F_HAS_SPHEROID)
+    props[::3, P["DISK_MASS_STELLAR"]:P["DISK_ANGMOM"] + 1] = 0.0
+    props[::3, P["SPH_MASS_STELLAR"]:P["SPH_ANGMOM"] + 1] = 0.0
+    p_ref, f_ref = props.copy(), flags.copy()
+    ev2.evolve_batch(p_ref, f_ref, t_end)
+    ph, fh = props.copy(), flags.copy()
+    po, fo = props.copy(), flags.copy()
+    pending = np.arange(props.shape[0])
+    n_round = 0
+    saw_interrupt = False
+    while pending.size and n_round < 16:
+        sub_p, sub_f = ph[pending].copy(), fh[pending].copy()
+        s, i, _ = ev.evolve_batch(sub_p, sub_f, t_end[pending])
+        sub_po, sub_fo = po[pending].copy(), fo[pending].copy()
+        so, io, _ = o.evolve_batch(sub_po, sub_fo, t_end[pending], n_threads=8)
+        np.testing.assert_array_equal(i, io)
+        assert (s == 0).all()
+        saw_interrupt |= bool((i != 0).any())
+        for code, bit in ((abi.GLC_INT_HOTHALO_CREATE, abi.GLC_F_HAS_HOTHALO), (abi.GLC_INT_DISK_CREATE, abi.GLC_F_HAS_DISK),
+                          (abi.GLC_INT_SPHEROID_CREATE, abi.GLC_F_HAS_SPHEROID)):
+            sub_f[i == code] |= bit
+            sub_fo[io == code] |= bit
+        ph[pending], fh[pending] = sub_p, sub_f
+        po[pending], fo[pending] = sub_po, sub_fo
+        pending = pending[(i != 0) & (sub_p[:, P["TIME"]] < t_end[pending])]
+        n_round += 1
+    assert saw_interrupt
+    np.testing.assert_array_equal(fh, f_ref)
+    cases.assert_close(ph[:, :abi.NY], p_ref[:, :abi.NY], 1e-12, scale=1.0, what="host-loop vs on-device")
+    cases.assert_close(ph[:, :abi.NY], po[:, :abi.NY], RTOL, scale=cases.y_scale(po)[:, None] * 1e3, what="vs oracle")
+
+
+def test_baryon_budget_full_size():
+    """Invariant at a size the oracle is not run at: baryons change only by accretion (and by the
+    reference's own negative-mass clamps), cf. testSuite/test-mass-conservation-standard.py:49-85."""
+    from galacticus_b200.evolver import Evolver
+
+    p = cases.standard_params()
+    ev = Evolver(0)
+    synthetic.install(ev, p)
+    n = 200_000
+    props, flags, t_end = synthetic.standard_nodes(p, n, seed=77)
+    p0 = props.copy()
+    s, i, c = ev.evolve_batch(props, flags, t_end)
+    assert (s == 0).all() and (i == 0).all()
+    assert not np.isnan(props).any()
+
+    def bary(q):
+        return sum(q[:, P[k]] for k in ("HH_MASS", "HH_OUTFLOWED_MASS", "HH_UNACCRETED_MASS", "HH_STRIPPED_MASS",
+                                        "DISK_MASS_GAS", "DISK_MASS_STELLAR", "SPH_MASS_GAS", "SPH_MASS_STELLAR"))
+
+    fb = p.OmegaBaryon / p.OmegaMatter
+    sat = (flags & abi.GLC_F_IS_SATELLITE) != 0
+    acc = np.where(sat, 0.0, fb * (props[:, P["BASIC_MASS"]] - p0[:, P["BASIC_MASS"]]))
+    tot = bary(p0) + np.abs(acc)
+    ok = tot > 0
+    d = np.abs(bary(props) - bary(p0) - acc)[ok] / tot[ok]
+    assert np.median(d) < 1e-12
+    assert (d < 1e-3).mean() > 0.9  # only nodes that hit the negative-mass clamps deviate
+    for k in ("HH_MASS", "DISK_MASS_GAS", "DISK_MASS_STELLAR", "SPH_MASS_GAS", "SPH_MASS_STELLAR"):
+        assert (props[:, P[k]] >= 0).all(), k
