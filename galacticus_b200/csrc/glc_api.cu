@@ -132,6 +132,64 @@ __global__ void rhs_kernel(KernelArgs A, double *dydt) {
     AR(GLC_P_BASIC_MASS) = ctx.basicMass;
 }
 
+// debugging aid for the bit-exact parity work: selected intermediates of one RHS evaluation
+__global__ void probe_kernel(KernelArgs A, double *out) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= A.n) return;
+    auto AR = [&](int prop) -> double & { return A.props[(int64_t)prop * A.cap + node]; };
+    NodeCtx c;
+    double y[NY];
+    for (int i = 0; i < NY; i++) y[i] = AR(i);
+    c.flags = A.flags[node];
+    c.massTarget = AR(GLC_P_MASS_TARGET);
+    c.massRate = AR(GLC_P_MASS_RATE);
+    c.timeTarget = AR(GLC_P_TIME_TARGET);
+    c.scaleTarget = AR(GLC_P_DMSCALE_TARGET);
+    c.scaleRate = AR(GLC_P_DMSCALE_RATE);
+    c.spinTarget = AR(GLC_P_SPIN_TARGET);
+    c.spinRate = AR(GLC_P_SPIN_RATE);
+    c.timeLastIsolated = AR(GLC_P_TIME_LAST_ISOLATED);
+    c.diskRadius = AR(GLC_P_DISK_RADIUS);
+    c.diskVelocity = AR(GLC_P_DISK_VELOCITY);
+    c.sphRadius = AR(GLC_P_SPH_RADIUS);
+    c.sphVelocity = AR(GLC_P_SPH_VELOCITY);
+    c.basicMass = AR(GLC_P_BASIC_MASS);
+    c.massBaryonicSubhalos = AR(GLC_P_MASS_BARYONIC_SUBHALOS);
+    c.numericsFailed = 0;
+    const double time = AR(GLC_P_TIME);
+    c.timeNode = time;
+    typedef ModelStandard M;
+    M::solve_analytics(c, time);
+    Work w;
+    int bad = 0;
+    M::halo_scales(c, time, w);
+    M::hh_profile(c, y, w);
+    const double r0 = c.diskRadius > 0.0 ? c.diskRadius : 0.01 * w.rvir;
+    const double nn = M::nfw_norm(c, w);
+    double *o = out + (int64_t)node * 16;
+    o[0] = w.rvir;
+    o[1] = w.vvir;
+    o[2] = w.tvir;
+    o[3] = w.hhRho0;
+    o[4] = M::nfw_mass(nn, c.dmScale, r0);
+    o[5] = M::ac_orbital_mean(w, r0);
+    o[6] = M::baryonic_vc2(c, y, w, r0);
+    o[7] = M::dark_matter_mass_enclosed(c, y, w, nn, r0, bad);
+    o[8] = M::disk_bessel_factor(0.37);
+    o[9] = M::hh_mass_enclosed(w, r0);
+    o[10] = fast_exponentiate(1.0e-3, 1.0, 0.7, 1.0e4, 0.0123);
+    o[11] = M::nfw_radius_from_j(c, w, nn, 0.3 * w.rvir * w.vvir);
+    o[12] = (c.flags & GLC_F_HAS_DISK) ? M::sfr_disk(c, y, bad) : 0.0;
+    double ls;
+    if ((c.flags & GLC_F_HAS_HOTHALO) && y[GLC_P_HH_MASS] > 0) {
+        M::cooling_prepare(y, w, ls);
+        o[13] = M::cooling_radius(y, w, bad);
+    } else
+        o[13] = 0.0;
+    o[14] = sqrt(kGInternal * o[7] / r0 + o[6]);
+    o[15] = dm_log(o[14] / r0);
+}
+
 __global__ void histogram_kernel(const double *__restrict__ v, int n, double lo, double hi, int nb,
                                  double *hist) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,9 +356,9 @@ int glc_evolver_set_table(glc_evolver *ev, int32_t id, int32_t n0, int32_t n1, c
         if (is_log) {
             first_zero = (hx0[0] == 0.0);
             if (first_zero) first_nonzero = hx0[1];
-            for (auto &z : hx0) z = (z > 0.0) ? std::log(z) : -999.0;
-            for (auto &T : hx1) T = std::log(T);
-            for (auto &v : hv) v = std::log(v);
+            for (auto &z : hx0) z = (z > 0.0) ? dm_log(z) : -999.0;
+            for (auto &T : hx1) T = dm_log(T);
+            for (auto &v : hv) v = dm_log(v);
         }
     }
     GLC_CHECK(ev, cudaMalloc(&t.d_x0, sizeof(double) * n0));
@@ -336,7 +394,7 @@ int glc_evolver_set_table(glc_evolver *ev, int32_t id, int32_t n0, int32_t n1, c
         if (n1 != 2) return -1;
         // store ln t on the device; the grid must be log-uniform
         std::vector<double> lnt(n0);
-        for (int i = 0; i < n0; i++) lnt[i] = std::log(hx0[i]);
+        for (int i = 0; i < n0; i++) lnt[i] = dm_log(hx0[i]);
         GLC_CHECK(ev, cudaMemcpy(t.d_x0, lnt.data(), sizeof(double) * n0, cudaMemcpyHostToDevice));
         ev->tables.density = d;
         ev->tables.density_lnt0 = lnt[0];
@@ -344,8 +402,8 @@ int glc_evolver_set_table(glc_evolver *ev, int32_t id, int32_t n0, int32_t n1, c
     } else if (id == GLC_TABLE_DISK_ROTATION_CURVE) {
         if (n1 != 1) return -1;
         ev->tables.diskrc = d;
-        ev->tables.diskrc_lnx0 = std::log(hx0[0]);
-        ev->tables.diskrc_inv_dlnx = (double)(n0 - 1) / (std::log(hx0[n0 - 1]) - std::log(hx0[0]));
+        ev->tables.diskrc_lnx0 = dm_log(hx0[0]);
+        ev->tables.diskrc_inv_dlnx = (double)(n0 - 1) / (dm_log(hx0[n0 - 1]) - dm_log(hx0[0]));
     }
     return 0;
 }
@@ -498,5 +556,27 @@ int glc_histogram_accumulate(glc_evolver *ev, int64_t n, int32_t prop, double lo
 }
 
 int glc_params_default(glc_params *P, int32_t model);  // defined in glc_params.cpp
+
+// not part of the public header: debugging aid (16 intermediates per node)
+int glc_debug_probe(glc_evolver *ev, int64_t n, const double *props, const int32_t *flags, double *out) {
+    std::vector<double> te((size_t)n, 0.0);
+    int rc = glc_arena_upload(ev, n, props, flags, te.data());
+    if (rc) return rc;
+    rc = upload_constants(ev);
+    if (rc) return rc;
+    double *d_out = nullptr;
+    GLC_CHECK(ev, cudaMalloc(&d_out, sizeof(double) * 16 * n));
+    KernelArgs A{};
+    A.props = ev->d_props;
+    A.flags = ev->d_flags;
+    A.cap = ev->cap;
+    A.n = (int)n;
+    probe_kernel<<<(int)((n + 63) / 64), 64, 0, ev->stream>>>(A, d_out);
+    GLC_CHECK(ev, cudaGetLastError());
+    GLC_CHECK(ev, cudaMemcpyAsync(out, d_out, sizeof(double) * 16 * n, cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    cudaFree(d_out);
+    return 0;
+}
 
 }  // extern "C"

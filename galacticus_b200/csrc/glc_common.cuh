@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/glc_b200.h"
+#include "glc_detmath.h"
 
 namespace glc {
 

@@ -21,6 +21,12 @@
 
 #include "glc_common.cuh"
 
+#ifdef GLC_TRACE
+#define GTR(...) printf(__VA_ARGS__)
+#else
+#define GTR(...)
+#endif
+
 namespace glc {
 
 // Cash-Karp tableau (Cash & Karp 1990). Row s = weights of k1..k6 used to build the input of
@@ -109,7 +115,18 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
             timeStepIn = AR(GLC_P_TIME_STEP, node);
             nSeg++;
             segmentsThisNode++;
-            Model::pre_evolve(ctx, y);
+            {
+                // pre-evolve hooks edit the node itself (they run before the solver's saved copy is taken,
+                // standard.F90:434-441 vs :518-527), so their edits must survive a solver restart
+                const int flagsBefore = ctx.flags;
+                Model::pre_evolve(ctx, y);
+                if (ctx.flags != flagsBefore) {
+#pragma unroll
+                    for (int i = 0; i < NY; i++) AR(i, node) = y[i];
+                    AR(GLC_P_BASIC_MASS, node) = ctx.basicMass;
+                    A.flags[node] = ctx.flags;
+                }
+            }
             mask = Model::active_mask(ctx.flags);
             Model::scales(ctx, y, s);
 #pragma unroll
@@ -136,7 +153,7 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
                 for (int i = 0; i < NY; i++) W(WS_YA, i) = AR(i, node);
             }
             yslot = 0;
-            double stepSize = c_params.reuseODEStepSize ? timeStepIn / exp2((double)trial) : -1.0;
+            double stepSize = c_params.reuseODEStepSize ? timeStepIn / dm_scale2(1.0, trial) : -1.0;
             x = timeStartSaved;
             x1 = tEnd;
             double xStep = x1 - x;
@@ -182,9 +199,13 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
                 } else if (stage < 6) {
 #pragma unroll
                     for (int i = 0; i < NY; i++) {
-                        double acc = c_rk_b[stage][0] * W(k1v, i);
-                        for (int j = 1; j < stage; j++) acc += c_rk_b[stage][j] * W(WS_K2 + j - 1, i);
-                        yt[i] = W(ySrc, i) + h0 * acc;
+                        if (stage == 1) {
+                            yt[i] = W(ySrc, i) + c_rk_b[1][0] * h0 * W(k1v, i);  // rkck.c: y + b21*h*k1
+                        } else {
+                            double acc = c_rk_b[stage][0] * W(k1v, i);
+                            for (int j = 1; j < stage; j++) acc += c_rk_b[stage][j] * W(WS_K2 + j - 1, i);
+                            yt[i] = W(ySrc, i) + h0 * acc;
+                        }
                     }
                 } else {
                     // 5th-order solution, error estimate and the controller's rmax (cscal2.c:109-126;
@@ -216,11 +237,11 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
                 Model::solve_analytics(ctx, ts);
                 int code = GLC_INT_NONE;
                 int ebadfunc = 0;
+                nRhs++;  // every call of the derivatives function counts (also the frozen ones past an interrupt)
                 if (interruptFound && ts >= timeInterruptFirst) {
                     Model::solve_analytics(ctx, timeInterruptFirst);
                 } else {
                     code = Model::rates(ctx, ts, yt, rate);
-                    nRhs++;
                     if (code != GLC_INT_NONE) {
 #pragma unroll
                         for (int i = 0; i < NY; i++) rate[i] = 0.0;
@@ -247,20 +268,32 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
                     break;
                 }
             }
+            GTR("attempt t0=%.17g h0=%.17g t1=%.17g final=%d count=%d aborted=%d rmax=%.17g\n", t0, h0, x1, finalStep, count, aborted, rmax);
             if (aborted) {
-                // odeSolverInterrupt: solver.F90:608-618 (x <= interruptedAtX always holds going forward)
+                // odeSolverInterrupt, solver.F90:608-618.  NB (GSL quirk, reproduced): gsl_odeiv2_evolve_apply
+                // leaves *t at the end of a REJECTED attempt when the retry returns early, so x may be ahead
+                // of t0 here; if it is beyond the interrupt time the solver restarts from the initial state.
                 x1 = timeInterruptFirst;
                 inApply = 0;
+                if (x > x1) {
+#pragma unroll
+                    for (int i = 0; i < NY; i++) W(WS_YA, i) = AR(i, node);
+                    yslot = 0;
+                    x = timeStartSaved;
+                    count = 0;  // GSL_ODEIV2_Driver_Reset
+                    outWritten = 0;
+                }
                 if (!(x < x1)) phase = PH_SOLVE_DONE;
                 continue;
             }
             count++;
             const double tNew = finalStep ? x1 : t0 + h0;
+            x = tNew;  // evolve.c sets *t before the controller runs and does not restore it on a retry
             // ---- sc2_control_hadjust (ord = 5)
             const double hOld = h0;
             int dec = 0;
             if (rmax > 1.1) {
-                double r = 0.9 / pow(rmax, 1.0 / 5.0);
+                double r = 0.9 / dm_pow(rmax, 1.0 / 5.0);
                 if (r < 0.2) r = 0.2;
                 h0 = r * hOld;
                 dec = 1;
@@ -268,11 +301,12 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
                 h0 = 0.5 * hOld;
                 dec = 1;
             } else if (rmax < 0.5) {
-                double r = 0.9 / pow(rmax, 1.0 / 6.0);
+                double r = 0.9 / dm_pow(rmax, 1.0 / 6.0);
                 if (r > 4.9) r = 4.9;
                 if (r < 1.0) r = 1.0;
                 h0 = r * hOld;
             }
+            GTR("  dec=%d h_old=%.17g h_new=%.17g\n", dec, hOld, h0);
             if (dec) {
                 const double tNext = tNew + h0;
                 if (fabs(h0) < fabs(hOld) && tNext != tNew) {
@@ -284,14 +318,12 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
                 h = h0;
                 inApply = 0;
                 solveFailed = 1;
-                x = tNew;
                 yslot ^= 1;  // as in GSL, y holds the failed step's result
                 phase = PH_SOLVE_DONE;
                 continue;
             }
             // ---- accepted
             if (!finalStep) h = h0;
-            x = tNew;
             yslot ^= 1;
             inApply = 0;
             nAcc++;
@@ -328,7 +360,7 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
                         }
                 }
                 if (rescued) {
-                    h = timeStepIn / exp2((double)trial);
+                    h = timeStepIn / dm_scale2(1.0, trial);
                     solveFailed = 0;
                 } else {
                     trial++;

@@ -28,9 +28,8 @@ struct Work {
     // hot-halo beta profile
     double hhRouter, hhRcore, hhRho0;
     bool hhValid;
-    // cooling: t_cool(rho) = coolA / rho for the node's (T_vir, Z_hot)
-    double coolA, coolTavail, rcool;
-    bool coolReady;
+    // cooling: CIE table values at the node's (T_vir, Z_hot), looked up once per RHS call
+    double coolLambda, coolEfrac, coolXH, coolFHn, coolTavail;
     bool plausible, solvable;
 };
 
@@ -71,7 +70,7 @@ struct CieFactors {
 __device__ __forceinline__ CieFactors cie_factors(const DeviceTable2D &t, bool isLog, bool firstZero,
                                                   double firstNonzero, double temperature, double metallicity) {
     CieFactors f;
-    double tu = isLog ? log(temperature) : temperature;
+    double tu = isLog ? dm_log(temperature) : temperature;
     int i = min(max(locate(t.x1, t.n1, tu), 1), t.n1 - 1);
     f.iT = i;
     f.hT = (tu - __ldg(t.x1 + i - 1)) / (__ldg(t.x1 + i) - __ldg(t.x1 + i - 1));
@@ -80,7 +79,7 @@ __device__ __forceinline__ CieFactors cie_factors(const DeviceTable2D &t, bool i
         f.iZ = 1;
         f.hZ = zu / firstNonzero;
     } else {
-        if (isLog) zu = log(zu);
+        if (isLog) zu = dm_log(zu);
         i = min(max(locate(t.x0, t.n0, zu), 1), t.n0 - 1);
         f.iZ = i;
         f.hZ = (zu - __ldg(t.x0 + i - 1)) / (__ldg(t.x0 + i) - __ldg(t.x0 + i - 1));
@@ -92,7 +91,7 @@ __device__ __forceinline__ double cie_interpolate(const DeviceTable2D &t, bool i
     const double *b = a + t.n1;
     const double r = __ldg(a) * (1.0 - f.hT) * (1.0 - f.hZ) + __ldg(b) * (1.0 - f.hT) * f.hZ +
                      __ldg(a + 1) * f.hT * (1.0 - f.hZ) + __ldg(b + 1) * f.hT * f.hZ;
-    return isLog ? exp(r) : r;
+    return isLog ? dm_exp(r) : r;
 }
 
 struct ModelStandard {
@@ -122,7 +121,7 @@ struct ModelStandard {
         double time = c.timeLastIsolated;
         if (!has(c, GLC_F_IS_SATELLITE) || time <= 0.0) time = timeNow;
         const DeviceTable2D &t = c_tables.density;
-        const double lnt = log(time);
+        const double lnt = dm_log(time);
         const double x = (lnt - c_tables.density_lnt0) * c_tables.density_inv_dlnt;
         int i = (int)x;
         if (lnt < c_tables.density_lnt0) i = 0;
@@ -130,7 +129,7 @@ struct ModelStandard {
         const double h = x - (double)i;
         w.rhoMean = __ldg(t.v + 2 * i) * (1.0 - h) + __ldg(t.v + 2 * (i + 1)) * h;
         w.dlnrhoDt = __ldg(t.v + 2 * i + 1) * (1.0 - h) + __ldg(t.v + 2 * (i + 1) + 1) * h;
-        w.rvir = cbrt(3.0 * c.basicMass / 4.0 / kPi / w.rhoMean);
+        w.rvir = dm_cbrt(3.0 * c.basicMass / 4.0 / kPi / w.rhoMean);
         w.vvir = sqrt(kGInternal * c.basicMass / w.rvir);
         w.tdyn = w.rvir / w.vvir * kMpcPerKmPerSToGyr;
         w.tvir = 0.5 * kAtomicMassUnit * kMeanAtomicMassPrimordial * ((kKilo * w.vvir) * (kKilo * w.vvir)) / kBoltzmann;
@@ -151,13 +150,13 @@ struct ModelStandard {
         w.hhRho0 = 0.0;
         if (!w.hhValid) return;
         const double r = w.hhRouter / w.hhRcore;
-        const double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - atan(r));
+        const double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - dm_atan(r));
         w.hhRho0 = mass / 4.0 / kPi / (w.hhRcore * w.hhRcore * w.hhRcore) * nf;
     }
     static __device__ __forceinline__ double hh_density(const Work &w, double radius) {
         if (!w.hhValid || radius > w.hhRouter) return 0.0;
         const double x = radius / w.hhRcore;
-        return w.hhRho0 / pow(1.0 + x * x, 1.5 * c_params.hotHaloBeta);
+        return w.hhRho0 / dm_pow(1.0 + x * x, 1.5 * c_params.hotHaloBeta);
     }
     static __device__ __forceinline__ double hh_mass_enclosed(const Work &w, double radius) {
         if (!w.hhValid) return 0.0;
@@ -166,13 +165,12 @@ struct ModelStandard {
         const double rc3 = w.hhRcore * w.hhRcore * w.hhRcore;
         if (x < 1.0e-6)
             return 4.0 * kPi * w.hhRho0 * rc3 * (x * x * x) * (1.0 / 3.0 + x * x * (-1.0 / 5.0 + x * x * (1.0 / 7.0)));
-        return 4.0 * kPi * w.hhRho0 * (x - atan(x)) * rc3;
+        return 4.0 * kPi * w.hhRho0 * (x - dm_atan(x)) * rc3;
     }
 
     // ---------------------------------------------------------------- cooling
-    // coolingTimeSimple (cooling/cooling_time/simple.F90:128-179) with the CIE tables evaluated once at
-    // (T_vir, Z_hot) -- the reference memoises the same way (CIE_file.F90:300-312): only n_H varies
-    // along the cooling-radius root find, so t_cool(rho) = coolA / rho.
+    // CIE table look-ups are done once per RHS call at (T_vir, Z_hot) -- the reference memoises the same
+    // way (CIE_file.F90:300-312): only n_H varies along the cooling-radius root find.
     static __device__ __forceinline__ void cooling_prepare(const double (&y)[NY], Work &w, double &logSlopeT) {
         const double z = mass_to_fraction(y[GLC_P_HH_ABUND], y[GLC_P_HH_MASS]);
         const DeviceTable2D &tc = c_tables.cooling;
@@ -207,19 +205,24 @@ struct ModelStandard {
         const CieFactors fe = cie_factors(te, c_tables.electron_log, c_tables.electron_first_z_zero,
                                           c_tables.electron_first_nonzero_z, te_t, te_z);
         const double efrac = cie_interpolate(te, c_tables.electron_log, fe);
-        // n_H = rho * c1 ; n_all = n_H (1/f_H + e) ; t_cool = dof/2 k T n_all / ergs / (Lambda n_H^2) / Gyr
-        const double c1 = hydrogen_mass_fraction(z) * kMassSolar / kMassHydrogenAtom / (kHecto * kHecto * kHecto) /
-                          (kMegaParsec * kMegaParsec * kMegaParsec);
-        const double nall = 1.0 / hydrogen_number_fraction(z) + efrac;
-        w.coolA = (lambda > 0.0)
-                      ? c_params.coolingDegreesOfFreedom / 2.0 * kBoltzmann * w.tvir * nall / kErgs / lambda / kGigaYear / c1
-                      : -1.0;
+        w.coolLambda = lambda;
+        w.coolEfrac = efrac;
+        w.coolXH = hydrogen_mass_fraction(z);
+        w.coolFHn = hydrogen_number_fraction(z);
         w.coolTavail = w.tdyn;  // whiteFrenk1991TimeAvailable, ageFactor = 0 (time_available/White-Frenk.F90:144-146)
-        w.coolReady = true;
     }
     static __device__ __forceinline__ double cooling_time(const Work &w, double density) {
+        // coolingTimeSimple::time, cooling/cooling_time/simple.F90:128-179
         const double timeLarge = 1.0e10;
-        return (w.coolA > 0.0 && density > 0.0) ? w.coolA / density : timeLarge;
+        const double nh = density * w.coolXH * kMassSolar / kMassHydrogenAtom / (kHecto * kHecto * kHecto) /
+                          (kMegaParsec * kMegaParsec * kMegaParsec);
+        const double nall = nh / w.coolFHn + w.coolEfrac * nh;
+        const double cf = w.coolLambda * nh * nh;
+        if (cf > 0.0) {
+            const double e = c_params.coolingDegreesOfFreedom / 2.0 * kBoltzmann * w.tvir * nall / kErgs;
+            return e / cf / kGigaYear;
+        }
+        return timeLarge;
     }
     static __device__ __forceinline__ double cooling_radius(const double (&y)[NY], Work &w, int &bad) {
         // coolingRadiusSimple::radius, cooling/cooling_radius/simple.F90:313-387
@@ -247,9 +250,9 @@ struct ModelStandard {
         // exponentialDiskBesselFactorRotationCurve, mass_distributions/cylindrical/exponential_disk.F90:675-733
         const double ln2 = 0.69314718055994530942, euler = 0.57721566490153286061;
         if (halfRadius <= 0.0) return 0.0;
-        if (halfRadius < 1.0e-3) return (ln2 - euler - 0.5 - log(halfRadius)) * halfRadius * halfRadius;
+        if (halfRadius < 1.0e-3) return (ln2 - euler - 0.5 - dm_log(halfRadius)) * halfRadius * halfRadius;
         const DeviceTable2D &t = c_tables.diskrc;
-        const double x = (log(halfRadius) - c_tables.diskrc_lnx0) * c_tables.diskrc_inv_dlnx;
+        const double x = (dm_log(halfRadius) - c_tables.diskrc_lnx0) * c_tables.diskrc_inv_dlnx;
         const int i = max(min((int)x, t.n0 - 2), 0);
         const double h = x - (double)i;
         return __ldg(t.v + i) * (1.0 - h) + __ldg(t.v + i + 1) * h;
@@ -275,14 +278,17 @@ struct ModelStandard {
     }
     static __device__ __forceinline__ double nfw_mass_scale_free(double x) {
         // massEnclosedScaleFree, mass_distributions/spherical/NFW.F90:550-571
-        if (x == 1.0) return log(2.0) - 0.5;
-        if (x >= 1.0e-6) return log(1.0 + x) - x / (1.0 + x);
+        if (x == 1.0) return dm_log(2.0) - 0.5;
+        if (x >= 1.0e-6) return dm_log(1.0 + x) - x / (1.0 + x);
         return x * x * (0.5 + x * (-2.0 / 3.0 + x * (0.75 + x * (-0.8))));
     }
     // NFW M(<r) = nfwNorm * m(r/rs), nfwNorm = M_vir / m(c)  (NFW.F90:254-255,444-464)
     static __device__ __forceinline__ double nfw_norm(const NodeCtx &c, const Work &w) {
         const double conc = w.rvir / c.dmScale;
-        return c.basicMass / (log(1.0 + conc) - conc / (1.0 + conc));
+        return c.basicMass / (dm_log(1.0 + conc) - conc / (1.0 + conc));
+    }
+    static __device__ __forceinline__ double nfw_mass(double nfwNorm, double rs, double radius) {
+        return nfwNorm * nfw_mass_scale_free(radius / rs);
     }
     static __device__ __forceinline__ double ac_orbital_mean(const Work &w, double radius) {
         // sphericalAdiabaticGnedin2004RadiusOrbitalMean, adiabatic_Gnedin2004.F90:664-687
@@ -302,7 +308,7 @@ struct ModelStandard {
         // dark_matter_profiles/adiabatic_Gnedin2004.F90:302-364
         const double rs = c.dmScale;
         const double fDm = 1.0 - c_params.OmegaBaryon / c_params.OmegaMatter;
-        if (!c_params.adiabaticContraction) return nfwNorm * nfw_mass_scale_free(radius / rs);
+        if (!c_params.adiabaticContraction) return nfw_mass(nfwNorm, rs, radius);
         if (radius <= 0.0) return 0.0;
         double rInit;
         if (radius >= w.rvir)
@@ -316,9 +322,9 @@ struct ModelStandard {
             const double rmean = ac_orbital_mean(w, radius);
             const double bterm = baryonic_vc2(c, y, w, rmean) * rmean * radius / kGInternal;
             auto solver = [&](double ri) {
-                return nfwNorm * nfw_mass_scale_free(ac_orbital_mean(w, ri) / rs) * (fi * ri - fd * radius) - bterm;
+                return nfw_mass(nfwNorm, rs, ac_orbital_mean(w, ri)) * (fi * ri - fd * radius) - bterm;
             };
-            const double menc = nfwNorm * nfw_mass_scale_free(rmean / rs);
+            const double menc = nfw_mass(nfwNorm, rs, rmean);
             double rup = radius;
             if (menc > 0.0) rup = fmax((bterm / menc + fd * radius) / fi, radius);
             // the reference first tests solver(r_vir) < 0 (:463-466)
@@ -332,21 +338,21 @@ struct ModelStandard {
                 if (st != 0) bad = 1;
             }
         }
-        return fDm * nfwNorm * nfw_mass_scale_free(rInit / rs);
+        return fDm * nfw_mass(nfwNorm, rs, rInit);
     }
     static __device__ __forceinline__ double nfw_radius_from_j(const NodeCtx &c, const Work &w, double nfwNorm, double j) {
         // stands in for nfwRadiusFromSpecificAngularMomentum (NFW.F90:589-625): solve j = sqrt(G M(<r) r)
         if (!(j > 0.0)) return 0.0;
-        const double lnj = log(j), rs = c.dmScale;
+        const double lnj = dm_log(j), rs = c.dmScale;
         const RootOptions o{1.0e-12, 0.0, EXPAND_ADDITIVE, 2.0, -2.0, SIGN_POSITIVE, SIGN_NEGATIVE};
         int st;
         const double lnr = root_find(
             [&](double lr) {
-                const double r = exp(lr);
-                return 0.5 * log(kGInternal * nfwNorm * nfw_mass_scale_free(r / rs) * r) - lnj;
+                const double r = dm_exp(lr);
+                return 0.5 * dm_log(kGInternal * nfw_mass(nfwNorm, rs, r) * r) - lnj;
             },
-            o, log(w.rvir) - 4.0, log(w.rvir), false, 0.0, 0.0, st);
-        return (st != 0) ? w.rvir : exp(lnr);
+            o, dm_log(w.rvir) - 4.0, dm_log(w.rvir), false, 0.0, 0.0, st);
+        return (st != 0) ? w.rvir : dm_exp(lnr);
     }
     static __device__ __forceinline__ void plausibility(const NodeCtx &c, const double (&y)[NY], double time, Work &w) {
         // basic/standard/_class.F90:105-123; disk/standard/_class.F90:999-1049; spheroid/standard/_class.F90:1249-1296
@@ -357,14 +363,15 @@ struct ModelStandard {
             w.solvable = false;
             return;
         }
-        const double s0 = w.rvir * w.vvir;
         if (has(c, GLC_F_HAS_DISK)) {
             const double m = y[GLC_P_DISK_MASS_STELLAR] + y[GLC_P_DISK_MASS_GAS], j = y[GLC_P_DISK_ANGMOM];
-            if (m >= 0.0 && j > 0.0 && (j > 1.0e1 * m * s0 || j < 1.0e-6 * m * s0)) w.plausible = false;
+            const double s = m * w.rvir * w.vvir;
+            if (m >= 0.0 && j > 0.0 && (j > 1.0e1 * s || j < 1.0e-6 * s)) w.plausible = false;
         }
         if (w.plausible && has(c, GLC_F_HAS_SPHEROID)) {
             const double m = y[GLC_P_SPH_MASS_STELLAR] + y[GLC_P_SPH_MASS_GAS], j = y[GLC_P_SPH_ANGMOM];
-            if (m >= 0.0 && j > 0.0 && (j > 1.0e1 * m * s0 || j < 1.0e-6 * m * s0)) w.plausible = false;
+            const double s = m * w.rvir * w.vvir;
+            if (m >= 0.0 && j > 0.0 && (j > 1.0e1 * s || j < 1.0e-6 * s)) w.plausible = false;
         }
     }
     static __device__ __forceinline__ double component_j(const double (&y)[NY], int comp) {
@@ -401,9 +408,9 @@ struct ModelStandard {
                     radius = comp == 0 ? c.diskRadius : c.sphRadius;
                     if (radius <= 0.0) {
                         const double radiusLarge = 1.0e10;
-                        const double jmax = sqrt(kGInternal * nfwNorm * nfw_mass_scale_free(radiusLarge / c.dmScale) / radiusLarge) * radiusLarge;
+                        const double jmax = sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radiusLarge) / radiusLarge) * radiusLarge;
                         radius = (jmax < j) ? w.rvir : nfw_radius_from_j(c, w, nfwNorm, j);
-                        velocity = (radius > 0.0) ? sqrt(kGInternal * nfwNorm * nfw_mass_scale_free(radius / c.dmScale) / radius) : 0.0;
+                        velocity = (radius > 0.0) ? sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radius) / radius) : 0.0;
                     } else
                         velocity = comp == 0 ? c.diskVelocity : c.sphVelocity;
                 } else {
@@ -427,7 +434,7 @@ struct ModelStandard {
                     }
                     h1 = h0;
                     h0 = radius;
-                    if (radius > 0.0 && radiusNew > 0.0) fit += fabs(log(radiusNew / radius));
+                    if (radius > 0.0 && radiusNew > 0.0) fit += fabs(dm_log(radiusNew / radius));
                     radius = radiusNew;
                     if (!(radius > 0.0)) bad = 1;
                 }
@@ -456,7 +463,7 @@ struct ModelStandard {
     };
     static __device__ __forceinline__ double kmt_rate(const Kmt &k, double radius) {
         // krumholz2009Rate :360-414 with the exponential-disk surface density (exponential_disk.F90:484-499)
-        const double sg = k.sigma0 * exp(-radius / k.rdisk);
+        const double sg = k.sigma0 * dm_exp(-radius / k.rdisk);
         const double sgd = k.xh * sg / 85.0e12;
         if (sg <= 1.0e-100) return 0.0;
         const double s = k.sNorm / (k.sigmaNorm * sg);
@@ -481,13 +488,13 @@ struct ModelStandard {
         k.rdisk = rdisk;
         k.sigma0 = fmax(0.0, mgas) / (2.0 * kPi * rdisk * rdisk);
         if (!(k.zsolar > 0.0)) return 0.0;
-        const double chi = 0.77 * (1.0 + 3.1 * pow(k.zsolar, 0.365));
+        const double chi = 0.77 * (1.0 + 3.1 * dm_pow(k.zsolar, 0.365));
         k.sigmaNorm = k.xh * c_params.clumpingFactorMolecularComplex / (kMega * kMega);
-        k.sNorm = log(1.0 + 0.6 * chi + 0.01 * chi * chi) / (0.04 * k.zsolar);
+        k.sNorm = dm_log(1.0 + 0.6 * chi + 0.01 * chi * chi) / (0.04 * k.zsolar);
         if (!(k.sigmaNorm > 0.0)) return 0.0;
         k.sigmaTrunc = k.sNorm / k.sigmaNorm / c_params.krumholzSTruncation;
         const double rIn = 0.0, rOut = 10.0 * rdisk;
-        auto sigma = [&](double r) { return k.sigma0 * exp(-r / k.rdisk); };
+        auto sigma = [&](double r) { return k.sigma0 * dm_exp(-r / k.rdisk); };
         double sg = sigma(rIn);
         const double sgdIn = k.xh * sg / 85.0e12;
         if (sg <= k.sigmaTrunc) return 0.0;
@@ -530,7 +537,7 @@ struct ModelStandard {
         // rates/spheroids/timescale.F90:109-130 + timescales/dynamical_time.F90:121-189
         const double v = c.sphVelocity, r = c.sphRadius;
         if (v <= 0.0 || c_params.sfSpheroidEfficiency == 0.0) return 0.0;
-        const double tau = fmax(kMpcPerKmPerSToGyr * r / v * pow(v / 200.0, c_params.sfSpheroidExponentVelocity) /
+        const double tau = fmax(kMpcPerKmPerSToGyr * r / v * dm_pow(v / 200.0, c_params.sfSpheroidExponentVelocity) /
                                     c_params.sfSpheroidEfficiency,
                                 c_params.sfSpheroidTimescaleMinimum);
         return (tau > 0.0) ? y[GLC_P_SPH_MASS_GAS] / tau : 0.0;
@@ -648,7 +655,7 @@ struct ModelStandard {
             const double vchar = IS_DISK ? c_params.fbDiskVelocityCharacteristic : c_params.fbSpheroidVelocityCharacteristic;
             const double expo = IS_DISK ? c_params.fbDiskExponent : c_params.fbSpheroidExponent;
             const double energy = kFeedbackEnergyInputAtInfinityCanonical * psi;
-            double outflow = (velocity <= 0.0) ? 0.0 : pow(vchar / velocity, expo) * energy / kFeedbackEnergyInputAtInfinityCanonical;
+            double outflow = (velocity <= 0.0) ? 0.0 : dm_pow(vchar / velocity, expo) * energy / kFeedbackEnergyInputAtInfinityCanonical;
             const double tdyn = (velocity <= 0.0 || radius <= 0.0) ? 1.0 : kMpcPerKmPerSToGyr * radius / velocity;
             const double outflowMax = fmax(massGas / tdyn / c_params.fbTimescaleOutflowFractionalMinimum, 0.0);
             if (outflow > outflowMax) outflow = outflow * outflowMax / outflow;
@@ -812,8 +819,8 @@ struct ModelStandard {
                 double jSpecific = 0.0;
                 if (rinfall > 0.0) {
                     const double x = w.hhRouter / w.hhRcore;
-                    const double m2 = (x < 1.0e-6) ? x * x * x * (1.0 / 3.0 - x * x / 5.0) : x - atan(x);
-                    const double m3 = (x < 1.0e-6) ? x * x * x * x * (1.0 / 4.0 - x * x / 6.0) : 0.5 * (x * x - log(1.0 + x * x));
+                    const double m2 = (x < 1.0e-6) ? x * x * x * (1.0 / 3.0 - x * x / 5.0) : x - dm_atan(x);
+                    const double m3 = (x < 1.0e-6) ? x * x * x * x * (1.0 / 4.0 - x * x / 6.0) : 0.5 * (x * x - dm_log(1.0 + x * x));
                     const double rc = w.hhRcore;
                     const double norm = (m2 * w.hhRho0 * (rc * rc * rc)) / (m3 * w.hhRho0 * (rc * rc * rc * rc));
                     jSpecific = norm * (y[GLC_P_HH_ANGMOM] / y[GLC_P_HH_MASS]) * rinfall;

@@ -259,11 +259,13 @@ __constant__ double c_wgk[8] = {0.022935322010529224963732008058970, 0.063092092
                                 0.204432940075298892414161999234649, 0.209482141084727828012999174891714};
 // xgk index visited by pair k = 0..6 (qk.c loops: jtw = 1,3,5 then jtwm1 = 0,2,4,6)
 __constant__ int c_qk_order[7] = {1, 3, 5, 0, 2, 4, 6};
+// position p of xgk index k in that visiting order (result_asc is summed in xgk order)
+__constant__ int c_qk_pos[7] = {3, 0, 4, 1, 5, 2, 6};
 
 __device__ __forceinline__ double rescale_error(double err, double resultAbs, double resultAsc) {
     err = fabs(err);
     if (resultAsc != 0 && err != 0) {
-        const double scale = pow((200 * err / resultAsc), 1.5);
+        const double scale = dm_pow((200 * err / resultAsc), 1.5);
         err = (scale < 1) ? resultAsc * scale : resultAsc;
     }
     if (resultAbs > DBL_MIN / (50 * DBL_EPSILON)) {
@@ -323,8 +325,10 @@ __device__ __forceinline__ double qag15(F &&f, double a, double b, double epsabs
             const double mean = resultKronrod * 0.5;
             double resultAsc = c_wgk[7] * fabs(fCenter - mean);
 #pragma unroll
-            for (int p = 0; p < 7; p++)
-                resultAsc += c_wgk[c_qk_order[p]] * (fabs(fv[1 + 2 * p] - mean) + fabs(fv[2 + 2 * p] - mean));
+            for (int k = 0; k < 7; k++) {
+                const int p = c_qk_pos[k];
+                resultAsc += c_wgk[k] * (fabs(fv[1 + 2 * p] - mean) + fabs(fv[2 + 2 * p] - mean));
+            }
             const double err = (resultKronrod - resultGauss) * halfLength;
             resultKronrod *= halfLength;
             resultAbs *= absHalfLength;
@@ -443,9 +447,9 @@ __device__ __forceinline__ double linear_table_eval(G &&g, double xmin, double x
 
 __device__ __forceinline__ double fast_exponentiate(double rangeMin, double rangeMax, double exponent,
                                                     double density, double x) {
-    if (x < rangeMin || x > rangeMax) return pow(x, exponent);
+    if (x < rangeMin || x > rangeMax) return dm_pow(x, exponent);
     const int pointCount = (int)((rangeMax - rangeMin) * density) + 1;
-    return linear_table_eval([exponent](double t) { return pow(t, exponent); }, rangeMin, rangeMax, pointCount, x,
+    return linear_table_eval([exponent](double t) { return dm_pow(t, exponent); }, rangeMin, rangeMax, pointCount, x,
                              false);
 }
 

@@ -24,6 +24,8 @@
  */
 #include <float.h>
 #include <math.h>
+
+#include "../galacticus_b200/csrc/glc_detmath.h"
 #include <string.h>
 
 #include "orc_constants.h"
@@ -96,9 +98,9 @@ static void halo_scales(std_work *w) {
     w->halo_done = 1;
     time = w->p[GLC_P_TIME_LAST_ISOLATED];
     if (!has(w, GLC_F_IS_SATELLITE) || time <= 0.0) time = w->time;
-    lnt = log(time);
+    lnt = dm_log(time);
     {
-        const double lnt0 = log(t->x0[0]), lnt1 = log(t->x0[t->n0 - 1]);
+        const double lnt0 = dm_log(t->x0[0]), lnt1 = dm_log(t->x0[t->n0 - 1]);
         const double inv = (double)(t->n0 - 1) / (lnt1 - lnt0);
         x = (lnt - lnt0) * inv;
         i = (int)x;
@@ -111,7 +113,7 @@ static void halo_scales(std_work *w) {
     w->dlnrho_dt = t->v[2 * i + 1] * (1.0 - h) + t->v[2 * (i + 1) + 1] * h;
     {
         double mass = w->p[GLC_P_BASIC_MASS];
-        w->rvir = cbrt(3.0 * mass / 4.0 / ORC_PI / w->rho_mean);
+        w->rvir = dm_cbrt(3.0 * mass / 4.0 / ORC_PI / w->rho_mean);
         w->vvir = sqrt(ORC_G_INTERNAL * mass / w->rvir);
         w->tdyn = w->rvir / w->vvir * ORC_MPC_PER_KMS_TO_GYR;
         w->tvir = 0.5 * ORC_ATOMIC_MASS_UNIT * ORC_MEAN_ATOMIC_MASS_PRIMORDIAL *
@@ -146,7 +148,7 @@ static void hh_profile(std_work *w) {
     if (!w->hh_valid) return;
     r = w->hh_router / w->hh_rcore;
     {
-        double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - atan(r));
+        double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - dm_atan(r));
         w->hh_rho0 = w->hh_mass / 4.0 / ORC_PI / (w->hh_rcore * w->hh_rcore * w->hh_rcore) * nf;
     }
 }
@@ -157,7 +159,7 @@ static double hh_density(std_work *w, double radius) {
     if (!w->hh_valid) return 0.0;
     if (radius > w->hh_router) return 0.0;
     x = radius / w->hh_rcore;
-    return w->hh_rho0 / pow(1.0 + x * x, 1.5 * w->P->hotHaloBeta);
+    return w->hh_rho0 / dm_pow(1.0 + x * x, 1.5 * w->P->hotHaloBeta);
 }
 static double hh_mass_enclosed(std_work *w, double radius) {
     /* betaProfileMassEnclosedBySphere :377-437, beta = 2/3 */
@@ -169,13 +171,13 @@ static double hh_mass_enclosed(std_work *w, double radius) {
     if (x < 1.0e-6)
         return 4.0 * ORC_PI * w->hh_rho0 * (w->hh_rcore * w->hh_rcore * w->hh_rcore) * (x * x * x) *
                (1.0 / 3.0 + x * x * (-1.0 / 5.0 + x * x * (1.0 / 7.0)));
-    return 4.0 * ORC_PI * w->hh_rho0 * (x - atan(x)) * (w->hh_rcore * w->hh_rcore * w->hh_rcore);
+    return 4.0 * ORC_PI * w->hh_rho0 * (x - dm_atan(x)) * (w->hh_rcore * w->hh_rcore * w->hh_rcore);
 }
 static double hh_radial_moment23(int m, double x) {
     /* radialMomentTwoThirds :667-728 */
     if (x <= 0.0) return 0.0;
-    if (m == 2) return (x < 1.0e-6) ? x * x * x * (1.0 / 3.0 - x * x / 5.0) : x - atan(x);
-    return (x < 1.0e-6) ? x * x * x * x * (1.0 / 4.0 - x * x / 6.0) : 0.5 * (x * x - log(1.0 + x * x));
+    if (m == 2) return (x < 1.0e-6) ? x * x * x * (1.0 / 3.0 - x * x / 5.0) : x - dm_atan(x);
+    return (x < 1.0e-6) ? x * x * x * x * (1.0 / 4.0 - x * x / 6.0) : 0.5 * (x * x - dm_log(1.0 + x * x));
 }
 
 /* ------------------------------------------------------------ cooling function (CIE tables) */
@@ -203,7 +205,7 @@ static void cie_interp_factors(const double *lnZ, const double *lnT, int nZ, int
     /* cieFileInterpolatingFactors, cooling/cooling_function/CIE_file.F90:665-715 */
     double tu = temperature, zu;
     int i;
-    if (is_log) tu = log(tu);
+    if (is_log) tu = dm_log(tu);
     i = locate(lnT, nT, tu);
     if (i > nT - 1) i = nT - 1;
     if (i < 1) i = 1;
@@ -214,7 +216,7 @@ static void cie_interp_factors(const double *lnZ, const double *lnT, int nZ, int
         f->iZ = 1;
         f->hZ = zu / first_nonzero;
     } else {
-        if (is_log) zu = log(zu);
+        if (is_log) zu = dm_log(zu);
         i = locate(lnZ, nZ, zu);
         if (i > nZ - 1) i = nZ - 1;
         if (i < 1) i = 1;
@@ -228,7 +230,7 @@ static double cie_interpolate(const double *v, int nT, int is_log, const cie_fac
     const double *b = a + nT;
     double r = a[0] * (1.0 - f->hT) * (1.0 - f->hZ) + b[0] * (1.0 - f->hT) * f->hZ +
                a[1] * f->hT * (1.0 - f->hZ) + b[1] * f->hT * f->hZ;
-    return is_log ? exp(r) : r;
+    return is_log ? dm_exp(r) : r;
 }
 
 /* Lambda(T,Z)/n_H^2: cieFileCoolingFunction :238-317 with all extrapolation types "fix" */
@@ -368,8 +370,11 @@ static double cooling_specific_angular_momentum(std_work *w, double radius) {
     hh_profile(w);
     x = w->hh_router / w->hh_rcore;
     /* densityRadialMoment(m) = I_m(x) rho0 rc^(1+m): ratio m=2 / m=3 */
-    norm = (hh_radial_moment23(2, x) * w->hh_rho0 * pow(w->hh_rcore, 3.0)) /
-           (hh_radial_moment23(3, x) * w->hh_rho0 * pow(w->hh_rcore, 4.0));
+    {
+        const double rc = w->hh_rcore;
+        norm = (hh_radial_moment23(2, x) * w->hh_rho0 * (rc * rc * rc)) /
+               (hh_radial_moment23(3, x) * w->hh_rho0 * (rc * rc * rc * rc));
+    }
     return norm * jmean * radius;
 }
 
@@ -389,10 +394,10 @@ static double disk_bessel_factor(const std_work *w, double half_radius) {
     double lx, lx0, lx1, inv, x, h;
     int i;
     if (half_radius <= 0.0) return 0.0;
-    if (half_radius < 1.0e-3) return (ln2 - euler - 0.5 - log(half_radius)) * half_radius * half_radius;
-    lx = log(half_radius);
-    lx0 = log(t->x0[0]);
-    lx1 = log(t->x0[t->n0 - 1]);
+    if (half_radius < 1.0e-3) return (ln2 - euler - 0.5 - dm_log(half_radius)) * half_radius * half_radius;
+    lx = dm_log(half_radius);
+    lx0 = dm_log(t->x0[0]);
+    lx1 = dm_log(t->x0[t->n0 - 1]);
     inv = (double)(t->n0 - 1) / (lx1 - lx0);
     x = (lx - lx0) * inv;
     i = (int)x;
@@ -428,18 +433,19 @@ static double baryonic_vc2(std_work *w, double radius) {
 
 static double nfw_mass_scale_free(double x) {
     /* massEnclosedScaleFree, mass_distributions/spherical/NFW.F90:550-571 (without the 4 pi) */
-    if (x == 1.0) return log(2.0) - 0.5;
-    if (x >= 1.0e-6) return log(1.0 + x) - x / (1.0 + x);
+    if (x == 1.0) return dm_log(2.0) - 0.5;
+    if (x >= 1.0e-6) return dm_log(1.0 + x) - x / (1.0 + x);
     return x * x * (0.5 + x * (-2.0 / 3.0 + x * (0.75 + x * (-0.8))));
 }
 static double nfw_mass_enclosed(std_work *w, double radius) {
     /* nfwMassEnclosedBySphere :444-464 with normalisation :254-255 */
+    /* M(<r) = [M_vir / m(c)] m(r/r_s): the 4 pi rho_0 r_s^3 of :254-255,458-460 folded into one factor */
     double rs = w->p[GLC_P_DMSCALE]; /* current scale radius */
-    double conc, rho0;
+    double conc, norm;
     halo_scales(w);
     conc = w->rvir / rs;
-    rho0 = w->p[GLC_P_BASIC_MASS] / 4.0 / ORC_PI / (rs * rs * rs) / (log(1.0 + conc) - conc / (1.0 + conc));
-    return 4.0 * ORC_PI * nfw_mass_scale_free(radius / rs) * rho0 * (rs * rs * rs);
+    norm = w->p[GLC_P_BASIC_MASS] / (dm_log(1.0 + conc) - conc / (1.0 + conc));
+    return norm * nfw_mass_scale_free(radius / rs);
 }
 
 static double ac_orbital_mean(std_work *w, double radius) {
@@ -508,8 +514,8 @@ static double dark_matter_mass_enclosed(std_work *w, double radius) {
 
 static double nfw_j_root(double lnr, void *vw) {
     std_work *w = (std_work *)vw;
-    double r = exp(lnr);
-    return 0.5 * log(ORC_G_INTERNAL * nfw_mass_enclosed(w, r) * r) - w->ac_bterm; /* ac_bterm = ln j here */
+    double r = dm_exp(lnr);
+    return 0.5 * dm_log(ORC_G_INTERNAL * nfw_mass_enclosed(w, r) * r) - w->ac_bterm; /* ac_bterm = ln j here */
 }
 static double nfw_radius_from_j(std_work *w, double j) {
     /* stands in for nfwRadiusFromSpecificAngularMomentum (NFW.F90:589-625): solve j = sqrt(G M(<r) r) */
@@ -517,17 +523,17 @@ static double nfw_radius_from_j(std_work *w, double j) {
     int st;
     double lnr, save = w->ac_bterm;
     if (!(j > 0.0)) return 0.0;
-    w->ac_bterm = log(j);
+    w->ac_bterm = dm_log(j);
     orc_root_init(&rf, nfw_j_root, w, 1.0e-12, 0.0);
     rf.expand_type = ORC_EXPAND_ADDITIVE;
     rf.expand_upward = 2.0;
     rf.expand_downward = -2.0;
     rf.sign_expect_upward = ORC_SIGN_POSITIVE;
     rf.sign_expect_downward = ORC_SIGN_NEGATIVE;
-    lnr = orc_root_find(&rf, log(w->rvir) - 4.0, log(w->rvir), 0, 0, 0, &st);
+    lnr = orc_root_find(&rf, dm_log(w->rvir) - 4.0, dm_log(w->rvir), 0, 0, 0, &st);
     w->ac_bterm = save;
     if (st != 0) return w->rvir;
-    return exp(lnr);
+    return dm_exp(lnr);
 }
 
 static void plausibility(std_work *w) {
@@ -627,7 +633,7 @@ static void structure_solve(std_work *w) {
                 }
                 history[comp][1] = history[comp][0];
                 history[comp][0] = radius;
-                if (radius > 0.0 && radius_new > 0.0) fit += fabs(log(radius_new / radius));
+                if (radius > 0.0 && radius_new > 0.0) fit += fabs(dm_log(radius_new / radius));
                 radius = radius_new;
                 if (!(radius > 0.0)) w->c->nonfinite = 1;
             }
@@ -649,9 +655,9 @@ static double kmt_fh2_fast(double s, void *u) {
     return (s < 2.0) ? 1.0 - 0.75 * s / (1.0 + 0.25 * s) : 0.0;
 }
 static double disk_sigma_gas(const std_work *w, double radius) {
-    /* exponentialDiskSurfaceDensity :484-499 scaled: M/(2 pi Rd^2) exp(-R/Rd) */
+    /* exponentialDiskSurfaceDensity :484-499 scaled: M/(2 pi Rd^2) dm_exp(-R/Rd) */
     double rd = w->k_rdisk;
-    return fmax(0.0, w->k_mgas) / (2.0 * ORC_PI * rd * rd) * exp(-radius / rd);
+    return fmax(0.0, w->k_mgas) / (2.0 * ORC_PI * rd * rd) * dm_exp(-radius / rd);
 }
 static void kmt_factors(std_work *w) {
     /* krumholz2009ComputeFactors :312-358 */
@@ -664,9 +670,9 @@ static void kmt_factors(std_work *w) {
     w->k_sigma_norm = 0.0;
     w->k_sigma_trunc = 0.0;
     if (w->k_zsolar > 0.0) {
-        w->k_chi = 0.77 * (1.0 + 3.1 * pow(w->k_zsolar, 0.365));
+        w->k_chi = 0.77 * (1.0 + 3.1 * dm_pow(w->k_zsolar, 0.365));
         w->k_sigma_norm = w->k_xh * w->P->clumpingFactorMolecularComplex / (ORC_MEGA * ORC_MEGA);
-        w->k_s_norm = log(1.0 + 0.6 * w->k_chi + 0.01 * w->k_chi * w->k_chi) / (0.04 * w->k_zsolar);
+        w->k_s_norm = dm_log(1.0 + 0.6 * w->k_chi + 0.01 * w->k_chi * w->k_chi) / (0.04 * w->k_zsolar);
         if (w->k_sigma_norm > 0.0)
             w->k_sigma_trunc = w->k_s_norm / w->k_sigma_norm / w->P->krumholzSTruncation;
         else
@@ -773,7 +779,7 @@ static double sfr_spheroid(const std_work *w) {
        starFormationTimescaleDynamicalTime (timescales/dynamical_time.F90:121-189) */
     double v = w->p[GLC_P_SPH_VELOCITY], r = w->p[GLC_P_SPH_RADIUS], tau;
     if (v <= 0.0 || w->P->sfSpheroidEfficiency == 0.0) return 0.0;
-    tau = fmax(ORC_MPC_PER_KMS_TO_GYR * r / v * pow(v / 200.0, w->P->sfSpheroidExponentVelocity) /
+    tau = fmax(ORC_MPC_PER_KMS_TO_GYR * r / v * dm_pow(v / 200.0, w->P->sfSpheroidExponentVelocity) /
                    w->P->sfSpheroidEfficiency,
                w->P->sfSpheroidTimescaleMinimum);
     return (tau > 0.0) ? w->p[GLC_P_SPH_MASS_GAS] / tau : 0.0;
@@ -841,7 +847,7 @@ static void feedback(rate_ctx *rc, int is_disk, double psi) {
     double energy = ORC_FEEDBACK_ENERGY_INPUT_AT_INFINITY_CANONICAL * psi;
     double outflow, tdyn, outflow_max, mass_comp, j_out, z_out;
     outflow = (velocity <= 0.0) ? 0.0
-                                : pow(vchar / velocity, expo) * energy / ORC_FEEDBACK_ENERGY_INPUT_AT_INFINITY_CANONICAL;
+                                : dm_pow(vchar / velocity, expo) * energy / ORC_FEEDBACK_ENERGY_INPUT_AT_INFINITY_CANONICAL;
     tdyn = (velocity <= 0.0 || radius <= 0.0) ? 1.0 : ORC_MPC_PER_KMS_TO_GYR * radius / velocity;
     outflow_max = fmax(mass_gas / tdyn / P->fbTimescaleOutflowFractionalMinimum, 0.0);
     if (outflow > outflow_max) outflow = outflow * outflow_max / outflow;
@@ -1254,4 +1260,37 @@ void orc_std_post_evolve(orc_evolve_ctx *c) {
     std_work w;
     work_init(&w, c, c->p[GLC_P_TIME]);
     structure_solve(&w);
+}
+
+/* debugging aid for the bit-exact parity work: selected intermediates of one RHS evaluation */
+void orc_probe_node(const glc_params *P, const orc_tables *T, double *props, int flags, double *out) {
+    orc_evolve_ctx c;
+    std_work w;
+    double r0;
+    memset(&c, 0, sizeof(c));
+    c.P = P;
+    c.T = T;
+    c.p = props;
+    c.flags = flags;
+    orc_std_solve_analytics(&c, props[GLC_P_TIME]);
+    work_init(&w, &c, props[GLC_P_TIME]);
+    halo_scales(&w);
+    hh_profile(&w);
+    r0 = props[GLC_P_DISK_RADIUS] > 0.0 ? props[GLC_P_DISK_RADIUS] : 0.01 * w.rvir;
+    out[0] = w.rvir;
+    out[1] = w.vvir;
+    out[2] = w.tvir;
+    out[3] = w.hh_rho0;
+    out[4] = nfw_mass_enclosed(&w, r0);
+    out[5] = ac_orbital_mean(&w, r0);
+    out[6] = baryonic_vc2(&w, r0);
+    out[7] = dark_matter_mass_enclosed(&w, r0);
+    out[8] = disk_bessel_factor(&w, 0.37);
+    out[9] = hh_mass_enclosed(&w, r0);
+    out[10] = orc_fast_exponentiate(1.0e-3, 1.0, 0.7, 1.0e4, 0.0123);
+    out[11] = nfw_radius_from_j(&w, 0.3 * w.rvir * w.vvir);
+    out[12] = has(&w, GLC_F_HAS_DISK) ? sfr_disk(&w) : 0.0;
+    out[13] = has(&w, GLC_F_HAS_HOTHALO) && props[GLC_P_HH_MASS] > 0 ? cooling_radius(&w) : 0.0;
+    out[14] = sqrt(ORC_G_INTERNAL * out[7] / r0 + out[6]);
+    out[15] = dm_log(out[14] / r0);
 }

@@ -4,6 +4,8 @@
  * table storage and the host-side interrupt procedures (component creation).
  */
 #include <math.h>
+
+#include "../galacticus_b200/csrc/glc_detmath.h"
 #include <stdlib.h>
 #include <string.h>
 
@@ -214,9 +216,9 @@ static void cie_prepare(const orc_table2d *t, int *is_log, int *first_zero, doub
         *first_zero = (t->x0[0] == 0.0);
         if (*first_zero) *first_nonzero = t->x0[1];
         for (i = 0; i < t->n0; i++)
-            (*lnZ)[i] = (t->x0[i] > 0.0) ? log(t->x0[i]) : metallicity_logarithmic_zero;
-        for (i = 0; i < t->n1; i++) (*lnT)[i] = log(t->x1[i]);
-        for (i = 0; i < n; i++) (*lnV)[i] = log(t->v[i]);
+            (*lnZ)[i] = (t->x0[i] > 0.0) ? dm_log(t->x0[i]) : metallicity_logarithmic_zero;
+        for (i = 0; i < t->n1; i++) (*lnT)[i] = dm_log(t->x1[i]);
+        for (i = 0; i < n; i++) (*lnV)[i] = dm_log(t->v[i]);
     }
 }
 

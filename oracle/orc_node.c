@@ -6,6 +6,8 @@
 #include "orc_node.h"
 
 #include <math.h>
+
+#include "../galacticus_b200/csrc/glc_detmath.h"
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -114,7 +116,7 @@ int orc_evolve_node_segment(const glc_params *P, const orc_tables *T, double *pr
         while (trial_count < TRIAL_COUNT_MAXIMUM &&
                !(ode_status == ORC_GSL_SUCCESS || ode_status == ORC_GSL_EBADFUNC)) {
             if (P->reuseODEStepSize)
-                step_size = props[GLC_P_TIME_STEP] / pow(2.0, (double)trial_count);
+                step_size = props[GLC_P_TIME_STEP] / dm_scale2(1.0, trial_count);
             else
                 step_size = -1.0;
             time_start = time_start_saved;
@@ -127,7 +129,7 @@ int orc_evolve_node_segment(const glc_params *P, const orc_tables *T, double *pr
                 if (any) {
                     for (i = 0; i < c.n_active; i++)
                         if (y[i] < 0.0 && nonneg[i]) y[i] = 0.0;
-                    step_size = props[GLC_P_TIME_STEP] / pow(2.0, (double)trial_count);
+                    step_size = props[GLC_P_TIME_STEP] / dm_scale2(1.0, trial_count);
                     ode_status = ORC_GSL_SUCCESS;
                 }
             }

@@ -5,6 +5,8 @@
 
 #include <float.h>
 #include <math.h>
+
+#include "../galacticus_b200/csrc/glc_detmath.h"
 #include <string.h>
 
 /* ------------------------------------------------------------------ Brent (GSL 2.6 roots/brent.c) */
@@ -262,7 +264,7 @@ static const double wgk[8] = {0.022935322010529224963732008058970, 0.06309209262
 static double rescale_error(double err, const double result_abs, const double result_asc) {
     err = fabs(err);
     if (result_asc != 0 && err != 0) {
-        double scale = pow((200 * err / result_asc), 1.5);
+        double scale = dm_pow((200 * err / result_asc), 1.5);
         if (scale < 1)
             err = result_asc * scale;
         else
@@ -460,12 +462,12 @@ double orc_linear_table_eval(orc_fn1 g, void *ctx, double xmin, double xmax, int
     return g(xi, ctx) * (1.0 - h) + g(xi1, ctx) * h;
 }
 
-static double powfn(double x, void *ctx) { return pow(x, *(double *)ctx); }
+static double powfn(double x, void *ctx) { return dm_pow(x, *(double *)ctx); }
 
 double orc_fast_exponentiate(double range_min, double range_max, double exponent, double density, double x) {
     /* math/exponentiation.F90:57-104 */
     int point_count;
-    if (x < range_min || x > range_max) return pow(x, exponent);
+    if (x < range_min || x > range_max) return dm_pow(x, exponent);
     point_count = (int)((range_max - range_min) * density) + 1;
     return orc_linear_table_eval(powfn, &exponent, range_min, range_max, point_count, x, 0);
 }

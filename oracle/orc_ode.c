@@ -7,7 +7,15 @@
 
 #include <float.h>
 #include <math.h>
+
+#include "../galacticus_b200/csrc/glc_detmath.h"
 #include <string.h>
+#ifdef ORC_TRACE
+#include <stdio.h>
+#define TR(...) fprintf(stderr, __VA_ARGS__)
+#else
+#define TR(...)
+#endif
 
 /* ---- Cash-Karp tableau: libgsl 2.6 ode-initval2/rkck.c (published coefficients,
  *      Cash & Karp 1990, ACM TOMS 16, 201) -------------------------------------- */
@@ -71,7 +79,7 @@ int orc_sc2_hadjust(const orc_ode_solver *s, unsigned int ord, const double *y,
         if (s->is_non_negative[i] && y[i] < 0.0) forbidden_negatives = 1;
     }
     if (rmax > 1.1) {
-        double r = S / pow(rmax, 1.0 / ord);
+        double r = S / dm_pow(rmax, 1.0 / ord);
         if (r < 0.2) r = 0.2;
         *h = r * h_old;
         return ORC_HADJ_DEC;
@@ -79,7 +87,7 @@ int orc_sc2_hadjust(const orc_ode_solver *s, unsigned int ord, const double *y,
         *h = 0.5 * h_old;
         return ORC_HADJ_DEC;
     } else if (rmax < 0.5) {
-        double r = S / pow(rmax, 1.0 / (ord + 1.0));
+        double r = S / dm_pow(rmax, 1.0 / (ord + 1.0));
         if (r > 4.9) r = 4.9;
         if (r < 1.0) r = 1.0;
         *h = r * h_old;
@@ -169,6 +177,7 @@ int orc_evolve_apply(orc_ode_solver *s, double *t, double t1, double *h, double 
             final_step = 0;
         }
         step_status = orc_rkck_apply(s, t0, h0, y, s->yerr, s->dydt_in, s->dydt_out);
+        TR("attempt t0=%.17g h0=%.17g t1=%.17g final=%d count=%lu status=%d\n", t0, h0, t1, final_step, s->count, step_status);
         if (step_status == ORC_GSL_EFAULT || step_status == ORC_GSL_EBADFUNC) return step_status;
         if (step_status != ORC_GSL_SUCCESS) {
             const double h_old = h0;
@@ -196,6 +205,7 @@ int orc_evolve_apply(orc_ode_solver *s, double *t, double t1, double *h, double 
         {
             const double h_old = h0;
             const int hadjust_status = orc_sc2_hadjust(s, RKCK_ORDER, y, s->yerr, s->dydt_out, &h0);
+            TR("  hadjust=%d h_old=%.17g h_new=%.17g\n", hadjust_status, h_old, h0);
             if (hadjust_status == ORC_HADJ_DEC) {
                 volatile double t_curr = *t;
                 volatile double t_next = (*t) + h0;

@@ -24,15 +24,17 @@ def make(orc, **kw):
 
 
 def compare(pg, po, fg, fo, sg, so, ig, io, what):
+    """north_star asks for 1e-6 relative; both sides are built from the same IEEE-only elementary
+    functions with contraction off, so we can (and do) demand bit-for-bit identity, which is the only
+    robust criterion given the chaotic accept/reject decisions of the nested loose-tolerance solvers."""
     np.testing.assert_array_equal(sg, so, err_msg=f"{what}: status")
     np.testing.assert_array_equal(ig, io, err_msg=f"{what}: interrupt")
     np.testing.assert_array_equal(fg, fo, err_msg=f"{what}: flags")
     np.testing.assert_array_equal(pg[:, P["TIME"]], po[:, P["TIME"]], err_msg=f"{what}: time")
     scale = cases.y_scale(po)[:, None]
-    # masses/abundances: relative 1e-6 with the ODE absolute scale (1e-6 of the node's baryons) as floor
-    cases.assert_close(pg[:, :abi.NY], po[:, :abi.NY], RTOL, scale=scale * 1e3, what=f"{what}: y")
-    for k in ("DISK_RADIUS", "DISK_VELOCITY", "SPH_RADIUS", "SPH_VELOCITY", "BASIC_MASS", "DMSCALE", "SPIN"):
-        cases.assert_close(pg[:, P[k]], po[:, P[k]], RTOL, what=f"{what}: {k}")
+    cases.assert_close(pg[:, :abi.NY], po[:, :abi.NY], RTOL, scale=scale * 1e3, what=f"{what}: y (1e-6)")
+    bad = np.argwhere(pg != po)
+    assert bad.size == 0, f"{what}: {len(bad)} entries not bit-identical, first {bad[:5].tolist()}"
 
 
 def test_rhs_parity(oracle_lib):
@@ -48,11 +50,12 @@ def test_rhs_parity(oracle_lib):
     np.testing.assert_array_equal(ig, io)
     scale = np.abs(do).max(axis=1, keepdims=True)
     cases.assert_close(dg, do, RTOL, scale=scale * 1e-3, what="dydt")
+    assert np.array_equal(dg, do), f"dydt not bit-identical in {(dg != do).sum()} entries"
     for k in ("DISK_RADIUS", "DISK_VELOCITY", "SPH_RADIUS", "SPH_VELOCITY"):
-        cases.assert_close(pg[:, P[k]], po[:, P[k]], RTOL, what=k)
+        assert np.array_equal(pg[:, P[k]], po[:, P[k]]), k
 
 
-@pytest.mark.parametrize("n", [1, 37, 3000])
+@pytest.mark.parametrize("n", [1, 37, 3000, 20000])
 def test_evolve_parity(oracle_lib, n):
     ev, o, p = make(oracle_lib)
     props, flags, t_end = synthetic.standard_nodes(p, n, seed=100 + n)
@@ -103,8 +106,8 @@ def test_interrupts_returned_to_host(oracle_lib):
         n_round += 1
     assert saw_interrupt
     np.testing.assert_array_equal(fh, f_ref)
-    cases.assert_close(ph[:, :abi.NY], p_ref[:, :abi.NY], 1e-12, scale=1.0, what="host-loop vs on-device")
-    cases.assert_close(ph[:, :abi.NY], po[:, :abi.NY], RTOL, scale=cases.y_scale(po)[:, None] * 1e3, what="vs oracle")
+    assert np.array_equal(ph[:, :abi.NY], p_ref[:, :abi.NY]), "host-loop vs on-device interrupt resolution"
+    assert np.array_equal(ph[:, :abi.NY], po[:, :abi.NY]), "vs oracle"
 
 
 def test_baryon_budget_full_size():
