@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- node-ODE hot path throughput on N B200s (one process per GPU).
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line.
+  value      : node-ODE steps/s (accepted RKCK steps, successful iterations of driver2.c:190) summed over all
+               ranks, inputs already resident in HBM (device-resident arena), CUDA-event timed, max over ranks.
+  e2e        : same metric through the reference-facing C-ABI call glc_evolve_batch with HOST buffers
+               (H2D + layout transpose + kernel + D2H inside the timed region).
+  roofline   : dominant kernel (evolve_kernel) against the HBM roofline (algorithmic bytes = the node records read
+               and written once per launch) plus, as north_star asks, the FP64 view: FP64 flop/s from the kernel's
+               own counters against a DFMA-chain peak measured in this process.
+  cpu_baseline: the CPU oracle (oracle/, OpenMP over nodes like the reference's OpenMP over trees) on a bounded
+               sample of the same workload, on this box's host cores.
+``--impl reference`` times the oracle alone (the reference Fortran cannot be built here: no gfortran/GSL/HDF5).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "node_ode_steps_per_s"
+UNIT = "accepted RKCK node-ODE steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=1_000_000, help="node records per GPU (weak scaling)")
+    ap.add_argument("--cpu-sample", type=int, default=40_000, help="node records of the CPU baseline sample")
+    ap.add_argument("--seed", type=int, default=219)
+    return ap.parse_args()
+
+
+def workload(n, seed):
+    from galacticus_b200 import abi, synthetic
+    from galacticus_b200.evolver import params_default
+
+    p = params_default(abi.GLC_MODEL_STANDARD)
+    # black-hole operators are not restated yet: run the same reduced operator set on both sides
+    p.operatorMask = abi.GLC_OP_ALL & ~(abi.GLC_OP_BLACK_HOLES_SEED | abi.GLC_OP_BLACK_HOLES_ACCRETION
+                                        | abi.GLC_OP_BLACK_HOLES_WINDS)
+    synthetic.finalize_params(p)
+    props, flags, t_end = synthetic.standard_nodes(p, n, seed=seed)
+    return p, props, flags, t_end
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle-reason sampling during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the path (the oracle port; the Fortran reference cannot be
+    compiled in this image) on the host cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from galacticus_b200 import synthetic
+    from oracle import orc
+
+    orc.build()
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample
+    p, props, flags, t_end = workload(n, args.seed)
+    o = orc.Oracle(fast=True)
+    synthetic.install(o, p)
+    times, steps = [], 0
+    for it in range(args.warmup + args.steps):
+        pp, ff = props.copy(), flags.copy()
+        t0 = time.perf_counter()
+        _, _, c = o.evolve_batch(pp, ff, t_end, n_threads=cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            steps = c["steps_accepted"]
+    tot = sum(times)
+    value = steps * len(times) / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"node-batch sample of {n} records, quickTest operator set (no BH ops), seed {args.seed}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} node records of the same generator/seed; nodes/s = {n * len(times) / tot:.1f}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from galacticus_b200 import abi, synthetic
+    from galacticus_b200.evolver import Evolver
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.nodes
+    # independent forests shard naturally: every rank owns its own forest queue (different seed), no data-path collective
+    p, props, flags, t_end = workload(n, args.seed + 1000 * rank)
+    ev = Evolver(local_rank)
+    synthetic.install(ev, p)
+    fp64_peak = ev.fp64_peak_tflops()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ("value")
+    ev.arena_upload(props, flags, t_end)
+    ev.arena_snapshot(n)
+    launches0 = ev.kernel_launch_count()
+    for _ in range(args.warmup):
+        ev.arena_restore(n)
+        ev.evolve_arena(n)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches1 = ev.kernel_launch_count()
+    t0 = time.perf_counter()
+    kernel_ms, counters = [], None
+    for _ in range(args.steps):
+        ev.arena_restore(n)
+        counters, ms = ev.evolve_arena(n)  # synchronises the evolver's stream; ms = CUDA events around the kernel
+        kernel_ms.append(ms)
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ev.kernel_launch_count() - launches1
+    clocks = sampler.stop()
+    dev_time = sum(kernel_ms) * 1e-3  # device time of the timed kernels on the launching stream
+
+    # ---------------- end-to-end arm through the C-ABI with host buffers
+    pin = torch.empty((n, abi.NPROP), dtype=torch.float64).pin_memory()
+    host_props = pin.numpy()
+    e2e_times = []
+    for it in range(1 + min(args.steps, 3)):
+        host_props[:] = props
+        ff = flags.copy()
+        barrier()
+        t1 = time.perf_counter()
+        s, i, c2 = ev.evolve_batch(host_props, ff, t_end)
+        torch.cuda.synchronize()
+        if it > 0:
+            e2e_times.append(time.perf_counter() - t1)
+    e2e_time = float(np.mean(e2e_times))
+    h2d = n * (abi.NPROP * 8 + 4 + 8)
+    d2h = n * (abi.NPROP * 8 + 4 + 4 + 4)
+
+    # ---------------- reduce over ranks: max time, summed work, NCCL all-reduce of an output statistic
+    steps_acc = counters["steps_accepted"]
+    stats = torch.tensor([dev_time, wall, e2e_time, float(steps_acc), float(counters["rhs_evaluations"]),
+                          float(counters["steps_rejected"]), float(n)], dtype=torch.float64, device="cuda")
+    tmax, tsum = stats.clone(), stats.clone()
+    # stellar mass function histogram of the evolved batch (mirrors output/analyses/volume_function_1d.F90:986-987)
+    final_props, _, st, _ = ev.arena_download(n)
+    mstar = final_props[:, abi.P["DISK_MASS_STELLAR"]] + final_props[:, abi.P["SPH_MASS_STELLAR"]]
+    hist = np.histogram(np.log10(np.maximum(mstar, 1.0)), bins=30, range=(5.0, 12.5))[0].astype(np.float64)
+    hist_t = torch.from_numpy(hist).cuda()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(hist_t, op=dist.ReduceOp.SUM)
+    tmax, tsum = tmax.cpu().numpy(), tsum.cpu().numpy()
+    ok_frac = float((st == 0).mean())
+
+    if rank == 0:
+        dev_time_max, e2e_max = float(tmax[0]), float(tmax[2])
+        total_steps = float(tsum[3]) * args.steps
+        value = total_steps / dev_time_max
+        ms_per_step = 1e3 * dev_time_max / args.steps
+        e2e_value = float(tsum[3]) / e2e_max
+        # roofline of the dominant kernel (rank 0's launches)
+        alg_bytes = n * (2 * abi.NPROP * 8 + 8 + 3 * 4)  # read + write one record per node (+ time_end, flags/status/interrupt)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach_gbs = alg_bytes / (np.mean(kernel_ms) * 1e-3) / 1e9
+        # FP64 view: flop per RHS evaluation and per step measured with ncu (profiles/)
+        flop_per_rhs = float(os.environ.get("GLC_FLOP_PER_RHS", "0") or 0)
+        rhs_total = float(counters["rhs_evaluations"])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": ("node-batch stand-in for testSuite benchmark-milkyWay: %d node records per GPU over the "
+                             "quickTest mass range (1e10-1e13 Msun), quickTest operator set without the black-hole "
+                             "operators, hotHaloRamPressureStripping=virialRadius, synthetic CIE tables" % n),
+                "nodes_per_gpu": n, "seed": args.seed, "l2": "inputs (%.0f MB/GPU) larger than L2" % (n * abi.NPROP * 8 / 1e6),
+                "nodes_per_s": float(tsum[6]) * args.steps / dev_time_max,
+                "rhs_evaluations_per_s": float(tsum[4]) * args.steps / dev_time_max,
+                "rejected_step_fraction": float(tsum[5]) / max(float(tsum[3]) + float(tsum[5]), 1.0),
+                "status_ok_fraction": ok_frac,
+                "wall_s_timed_region": float(tmax[1]),
+                "stellar_mass_function_counts": hist_t.cpu().numpy().tolist(),
+            },
+            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "note": "latency/FP64-issue bound kernel: see roofline_fp64 and profiles/"},
+            "roofline_fp64": {"peak_tflops_measured": fp64_peak,
+                              "flop_per_rhs": flop_per_rhs or None,
+                              "achieved_tflops": (rhs_total * flop_per_rhs / (np.mean(kernel_ms) * 1e-3) / 1e12) if flop_per_rhs else None,
+                              "frac": (rhs_total * flop_per_rhs / (np.mean(kernel_ms) * 1e-3) / 1e12 / fp64_peak) if (flop_per_rhs and fp64_peak) else None},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        # CPU baseline (rank 0, N=1 only): the oracle on a bounded sample
+        if world == 1:
+            try:
+                from oracle import orc
+
+                orc.build()
+                cores = os.cpu_count() or 1
+                ns = min(args.cpu_sample, n)
+                o = orc.Oracle(fast=True)
+                synthetic.install(o, p)
+                pp, ff = props[:ns].copy(), flags[:ns].copy()
+                tc = time.perf_counter()
+                _, _, cc = o.evolve_batch(pp, ff, t_end[:ns], n_threads=cores)
+                dtc = time.perf_counter() - tc
+                line["cpu_baseline"] = {"value": cc["steps_accepted"] / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": "first %d node records of the GPU workload, %.1f s, %.0f nodes/s" % (ns, dtc, ns / dtc)}
+            except Exception as e:  # the checker is optional for the bench line
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

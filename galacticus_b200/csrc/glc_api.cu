@@ -42,6 +42,10 @@ struct glc_evolver {
     double *d_time_end = nullptr;
     double *d_stage = nullptr;  // node-major staging [cap][NPROP] for transposes
     double *d_dydt = nullptr;   // [cap][NY] for glc_rhs_batch
+    double *d_snap_props = nullptr;  // snapshot of the arena (glc_arena_snapshot)
+    int32_t *d_snap_flags = nullptr;
+    int64_t snap_cap = 0;
+    int64_t launches = 0;
     // workspace
     double *d_ws = nullptr;
     int64_t nslots = 0;
@@ -130,6 +134,23 @@ __global__ void rhs_kernel(KernelArgs A, double *dydt) {
     AR(GLC_P_SPH_RADIUS) = ctx.sphRadius;
     AR(GLC_P_SPH_VELOCITY) = ctx.sphVelocity;
     AR(GLC_P_BASIC_MASS) = ctx.basicMass;
+}
+
+// FP64 FMA-chain microbenchmark (8 independent chains per thread): the measured FP64 roofline denominator
+__global__ void fp64_peak_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1.0e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1.0e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c);
+        a1 = fma(a1, b, c);
+        a2 = fma(a2, b, c);
+        a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c);
+        a5 = fma(a5, b, c);
+        a6 = fma(a6, b, c);
+        a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 // debugging aid for the bit-exact parity work: selected intermediates of one RHS evaluation
@@ -238,6 +259,7 @@ static int launch_evolve(glc_evolver *ev, int n) {
     GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
     GLC_CHECK(ev, cudaEventRecord(ev->ev0, ev->stream));
     evolve_kernel<Model><<<grid, kBlock, 0, ev->stream>>>(A);
+    ev->launches++;
     GLC_CHECK(ev, cudaGetLastError());
     GLC_CHECK(ev, cudaEventRecord(ev->ev1, ev->stream));
     return 0;
@@ -302,6 +324,8 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaFree(ev->d_time_end);
     cudaFree(ev->d_stage);
     cudaFree(ev->d_dydt);
+    cudaFree(ev->d_snap_props);
+    cudaFree(ev->d_snap_flags);
     cudaFree(ev->d_ws);
     cudaFree(ev->d_work);
     cudaFree(ev->d_counters);
@@ -443,6 +467,7 @@ int glc_arena_upload(glc_evolver *ev, int64_t n, const double *props, const int3
     GLC_CHECK(ev, cudaMemcpyAsync(ev->d_flags, flags, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ev->stream));
     GLC_CHECK(ev, cudaMemcpyAsync(ev->d_time_end, time_end, sizeof(double) * n, cudaMemcpyHostToDevice, ev->stream));
     aos_to_soa_kernel<<<(int)((n + 63) / 64), 256, 0, ev->stream>>>(ev->d_stage, ev->d_props, (int)n, ev->cap);
+    ev->launches++;
     GLC_CHECK(ev, cudaGetLastError());
     return 0;
 }
@@ -454,6 +479,7 @@ int glc_arena_download(glc_evolver *ev, int64_t n, double *props, int32_t *flags
     cudaSetDevice(ev->device);
     if (props) {
         soa_to_aos_kernel<<<(int)((n + 63) / 64), 256, 0, ev->stream>>>(ev->d_props, ev->d_stage, (int)n, ev->cap);
+        ev->launches++;
         GLC_CHECK(ev, cudaGetLastError());
         GLC_CHECK(ev, cudaMemcpyAsync(props, ev->d_stage, sizeof(double) * NPROP * n, cudaMemcpyDeviceToHost, ev->stream));
     }
@@ -496,6 +522,62 @@ int glc_evolve_arena(glc_evolver *ev, int64_t n, glc_counters *counters) {
         counters->nodes = hc[5];
     }
     return 0;
+}
+
+int glc_arena_snapshot(glc_evolver *ev, int64_t n) {
+    if (!ev || n < 0 || n > ev->cap) return -1;
+    cudaSetDevice(ev->device);
+    if (ev->snap_cap != ev->cap) {
+        cudaFree(ev->d_snap_props);
+        cudaFree(ev->d_snap_flags);
+        ev->d_snap_props = nullptr;
+        ev->d_snap_flags = nullptr;
+        GLC_CHECK(ev, cudaMalloc(&ev->d_snap_props, sizeof(double) * NPROP * ev->cap));
+        GLC_CHECK(ev, cudaMalloc(&ev->d_snap_flags, sizeof(int32_t) * ev->cap));
+        ev->snap_cap = ev->cap;
+    }
+    GLC_CHECK(ev, cudaMemcpyAsync(ev->d_snap_props, ev->d_props, sizeof(double) * NPROP * ev->cap, cudaMemcpyDeviceToDevice, ev->stream));
+    GLC_CHECK(ev, cudaMemcpyAsync(ev->d_snap_flags, ev->d_flags, sizeof(int32_t) * ev->cap, cudaMemcpyDeviceToDevice, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    return 0;
+}
+
+int glc_arena_restore(glc_evolver *ev, int64_t n) {
+    if (!ev || n < 0 || n > ev->cap || ev->snap_cap != ev->cap) return -1;
+    cudaSetDevice(ev->device);
+    GLC_CHECK(ev, cudaMemcpyAsync(ev->d_props, ev->d_snap_props, sizeof(double) * NPROP * ev->cap, cudaMemcpyDeviceToDevice, ev->stream));
+    GLC_CHECK(ev, cudaMemcpyAsync(ev->d_flags, ev->d_snap_flags, sizeof(int32_t) * ev->cap, cudaMemcpyDeviceToDevice, ev->stream));
+    return 0;
+}
+
+int64_t glc_arena_capacity(const glc_evolver *ev) { return ev ? ev->cap : 0; }
+int64_t glc_kernel_launch_count(const glc_evolver *ev) { return ev ? ev->launches : 0; }
+
+double glc_measure_fp64_peak_tflops(glc_evolver *ev) {
+    if (!ev) return 0.0;
+    cudaSetDevice(ev->device);
+    double *d_out = nullptr;
+    const int grid = ev->num_sms * 8, block = 256, iters = 4096;
+    if (cudaMalloc(&d_out, sizeof(double) * grid * block) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, ev->stream);
+        fp64_peak_kernel<<<grid, block, 0, ev->stream>>>(d_out, iters);
+        cudaEventRecord(e1, ev->stream);
+        cudaStreamSynchronize(ev->stream);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)iters * (double)grid * block;  // 8 independent FMA chains
+        if (ms > 0.f) best = std::max(best, flops / (ms * 1.0e-3) / 1.0e12);
+    }
+    ev->launches += 5;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return best;
 }
 
 float glc_last_kernel_ms(const glc_evolver *ev) { return ev ? ev->last_ms : 0.f; }

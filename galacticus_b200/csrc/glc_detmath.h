@@ -20,8 +20,12 @@
 
 #if defined(__CUDACC__)
 #define GLC_HD __host__ __device__ __forceinline__
+/* the big kernels call exp/log/pow/atan/cbrt as real functions: inlining their polynomial kernels at every
+   call site blew the evolve kernel up to 665 KB of SASS and made it instruction-fetch bound */
+#define GLC_HD_BIG __host__ __device__ __noinline__
 #else
 #define GLC_HD static inline
+#define GLC_HD_BIG static inline
 #endif
 
 typedef union {
@@ -54,7 +58,7 @@ GLC_HD double dm_scale2(double x, int k) {
     return x * dm_from_bits((unsigned long long)(k + 1023) << 52);
 }
 
-GLC_HD double dm_log(double x) {
+GLC_HD_BIG double dm_log(double x) {
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
     const double sqrt2 = 1.41421356237309514547;
     unsigned long long u;
@@ -101,7 +105,7 @@ GLC_HD double dm_log(double x) {
     }
 }
 
-GLC_HD double dm_exp(double x) {
+GLC_HD_BIG double dm_exp(double x) {
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
     const double inv_ln2 = 1.44269504088896338700e+00;
     double r, p, fk;
@@ -132,7 +136,7 @@ GLC_HD double dm_exp(double x) {
     return dm_scale2(p, k);
 }
 
-GLC_HD double dm_pow(double x, double y) {
+GLC_HD_BIG double dm_pow(double x, double y) {
     if (y == 0.0) return 1.0;
     if (x == 1.0) return 1.0;
     if (x != x || y != y) return x + y;
@@ -144,7 +148,7 @@ GLC_HD double dm_pow(double x, double y) {
     return dm_exp(y * dm_log(x));
 }
 
-GLC_HD double dm_atan(double x) {
+GLC_HD_BIG double dm_atan(double x) {
     const double atanhi0 = 4.63647609000806093515e-01, atanhi1 = 7.85398163397448278999e-01,
                  atanhi2 = 9.82793723247329054082e-01, atanhi3 = 1.57079632679489655800e+00;
     const double atanlo0 = 2.26987774529616870924e-17, atanlo1 = 3.06161699786838301793e-17,
@@ -196,7 +200,7 @@ GLC_HD double dm_atan(double x) {
     return neg ? -res : res;
 }
 
-GLC_HD double dm_cbrt(double x) {
+GLC_HD_BIG double dm_cbrt(double x) {
     double a, t;
     int neg;
     if (x != x || x == 0.0) return x;

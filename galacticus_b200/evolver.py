@@ -57,6 +57,14 @@ def load_library() -> C.CDLL:
     L.glc_evolver_stream.restype = vp
     L.glc_evolver_stream.argtypes = [vp]
     L.glc_rhs_batch.argtypes = [vp, C.c_int64, _dp, _ip, _dp, _ip]
+    L.glc_arena_snapshot.argtypes = [vp, C.c_int64]
+    L.glc_arena_restore.argtypes = [vp, C.c_int64]
+    L.glc_arena_capacity.restype = C.c_int64
+    L.glc_arena_capacity.argtypes = [vp]
+    L.glc_kernel_launch_count.restype = C.c_int64
+    L.glc_kernel_launch_count.argtypes = [vp]
+    L.glc_measure_fp64_peak_tflops.restype = C.c_double
+    L.glc_measure_fp64_peak_tflops.argtypes = [vp]
     L.glc_histogram_accumulate.argtypes = [vp, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int32, vp]
     if L.glc_abi_version() != abi.GLC_ABI_VERSION:
         raise GlcError("libglcb200.so ABI version does not match include/glc_b200.h")
@@ -150,6 +158,21 @@ class Evolver:
                                               status.ctypes.data_as(vp), interrupt.ctypes.data_as(vp)),
                     "glc_arena_download")
         return props, flags, status, interrupt
+
+    def arena_snapshot(self, n: int):
+        self._check(self.L.glc_arena_snapshot(self.h, n), "glc_arena_snapshot")
+
+    def arena_restore(self, n: int):
+        self._check(self.L.glc_arena_restore(self.h, n), "glc_arena_restore")
+
+    def kernel_launch_count(self) -> int:
+        return int(self.L.glc_kernel_launch_count(self.h))
+
+    def fp64_peak_tflops(self) -> float:
+        return float(self.L.glc_measure_fp64_peak_tflops(self.h))
+
+    def device_props_ptr(self) -> int:
+        return int(self.L.glc_arena_device_props(self.h) or 0)
 
     def rhs_batch(self, props, flags):
         n = props.shape[0]

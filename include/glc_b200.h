@@ -295,10 +295,20 @@ int glc_arena_upload(glc_evolver *ev, int64_t n, const double *props, const int3
 int glc_arena_download(glc_evolver *ev, int64_t n, double *props, int32_t *flags, int32_t *status,
                        int32_t *interrupt);
 int glc_evolve_arena(glc_evolver *ev, int64_t n, glc_counters *counters);
+/* keep / restore a device-side copy of the first n arena records (device-to-device), so that a resident
+ * batch can be evolved repeatedly from the same initial state */
+int glc_arena_snapshot(glc_evolver *ev, int64_t n);
+int glc_arena_restore(glc_evolver *ev, int64_t n);
 /* duration (ms, CUDA events on the evolver's stream) of the last glc_evolve_arena kernel */
 float glc_last_kernel_ms(const glc_evolver *ev);
 /* raw device pointers for zero-copy interop (e.g. torch.distributed/NCCL reductions) */
 void *glc_arena_device_props(glc_evolver *ev);
+int64_t glc_arena_capacity(const glc_evolver *ev);
+/* number of CUDA kernels of this library launched through this evolver since creation */
+int64_t glc_kernel_launch_count(const glc_evolver *ev);
+/* sustained FP64 FMA throughput of this device (TFLOP/s) from an in-library DFMA-chain microbenchmark;
+ * the denominator of the FP64 roofline fraction (MEASURED_PEAKS.json has no FP64 entry) */
+double glc_measure_fp64_peak_tflops(glc_evolver *ev);
 void *glc_evolver_stream(glc_evolver *ev);
 
 /* one evaluation of the RHS (standardODEs) for each node, for unit-level parity tests:
