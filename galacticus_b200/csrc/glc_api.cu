@@ -6,8 +6,10 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <time.h>
 
 #include "glc_common.cuh"
+#include "glc_tables_host.h"
 
 #include "glc_evolve_kernel.cuh"
 #include "glc_model_box.cuh"
@@ -17,7 +19,7 @@ using namespace glc;
 
 namespace {
 
-constexpr int kBlock = 128;
+constexpr int kBlock = GLC_BLOCK;
 
 struct HostTable {
     int n0 = 0, n1 = 0;
@@ -51,9 +53,26 @@ struct glc_evolver {
     int64_t nslots = 0;
     int *d_work = nullptr;
     unsigned long long *d_counters = nullptr;
+    double *d_pow_ac = nullptr, *d_pow_kmt = nullptr;  // fastExponentiator tables
+    double pow_ac_exponent = 0.0;
+    LaneState *d_lanes = nullptr;   // parked lane states, one per resident lane
+    int32_t *d_order = nullptr;     // queue order (component-sorted node ids)
+    int *d_sort = nullptr;          // 2 x 64 bucket counters
+    int64_t order_cap = 0;
+    int32_t slice_budget = 0;       // heavy calls per lane per launch; 0 = run to completion in one launch
+    int32_t sort_queue = 1;
+    int32_t slice_log = 0;
+    int32_t max_slices = 0;
+    int64_t slices = 0;
     float last_ms = 0.f;
     std::string err;
 };
+
+static double now_s() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 #define GLC_CHECK(ev, call)                                                                  \
     do {                                                                                     \
@@ -95,8 +114,10 @@ __global__ void soa_to_aos_kernel(const double *__restrict__ soa, double *__rest
 // one RHS evaluation per node (unit-level parity tests)
 template <class Model>
 __global__ void rhs_kernel(KernelArgs A, double *dydt) {
-    const int node = blockIdx.x * blockDim.x + threadIdx.x;
-    if (node >= A.n) return;
+    // the rate function is warp-synchronous: out-of-range lanes go through it with on = false
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = gid < A.n;
+    const int node = on ? gid : A.n - 1;
     auto AR = [&](int prop) -> double & { return A.props[(int64_t)prop * A.cap + node]; };
     NodeCtx ctx;
     double y[NY], rate[NY];
@@ -125,9 +146,9 @@ __global__ void rhs_kernel(KernelArgs A, double *dydt) {
     const double time = AR(GLC_P_TIME);
     ctx.timeNode = time;
     Model::solve_analytics(ctx, time);
-    const int code = Model::rates(ctx, time, y, rate);
-    const uint32_t mask = Model::active_mask(ctx.flags);
-    for (int i = 0; i < NY; i++) dydt[(int64_t)node * NY + i] = (mask & (1u << i)) ? rate[i] : rate[i];
+    const int code = Model::rates(ctx, time, y, rate, false, on);
+    if (!on) return;
+    for (int i = 0; i < NY; i++) dydt[(int64_t)node * NY + i] = rate[i];
     A.interrupt[node] = code;
     AR(GLC_P_DISK_RADIUS) = ctx.diskRadius;
     AR(GLC_P_DISK_VELOCITY) = ctx.diskVelocity;
@@ -153,64 +174,6 @@ __global__ void fp64_peak_kernel(double *out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
-// debugging aid for the bit-exact parity work: selected intermediates of one RHS evaluation
-__global__ void probe_kernel(KernelArgs A, double *out) {
-    const int node = blockIdx.x * blockDim.x + threadIdx.x;
-    if (node >= A.n) return;
-    auto AR = [&](int prop) -> double & { return A.props[(int64_t)prop * A.cap + node]; };
-    NodeCtx c;
-    double y[NY];
-    for (int i = 0; i < NY; i++) y[i] = AR(i);
-    c.flags = A.flags[node];
-    c.massTarget = AR(GLC_P_MASS_TARGET);
-    c.massRate = AR(GLC_P_MASS_RATE);
-    c.timeTarget = AR(GLC_P_TIME_TARGET);
-    c.scaleTarget = AR(GLC_P_DMSCALE_TARGET);
-    c.scaleRate = AR(GLC_P_DMSCALE_RATE);
-    c.spinTarget = AR(GLC_P_SPIN_TARGET);
-    c.spinRate = AR(GLC_P_SPIN_RATE);
-    c.timeLastIsolated = AR(GLC_P_TIME_LAST_ISOLATED);
-    c.diskRadius = AR(GLC_P_DISK_RADIUS);
-    c.diskVelocity = AR(GLC_P_DISK_VELOCITY);
-    c.sphRadius = AR(GLC_P_SPH_RADIUS);
-    c.sphVelocity = AR(GLC_P_SPH_VELOCITY);
-    c.basicMass = AR(GLC_P_BASIC_MASS);
-    c.massBaryonicSubhalos = AR(GLC_P_MASS_BARYONIC_SUBHALOS);
-    c.numericsFailed = 0;
-    const double time = AR(GLC_P_TIME);
-    c.timeNode = time;
-    typedef ModelStandard M;
-    M::solve_analytics(c, time);
-    Work w;
-    int bad = 0;
-    M::halo_scales(c, time, w);
-    M::hh_profile(c, y, w);
-    const double r0 = c.diskRadius > 0.0 ? c.diskRadius : 0.01 * w.rvir;
-    const double nn = M::nfw_norm(c, w);
-    double *o = out + (int64_t)node * 16;
-    o[0] = w.rvir;
-    o[1] = w.vvir;
-    o[2] = w.tvir;
-    o[3] = w.hhRho0;
-    o[4] = M::nfw_mass(nn, c.dmScale, r0);
-    o[5] = M::ac_orbital_mean(w, r0);
-    o[6] = M::baryonic_vc2(c, y, w, r0);
-    o[7] = M::dark_matter_mass_enclosed(c, y, w, nn, r0, bad);
-    o[8] = M::disk_bessel_factor(0.37);
-    o[9] = M::hh_mass_enclosed(w, r0);
-    o[10] = fast_exponentiate(1.0e-3, 1.0, 0.7, 1.0e4, 0.0123);
-    o[11] = M::nfw_radius_from_j(c, w, nn, 0.3 * w.rvir * w.vvir);
-    o[12] = (c.flags & GLC_F_HAS_DISK) ? M::sfr_disk(c, y, bad) : 0.0;
-    double ls;
-    if ((c.flags & GLC_F_HAS_HOTHALO) && y[GLC_P_HH_MASS] > 0) {
-        M::cooling_prepare(y, w, ls);
-        o[13] = M::cooling_radius(y, w, bad);
-    } else
-        o[13] = 0.0;
-    o[14] = sqrt(kGInternal * o[7] / r0 + o[6]);
-    o[15] = dm_log(o[14] / r0);
-}
-
 __global__ void histogram_kernel(const double *__restrict__ v, int n, double lo, double hi, int nb,
                                  double *hist) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -222,19 +185,70 @@ __global__ void histogram_kernel(const double *__restrict__ v, int n, double lo,
     if (b >= 0 && b < nb) atomicAdd(&hist[b], 1.0);
 }
 
+// ---------------------------------------------------------------------------- queue order
+// Nodes are handed to lanes in an order sorted by component set, so that the lanes of a warp -- which
+// fetch consecutive queue entries -- mostly run the same branches of the rate function.  Bucket order:
+// nodes that still lack a hot halo first (they go through component-creation segments and tend to be
+// the longest), then from the richest component set to the poorest.
+__global__ void queue_hist_kernel(const int32_t *__restrict__ flags, int n, int *hist) {
+    __shared__ int sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&sh[queue_bucket(flags[i])], 1);
+    __syncthreads();
+    if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void queue_scan_kernel(int *hist) {  // hist[0..63] counts -> hist[64..127] exclusive offsets
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < 64; b++) {
+            hist[64 + b] = acc;
+            acc += hist[b];
+        }
+    }
+}
+__global__ void queue_scatter_kernel(const int32_t *__restrict__ flags, int n, int *hist, int32_t *order) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        order[atomicAdd(&hist[64 + queue_bucket(flags[i])], 1)] = i;
+}
+
 // ---------------------------------------------------------------------------- helpers
 static int ensure_workspace(glc_evolver *ev, int grid) {
     const int64_t need = (int64_t)grid * kBlock;
     if (need <= ev->nslots) return 0;
     if (ev->d_ws) cudaFree(ev->d_ws);
+    if (ev->d_lanes) cudaFree(ev->d_lanes);
     ev->d_ws = nullptr;
+    ev->d_lanes = nullptr;
     GLC_CHECK(ev, cudaMalloc(&ev->d_ws, sizeof(double) * WS_NVEC * NY * need));
+    GLC_CHECK(ev, cudaMalloc(&ev->d_lanes, sizeof(LaneState) * need));
     ev->nslots = need;
     return 0;
 }
 
+static int build_queue_order(glc_evolver *ev, int n) {
+    if (!ev->sort_queue || n < 2 * kBlock) return 0;
+    if (n > ev->order_cap) {
+        cudaFree(ev->d_order);
+        ev->d_order = nullptr;
+        GLC_CHECK(ev, cudaMalloc(&ev->d_order, sizeof(int32_t) * (size_t)n));
+        ev->order_cap = n;
+    }
+    if (!ev->d_sort) GLC_CHECK(ev, cudaMalloc(&ev->d_sort, sizeof(int) * 128));
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_sort, 0, sizeof(int) * 128, ev->stream));
+    const int grid = std::min((n + 255) / 256, ev->num_sms * 8);
+    queue_hist_kernel<<<grid, 256, 0, ev->stream>>>(ev->d_flags, n, ev->d_sort);
+    queue_scan_kernel<<<1, 32, 0, ev->stream>>>(ev->d_sort);
+    queue_scatter_kernel<<<grid, 256, 0, ev->stream>>>(ev->d_flags, n, ev->d_sort, ev->d_order);
+    ev->launches += 3;
+    GLC_CHECK(ev, cudaGetLastError());
+    return 1;
+}
+
+// One batch = one or more time slices of the persistent evolve kernel.
 template <class Model>
-static int launch_evolve(glc_evolver *ev, int n) {
+static int launch_evolve(glc_evolver *ev, int n, unsigned long long *hc) {
     int blocksPerSm = 0;
     GLC_CHECK(ev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, evolve_kernel<Model>,
                                                                  kBlock, 0));
@@ -244,6 +258,9 @@ static int launch_evolve(glc_evolver *ev, int n) {
     if (grid < 1) grid = 1;
     int rc = ensure_workspace(ev, ev->num_sms * blocksPerSm);
     if (rc) return rc;
+    GLC_CHECK(ev, cudaEventRecord(ev->ev0, ev->stream));
+    const int sorted = build_queue_order(ev, n);
+    if (sorted < 0) return sorted;
     KernelArgs A;
     A.props = ev->d_props;
     A.flags = ev->d_flags;
@@ -256,12 +273,33 @@ static int launch_evolve(glc_evolver *ev, int n) {
     A.nslots = ev->nslots;
     A.work_counter = ev->d_work;
     A.counters = ev->d_counters;
+    A.order = sorted ? ev->d_order : nullptr;
+    A.lanes = ev->d_lanes;
+    A.resume = 0;
+    A.budget = ev->slice_budget > 0 ? ev->slice_budget : 0x7fffffff;
     GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
-    GLC_CHECK(ev, cudaEventRecord(ev->ev0, ev->stream));
-    evolve_kernel<Model><<<grid, kBlock, 0, ev->stream>>>(A);
-    ev->launches++;
-    GLC_CHECK(ev, cudaGetLastError());
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 8, ev->stream));
+    const double t_start = now_s();
+    int nslice = 0;
+    for (;;) {
+        evolve_kernel<Model><<<grid, kBlock, 0, ev->stream>>>(A);
+        ev->launches++;
+        ev->slices++;
+        GLC_CHECK(ev, cudaGetLastError());
+        GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost,
+                                      ev->stream));
+        if (ev->slice_budget <= 0) break;
+        GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+        if (ev->slice_log)
+            fprintf(stderr, "[glc slice %lld] t=%.3f ms done=%llu/%d rhs=%llu accepted=%llu parked=%llu\n",
+                    (long long)ev->slices, 1e3 * (now_s() - t_start), hc[6], n, hc[2], hc[0], hc[7]);
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long), ev->stream));
+        if (hc[6] >= (unsigned long long)n) break;
+        if (ev->max_slices > 0 && ++nslice >= ev->max_slices) break;  // profiling aid: leaves the batch unfinished
+        A.resume = 1;
+    }
     GLC_CHECK(ev, cudaEventRecord(ev->ev1, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
     return 0;
 }
 
@@ -295,6 +333,10 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device_ordinal);
     ev->num_sms = prop.multiProcessorCount;
+    if (const char *e = getenv("GLC_SLICE_BUDGET")) ev->slice_budget = atoi(e);
+    if (const char *e = getenv("GLC_SORT_QUEUE")) ev->sort_queue = atoi(e);
+    if (const char *e = getenv("GLC_SLICE_LOG")) ev->slice_log = atoi(e);
+    if (const char *e = getenv("GLC_MAX_SLICES")) ev->max_slices = atoi(e);
     cudaStreamCreateWithFlags(&ev->stream, cudaStreamNonBlocking);
     cudaEventCreate(&ev->ev0);
     cudaEventCreate(&ev->ev1);
@@ -329,6 +371,11 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaFree(ev->d_ws);
     cudaFree(ev->d_work);
     cudaFree(ev->d_counters);
+    cudaFree(ev->d_pow_ac);
+    cudaFree(ev->d_pow_kmt);
+    cudaFree(ev->d_lanes);
+    cudaFree(ev->d_order);
+    cudaFree(ev->d_sort);
     cudaEventDestroy(ev->ev0);
     cudaEventDestroy(ev->ev1);
     cudaStreamDestroy(ev->stream);
@@ -351,6 +398,24 @@ int glc_evolver_set_params(glc_evolver *ev, const glc_params *params) {
         ev->err = "at least one of absolute and relative tolerance must be greater than zero";
         return -8;
     }
+    cudaSetDevice(ev->device);
+    if (params->model == GLC_MODEL_STANDARD && (!ev->d_pow_ac || ev->pow_ac_exponent != params->adiabaticOmega)) {
+        // fastExponentiator tables, tabulated once as the reference's constructors do
+        const std::vector<double> ac = build_pow_table(1.0e-3, 1.0, params->adiabaticOmega, 1.0e4);
+        const std::vector<double> kmt = build_pow_table(1.0, 1000.0, 0.33, 100.0);
+        cudaFree(ev->d_pow_ac);
+        cudaFree(ev->d_pow_kmt);
+        ev->d_pow_ac = ev->d_pow_kmt = nullptr;
+        GLC_CHECK(ev, cudaMalloc(&ev->d_pow_ac, sizeof(double) * ac.size()));
+        GLC_CHECK(ev, cudaMalloc(&ev->d_pow_kmt, sizeof(double) * kmt.size()));
+        GLC_CHECK(ev, cudaMemcpy(ev->d_pow_ac, ac.data(), sizeof(double) * ac.size(), cudaMemcpyHostToDevice));
+        GLC_CHECK(ev, cudaMemcpy(ev->d_pow_kmt, kmt.data(), sizeof(double) * kmt.size(), cudaMemcpyHostToDevice));
+        ev->tables.powAc = ev->d_pow_ac;
+        ev->tables.powAcN = (int)ac.size();
+        ev->tables.powKmt = ev->d_pow_kmt;
+        ev->tables.powKmtN = (int)kmt.size();
+        ev->pow_ac_exponent = params->adiabaticOmega;
+    }
     ev->params = *params;
     ev->params_set = true;
     return 0;
@@ -358,77 +423,26 @@ int glc_evolver_set_params(glc_evolver *ev, const glc_params *params) {
 
 int glc_evolver_set_table(glc_evolver *ev, int32_t id, int32_t n0, int32_t n1, const double *x0,
                           const double *x1, const double *values) {
-    if (!ev || id < 0 || id >= GLC_NTABLES || n0 < 2 || n1 < 1 || !x0 || !values) return -1;
+    if (!ev) return -1;
     cudaSetDevice(ev->device);
+    PreparedTable pt;
+    if (prepare_table(id, n0, n1, x0, x1, values, pt) != 0) return -1;
     HostTable &t = ev->host_tables[id];
     cudaFree(t.d_x0);
     cudaFree(t.d_x1);
     cudaFree(t.d_v);
     t = HostTable();
-    std::vector<double> hx0(x0, x0 + n0), hx1, hv(values, values + (size_t)n0 * n1);
-    if (x1) hx1.assign(x1, x1 + n1);
-    int is_log = 0, first_zero = 0;
-    double first_nonzero = 0.0;
-    const double zmin = hx0.front(), zmax = hx0.back();
-    const double tmin = x1 ? hx1.front() : 0.0, tmax = x1 ? hx1.back() : 0.0;
-    if (id == GLC_TABLE_COOLING_FUNCTION || id == GLC_TABLE_ELECTRON_FRACTION) {
-        // cieFileReadFile, cooling/cooling_function/CIE_file.F90:627-659
-        if (!x1 || n1 < 2) return -1;
-        is_log = 1;
-        for (double v : hv)
-            if (!(v > 0.0)) is_log = 0;
-        if (is_log) {
-            first_zero = (hx0[0] == 0.0);
-            if (first_zero) first_nonzero = hx0[1];
-            for (auto &z : hx0) z = (z > 0.0) ? dm_log(z) : -999.0;
-            for (auto &T : hx1) T = dm_log(T);
-            for (auto &v : hv) v = dm_log(v);
-        }
-    }
     GLC_CHECK(ev, cudaMalloc(&t.d_x0, sizeof(double) * n0));
-    GLC_CHECK(ev, cudaMemcpy(t.d_x0, hx0.data(), sizeof(double) * n0, cudaMemcpyHostToDevice));
-    if (x1) {
+    GLC_CHECK(ev, cudaMemcpy(t.d_x0, pt.x0.data(), sizeof(double) * n0, cudaMemcpyHostToDevice));
+    if (!pt.x1.empty()) {
         GLC_CHECK(ev, cudaMalloc(&t.d_x1, sizeof(double) * n1));
-        GLC_CHECK(ev, cudaMemcpy(t.d_x1, hx1.data(), sizeof(double) * n1, cudaMemcpyHostToDevice));
+        GLC_CHECK(ev, cudaMemcpy(t.d_x1, pt.x1.data(), sizeof(double) * n1, cudaMemcpyHostToDevice));
     }
     GLC_CHECK(ev, cudaMalloc(&t.d_v, sizeof(double) * (size_t)n0 * n1));
-    GLC_CHECK(ev, cudaMemcpy(t.d_v, hv.data(), sizeof(double) * (size_t)n0 * n1, cudaMemcpyHostToDevice));
+    GLC_CHECK(ev, cudaMemcpy(t.d_v, pt.v.data(), sizeof(double) * (size_t)n0 * n1, cudaMemcpyHostToDevice));
     t.n0 = n0;
     t.n1 = n1;
-    DeviceTable2D d{n0, n1, t.d_x0, t.d_x1, t.d_v};
-    if (id == GLC_TABLE_COOLING_FUNCTION) {
-        ev->tables.cooling = d;
-        ev->tables.cooling_log = is_log;
-        ev->tables.cooling_first_z_zero = first_zero;
-        ev->tables.cooling_first_nonzero_z = first_nonzero;
-        ev->tables.cooling_z_min = zmin;
-        ev->tables.cooling_z_max = zmax;
-        ev->tables.cooling_t_min = tmin;
-        ev->tables.cooling_t_max = tmax;
-    } else if (id == GLC_TABLE_ELECTRON_FRACTION) {
-        ev->tables.electron = d;
-        ev->tables.electron_log = is_log;
-        ev->tables.electron_first_z_zero = first_zero;
-        ev->tables.electron_first_nonzero_z = first_nonzero;
-        ev->tables.electron_z_min = zmin;
-        ev->tables.electron_z_max = zmax;
-        ev->tables.electron_t_min = tmin;
-        ev->tables.electron_t_max = tmax;
-    } else if (id == GLC_TABLE_HALO_MEAN_DENSITY) {
-        if (n1 != 2) return -1;
-        // store ln t on the device; the grid must be log-uniform
-        std::vector<double> lnt(n0);
-        for (int i = 0; i < n0; i++) lnt[i] = dm_log(hx0[i]);
-        GLC_CHECK(ev, cudaMemcpy(t.d_x0, lnt.data(), sizeof(double) * n0, cudaMemcpyHostToDevice));
-        ev->tables.density = d;
-        ev->tables.density_lnt0 = lnt[0];
-        ev->tables.density_inv_dlnt = (double)(n0 - 1) / (lnt[n0 - 1] - lnt[0]);
-    } else if (id == GLC_TABLE_DISK_ROTATION_CURVE) {
-        if (n1 != 1) return -1;
-        ev->tables.diskrc = d;
-        ev->tables.diskrc_lnx0 = dm_log(hx0[0]);
-        ev->tables.diskrc_inv_dlnx = (double)(n0 - 1) / (dm_log(hx0[n0 - 1]) - dm_log(hx0[0]));
-    }
+    install_table(ev->tables, id, pt, DeviceTable2D{n0, n1, t.d_x0, t.d_x1, t.d_v});
     return 0;
 }
 
@@ -503,15 +517,12 @@ int glc_evolve_arena(glc_evolver *ev, int64_t n, glc_counters *counters) {
     cudaSetDevice(ev->device);
     int rc = upload_constants(ev);
     if (rc) return rc;
-    GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 8, ev->stream));
+    unsigned long long hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (ev->params.model == GLC_MODEL_BOX)
-        rc = launch_evolve<ModelBox>(ev, (int)n);
+        rc = launch_evolve<ModelBox>(ev, (int)n, hc);
     else
-        rc = launch_evolve<ModelStandard>(ev, (int)n);
+        rc = launch_evolve<ModelStandard>(ev, (int)n, hc);
     if (rc) return rc;
-    unsigned long long hc[8];
-    GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(hc), cudaMemcpyDeviceToHost, ev->stream));
-    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
     GLC_CHECK(ev, cudaEventElapsedTime(&ev->last_ms, ev->ev0, ev->ev1));
     if (counters) {
         counters->steps_accepted = hc[0];
@@ -551,6 +562,16 @@ int glc_arena_restore(glc_evolver *ev, int64_t n) {
 }
 
 int64_t glc_arena_capacity(const glc_evolver *ev) { return ev ? ev->cap : 0; }
+int64_t glc_slice_count(const glc_evolver *ev) { return ev ? ev->slices : 0; }
+
+int glc_evolver_set_option(glc_evolver *ev, int32_t option, int64_t value) {
+    if (!ev) return -1;
+    switch (option) {
+        case GLC_OPT_SLICE_BUDGET: ev->slice_budget = (int32_t)std::max<int64_t>(0, std::min<int64_t>(value, 0x7fffffff)); return 0;
+        case GLC_OPT_SORT_QUEUE: ev->sort_queue = value ? 1 : 0; return 0;
+        default: ev->err = "unknown option"; return -10;
+    }
+}
 int64_t glc_kernel_launch_count(const glc_evolver *ev) { return ev ? ev->launches : 0; }
 
 double glc_measure_fp64_peak_tflops(glc_evolver *ev) {
@@ -638,27 +659,5 @@ int glc_histogram_accumulate(glc_evolver *ev, int64_t n, int32_t prop, double lo
 }
 
 int glc_params_default(glc_params *P, int32_t model);  // defined in glc_params.cpp
-
-// not part of the public header: debugging aid (16 intermediates per node)
-int glc_debug_probe(glc_evolver *ev, int64_t n, const double *props, const int32_t *flags, double *out) {
-    std::vector<double> te((size_t)n, 0.0);
-    int rc = glc_arena_upload(ev, n, props, flags, te.data());
-    if (rc) return rc;
-    rc = upload_constants(ev);
-    if (rc) return rc;
-    double *d_out = nullptr;
-    GLC_CHECK(ev, cudaMalloc(&d_out, sizeof(double) * 16 * n));
-    KernelArgs A{};
-    A.props = ev->d_props;
-    A.flags = ev->d_flags;
-    A.cap = ev->cap;
-    A.n = (int)n;
-    probe_kernel<<<(int)((n + 63) / 64), 64, 0, ev->stream>>>(A, d_out);
-    GLC_CHECK(ev, cudaGetLastError());
-    GLC_CHECK(ev, cudaMemcpyAsync(out, d_out, sizeof(double) * 16 * n, cudaMemcpyDeviceToHost, ev->stream));
-    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
-    cudaFree(d_out);
-    return 0;
-}
 
 }  // extern "C"

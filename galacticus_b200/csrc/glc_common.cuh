@@ -7,8 +7,60 @@
 //                 slot = global thread id, so every access is a coalesced 256-B line per warp
 #pragma once
 
-#include <cuda_runtime.h>
 #include <stdint.h>
+
+// ---- platform layer.  The product is compiled by nvcc for sm_100a.  The SAME headers can also be compiled by
+// g++ into tests/emu (TEST INFRASTRUCTURE: lets the CPU-only test suite execute the kernels' per-lane logic
+// bit-for-bit against the reference restatement without a GPU); nothing in the product path ever loads that build.
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define GLC_DEVICE_INLINE static __device__ __forceinline__
+#define GLC_DEVICE_METHOD __device__ __forceinline__
+#define GLC_DEVICE_NOINLINE __device__ __noinline__
+#define GLC_LDG(p) __ldg(p)
+#define GLC_PARAMS c_params
+#define GLC_TABLES c_tables
+#define glc_atomic_add(p, v) atomicAdd((p), (v))
+#define GLC_ANY(p) __any_sync(0xffffffffu, (p))
+#define GLC_COUNT(k) ((void)0)
+#define GLC_SYNCWARP() __syncwarp()
+#ifndef GLC_BLOCK
+#define GLC_BLOCK 128
+#endif
+#ifndef GLC_MIN_BLOCKS
+#define GLC_MIN_BLOCKS 2
+#endif
+#else
+#include <math.h>
+#include <algorithm>
+#define GLC_DEVICE_INLINE static inline
+#define GLC_DEVICE_METHOD inline
+#define GLC_DEVICE_NOINLINE static __attribute__((noinline))
+#define GLC_LDG(p) (*(p))
+#define GLC_PARAMS c_params
+#define GLC_TABLES c_tables
+#define __constant__ static
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define GLC_ANY(p) (p)
+#ifdef GLC_EMU_COUNTERS
+static long long g_emu_count[8];
+#define GLC_COUNT(k) (g_emu_count[k]++)
+#else
+#define GLC_COUNT(k) ((void)0)
+#endif
+#define GLC_SYNCWARP() ((void)0)
+template <class T>
+static inline T glc_atomic_add(T *p, T v) {
+    T o = *p;
+    *p = o + v;
+    return o;
+}
+using std::max;
+using std::min;
+#endif
 
 #include "../../include/glc_b200.h"
 #include "glc_detmath.h"
@@ -68,7 +120,13 @@ struct DeviceTables {
     // exponential-disk rotation-curve factor, uniform in ln(half-radius)
     DeviceTable2D diskrc;
     double diskrc_lnx0, diskrc_inv_dlnx;
+    // fastExponentiator tables (math/exponentiation.F90:57-104), tabulated once like the reference does:
+    // x^adiabaticOmega on [1e-3,1] (adiabatic_Gnedin2004.F90:664-687) and x^0.33 on [1,1000] (Krumholz2009.F90)
+    const double *powAc, *powKmt;
+    int powAcN, powKmtN;
 };
+
+struct LaneState;
 
 struct KernelArgs {
     double *props;        // [NPROP][cap]
@@ -80,8 +138,12 @@ struct KernelArgs {
     int n;
     double *ws;           // [WS_NVEC][NY][nslots]
     int64_t nslots;
-    int *work_counter;
-    unsigned long long *counters;  // 6 x u64, layout of glc_counters
+    int *work_counter;             // queue cursor (persists across time slices)
+    unsigned long long *counters;  // 8 x u64: glc_counters fields, nodes done, lanes parked mid-node
+    const int32_t *order;          // queue order (node ids sorted by component set) or null = identity
+    struct LaneState *lanes;       // [nslots] parked lane states
+    int resume;                    // 0: first slice of a batch (lanes start empty), 1: resume parked lanes
+    int budget;                    // heavy calls per lane in this slice
 };
 
 // Per-node context kept in registers while a node is resident in a thread.

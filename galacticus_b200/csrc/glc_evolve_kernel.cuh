@@ -1,11 +1,15 @@
 // glc_evolve_kernel.cuh -- the batched adaptive Cash-Karp solver.
 //
-// One thread integrates one node; a thread that finishes its node pulls the next one from a
-// global queue (atomic counter), so divergence in step counts between nodes is absorbed at
-// step granularity ("compaction by refill") instead of idling lanes until the slowest node of
-// a warp is done.  One iteration of the main loop = one attempt of gsl_odeiv2_evolve_apply's
-// try_step: the 5 intermediate Cash-Karp stages + the dydt_out evaluation, all through ONE
-// call site of the model's rate function (the RHS is by far the largest piece of code).
+// Execution model (B200): one lane integrates one node; a lane that finishes its node pulls the next
+// one from a global queue (atomic counter over a component-sorted order), so divergence in step counts
+// between nodes is absorbed at RHS granularity ("compaction by refill").  The per-lane solver is an
+// explicit state machine whose main loop performs EXACTLY ONE heavy call per iteration -- one evaluation
+// of the model's rate function (a Cash-Karp stage, the dydt_out evaluation, or the post-evolve structure
+// solve, all through the same call site) -- so the 32 lanes of a warp re-converge at the top of the rate
+// function every iteration whatever stage/attempt/segment each of them is in.  The bookkeeping between
+// heavy calls (tableau combinations, error norm, step-size controller, post-step clamps, node fetch and
+// write-back) is short.  A launch is a TIME SLICE: every lane performs at most `budget` heavy calls and
+// then parks its state in HBM (LaneState, one record per resident lane); the next launch resumes it.
 //
 // Semantics restated (reference paths relative to /root/reference):
 //   standardEvolve          source/merger_trees/node_evolver/standard.F90:385-755
@@ -31,420 +35,521 @@ namespace glc {
 
 // Cash-Karp tableau (Cash & Karp 1990). Row s = weights of k1..k6 used to build the input of
 // stage s (s=1..5 -> k2..k6; s=6 -> 5th-order solution); row 0 = error weights (5th-4th order).
-__constant__ double c_rk_b[7][6] = {
-    {37.0 / 378.0 - 2825.0 / 27648.0, 0.0, 250.0 / 621.0 - 18575.0 / 48384.0,
-     125.0 / 594.0 - 13525.0 / 55296.0, -277.0 / 14336.0, 512.0 / 1771.0 - 0.25},
-    {1.0 / 5.0, 0, 0, 0, 0, 0},
-    {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0},
-    {0.3, -0.9, 1.2, 0, 0, 0},
-    {-11.0 / 54.0, 2.5, -70.0 / 27.0, 35.0 / 27.0, 0, 0},
-    {1631.0 / 55296.0, 175.0 / 512.0, 575.0 / 13824.0, 44275.0 / 110592.0, 253.0 / 4096.0, 0},
-    {37.0 / 378.0, 0.0, 250.0 / 621.0, 125.0 / 594.0, 0.0, 512.0 / 1771.0}};
+#define GLC_RK_B_INIT                                                                                    \
+    {                                                                                                    \
+        {37.0 / 378.0 - 2825.0 / 27648.0, 0.0, 250.0 / 621.0 - 18575.0 / 48384.0,                        \
+         125.0 / 594.0 - 13525.0 / 55296.0, -277.0 / 14336.0, 512.0 / 1771.0 - 0.25},                    \
+            {1.0 / 5.0, 0, 0, 0, 0, 0}, {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0}, {0.3, -0.9, 1.2, 0, 0, 0}, \
+            {-11.0 / 54.0, 2.5, -70.0 / 27.0, 35.0 / 27.0, 0, 0},                                        \
+            {1631.0 / 55296.0, 175.0 / 512.0, 575.0 / 13824.0, 44275.0 / 110592.0, 253.0 / 4096.0, 0},   \
+        {                                                                                                \
+            37.0 / 378.0, 0.0, 250.0 / 621.0, 125.0 / 594.0, 0.0, 512.0 / 1771.0                         \
+        }                                                                                                \
+    }
+__constant__ double c_rk_b[7][6] = GLC_RK_B_INIT;
 __constant__ double c_rk_a[7] = {0.0, 1.0 / 5.0, 0.3, 3.0 / 5.0, 1.0, 7.0 / 8.0, 1.0};
 
-enum Phase : int { PH_FETCH = 0, PH_SEGMENT, PH_TRIAL, PH_STEP, PH_SOLVE_DONE, PH_IDLE };
+enum Phase : int { PH_FETCH = 0, PH_SEGMENT, PH_TRIAL, PH_ATTEMPT, PH_STAGE, PH_SOLVE_DONE, PH_WRITEBACK, PH_IDLE };
+enum Heavy : int { HV_NONE = 0, HV_RHS, HV_FROZEN, HV_POST_EVOLVE };
 
 constexpr int kTrialCountMaximum = 8;  // standard.F90:135
 constexpr int kSegmentGuard = 64;
 
-__device__ __forceinline__ bool prop_is_non_negative(int prop) {
+// Everything a lane carries between heavy calls.  POD: parked in HBM between time slices.
+struct LaneState {
+    NodeCtx ctx;
+    double tEnd, x, x1, h, t0, h0, timeStartSaved, timeStepIn, timeInterruptFirst, rmax, ts;
+    int phase, node, stage, heavy;
+    uint32_t mask;
+    int interruptFound, interruptCode, count, inApply, outWritten, yslot, kslot, trial, finalStep;
+    int segmentsThisNode, nodeStatus, solveFailed, forbiddenNegatives;
+    unsigned int nAcc, nRej, nRhs, nSeg, nTrialFail, nNodes, nDone, pad;
+};
+
+GLC_DEVICE_INLINE void lane_reset(LaneState &L) {
+    L = LaneState();
+    L.phase = PH_FETCH;
+    L.node = -1;
+    L.h = 1.0;
+}
+
+GLC_DEVICE_INLINE bool prop_is_non_negative(int prop) {
     return prop != GLC_P_SAT_BOUND_MASS;  // isNonNegative attributes of the component definitions
 }
 
+// Queue order key (see glc_api.cu, "queue order"): ascending bucket id = position in the queue.
+GLC_DEVICE_INLINE int queue_bucket(int flags) {
+    const int rich = ((flags & GLC_F_HAS_SPHEROID) ? 8 : 0) | ((flags & GLC_F_HAS_DISK) ? 4 : 0) |
+                     ((flags & GLC_F_HAS_BH) ? 2 : 0) | ((flags & GLC_F_IS_SATELLITE) ? 1 : 0);
+    const int fresh = (flags & GLC_F_HAS_HOTHALO) ? ((flags & GLC_F_HH_INITIALIZED) ? 0 : 1) : 2;
+    return (2 - fresh) * 16 + (15 - rich);  // ascending bucket id = queue order; < 64
+}
+
+// Accessors of one lane's slice of the arena / workspace (both SoA: consecutive lanes touch consecutive
+// addresses, so every access is one coalesced 256-B line per warp).
+struct LaneMem {
+    const KernelArgs *A;
+    double *ws;
+    GLC_DEVICE_METHOD double &W(int vec, int comp) const { return ws[((int64_t)vec * NY + comp) * A->nslots]; }
+    GLC_DEVICE_METHOD double &AR(int prop, int node) const { return A->props[(int64_t)prop * A->cap + node]; }
+};
+
+// standardEvolve epilogue, part 2 (:657-753): interrupt hand-off and write-back of the final state yt.
 template <class Model>
-__global__ void __launch_bounds__(128) evolve_kernel(KernelArgs A) {
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t S = A.nslots;
-    double *ws = A.ws + slot;
-    auto W = [&](int vec, int comp) -> double & { return ws[((int64_t)vec * NY + comp) * S]; };
-    auto AR = [&](int prop, int node) -> double & { return A.props[(int64_t)prop * A.cap + node]; };
+GLC_DEVICE_INLINE void lane_writeback(LaneState &L, const LaneMem &M, double (&yt)[NY]) {
+    const KernelArgs &A = *M.A;
+    NodeCtx &ctx = L.ctx;
+    const int node = L.node;
+    double timeOut, timeStepOut;
+    int interrupted = 0;
+    if (L.timeInterruptFirst != 0.0) {
+        interrupted = 1;
+        timeOut = L.timeInterruptFirst;
+        timeStepOut = -1.0;
+    } else {
+        timeOut = L.tEnd;
+        timeStepOut = (L.timeStartSaved != L.tEnd && L.mask != 0u) ? L.h : -1.0;
+    }
+    if (ctx.numericsFailed) L.nodeStatus = GLC_STATUS_NONFINITE;
+    int code = interrupted ? L.interruptCode : GLC_INT_NONE;
+    if (interrupted && GLC_PARAMS.resolveInterruptsOnDevice) {
+        // functionInterrupt: <class>CreateByInterrupt / blackHoleCreate
+        if (code == GLC_INT_HOTHALO_CREATE) ctx.flags |= GLC_F_HAS_HOTHALO;
+        if (code == GLC_INT_DISK_CREATE) ctx.flags |= GLC_F_HAS_DISK;
+        if (code == GLC_INT_SPHEROID_CREATE) ctx.flags |= GLC_F_HAS_SPHEROID;
+        if (code == GLC_INT_BH_CREATE) {
+            ctx.flags |= GLC_F_HAS_BH;
+            yt[GLC_P_BH_MASS] = GLC_PARAMS.bhSeedMass;
+            yt[GLC_P_BH_SPIN] = GLC_PARAMS.bhSeedSpin;
+        }
+        code = GLC_INT_NONE;
+    }
+#pragma unroll
+    for (int i = 0; i < NY; i++) M.AR(i, node) = yt[i];
+    M.AR(GLC_P_TIME, node) = timeOut;
+    M.AR(GLC_P_TIME_STEP, node) = timeStepOut;
+    M.AR(GLC_P_DISK_RADIUS, node) = ctx.diskRadius;
+    M.AR(GLC_P_DISK_VELOCITY, node) = ctx.diskVelocity;
+    M.AR(GLC_P_SPH_RADIUS, node) = ctx.sphRadius;
+    M.AR(GLC_P_SPH_VELOCITY, node) = ctx.sphVelocity;
+    M.AR(GLC_P_BASIC_MASS, node) = ctx.basicMass;
+    M.AR(GLC_P_DMSCALE, node) = ctx.dmScale;
+    M.AR(GLC_P_SPIN, node) = ctx.spinJ;
+    A.flags[node] = ctx.flags;
+    if (interrupted && code == GLC_INT_NONE && timeOut < L.tEnd) {
+        if (L.segmentsThisNode < kSegmentGuard) {
+            L.phase = PH_SEGMENT;  // host loop evolver/standard.F90:425-476, resolved in place
+            return;
+        }
+        L.nodeStatus = GLC_STATUS_FAIL;
+    }
+    A.status[node] = L.nodeStatus;
+    A.interrupt[node] = code;
+    L.nDone++;
+    L.phase = PH_FETCH;
+}
 
-    const double epsAbs = c_params.odeToleranceAbsolute;
-    const double epsRel = c_params.odeToleranceRelative;
-
-    int phase = PH_FETCH;
-    int node = -1;
-    NodeCtx ctx;
-    uint32_t mask = 0;
-    double tEnd = 0, x = 0, x1 = 0, h = 1.0, t0 = 0, h0 = 0, timeStartSaved = 0, timeStepIn = -1;
-    double timeInterruptFirst = 0;
-    int interruptFound = 0, interruptCode = 0;
-    int count = 0, inApply = 0, outWritten = 0, yslot = 0, kslot = 0, trial = 0, finalStep = 0;
-    int segmentsThisNode = 0, nodeStatus = GLC_STATUS_SUCCESS, solveFailed = 0;
-    unsigned int nAcc = 0, nRej = 0, nRhs = 0, nSeg = 0, nTrialFail = 0, nNodes = 0;
-
+// Runs the lane's bookkeeping up to the next heavy call.  On return L.heavy says what the caller must
+// evaluate (HV_RHS / HV_POST_EVOLVE: Model::rates on yt at time L.ts; HV_FROZEN: nothing) before calling
+// lane_consume; HV_NONE means the lane is out of work.
+template <class Model>
+GLC_DEVICE_INLINE void lane_prepare(LaneState &L, const LaneMem &M, double (&yt)[NY]) {
+    const KernelArgs &A = *M.A;
     for (;;) {
-        // All 32 lanes stay in this loop until the whole warp is out of work, and the vote below is a
-        // reconvergence point: with independent thread scheduling the lanes would otherwise drift apart
-        // after the first divergent `continue` and execute serially for the rest of the kernel
-        // (measured: 2.0 active threads per warp instruction without it).
-        if (__all_sync(0xffffffffu, phase == PH_IDLE)) break;
         // ------------------------------------------------------------------ fetch a node
-        if (phase == PH_FETCH) {
-            node = atomicAdd(A.work_counter, 1);
-            if (node >= A.n) {
-                phase = PH_IDLE;
-                continue;
+        if (L.phase == PH_FETCH) {
+            const int q = glc_atomic_add(A.work_counter, 1);
+            if (q >= A.n) {
+                glc_atomic_add(A.work_counter, -1);  // keep the cursor at n: the queue may grow between slices
+                L.phase = PH_IDLE;
+                L.heavy = HV_NONE;
+                return;
             }
-            nNodes++;
-            ctx.flags = A.flags[node];
-            tEnd = A.time_end[node];
-            segmentsThisNode = 0;
-            nodeStatus = GLC_STATUS_SUCCESS;
-            phase = PH_SEGMENT;
+            L.node = A.order ? A.order[q] : q;
+            L.nNodes++;
+            L.ctx.flags = A.flags[L.node];
+            L.tEnd = A.time_end[L.node];
+            L.segmentsThisNode = 0;
+            L.nodeStatus = GLC_STATUS_SUCCESS;
+            L.phase = PH_SEGMENT;
         }
         // ------------------------------------------------- standardEvolve prologue (:434-576)
-        if (phase == PH_SEGMENT) {
-            double y[NY], s[NY];
+        if (L.phase == PH_SEGMENT) {
+            const int node = L.node;
+            NodeCtx &ctx = L.ctx;
+            double s[NY];
 #pragma unroll
             for (int i = 0; i < NY; i++) {
-                y[i] = AR(i, node);
+                yt[i] = M.AR(i, node);
                 s[i] = 0.0;
             }
-            ctx.massTarget = AR(GLC_P_MASS_TARGET, node);
-            ctx.massRate = AR(GLC_P_MASS_RATE, node);
-            ctx.timeTarget = AR(GLC_P_TIME_TARGET, node);
-            ctx.scaleTarget = AR(GLC_P_DMSCALE_TARGET, node);
-            ctx.scaleRate = AR(GLC_P_DMSCALE_RATE, node);
-            ctx.spinTarget = AR(GLC_P_SPIN_TARGET, node);
-            ctx.spinRate = AR(GLC_P_SPIN_RATE, node);
-            ctx.timeLastIsolated = AR(GLC_P_TIME_LAST_ISOLATED, node);
-            ctx.diskRadius = AR(GLC_P_DISK_RADIUS, node);
-            ctx.diskVelocity = AR(GLC_P_DISK_VELOCITY, node);
-            ctx.sphRadius = AR(GLC_P_SPH_RADIUS, node);
-            ctx.sphVelocity = AR(GLC_P_SPH_VELOCITY, node);
-            ctx.basicMass = AR(GLC_P_BASIC_MASS, node);
-            ctx.dmScale = AR(GLC_P_DMSCALE, node);
-            ctx.spinJ = AR(GLC_P_SPIN, node);
-            ctx.massBaryonicSubhalos = AR(GLC_P_MASS_BARYONIC_SUBHALOS, node);
+            ctx.massTarget = M.AR(GLC_P_MASS_TARGET, node);
+            ctx.massRate = M.AR(GLC_P_MASS_RATE, node);
+            ctx.timeTarget = M.AR(GLC_P_TIME_TARGET, node);
+            ctx.scaleTarget = M.AR(GLC_P_DMSCALE_TARGET, node);
+            ctx.scaleRate = M.AR(GLC_P_DMSCALE_RATE, node);
+            ctx.spinTarget = M.AR(GLC_P_SPIN_TARGET, node);
+            ctx.spinRate = M.AR(GLC_P_SPIN_RATE, node);
+            ctx.timeLastIsolated = M.AR(GLC_P_TIME_LAST_ISOLATED, node);
+            ctx.diskRadius = M.AR(GLC_P_DISK_RADIUS, node);
+            ctx.diskVelocity = M.AR(GLC_P_DISK_VELOCITY, node);
+            ctx.sphRadius = M.AR(GLC_P_SPH_RADIUS, node);
+            ctx.sphVelocity = M.AR(GLC_P_SPH_VELOCITY, node);
+            ctx.basicMass = M.AR(GLC_P_BASIC_MASS, node);
+            ctx.dmScale = M.AR(GLC_P_DMSCALE, node);
+            ctx.spinJ = M.AR(GLC_P_SPIN, node);
+            ctx.massBaryonicSubhalos = M.AR(GLC_P_MASS_BARYONIC_SUBHALOS, node);
             ctx.numericsFailed = 0;
-            timeStartSaved = AR(GLC_P_TIME, node);
-            ctx.timeNode = timeStartSaved;
-            timeStepIn = AR(GLC_P_TIME_STEP, node);
-            nSeg++;
-            segmentsThisNode++;
+            L.timeStartSaved = M.AR(GLC_P_TIME, node);
+            ctx.timeNode = L.timeStartSaved;
+            L.timeStepIn = M.AR(GLC_P_TIME_STEP, node);
+            L.nSeg++;
+            L.segmentsThisNode++;
             {
                 // pre-evolve hooks edit the node itself (they run before the solver's saved copy is taken,
                 // standard.F90:434-441 vs :518-527), so their edits must survive a solver restart
                 const int flagsBefore = ctx.flags;
-                Model::pre_evolve(ctx, y);
+                Model::pre_evolve(ctx, yt);
                 if (ctx.flags != flagsBefore) {
 #pragma unroll
-                    for (int i = 0; i < NY; i++) AR(i, node) = y[i];
-                    AR(GLC_P_BASIC_MASS, node) = ctx.basicMass;
+                    for (int i = 0; i < NY; i++) M.AR(i, node) = yt[i];
+                    M.AR(GLC_P_BASIC_MASS, node) = ctx.basicMass;
                     A.flags[node] = ctx.flags;
                 }
             }
-            mask = Model::active_mask(ctx.flags);
-            Model::scales(ctx, y, s);
+            L.mask = Model::active_mask(ctx.flags);
+            Model::scales(ctx, yt, s);
 #pragma unroll
             for (int i = 0; i < NY; i++) {
-                W(WS_YA, i) = y[i];
-                W(WS_SCALE, i) = s[i];
+                M.W(WS_YA, i) = yt[i];
+                M.W(WS_SCALE, i) = s[i];
             }
-            yslot = 0;
-            interruptFound = 0;
-            timeInterruptFirst = 0.0;
-            interruptCode = GLC_INT_NONE;
-            trial = 0;
-            solveFailed = 0;
-            x = timeStartSaved;
-            if (timeStartSaved != tEnd && mask != 0u)
-                phase = PH_TRIAL;
-            else
-                phase = PH_SOLVE_DONE;
+            L.yslot = 0;
+            L.interruptFound = 0;
+            L.timeInterruptFirst = 0.0;
+            L.interruptCode = GLC_INT_NONE;
+            L.trial = 0;
+            L.solveFailed = 0;
+            L.x = L.timeStartSaved;
+            L.phase = (L.timeStartSaved != L.tEnd && L.mask != 0u) ? PH_TRIAL : PH_SOLVE_DONE;
         }
         // ------------------------------ trial start (:587-652) + odeSolverSolve prologue
-        if (phase == PH_TRIAL) {
-            if (trial > 0) {
+        if (L.phase == PH_TRIAL) {
+            if (L.trial > 0) {
 #pragma unroll
-                for (int i = 0; i < NY; i++) W(WS_YA, i) = AR(i, node);
+                for (int i = 0; i < NY; i++) M.W(WS_YA, i) = M.AR(i, L.node);
             }
-            yslot = 0;
-            double stepSize = c_params.reuseODEStepSize ? timeStepIn / dm_scale2(1.0, trial) : -1.0;
-            x = timeStartSaved;
-            x1 = tEnd;
-            double xStep = x1 - x;
+            L.yslot = 0;
+            const double stepSize = GLC_PARAMS.reuseODEStepSize ? L.timeStepIn / dm_scale2(1.0, L.trial) : -1.0;
+            L.x = L.timeStartSaved;
+            L.x1 = L.tEnd;
+            double xStep = L.x1 - L.x;
             if (stepSize > 0.0) xStep = fmin(stepSize, xStep);
-            count = 0;  // GSL_ODEIV2_Driver_Reset
-            if (xStep != 0.0) h = xStep;
-            inApply = 0;
-            outWritten = 0;
-            phase = PH_STEP;
+            L.count = 0;  // GSL_ODEIV2_Driver_Reset
+            if (xStep != 0.0) L.h = xStep;
+            L.inApply = 0;
+            L.outWritten = 0;
+            L.phase = PH_ATTEMPT;
         }
-        // --------------------------------------------- one try_step of evolve_apply
-        if (phase == PH_STEP) {
+        // --------------------------------------------- start of one try_step of evolve_apply
+        if (L.phase == PH_ATTEMPT) {
             int needK1 = 0;
-            if (!inApply) {
-                t0 = x;
-                h0 = h;
-                if (count > 0 && outWritten) kslot ^= 1;  // dydt_in := dydt_out
-                outWritten = 0;
-                needK1 = (count == 0);
+            if (!L.inApply) {
+                L.t0 = L.x;
+                L.h0 = L.h;
+                if (L.count > 0 && L.outWritten) L.kslot ^= 1;  // dydt_in := dydt_out
+                L.outWritten = 0;
+                needK1 = (L.count == 0);
             }
-            {
-                const double dt = x1 - t0;
-                if (h0 > dt) {
-                    h0 = dt;
-                    finalStep = 1;
-                } else {
-                    finalStep = 0;
-                }
+            const double dt = L.x1 - L.t0;
+            if (L.h0 > dt) {
+                L.h0 = dt;
+                L.finalStep = 1;
+            } else {
+                L.finalStep = 0;
             }
-            const int ySrc = WS_YA + yslot, yDst = WS_YA + (yslot ^ 1);
-            const int k1v = WS_KA + kslot, kOutv = WS_KA + (kslot ^ 1);
-            double rmax = DBL_MIN;
-            int forbiddenNegatives = 0;
-            int aborted = 0;
-#pragma unroll 1
-            for (int stage = needK1 ? 0 : 1; stage <= 6; ++stage) {
-                double yt[NY], rate[NY];
-                const double ts = t0 + c_rk_a[stage] * h0;
-                // ---- stage input
-                if (stage == 0) {
-#pragma unroll
-                    for (int i = 0; i < NY; i++) yt[i] = W(ySrc, i);
-                } else if (stage < 6) {
-#pragma unroll
-                    for (int i = 0; i < NY; i++) {
-                        if (stage == 1) {
-                            yt[i] = W(ySrc, i) + c_rk_b[1][0] * h0 * W(k1v, i);  // rkck.c: y + b21*h*k1
-                        } else {
-                            double acc = c_rk_b[stage][0] * W(k1v, i);
-                            for (int j = 1; j < stage; j++) acc += c_rk_b[stage][j] * W(WS_K2 + j - 1, i);
-                            yt[i] = W(ySrc, i) + h0 * acc;
-                        }
-                    }
-                } else {
-                    // 5th-order solution, error estimate and the controller's rmax (cscal2.c:109-126;
-                    // a_dydt = 0 so rmax does not depend on dydt_out)
-#pragma unroll
-                    for (int i = 0; i < NY; i++) {
-                        const double k1 = W(k1v, i), k3 = W(WS_K3, i), k4 = W(WS_K4, i),
-                                     k5 = W(WS_K5, i), k6 = W(WS_K6, i);
-                        const double d = c_rk_b[6][0] * k1 + c_rk_b[6][2] * k3 + c_rk_b[6][3] * k4 +
-                                         c_rk_b[6][5] * k6;
-                        const double ynew = W(ySrc, i) + h0 * d;
-                        const double yerr = h0 * (c_rk_b[0][0] * k1 + c_rk_b[0][2] * k3 +
-                                                  c_rk_b[0][3] * k4 + c_rk_b[0][4] * k5 +
-                                                  c_rk_b[0][5] * k6);
-                        yt[i] = ynew;
-                        W(yDst, i) = ynew;
-                        if (mask & (1u << i)) {
-                            const double D0 = epsRel * fabs(ynew) + epsAbs * W(WS_SCALE, i);
-                            const double r = fabs(yerr) / fabs(D0);
-                            rmax = fmax(r, rmax);
-                            if (c_params.enforceNonNegativity && prop_is_non_negative(i) && ynew < 0.0)
-                                forbiddenNegatives = 1;
-                        }
-                    }
-                }
-                // ---- standardODEs
-#pragma unroll
-                for (int i = 0; i < NY; i++) rate[i] = 0.0;
-                Model::solve_analytics(ctx, ts);
-                int code = GLC_INT_NONE;
-                int ebadfunc = 0;
-                nRhs++;  // every call of the derivatives function counts (also the frozen ones past an interrupt)
-                if (interruptFound && ts >= timeInterruptFirst) {
-                    Model::solve_analytics(ctx, timeInterruptFirst);
-                } else {
-                    code = Model::rates(ctx, ts, yt, rate);
-                    if (code != GLC_INT_NONE) {
-#pragma unroll
-                        for (int i = 0; i < NY; i++) rate[i] = 0.0;
-                        if (ts < timeInterruptFirst || !interruptFound) {
-                            interruptFound = 1;
-                            timeInterruptFirst = ts;
-                            interruptCode = code;
-                            ebadfunc = 1;
-                        }
-                    }
-                }
-                {
-                    const int kv = (stage == 0) ? k1v : ((stage == 6) ? kOutv : WS_K2 + stage - 1);
-#pragma unroll
-                    for (int i = 0; i < NY; i++) {
-                        const double r = (mask & (1u << i)) ? rate[i] : 0.0;
-                        if (!isfinite(r)) nodeStatus = GLC_STATUS_NONFINITE;
-                        W(kv, i) = r;
-                    }
-                    if (stage == 6) outWritten = 1;
-                }
-                if (ebadfunc) {
-                    aborted = 1;
-                    break;
-                }
-            }
-            GTR("attempt t0=%.17g h0=%.17g t1=%.17g final=%d count=%d aborted=%d rmax=%.17g\n", t0, h0, x1, finalStep, count, aborted, rmax);
-            if (aborted) {
-                // odeSolverInterrupt, solver.F90:608-618.  NB (GSL quirk, reproduced): gsl_odeiv2_evolve_apply
-                // leaves *t at the end of a REJECTED attempt when the retry returns early, so x may be ahead
-                // of t0 here; if it is beyond the interrupt time the solver restarts from the initial state.
-                x1 = timeInterruptFirst;
-                inApply = 0;
-                if (x > x1) {
-#pragma unroll
-                    for (int i = 0; i < NY; i++) W(WS_YA, i) = AR(i, node);
-                    yslot = 0;
-                    x = timeStartSaved;
-                    count = 0;  // GSL_ODEIV2_Driver_Reset
-                    outWritten = 0;
-                }
-                if (!(x < x1)) phase = PH_SOLVE_DONE;
-                continue;
-            }
-            count++;
-            const double tNew = finalStep ? x1 : t0 + h0;
-            x = tNew;  // evolve.c sets *t before the controller runs and does not restore it on a retry
-            // ---- sc2_control_hadjust (ord = 5)
-            const double hOld = h0;
-            int dec = 0;
-            if (rmax > 1.1) {
-                double r = 0.9 / dm_pow(rmax, 1.0 / 5.0);
-                if (r < 0.2) r = 0.2;
-                h0 = r * hOld;
-                dec = 1;
-            } else if (forbiddenNegatives) {
-                h0 = 0.5 * hOld;
-                dec = 1;
-            } else if (rmax < 0.5) {
-                double r = 0.9 / dm_pow(rmax, 1.0 / 6.0);
-                if (r > 4.9) r = 4.9;
-                if (r < 1.0) r = 1.0;
-                h0 = r * hOld;
-            }
-            GTR("  dec=%d h_old=%.17g h_new=%.17g\n", dec, hOld, h0);
-            if (dec) {
-                const double tNext = tNew + h0;
-                if (fabs(h0) < fabs(hOld) && tNext != tNew) {
-                    nRej++;
-                    inApply = 1;  // y := y0 is implicit (yslot unchanged)
-                    continue;
-                }
-                // GSL_FAILURE: step-size underflow
-                h = h0;
-                inApply = 0;
-                solveFailed = 1;
-                yslot ^= 1;  // as in GSL, y holds the failed step's result
-                phase = PH_SOLVE_DONE;
-                continue;
-            }
-            // ---- accepted
-            if (!finalStep) h = h0;
-            yslot ^= 1;
-            inApply = 0;
-            nAcc++;
-            {
-                // standardPostStepProcessing
-                double y[NY];
-                const int yv = WS_YA + yslot;
-#pragma unroll
-                for (int i = 0; i < NY; i++) y[i] = W(yv, i);
-                Model::solve_analytics(ctx, x);
-                const int st = Model::post_step(ctx, y);
-                if (st != kGslSuccess) {
-#pragma unroll
-                    for (int i = 0; i < NY; i++) W(yv, i) = y[i];
-                }
-                if (st != kGslSuccess && st != kGslContinue) count = 0;  // gsl_odeiv2_evolve_reset
-            }
-            if (!(x < x1)) phase = PH_SOLVE_DONE;
+            L.rmax = DBL_MIN;
+            L.forbiddenNegatives = 0;
+            L.stage = needK1 ? 0 : 1;
+            L.phase = PH_STAGE;
         }
-        // -------------------------------- trial epilogue + standardEvolve epilogue (:657-753)
-        if (phase == PH_SOLVE_DONE) {
-            double y[NY];
-            const int yv = WS_YA + yslot;
+        // --------------------------------------------- input of one Cash-Karp stage
+        if (L.phase == PH_STAGE) {
+            const int stage = L.stage;
+            const int ySrc = WS_YA + L.yslot, yDst = WS_YA + (L.yslot ^ 1);
+            const int k1v = WS_KA + L.kslot;
+            const double h0 = L.h0;
+            L.ts = L.t0 + c_rk_a[stage] * h0;
+            if (stage == 0) {
 #pragma unroll
-            for (int i = 0; i < NY; i++) y[i] = W(yv, i);
-            if (solveFailed) {
+                for (int i = 0; i < NY; i++) yt[i] = M.W(ySrc, i);
+            } else if (stage == 1) {
+                const double b10 = c_rk_b[1][0];
+#pragma unroll
+                for (int i = 0; i < NY; i++) yt[i] = M.W(ySrc, i) + b10 * h0 * M.W(k1v, i);  // rkck.c: y + b21*h*k1
+            } else if (stage < 6) {
+                double b[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) b[j] = c_rk_b[stage][j];
+#pragma unroll
+                for (int i = 0; i < NY; i++) {
+                    double acc = b[0] * M.W(k1v, i);
+                    for (int j = 1; j < stage; j++) acc += b[j] * M.W(WS_K2 + j - 1, i);
+                    yt[i] = M.W(ySrc, i) + h0 * acc;
+                }
+            } else {
+                // 5th-order solution, error estimate and the controller's rmax (cscal2.c:109-126;
+                // a_dydt = 0 so rmax does not depend on dydt_out)
+                const double epsAbs = GLC_PARAMS.odeToleranceAbsolute, epsRel = GLC_PARAMS.odeToleranceRelative;
+                const bool nonNeg = GLC_PARAMS.enforceNonNegativity != 0;
+                double rmax = L.rmax;
+                int forbidden = L.forbiddenNegatives;
+#pragma unroll
+                for (int i = 0; i < NY; i++) {
+                    const double k1 = M.W(k1v, i), k3 = M.W(WS_K3, i), k4 = M.W(WS_K4, i), k5 = M.W(WS_K5, i),
+                                 k6 = M.W(WS_K6, i);
+                    const double d = c_rk_b[6][0] * k1 + c_rk_b[6][2] * k3 + c_rk_b[6][3] * k4 + c_rk_b[6][5] * k6;
+                    const double ynew = M.W(ySrc, i) + h0 * d;
+                    const double yerr = h0 * (c_rk_b[0][0] * k1 + c_rk_b[0][2] * k3 + c_rk_b[0][3] * k4 +
+                                              c_rk_b[0][4] * k5 + c_rk_b[0][5] * k6);
+                    yt[i] = ynew;
+                    M.W(yDst, i) = ynew;
+                    if (L.mask & (1u << i)) {
+                        const double D0 = epsRel * fabs(ynew) + epsAbs * M.W(WS_SCALE, i);
+                        const double r = fabs(yerr) / fabs(D0);
+                        rmax = fmax(r, rmax);
+                        if (nonNeg && prop_is_non_negative(i) && ynew < 0.0) forbidden = 1;
+                    }
+                }
+                L.rmax = rmax;
+                L.forbiddenNegatives = forbidden;
+            }
+            // ---- standardODEs, part 1
+            Model::solve_analytics(L.ctx, L.ts);
+            L.nRhs++;  // every call of the derivatives function counts (also the frozen ones past an interrupt)
+            if (L.interruptFound && L.ts >= L.timeInterruptFirst) {
+                Model::solve_analytics(L.ctx, L.timeInterruptFirst);
+                L.heavy = HV_FROZEN;
+            } else {
+                L.heavy = HV_RHS;
+            }
+            return;
+        }
+        // -------------------------------- trial epilogue + standardEvolve epilogue (:657-753), part 1
+        if (L.phase == PH_SOLVE_DONE) {
+            const int yv = WS_YA + L.yslot;
+#pragma unroll
+            for (int i = 0; i < NY; i++) yt[i] = M.W(yv, i);
+            if (L.solveFailed) {
                 int rescued = 0;
-                if (c_params.enforceNonNegativity) {
+                if (GLC_PARAMS.enforceNonNegativity) {
 #pragma unroll
                     for (int i = 0; i < NY; i++)
-                        if ((mask & (1u << i)) && prop_is_non_negative(i) && y[i] < 0.0) {
-                            y[i] = 0.0;
+                        if ((L.mask & (1u << i)) && prop_is_non_negative(i) && yt[i] < 0.0) {
+                            yt[i] = 0.0;
                             rescued = 1;
                         }
                 }
                 if (rescued) {
-                    h = timeStepIn / dm_scale2(1.0, trial);
-                    solveFailed = 0;
+                    L.h = L.timeStepIn / dm_scale2(1.0, L.trial);
+                    L.solveFailed = 0;
                 } else {
-                    trial++;
-                    nTrialFail++;
-                    solveFailed = 0;
-                    if (trial < kTrialCountMaximum) {
-                        phase = PH_TRIAL;
+                    L.trial++;
+                    L.nTrialFail++;
+                    L.solveFailed = 0;
+                    if (L.trial < kTrialCountMaximum) {
+                        L.phase = PH_TRIAL;
                         continue;
                     }
                     // errorStatusUnderflow: node left at its saved values
-                    A.status[node] = GLC_STATUS_UNDERFLOW;
-                    A.interrupt[node] = GLC_INT_NONE;
-                    phase = PH_FETCH;
+                    A.status[L.node] = GLC_STATUS_UNDERFLOW;
+                    A.interrupt[L.node] = GLC_INT_NONE;
+                    L.nDone++;
+                    L.phase = PH_FETCH;
                     continue;
                 }
             }
-            Model::solve_analytics(ctx, tEnd);
-            double timeOut, timeStepOut;
-            int interrupted = 0;
-            if (timeInterruptFirst != 0.0) {
-                interrupted = 1;
-                timeOut = timeInterruptFirst;
-                timeStepOut = -1.0;
-            } else {
-                timeOut = tEnd;
-                timeStepOut = (timeStartSaved != tEnd && mask != 0u) ? h : -1.0;
+            Model::solve_analytics(L.ctx, L.tEnd);
+            L.ctx.timeNode = (L.timeInterruptFirst != 0.0) ? L.timeInterruptFirst : L.tEnd;
+            L.ts = L.ctx.timeNode;
+            L.phase = PH_WRITEBACK;
+            if (Model::kHasPostEvolve) {
+                L.heavy = HV_POST_EVOLVE;  // <eventHook postEvolve>: structure solve at the final state
+                return;                    // lane_consume writes the node back
             }
-            ctx.timeNode = timeOut;
-            Model::post_evolve(ctx, y);
-            if (ctx.numericsFailed) nodeStatus = GLC_STATUS_NONFINITE;
-            int code = interrupted ? interruptCode : GLC_INT_NONE;
-            if (interrupted && c_params.resolveInterruptsOnDevice) {
-                // functionInterrupt: <class>CreateByInterrupt / blackHoleCreate
-                if (code == GLC_INT_HOTHALO_CREATE) ctx.flags |= GLC_F_HAS_HOTHALO;
-                if (code == GLC_INT_DISK_CREATE) ctx.flags |= GLC_F_HAS_DISK;
-                if (code == GLC_INT_SPHEROID_CREATE) ctx.flags |= GLC_F_HAS_SPHEROID;
-                if (code == GLC_INT_BH_CREATE) {
-                    ctx.flags |= GLC_F_HAS_BH;
-                    y[GLC_P_BH_MASS] = c_params.bhSeedMass;
-                    y[GLC_P_BH_SPIN] = c_params.bhSeedSpin;
-                }
-                code = GLC_INT_NONE;
-            }
-#pragma unroll
-            for (int i = 0; i < NY; i++) AR(i, node) = y[i];
-            AR(GLC_P_TIME, node) = timeOut;
-            AR(GLC_P_TIME_STEP, node) = timeStepOut;
-            AR(GLC_P_DISK_RADIUS, node) = ctx.diskRadius;
-            AR(GLC_P_DISK_VELOCITY, node) = ctx.diskVelocity;
-            AR(GLC_P_SPH_RADIUS, node) = ctx.sphRadius;
-            AR(GLC_P_SPH_VELOCITY, node) = ctx.sphVelocity;
-            AR(GLC_P_BASIC_MASS, node) = ctx.basicMass;
-            AR(GLC_P_DMSCALE, node) = ctx.dmScale;
-            AR(GLC_P_SPIN, node) = ctx.spinJ;
-            A.flags[node] = ctx.flags;
-            if (interrupted && code == GLC_INT_NONE && timeOut < tEnd) {
-                if (segmentsThisNode < kSegmentGuard) {
-                    phase = PH_SEGMENT;  // host loop evolver/standard.F90:425-476, resolved in place
-                    continue;
-                }
-                nodeStatus = GLC_STATUS_FAIL;
-            }
-            A.status[node] = nodeStatus;
-            A.interrupt[node] = code;
-            phase = PH_FETCH;
+        }
+        if (L.phase == PH_WRITEBACK) {
+            lane_writeback<Model>(L, M, yt);
+            continue;
+        }
+        if (L.phase == PH_IDLE) {
+            L.heavy = HV_NONE;
+            return;
         }
     }
+}
+
+// Digests the result of the heavy call: stores the stage derivative, and at the end of an attempt runs the
+// step-size controller, the accept/reject logic of gsl_odeiv2_evolve_apply and the post-step hook.
+template <class Model>
+GLC_DEVICE_INLINE void lane_consume(LaneState &L, const LaneMem &M, double (&yt)[NY], double (&rate)[NY], int code) {
+    if (L.heavy == HV_NONE) return;
+    if (L.heavy == HV_POST_EVOLVE) {
+        if (Model::kHasPostEvolve) lane_writeback<Model>(L, M, yt);
+        return;
+    }
+    // ---- standardODEs, part 2 (interrupt bookkeeping :901-928)
+    int ebadfunc = 0;
+    if (L.heavy == HV_RHS && code != GLC_INT_NONE) {
+#pragma unroll
+        for (int i = 0; i < NY; i++) rate[i] = 0.0;
+        if (L.ts < L.timeInterruptFirst || !L.interruptFound) {
+            L.interruptFound = 1;
+            L.timeInterruptFirst = L.ts;
+            L.interruptCode = code;
+            ebadfunc = 1;
+        }
+    }
+    {
+        const int stage = L.stage;
+        const int kv = (stage == 0) ? WS_KA + L.kslot : ((stage == 6) ? WS_KA + (L.kslot ^ 1) : WS_K2 + stage - 1);
+        int nonfinite = 0;
+#pragma unroll
+        for (int i = 0; i < NY; i++) {
+            const double r = (L.mask & (1u << i)) ? rate[i] : 0.0;
+            if (!isfinite(r)) nonfinite = 1;
+            M.W(kv, i) = r;
+        }
+        if (nonfinite) L.nodeStatus = GLC_STATUS_NONFINITE;
+        if (stage == 6) L.outWritten = 1;
+    }
+    if (ebadfunc) {
+        // odeSolverInterrupt, solver.F90:608-618.  NB (GSL quirk, reproduced): gsl_odeiv2_evolve_apply
+        // leaves *t at the end of a REJECTED attempt when the retry returns early, so x may be ahead
+        // of t0 here; if it is beyond the interrupt time the solver restarts from the initial state.
+        L.x1 = L.timeInterruptFirst;
+        L.inApply = 0;
+        if (L.x > L.x1) {
+#pragma unroll
+            for (int i = 0; i < NY; i++) M.W(WS_YA, i) = M.AR(i, L.node);
+            L.yslot = 0;
+            L.x = L.timeStartSaved;
+            L.count = 0;  // GSL_ODEIV2_Driver_Reset
+            L.outWritten = 0;
+        }
+        L.phase = (L.x < L.x1) ? PH_ATTEMPT : PH_SOLVE_DONE;
+        return;
+    }
+    if (L.stage < 6) {
+        L.stage++;
+        return;  // phase stays PH_STAGE
+    }
+    // ---------------------------------------------------------------- end of the attempt
+    L.count++;
+    const double tNew = L.finalStep ? L.x1 : L.t0 + L.h0;
+    L.x = tNew;  // evolve.c sets *t before the controller runs and does not restore it on a retry
+    // ---- sc2_control_hadjust (ord = 5)
+    const double hOld = L.h0;
+    const double rmax = L.rmax;
+    int dec = 0;
+    if (rmax > 1.1) {
+        double r = 0.9 / dm_pow(rmax, 1.0 / 5.0);
+        if (r < 0.2) r = 0.2;
+        L.h0 = r * hOld;
+        dec = 1;
+    } else if (L.forbiddenNegatives) {
+        L.h0 = 0.5 * hOld;
+        dec = 1;
+    } else if (rmax < 0.5) {
+        double r = 0.9 / dm_pow(rmax, 1.0 / 6.0);
+        if (r > 4.9) r = 4.9;
+        if (r < 1.0) r = 1.0;
+        L.h0 = r * hOld;
+    }
+    if (dec) {
+        const double tNext = tNew + L.h0;
+        if (fabs(L.h0) < fabs(hOld) && tNext != tNew) {
+            L.nRej++;
+            L.inApply = 1;  // y := y0 is implicit (yslot unchanged)
+            L.phase = PH_ATTEMPT;
+            return;
+        }
+        // GSL_FAILURE: step-size underflow
+        L.h = L.h0;
+        L.inApply = 0;
+        L.solveFailed = 1;
+        L.yslot ^= 1;  // as in GSL, y holds the failed step's result
+        L.phase = PH_SOLVE_DONE;
+        return;
+    }
+    // ---- accepted
+    if (!L.finalStep) L.h = L.h0;
+    L.yslot ^= 1;
+    L.inApply = 0;
+    L.nAcc++;
+    {
+        // standardPostStepProcessing (rate[] is dead here and is re-used as the state buffer)
+        const int yv = WS_YA + L.yslot;
+#pragma unroll
+        for (int i = 0; i < NY; i++) rate[i] = M.W(yv, i);
+        Model::solve_analytics(L.ctx, L.x);
+        const int st = Model::post_step(L.ctx, rate);
+        if (st != kGslSuccess) {
+#pragma unroll
+            for (int i = 0; i < NY; i++) M.W(yv, i) = rate[i];
+        }
+        if (st != kGslSuccess && st != kGslContinue) L.count = 0;  // gsl_odeiv2_evolve_reset
+    }
+    L.phase = (L.x < L.x1) ? PH_ATTEMPT : PH_SOLVE_DONE;
+}
+
+// One iteration of a lane: bookkeeping, ONE heavy call, digestion.  Returns false when the lane is idle.
+template <class Model>
+GLC_DEVICE_INLINE bool lane_iterate(LaneState &L, const LaneMem &M) {
+    double yt[NY], rate[NY];
+    lane_prepare<Model>(L, M, yt);
+    int code = GLC_INT_NONE;
+#pragma unroll
+    for (int i = 0; i < NY; i++) rate[i] = 0.0;
+    // The single heavy call site.  Warp-synchronous: every lane of the warp calls it in every iteration (idle and
+    // frozen lanes with on = false), so the votes inside the rate function see the whole warp.
+    GLC_SYNCWARP();
+    code = Model::rates(L.ctx, L.ts, yt, rate, L.heavy == HV_POST_EVOLVE, L.heavy == HV_RHS || L.heavy == HV_POST_EVOLVE);
+    lane_consume<Model>(L, M, yt, rate, code);
+    return L.heavy != HV_NONE;
+}
+
+#if defined(__CUDACC__)
+template <class Model>
+__global__ void __launch_bounds__(GLC_BLOCK, GLC_MIN_BLOCKS) evolve_kernel(KernelArgs A) {
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    LaneMem M{&A, A.ws + slot};
+    LaneState L;
+    if (A.resume)
+        L = A.lanes[slot];
+    else
+        lane_reset(L);
+    L.nAcc = L.nRej = L.nRhs = L.nSeg = L.nTrialFail = L.nNodes = L.nDone = 0;
+    if (L.phase == PH_IDLE) L.phase = PH_FETCH;  // the queue may have grown since the last slice
+
+    for (int it = 0; it < A.budget; ++it) {
+        // All 32 lanes stay in this loop until the whole warp is out of work; the vote is a reconvergence
+        // point in front of the heavy call.
+        const bool active = lane_iterate<Model>(L, M);
+        if (!__any_sync(0xffffffffu, active)) break;
+    }
+    A.lanes[slot] = L;
 
     // ---- counters: warp-reduce then one atomic per warp per counter
-    unsigned int vals[6] = {nAcc, nRej, nRhs, nSeg, nTrialFail, nNodes};
+    unsigned int vals[8] = {L.nAcc, L.nRej, L.nRhs, L.nSeg, L.nTrialFail, L.nNodes, L.nDone,
+                            (L.phase != PH_IDLE && L.phase != PH_FETCH) ? 1u : 0u};
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < 8; k++) {
         unsigned int v = vals[k];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&A.counters[k], (unsigned long long)v);
     }
 }
+#endif
 
 }  // namespace glc

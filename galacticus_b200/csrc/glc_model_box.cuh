@@ -13,7 +13,7 @@
 namespace glc {
 
 struct ModelBox {
-    static __device__ __forceinline__ uint32_t active_mask(int flags) {
+    GLC_DEVICE_INLINE uint32_t active_mask(int flags) {
         uint32_t m = 0;
         if (flags & GLC_F_HAS_DISK)
             m |= (1u << GLC_P_DISK_MASS_STELLAR) | (1u << GLC_P_DISK_ABUND_STELLAR) |
@@ -22,12 +22,12 @@ struct ModelBox {
         return m;
     }
 
-    static __device__ __forceinline__ void solve_analytics(NodeCtx &c, double time) {
+    GLC_DEVICE_INLINE void solve_analytics(NodeCtx &c, double time) {
         // dmoInterpolateDifferentialEvolutionSolveAnalytics, dark_matter_only_mass/interpolate.F90:217-239
         if (c.massRate != 0.0) c.basicMass = c.massTarget + c.massRate * (time - c.timeTarget);
     }
 
-    static __device__ __forceinline__ void scales(const NodeCtx &c, const double (&y)[NY],
+    GLC_DEVICE_INLINE void scales(const NodeCtx &c, const double (&y)[NY],
                                                   double (&s)[NY]) {
         const double scaleAbsoluteMass = 100.0;  // disk/very_simple/_class.F90:137-138
         if (c.flags & GLC_F_HAS_DISK) {
@@ -46,27 +46,28 @@ struct ModelBox {
     }
 
     // returns an interrupt code (GLC_INT_NONE here: the box trees never create components)
-    static __device__ __forceinline__ int rates(NodeCtx &c, double /*time*/, const double (&y)[NY],
-                                                double (&rate)[NY]) {
-        if (!(c.flags & GLC_F_HAS_DISK)) return GLC_INT_NONE;
+    static constexpr bool kHasPostEvolve = false;
+    GLC_DEVICE_INLINE int rates(NodeCtx &c, double /*time*/, const double (&y)[NY], double (&rate)[NY],
+                                bool /*structureOnly*/, bool on) {
+        if (!on || !(c.flags & GLC_F_HAS_DISK)) return GLC_INT_NONE;
         const double massGas = y[GLC_P_DISK_MASS_GAS];
         if (massGas < 0.0) return GLC_INT_NONE;
-        const double tau = c_params.box_timescaleStarFormation;
+        const double tau = GLC_PARAMS.box_timescaleStarFormation;
         const double psi = (tau > 0.0) ? massGas / tau : 0.0;
         // abundances%massToMassFraction, objects/abundances.F90:811-828
         double zFuel = y[GLC_P_DISK_ABUND_GAS];
         zFuel = (zFuel > massGas) ? 1.0 : ((zFuel <= 0.0) ? 0.0 : zFuel / massGas);
-        const double rateMassStellar = (1.0 - c_params.recycledFraction) * psi;
+        const double rateMassStellar = (1.0 - GLC_PARAMS.recycledFraction) * psi;
         const double rateMetalsStellar = zFuel * rateMassStellar;
-        const double rateMetalsFuel = -rateMetalsStellar + c_params.metalYield * psi;
+        const double rateMetalsFuel = -rateMetalsStellar + GLC_PARAMS.metalYield * psi;
         rate[GLC_P_DISK_MASS_STELLAR] += rateMassStellar;
         rate[GLC_P_DISK_MASS_GAS] += -rateMassStellar;
         rate[GLC_P_DISK_ABUND_STELLAR] += rateMetalsStellar;
         rate[GLC_P_DISK_ABUND_GAS] += rateMetalsFuel;
-        if (c_params.box_fractionOutflow > 0.0 && (c.flags & GLC_F_HAS_HOTHALO)) {
+        if (GLC_PARAMS.box_fractionOutflow > 0.0 && (c.flags & GLC_F_HAS_HOTHALO)) {
             const double rateEnergy = kFeedbackEnergyInputAtInfinityCanonical * psi;
             const double outflow =
-                c_params.box_fractionOutflow * rateEnergy / kFeedbackEnergyInputAtInfinityCanonical;
+                GLC_PARAMS.box_fractionOutflow * rateEnergy / kFeedbackEnergyInputAtInfinityCanonical;
             if (outflow > 0.0) {
                 const double abOut = (massGas > 0.0) ? zFuel * outflow : 0.0;
                 rate[GLC_P_HH_MASS] += outflow;
@@ -79,7 +80,7 @@ struct ModelBox {
     }
 
     // Node_Component_Disk_Very_Simple_Post_Step; returns GSL status (Success / Continue / Failure)
-    static __device__ __forceinline__ int post_step(NodeCtx &c, double (&y)[NY]) {
+    GLC_DEVICE_INLINE int post_step(NodeCtx &c, double (&y)[NY]) {
         int status = kGslSuccess;
         if ((c.flags & GLC_F_HAS_DISK) && y[GLC_P_DISK_MASS_GAS] < 0.0) {
             const double massDisk = y[GLC_P_DISK_MASS_GAS] + y[GLC_P_DISK_MASS_STELLAR];
@@ -94,8 +95,7 @@ struct ModelBox {
         return status;
     }
 
-    static __device__ __forceinline__ void pre_evolve(NodeCtx &, double (&)[NY]) {}
-    static __device__ __forceinline__ void post_evolve(NodeCtx &, double (&)[NY]) {}
+    GLC_DEVICE_INLINE void pre_evolve(NodeCtx &, double (&)[NY]) {}
 };
 
 }  // namespace glc

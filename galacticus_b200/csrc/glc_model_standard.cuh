@@ -33,16 +33,16 @@ struct Work {
     bool plausible, solvable;
 };
 
-__device__ __forceinline__ double mass_to_fraction(double ab, double mass) {
+GLC_DEVICE_INLINE double mass_to_fraction(double ab, double mass) {
     // Abundances_Mass_To_Mass_Fraction, objects/abundances.F90:811-828
     return (ab > mass) ? 1.0 : ((ab <= 0.0) ? 0.0 : ab / mass);
 }
-__device__ __forceinline__ double hydrogen_mass_fraction(double z) {
+GLC_DEVICE_INLINE double hydrogen_mass_fraction(double z) {
     // objects/abundances.F90:830-850
     double x = z / kMetallicitySolar * (kHydrogenByMassSolar - kHydrogenByMassPrimordial) + kHydrogenByMassPrimordial;
     return fmin(fmax(x, 0.7), kHydrogenByMassPrimordial);
 }
-__device__ __forceinline__ double hydrogen_number_fraction(double z) {
+GLC_DEVICE_INLINE double hydrogen_number_fraction(double z) {
     const double nh = hydrogen_mass_fraction(z) / kAtomicMassHydrogen;
     const double nhe = fmin(z / kMetallicitySolar * (kHeliumByMassSolar - kHeliumByMassPrimordial) + kHeliumByMassPrimordial,
                             kHeliumByMassPrimordial) / kAtomicMassHelium;
@@ -50,11 +50,11 @@ __device__ __forceinline__ double hydrogen_number_fraction(double z) {
 }
 
 // ------------------------------------------------------------------ CIE tables (CIE_file.F90:665-735)
-__device__ __forceinline__ int locate(const double *__restrict__ x, int n, double v) {
+GLC_DEVICE_INLINE int locate(const double *__restrict__ x, int n, double v) {
     int lo = 0, hi = n - 1;
     while (hi > lo + 1) {
         const int mid = (hi + lo) >> 1;
-        if (__ldg(x + mid) > v)
+        if (GLC_LDG(x + mid) > v)
             hi = mid;
         else
             lo = mid;
@@ -67,13 +67,13 @@ struct CieFactors {
     double hT, hZ;
 };
 
-__device__ __forceinline__ CieFactors cie_factors(const DeviceTable2D &t, bool isLog, bool firstZero,
+GLC_DEVICE_INLINE CieFactors cie_factors(const DeviceTable2D &t, bool isLog, bool firstZero,
                                                   double firstNonzero, double temperature, double metallicity) {
     CieFactors f;
     double tu = isLog ? dm_log(temperature) : temperature;
     int i = min(max(locate(t.x1, t.n1, tu), 1), t.n1 - 1);
     f.iT = i;
-    f.hT = (tu - __ldg(t.x1 + i - 1)) / (__ldg(t.x1 + i) - __ldg(t.x1 + i - 1));
+    f.hT = (tu - GLC_LDG(t.x1 + i - 1)) / (GLC_LDG(t.x1 + i) - GLC_LDG(t.x1 + i - 1));
     double zu = fmax(metallicity, 0.0);
     if (firstZero && zu < firstNonzero) {
         f.iZ = 1;
@@ -82,23 +82,23 @@ __device__ __forceinline__ CieFactors cie_factors(const DeviceTable2D &t, bool i
         if (isLog) zu = dm_log(zu);
         i = min(max(locate(t.x0, t.n0, zu), 1), t.n0 - 1);
         f.iZ = i;
-        f.hZ = (zu - __ldg(t.x0 + i - 1)) / (__ldg(t.x0 + i) - __ldg(t.x0 + i - 1));
+        f.hZ = (zu - GLC_LDG(t.x0 + i - 1)) / (GLC_LDG(t.x0 + i) - GLC_LDG(t.x0 + i - 1));
     }
     return f;
 }
-__device__ __forceinline__ double cie_interpolate(const DeviceTable2D &t, bool isLog, const CieFactors &f) {
+GLC_DEVICE_INLINE double cie_interpolate(const DeviceTable2D &t, bool isLog, const CieFactors &f) {
     const double *a = t.v + (size_t)(f.iZ - 1) * t.n1 + (f.iT - 1);
     const double *b = a + t.n1;
-    const double r = __ldg(a) * (1.0 - f.hT) * (1.0 - f.hZ) + __ldg(b) * (1.0 - f.hT) * f.hZ +
-                     __ldg(a + 1) * f.hT * (1.0 - f.hZ) + __ldg(b + 1) * f.hT * f.hZ;
+    const double r = GLC_LDG(a) * (1.0 - f.hT) * (1.0 - f.hZ) + GLC_LDG(b) * (1.0 - f.hT) * f.hZ +
+                     GLC_LDG(a + 1) * f.hT * (1.0 - f.hZ) + GLC_LDG(b + 1) * f.hT * f.hZ;
     return isLog ? dm_exp(r) : r;
 }
 
 struct ModelStandard {
     // ---------------------------------------------------------------- small accessors
-    static __device__ __forceinline__ bool has(const NodeCtx &c, int f) { return (c.flags & f) != 0; }
+    GLC_DEVICE_INLINE bool has(const NodeCtx &c, int f) { return (c.flags & f) != 0; }
 
-    static __device__ __forceinline__ uint32_t active_mask(int flags) {
+    GLC_DEVICE_INLINE uint32_t active_mask(int flags) {
         uint32_t m = 1u << GLC_P_SAT_BOUND_MASS;
         if (flags & GLC_F_HAS_BH) m |= (1u << GLC_P_BH_MASS) | (1u << GLC_P_BH_SPIN);
         if (flags & GLC_F_HAS_DISK) m |= 0x1fu << GLC_P_DISK_MASS_STELLAR;
@@ -107,7 +107,7 @@ struct ModelStandard {
         return m;
     }
 
-    static __device__ __forceinline__ void solve_analytics(NodeCtx &c, double time) {
+    GLC_DEVICE_INLINE void solve_analytics(NodeCtx &c, double time) {
         // {dmo,dmpScale,haloAngMom}Interpolate...SolveAnalytics (dark_matter_only_mass/interpolate.F90:217-239,
         // dark_matter_profile_scale/interpolate.F90:153-178, halo_angular_momentum_interpolate.F90:147-192)
         if (c.massRate != 0.0) c.basicMass = c.massTarget + c.massRate * (time - c.timeTarget);
@@ -116,19 +116,19 @@ struct ModelStandard {
     }
 
     // ---------------------------------------------------------------- halo scales
-    static __device__ __forceinline__ void halo_scales(const NodeCtx &c, double timeNow, Work &w) {
+    GLC_DEVICE_INLINE void halo_scales(const NodeCtx &c, double timeNow, Work &w) {
         // dark_matter_halos/scales/virial_density_contrast.F90:195-417
         double time = c.timeLastIsolated;
         if (!has(c, GLC_F_IS_SATELLITE) || time <= 0.0) time = timeNow;
-        const DeviceTable2D &t = c_tables.density;
+        const DeviceTable2D &t = GLC_TABLES.density;
         const double lnt = dm_log(time);
-        const double x = (lnt - c_tables.density_lnt0) * c_tables.density_inv_dlnt;
+        const double x = (lnt - GLC_TABLES.density_lnt0) * GLC_TABLES.density_inv_dlnt;
         int i = (int)x;
-        if (lnt < c_tables.density_lnt0) i = 0;
+        if (lnt < GLC_TABLES.density_lnt0) i = 0;
         i = max(min(i, t.n0 - 2), 0);
         const double h = x - (double)i;
-        w.rhoMean = __ldg(t.v + 2 * i) * (1.0 - h) + __ldg(t.v + 2 * (i + 1)) * h;
-        w.dlnrhoDt = __ldg(t.v + 2 * i + 1) * (1.0 - h) + __ldg(t.v + 2 * (i + 1) + 1) * h;
+        w.rhoMean = GLC_LDG(t.v + 2 * i) * (1.0 - h) + GLC_LDG(t.v + 2 * (i + 1)) * h;
+        w.dlnrhoDt = GLC_LDG(t.v + 2 * i + 1) * (1.0 - h) + GLC_LDG(t.v + 2 * (i + 1) + 1) * h;
         w.rvir = dm_cbrt(3.0 * c.basicMass / 4.0 / kPi / w.rhoMean);
         w.vvir = sqrt(kGInternal * c.basicMass / w.rvir);
         w.tdyn = w.rvir / w.vvir * kMpcPerKmPerSToGyr;
@@ -136,16 +136,16 @@ struct ModelStandard {
     }
 
     // ---------------------------------------------------------------- hot halo beta profile (beta = 2/3)
-    static __device__ __forceinline__ double hh_outer_radius(const Work &w, const double (&y)[NY]) {
+    GLC_DEVICE_INLINE double hh_outer_radius(const Work &w, const double (&y)[NY]) {
         // Node_Component_Hot_Halo_Standard_Outer_Radius, hot_halo/standard/_class.F90:430-450
-        return fmax(fmin(y[GLC_P_HH_OUTER_RADIUS], w.rvir), c_params.hotHaloScaleRadiusRelative * w.rvir);
+        return fmax(fmin(y[GLC_P_HH_OUTER_RADIUS], w.rvir), GLC_PARAMS.hotHaloScaleRadiusRelative * w.rvir);
     }
-    static __device__ __forceinline__ void hh_profile(const NodeCtx &c, const double (&y)[NY], Work &w) {
+    GLC_DEVICE_INLINE void hh_profile(const NodeCtx &c, const double (&y)[NY], Work &w) {
         // hot_halo/mass_distribution/beta_profile.F90:140-215; mass_distributions/spherical/beta_profile.F90:190-301
         const bool hh = has(c, GLC_F_HAS_HOTHALO);
         w.hhRouter = hh ? hh_outer_radius(w, y) : 0.0;
         const double mass = hh ? y[GLC_P_HH_MASS] : 0.0;
-        w.hhRcore = c_params.coreRadiusOverVirialRadius * w.rvir;
+        w.hhRcore = GLC_PARAMS.coreRadiusOverVirialRadius * w.rvir;
         w.hhValid = !(w.hhRouter <= 0.0 || mass <= 0.0);
         w.hhRho0 = 0.0;
         if (!w.hhValid) return;
@@ -153,12 +153,12 @@ struct ModelStandard {
         const double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - dm_atan(r));
         w.hhRho0 = mass / 4.0 / kPi / (w.hhRcore * w.hhRcore * w.hhRcore) * nf;
     }
-    static __device__ __forceinline__ double hh_density(const Work &w, double radius) {
+    GLC_DEVICE_INLINE double hh_density(const Work &w, double radius) {
         if (!w.hhValid || radius > w.hhRouter) return 0.0;
         const double x = radius / w.hhRcore;
-        return w.hhRho0 / dm_pow(1.0 + x * x, 1.5 * c_params.hotHaloBeta);
+        return w.hhRho0 / dm_pow(1.0 + x * x, 1.5 * GLC_PARAMS.hotHaloBeta);
     }
-    static __device__ __forceinline__ double hh_mass_enclosed(const Work &w, double radius) {
+    GLC_DEVICE_INLINE double hh_mass_enclosed(const Work &w, double radius) {
         if (!w.hhValid) return 0.0;
         if (radius > w.hhRouter) radius = w.hhRouter;
         const double x = radius / w.hhRcore;
@@ -171,47 +171,47 @@ struct ModelStandard {
     // ---------------------------------------------------------------- cooling
     // CIE table look-ups are done once per RHS call at (T_vir, Z_hot) -- the reference memoises the same
     // way (CIE_file.F90:300-312): only n_H varies along the cooling-radius root find.
-    static __device__ __forceinline__ void cooling_prepare(const double (&y)[NY], Work &w, double &logSlopeT) {
+    GLC_DEVICE_INLINE void cooling_prepare(const double (&y)[NY], Work &w, double &logSlopeT) {
         const double z = mass_to_fraction(y[GLC_P_HH_ABUND], y[GLC_P_HH_MASS]);
-        const DeviceTable2D &tc = c_tables.cooling;
-        const DeviceTable2D &te = c_tables.electron;
+        const DeviceTable2D &tc = GLC_TABLES.cooling;
+        const DeviceTable2D &te = GLC_TABLES.electron;
         double tu = w.tvir, zu = z / kMetallicitySolar;
         bool outsideT = false;
-        if (tu < c_tables.cooling_t_min) {
-            tu = c_tables.cooling_t_min;
+        if (tu < GLC_TABLES.cooling_t_min) {
+            tu = GLC_TABLES.cooling_t_min;
             outsideT = true;
         }
-        if (tu > c_tables.cooling_t_max) {
-            tu = c_tables.cooling_t_max;
+        if (tu > GLC_TABLES.cooling_t_max) {
+            tu = GLC_TABLES.cooling_t_max;
             outsideT = true;
         }
-        zu = fmin(fmax(zu, c_tables.cooling_z_min), c_tables.cooling_z_max);
-        const CieFactors f = cie_factors(tc, c_tables.cooling_log, c_tables.cooling_first_z_zero,
-                                         c_tables.cooling_first_nonzero_z, tu, zu);
-        const double lambda = cie_interpolate(tc, c_tables.cooling_log, f);
+        zu = fmin(fmax(zu, GLC_TABLES.cooling_z_min), GLC_TABLES.cooling_z_max);
+        const CieFactors f = cie_factors(tc, GLC_TABLES.cooling_log, GLC_TABLES.cooling_first_z_zero,
+                                         GLC_TABLES.cooling_first_nonzero_z, tu, zu);
+        const double lambda = cie_interpolate(tc, GLC_TABLES.cooling_log, f);
         if (outsideT)
             logSlopeT = 0.0;
         else {
             // cieFileCoolingFunctionTemperatureLogSlope :410-512
             const double *a = tc.v + (size_t)(f.iZ - 1) * tc.n1 + (f.iT - 1);
             const double *b = a + tc.n1;
-            double s = ((__ldg(a + 1) - __ldg(a)) * (1.0 - f.hZ) + (__ldg(b + 1) - __ldg(b)) * f.hZ) /
-                       (__ldg(tc.x1 + f.iT) - __ldg(tc.x1 + f.iT - 1));
-            if (!c_tables.cooling_log) s = s * w.tvir / lambda;
+            double s = ((GLC_LDG(a + 1) - GLC_LDG(a)) * (1.0 - f.hZ) + (GLC_LDG(b + 1) - GLC_LDG(b)) * f.hZ) /
+                       (GLC_LDG(tc.x1 + f.iT) - GLC_LDG(tc.x1 + f.iT - 1));
+            if (!GLC_TABLES.cooling_log) s = s * w.tvir / lambda;
             logSlopeT = s;
         }
-        double te_t = fmin(fmax(w.tvir, c_tables.electron_t_min), c_tables.electron_t_max);
-        double te_z = fmin(fmax(z / kMetallicitySolar, c_tables.electron_z_min), c_tables.electron_z_max);
-        const CieFactors fe = cie_factors(te, c_tables.electron_log, c_tables.electron_first_z_zero,
-                                          c_tables.electron_first_nonzero_z, te_t, te_z);
-        const double efrac = cie_interpolate(te, c_tables.electron_log, fe);
+        double te_t = fmin(fmax(w.tvir, GLC_TABLES.electron_t_min), GLC_TABLES.electron_t_max);
+        double te_z = fmin(fmax(z / kMetallicitySolar, GLC_TABLES.electron_z_min), GLC_TABLES.electron_z_max);
+        const CieFactors fe = cie_factors(te, GLC_TABLES.electron_log, GLC_TABLES.electron_first_z_zero,
+                                          GLC_TABLES.electron_first_nonzero_z, te_t, te_z);
+        const double efrac = cie_interpolate(te, GLC_TABLES.electron_log, fe);
         w.coolLambda = lambda;
         w.coolEfrac = efrac;
         w.coolXH = hydrogen_mass_fraction(z);
         w.coolFHn = hydrogen_number_fraction(z);
         w.coolTavail = w.tdyn;  // whiteFrenk1991TimeAvailable, ageFactor = 0 (time_available/White-Frenk.F90:144-146)
     }
-    static __device__ __forceinline__ double cooling_time(const Work &w, double density) {
+    GLC_DEVICE_INLINE double cooling_time(const Work &w, double density) {
         // coolingTimeSimple::time, cooling/cooling_time/simple.F90:128-179
         const double timeLarge = 1.0e10;
         const double nh = density * w.coolXH * kMassSolar / kMassHydrogenAtom / (kHecto * kHecto * kHecto) /
@@ -219,45 +219,62 @@ struct ModelStandard {
         const double nall = nh / w.coolFHn + w.coolEfrac * nh;
         const double cf = w.coolLambda * nh * nh;
         if (cf > 0.0) {
-            const double e = c_params.coolingDegreesOfFreedom / 2.0 * kBoltzmann * w.tvir * nall / kErgs;
+            const double e = GLC_PARAMS.coolingDegreesOfFreedom / 2.0 * kBoltzmann * w.tvir * nall / kErgs;
             return e / cf / kGigaYear;
         }
         return timeLarge;
     }
-    static __device__ __forceinline__ double cooling_radius(const double (&y)[NY], Work &w, int &bad) {
-        // coolingRadiusSimple::radius, cooling/cooling_radius/simple.F90:313-387
+    GLC_DEVICE_INLINE double cooling_radius(const double (&y)[NY], Work &w, int &bad, bool on) {
+        // coolingRadiusSimple::radius, cooling/cooling_radius/simple.F90:313-387   [warp-synchronous]
         const double router = w.hhRouter;
-        const double rootOuter = cooling_time(w, hh_density(w, router)) - w.coolTavail;
-        if (rootOuter < 0.0) return router;
-        const double rootZero = cooling_time(w, hh_density(w, 0.0)) - w.coolTavail;
-        if (rootZero > 0.0) return 0.0;
+        double result = 0.0, rootOuter = 0.0, rootZero = 0.0;
+        bool need = false;
+        if (on) {
+            rootOuter = cooling_time(w, hh_density(w, router)) - w.coolTavail;
+            if (rootOuter < 0.0)
+                result = router;
+            else {
+                rootZero = cooling_time(w, hh_density(w, 0.0)) - w.coolTavail;
+                if (rootZero > 0.0)
+                    result = 0.0;
+                else
+                    need = true;
+            }
+        }
         const RootOptions o{0.0, 1.0e-6, EXPAND_NONE, 0.0, 0.0, SIGN_NONE, SIGN_NONE};
         int st;
-        const double r = root_find([&](double radius) { return cooling_time(w, hh_density(w, radius)) - w.coolTavail; },
-                                   o, 0.0, router, true, rootZero, rootOuter, st);
-        if (st != 0) bad = 1;
-        return r;
+        const double r = root_find(
+            [&](double radius) {
+                GLC_COUNT(3);
+                return cooling_time(w, hh_density(w, radius)) - w.coolTavail;
+            },
+            need, o, 0.0, router, true, rootZero, rootOuter, st);
+        if (need) {
+            result = r;
+            if (st != 0) bad = 1;
+        }
+        return result;
     }
 
     // ---------------------------------------------------------------- galactic structure
-    static __device__ __forceinline__ double disk_mass(const double (&y)[NY]) {
+    GLC_DEVICE_INLINE double disk_mass(const double (&y)[NY]) {
         return fmax(0.0, y[GLC_P_DISK_MASS_STELLAR]) + fmax(0.0, y[GLC_P_DISK_MASS_GAS]);
     }
-    static __device__ __forceinline__ double sph_mass(const double (&y)[NY]) {
+    GLC_DEVICE_INLINE double sph_mass(const double (&y)[NY]) {
         return fmax(0.0, y[GLC_P_SPH_MASS_STELLAR]) + fmax(0.0, y[GLC_P_SPH_MASS_GAS]);
     }
-    static __device__ __forceinline__ double disk_bessel_factor(double halfRadius) {
+    GLC_DEVICE_INLINE double disk_bessel_factor(double halfRadius) {
         // exponentialDiskBesselFactorRotationCurve, mass_distributions/cylindrical/exponential_disk.F90:675-733
         const double ln2 = 0.69314718055994530942, euler = 0.57721566490153286061;
         if (halfRadius <= 0.0) return 0.0;
         if (halfRadius < 1.0e-3) return (ln2 - euler - 0.5 - dm_log(halfRadius)) * halfRadius * halfRadius;
-        const DeviceTable2D &t = c_tables.diskrc;
-        const double x = (dm_log(halfRadius) - c_tables.diskrc_lnx0) * c_tables.diskrc_inv_dlnx;
+        const DeviceTable2D &t = GLC_TABLES.diskrc;
+        const double x = (dm_log(halfRadius) - GLC_TABLES.diskrc_lnx0) * GLC_TABLES.diskrc_inv_dlnx;
         const int i = max(min((int)x, t.n0 - 2), 0);
         const double h = x - (double)i;
-        return __ldg(t.v + i) * (1.0 - h) + __ldg(t.v + i + 1) * h;
+        return GLC_LDG(t.v + i) * (1.0 - h) + GLC_LDG(t.v + i + 1) * h;
     }
-    static __device__ __forceinline__ double baryonic_vc2(const NodeCtx &c, const double (&y)[NY], const Work &w,
+    GLC_DEVICE_INLINE double baryonic_vc2(const NodeCtx &c, const double (&y)[NY], const Work &w,
                                                           double radius) {
         // rotation curve of massType=massTypeBaryonic: disk + spheroid + hot halo (gas + stars)
         double v2 = 0.0;
@@ -276,74 +293,80 @@ struct ModelStandard {
         if (has(c, GLC_F_HAS_HOTHALO)) v2 += kGInternal * hh_mass_enclosed(w, radius) / radius;
         return v2;
     }
-    static __device__ __forceinline__ double nfw_mass_scale_free(double x) {
+    GLC_DEVICE_INLINE double nfw_mass_scale_free(double x) {
         // massEnclosedScaleFree, mass_distributions/spherical/NFW.F90:550-571
         if (x == 1.0) return dm_log(2.0) - 0.5;
         if (x >= 1.0e-6) return dm_log(1.0 + x) - x / (1.0 + x);
         return x * x * (0.5 + x * (-2.0 / 3.0 + x * (0.75 + x * (-0.8))));
     }
     // NFW M(<r) = nfwNorm * m(r/rs), nfwNorm = M_vir / m(c)  (NFW.F90:254-255,444-464)
-    static __device__ __forceinline__ double nfw_norm(const NodeCtx &c, const Work &w) {
+    GLC_DEVICE_INLINE double nfw_norm(const NodeCtx &c, const Work &w) {
         const double conc = w.rvir / c.dmScale;
         return c.basicMass / (dm_log(1.0 + conc) - conc / (1.0 + conc));
     }
-    static __device__ __forceinline__ double nfw_mass(double nfwNorm, double rs, double radius) {
+    GLC_DEVICE_INLINE double nfw_mass(double nfwNorm, double rs, double radius) {
         return nfwNorm * nfw_mass_scale_free(radius / rs);
     }
-    static __device__ __forceinline__ double ac_orbital_mean(const Work &w, double radius) {
+    GLC_DEVICE_INLINE double ac_orbital_mean(const Work &w, double radius) {
         // sphericalAdiabaticGnedin2004RadiusOrbitalMean, adiabatic_Gnedin2004.F90:664-687
-        return c_params.adiabaticA * w.rvir * fast_exponentiate(1.0e-3, 1.0, c_params.adiabaticOmega, 1.0e4, radius / w.rvir);
+        return GLC_PARAMS.adiabaticA * w.rvir *
+               fast_exponentiate(GLC_TABLES.powAc, GLC_TABLES.powAcN, 1.0e-3, 1.0, GLC_PARAMS.adiabaticOmega, radius / w.rvir);
     }
-    static __device__ __forceinline__ double baryonic_mass_self(const NodeCtx &c, const double (&y)[NY]) {
+    GLC_DEVICE_INLINE double baryonic_mass_self(const NodeCtx &c, const double (&y)[NY]) {
         double m = 0.0;
         if (has(c, GLC_F_HAS_DISK)) m += disk_mass(y);
         if (has(c, GLC_F_HAS_SPHEROID)) m += sph_mass(y);
         if (has(c, GLC_F_HAS_HOTHALO)) m += fmax(0.0, y[GLC_P_HH_MASS]) + fmax(0.0, y[GLC_P_HH_OUTFLOWED_MASS]);
         return m;
     }
-    static __device__ __forceinline__ double dark_matter_mass_enclosed(const NodeCtx &c, const double (&y)[NY],
-                                                                       const Work &w, double nfwNorm, double radius,
-                                                                       int &bad) {
+    GLC_DEVICE_INLINE double dark_matter_mass_enclosed(const NodeCtx &c, const double (&y)[NY], const Work &w,
+                                                       double nfwNorm, double radius, int &bad, bool on) {
         // adiabaticGnedin2004 over NFW: mass_distributions/spherical/adiabatic_Gnedin2004.F90:410-530,707-727;
-        // dark_matter_profiles/adiabatic_Gnedin2004.F90:302-364
+        // dark_matter_profiles/adiabatic_Gnedin2004.F90:302-364   [warp-synchronous]
         const double rs = c.dmScale;
-        const double fDm = 1.0 - c_params.OmegaBaryon / c_params.OmegaMatter;
-        if (!c_params.adiabaticContraction) return nfw_mass(nfwNorm, rs, radius);
-        if (radius <= 0.0) return 0.0;
-        double rInit;
-        if (radius >= w.rvir)
-            rInit = radius;
-        else {
+        const double fDm = 1.0 - GLC_PARAMS.OmegaBaryon / GLC_PARAMS.OmegaMatter;
+        if (!GLC_PARAMS.adiabaticContraction) return on ? nfw_mass(nfwNorm, rs, radius) : 0.0;
+        const bool live = on && !(radius <= 0.0);
+        double rInit = radius, fd = 0.0, fi = 0.0, bterm = 0.0, rup = radius;
+        bool need = false;
+        if (live && !(radius >= w.rvir)) {
             const double mSelfRaw = baryonic_mass_self(c, y);
             const double mSelf = fmax(mSelfRaw, 0.0);
             const double mTot = fmax(mSelfRaw + c.massBaryonicSubhalos, 0.0);
-            const double fd = fmin(fDm + (mTot - mSelf) / c.basicMass, 1.0);
-            const double fi = fmin(fDm + mTot / c.basicMass, 1.0);
+            fd = fmin(fDm + (mTot - mSelf) / c.basicMass, 1.0);
+            fi = fmin(fDm + mTot / c.basicMass, 1.0);
             const double rmean = ac_orbital_mean(w, radius);
-            const double bterm = baryonic_vc2(c, y, w, rmean) * rmean * radius / kGInternal;
-            auto solver = [&](double ri) {
-                return nfw_mass(nfwNorm, rs, ac_orbital_mean(w, ri)) * (fi * ri - fd * radius) - bterm;
-            };
+            bterm = baryonic_vc2(c, y, w, rmean) * rmean * radius / kGInternal;
             const double menc = nfw_mass(nfwNorm, rs, rmean);
-            double rup = radius;
             if (menc > 0.0) rup = fmax((bterm / menc + fd * radius) / fi, radius);
             // the reference first tests solver(r_vir) < 0 (:463-466)
-            const RootOptions o{0.0, 1.0e-2, EXPAND_MULTIPLICATIVE, 1.1, 0.9, SIGN_POSITIVE, SIGN_NEGATIVE};
-            int st = 0;
-            const double fVir = solver(w.rvir);
+            const double fVir = nfw_mass(nfwNorm, rs, ac_orbital_mean(w, w.rvir)) * (fi * w.rvir - fd * radius) - bterm;
             if (fVir < 0.0)
                 rInit = w.rvir;
-            else {
-                rInit = root_find(solver, o, radius, rup, false, 0.0, 0.0, st);
-                if (st != 0) bad = 1;
-            }
+            else
+                need = true;
         }
-        return fDm * nfw_mass(nfwNorm, rs, rInit);
+        const RootOptions o{0.0, 1.0e-2, EXPAND_MULTIPLICATIVE, 1.1, 0.9, SIGN_POSITIVE, SIGN_NEGATIVE};
+        int st = 0;
+        const double root = root_find(
+            [&](double ri) {
+                GLC_COUNT(0);
+                return nfw_mass(nfwNorm, rs, ac_orbital_mean(w, ri)) * (fi * ri - fd * radius) - bterm;
+            },
+            need,
+            o, radius, rup, false, 0.0, 0.0, st);
+        if (need) {
+            rInit = root;
+            if (st != 0) bad = 1;
+        }
+        return live ? fDm * nfw_mass(nfwNorm, rs, rInit) : 0.0;
     }
-    static __device__ __forceinline__ double nfw_radius_from_j(const NodeCtx &c, const Work &w, double nfwNorm, double j) {
+    GLC_DEVICE_INLINE double nfw_radius_from_j(const NodeCtx &c, const Work &w, double nfwNorm, double j, bool on) {
         // stands in for nfwRadiusFromSpecificAngularMomentum (NFW.F90:589-625): solve j = sqrt(G M(<r) r)
-        if (!(j > 0.0)) return 0.0;
-        const double lnj = dm_log(j), rs = c.dmScale;
+        // [warp-synchronous]
+        const bool live = on && (j > 0.0);
+        const double lnj = live ? dm_log(j) : 0.0, rs = c.dmScale;
+        const double lnrv = live ? dm_log(w.rvir) : 0.0;
         const RootOptions o{1.0e-12, 0.0, EXPAND_ADDITIVE, 2.0, -2.0, SIGN_POSITIVE, SIGN_NEGATIVE};
         int st;
         const double lnr = root_find(
@@ -351,10 +374,11 @@ struct ModelStandard {
                 const double r = dm_exp(lr);
                 return 0.5 * dm_log(kGInternal * nfw_mass(nfwNorm, rs, r) * r) - lnj;
             },
-            o, dm_log(w.rvir) - 4.0, dm_log(w.rvir), false, 0.0, 0.0, st);
+            live, o, lnrv - 4.0, lnrv, false, 0.0, 0.0, st);
+        if (!live) return 0.0;
         return (st != 0) ? w.rvir : dm_exp(lnr);
     }
-    static __device__ __forceinline__ void plausibility(const NodeCtx &c, const double (&y)[NY], double time, Work &w) {
+    GLC_DEVICE_INLINE void plausibility(const NodeCtx &c, const double (&y)[NY], double time, Work &w) {
         // basic/standard/_class.F90:105-123; disk/standard/_class.F90:999-1049; spheroid/standard/_class.F90:1249-1296
         w.plausible = true;
         w.solvable = true;
@@ -374,51 +398,69 @@ struct ModelStandard {
             if (m >= 0.0 && j > 0.0 && (j > 1.0e1 * s || j < 1.0e-6 * s)) w.plausible = false;
         }
     }
-    static __device__ __forceinline__ double component_j(const double (&y)[NY], int comp) {
+    GLC_DEVICE_INLINE double component_j(const double (&y)[NY], int comp) {
         // disk/standard/_class.F90:1112-1177 (ratio 1/2 for the exponential disk :345-356);
         // spheroid/standard/_class.F90:1359-1407
         const double j = comp == 0 ? y[GLC_P_DISK_ANGMOM] : y[GLC_P_SPH_ANGMOM];
         const double m = comp == 0 ? y[GLC_P_DISK_MASS_GAS] + y[GLC_P_DISK_MASS_STELLAR]
                                    : y[GLC_P_SPH_MASS_GAS] + y[GLC_P_SPH_MASS_STELLAR];
         if (!(j >= 0.0)) return 0.0;
-        const double ratio = comp == 0 ? 0.5 : c_params.spheroidRatioAngularMomentumScaleRadius;
+        const double ratio = comp == 0 ? 0.5 : GLC_PARAMS.spheroidRatioAngularMomentumScaleRadius;
         return ratio * ((m > 0.0) ? j / m : 0.0);
     }
     // galacticStructureSolverEquilibrium::solve, galactic_structure/radius_solver/equilibrium.F90:243-506
-    static __device__ __forceinline__ void structure_solve(NodeCtx &c, const double (&y)[NY], double time, Work &w,
-                                                           int &bad) {
-        plausibility(c, y, time, w);
-        if (!w.plausible) return;
-        const double tolerance = c_params.structureSolutionTolerance;
-        const double nfwNorm = nfw_norm(c, w);
+    // [warp-synchronous: all lanes iterate together, a lane drops out when its own fixed point has converged]
+    GLC_DEVICE_INLINE void structure_solve(NodeCtx &c, const double (&y)[NY], double time, Work &w, int &bad, bool on) {
+        w.plausible = false;
+        w.solvable = false;
+        if (on) plausibility(c, y, time, w);
+        const double tolerance = GLC_PARAMS.structureSolutionTolerance;
+        bool looping = on && w.plausible;
+        const double nfwNorm = looping ? nfw_norm(c, w) : 0.0;
         double hist00 = -1.0, hist01 = -1.0, hist10 = -1.0, hist11 = -1.0;
         double fit = 2.0 * tolerance;
         int count = 0;
-        while (count <= 1 || (fit > tolerance && count < 100)) {
+        while (GLC_ANY(looping)) {
             int active = 0;
-            count++;
-            if (count > 1) fit = 0.0;
+            if (looping) {
+                GLC_COUNT(1);
+                count++;
+                if (count > 1) fit = 0.0;
+            }
 #pragma unroll 1
             for (int comp = 0; comp < 2; comp++) {
-                if (!has(c, comp == 0 ? GLC_F_HAS_DISK : GLC_F_HAS_SPHEROID)) continue;
-                const double j = component_j(y, comp);
-                double radius, velocity;
-                active++;
-                if (count == 1) {
+                const bool compOn = looping && has(c, comp == 0 ? GLC_F_HAS_DISK : GLC_F_HAS_SPHEROID);
+                const double j = compOn ? component_j(y, comp) : 0.0;
+                double radius = 0.0, velocity = 0.0;
+                if (compOn) active++;
+                // ---- first pass: previous solution or a first guess from the dark-matter-only rotation curve
+                const bool first = compOn && count == 1;
+                bool guess = false, needRoot = false;
+                if (first) {
                     radius = comp == 0 ? c.diskRadius : c.sphRadius;
                     if (radius <= 0.0) {
                         const double radiusLarge = 1.0e10;
                         const double jmax = sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radiusLarge) / radiusLarge) * radiusLarge;
-                        radius = (jmax < j) ? w.rvir : nfw_radius_from_j(c, w, nfwNorm, j);
-                        velocity = (radius > 0.0) ? sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radius) / radius) : 0.0;
+                        guess = true;
+                        if (jmax < j)
+                            radius = w.rvir;
+                        else
+                            needRoot = true;
                     } else
                         velocity = comp == 0 ? c.diskVelocity : c.sphVelocity;
-                } else {
-                    if (j <= 0.0) continue;
-                    radius = comp == 0 ? c.diskRadius : c.sphRadius;
-                    const double mdm = dark_matter_mass_enclosed(c, y, w, nfwNorm, radius, bad);
+                }
+                const double rGuess = nfw_radius_from_j(c, w, nfwNorm, j, needRoot);
+                if (guess) {
+                    if (needRoot) radius = rGuess;
+                    velocity = (radius > 0.0) ? sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radius) / radius) : 0.0;
+                }
+                // ---- later passes: one fixed-point update in the current potential
+                const bool later = compOn && count > 1 && !(j <= 0.0);
+                if (later) radius = comp == 0 ? c.diskRadius : c.sphRadius;
+                const double mdm = dark_matter_mass_enclosed(c, y, w, nfwNorm, radius, bad, later);
+                if (later) {
                     const double vdm2 = kGInternal * mdm / radius;
-                    const double vb2 = c_params.includeBaryonGravity ? baryonic_vc2(c, y, w, radius) : 0.0;
+                    const double vb2 = GLC_PARAMS.includeBaryonGravity ? baryonic_vc2(c, y, w, radius) : 0.0;
                     velocity = sqrt(vdm2 + vb2);
                     const double radiusNew = (radius > 0.0) ? sqrt(j / velocity * radius) : j / velocity;
                     double &h0 = comp == 0 ? hist00 : hist10;
@@ -438,30 +480,36 @@ struct ModelStandard {
                     radius = radiusNew;
                     if (!(radius > 0.0)) bad = 1;
                 }
-                if (comp == 0) {
-                    c.diskRadius = fmax(radius, 0.0);
-                    c.diskVelocity = velocity;
-                } else {
-                    c.sphRadius = fmax(radius, 0.0);
-                    c.sphVelocity = velocity;
+                if (first || later) {
+                    if (comp == 0) {
+                        c.diskRadius = fmax(radius, 0.0);
+                        c.diskVelocity = velocity;
+                    } else {
+                        c.sphRadius = fmax(radius, 0.0);
+                        c.sphVelocity = velocity;
+                    }
                 }
             }
-            if (active == 0) {
-                fit = 0.0;
-                break;
+            if (looping) {
+                if (active == 0) {
+                    fit = 0.0;
+                    looping = false;
+                } else {
+                    fit /= (double)active;
+                    looping = count <= 1 || (fit > tolerance && count < 100);
+                }
             }
-            fit /= (double)active;
         }
     }
 
     // ---------------------------------------------------------------- star formation in disks
-    static __device__ __forceinline__ double kmt_fh2_fast(double s) {
+    GLC_DEVICE_INLINE double kmt_fh2_fast(double s) {
         return (s < 2.0) ? 1.0 - 0.75 * s / (1.0 + 0.25 * s) : 0.0;  // Krumholz2009.F90:462-476
     }
     struct Kmt {
         double xh, zsolar, sigmaNorm, sNorm, sigmaTrunc, sigma0, rdisk;  // sigma0 = M_gas/(2 pi Rd^2)
     };
-    static __device__ __forceinline__ double kmt_rate(const Kmt &k, double radius) {
+    GLC_DEVICE_INLINE double kmt_rate(const Kmt &k, double radius) {
         // krumholz2009Rate :360-414 with the exponential-disk surface density (exponential_disk.F90:484-499)
         const double sg = k.sigma0 * dm_exp(-radius / k.rdisk);
         const double sgd = k.xh * sg / 85.0e12;
@@ -473,78 +521,93 @@ struct ModelStandard {
         if (sgd <= 0.0)
             factor = 0.0;
         else
-            factor = fast_exponentiate(1.0, 1000.0, 0.33, 100.0, (sgd < 1.0) ? 1.0 / sgd : sgd);
-        return c_params.frequencyStarFormation * sg * factor * fh2;
+            factor = fast_exponentiate(GLC_TABLES.powKmt, GLC_TABLES.powKmtN, 1.0, 1000.0, 0.33, (sgd < 1.0) ? 1.0 / sgd : sgd);
+        return GLC_PARAMS.frequencyStarFormation * sg * factor * fh2;
     }
     // starFormationRateDisksIntgrtdSurfaceDensity::rate (rates/disks/integrated_surface_density.F90:131-190)
     // with krumholz2009Intervals (rate_surface_density/disks/Krumholz2009.F90:478-587)
-    static __device__ __forceinline__ double sfr_disk(const NodeCtx &c, const double (&y)[NY], int &bad) {
+    GLC_DEVICE_INLINE double sfr_disk(const NodeCtx &c, const double (&y)[NY], int &bad, bool on) {
+        // [warp-synchronous]
         const double mgas = y[GLC_P_DISK_MASS_GAS], rdisk = c.diskRadius;
-        if (mgas <= 0.0 || rdisk <= 0.0) return 0.0;
+        bool live = on && !(mgas <= 0.0 || rdisk <= 0.0);
         Kmt k;
-        const double z = mass_to_fraction(y[GLC_P_DISK_ABUND_GAS], mgas);
-        k.xh = hydrogen_mass_fraction(z);
-        k.zsolar = z / kMetallicitySolar;
-        k.rdisk = rdisk;
-        k.sigma0 = fmax(0.0, mgas) / (2.0 * kPi * rdisk * rdisk);
-        if (!(k.zsolar > 0.0)) return 0.0;
-        const double chi = 0.77 * (1.0 + 3.1 * dm_pow(k.zsolar, 0.365));
-        k.sigmaNorm = k.xh * c_params.clumpingFactorMolecularComplex / (kMega * kMega);
-        k.sNorm = dm_log(1.0 + 0.6 * chi + 0.01 * chi * chi) / (0.04 * k.zsolar);
-        if (!(k.sigmaNorm > 0.0)) return 0.0;
-        k.sigmaTrunc = k.sNorm / k.sigmaNorm / c_params.krumholzSTruncation;
+        k.xh = k.zsolar = k.sigmaNorm = k.sNorm = k.sigmaTrunc = k.sigma0 = 0.0;
+        k.rdisk = 1.0;
+        if (live) {
+            const double z = mass_to_fraction(y[GLC_P_DISK_ABUND_GAS], mgas);
+            k.xh = hydrogen_mass_fraction(z);
+            k.zsolar = z / kMetallicitySolar;
+            k.rdisk = rdisk;
+            k.sigma0 = fmax(0.0, mgas) / (2.0 * kPi * rdisk * rdisk);
+            if (!(k.zsolar > 0.0)) live = false;
+        }
+        if (live) {
+            const double chi = 0.77 * (1.0 + 3.1 * dm_pow(k.zsolar, 0.365));
+            k.sigmaNorm = k.xh * GLC_PARAMS.clumpingFactorMolecularComplex / (kMega * kMega);
+            k.sNorm = dm_log(1.0 + 0.6 * chi + 0.01 * chi * chi) / (0.04 * k.zsolar);
+            if (!(k.sigmaNorm > 0.0)) live = false;
+        }
         const double rIn = 0.0, rOut = 10.0 * rdisk;
         auto sigma = [&](double r) { return k.sigma0 * dm_exp(-r / k.rdisk); };
-        double sg = sigma(rIn);
-        const double sgdIn = k.xh * sg / 85.0e12;
-        if (sg <= k.sigmaTrunc) return 0.0;
-        sg = sigma(rOut);
-        double sgd = k.xh * sg / 85.0e12;
-        double rMax = rOut;
+        double sgdIn = 0.0, sgd = 0.0, rMax = rOut;
+        bool needRmax = false;
+        if (live) {
+            k.sigmaTrunc = k.sNorm / k.sigmaNorm / GLC_PARAMS.krumholzSTruncation;
+            double sg = sigma(rIn);
+            sgdIn = k.xh * sg / 85.0e12;
+            if (sg <= k.sigmaTrunc)
+                live = false;
+            else {
+                sg = sigma(rOut);
+                sgd = k.xh * sg / 85.0e12;
+                needRmax = sg <= k.sigmaTrunc;
+            }
+        }
         const RootOptions o{0.0, 1.0e-4, EXPAND_MULTIPLICATIVE, 2.0, 0.5, SIGN_NEGATIVE, SIGN_POSITIVE};
         int st;
-        if (sg <= k.sigmaTrunc) {
-            rMax = root_find([&](double r) { return sigma(r) - k.sigmaTrunc; }, o, rIn, rOut, false, 0.0, 0.0, st);
+        const double rTrunc = root_find([&](double r) { return sigma(r) - k.sigmaTrunc; }, needRmax, o, rIn, rOut, false,
+                                        0.0, 0.0, st);
+        if (needRmax) {
+            rMax = rTrunc;
             if (st != 0) bad = 1;
             sgd = k.xh * sigma(rMax) / 85.0e12;
         }
-        double lo[2], hi[2];
-        int nIv;
-        if (sgdIn <= 1.0 || sgd >= 1.0) {
-            lo[0] = rIn;
-            hi[0] = rMax;
-            nIv = 1;
-        } else {
-            const double rCrit =
-                root_find([&](double r) { return k.xh * sigma(r) / 85.0e12 - 1.0; }, o, rIn, rMax, false, 0.0, 0.0, st);
-            if (st != 0) bad = 1;
-            lo[0] = rIn;
-            hi[0] = rCrit;
-            lo[1] = rCrit;
-            hi[1] = rMax;
-            nIv = 2;
-        }
+        const bool two = live && !(sgdIn <= 1.0 || sgd >= 1.0);
+        const double rCrit = root_find([&](double r) { return k.xh * sigma(r) / 85.0e12 - 1.0; }, two, o, rIn, rMax, false,
+                                       0.0, 0.0, st);
+        if (two && st != 0) bad = 1;
+        double lo[2] = {rIn, rCrit}, hi[2] = {two ? rCrit : rMax, rMax};
+        const int nIv = two ? 2 : 1;
         double total = 0.0;
 #pragma unroll 1
-        for (int i = 0; i < nIv; i++) {
-            total += qag15([&](double r) { return r * kmt_rate(k, r); }, lo[i], hi[i], 1.0e-12,
-                           c_params.sfrIntegrationTolerance, st);
-            if (st == 11) bad = 1;
+        for (int i = 0; i < 2; i++) {
+            const bool ion = live && i < nIv;
+            const double v = qag15(
+                [&](double r) {
+                    GLC_COUNT(2);
+                    return r * kmt_rate(k, r);
+                },
+                ion, lo[i], hi[i], 1.0e-12,
+                                   GLC_PARAMS.sfrIntegrationTolerance, st);
+            if (ion) {
+                total += v;
+                if (st == 11) bad = 1;
+            }
         }
-        return 2.0 * kPi * total;
+        return live ? 2.0 * kPi * total : 0.0;
     }
-    static __device__ __forceinline__ double sfr_spheroid(const NodeCtx &c, const double (&y)[NY]) {
+    GLC_DEVICE_INLINE double sfr_spheroid(const NodeCtx &c, const double (&y)[NY]) {
         // rates/spheroids/timescale.F90:109-130 + timescales/dynamical_time.F90:121-189
         const double v = c.sphVelocity, r = c.sphRadius;
-        if (v <= 0.0 || c_params.sfSpheroidEfficiency == 0.0) return 0.0;
-        const double tau = fmax(kMpcPerKmPerSToGyr * r / v * dm_pow(v / 200.0, c_params.sfSpheroidExponentVelocity) /
-                                    c_params.sfSpheroidEfficiency,
-                                c_params.sfSpheroidTimescaleMinimum);
+        if (v <= 0.0 || GLC_PARAMS.sfSpheroidEfficiency == 0.0) return 0.0;
+        const double tau = fmax(kMpcPerKmPerSToGyr * r / v * dm_pow(v / 200.0, GLC_PARAMS.sfSpheroidExponentVelocity) /
+                                    GLC_PARAMS.sfSpheroidEfficiency,
+                                GLC_PARAMS.sfSpheroidTimescaleMinimum);
         return (tau > 0.0) ? y[GLC_P_SPH_MASS_GAS] / tau : 0.0;
     }
 
     // ---------------------------------------------------------------- scales (scaleSetTask hooks)
-    static __device__ __forceinline__ void scales(const NodeCtx &c, const double (&y)[NY], double (&s)[NY]) {
+    GLC_DEVICE_INLINE void scales(const NodeCtx &c, const double (&y)[NY], double (&s)[NY]) {
         Work w;
         halo_scales(c, c.timeNode, w);
         s[GLC_P_SAT_BOUND_MASS] = 1.0e-6 * c.basicMass;  // satellite/standard.F90:209-232
@@ -572,19 +635,19 @@ struct ModelStandard {
         }
         if (has(c, GLC_F_HAS_HOTHALO)) {
             // hot_halo/standard/_class.F90:804-850
-            const double sm = c.basicMass * c_params.hotHaloScaleMassRelative;
-            const double sj = c.basicMass * w.rvir * w.vvir * c_params.hotHaloScaleMassRelative;
+            const double sm = c.basicMass * GLC_PARAMS.hotHaloScaleMassRelative;
+            const double sj = c.basicMass * w.rvir * w.vvir * GLC_PARAMS.hotHaloScaleMassRelative;
             s[GLC_P_HH_MASS] = s[GLC_P_HH_OUTFLOWED_MASS] = s[GLC_P_HH_UNACCRETED_MASS] = sm;
             s[GLC_P_HH_ABUND] = s[GLC_P_HH_UNACCRETED_ABUND] = s[GLC_P_HH_OUTFLOWED_ABUND] = sm;
             s[GLC_P_HH_ANGMOM] = s[GLC_P_HH_OUTFLOWED_ANGMOM] = sj;
-            s[GLC_P_HH_OUTER_RADIUS] = w.rvir * c_params.hotHaloScaleRadiusRelative;
+            s[GLC_P_HH_OUTER_RADIUS] = w.rvir * GLC_PARAMS.hotHaloScaleRadiusRelative;
             const double ss = has(c, GLC_F_IS_SATELLITE) ? sm : 1.0;
             s[GLC_P_HH_STRIPPED_MASS] = s[GLC_P_HH_STRIPPED_ABUND] = ss;
         }
         if (has(c, GLC_F_HAS_BH)) s[GLC_P_BH_MASS] = s[GLC_P_BH_SPIN] = 1.0;
     }
 
-    static __device__ __forceinline__ void pre_evolve(NodeCtx &c, double (&y)[NY]) {
+    GLC_DEVICE_INLINE void pre_evolve(NodeCtx &c, double (&y)[NY]) {
         // Node_Component_Hot_Halo_Standard_Pre_Evolve -> Initializor (hot_halo/standard/_class.F90:725-747,871-891)
         if (has(c, GLC_F_HAS_HOTHALO) && !has(c, GLC_F_HH_INITIALIZED)) {
             Work w;
@@ -600,10 +663,10 @@ struct ModelStandard {
     // (python/Galacticus/Build/Components/Properties/Evolve.py:202-493)
     struct Acc {
         int flags, interrupt;
-        __device__ __forceinline__ void add(double &slot, int compFlag, double v) const {
+        GLC_DEVICE_METHOD void add(double &slot, int compFlag, double v) const {
             if (flags & compFlag) slot += v;
         }
-        __device__ __forceinline__ void addCreate(double &slot, int compFlag, int code, double v) {
+        GLC_DEVICE_METHOD void addCreate(double &slot, int compFlag, int code, double v) {
             if (flags & compFlag)
                 slot += v;
             else if (v != 0.0)
@@ -611,24 +674,24 @@ struct ModelStandard {
         }
     };
 
-    static __device__ __forceinline__ void hh_outflowing(Acc &a, const NodeCtx &c, const Work &w, double (&rate)[NY],
+    GLC_DEVICE_INLINE void hh_outflowing(Acc &a, const NodeCtx &c, const Work &w, double (&rate)[NY],
                                                          double mass, double angmom, double abund) {
         // hot_halo/standard/_class.F90:598-722 with hotHaloOutflowStrippingStandard (outflow_stripping/standard.F90:133-173)
         if (!has(c, GLC_F_HAS_HOTHALO)) return;
         double fs = 0.0;
         if (has(c, GLC_F_IS_SATELLITE)) {
             const double mo = hh_mass_enclosed(w, w.hhRouter), mv = hh_mass_enclosed(w, w.rvir);
-            fs = (mv > 0.0) ? c_params.outflowStrippingEfficiency * (1.0 - mo / mv) : c_params.outflowStrippingEfficiency;
+            fs = (mv > 0.0) ? GLC_PARAMS.outflowStrippingEfficiency * (1.0 - mo / mv) : GLC_PARAMS.outflowStrippingEfficiency;
         }
         rate[GLC_P_HH_STRIPPED_MASS] += mass * fs;
         rate[GLC_P_HH_OUTFLOWED_MASS] += mass * (1.0 - fs);
-        rate[GLC_P_HH_OUTFLOWED_ANGMOM] += angmom * (1.0 - fs) / (1.0 - c_params.fractionLossAngularMomentum);
+        rate[GLC_P_HH_OUTFLOWED_ANGMOM] += angmom * (1.0 - fs) / (1.0 - GLC_PARAMS.fractionLossAngularMomentum);
         rate[GLC_P_HH_OUTFLOWED_ABUND] += abund * (1.0 - fs);
         (void)a;
     }
 
     template <bool IS_DISK>
-    static __device__ __forceinline__ void star_formation_and_feedback(Acc &a, const NodeCtx &c, const Work &w,
+    GLC_DEVICE_INLINE void star_formation_and_feedback(Acc &a, const NodeCtx &c, const Work &w,
                                                                        const double (&y)[NY], double (&rate)[NY],
                                                                        double psi, bool doSf, bool doFb) {
         constexpr int pm = IS_DISK ? GLC_P_DISK_MASS_GAS : GLC_P_SPH_MASS_GAS;
@@ -640,24 +703,24 @@ struct ModelStandard {
         const double z = mass_to_fraction(y[pa], massGas);
         if (doSf) {
             // instantaneousRates, stellar_populations/properties/instantaneous.F90:173-182
-            const double rateStellar = (1.0 - c_params.recycledFraction) * psi;
+            const double rateStellar = (1.0 - GLC_PARAMS.recycledFraction) * psi;
             const double rateZStellar = z * rateStellar;
             rate[ps] += rateStellar;
             rate[pm] += -rateStellar;
             rate[pz] += rateZStellar;
-            rate[pa] += -rateZStellar + c_params.metalYield * psi;
+            rate[pa] += -rateZStellar + GLC_PARAMS.metalYield * psi;
         }
         if (doFb) {
             // stellar_feedback/{disks,spheroids}.F90:116-206; outflows/power_law/_class.F90:118-164;
             // outflows/rate_limit.F90:111-170
             const double radius = IS_DISK ? c.diskRadius : c.sphRadius;
             const double velocity = IS_DISK ? c.diskVelocity : c.sphVelocity;
-            const double vchar = IS_DISK ? c_params.fbDiskVelocityCharacteristic : c_params.fbSpheroidVelocityCharacteristic;
-            const double expo = IS_DISK ? c_params.fbDiskExponent : c_params.fbSpheroidExponent;
+            const double vchar = IS_DISK ? GLC_PARAMS.fbDiskVelocityCharacteristic : GLC_PARAMS.fbSpheroidVelocityCharacteristic;
+            const double expo = IS_DISK ? GLC_PARAMS.fbDiskExponent : GLC_PARAMS.fbSpheroidExponent;
             const double energy = kFeedbackEnergyInputAtInfinityCanonical * psi;
             double outflow = (velocity <= 0.0) ? 0.0 : dm_pow(vchar / velocity, expo) * energy / kFeedbackEnergyInputAtInfinityCanonical;
             const double tdyn = (velocity <= 0.0 || radius <= 0.0) ? 1.0 : kMpcPerKmPerSToGyr * radius / velocity;
-            const double outflowMax = fmax(massGas / tdyn / c_params.fbTimescaleOutflowFractionalMinimum, 0.0);
+            const double outflowMax = fmax(massGas / tdyn / GLC_PARAMS.fbTimescaleOutflowFractionalMinimum, 0.0);
             if (outflow > outflowMax) outflow = outflow * outflowMax / outflow;
             if (outflow > 0.0) {
                 const double massComp = massGas + y[ps];
@@ -671,31 +734,43 @@ struct ModelStandard {
         }
     }
 
-    static __device__ __forceinline__ int rates(NodeCtx &c, double time, const double (&y)[NY], double (&rate)[NY]) {
+    static constexpr bool kHasPostEvolve = true;
+    // structureOnly: the <eventHook postEvolve> call -- galactic structure solve at the final state
+    // (equilibrium.F90:172,197-217) -- shares this entry point so that the kernel has ONE heavy call site.
+    GLC_DEVICE_INLINE int rates(NodeCtx &c, double time, const double (&y)[NY], double (&rate)[NY],
+                                bool structureOnly, bool on) {
+        // [warp-synchronous: called by every lane of the warp; `on` = this lane wants an evaluation]
         Work w;
         Acc a{c.flags, GLC_INT_NONE};
         int bad = 0;
-        const uint32_t ops = c_params.operatorMask;
+        const uint32_t ops = GLC_PARAMS.operatorMask;
         const bool hh = has(c, GLC_F_HAS_HOTHALO), hd = has(c, GLC_F_HAS_DISK), hs = has(c, GLC_F_HAS_SPHEROID);
         const bool sat = has(c, GLC_F_IS_SATELLITE);
-        halo_scales(c, time, w);
-        hh_profile(c, y, w);
+        w.hhRouter = w.hhRcore = w.hhRho0 = w.rvir = w.vvir = w.tdyn = w.tvir = w.rhoMean = w.dlnrhoDt = 0.0;
+        w.hhValid = false;
+        w.coolLambda = w.coolEfrac = w.coolXH = w.coolFHn = w.coolTavail = 0.0;
+        if (on) {
+            halo_scales(c, time, w);
+            hh_profile(c, y, w);
+        }
         // <eventHook preDerivative>: galactic structure solve (standard.F90:1045)
-        structure_solve(c, y, time, w, bad);
-        if (!w.solvable) return GLC_INT_NONE;
+        structure_solve(c, y, time, w, bad, on);
+        const bool go = on && !structureOnly && w.solvable;
 
         // satelliteMassLoss (satellite/mass_loss/_class.F90:230-257; darkMatterHaloMassLossRate "zero")
-        if (ops & GLC_OP_SATELLITE_MASS_LOSS) rate[GLC_P_SAT_BOUND_MASS] += sat ? 0.0 : c.massRate;
+        if (go && (ops & GLC_OP_SATELLITE_MASS_LOSS)) rate[GLC_P_SAT_BOUND_MASS] += sat ? 0.0 : c.massRate;
 
         // star formation + stellar feedback, disks (star_formation/disks.F90:200-284, stellar_feedback/disks.F90:116-206)
-        if (hd && (ops & (GLC_OP_STAR_FORMATION_DISKS | GLC_OP_STELLAR_FEEDBACK_DISKS)) &&
-            !(y[GLC_P_DISK_ANGMOM] < 0.0 || c.diskRadius < 0.0 || y[GLC_P_DISK_MASS_GAS] < 0.0)) {
-            const double psi = sfr_disk(c, y, bad);
-            star_formation_and_feedback<true>(a, c, w, y, rate, psi, (ops & GLC_OP_STAR_FORMATION_DISKS) != 0,
-                                              (ops & GLC_OP_STELLAR_FEEDBACK_DISKS) != 0);
+        {
+            const bool dOn = go && hd && (ops & (GLC_OP_STAR_FORMATION_DISKS | GLC_OP_STELLAR_FEEDBACK_DISKS)) &&
+                             !(y[GLC_P_DISK_ANGMOM] < 0.0 || c.diskRadius < 0.0 || y[GLC_P_DISK_MASS_GAS] < 0.0);
+            const double psi = sfr_disk(c, y, bad, dOn);
+            if (dOn)
+                star_formation_and_feedback<true>(a, c, w, y, rate, psi, (ops & GLC_OP_STAR_FORMATION_DISKS) != 0,
+                                                  (ops & GLC_OP_STELLAR_FEEDBACK_DISKS) != 0);
         }
         // spheroids (star_formation/spheroids.F90:152-240, stellar_feedback/spheroids.F90:116-208)
-        if (hs && (ops & (GLC_OP_STAR_FORMATION_SPHEROIDS | GLC_OP_STELLAR_FEEDBACK_SPHEROIDS)) &&
+        if (go && hs && (ops & (GLC_OP_STAR_FORMATION_SPHEROIDS | GLC_OP_STELLAR_FEEDBACK_SPHEROIDS)) &&
             !(y[GLC_P_SPH_ANGMOM] < 1.0e-20 || c.sphRadius < 1.0e-12 || y[GLC_P_SPH_MASS_GAS] < 1.0e-6)) {
             const double psi = sfr_spheroid(c, y);
             star_formation_and_feedback<false>(a, c, w, y, rate, psi, (ops & GLC_OP_STAR_FORMATION_SPHEROIDS) != 0,
@@ -703,14 +778,14 @@ struct ModelStandard {
         }
 
         // barInstability (bar_instability.F90:145-249; galactic_dynamics/bar_instability/Efstathiou1982.F90:153-258)
-        if ((ops & GLC_OP_BAR_INSTABILITY) && hd &&
+        if (go && (ops & GLC_OP_BAR_INSTABILITY) && hd &&
             !(y[GLC_P_DISK_ANGMOM] < 0.0 || c.diskRadius < 0.0 || y[GLC_P_DISK_MASS_GAS] < 0.0)) {
             double timescale = -1.0;
             if (w.plausible && y[GLC_P_DISK_ANGMOM] > 0.0 && c.diskVelocity > 0.0 && c.diskRadius > 0.0) {
                 const double stabilityIsolated = 0.6221297315, boost = 1.1800237580;
                 const double md = y[GLC_P_DISK_MASS_GAS] + y[GLC_P_DISK_MASS_STELLAR];
                 const double fgas = y[GLC_P_DISK_MASS_GAS] / md;
-                const double thr = c_params.barStabilityThresholdStellar * (1.0 - fgas) + c_params.barStabilityThresholdGaseous * fgas;
+                const double thr = GLC_PARAMS.barStabilityThresholdStellar * (1.0 - fgas) + GLC_PARAMS.barStabilityThresholdGaseous * fgas;
                 double est = DBL_MAX;
                 if (md >= 0.0) {
                     const double vself = sqrt(kGInternal * md / c.diskRadius);
@@ -743,11 +818,11 @@ struct ModelStandard {
         }
 
         // CGMAccretion (circumgalactic_medium/accretion.F90:517-593; accretion/halo/simple.F90:281-378,592-613)
-        if (ops & GLC_OP_CGM_ACCRETION) {
+        if (go && (ops & GLC_OP_CGM_ACCRETION)) {
             double rateHot = 0.0, rateFailed = 0.0, rateJ = 0.0;
-            const double fb = c_params.OmegaBaryon / c_params.OmegaMatter;
+            const double fb = GLC_PARAMS.OmegaBaryon / GLC_PARAMS.OmegaMatter;
             if (!sat) {
-                const double failed = (time > c_params.timeReionization && w.vvir < c_params.velocitySuppressionReionization) ? 1.0 : 0.0;
+                const double failed = (time > GLC_PARAMS.timeReionization && w.vvir < GLC_PARAMS.velocitySuppressionReionization) ? 1.0 : 0.0;
                 const double unaccreted = hh ? y[GLC_P_HH_UNACCRETED_MASS] : 0.0;
                 const double growth = c.massRate / c.basicMass;
                 rateHot = fb * c.massRate * (1.0 - failed) + unaccreted * growth * (1.0 - failed);
@@ -755,16 +830,16 @@ struct ModelStandard {
             }
             if (c.massRate != 0.0) rateJ = c.spinRate * rateHot / c.massRate;
             const bool hotPositive = hh && y[GLC_P_HH_MASS] > 0.0;
-            if (rateHot > 0.0 || hotPositive || c_params.allowNegativeCGMMass)
+            if (rateHot > 0.0 || hotPositive || GLC_PARAMS.allowNegativeCGMMass)
                 a.addCreate(rate[GLC_P_HH_MASS], GLC_F_HAS_HOTHALO, GLC_INT_HOTHALO_CREATE, rateHot);
-            if (rateFailed > 0.0 || hotPositive || c_params.allowNegativeCGMMass)
+            if (rateFailed > 0.0 || hotPositive || GLC_PARAMS.allowNegativeCGMMass)
                 a.addCreate(rate[GLC_P_HH_UNACCRETED_MASS], GLC_F_HAS_HOTHALO, GLC_INT_HOTHALO_CREATE, rateFailed);
             a.addCreate(rate[GLC_P_HH_ANGMOM], GLC_F_HAS_HOTHALO, GLC_INT_HOTHALO_CREATE, rateJ);
         }
 
         // CGMOutflowReincorporation (outflow_reincorporation.F90:272-349; halo_dynamical_time.F90:113-128)
-        const double massReturnRate = hh ? y[GLC_P_HH_OUTFLOWED_MASS] * c_params.reincorporationMultiplier / w.tdyn : 0.0;
-        if ((ops & GLC_OP_CGM_OUTFLOW_REINCORPORATION) && hh && y[GLC_P_HH_OUTFLOWED_MASS] > 0.0) {
+        const double massReturnRate = hh ? y[GLC_P_HH_OUTFLOWED_MASS] * GLC_PARAMS.reincorporationMultiplier / w.tdyn : 0.0;
+        if (go && (ops & GLC_OP_CGM_OUTFLOW_REINCORPORATION) && hh && y[GLC_P_HH_OUTFLOWED_MASS] > 0.0) {
             const double mo = y[GLC_P_HH_OUTFLOWED_MASS];
             const double rj = y[GLC_P_HH_OUTFLOWED_ANGMOM] * (massReturnRate / mo);
             const double rz = y[GLC_P_HH_OUTFLOWED_ABUND] * (massReturnRate / mo);
@@ -777,20 +852,23 @@ struct ModelStandard {
         }
 
         // CGMCoolingHeating (cooling_heating.F90:216-381; component=disk, coolingFrom=currentNode)
-        if ((ops & GLC_OP_CGM_COOLING_HEATING) && hh && y[GLC_P_HH_MASS] > 0.0 &&
-            !(y[GLC_P_HH_ANGMOM] <= 0.0 || w.hhRouter <= 0.0)) {
-            // coolingRateWhiteFrenk1991::rate, cooling/cooling_rate/White-Frenk.F90:131-185
+        const bool coolOn = go && (ops & GLC_OP_CGM_COOLING_HEATING) && hh && y[GLC_P_HH_MASS] > 0.0 &&
+                            !(y[GLC_P_HH_ANGMOM] <= 0.0 || w.hhRouter <= 0.0);
+        // coolingRateWhiteFrenk1991::rate, cooling/cooling_rate/White-Frenk.F90:131-185
+        const bool radiusOn = coolOn && !(w.vvir > GLC_PARAMS.coolingVelocityCutOff);
+        double logSlopeT = 0.0;
+        if (radiusOn) cooling_prepare(y, w, logSlopeT);
+        const double rinfallSolved = cooling_radius(y, w, bad, radiusOn);
+        if (coolOn) {
             double cool = 0.0, rinfall = 0.0;
-            if (!(w.vvir > c_params.coolingVelocityCutOff)) {
-                double logSlopeT;
-                cooling_prepare(y, w, logSlopeT);
-                rinfall = cooling_radius(y, w, bad);
+            if (radiusOn) {
+                rinfall = rinfallSolved;
                 if (rinfall >= w.hhRouter)
                     cool = y[GLC_P_HH_MASS] / w.tdyn;
                 else {
                     // coolingRadiusSimple::radiusGrowthRate :229-311 (isothermal: temperature slope 0)
                     const double x = rinfall / w.hhRcore;
-                    const double densityLogSlope = -3.0 * c_params.hotHaloBeta * x * x / (x * x + 1.0);
+                    const double densityLogSlope = -3.0 * GLC_PARAMS.hotHaloBeta * x * x / (x * x + 1.0);
                     double growth = 0.0;
                     if (rinfall > 0.0) {
                         const double slope = densityLogSlope * (1.0 - 2.0) + 0.0 * (-logSlopeT);
@@ -801,8 +879,8 @@ struct ModelStandard {
             }
             const double heat = 0.0 / (w.vvir * w.vvir);  // circumgalacticMediumHeatingAGNFeedback: no black holes yet
             if (heat > cool) {
-                if (c_params.excessHeatDrivesOutflow) {
-                    const double out = fmin(heat - cool, c_params.rateMaximumExpulsion * y[GLC_P_HH_MASS] / w.tdyn);
+                if (GLC_PARAMS.excessHeatDrivesOutflow) {
+                    const double out = fmin(heat - cool, GLC_PARAMS.rateMaximumExpulsion * y[GLC_P_HH_MASS] / w.tdyn);
                     const double rz = y[GLC_P_HH_ABUND] * (out / y[GLC_P_HH_MASS]);
                     const double rj = y[GLC_P_HH_ANGMOM] * (out / y[GLC_P_HH_MASS]);
                     rate[GLC_P_HH_MASS] += -out;
@@ -833,18 +911,18 @@ struct ModelStandard {
                 a.addCreate(rate[GLC_P_DISK_MASS_GAS], GLC_F_HAS_DISK, GLC_INT_DISK_CREATE, cool);
                 a.addCreate(rate[GLC_P_DISK_ABUND_GAS], GLC_F_HAS_DISK, GLC_INT_DISK_CREATE, rz);
                 a.addCreate(rate[GLC_P_DISK_ANGMOM], GLC_F_HAS_DISK, GLC_INT_DISK_CREATE,
-                            rj * (1.0 - c_params.fractionLossAngularMomentum));
+                            rj * (1.0 - GLC_PARAMS.fractionLossAngularMomentum));
             }
         }
 
         // CGMOuterRadiusRamPressureStripping (outer_radius/ram_pressure_stripping.F90:151-313) with
         // hotHaloRamPressureStripping=virialRadius
-        if ((ops & GLC_OP_CGM_OUTER_RADIUS) && hh) {
+        if (go && (ops & GLC_OP_CGM_OUTER_RADIUS) && hh) {
             const double router = w.hhRouter;
             if (router < w.rvir) {
                 const double rho = hh_density(w, router);
                 if (router > 0.0 && rho > 0.0) {
-                    const double rhoMin = c_params.OmegaBaryon / c_params.OmegaMatter * c.basicMass / (w.rvir * w.rvir * w.rvir) / 4.0 / kPi;
+                    const double rhoMin = GLC_PARAMS.OmegaBaryon / GLC_PARAMS.OmegaMatter * c.basicMass / (w.rvir * w.rvir * w.rvir) / 4.0 / kPi;
                     rate[GLC_P_HH_OUTER_RADIUS] += massReturnRate / 4.0 / kPi / (router * router) / fmax(rho, rhoMin);
                 } else if (massReturnRate > 0.0) {
                     rate[GLC_P_HH_OUTER_RADIUS] += massReturnRate / c.basicMass * w.rvir;
@@ -860,7 +938,7 @@ struct ModelStandard {
     }
 
     // ---------------------------------------------------------------- post-step clamps
-    static __device__ __forceinline__ int post_step(NodeCtx &c, double (&y)[NY]) {
+    GLC_DEVICE_INLINE int post_step(NodeCtx &c, double (&y)[NY]) {
         int status = kGslSuccess;
         // Node_Component_Disk_Standard_Post_Step, disk/standard/_class.F90:473-677
         if (has(c, GLC_F_HAS_DISK)) {
@@ -937,22 +1015,12 @@ struct ModelStandard {
                 status = kGslContinue;
             }
             if (y[GLC_P_SPH_ANGMOM] < 0.0) {
-                const double j = c.sphRadius * c.sphVelocity / c_params.spheroidRatioAngularMomentumScaleRadius;
+                const double j = c.sphRadius * c.sphVelocity / GLC_PARAMS.spheroidRatioAngularMomentumScaleRadius;
                 y[GLC_P_SPH_ANGMOM] = j * (y[GLC_P_SPH_MASS_GAS] + y[GLC_P_SPH_MASS_STELLAR]);
                 status = kGslContinue;
             }
         }
         return status;
-    }
-
-    static __device__ __forceinline__ void post_evolve(NodeCtx &c, double (&y)[NY]) {
-        // <eventHook postEvolve>: structure solve at the final state (equilibrium.F90:172,197-217)
-        Work w;
-        int bad = 0;
-        halo_scales(c, c.timeNode, w);
-        hh_profile(c, y, w);
-        structure_solve(c, y, c.timeNode, w, bad);
-        if (bad) c.numericsFailed = 1;
     }
 };
 

@@ -65,6 +65,9 @@ def load_library() -> C.CDLL:
     L.glc_kernel_launch_count.argtypes = [vp]
     L.glc_measure_fp64_peak_tflops.restype = C.c_double
     L.glc_measure_fp64_peak_tflops.argtypes = [vp]
+    L.glc_evolver_set_option.argtypes = [vp, C.c_int32, C.c_int64]
+    L.glc_slice_count.restype = C.c_int64
+    L.glc_slice_count.argtypes = [vp]
     L.glc_histogram_accumulate.argtypes = [vp, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int32, vp]
     if L.glc_abi_version() != abi.GLC_ABI_VERSION:
         raise GlcError("libglcb200.so ABI version does not match include/glc_b200.h")
@@ -164,6 +167,12 @@ class Evolver:
 
     def arena_restore(self, n: int):
         self._check(self.L.glc_arena_restore(self.h, n), "glc_arena_restore")
+
+    def set_option(self, option: int, value: int) -> None:
+        self._check(self.L.glc_evolver_set_option(self.h, option, value), "glc_evolver_set_option")
+
+    def slice_count(self) -> int:
+        return int(self.L.glc_slice_count(self.h))
 
     def kernel_launch_count(self) -> int:
         return int(self.L.glc_kernel_launch_count(self.h))

@@ -304,6 +304,15 @@ float glc_last_kernel_ms(const glc_evolver *ev);
 /* raw device pointers for zero-copy interop (e.g. torch.distributed/NCCL reductions) */
 void *glc_arena_device_props(glc_evolver *ev);
 int64_t glc_arena_capacity(const glc_evolver *ev);
+/* execution options (not physics): */
+enum glc_option {
+    GLC_OPT_SLICE_BUDGET = 0, /* rate-function evaluations per lane per kernel launch (time slice); lanes park
+                                 their solver state in HBM between slices.  0 = one launch runs to completion */
+    GLC_OPT_SORT_QUEUE = 1    /* 1 (default): hand nodes to lanes in component-sorted order */
+};
+int glc_evolver_set_option(glc_evolver *ev, int32_t option, int64_t value);
+/* number of time slices (evolve-kernel launches) so far */
+int64_t glc_slice_count(const glc_evolver *ev);
 /* number of CUDA kernels of this library launched through this evolver since creation */
 int64_t glc_kernel_launch_count(const glc_evolver *ev);
 /* sustained FP64 FMA throughput of this device (TFLOP/s) from an in-library DFMA-chain microbenchmark;

@@ -1,11 +1,11 @@
-"""Attribute warp instructions of a kernel to source lines.  usage: ncu_lines.py REP KERNEL_SUBSTR"""
+"""Attribute warp instructions of a kernel to source lines.  usage: ncu_lines.py REP KERNEL_SUBSTR [TOPN]"""
 import csv, subprocess, sys, collections, re, os, glob, tempfile
 rep, kname = sys.argv[1], sys.argv[2]
+topn = int(sys.argv[3]) if len(sys.argv) > 3 else 45
 tmp = tempfile.mkdtemp()
 subprocess.run("cd %s && cuobjdump -xelf all %s >/dev/null 2>&1" % (tmp, os.path.abspath("galacticus_b200/libglcb200.so")), shell=True)
 cub = [c for c in glob.glob(tmp + "/*.cubin") if "params" not in c][0]
 dis = subprocess.run(["nvdisasm", "--print-line-info", cub], capture_output=True, text=True).stdout.split("\n")
-# locate the kernel's text section
 start = None
 for i, l in enumerate(dis):
     if l.startswith("\t.section\t.text.") and kname in l:
@@ -16,7 +16,6 @@ for l in dis[start + 1:]:
     if l.startswith("\t.section"): break
     m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', l)
     if m:
-        inl = re.findall(r'inlined at "([^"]+)", line (\d+)', l)
         cur = (m.group(1).split("/")[-1], int(m.group(2)))
         continue
     m2 = pat.search(l)
@@ -33,4 +32,4 @@ for r in data:
 byfile = collections.Counter()
 for k, v in agg.items(): byfile[k[0]] += v
 print({k: "%.1f%%" % (100 * v / tot) for k, v in byfile.most_common()})
-for k, v in agg.most_common(45): print("%-28s line %4d  %5.2f%%  avg thr %.1f" % (k[0], k[1], 100 * v / tot, aggt[k] / max(v, 1)))
+for k, v in agg.most_common(topn): print("%-28s line %4d  %5.2f%%  avg thr %.1f" % (k[0], k[1], 100 * v / tot, aggt[k] / max(v, 1)))
