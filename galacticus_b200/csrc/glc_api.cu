@@ -14,6 +14,7 @@
 #include "glc_evolve_kernel.cuh"
 #include "glc_model_box.cuh"
 #include "glc_model_standard.cuh"
+#include "glc_machine.cuh"
 
 using namespace glc;
 
@@ -56,6 +57,9 @@ struct glc_evolver {
     double *d_pow_ac = nullptr, *d_pow_kmt = nullptr;  // fastExponentiator tables
     double pow_ac_exponent = 0.0;
     LaneState *d_lanes = nullptr;   // parked lane states, one per resident lane
+    SlotState *d_slots = nullptr;   // micro-task machine: one continuation per resident slot
+    int64_t nslots_machine = 0;
+    int32_t use_machine = 1;        // standard model: 1 = micro-task machine, 0 = warp-synchronous evolve_kernel
     int32_t *d_order = nullptr;     // queue order (component-sorted node ids)
     int *d_sort = nullptr;          // 2 x 64 bucket counters
     int64_t order_cap = 0;
@@ -303,6 +307,67 @@ static int launch_evolve(glc_evolver *ev, int n, unsigned long long *hc) {
     return 0;
 }
 
+// One batch on the micro-task machine (standard model): same slice protocol as launch_evolve.
+static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc) {
+    const int gridMax = ev->num_sms;  // one block per SM
+    int grid = std::min(gridMax, (n + GLC_MSLOTS - 1) / GLC_MSLOTS);
+    if (grid < 1) grid = 1;
+    const int64_t need = (int64_t)gridMax * GLC_MSLOTS;
+    if (need > ev->nslots_machine) {
+        cudaFree(ev->d_slots);
+        ev->d_slots = nullptr;
+        GLC_CHECK(ev, cudaMalloc(&ev->d_slots, sizeof(SlotState) * need));
+        ev->nslots_machine = need;
+    }
+    int rc = ensure_workspace(ev, (int)((need + kBlock - 1) / kBlock));
+    if (rc) return rc;
+    GLC_CHECK(ev, cudaEventRecord(ev->ev0, ev->stream));
+    const int sorted = build_queue_order(ev, n);
+    if (sorted < 0) return sorted;
+    KernelArgs A;
+    A.props = ev->d_props;
+    A.flags = ev->d_flags;
+    A.time_end = ev->d_time_end;
+    A.status = ev->d_status;
+    A.interrupt = ev->d_interrupt;
+    A.cap = ev->cap;
+    A.n = n;
+    A.ws = ev->d_ws;
+    A.nslots = ev->nslots;
+    A.work_counter = ev->d_work;
+    A.counters = ev->d_counters;
+    A.order = sorted ? ev->d_order : nullptr;
+    A.lanes = nullptr;
+    A.resume = 0;
+    A.budget = ev->slice_budget > 0 ? ev->slice_budget : 0x7fffffff;
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 8, ev->stream));
+    const double t_start = now_s();
+    int nslice = 0;
+    unsigned long long tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (;;) {
+        machine_kernel<GLC_MTHREADS, GLC_MSLOTS><<<grid, GLC_MTHREADS, 0, ev->stream>>>(A, ev->d_slots);
+        ev->launches++;
+        ev->slices++;
+        GLC_CHECK(ev, cudaGetLastError());
+        GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost,
+                                      ev->stream));
+        if (ev->slice_budget <= 0) break;
+        GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+        if (ev->slice_log)
+            fprintf(stderr, "[glc slice %lld] t=%.3f ms done=%llu/%d rhs=%llu accepted=%llu parked=%llu\n",
+                    (long long)ev->slices, 1e3 * (now_s() - t_start), hc[6], n, hc[2], hc[0], hc[7]);
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long), ev->stream));
+        if (hc[6] >= (unsigned long long)n) break;
+        if (ev->max_slices > 0 && ++nslice >= ev->max_slices) break;  // profiling aid: leaves the batch unfinished
+        A.resume = 1;
+    }
+    (void)tot;
+    GLC_CHECK(ev, cudaEventRecord(ev->ev1, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    return 0;
+}
+
 static int upload_constants(glc_evolver *ev) {
     GLC_CHECK(ev, cudaMemcpyToSymbolAsync(c_params, &ev->params, sizeof(glc_params), 0,
                                           cudaMemcpyHostToDevice, ev->stream));
@@ -337,6 +402,7 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_SORT_QUEUE")) ev->sort_queue = atoi(e);
     if (const char *e = getenv("GLC_SLICE_LOG")) ev->slice_log = atoi(e);
     if (const char *e = getenv("GLC_MAX_SLICES")) ev->max_slices = atoi(e);
+    if (const char *e = getenv("GLC_MACHINE")) ev->use_machine = atoi(e);
     cudaStreamCreateWithFlags(&ev->stream, cudaStreamNonBlocking);
     cudaEventCreate(&ev->ev0);
     cudaEventCreate(&ev->ev1);
@@ -374,6 +440,7 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaFree(ev->d_pow_ac);
     cudaFree(ev->d_pow_kmt);
     cudaFree(ev->d_lanes);
+    cudaFree(ev->d_slots);
     cudaFree(ev->d_order);
     cudaFree(ev->d_sort);
     cudaEventDestroy(ev->ev0);
@@ -520,6 +587,8 @@ int glc_evolve_arena(glc_evolver *ev, int64_t n, glc_counters *counters) {
     unsigned long long hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (ev->params.model == GLC_MODEL_BOX)
         rc = launch_evolve<ModelBox>(ev, (int)n, hc);
+    else if (ev->use_machine)
+        rc = launch_machine(ev, (int)n, hc);
     else
         rc = launch_evolve<ModelStandard>(ev, (int)n, hc);
     if (rc) return rc;
@@ -569,6 +638,7 @@ int glc_evolver_set_option(glc_evolver *ev, int32_t option, int64_t value) {
     switch (option) {
         case GLC_OPT_SLICE_BUDGET: ev->slice_budget = (int32_t)std::max<int64_t>(0, std::min<int64_t>(value, 0x7fffffff)); return 0;
         case GLC_OPT_SORT_QUEUE: ev->sort_queue = value ? 1 : 0; return 0;
+        case GLC_OPT_MICROTASK_MACHINE: ev->use_machine = value ? 1 : 0; return 0;
         default: ev->err = "unknown option"; return -10;
     }
 }

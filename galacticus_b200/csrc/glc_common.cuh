@@ -30,6 +30,12 @@
 #ifndef GLC_MIN_BLOCKS
 #define GLC_MIN_BLOCKS 2
 #endif
+#ifndef GLC_MTHREADS
+#define GLC_MTHREADS 512  // threads per block of the micro-task machine (one block per SM)
+#endif
+#ifndef GLC_MSLOTS
+#define GLC_MSLOTS 2048   // slots per block = regrouping domain
+#endif
 #else
 #include <math.h>
 #include <algorithm>

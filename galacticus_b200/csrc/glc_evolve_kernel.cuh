@@ -89,8 +89,9 @@ GLC_DEVICE_INLINE int queue_bucket(int flags) {
 // addresses, so every access is one coalesced 256-B line per warp).
 struct LaneMem {
     const KernelArgs *A;
-    double *ws;
-    GLC_DEVICE_METHOD double &W(int vec, int comp) const { return ws[((int64_t)vec * NY + comp) * A->nslots]; }
+    double *ws;       // this lane's / slot's first workspace word
+    int64_t wstride;  // nslots: SoA over resident lanes (evolve_kernel); 1: one contiguous record per slot (machine)
+    GLC_DEVICE_METHOD double &W(int vec, int comp) const { return ws[((int64_t)vec * NY + comp) * wstride]; }
     GLC_DEVICE_METHOD double &AR(int prop, int node) const { return A->props[(int64_t)prop * A->cap + node]; }
 };
 
@@ -523,7 +524,7 @@ GLC_DEVICE_INLINE bool lane_iterate(LaneState &L, const LaneMem &M) {
 template <class Model>
 __global__ void __launch_bounds__(GLC_BLOCK, GLC_MIN_BLOCKS) evolve_kernel(KernelArgs A) {
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    LaneMem M{&A, A.ws + slot};
+    LaneMem M{&A, A.ws + slot, A.nslots};
     LaneState L;
     if (A.resume)
         L = A.lanes[slot];

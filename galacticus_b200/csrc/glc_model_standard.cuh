@@ -224,31 +224,43 @@ struct ModelStandard {
         }
         return timeLarge;
     }
-    GLC_DEVICE_INLINE double cooling_radius(const double (&y)[NY], Work &w, int &bad, bool on) {
-        // coolingRadiusSimple::radius, cooling/cooling_radius/simple.F90:313-387   [warp-synchronous]
+    // coolingRadiusSimple::radius, cooling/cooling_radius/simple.F90:313-387: root of t_cool(r) - t_available on
+    // [0, r_outer] with the two shortcuts of :363-381
+    GLC_DEVICE_INLINE double cooling_function(const Work &w, double radius) {
+        return cooling_time(w, hh_density(w, radius)) - w.coolTavail;
+    }
+    GLC_DEVICE_INLINE void cooling_setup(const Work &w, double &rootOuter, double &rootZero, double &result, bool &need) {
         const double router = w.hhRouter;
+        need = false;
+        result = 0.0;
+        rootZero = 0.0;
+        rootOuter = cooling_function(w, router);
+        if (rootOuter < 0.0)
+            result = router;
+        else {
+            rootZero = cooling_function(w, 0.0);
+            if (rootZero > 0.0)
+                result = 0.0;
+            else
+                need = true;
+        }
+    }
+    GLC_DEVICE_INLINE RootOptions cooling_root_options() {
+        return RootOptions{0.0, 1.0e-6, EXPAND_NONE, 0.0, 0.0, SIGN_NONE, SIGN_NONE};
+    }
+    GLC_DEVICE_INLINE double cooling_radius(const double (&y)[NY], Work &w, int &bad, bool on) {
+        // [warp-synchronous]
         double result = 0.0, rootOuter = 0.0, rootZero = 0.0;
         bool need = false;
-        if (on) {
-            rootOuter = cooling_time(w, hh_density(w, router)) - w.coolTavail;
-            if (rootOuter < 0.0)
-                result = router;
-            else {
-                rootZero = cooling_time(w, hh_density(w, 0.0)) - w.coolTavail;
-                if (rootZero > 0.0)
-                    result = 0.0;
-                else
-                    need = true;
-            }
-        }
-        const RootOptions o{0.0, 1.0e-6, EXPAND_NONE, 0.0, 0.0, SIGN_NONE, SIGN_NONE};
+        if (on) cooling_setup(w, rootOuter, rootZero, result, need);
+        const RootOptions o = cooling_root_options();
         int st;
         const double r = root_find(
             [&](double radius) {
                 GLC_COUNT(3);
-                return cooling_time(w, hh_density(w, radius)) - w.coolTavail;
+                return cooling_function(w, radius);
             },
-            need, o, 0.0, router, true, rootZero, rootOuter, st);
+            need, o, 0.0, w.hhRouter, true, rootZero, rootOuter, st);
         if (need) {
             result = r;
             if (st != 0) bad = 1;
@@ -319,62 +331,88 @@ struct ModelStandard {
         if (has(c, GLC_F_HAS_HOTHALO)) m += fmax(0.0, y[GLC_P_HH_MASS]) + fmax(0.0, y[GLC_P_HH_OUTFLOWED_MASS]);
         return m;
     }
+    // adiabaticGnedin2004 over NFW: mass_distributions/spherical/adiabatic_Gnedin2004.F90:410-530,707-727;
+    // dark_matter_profiles/adiabatic_Gnedin2004.F90:302-364.  The initial radius r_i of the shell now at `radius`
+    // solves  M_i(rbar(r_i)) (f_i r_i - f_d r) - M_b(rbar(r)) rbar(r) r / G... = 0  (:707-727).
+    struct AcProblem {
+        double fd, fi, bterm, rup, rInit;
+        int need;  // 1: r_i must be found by the root finder on [radius, rup]; 0: rInit is final
+    };
+    GLC_DEVICE_INLINE double ac_function(double nfwNorm, double rs, const Work &w, const AcProblem &P, double radius,
+                                         double ri) {
+        return nfw_mass(nfwNorm, rs, ac_orbital_mean(w, ri)) * (P.fi * ri - P.fd * radius) - P.bterm;
+    }
+    // set-up for a shell inside the virial radius (radius > 0)
+    GLC_DEVICE_INLINE void ac_setup(const NodeCtx &c, const double (&y)[NY], const Work &w, double nfwNorm, double radius,
+                                    AcProblem &P) {
+        const double rs = c.dmScale;
+        const double fDm = 1.0 - GLC_PARAMS.OmegaBaryon / GLC_PARAMS.OmegaMatter;
+        P.fd = P.fi = P.bterm = 0.0;
+        P.rup = radius;
+        P.rInit = radius;
+        P.need = 0;
+        if (radius >= w.rvir) return;
+        const double mSelfRaw = baryonic_mass_self(c, y);
+        const double mSelf = fmax(mSelfRaw, 0.0);
+        const double mTot = fmax(mSelfRaw + c.massBaryonicSubhalos, 0.0);
+        P.fd = fmin(fDm + (mTot - mSelf) / c.basicMass, 1.0);
+        P.fi = fmin(fDm + mTot / c.basicMass, 1.0);
+        const double rmean = ac_orbital_mean(w, radius);
+        P.bterm = baryonic_vc2(c, y, w, rmean) * rmean * radius / kGInternal;
+        const double menc = nfw_mass(nfwNorm, rs, rmean);
+        if (menc > 0.0) P.rup = fmax((P.bterm / menc + P.fd * radius) / P.fi, radius);
+        // the reference first tests solver(r_vir) < 0 (:463-466)
+        const double fVir = ac_function(nfwNorm, rs, w, P, radius, w.rvir);
+        if (fVir < 0.0)
+            P.rInit = w.rvir;
+        else
+            P.need = 1;
+    }
+    GLC_DEVICE_INLINE RootOptions ac_root_options() {
+        return RootOptions{0.0, 1.0e-2, EXPAND_MULTIPLICATIVE, 1.1, 0.9, SIGN_POSITIVE, SIGN_NEGATIVE};
+    }
     GLC_DEVICE_INLINE double dark_matter_mass_enclosed(const NodeCtx &c, const double (&y)[NY], const Work &w,
                                                        double nfwNorm, double radius, int &bad, bool on) {
-        // adiabaticGnedin2004 over NFW: mass_distributions/spherical/adiabatic_Gnedin2004.F90:410-530,707-727;
-        // dark_matter_profiles/adiabatic_Gnedin2004.F90:302-364   [warp-synchronous]
+        // [warp-synchronous]
         const double rs = c.dmScale;
         const double fDm = 1.0 - GLC_PARAMS.OmegaBaryon / GLC_PARAMS.OmegaMatter;
         if (!GLC_PARAMS.adiabaticContraction) return on ? nfw_mass(nfwNorm, rs, radius) : 0.0;
         const bool live = on && !(radius <= 0.0);
-        double rInit = radius, fd = 0.0, fi = 0.0, bterm = 0.0, rup = radius;
-        bool need = false;
-        if (live && !(radius >= w.rvir)) {
-            const double mSelfRaw = baryonic_mass_self(c, y);
-            const double mSelf = fmax(mSelfRaw, 0.0);
-            const double mTot = fmax(mSelfRaw + c.massBaryonicSubhalos, 0.0);
-            fd = fmin(fDm + (mTot - mSelf) / c.basicMass, 1.0);
-            fi = fmin(fDm + mTot / c.basicMass, 1.0);
-            const double rmean = ac_orbital_mean(w, radius);
-            bterm = baryonic_vc2(c, y, w, rmean) * rmean * radius / kGInternal;
-            const double menc = nfw_mass(nfwNorm, rs, rmean);
-            if (menc > 0.0) rup = fmax((bterm / menc + fd * radius) / fi, radius);
-            // the reference first tests solver(r_vir) < 0 (:463-466)
-            const double fVir = nfw_mass(nfwNorm, rs, ac_orbital_mean(w, w.rvir)) * (fi * w.rvir - fd * radius) - bterm;
-            if (fVir < 0.0)
-                rInit = w.rvir;
-            else
-                need = true;
-        }
-        const RootOptions o{0.0, 1.0e-2, EXPAND_MULTIPLICATIVE, 1.1, 0.9, SIGN_POSITIVE, SIGN_NEGATIVE};
+        AcProblem P;
+        P.fd = P.fi = P.bterm = 0.0;
+        P.rup = P.rInit = radius;
+        P.need = 0;
+        if (live) ac_setup(c, y, w, nfwNorm, radius, P);
+        const RootOptions o = ac_root_options();
         int st = 0;
-        const double root = root_find(
-            [&](double ri) {
+        const double root = root_find([&](double ri) {
                 GLC_COUNT(0);
-                return nfw_mass(nfwNorm, rs, ac_orbital_mean(w, ri)) * (fi * ri - fd * radius) - bterm;
+                return ac_function(nfwNorm, rs, w, P, radius, ri);
             },
-            need,
-            o, radius, rup, false, 0.0, 0.0, st);
-        if (need) {
-            rInit = root;
+            P.need != 0, o, radius, P.rup, false, 0.0, 0.0, st);
+        if (P.need) {
+            P.rInit = root;
             if (st != 0) bad = 1;
         }
-        return live ? fDm * nfw_mass(nfwNorm, rs, rInit) : 0.0;
+        return live ? fDm * nfw_mass(nfwNorm, rs, P.rInit) : 0.0;
+    }
+    // stands in for nfwRadiusFromSpecificAngularMomentum (NFW.F90:589-625): solve j = sqrt(G M(<r) r) in ln r
+    GLC_DEVICE_INLINE double jroot_function(double nfwNorm, double rs, double lnj, double lr) {
+        const double r = dm_exp(lr);
+        return 0.5 * dm_log(kGInternal * nfw_mass(nfwNorm, rs, r) * r) - lnj;
+    }
+    GLC_DEVICE_INLINE RootOptions jroot_options() {
+        return RootOptions{1.0e-12, 0.0, EXPAND_ADDITIVE, 2.0, -2.0, SIGN_POSITIVE, SIGN_NEGATIVE};
     }
     GLC_DEVICE_INLINE double nfw_radius_from_j(const NodeCtx &c, const Work &w, double nfwNorm, double j, bool on) {
-        // stands in for nfwRadiusFromSpecificAngularMomentum (NFW.F90:589-625): solve j = sqrt(G M(<r) r)
         // [warp-synchronous]
         const bool live = on && (j > 0.0);
         const double lnj = live ? dm_log(j) : 0.0, rs = c.dmScale;
         const double lnrv = live ? dm_log(w.rvir) : 0.0;
-        const RootOptions o{1.0e-12, 0.0, EXPAND_ADDITIVE, 2.0, -2.0, SIGN_POSITIVE, SIGN_NEGATIVE};
+        const RootOptions o = jroot_options();
         int st;
-        const double lnr = root_find(
-            [&](double lr) {
-                const double r = dm_exp(lr);
-                return 0.5 * dm_log(kGInternal * nfw_mass(nfwNorm, rs, r) * r) - lnj;
-            },
-            live, o, lnrv - 4.0, lnrv, false, 0.0, 0.0, st);
+        const double lnr = root_find([&](double lr) { return jroot_function(nfwNorm, rs, lnj, lr); }, live, o, lnrv - 4.0,
+                                     lnrv, false, 0.0, 0.0, st);
         if (!live) return 0.0;
         return (st != 0) ? w.rvir : dm_exp(lnr);
     }
@@ -408,7 +446,61 @@ struct ModelStandard {
         const double ratio = comp == 0 ? 0.5 : GLC_PARAMS.spheroidRatioAngularMomentumScaleRadius;
         return ratio * ((m > 0.0) ? j / m : 0.0);
     }
-    // galacticStructureSolverEquilibrium::solve, galactic_structure/radius_solver/equilibrium.F90:243-506
+    // galacticStructureSolverEquilibrium::solve, galactic_structure/radius_solver/equilibrium.F90:243-506.
+    // The pieces of one (iteration, component) visit, shared by the warp-synchronous solver below and by the
+    // micro-task machine (glc_machine.cuh).
+    //   first pass (:356-404): previous solution, else a first guess from the dark-matter-only rotation curve
+    GLC_DEVICE_INLINE void structure_first_pass(const NodeCtx &c, const Work &w, double nfwNorm, int comp, double j,
+                                                double &radius, double &velocity, bool &guess, bool &needRoot) {
+        guess = needRoot = false;
+        velocity = 0.0;
+        radius = comp == 0 ? c.diskRadius : c.sphRadius;
+        if (radius <= 0.0) {
+            const double radiusLarge = 1.0e10;
+            const double jmax = sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radiusLarge) / radiusLarge) * radiusLarge;
+            guess = true;
+            if (jmax < j)
+                radius = w.rvir;
+            else
+                needRoot = true;
+        } else
+            velocity = comp == 0 ? c.diskVelocity : c.sphVelocity;
+    }
+    GLC_DEVICE_INLINE double structure_guess_velocity(const NodeCtx &c, double nfwNorm, double radius) {
+        return (radius > 0.0) ? sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radius) / radius) : 0.0;
+    }
+    //   later passes (:406-481): one fixed-point update in the current potential, with the oscillation breaker
+    GLC_DEVICE_INLINE void structure_update(const NodeCtx &c, const double (&y)[NY], const Work &w, double j, double mdm,
+                                            int count, double &h0, double &h1, double &fit, int &bad, double &radius,
+                                            double &velocity) {
+        const double vdm2 = kGInternal * mdm / radius;
+        const double vb2 = GLC_PARAMS.includeBaryonGravity ? baryonic_vc2(c, y, w, radius) : 0.0;
+        velocity = sqrt(vdm2 + vb2);
+        const double radiusNew = (radius > 0.0) ? sqrt(j / velocity * radius) : j / velocity;
+        if (count > 10 && h0 >= 0.0 && h1 >= 0.0 && (h1 - h0) * (h0 - radius) < 0.0) {
+            switch (count % 4) {
+                case 0: radius = sqrt(radius * h0); break;
+                case 1: radius = 0.5 * (radius + h0); break;
+                case 2: radius = sqrt(h0 * h1); break;
+                default: radius = 0.5 * (h0 + h1); break;
+            }
+            h0 = h1 = -1.0;
+        }
+        h1 = h0;
+        h0 = radius;
+        if (radius > 0.0 && radiusNew > 0.0) fit += fabs(dm_log(radiusNew / radius));
+        radius = radiusNew;
+        if (!(radius > 0.0)) bad = 1;
+    }
+    GLC_DEVICE_INLINE void structure_store(NodeCtx &c, int comp, double radius, double velocity) {
+        if (comp == 0) {
+            c.diskRadius = fmax(radius, 0.0);
+            c.diskVelocity = velocity;
+        } else {
+            c.sphRadius = fmax(radius, 0.0);
+            c.sphVelocity = velocity;
+        }
+    }
     // [warp-synchronous: all lanes iterate together, a lane drops out when its own fixed point has converged]
     GLC_DEVICE_INLINE void structure_solve(NodeCtx &c, const double (&y)[NY], double time, Work &w, int &bad, bool on) {
         w.plausible = false;
@@ -433,62 +525,21 @@ struct ModelStandard {
                 const double j = compOn ? component_j(y, comp) : 0.0;
                 double radius = 0.0, velocity = 0.0;
                 if (compOn) active++;
-                // ---- first pass: previous solution or a first guess from the dark-matter-only rotation curve
                 const bool first = compOn && count == 1;
                 bool guess = false, needRoot = false;
-                if (first) {
-                    radius = comp == 0 ? c.diskRadius : c.sphRadius;
-                    if (radius <= 0.0) {
-                        const double radiusLarge = 1.0e10;
-                        const double jmax = sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radiusLarge) / radiusLarge) * radiusLarge;
-                        guess = true;
-                        if (jmax < j)
-                            radius = w.rvir;
-                        else
-                            needRoot = true;
-                    } else
-                        velocity = comp == 0 ? c.diskVelocity : c.sphVelocity;
-                }
+                if (first) structure_first_pass(c, w, nfwNorm, comp, j, radius, velocity, guess, needRoot);
                 const double rGuess = nfw_radius_from_j(c, w, nfwNorm, j, needRoot);
                 if (guess) {
                     if (needRoot) radius = rGuess;
-                    velocity = (radius > 0.0) ? sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radius) / radius) : 0.0;
+                    velocity = structure_guess_velocity(c, nfwNorm, radius);
                 }
-                // ---- later passes: one fixed-point update in the current potential
                 const bool later = compOn && count > 1 && !(j <= 0.0);
                 if (later) radius = comp == 0 ? c.diskRadius : c.sphRadius;
                 const double mdm = dark_matter_mass_enclosed(c, y, w, nfwNorm, radius, bad, later);
-                if (later) {
-                    const double vdm2 = kGInternal * mdm / radius;
-                    const double vb2 = GLC_PARAMS.includeBaryonGravity ? baryonic_vc2(c, y, w, radius) : 0.0;
-                    velocity = sqrt(vdm2 + vb2);
-                    const double radiusNew = (radius > 0.0) ? sqrt(j / velocity * radius) : j / velocity;
-                    double &h0 = comp == 0 ? hist00 : hist10;
-                    double &h1 = comp == 0 ? hist01 : hist11;
-                    if (count > 10 && h0 >= 0.0 && h1 >= 0.0 && (h1 - h0) * (h0 - radius) < 0.0) {
-                        switch (count % 4) {
-                            case 0: radius = sqrt(radius * h0); break;
-                            case 1: radius = 0.5 * (radius + h0); break;
-                            case 2: radius = sqrt(h0 * h1); break;
-                            default: radius = 0.5 * (h0 + h1); break;
-                        }
-                        h0 = h1 = -1.0;
-                    }
-                    h1 = h0;
-                    h0 = radius;
-                    if (radius > 0.0 && radiusNew > 0.0) fit += fabs(dm_log(radiusNew / radius));
-                    radius = radiusNew;
-                    if (!(radius > 0.0)) bad = 1;
-                }
-                if (first || later) {
-                    if (comp == 0) {
-                        c.diskRadius = fmax(radius, 0.0);
-                        c.diskVelocity = velocity;
-                    } else {
-                        c.sphRadius = fmax(radius, 0.0);
-                        c.sphVelocity = velocity;
-                    }
-                }
+                if (later)
+                    structure_update(c, y, w, j, mdm, count, comp == 0 ? hist00 : hist10, comp == 0 ? hist01 : hist11, fit,
+                                     bad, radius, velocity);
+                if (first || later) structure_store(c, comp, radius, velocity);
             }
             if (looping) {
                 if (active == 0) {
@@ -526,11 +577,18 @@ struct ModelStandard {
     }
     // starFormationRateDisksIntgrtdSurfaceDensity::rate (rates/disks/integrated_surface_density.F90:131-190)
     // with krumholz2009Intervals (rate_surface_density/disks/Krumholz2009.F90:478-587)
-    GLC_DEVICE_INLINE double sfr_disk(const NodeCtx &c, const double (&y)[NY], int &bad, bool on) {
-        // [warp-synchronous]
+    // starFormationRateDisksIntgrtdSurfaceDensity::rate with krumholz2009Intervals: the pieces, shared by the
+    // warp-synchronous sfr_disk below and by the micro-task machine
+    struct SfrProblem {
+        Kmt k;
+        double rOut, rMax, sgdIn, sgd;
+        int live, needRmax;
+    };
+    GLC_DEVICE_INLINE double sfr_sigma(const Kmt &k, double r) { return k.sigma0 * dm_exp(-r / k.rdisk); }
+    GLC_DEVICE_INLINE void sfr_setup(const NodeCtx &c, const double (&y)[NY], bool on, SfrProblem &S) {
         const double mgas = y[GLC_P_DISK_MASS_GAS], rdisk = c.diskRadius;
         bool live = on && !(mgas <= 0.0 || rdisk <= 0.0);
-        Kmt k;
+        Kmt &k = S.k;
         k.xh = k.zsolar = k.sigmaNorm = k.sNorm = k.sigmaTrunc = k.sigma0 = 0.0;
         k.rdisk = 1.0;
         if (live) {
@@ -547,54 +605,70 @@ struct ModelStandard {
             k.sNorm = dm_log(1.0 + 0.6 * chi + 0.01 * chi * chi) / (0.04 * k.zsolar);
             if (!(k.sigmaNorm > 0.0)) live = false;
         }
-        const double rIn = 0.0, rOut = 10.0 * rdisk;
-        auto sigma = [&](double r) { return k.sigma0 * dm_exp(-r / k.rdisk); };
-        double sgdIn = 0.0, sgd = 0.0, rMax = rOut;
-        bool needRmax = false;
+        S.rOut = 10.0 * rdisk;
+        S.rMax = S.rOut;
+        S.sgdIn = S.sgd = 0.0;
+        S.needRmax = 0;
         if (live) {
             k.sigmaTrunc = k.sNorm / k.sigmaNorm / GLC_PARAMS.krumholzSTruncation;
-            double sg = sigma(rIn);
-            sgdIn = k.xh * sg / 85.0e12;
+            double sg = sfr_sigma(k, 0.0);
+            S.sgdIn = k.xh * sg / 85.0e12;
             if (sg <= k.sigmaTrunc)
                 live = false;
             else {
-                sg = sigma(rOut);
-                sgd = k.xh * sg / 85.0e12;
-                needRmax = sg <= k.sigmaTrunc;
+                sg = sfr_sigma(k, S.rOut);
+                S.sgd = k.xh * sg / 85.0e12;
+                S.needRmax = sg <= k.sigmaTrunc;
             }
         }
-        const RootOptions o{0.0, 1.0e-4, EXPAND_MULTIPLICATIVE, 2.0, 0.5, SIGN_NEGATIVE, SIGN_POSITIVE};
-        int st;
-        const double rTrunc = root_find([&](double r) { return sigma(r) - k.sigmaTrunc; }, needRmax, o, rIn, rOut, false,
-                                        0.0, 0.0, st);
-        if (needRmax) {
-            rMax = rTrunc;
+        S.live = live;
+    }
+    GLC_DEVICE_INLINE RootOptions sfr_root_options() {
+        return RootOptions{0.0, 1.0e-4, EXPAND_MULTIPLICATIVE, 2.0, 0.5, SIGN_NEGATIVE, SIGN_POSITIVE};
+    }
+    GLC_DEVICE_INLINE double sfr_trunc_function(const Kmt &k, double r) { return sfr_sigma(k, r) - k.sigmaTrunc; }
+    GLC_DEVICE_INLINE double sfr_crit_function(const Kmt &k, double r) { return k.xh * sfr_sigma(k, r) / 85.0e12 - 1.0; }
+    // after the truncation-radius root find; returns whether the critical-density radius must be found too
+    GLC_DEVICE_INLINE bool sfr_after_trunc(SfrProblem &S, double rTrunc, int st, int &bad) {
+        if (S.needRmax) {
+            S.rMax = rTrunc;
             if (st != 0) bad = 1;
-            sgd = k.xh * sigma(rMax) / 85.0e12;
+            S.sgd = S.k.xh * sfr_sigma(S.k, S.rMax) / 85.0e12;
         }
-        const bool two = live && !(sgdIn <= 1.0 || sgd >= 1.0);
-        const double rCrit = root_find([&](double r) { return k.xh * sigma(r) / 85.0e12 - 1.0; }, two, o, rIn, rMax, false,
-                                       0.0, 0.0, st);
+        return S.live && !(S.sgdIn <= 1.0 || S.sgd >= 1.0);
+    }
+    GLC_DEVICE_INLINE double sfr_integrand(const Kmt &k, double r) { return r * kmt_rate(k, r); }
+    GLC_DEVICE_INLINE double sfr_disk(const NodeCtx &c, const double (&y)[NY], int &bad, bool on) {
+        // [warp-synchronous]
+        SfrProblem S;
+        sfr_setup(c, y, on, S);
+        const Kmt &k = S.k;
+        const double rIn = 0.0;
+        const RootOptions o = sfr_root_options();
+        int st;
+        const double rTrunc =
+            root_find([&](double r) { return sfr_trunc_function(k, r); }, S.needRmax != 0, o, rIn, S.rOut, false, 0.0, 0.0, st);
+        const bool two = sfr_after_trunc(S, rTrunc, st, bad);
+        const double rCrit = root_find([&](double r) { return sfr_crit_function(k, r); }, two, o, rIn, S.rMax, false, 0.0, 0.0, st);
         if (two && st != 0) bad = 1;
-        double lo[2] = {rIn, rCrit}, hi[2] = {two ? rCrit : rMax, rMax};
+        double lo[2] = {rIn, rCrit}, hi[2] = {two ? rCrit : S.rMax, S.rMax};
         const int nIv = two ? 2 : 1;
         double total = 0.0;
 #pragma unroll 1
         for (int i = 0; i < 2; i++) {
-            const bool ion = live && i < nIv;
+            const bool ion = S.live && i < nIv;
             const double v = qag15(
                 [&](double r) {
                     GLC_COUNT(2);
-                    return r * kmt_rate(k, r);
+                    return sfr_integrand(k, r);
                 },
-                ion, lo[i], hi[i], 1.0e-12,
-                                   GLC_PARAMS.sfrIntegrationTolerance, st);
+                ion, lo[i], hi[i], 1.0e-12, GLC_PARAMS.sfrIntegrationTolerance, st);
             if (ion) {
                 total += v;
                 if (st == 11) bad = 1;
             }
         }
-        return live ? 2.0 * kPi * total : 0.0;
+        return S.live ? 2.0 * kPi * total : 0.0;
     }
     GLC_DEVICE_INLINE double sfr_spheroid(const NodeCtx &c, const double (&y)[NY]) {
         // rates/spheroids/timescale.F90:109-130 + timescales/dynamical_time.F90:121-189
@@ -735,40 +809,45 @@ struct ModelStandard {
     }
 
     static constexpr bool kHasPostEvolve = true;
-    // structureOnly: the <eventHook postEvolve> call -- galactic structure solve at the final state
-    // (equilibrium.F90:172,197-217) -- shares this entry point so that the kernel has ONE heavy call site.
-    GLC_DEVICE_INLINE int rates(NodeCtx &c, double time, const double (&y)[NY], double (&rate)[NY],
-                                bool structureOnly, bool on) {
-        // [warp-synchronous: called by every lane of the warp; `on` = this lane wants an evaluation]
-        Work w;
-        Acc a{c.flags, GLC_INT_NONE};
-        int bad = 0;
-        const uint32_t ops = GLC_PARAMS.operatorMask;
-        const bool hh = has(c, GLC_F_HAS_HOTHALO), hd = has(c, GLC_F_HAS_DISK), hs = has(c, GLC_F_HAS_SPHEROID);
-        const bool sat = has(c, GLC_F_IS_SATELLITE);
+
+    GLC_DEVICE_INLINE void work_clear(Work &w) {
         w.hhRouter = w.hhRcore = w.hhRho0 = w.rvir = w.vvir = w.tdyn = w.tvir = w.rhoMean = w.dlnrhoDt = 0.0;
         w.hhValid = false;
         w.coolLambda = w.coolEfrac = w.coolXH = w.coolFHn = w.coolTavail = 0.0;
-        if (on) {
-            halo_scales(c, time, w);
-            hh_profile(c, y, w);
-        }
-        // <eventHook preDerivative>: galactic structure solve (standard.F90:1045)
-        structure_solve(c, y, time, w, bad, on);
-        const bool go = on && !structureOnly && w.solvable;
+        w.plausible = w.solvable = false;
+    }
+    // which of the nested solvers an evaluation needs (operator gates of nodeOperatorMulti)
+    GLC_DEVICE_INLINE bool disk_sfr_on(const NodeCtx &c, const double (&y)[NY], bool go) {
+        return go && has(c, GLC_F_HAS_DISK) &&
+               (GLC_PARAMS.operatorMask & (GLC_OP_STAR_FORMATION_DISKS | GLC_OP_STELLAR_FEEDBACK_DISKS)) &&
+               !(y[GLC_P_DISK_ANGMOM] < 0.0 || c.diskRadius < 0.0 || y[GLC_P_DISK_MASS_GAS] < 0.0);
+    }
+    GLC_DEVICE_INLINE bool cooling_on(const NodeCtx &c, const double (&y)[NY], const Work &w, bool go) {
+        return go && (GLC_PARAMS.operatorMask & GLC_OP_CGM_COOLING_HEATING) && has(c, GLC_F_HAS_HOTHALO) &&
+               y[GLC_P_HH_MASS] > 0.0 && !(y[GLC_P_HH_ANGMOM] <= 0.0 || w.hhRouter <= 0.0);
+    }
+    // coolingRateWhiteFrenk1991::rate needs the cooling radius unless the halo is above the velocity cut-off
+    GLC_DEVICE_INLINE bool cooling_radius_on(const Work &w, bool coolOn) {
+        return coolOn && !(w.vvir > GLC_PARAMS.coolingVelocityCutOff);
+    }
 
+    // Everything of the RHS that is straight-line once the nested solvers have delivered the disk star formation
+    // rate (psiDisk) and the cooling radius (rinfallSolved): accumulates the operators' rates in the order of
+    // nodeOperatorMulti (multi.F90:313-332) and returns the interrupt code.
+    GLC_DEVICE_INLINE int rates_accumulate(NodeCtx &c, double time, const double (&y)[NY], double (&rate)[NY], const Work &w,
+                                           bool go, bool dOn, double psiDisk, bool coolOn, bool radiusOn,
+                                           double rinfallSolved, double logSlopeT, int bad) {
+        Acc a{c.flags, GLC_INT_NONE};
+        const uint32_t ops = GLC_PARAMS.operatorMask;
+        const bool hh = has(c, GLC_F_HAS_HOTHALO), hd = has(c, GLC_F_HAS_DISK), hs = has(c, GLC_F_HAS_SPHEROID);
+        const bool sat = has(c, GLC_F_IS_SATELLITE);
         // satelliteMassLoss (satellite/mass_loss/_class.F90:230-257; darkMatterHaloMassLossRate "zero")
         if (go && (ops & GLC_OP_SATELLITE_MASS_LOSS)) rate[GLC_P_SAT_BOUND_MASS] += sat ? 0.0 : c.massRate;
 
         // star formation + stellar feedback, disks (star_formation/disks.F90:200-284, stellar_feedback/disks.F90:116-206)
-        {
-            const bool dOn = go && hd && (ops & (GLC_OP_STAR_FORMATION_DISKS | GLC_OP_STELLAR_FEEDBACK_DISKS)) &&
-                             !(y[GLC_P_DISK_ANGMOM] < 0.0 || c.diskRadius < 0.0 || y[GLC_P_DISK_MASS_GAS] < 0.0);
-            const double psi = sfr_disk(c, y, bad, dOn);
-            if (dOn)
-                star_formation_and_feedback<true>(a, c, w, y, rate, psi, (ops & GLC_OP_STAR_FORMATION_DISKS) != 0,
-                                                  (ops & GLC_OP_STELLAR_FEEDBACK_DISKS) != 0);
-        }
+        if (dOn)
+            star_formation_and_feedback<true>(a, c, w, y, rate, psiDisk, (ops & GLC_OP_STAR_FORMATION_DISKS) != 0,
+                                              (ops & GLC_OP_STELLAR_FEEDBACK_DISKS) != 0);
         // spheroids (star_formation/spheroids.F90:152-240, stellar_feedback/spheroids.F90:116-208)
         if (go && hs && (ops & (GLC_OP_STAR_FORMATION_SPHEROIDS | GLC_OP_STELLAR_FEEDBACK_SPHEROIDS)) &&
             !(y[GLC_P_SPH_ANGMOM] < 1.0e-20 || c.sphRadius < 1.0e-12 || y[GLC_P_SPH_MASS_GAS] < 1.0e-6)) {
@@ -852,13 +931,6 @@ struct ModelStandard {
         }
 
         // CGMCoolingHeating (cooling_heating.F90:216-381; component=disk, coolingFrom=currentNode)
-        const bool coolOn = go && (ops & GLC_OP_CGM_COOLING_HEATING) && hh && y[GLC_P_HH_MASS] > 0.0 &&
-                            !(y[GLC_P_HH_ANGMOM] <= 0.0 || w.hhRouter <= 0.0);
-        // coolingRateWhiteFrenk1991::rate, cooling/cooling_rate/White-Frenk.F90:131-185
-        const bool radiusOn = coolOn && !(w.vvir > GLC_PARAMS.coolingVelocityCutOff);
-        double logSlopeT = 0.0;
-        if (radiusOn) cooling_prepare(y, w, logSlopeT);
-        const double rinfallSolved = cooling_radius(y, w, bad, radiusOn);
         if (coolOn) {
             double cool = 0.0, rinfall = 0.0;
             if (radiusOn) {
@@ -935,6 +1007,31 @@ struct ModelStandard {
         }
         if (bad) c.numericsFailed = 1;
         return a.interrupt;
+    }
+
+    // structureOnly: the <eventHook postEvolve> call -- galactic structure solve at the final state
+    // (equilibrium.F90:172,197-217) -- shares this entry point so that the kernel has ONE heavy call site.
+    GLC_DEVICE_INLINE int rates(NodeCtx &c, double time, const double (&y)[NY], double (&rate)[NY],
+                                bool structureOnly, bool on) {
+        // [warp-synchronous: called by every lane of the warp; `on` = this lane wants an evaluation]
+        Work w;
+        int bad = 0;
+        work_clear(w);
+        if (on) {
+            halo_scales(c, time, w);
+            hh_profile(c, y, w);
+        }
+        // <eventHook preDerivative>: galactic structure solve (standard.F90:1045)
+        structure_solve(c, y, time, w, bad, on);
+        const bool go = on && !structureOnly && w.solvable;
+        const bool dOn = disk_sfr_on(c, y, go);
+        const double psiDisk = sfr_disk(c, y, bad, dOn);
+        const bool coolOn = cooling_on(c, y, w, go);
+        const bool radiusOn = cooling_radius_on(w, coolOn);
+        double logSlopeT = 0.0;
+        if (radiusOn) cooling_prepare(y, w, logSlopeT);
+        const double rinfallSolved = cooling_radius(y, w, bad, radiusOn);
+        return rates_accumulate(c, time, y, rate, w, go, dOn, psiDisk, coolOn, radiusOn, rinfallSolved, logSlopeT, bad);
     }
 
     // ---------------------------------------------------------------- post-step clamps

@@ -27,248 +27,273 @@ struct RootOptions {
 
 GLC_DEVICE_INLINE double fsign1(double x) { return signbit(x) ? -1.0 : 1.0; }
 
-// Warp-synchronous calling discipline.  Every routine below that contains a data-dependent loop must be
-// called by ALL lanes of the warp from uniform control flow; `on` tells whether this lane really wants the
-// result.  The loops run `while (GLC_ANY(lane still busy))`: the vote is an explicit reconvergence point
-// in every iteration, lanes that are finished idle through the body.  (Left to itself the compiler does not
-// re-converge the multi-exit state machines reliably: measured 3 active lanes per warp instruction.)
+// Re-entrant form of rootFinder%find (Brent branch): the caller owns the loop.
+//   brent_begin(...)            initialise;
+//   brent_advance(B) -> bool    run the state machine to the next abscissa B.x at which the function is needed
+//                               (false: nothing to evaluate -- finished, B.busy == 0, B.result/B.status are set);
+//   brent_feed(B, f(B.x))       digest the value.
+// status 0 = ok, 2 = could not bracket, 3 = bad bracket
+struct BrentState {
+    RootOptions o;
+    double xLow, xHigh, fLow, fHigh;
+    double a, b, c, d, e, fa, fb, fc, xl, xh, root, x, result;
+    int state, iteration, status;
+    int lowerOk, upperOk, rangeChanged, first, busy;
+};
+enum : int { ST_FLO, ST_FHI, ST_BRACKET, ST_EXP_UP, ST_EXP_DOWN, ST_BRENT };
 
-// returns the root; status 0 = ok, 2 = could not bracket, 3 = bad bracket, 4 = no convergence
-template <class F>
-GLC_DEVICE_INLINE double root_find(F &&f, bool on, const RootOptions &o, double xLow, double xHigh,
-                                            bool haveValues, double fLow, double fHigh, int &status) {
-    enum : int { ST_FLO, ST_FHI, ST_BRACKET, ST_EXP_UP, ST_EXP_DOWN, ST_BRENT };
-    int state = haveValues ? ST_BRACKET : ST_FLO;
-    bool lowerOk = false, upperOk = false, rangeChanged = false, first = true;
-    // Brent state (GSL brent_state_t)
-    double a = 0, b = 0, c = 0, d = 0, e = 0, fa = 0, fb = 0, fc = 0;
-    double xl = 0, xh = 0, root = 0;
-    int iteration = 0;
-    bool busy = on;
-    double result = 0.0;
-    status = 0;
-    while (GLC_ANY(busy)) {
-        double x = 0.0;
-        bool evaluate = false;
-        // ---- advance the state machine to the next point at which the function is needed (short, no heavy work)
-        while (busy && !evaluate) {
+GLC_DEVICE_INLINE void brent_begin(BrentState &B, bool on, const RootOptions &o, double xLow, double xHigh, bool haveValues,
+                                   double fLow, double fHigh) {
+    B.o = o;
+    B.xLow = xLow;
+    B.xHigh = xHigh;
+    B.fLow = fLow;
+    B.fHigh = fHigh;
+    B.a = B.b = B.c = B.d = B.e = B.fa = B.fb = B.fc = B.xl = B.xh = B.root = B.x = B.result = 0.0;
+    B.state = haveValues ? ST_BRACKET : ST_FLO;
+    B.iteration = 0;
+    B.status = 0;
+    B.lowerOk = B.upperOk = B.rangeChanged = 0;
+    B.first = 1;
+    B.busy = on ? 1 : 0;
+}
+
+GLC_DEVICE_INLINE bool brent_advance(BrentState &B) {
+    double x = 0.0;
+    bool evaluate = false;
+    while (B.busy && !evaluate) {
             evaluate = true;
-            if (state == ST_FLO) {
-                x = xLow;
-            } else if (state == ST_FHI) {
-                x = xHigh;
-            } else if (state == ST_BRACKET) {
+            if (B.state == ST_FLO) {
+                x = B.xLow;
+            } else if (B.state == ST_FHI) {
+                x = B.xHigh;
+            } else if (B.state == ST_BRACKET) {
                 evaluate = false;
-                if (first) {
-                    if (xHigh == xLow) fHigh = fLow;
-                    first = false;
+                if (B.first) {
+                    if (B.xHigh == B.xLow) B.fHigh = B.fLow;
+                    B.first = false;
                 }
-                if (fsign1(fLow) * fsign1(fHigh) > 0.0 && fLow != 0.0 && fHigh != 0.0) {
-                    lowerOk = o.signExpectDownward == SIGN_NEGATIVE   ? (fLow < 0.0)
-                              : o.signExpectDownward == SIGN_POSITIVE ? (fLow > 0.0)
+                if (fsign1(B.fLow) * fsign1(B.fHigh) > 0.0 && B.fLow != 0.0 && B.fHigh != 0.0) {
+                    B.lowerOk = B.o.signExpectDownward == SIGN_NEGATIVE   ? (B.fLow < 0.0)
+                              : B.o.signExpectDownward == SIGN_POSITIVE ? (B.fLow > 0.0)
                                                                       : false;
-                    upperOk = o.signExpectUpward == SIGN_NEGATIVE   ? (fHigh < 0.0)
-                              : o.signExpectUpward == SIGN_POSITIVE ? (fHigh > 0.0)
+                    B.upperOk = B.o.signExpectUpward == SIGN_NEGATIVE   ? (B.fHigh < 0.0)
+                              : B.o.signExpectUpward == SIGN_POSITIVE ? (B.fHigh > 0.0)
                                                                     : false;
-                    rangeChanged = false;
-                    state = ST_EXP_UP;
+                    B.rangeChanged = false;
+                    B.state = ST_EXP_UP;
                 } else {
                     // brent_init (function values at the bracket ends are already known)
-                    a = xLow;
-                    fa = fLow;
-                    b = xHigh;
-                    fb = fHigh;
-                    c = xHigh;
-                    fc = fHigh;
-                    d = xHigh - xLow;
-                    e = xHigh - xLow;
-                    if ((fLow < 0.0 && fHigh < 0.0) || (fLow > 0.0 && fHigh > 0.0)) {
-                        status = 3;
-                        result = 0.0;
-                        busy = false;
+                    B.a = B.xLow;
+                    B.fa = B.fLow;
+                    B.b = B.xHigh;
+                    B.fb = B.fHigh;
+                    B.c = B.xHigh;
+                    B.fc = B.fHigh;
+                    B.d = B.xHigh - B.xLow;
+                    B.e = B.xHigh - B.xLow;
+                    if ((B.fLow < 0.0 && B.fHigh < 0.0) || (B.fLow > 0.0 && B.fHigh > 0.0)) {
+                        B.status = 3;
+                        B.result = 0.0;
+                        B.busy = false;
                     }
-                    state = ST_BRENT;
+                    B.state = ST_BRENT;
                 }
-            } else if (state == ST_EXP_UP) {
+            } else if (B.state == ST_EXP_UP) {
                 bool move;
-                if (o.expandType == EXPAND_ADDITIVE)
-                    move = o.expandUpward > 0.0 && !upperOk;
-                else if (o.expandType == EXPAND_MULTIPLICATIVE)
-                    move = ((o.expandUpward > 1.0 && xHigh > 0.0) || (o.expandUpward < 1.0 && xHigh < 0.0)) && !upperOk;
+                if (B.o.expandType == EXPAND_ADDITIVE)
+                    move = B.o.expandUpward > 0.0 && !B.upperOk;
+                else if (B.o.expandType == EXPAND_MULTIPLICATIVE)
+                    move = ((B.o.expandUpward > 1.0 && B.xHigh > 0.0) || (B.o.expandUpward < 1.0 && B.xHigh < 0.0)) && !B.upperOk;
                 else
                     move = false;
                 if (move) {
-                    if (lowerOk) {
-                        xLow = xHigh;
-                        fLow = fHigh;
+                    if (B.lowerOk) {
+                        B.xLow = B.xHigh;
+                        B.fLow = B.fHigh;
                     }
-                    xHigh = (o.expandType == EXPAND_ADDITIVE) ? xHigh + o.expandUpward : xHigh * o.expandUpward;
-                    x = xHigh;
-                    rangeChanged = true;
+                    B.xHigh = (B.o.expandType == EXPAND_ADDITIVE) ? B.xHigh + B.o.expandUpward : B.xHigh * B.o.expandUpward;
+                    x = B.xHigh;
+                    B.rangeChanged = true;
                 } else {
                     evaluate = false;
-                    state = ST_EXP_DOWN;
+                    B.state = ST_EXP_DOWN;
                 }
-            } else if (state == ST_EXP_DOWN) {
+            } else if (B.state == ST_EXP_DOWN) {
                 bool move;
-                if (o.expandType == EXPAND_ADDITIVE)
-                    move = o.expandDownward < 0.0 && !lowerOk;
-                else if (o.expandType == EXPAND_MULTIPLICATIVE)
-                    move = ((o.expandDownward < 1.0 && xLow > 0.0) || (o.expandDownward > 1.0 && xLow < 0.0)) && !lowerOk;
+                if (B.o.expandType == EXPAND_ADDITIVE)
+                    move = B.o.expandDownward < 0.0 && !B.lowerOk;
+                else if (B.o.expandType == EXPAND_MULTIPLICATIVE)
+                    move = ((B.o.expandDownward < 1.0 && B.xLow > 0.0) || (B.o.expandDownward > 1.0 && B.xLow < 0.0)) && !B.lowerOk;
                 else
                     move = false;
                 if (move) {
-                    if (upperOk) {
-                        xHigh = xLow;
-                        fHigh = fLow;
+                    if (B.upperOk) {
+                        B.xHigh = B.xLow;
+                        B.fHigh = B.fLow;
                     }
-                    xLow = (o.expandType == EXPAND_ADDITIVE) ? xLow + o.expandDownward : xLow * o.expandDownward;
-                    x = xLow;
-                    rangeChanged = true;
+                    B.xLow = (B.o.expandType == EXPAND_ADDITIVE) ? B.xLow + B.o.expandDownward : B.xLow * B.o.expandDownward;
+                    x = B.xLow;
+                    B.rangeChanged = true;
                 } else {
                     evaluate = false;
-                    if (!rangeChanged) {
-                        status = 2;
-                        result = 0.0;
-                        busy = false;
+                    if (!B.rangeChanged) {
+                        B.status = 2;
+                        B.result = 0.0;
+                        B.busy = false;
                     }
-                    state = ST_BRACKET;
+                    B.state = ST_BRACKET;
                 }
-            } else {  // ST_BRENT: brent_iterate up to the point where f(b) is needed
+            } else {  // ST_BRENT: brent_iterate up to the point where f(B.b) is needed
                 double tol, m;
                 bool acEqual = false;
-                iteration++;
-                if ((fb < 0 && fc < 0) || (fb > 0 && fc > 0)) {
+                B.iteration++;
+                if ((B.fb < 0 && B.fc < 0) || (B.fb > 0 && B.fc > 0)) {
                     acEqual = true;
-                    c = a;
-                    fc = fa;
-                    d = b - a;
-                    e = b - a;
+                    B.c = B.a;
+                    B.fc = B.fa;
+                    B.d = B.b - B.a;
+                    B.e = B.b - B.a;
                 }
-                if (fabs(fc) < fabs(fb)) {
+                if (fabs(B.fc) < fabs(B.fb)) {
                     acEqual = true;
-                    a = b;
-                    b = c;
-                    c = a;
-                    fa = fb;
-                    fb = fc;
-                    fc = fa;
+                    B.a = B.b;
+                    B.b = B.c;
+                    B.c = B.a;
+                    B.fa = B.fb;
+                    B.fb = B.fc;
+                    B.fc = B.fa;
                 }
-                tol = 0.5 * DBL_EPSILON * fabs(b);
-                m = 0.5 * (c - b);
+                tol = 0.5 * DBL_EPSILON * fabs(B.b);
+                m = 0.5 * (B.c - B.b);
                 bool done = false;
-                if (fb == 0) {
-                    root = b;
-                    xl = b;
-                    xh = b;
+                if (B.fb == 0) {
+                    B.root = B.b;
+                    B.xl = B.b;
+                    B.xh = B.b;
                     done = true;
                 } else if (fabs(m) <= tol) {
-                    root = b;
-                    if (b < c) {
-                        xl = b;
-                        xh = c;
+                    B.root = B.b;
+                    if (B.b < B.c) {
+                        B.xl = B.b;
+                        B.xh = B.c;
                     } else {
-                        xl = c;
-                        xh = b;
+                        B.xl = B.c;
+                        B.xh = B.b;
                     }
                     done = true;
                 }
                 if (done) {
                     evaluate = false;
-                    // convergence test happens only from the second iteration on (root_finder.F90:1029)
-                    if (iteration > 1) {
-                        const double al = fabs(xl), au = fabs(xh);
-                        const double minAbs = ((xl > 0.0 && xh > 0.0) || (xl < 0.0 && xh < 0.0)) ? fmin(al, au) : 0.0;
-                        if (fabs(xh - xl) < o.tolAbs + o.tolRel * minAbs) {
-                            result = root;
-                            busy = false;
+                    // convergence test happens only from the second B.iteration on (root_finder.F90:1029)
+                    if (B.iteration > 1) {
+                        const double al = fabs(B.xl), au = fabs(B.xh);
+                        const double minAbs = ((B.xl > 0.0 && B.xh > 0.0) || (B.xl < 0.0 && B.xh < 0.0)) ? fmin(al, au) : 0.0;
+                        if (fabs(B.xh - B.xl) < B.o.tolAbs + B.o.tolRel * minAbs) {
+                            B.result = B.root;
+                            B.busy = false;
                         }
                     }
-                    if (busy && iteration > 1000) {  // iterationMaximum, root_finder.F90:1028
-                        result = root;
-                        busy = false;
+                    if (B.busy && B.iteration > 1000) {  // iterationMaximum, root_finder.F90:1028
+                        B.result = B.root;
+                        B.busy = false;
                     }
                 } else {
-                    if (fabs(e) < tol || fabs(fa) <= fabs(fb)) {
-                        d = m;
-                        e = m;
+                    if (fabs(B.e) < tol || fabs(B.fa) <= fabs(B.fb)) {
+                        B.d = m;
+                        B.e = m;
                     } else {
                         double p, q, r;
-                        const double s = fb / fa;
+                        const double s = B.fb / B.fa;
                         if (acEqual) {
                             p = 2 * m * s;
                             q = 1 - s;
                         } else {
-                            q = fa / fc;
-                            r = fb / fc;
-                            p = s * (2 * m * q * (q - r) - (b - a) * (r - 1));
+                            q = B.fa / B.fc;
+                            r = B.fb / B.fc;
+                            p = s * (2 * m * q * (q - r) - (B.b - B.a) * (r - 1));
                             q = (q - 1) * (r - 1) * (s - 1);
                         }
                         if (p > 0)
                             q = -q;
                         else
                             p = -p;
-                        if (2 * p < fmin(3 * m * q - fabs(tol * q), fabs(e * q))) {
-                            e = d;
-                            d = p / q;
+                        if (2 * p < fmin(3 * m * q - fabs(tol * q), fabs(B.e * q))) {
+                            B.e = B.d;
+                            B.d = p / q;
                         } else {
-                            d = m;
-                            e = m;
+                            B.d = m;
+                            B.e = m;
                         }
                     }
-                    a = b;
-                    fa = fb;
-                    if (fabs(d) > tol)
-                        b += d;
+                    B.a = B.b;
+                    B.fa = B.fb;
+                    if (fabs(B.d) > tol)
+                        B.b += B.d;
                     else
-                        b += (m > 0 ? +tol : -tol);
-                    x = b;
+                        B.b += (m > 0 ? +tol : -tol);
+                    x = B.b;
                 }
             }
         }
-        if (busy && evaluate) {
-            const double fx = f(x);  // ---- the single call site (straight-line integrands only)
+    B.x = x;
+    return B.busy && evaluate;
+}
 
-            if (state == ST_FLO) {
-                fLow = fx;
-                state = ST_FHI;
-            } else if (state == ST_FHI) {
-                fHigh = fx;
-                state = ST_BRACKET;
-            } else if (state == ST_EXP_UP) {
-                fHigh = fx;
-                state = ST_EXP_DOWN;
-            } else if (state == ST_EXP_DOWN) {
-                fLow = fx;
-                state = ST_BRACKET;
+GLC_DEVICE_INLINE void brent_feed(BrentState &B, double fx) {
+            if (B.state == ST_FLO) {
+                B.fLow = fx;
+                B.state = ST_FHI;
+            } else if (B.state == ST_FHI) {
+                B.fHigh = fx;
+                B.state = ST_BRACKET;
+            } else if (B.state == ST_EXP_UP) {
+                B.fHigh = fx;
+                B.state = ST_EXP_DOWN;
+            } else if (B.state == ST_EXP_DOWN) {
+                B.fLow = fx;
+                B.state = ST_BRACKET;
             } else {
-                fb = fx;
-                root = b;
-                double cc = c;
-                if ((fb < 0 && fc < 0) || (fb > 0 && fc > 0)) cc = a;
-                if (b < cc) {
-                    xl = b;
-                    xh = cc;
+                B.fb = fx;
+                B.root = B.b;
+                double cc = B.c;
+                if ((B.fb < 0 && B.fc < 0) || (B.fb > 0 && B.fc > 0)) cc = B.a;
+                if (B.b < cc) {
+                    B.xl = B.b;
+                    B.xh = cc;
                 } else {
-                    xl = cc;
-                    xh = b;
+                    B.xl = cc;
+                    B.xh = B.b;
                 }
-                if (iteration > 1) {
-                    const double al = fabs(xl), au = fabs(xh);
-                    const double minAbs = ((xl > 0.0 && xh > 0.0) || (xl < 0.0 && xh < 0.0)) ? fmin(al, au) : 0.0;
-                    if (fabs(xh - xl) < o.tolAbs + o.tolRel * minAbs) {
-                        result = root;
-                        busy = false;
+                if (B.iteration > 1) {
+                    const double al = fabs(B.xl), au = fabs(B.xh);
+                    const double minAbs = ((B.xl > 0.0 && B.xh > 0.0) || (B.xl < 0.0 && B.xh < 0.0)) ? fmin(al, au) : 0.0;
+                    if (fabs(B.xh - B.xl) < B.o.tolAbs + B.o.tolRel * minAbs) {
+                        B.result = B.root;
+                        B.busy = false;
                     }
                 }
-                if (busy && iteration > 1000) {
-                    result = root;
-                    busy = false;
+                if (B.busy && B.iteration > 1000) {
+                    B.result = B.root;
+                    B.busy = false;
                 }
             }
-        }
+}
+
+// Warp-synchronous calling discipline.  Every routine below that contains a data-dependent loop must be
+// called by ALL lanes of the warp from uniform control flow; `on` tells whether this lane really wants the
+// result.  The loops run `while (GLC_ANY(lane still busy))`: the vote is an explicit reconvergence point
+// in every iteration, lanes that are finished idle through the body.
+template <class F>
+GLC_DEVICE_INLINE double root_find(F &&f, bool on, const RootOptions &o, double xLow, double xHigh,
+                                            bool haveValues, double fLow, double fHigh, int &status) {
+    BrentState B;
+    brent_begin(B, on, o, xLow, xHigh, haveValues, fLow, fHigh);
+    while (GLC_ANY(B.busy != 0)) {
+        if (brent_advance(B)) brent_feed(B, f(B.x));  // ---- the single call site (straight-line integrands only)
     }
-    return result;
+    status = B.status;
+    return B.result;
 }
 
 // ---------------------------------------------------------------- Gauss-Kronrod 15 / QAG
@@ -304,167 +329,193 @@ GLC_DEVICE_INLINE double rescale_error(double err, double resultAbs, double resu
 
 constexpr int kQagLimitDevice = 24;  // intervals kept per thread; the reference allows 1000 and aborts beyond
 
-// gsl_integration_qag(key = GAUSS15). status: 0 ok, 11 interval budget exhausted, 18/21 round-off/singular.
+// Re-entrant form of gsl_integration_qag(key = GAUSS15): the caller owns the loop.
+//   qag_begin(...)      initialise;   qag_pass(Q, f)  one 15-point rule on the pending (sub)interval + bookkeeping
+//   (requires Q.busy);  qag_finish(Q) the integral once Q.busy == 0.
+// status: 0 ok, 11 interval budget exhausted, 18/21 round-off/singular
+struct QagState {
+    double alist[kQagLimitDevice], blist[kQagLimitDevice], rlist[kQagLimitDevice], elist[kQagLimitDevice];
+    double a, b, epsabs, epsrel;
+    double area, errsum, tolerance, ia, ib, a1, b1, a2, b2, rI, eI, area1, error1, resasc1, answer;
+    int size, iteration, errorType, roundoff1, roundoff2, phase, iMax, status, busy, summed;
+};
+
+GLC_DEVICE_INLINE void qag_begin(QagState &Q, bool on, double a, double b, double epsabs, double epsrel) {
+    Q.a = a;
+    Q.b = b;
+    Q.epsabs = epsabs;
+    Q.epsrel = epsrel;
+    Q.area = Q.errsum = Q.tolerance = 0.0;
+    Q.ia = a;
+    Q.ib = b;
+    Q.a1 = Q.b1 = Q.a2 = Q.b2 = Q.rI = Q.eI = Q.area1 = Q.error1 = Q.resasc1 = Q.answer = 0.0;
+    Q.size = Q.iteration = Q.errorType = Q.roundoff1 = Q.roundoff2 = 0;
+    Q.phase = 0;  // 0: initial interval, 1: first half, 2: second half
+    Q.iMax = 0;
+    Q.status = 0;
+    Q.busy = on ? 1 : 0;
+    Q.summed = 0;
+}
+
+template <class F>
+GLC_DEVICE_INLINE void qag_pass(QagState &Q, F &&f) {
+    // ---- qk15 on (Q.ia, Q.ib): one call site of f
+    double result, abserr, resabs, resasc;
+    {
+        double fv[15];
+        const double center = 0.5 * (Q.ia + Q.ib);
+        const double halfLength = 0.5 * (Q.ib - Q.ia);
+        const double absHalfLength = fabs(halfLength);
+#pragma unroll 1
+        for (int j = 0; j < 15; j++) {
+            double x;
+            if (j == 0)
+                x = center;
+            else {
+                const int k = c_qk_order[(j - 1) >> 1];
+                const double absc = halfLength * c_xgk[k];
+                x = ((j - 1) & 1) ? center + absc : center - absc;
+            }
+            fv[j] = f(x);
+        }
+        const double fCenter = fv[0];
+        double resultGauss = fCenter * c_wg[3];
+        double resultKronrod = fCenter * c_wgk[7];
+        double resultAbs = fabs(resultKronrod);
+#pragma unroll
+        for (int p = 0; p < 7; p++) {
+            const int k = c_qk_order[p];
+            const double f1 = fv[1 + 2 * p], f2 = fv[2 + 2 * p];
+            if (p < 3) resultGauss += c_wg[p] * (f1 + f2);
+            resultKronrod += c_wgk[k] * (f1 + f2);
+            resultAbs += c_wgk[k] * (fabs(f1) + fabs(f2));
+        }
+        const double mean = resultKronrod * 0.5;
+        double resultAsc = c_wgk[7] * fabs(fCenter - mean);
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const int p = c_qk_pos[k];
+            resultAsc += c_wgk[k] * (fabs(fv[1 + 2 * p] - mean) + fabs(fv[2 + 2 * p] - mean));
+        }
+        const double err = (resultKronrod - resultGauss) * halfLength;
+        resultKronrod *= halfLength;
+        resultAbs *= absHalfLength;
+        resultAsc *= absHalfLength;
+        result = resultKronrod;
+        resabs = resultAbs;
+        resasc = resultAsc;
+        abserr = rescale_error(err, resultAbs, resultAsc);
+    }
+    bool bisect = true;
+    if (Q.phase == 0) {
+        Q.alist[0] = Q.a;
+        Q.blist[0] = Q.b;
+        Q.rlist[0] = result;
+        Q.elist[0] = abserr;
+        Q.size = 1;
+        Q.tolerance = fmax(Q.epsabs, Q.epsrel * fabs(result));
+        const double roundOff = 50 * DBL_EPSILON * resabs;
+        if (abserr <= roundOff && abserr > Q.tolerance) {
+            Q.status = 18;
+            Q.answer = result;
+            Q.busy = false;
+        } else if ((abserr <= Q.tolerance && abserr != resasc) || abserr == 0.0) {
+            Q.answer = result;
+            Q.busy = false;
+        }
+        Q.area = result;
+        Q.errsum = abserr;
+        Q.iteration = 1;
+    } else if (Q.phase == 1) {
+        Q.area1 = result;
+        Q.error1 = abserr;
+        Q.resasc1 = resasc;
+        Q.ia = Q.a2;
+        Q.ib = Q.b2;
+        Q.phase = 2;
+        bisect = false;
+    } else {
+        const double area2 = result, error2 = abserr, resasc2 = resasc;
+        const double area12 = Q.area1 + area2, error12 = Q.error1 + error2;
+        Q.errsum += (error12 - Q.eI);
+        Q.area += area12 - Q.rI;
+        if (Q.resasc1 != Q.error1 && resasc2 != error2) {
+            const double delta = Q.rI - area12;
+            if (fabs(delta) <= 1.0e-5 * fabs(area12) && error12 >= 0.99 * Q.eI) Q.roundoff1++;
+            if (Q.iteration >= 10 && error12 > Q.eI) Q.roundoff2++;
+        }
+        Q.tolerance = fmax(Q.epsabs, Q.epsrel * fabs(Q.area));
+        if (Q.errsum > Q.tolerance) {
+            if (Q.roundoff1 >= 6 || Q.roundoff2 >= 20) Q.errorType = 2;
+            const double tmp = (1 + 100 * DBL_EPSILON) * (fabs(Q.a2) + 1000 * DBL_MIN);
+            if (fabs(Q.a1) <= tmp && fabs(Q.b2) <= tmp) Q.errorType = 3;
+        }
+        if (error2 > Q.error1) {
+            Q.alist[Q.iMax] = Q.a2;
+            Q.rlist[Q.iMax] = area2;
+            Q.elist[Q.iMax] = error2;
+            Q.alist[Q.size] = Q.a1;
+            Q.blist[Q.size] = Q.b1;
+            Q.rlist[Q.size] = Q.area1;
+            Q.elist[Q.size] = Q.error1;
+        } else {
+            Q.blist[Q.iMax] = Q.b1;
+            Q.rlist[Q.iMax] = Q.area1;
+            Q.elist[Q.iMax] = Q.error1;
+            Q.alist[Q.size] = Q.a2;
+            Q.blist[Q.size] = Q.b2;
+            Q.rlist[Q.size] = area2;
+            Q.elist[Q.size] = error2;
+        }
+        Q.size++;
+        Q.iteration++;
+        if (!(Q.iteration < 1000 && !Q.errorType && Q.errsum > Q.tolerance)) {
+            Q.busy = false;
+            Q.summed = true;
+        } else if (Q.size >= kQagLimitDevice) {
+            Q.status = 11;
+            Q.busy = false;
+            Q.summed = true;
+        }
+    }
+    if (Q.busy && bisect) {
+        // ---- bisect the interval with the largest error
+        Q.iMax = 0;
+        for (int i = 1; i < Q.size; i++)
+            if (Q.elist[i] > Q.elist[Q.iMax]) Q.iMax = i;
+        Q.rI = Q.rlist[Q.iMax];
+        Q.eI = Q.elist[Q.iMax];
+        Q.a1 = Q.alist[Q.iMax];
+        Q.b1 = 0.5 * (Q.alist[Q.iMax] + Q.blist[Q.iMax]);
+        Q.a2 = Q.b1;
+        Q.b2 = Q.blist[Q.iMax];
+        Q.ia = Q.a1;
+        Q.ib = Q.b1;
+        Q.phase = 1;
+    }
+}
+
+GLC_DEVICE_INLINE double qag_finish(QagState &Q) {
+    if (Q.summed) {
+        double sum = 0;
+        for (int i = 0; i < Q.size; i++) sum += Q.rlist[i];
+        if (Q.status == 0 && Q.errsum > Q.tolerance) Q.status = (Q.errorType == 2) ? 18 : ((Q.errorType == 3) ? 21 : 11);
+        Q.answer = sum;
+    }
+    return Q.answer;
+}
+
 // Warp-synchronous (see root_find): one pass of the loop = one 15-point rule on one (sub)interval.
 template <class F>
 GLC_DEVICE_INLINE double qag15(F &&f, bool on, double a, double b, double epsabs, double epsrel, int &status) {
-    double alist[kQagLimitDevice], blist[kQagLimitDevice], rlist[kQagLimitDevice], elist[kQagLimitDevice];
-    int size = 0, iteration = 0, errorType = 0, roundoff1 = 0, roundoff2 = 0;
-    double area = 0, errsum = 0, tolerance = 0;
-    status = 0;
-    // work list: first the whole interval, then (a1,b1),(a2,b2) of each bisection
-    double ia = a, ib = b;
-    int phase = 0;  // 0: initial interval, 1: first half, 2: second half
-    int iMax = 0;
-    double a1 = 0, b1 = 0, a2 = 0, b2 = 0, rI = 0, eI = 0;
-    double area1 = 0, error1 = 0, resasc1 = 0;
-    bool busy = on, summed = false;
-    double answer = 0.0;
-    while (GLC_ANY(busy)) {
-        if (busy) {
-            // ---- qk15 on (ia, ib): one call site of f
-            double result, abserr, resabs, resasc;
-            {
-                double fv[15];
-                const double center = 0.5 * (ia + ib);
-                const double halfLength = 0.5 * (ib - ia);
-                const double absHalfLength = fabs(halfLength);
-#pragma unroll 1
-                for (int j = 0; j < 15; j++) {
-                    double x;
-                    if (j == 0)
-                        x = center;
-                    else {
-                        const int k = c_qk_order[(j - 1) >> 1];
-                        const double absc = halfLength * c_xgk[k];
-                        x = ((j - 1) & 1) ? center + absc : center - absc;
-                    }
-                    fv[j] = f(x);
-                }
-                const double fCenter = fv[0];
-                double resultGauss = fCenter * c_wg[3];
-                double resultKronrod = fCenter * c_wgk[7];
-                double resultAbs = fabs(resultKronrod);
-#pragma unroll
-                for (int p = 0; p < 7; p++) {
-                    const int k = c_qk_order[p];
-                    const double f1 = fv[1 + 2 * p], f2 = fv[2 + 2 * p];
-                    if (p < 3) resultGauss += c_wg[p] * (f1 + f2);
-                    resultKronrod += c_wgk[k] * (f1 + f2);
-                    resultAbs += c_wgk[k] * (fabs(f1) + fabs(f2));
-                }
-                const double mean = resultKronrod * 0.5;
-                double resultAsc = c_wgk[7] * fabs(fCenter - mean);
-#pragma unroll
-                for (int k = 0; k < 7; k++) {
-                    const int p = c_qk_pos[k];
-                    resultAsc += c_wgk[k] * (fabs(fv[1 + 2 * p] - mean) + fabs(fv[2 + 2 * p] - mean));
-                }
-                const double err = (resultKronrod - resultGauss) * halfLength;
-                resultKronrod *= halfLength;
-                resultAbs *= absHalfLength;
-                resultAsc *= absHalfLength;
-                result = resultKronrod;
-                resabs = resultAbs;
-                resasc = resultAsc;
-                abserr = rescale_error(err, resultAbs, resultAsc);
-            }
-            bool bisect = true;
-            if (phase == 0) {
-                alist[0] = a;
-                blist[0] = b;
-                rlist[0] = result;
-                elist[0] = abserr;
-                size = 1;
-                tolerance = fmax(epsabs, epsrel * fabs(result));
-                const double roundOff = 50 * DBL_EPSILON * resabs;
-                if (abserr <= roundOff && abserr > tolerance) {
-                    status = 18;
-                    answer = result;
-                    busy = false;
-                } else if ((abserr <= tolerance && abserr != resasc) || abserr == 0.0) {
-                    answer = result;
-                    busy = false;
-                }
-                area = result;
-                errsum = abserr;
-                iteration = 1;
-            } else if (phase == 1) {
-                area1 = result;
-                error1 = abserr;
-                resasc1 = resasc;
-                ia = a2;
-                ib = b2;
-                phase = 2;
-                bisect = false;
-            } else {
-                const double area2 = result, error2 = abserr, resasc2 = resasc;
-                const double area12 = area1 + area2, error12 = error1 + error2;
-                errsum += (error12 - eI);
-                area += area12 - rI;
-                if (resasc1 != error1 && resasc2 != error2) {
-                    const double delta = rI - area12;
-                    if (fabs(delta) <= 1.0e-5 * fabs(area12) && error12 >= 0.99 * eI) roundoff1++;
-                    if (iteration >= 10 && error12 > eI) roundoff2++;
-                }
-                tolerance = fmax(epsabs, epsrel * fabs(area));
-                if (errsum > tolerance) {
-                    if (roundoff1 >= 6 || roundoff2 >= 20) errorType = 2;
-                    const double tmp = (1 + 100 * DBL_EPSILON) * (fabs(a2) + 1000 * DBL_MIN);
-                    if (fabs(a1) <= tmp && fabs(b2) <= tmp) errorType = 3;
-                }
-                if (error2 > error1) {
-                    alist[iMax] = a2;
-                    rlist[iMax] = area2;
-                    elist[iMax] = error2;
-                    alist[size] = a1;
-                    blist[size] = b1;
-                    rlist[size] = area1;
-                    elist[size] = error1;
-                } else {
-                    blist[iMax] = b1;
-                    rlist[iMax] = area1;
-                    elist[iMax] = error1;
-                    alist[size] = a2;
-                    blist[size] = b2;
-                    rlist[size] = area2;
-                    elist[size] = error2;
-                }
-                size++;
-                iteration++;
-                if (!(iteration < 1000 && !errorType && errsum > tolerance)) {
-                    busy = false;
-                    summed = true;
-                } else if (size >= kQagLimitDevice) {
-                    status = 11;
-                    busy = false;
-                    summed = true;
-                }
-            }
-            if (busy && bisect) {
-                // ---- bisect the interval with the largest error
-                iMax = 0;
-                for (int i = 1; i < size; i++)
-                    if (elist[i] > elist[iMax]) iMax = i;
-                rI = rlist[iMax];
-                eI = elist[iMax];
-                a1 = alist[iMax];
-                b1 = 0.5 * (alist[iMax] + blist[iMax]);
-                a2 = b1;
-                b2 = blist[iMax];
-                ia = a1;
-                ib = b1;
-                phase = 1;
-            }
-        }
+    QagState Q;
+    qag_begin(Q, on, a, b, epsabs, epsrel);
+    while (GLC_ANY(Q.busy != 0)) {
+        if (Q.busy) qag_pass(Q, f);
     }
-    if (summed) {
-        double sum = 0;
-        for (int i = 0; i < size; i++) sum += rlist[i];
-        if (status == 0 && errsum > tolerance) status = (errorType == 2) ? 18 : ((errorType == 3) ? 21 : 11);
-        answer = sum;
-    }
-    return answer;
+    const double r = qag_finish(Q);
+    status = Q.status;
+    return r;
 }
 
 // value of a table1DLinearLinear with n points on [xmin,xmax] populated by g (evaluated on the fly)

@@ -39,7 +39,7 @@ def lib() -> C.CDLL:
         L.emu_set_params.argtypes = [C.c_void_p, C.POINTER(abi.glc_params)]
         L.emu_set_table.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_void_p, _dp]
         L.emu_evolve_batch.argtypes = [C.c_void_p, C.c_int64, _dp, _ip, _dp, _ip, _ip, C.POINTER(abi.glc_counters),
-                                       C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
         _LIB = L
     return _LIB
 
@@ -47,10 +47,10 @@ def lib() -> C.CDLL:
 class EmuEvolver:
     """Same calling convention as galacticus_b200.Evolver.evolve_batch, executed lane by lane on the host."""
 
-    def __init__(self, nslots: int = 64, budget: int = 0, sort: bool = True):
+    def __init__(self, nslots: int = 64, budget: int = 0, sort: bool = True, machine: bool = True):
         self.L = lib()
         self.h = C.c_void_p(self.L.emu_create())
-        self.nslots, self.budget, self.sort = nslots, budget, sort
+        self.nslots, self.budget, self.sort, self.machine = nslots, budget, sort, machine
         self.slices = 0
         self._keep = []
 
@@ -82,7 +82,7 @@ class EmuEvolver:
         s = C.c_int64(0)
         te = np.ascontiguousarray(time_end, dtype=np.float64)
         rc = self.L.emu_evolve_batch(self.h, n, props, flags, te, status, interrupt, C.byref(c), self.nslots,
-                                     self.budget, int(self.sort), C.byref(s))
+                                     self.budget, int(self.sort), int(self.machine), C.byref(s))
         assert rc == 0
         self.slices = s.value
         return status, interrupt, abi.counters_dict(c)

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <random>
 #include <vector>
 
 #include "../../galacticus_b200/csrc/glc_common.cuh"
@@ -20,6 +21,7 @@
 #include "../../galacticus_b200/csrc/glc_evolve_kernel.cuh"
 #include "../../galacticus_b200/csrc/glc_model_box.cuh"
 #include "../../galacticus_b200/csrc/glc_model_standard.cuh"
+#include "../../galacticus_b200/csrc/glc_machine.cuh"
 
 using namespace glc;
 
@@ -77,7 +79,7 @@ static void run(Emu *e, int64_t n, double *props, int32_t *flags, const double *
             for (int it = 0; it < A.budget; ++it) {
                 bool any = false;
                 for (int s = w0; s < w1; s++) {
-                    LaneMem M{&A, A.ws + s};
+                    LaneMem M{&A, A.ws + s, A.nslots};
                     any |= lane_iterate<Model>(lanes[s], M);
                 }
                 if (!any) break;
@@ -92,6 +94,91 @@ static void run(Emu *e, int64_t n, double *props, int32_t *flags, const double *
                 hc[5] += L.nNodes;
                 hc[6] += L.nDone;
             }
+        }
+        (*slices)++;
+        if (hc[6] >= (unsigned long long)n) break;
+        A.resume = 1;
+    }
+    for (int64_t i = 0; i < n; i++)
+        for (int p = 0; p < NPROP; p++) props[i * NPROP + p] = soa[(size_t)p * cap + i];
+    if (counters) {
+        counters->steps_accepted = hc[0];
+        counters->steps_rejected = hc[1];
+        counters->rhs_evaluations = hc[2];
+        counters->segments = hc[3];
+        counters->trials_failed = hc[4];
+        counters->nodes = hc[5];
+    }
+}
+
+// The micro-task machine (glc_machine.cuh) driven on the host: every iteration each slot executes one unit; the
+// order in which the slots of a block are visited is shuffled (seeded) to mimic the device's regrouping, which
+// must not change any result.
+static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const double *time_end, int32_t *status,
+                        int32_t *interrupt, glc_counters *counters, int nslots, int budget, int sort, int64_t *slices) {
+    const int64_t cap = n;
+    std::vector<double> soa((size_t)NPROP * cap);
+    for (int64_t i = 0; i < n; i++)
+        for (int p = 0; p < NPROP; p++) soa[(size_t)p * cap + i] = props[i * NPROP + p];
+    std::vector<double> ws((size_t)WS_NVEC * NY * nslots);
+    std::vector<SlotState> slots(nslots);
+    std::vector<int32_t> order;
+    if (sort) {
+        order.resize(n);
+        for (int64_t i = 0; i < n; i++) order[i] = (int32_t)i;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int32_t a, int32_t b) { return queue_bucket(flags[a]) < queue_bucket(flags[b]); });
+    }
+    int work = 0;
+    unsigned long long hc[8] = {0};
+    KernelArgs A;
+    A.props = soa.data();
+    A.flags = flags;
+    A.time_end = time_end;
+    A.status = status;
+    A.interrupt = interrupt;
+    A.cap = cap;
+    A.n = (int)n;
+    A.ws = ws.data();
+    A.nslots = nslots;
+    A.work_counter = &work;
+    A.counters = hc;
+    A.order = sort ? order.data() : nullptr;
+    A.lanes = nullptr;
+    A.resume = 0;
+    A.budget = budget > 0 ? budget : 0x7fffffff;
+    *slices = 0;
+    std::mt19937 rng(12345);
+    std::vector<int> perm(nslots);
+    for (int s = 0; s < nslots; s++) perm[s] = s;
+    for (;;) {
+        for (int s = 0; s < nslots; s++) {
+            if (!A.resume) slot_reset(slots[s]);
+            if (slots[s].unit == U_IDLE) {
+                slots[s].L.phase = PH_FETCH;
+                slots[s].unit = U_RK;
+            }
+        }
+        for (int it = 0; it < A.budget; ++it) {
+            bool any = false;
+            std::shuffle(perm.begin(), perm.end(), rng);
+            for (int p = 0; p < nslots; p++) {
+                const int s = perm[p];
+                LaneMem M{&A, A.ws + (int64_t)s * (WS_NVEC * NY), 1};
+                any |= machine_step(slots[s], M);
+            }
+            if (!any) break;
+        }
+        for (int s = 0; s < nslots; s++) {
+            LaneState &L = slots[s].L;
+            hc[0] += L.nAcc;
+            hc[1] += L.nRej;
+            hc[2] += L.nRhs;
+            hc[3] += L.nSeg;
+            hc[4] += L.nTrialFail;
+            hc[5] += L.nNodes;
+            hc[6] += L.nDone;
+            L.nAcc = L.nRej = L.nRhs = L.nSeg = L.nTrialFail = L.nNodes = L.nDone = 0;
         }
         (*slices)++;
         if (hc[6] >= (unsigned long long)n) break;
@@ -134,7 +221,8 @@ int emu_set_table(void *h, int id, int n0, int n1, const double *x0, const doubl
 }
 
 int emu_evolve_batch(void *h, int64_t n, double *props, int32_t *flags, const double *time_end, int32_t *status,
-                     int32_t *interrupt, glc_counters *counters, int nslots, int budget, int sort, int64_t *slices) {
+                     int32_t *interrupt, glc_counters *counters, int nslots, int budget, int sort, int machine,
+                     int64_t *slices) {
     Emu *e = (Emu *)h;
     c_params = e->params;
     c_tables = e->dt;
@@ -144,6 +232,8 @@ int emu_evolve_batch(void *h, int64_t n, double *props, int32_t *flags, const do
     }
     if (e->params.model == GLC_MODEL_BOX)
         run<ModelBox>(e, n, props, flags, time_end, status, interrupt, counters, nslots, budget, sort, slices);
+    else if (machine)
+        run_machine(e, n, props, flags, time_end, status, interrupt, counters, nslots, budget, sort, slices);
     else
         run<ModelStandard>(e, n, props, flags, time_end, status, interrupt, counters, nslots, budget, sort, slices);
     return 0;
