@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <time.h>
+#include <unistd.h>
 
 #include "glc_common.cuh"
 #include "glc_tables_host.h"
@@ -57,7 +58,7 @@ struct glc_evolver {
     double *d_pow_ac = nullptr, *d_pow_kmt = nullptr;  // fastExponentiator tables
     double pow_ac_exponent = 0.0;
     LaneState *d_lanes = nullptr;   // parked lane states, one per resident lane
-    SlotState *d_slots = nullptr;   // micro-task machine: one continuation per resident slot
+    SlotArrays d_slots{};           // micro-task machine: per-slot continuations, split by access group
     int64_t nslots_machine = 0;
     int32_t use_machine = 1;        // standard model: 1 = micro-task machine, 0 = warp-synchronous evolve_kernel
     int32_t *d_order = nullptr;     // queue order (component-sorted node ids)
@@ -307,16 +308,34 @@ static int launch_evolve(glc_evolver *ev, int n, unsigned long long *hc) {
     return 0;
 }
 
+static void free_slots(glc_evolver *ev) {
+    cudaFree(ev->d_slots.L);
+    cudaFree(ev->d_slots.R);
+    cudaFree(ev->d_slots.root);
+    cudaFree(ev->d_slots.yt);
+    cudaFree(ev->d_slots.Q);
+    cudaFree(ev->d_slots.unit);
+    ev->d_slots = SlotArrays{};
+    ev->nslots_machine = 0;
+}
+
 // One batch on the micro-task machine (standard model): same slice protocol as launch_evolve.
 static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc) {
+    constexpr size_t kMachineSmem = sizeof(unsigned short) * (size_t)U_IDLE * GLC_MSLOTS;
+    GLC_CHECK(ev, cudaFuncSetAttribute(machine_kernel<GLC_MTHREADS, GLC_MSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kMachineSmem));
     const int gridMax = ev->num_sms;  // one block per SM
     int grid = std::min(gridMax, (n + GLC_MSLOTS - 1) / GLC_MSLOTS);
     if (grid < 1) grid = 1;
     const int64_t need = (int64_t)gridMax * GLC_MSLOTS;
     if (need > ev->nslots_machine) {
-        cudaFree(ev->d_slots);
-        ev->d_slots = nullptr;
-        GLC_CHECK(ev, cudaMalloc(&ev->d_slots, sizeof(SlotState) * need));
+        free_slots(ev);
+        GLC_CHECK(ev, cudaMalloc(&ev->d_slots.L, sizeof(LaneState) * need));
+        GLC_CHECK(ev, cudaMalloc(&ev->d_slots.R, sizeof(RhsState) * need));
+        GLC_CHECK(ev, cudaMalloc(&ev->d_slots.root, sizeof(RootState) * need));
+        GLC_CHECK(ev, cudaMalloc(&ev->d_slots.yt, sizeof(double) * NY * need));
+        GLC_CHECK(ev, cudaMalloc(&ev->d_slots.Q, sizeof(QagState) * need));
+        GLC_CHECK(ev, cudaMalloc(&ev->d_slots.unit, sizeof(int) * need));
         ev->nslots_machine = need;
     }
     int rc = ensure_workspace(ev, (int)((need + kBlock - 1) / kBlock));
@@ -340,18 +359,55 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc) {
     A.lanes = nullptr;
     A.resume = 0;
     A.budget = ev->slice_budget > 0 ? ev->slice_budget : 0x7fffffff;
+    A.debug = nullptr;
+#ifdef GLC_DEBUG_HANG
+    static int *h_dbg = nullptr;
+    const int nDbg = gridMax * (GLC_MTHREADS / 32) * 8;
+    if (!h_dbg) cudaHostAlloc(&h_dbg, sizeof(int) * nDbg, cudaHostAllocMapped);
+    memset(h_dbg, 0, sizeof(int) * nDbg);
+    {
+        int *d_dbg = nullptr;
+        cudaHostGetDevicePointer(&d_dbg, h_dbg, 0);
+        A.debug = d_dbg;
+    }
+#endif
     GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
     GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 8, ev->stream));
     const double t_start = now_s();
     int nslice = 0;
     unsigned long long tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (;;) {
-        machine_kernel<GLC_MTHREADS, GLC_MSLOTS><<<grid, GLC_MTHREADS, 0, ev->stream>>>(A, ev->d_slots);
+        if (ev->slice_log > 1) fprintf(stderr, "[glc host] launching machine_kernel grid=%d budget=%d resume=%d n=%d\n", grid, A.budget, A.resume, n);
+        machine_kernel<GLC_MTHREADS, GLC_MSLOTS><<<grid, GLC_MTHREADS, kMachineSmem, ev->stream>>>(A, ev->d_slots);
         ev->launches++;
         ev->slices++;
         GLC_CHECK(ev, cudaGetLastError());
+        if (ev->slice_log > 1) fprintf(stderr, "[glc host] launched; copying counters\n");
+#ifdef GLC_DEBUG_HANG
+        {
+            const double t0 = now_s();
+            bool dumped = false;
+            while (cudaStreamQuery(ev->stream) == cudaErrorNotReady) {
+                if (!dumped && now_s() - t0 > 8.0) {
+                    dumped = true;
+                    fprintf(stderr, "[glc hang] kernel still running after 8 s; per-warp progress (state it u start take idle lane slot):\n");
+                    for (int b = 0; b < grid; b++)
+                        for (int w = 0; w < GLC_MTHREADS / 32; w++) {
+                            const int *d = h_dbg + ((size_t)b * (GLC_MTHREADS / 32) + w) * 8;
+                            fprintf(stderr, "  block %d warp %2d: state %d it %d u %d start %d take %d idle %d lane %d slot %d\n", b, w,
+                                    d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+                        }
+                }
+                if (now_s() - t0 > 20.0) {
+                    fprintf(stderr, "[glc hang] giving up\n");
+                    _exit(3);
+                }
+            }
+        }
+#endif
         GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost,
                                       ev->stream));
+        if (ev->slice_log > 1) fprintf(stderr, "[glc host] counters copy issued: done=%llu\n", hc[6]);
         if (ev->slice_budget <= 0) break;
         GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
         if (ev->slice_log)
@@ -440,7 +496,7 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaFree(ev->d_pow_ac);
     cudaFree(ev->d_pow_kmt);
     cudaFree(ev->d_lanes);
-    cudaFree(ev->d_slots);
+    free_slots(ev);
     cudaFree(ev->d_order);
     cudaFree(ev->d_sort);
     cudaEventDestroy(ev->ev0);

@@ -150,6 +150,7 @@ struct KernelArgs {
     struct LaneState *lanes;       // [nslots] parked lane states
     int resume;                    // 0: first slice of a batch (lanes start empty), 1: resume parked lanes
     int budget;                    // heavy calls per lane in this slice
+    volatile int *debug;           // GLC_DEBUG_HANG builds: host-mapped per-warp progress words (else null)
 };
 
 // Per-node context kept in registers while a node is resident in a thread.

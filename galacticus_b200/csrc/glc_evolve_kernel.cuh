@@ -31,6 +31,16 @@
 #define GTR(...)
 #endif
 
+// NB: the 24-component loops of the RK bookkeeping are kept rolled (#pragma unroll 1): the kernels are
+// instruction-fetch bound, not issue bound, so a compact loop that runs out of the L0 instruction cache beats
+// 24 unrolled copies streamed from L2.
+
+#ifdef GLC_RK_FULL_UNROLL
+#define GLC_UNROLL_RK _Pragma("unroll")
+#else
+#define GLC_UNROLL_RK _Pragma("unroll 1")
+#endif
+
 namespace glc {
 
 // Cash-Karp tableau (Cash & Karp 1990). Row s = weights of k1..k6 used to build the input of
@@ -125,7 +135,7 @@ GLC_DEVICE_INLINE void lane_writeback(LaneState &L, const LaneMem &M, double (&y
         }
         code = GLC_INT_NONE;
     }
-#pragma unroll
+GLC_UNROLL_RK
     for (int i = 0; i < NY; i++) M.AR(i, node) = yt[i];
     M.AR(GLC_P_TIME, node) = timeOut;
     M.AR(GLC_P_TIME_STEP, node) = timeStepOut;
@@ -179,7 +189,7 @@ GLC_DEVICE_INLINE void lane_prepare(LaneState &L, const LaneMem &M, double (&yt)
             const int node = L.node;
             NodeCtx &ctx = L.ctx;
             double s[NY];
-#pragma unroll
+GLC_UNROLL_RK
             for (int i = 0; i < NY; i++) {
                 yt[i] = M.AR(i, node);
                 s[i] = 0.0;
@@ -212,7 +222,7 @@ GLC_DEVICE_INLINE void lane_prepare(LaneState &L, const LaneMem &M, double (&yt)
                 const int flagsBefore = ctx.flags;
                 Model::pre_evolve(ctx, yt);
                 if (ctx.flags != flagsBefore) {
-#pragma unroll
+GLC_UNROLL_RK
                     for (int i = 0; i < NY; i++) M.AR(i, node) = yt[i];
                     M.AR(GLC_P_BASIC_MASS, node) = ctx.basicMass;
                     A.flags[node] = ctx.flags;
@@ -220,7 +230,7 @@ GLC_DEVICE_INLINE void lane_prepare(LaneState &L, const LaneMem &M, double (&yt)
             }
             L.mask = Model::active_mask(ctx.flags);
             Model::scales(ctx, yt, s);
-#pragma unroll
+GLC_UNROLL_RK
             for (int i = 0; i < NY; i++) {
                 M.W(WS_YA, i) = yt[i];
                 M.W(WS_SCALE, i) = s[i];
@@ -237,7 +247,7 @@ GLC_DEVICE_INLINE void lane_prepare(LaneState &L, const LaneMem &M, double (&yt)
         // ------------------------------ trial start (:587-652) + odeSolverSolve prologue
         if (L.phase == PH_TRIAL) {
             if (L.trial > 0) {
-#pragma unroll
+GLC_UNROLL_RK
                 for (int i = 0; i < NY; i++) M.W(WS_YA, i) = M.AR(i, L.node);
             }
             L.yslot = 0;
@@ -282,17 +292,17 @@ GLC_DEVICE_INLINE void lane_prepare(LaneState &L, const LaneMem &M, double (&yt)
             const double h0 = L.h0;
             L.ts = L.t0 + c_rk_a[stage] * h0;
             if (stage == 0) {
-#pragma unroll
+GLC_UNROLL_RK
                 for (int i = 0; i < NY; i++) yt[i] = M.W(ySrc, i);
             } else if (stage == 1) {
                 const double b10 = c_rk_b[1][0];
-#pragma unroll
+GLC_UNROLL_RK
                 for (int i = 0; i < NY; i++) yt[i] = M.W(ySrc, i) + b10 * h0 * M.W(k1v, i);  // rkck.c: y + b21*h*k1
             } else if (stage < 6) {
                 double b[5];
-#pragma unroll
+GLC_UNROLL_RK
                 for (int j = 0; j < 5; j++) b[j] = c_rk_b[stage][j];
-#pragma unroll
+GLC_UNROLL_RK
                 for (int i = 0; i < NY; i++) {
                     double acc = b[0] * M.W(k1v, i);
                     for (int j = 1; j < stage; j++) acc += b[j] * M.W(WS_K2 + j - 1, i);
@@ -305,7 +315,7 @@ GLC_DEVICE_INLINE void lane_prepare(LaneState &L, const LaneMem &M, double (&yt)
                 const bool nonNeg = GLC_PARAMS.enforceNonNegativity != 0;
                 double rmax = L.rmax;
                 int forbidden = L.forbiddenNegatives;
-#pragma unroll
+GLC_UNROLL_RK
                 for (int i = 0; i < NY; i++) {
                     const double k1 = M.W(k1v, i), k3 = M.W(WS_K3, i), k4 = M.W(WS_K4, i), k5 = M.W(WS_K5, i),
                                  k6 = M.W(WS_K6, i);
@@ -339,12 +349,12 @@ GLC_DEVICE_INLINE void lane_prepare(LaneState &L, const LaneMem &M, double (&yt)
         // -------------------------------- trial epilogue + standardEvolve epilogue (:657-753), part 1
         if (L.phase == PH_SOLVE_DONE) {
             const int yv = WS_YA + L.yslot;
-#pragma unroll
+GLC_UNROLL_RK
             for (int i = 0; i < NY; i++) yt[i] = M.W(yv, i);
             if (L.solveFailed) {
                 int rescued = 0;
                 if (GLC_PARAMS.enforceNonNegativity) {
-#pragma unroll
+GLC_UNROLL_RK
                     for (int i = 0; i < NY; i++)
                         if ((L.mask & (1u << i)) && prop_is_non_negative(i) && yt[i] < 0.0) {
                             yt[i] = 0.0;
@@ -402,7 +412,7 @@ GLC_DEVICE_INLINE void lane_consume(LaneState &L, const LaneMem &M, double (&yt)
     // ---- standardODEs, part 2 (interrupt bookkeeping :901-928)
     int ebadfunc = 0;
     if (L.heavy == HV_RHS && code != GLC_INT_NONE) {
-#pragma unroll
+GLC_UNROLL_RK
         for (int i = 0; i < NY; i++) rate[i] = 0.0;
         if (L.ts < L.timeInterruptFirst || !L.interruptFound) {
             L.interruptFound = 1;
@@ -415,7 +425,7 @@ GLC_DEVICE_INLINE void lane_consume(LaneState &L, const LaneMem &M, double (&yt)
         const int stage = L.stage;
         const int kv = (stage == 0) ? WS_KA + L.kslot : ((stage == 6) ? WS_KA + (L.kslot ^ 1) : WS_K2 + stage - 1);
         int nonfinite = 0;
-#pragma unroll
+GLC_UNROLL_RK
         for (int i = 0; i < NY; i++) {
             const double r = (L.mask & (1u << i)) ? rate[i] : 0.0;
             if (!isfinite(r)) nonfinite = 1;
@@ -431,7 +441,7 @@ GLC_DEVICE_INLINE void lane_consume(LaneState &L, const LaneMem &M, double (&yt)
         L.x1 = L.timeInterruptFirst;
         L.inApply = 0;
         if (L.x > L.x1) {
-#pragma unroll
+GLC_UNROLL_RK
             for (int i = 0; i < NY; i++) M.W(WS_YA, i) = M.AR(i, L.node);
             L.yslot = 0;
             L.x = L.timeStartSaved;
@@ -491,12 +501,12 @@ GLC_DEVICE_INLINE void lane_consume(LaneState &L, const LaneMem &M, double (&yt)
     {
         // standardPostStepProcessing (rate[] is dead here and is re-used as the state buffer)
         const int yv = WS_YA + L.yslot;
-#pragma unroll
+GLC_UNROLL_RK
         for (int i = 0; i < NY; i++) rate[i] = M.W(yv, i);
         Model::solve_analytics(L.ctx, L.x);
         const int st = Model::post_step(L.ctx, rate);
         if (st != kGslSuccess) {
-#pragma unroll
+GLC_UNROLL_RK
             for (int i = 0; i < NY; i++) M.W(yv, i) = rate[i];
         }
         if (st != kGslSuccess && st != kGslContinue) L.count = 0;  // gsl_odeiv2_evolve_reset
@@ -510,7 +520,7 @@ GLC_DEVICE_INLINE bool lane_iterate(LaneState &L, const LaneMem &M) {
     double yt[NY], rate[NY];
     lane_prepare<Model>(L, M, yt);
     int code = GLC_INT_NONE;
-#pragma unroll
+GLC_UNROLL_RK
     for (int i = 0; i < NY; i++) rate[i] = 0.0;
     // The single heavy call site.  Warp-synchronous: every lane of the warp calls it in every iteration (idle and
     // frozen lanes with on = false), so the votes inside the rate function see the whole warp.

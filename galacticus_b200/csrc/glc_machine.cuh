@@ -31,15 +31,17 @@ enum Unit : int {
     U_RK = 0,       // rate accumulation of the finished evaluation + RK bookkeeping up to the next evaluation
     U_RHS_BEGIN,    // halo scales, hot-halo profile, plausibility, NFW normalisation
     U_STRUCT,       // structure solver: one (iteration, component) visit up to its root find
-    U_STRUCT_FIN,   // structure solver: digest the root, fixed-point update
     U_ROOT_AC,      // Brent step + adiabatic-contraction function
+    U_STRUCT_FIN,   // structure solver: digest the root, fixed-point update
     U_ROOT_J,       // Brent step + specific-angular-momentum function (first-guess radius)
-    U_ROOT_TRUNC,   // Brent step + surface-density truncation function
-    U_ROOT_CRIT,    // Brent step + critical-surface-density function
-    U_ROOT_COOL,    // Brent step + cooling-time function
     U_SFR_BEGIN,    // Krumholz-McKee-Tumlinson set-up
+    U_ROOT_TRUNC,   // Brent step + surface-density truncation function
+    U_SFR_MID,      // after the truncation radius: second root find or the integration intervals
+    U_ROOT_CRIT,    // Brent step + critical-surface-density function
+    U_SFR_MID2,     // after the critical radius: the integration intervals
     U_QAG,          // one 15-point Gauss-Kronrod pass of the star-formation-rate integral
     U_COOL_BEGIN,   // CIE table look-ups + cooling-radius shortcuts
+    U_ROOT_COOL,    // Brent step + cooling-time function
     U_IDLE,
     U_COUNT
 };
@@ -53,25 +55,50 @@ struct RhsState {
     MS::AcProblem ac;
     MS::SfrProblem sfr;
     double lo[2], hi[2], total, psiDisk, rinfall, logSlopeT;
-    int count, comp, active, bad, structureOnly, go, dOn, coolOn, radiusOn, two, nIv, iv, guess;
+    int count, comp, active, bad, structureOnly, go, dOn, coolOn, radiusOn, two, nIv, iv, guess, pad;
 };
 
-struct SlotState {
-    LaneState L;
-    RhsState R;
+// Everything a root-find unit touches: the Brent state and the parameters of the function being solved.
+//   AC    p = {nfwNorm, rs, rvir, fi, fd, radius, bterm}      J     p = {nfwNorm, rs, lnj}
+//   TRUNC/CRIT p = {sigma0, rdisk, sigmaTrunc, xh}
+//   COOL  p = {coolXH, coolFHn, coolEfrac, coolLambda, tvir, coolTavail, hhRho0, hhRcore, hhRouter, hhValid}
+struct RootState {
     BrentState B;
-    double yt[NY];
-    int unit, pad;
-    QagState Q;
+    double p[10];
+    double pad;  // 256 bytes = two 128-byte lines
 };
+static_assert(sizeof(RootState) == 256, "RootState must stay two cache lines");
 
-GLC_DEVICE_INLINE void slot_reset(SlotState &S) {
+// The per-slot continuation, split by access group into separate HBM arrays so that the most frequent units
+// (root-find steps: ~2/3 of all unit executions) touch one compact 256-byte record that stays L2-resident.
+struct SlotArrays {
+    LaneState *L;
+    RhsState *R;
+    RootState *root;
+    double *yt;  // [nslots][NY]
+    QagState *Q;
+    int *unit;
+};
+struct SlotRef {
+    LaneState &L;
+    RhsState &R;
+    BrentState &B;
+    double (&p)[10];
+    double (&yt)[NY];
+    QagState &Q;
+    int &unit;
+};
+GLC_DEVICE_INLINE SlotRef slot_ref(const SlotArrays &a, int64_t s) {
+    return SlotRef{a.L[s], a.R[s], a.root[s].B, a.root[s].p, *reinterpret_cast<double (*)[NY]>(a.yt + s * NY), a.Q[s], a.unit[s]};
+}
+
+GLC_DEVICE_INLINE void slot_reset(const SlotRef &S) {
     lane_reset(S.L);
     S.unit = U_RK;
 }
 
 // ---------------------------------------------------------------- cheap transitions (a few instructions)
-GLC_DEVICE_INLINE void m_cool_decide(SlotState &S) {
+GLC_DEVICE_INLINE void m_cool_decide(const SlotRef &S) {
     RhsState &R = S.R;
     R.coolOn = MS::cooling_on(S.L.ctx, S.yt, R.w, R.go != 0) ? 1 : 0;
     R.radiusOn = MS::cooling_radius_on(R.w, R.coolOn != 0) ? 1 : 0;
@@ -80,7 +107,7 @@ GLC_DEVICE_INLINE void m_cool_decide(SlotState &S) {
     S.unit = R.radiusOn ? U_COOL_BEGIN : U_RK;
 }
 
-GLC_DEVICE_INLINE void m_after_struct(SlotState &S) {
+GLC_DEVICE_INLINE void m_after_struct(const SlotRef &S) {
     RhsState &R = S.R;
     R.psiDisk = 0.0;
     R.rinfall = 0.0;
@@ -101,7 +128,7 @@ GLC_DEVICE_INLINE void m_after_struct(SlotState &S) {
 
 // loop control of galacticStructureSolverEquilibrium::solve (equilibrium.F90:278-292): next component to
 // visit, next iteration, or convergence
-GLC_DEVICE_INLINE void m_struct_next(SlotState &S) {
+GLC_DEVICE_INLINE void m_struct_next(const SlotRef &S) {
     RhsState &R = S.R;
     const double tolerance = GLC_PARAMS.structureSolutionTolerance;
     for (;;) {
@@ -125,24 +152,50 @@ GLC_DEVICE_INLINE void m_struct_next(SlotState &S) {
     m_after_struct(S);
 }
 
-GLC_DEVICE_INLINE void m_root_complete(SlotState &S, int unit);
-
-// first advance of a freshly initialised root find: usually yields the first abscissa
-GLC_DEVICE_INLINE void m_root_start(SlotState &S, int unit) {
-    brent_advance(S.B);
-    if (S.B.busy)
-        S.unit = unit;
+template <int UNIT>
+GLC_DEVICE_INLINE RootOptions m_root_options() {
+    return UNIT == U_ROOT_AC     ? MS::ac_root_options()
+           : UNIT == U_ROOT_J    ? MS::jroot_options()
+           : UNIT == U_ROOT_COOL ? MS::cooling_root_options()
+                                 : MS::sfr_root_options();
+}
+// unit that digests the finished root find of type UNIT
+template <int UNIT>
+GLC_DEVICE_INLINE int m_root_done_unit() {
+    return (UNIT == U_ROOT_AC || UNIT == U_ROOT_J) ? U_STRUCT_FIN
+           : UNIT == U_ROOT_TRUNC                  ? U_SFR_MID
+           : UNIT == U_ROOT_CRIT                   ? U_SFR_MID2
+                                                   : U_RK;
+}
+template <int UNIT>
+GLC_DEVICE_INLINE void m_root_finish(const SlotRef &S) {
+    if (UNIT == U_ROOT_COOL) {
+        S.R.rinfall = S.B.result;
+        if (S.B.status != 0) S.R.bad = 1;
+    }
+    S.unit = m_root_done_unit<UNIT>();
+}
+// initialise a root find and run the state machine to its first abscissa
+template <int UNIT>
+GLC_DEVICE_INLINE void m_root_start(const SlotRef &S, double xLow, double xHigh, bool haveValues, double fLow,
+                                    double fHigh) {
+    BrentState B;
+    brent_begin(B, true, xLow, xHigh, haveValues, fLow, fHigh);
+    brent_advance(B, m_root_options<UNIT>());
+    S.B = B;
+    if (B.busy)
+        S.unit = UNIT;
     else
-        m_root_complete(S, unit);
+        m_root_finish<UNIT>(S);
 }
 
-GLC_DEVICE_INLINE void m_qag_start(SlotState &S) {
+GLC_DEVICE_INLINE void m_qag_start(const SlotRef &S) {
     RhsState &R = S.R;
     qag_begin(S.Q, true, R.lo[R.iv], R.hi[R.iv], 1.0e-12, GLC_PARAMS.sfrIntegrationTolerance);
     S.unit = U_QAG;
 }
 
-GLC_DEVICE_INLINE void m_sfr_intervals(SlotState &S, double rCrit) {
+GLC_DEVICE_INLINE void m_sfr_intervals(const SlotRef &S, double rCrit) {
     RhsState &R = S.R;
     R.lo[0] = 0.0;
     R.lo[1] = rCrit;
@@ -154,41 +207,33 @@ GLC_DEVICE_INLINE void m_sfr_intervals(SlotState &S, double rCrit) {
     m_qag_start(S);
 }
 
-GLC_DEVICE_INLINE void m_sfr_after_trunc(SlotState &S, double rTrunc, int st) {
+GLC_DEVICE_INLINE void m_sfr_root_params(const SlotRef &S) {
+    const MS::Kmt &k = S.R.sfr.k;
+    S.p[0] = k.sigma0;
+    S.p[1] = k.rdisk;
+    S.p[2] = k.sigmaTrunc;
+    S.p[3] = k.xh;
+}
+
+GLC_DEVICE_INLINE void m_sfr_after_trunc(const SlotRef &S, double rTrunc, int st) {
     RhsState &R = S.R;
     R.two = MS::sfr_after_trunc(R.sfr, rTrunc, st, R.bad) ? 1 : 0;
     if (R.two) {
-        brent_begin(S.B, true, MS::sfr_root_options(), 0.0, R.sfr.rMax, false, 0.0, 0.0);
-        m_root_start(S, U_ROOT_CRIT);
+        m_sfr_root_params(S);
+        m_root_start<U_ROOT_CRIT>(S, 0.0, R.sfr.rMax, false, 0.0, 0.0);
     } else
         m_sfr_intervals(S, 0.0);
-}
-
-GLC_DEVICE_INLINE void m_root_complete(SlotState &S, int unit) {
-    RhsState &R = S.R;
-    if (unit == U_ROOT_AC || unit == U_ROOT_J) {
-        S.unit = U_STRUCT_FIN;
-    } else if (unit == U_ROOT_TRUNC) {
-        m_sfr_after_trunc(S, S.B.result, S.B.status);
-    } else if (unit == U_ROOT_CRIT) {
-        if (S.B.status != 0) R.bad = 1;
-        m_sfr_intervals(S, S.B.result);
-    } else {  // U_ROOT_COOL
-        R.rinfall = S.B.result;
-        if (S.B.status != 0) R.bad = 1;
-        S.unit = U_RK;
-    }
 }
 
 // ---------------------------------------------------------------- the units
 // U_RK: rates_accumulate of the evaluation whose nested solvers have just finished, lane_consume (store the
 // stage derivative; at the end of an attempt: controller, accept/reject, post-step), lane_prepare (next stage
 // input, or epilogue/fetch/prologue).
-GLC_DEVICE_INLINE void unit_rk(SlotState &S, const LaneMem &M) {
+GLC_DEVICE_NOINLINE void unit_rk(const SlotRef S, const LaneMem M) {
     LaneState L = S.L;
     double yt[NY], rate[NY];
     int code = GLC_INT_NONE;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < NY; i++) {
         yt[i] = S.yt[i];
         rate[i] = 0.0;
@@ -203,7 +248,7 @@ GLC_DEVICE_INLINE void unit_rk(SlotState &S, const LaneMem &M) {
         lane_prepare<MS>(L, M, yt);
         if (L.heavy != HV_FROZEN) break;
         code = GLC_INT_NONE;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < NY; i++) rate[i] = 0.0;
     }
     S.L = L;
@@ -211,12 +256,12 @@ GLC_DEVICE_INLINE void unit_rk(SlotState &S, const LaneMem &M) {
         S.unit = U_IDLE;
         return;
     }
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < NY; i++) S.yt[i] = yt[i];
     S.unit = U_RHS_BEGIN;
 }
 
-GLC_DEVICE_INLINE void unit_rhs_begin(SlotState &S) {
+GLC_DEVICE_NOINLINE void unit_rhs_begin(const SlotRef S) {
     RhsState &R = S.R;
     NodeCtx &c = S.L.ctx;
     Work w;
@@ -242,7 +287,7 @@ GLC_DEVICE_INLINE void unit_rhs_begin(SlotState &S) {
 }
 
 // one (iteration, component) visit of the structure solver, up to the point where a root is needed
-GLC_DEVICE_INLINE void unit_struct(SlotState &S) {
+GLC_DEVICE_NOINLINE void unit_struct(const SlotRef S) {
     RhsState &R = S.R;
     NodeCtx &c = S.L.ctx;
     const int comp = R.comp;
@@ -259,8 +304,10 @@ GLC_DEVICE_INLINE void unit_struct(SlotState &S) {
                 R.lnj = dm_log(j);
                 const double lnrv = dm_log(R.w.rvir);
                 R.guess = 1;
-                brent_begin(S.B, true, MS::jroot_options(), lnrv - 4.0, lnrv, false, 0.0, 0.0);
-                m_root_start(S, U_ROOT_J);
+                S.p[0] = R.nfwNorm;
+                S.p[1] = c.dmScale;
+                S.p[2] = R.lnj;
+                m_root_start<U_ROOT_J>(S, lnrv - 4.0, lnrv, false, 0.0, 0.0);
                 return;
             }
             radius = 0.0;  // nfw_radius_from_j of a non-positive j
@@ -285,8 +332,14 @@ GLC_DEVICE_INLINE void unit_struct(SlotState &S) {
     if (GLC_PARAMS.adiabaticContraction && !(radius <= 0.0)) MS::ac_setup(c, S.yt, R.w, R.nfwNorm, radius, P);
     R.ac = P;
     if (P.need) {
-        brent_begin(S.B, true, MS::ac_root_options(), radius, P.rup, false, 0.0, 0.0);
-        m_root_start(S, U_ROOT_AC);
+        S.p[0] = R.nfwNorm;
+        S.p[1] = c.dmScale;
+        S.p[2] = R.w.rvir;
+        S.p[3] = P.fi;
+        S.p[4] = P.fd;
+        S.p[5] = radius;
+        S.p[6] = P.bterm;
+        m_root_start<U_ROOT_AC>(S, radius, P.rup, false, 0.0, 0.0);
     } else {
         S.B.busy = 0;
         S.B.status = 0;
@@ -296,7 +349,7 @@ GLC_DEVICE_INLINE void unit_struct(SlotState &S) {
 
 // digest the root of a structure visit: first-guess radius, or the contracted dark-matter mass and the
 // fixed-point update
-GLC_DEVICE_INLINE void unit_struct_fin(SlotState &S) {
+GLC_DEVICE_NOINLINE void unit_struct_fin(const SlotRef S) {
     RhsState &R = S.R;
     NodeCtx &c = S.L.ctx;
     const int comp = R.comp;
@@ -329,31 +382,54 @@ GLC_DEVICE_INLINE void unit_struct_fin(SlotState &S) {
     m_struct_next(S);
 }
 
-GLC_DEVICE_INLINE void unit_root(SlotState &S, int unit) {
-    RhsState &R = S.R;
+// One Brent step: evaluate the function at the pending abscissa, digest it, advance to the next abscissa.
+// Touches only the slot's RootState record.
+template <int UNIT>
+GLC_DEVICE_NOINLINE void unit_root(const SlotRef S) {
     BrentState B = S.B;
     const double x = B.x;
     double fx;
-    if (unit == U_ROOT_AC) {
+    if (UNIT == U_ROOT_AC) {
         GLC_COUNT(0);
-        fx = MS::ac_function(R.nfwNorm, S.L.ctx.dmScale, R.w, R.ac, R.radius, x);
-    } else if (unit == U_ROOT_J) {
-        fx = MS::jroot_function(R.nfwNorm, S.L.ctx.dmScale, R.lnj, x);
-    } else if (unit == U_ROOT_TRUNC) {
-        fx = MS::sfr_trunc_function(R.sfr.k, x);
-    } else if (unit == U_ROOT_CRIT) {
-        fx = MS::sfr_crit_function(R.sfr.k, x);
+        Work w;
+        w.rvir = S.p[2];
+        MS::AcProblem P;
+        P.fi = S.p[3];
+        P.fd = S.p[4];
+        P.bterm = S.p[6];
+        fx = MS::ac_function(S.p[0], S.p[1], w, P, S.p[5], x);
+    } else if (UNIT == U_ROOT_J) {
+        fx = MS::jroot_function(S.p[0], S.p[1], S.p[2], x);
+    } else if (UNIT == U_ROOT_TRUNC || UNIT == U_ROOT_CRIT) {
+        MS::Kmt k;
+        k.sigma0 = S.p[0];
+        k.rdisk = S.p[1];
+        k.sigmaTrunc = S.p[2];
+        k.xh = S.p[3];
+        fx = (UNIT == U_ROOT_TRUNC) ? MS::sfr_trunc_function(k, x) : MS::sfr_crit_function(k, x);
     } else {
         GLC_COUNT(3);
-        fx = MS::cooling_function(R.w, x);
+        Work w;
+        w.coolXH = S.p[0];
+        w.coolFHn = S.p[1];
+        w.coolEfrac = S.p[2];
+        w.coolLambda = S.p[3];
+        w.tvir = S.p[4];
+        w.coolTavail = S.p[5];
+        w.hhRho0 = S.p[6];
+        w.hhRcore = S.p[7];
+        w.hhRouter = S.p[8];
+        w.hhValid = S.p[9] != 0.0;
+        fx = MS::cooling_function(w, x);
     }
-    brent_feed(B, fx);
-    brent_advance(B);
+    const RootOptions o = m_root_options<UNIT>();
+    brent_feed(B, o, fx);
+    brent_advance(B, o);
     S.B = B;
-    if (!B.busy) m_root_complete(S, unit);
+    if (!B.busy) m_root_finish<UNIT>(S);
 }
 
-GLC_DEVICE_INLINE void unit_sfr_begin(SlotState &S) {
+GLC_DEVICE_NOINLINE void unit_sfr_begin(const SlotRef S) {
     RhsState &R = S.R;
     MS::sfr_setup(S.L.ctx, S.yt, true, R.sfr);
     if (!R.sfr.live) {
@@ -362,13 +438,18 @@ GLC_DEVICE_INLINE void unit_sfr_begin(SlotState &S) {
         return;
     }
     if (R.sfr.needRmax) {
-        brent_begin(S.B, true, MS::sfr_root_options(), 0.0, R.sfr.rOut, false, 0.0, 0.0);
-        m_root_start(S, U_ROOT_TRUNC);
+        m_sfr_root_params(S);
+        m_root_start<U_ROOT_TRUNC>(S, 0.0, R.sfr.rOut, false, 0.0, 0.0);
     } else
         m_sfr_after_trunc(S, 0.0, 0);
 }
+GLC_DEVICE_NOINLINE void unit_sfr_mid(const SlotRef S) { m_sfr_after_trunc(S, S.B.result, S.B.status); }
+GLC_DEVICE_NOINLINE void unit_sfr_mid2(const SlotRef S) {
+    if (S.B.status != 0) S.R.bad = 1;
+    m_sfr_intervals(S, S.B.result);
+}
 
-GLC_DEVICE_INLINE void unit_qag(SlotState &S) {
+GLC_DEVICE_NOINLINE void unit_qag(const SlotRef S) {
     RhsState &R = S.R;
     const MS::Kmt k = R.sfr.k;
     qag_pass(S.Q, [&](double r) {
@@ -388,7 +469,7 @@ GLC_DEVICE_INLINE void unit_qag(SlotState &S) {
     m_cool_decide(S);
 }
 
-GLC_DEVICE_INLINE void unit_cool_begin(SlotState &S) {
+GLC_DEVICE_NOINLINE void unit_cool_begin(const SlotRef S) {
     RhsState &R = S.R;
     Work w = R.w;
     double logSlopeT = 0.0, rootOuter, rootZero, result;
@@ -398,8 +479,17 @@ GLC_DEVICE_INLINE void unit_cool_begin(SlotState &S) {
     R.w = w;
     R.logSlopeT = logSlopeT;
     if (need) {
-        brent_begin(S.B, true, MS::cooling_root_options(), 0.0, w.hhRouter, true, rootZero, rootOuter);
-        m_root_start(S, U_ROOT_COOL);
+        S.p[0] = w.coolXH;
+        S.p[1] = w.coolFHn;
+        S.p[2] = w.coolEfrac;
+        S.p[3] = w.coolLambda;
+        S.p[4] = w.tvir;
+        S.p[5] = w.coolTavail;
+        S.p[6] = w.hhRho0;
+        S.p[7] = w.hhRcore;
+        S.p[8] = w.hhRouter;
+        S.p[9] = w.hhValid ? 1.0 : 0.0;
+        m_root_start<U_ROOT_COOL>(S, 0.0, w.hhRouter, true, rootZero, rootOuter);
     } else {
         R.rinfall = result;
         S.unit = U_RK;
@@ -407,19 +497,20 @@ GLC_DEVICE_INLINE void unit_cool_begin(SlotState &S) {
 }
 
 // One unit of one slot.  Returns false when the slot is idle.
-GLC_DEVICE_INLINE bool machine_step(SlotState &S, const LaneMem &M) {
-    const int unit = S.unit;
-    switch (unit) {
+GLC_DEVICE_INLINE bool machine_step(const SlotRef &S, const LaneMem &M) {
+    switch (S.unit) {
         case U_RK: unit_rk(S, M); break;
         case U_RHS_BEGIN: unit_rhs_begin(S); break;
         case U_STRUCT: unit_struct(S); break;
         case U_STRUCT_FIN: unit_struct_fin(S); break;
-        case U_ROOT_AC:
-        case U_ROOT_J:
-        case U_ROOT_TRUNC:
-        case U_ROOT_CRIT:
-        case U_ROOT_COOL: unit_root(S, unit); break;
+        case U_ROOT_AC: unit_root<U_ROOT_AC>(S); break;
+        case U_ROOT_J: unit_root<U_ROOT_J>(S); break;
+        case U_ROOT_TRUNC: unit_root<U_ROOT_TRUNC>(S); break;
+        case U_ROOT_CRIT: unit_root<U_ROOT_CRIT>(S); break;
+        case U_ROOT_COOL: unit_root<U_ROOT_COOL>(S); break;
         case U_SFR_BEGIN: unit_sfr_begin(S); break;
+        case U_SFR_MID: unit_sfr_mid(S); break;
+        case U_SFR_MID2: unit_sfr_mid2(S); break;
         case U_QAG: unit_qag(S); break;
         case U_COOL_BEGIN: unit_cool_begin(S); break;
         default: return false;
@@ -428,80 +519,171 @@ GLC_DEVICE_INLINE bool machine_step(SlotState &S, const LaneMem &M) {
 }
 
 #if defined(__CUDACC__)
-// Persistent time-sliced kernel.  One block per SM owns SLOTS slots (SLOTS a multiple of THREADS).  Every
-// iteration it (1) counting-sorts its slots by pending unit in shared memory, (2) sweeps the sorted list: warp w
-// executes chunks w, w+W, w+2W, ... of 32 consecutive sorted slots, one unit per slot.  Because the warps of the
-// SM walk through the sorted list side by side, they execute the same one or two units at any instant: the
-// instruction working set of the SM is one unit's code, not the whole machine's, and a warp is pure except at the
-// few unit boundaries of the list.  All per-slot state lives in HBM/L2 (SlotState + the RK stage vectors), so
-// parking at the end of a time slice costs nothing.
+// Persistent time-sliced kernel.  One block per SM owns SLOTS slots.  Scheduling is barrier-free: the block keeps
+// one ring-buffer queue per unit type in shared memory; a warp pops up to 32 slots that all wait for the SAME unit
+// (preferring the unit it executed last, whose code is hot in its instruction cache, else the fullest queue),
+// executes that unit once per lane, and pushes every slot onto the queue of its next unit.  Lanes are bound to
+// slots only for the duration of one unit, warps are pure by construction, and a slow unit (the RK bookkeeping,
+// a cold-started structure solve) delays only its own slots.  All per-slot state lives in HBM/L2 (SlotArrays +
+// the RK stage vectors); the queues are rebuilt from the slots' pending-unit words at the start of every time
+// slice, so parking costs nothing.
 template <int THREADS, int SLOTS>
-__global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotState *slots) {
+__global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotArrays slots) {
+    static_assert((SLOTS & (SLOTS - 1)) == 0 && SLOTS <= 2048, "SLOTS must be a power of two <= 2048 (11-bit ids)");
     constexpr int PER = SLOTS / THREADS;
-    constexpr int WARPS = THREADS / 32;
-    __shared__ int s_hist[U_COUNT];
-    __shared__ int s_off[U_COUNT];
-    __shared__ unsigned short s_perm[SLOTS];
-    __shared__ unsigned char s_unit[SLOTS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr unsigned short EMPTY = 0xf800u;  // lap tag 31: never the tag of lap 0
+    extern __shared__ unsigned short s_qdyn[];  // [U_IDLE][SLOTS] ring buffers (dynamic: > 48 KB)
+    unsigned short(*s_q)[SLOTS] = reinterpret_cast<unsigned short(*)[SLOTS]>(s_qdyn);
+    __shared__ unsigned int s_head[U_IDLE], s_tail[U_IDLE];
+    __shared__ int s_idle, s_cur;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int64_t base = (int64_t)blockIdx.x * SLOTS;
+    for (int i = tid; i < U_IDLE * SLOTS; i += THREADS) s_qdyn[i] = EMPTY;
+    if (tid < U_IDLE) s_head[tid] = s_tail[tid] = 0u;
+    if (tid == 0) {
+        s_idle = 0;
+        s_cur = U_RK;
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int k = 0; k < PER; k++) {
         const int s = tid + k * THREADS;
-        SlotState &own = slots[base + s];
+        const SlotRef own = slot_ref(slots, base + s);
         if (!A.resume) slot_reset(own);
         if (own.unit == U_IDLE) {  // the queue may have grown since the last slice
             own.L.phase = PH_FETCH;
             own.unit = U_RK;
         }
-        s_unit[s] = (unsigned char)own.unit;
+        const int u = own.unit;
+        s_q[u][atomicAdd(&s_tail[u], 1u) & (SLOTS - 1)] = (unsigned short)s;  // lap 0: tag 0
     }
     __syncthreads();
-    for (int it = 0; it < A.budget; ++it) {
-        // ---- regroup the block's slots by pending unit
-        if (tid < U_COUNT) s_hist[tid] = 0;
-        __syncthreads();
-        int myUnit[PER], myRank[PER];
-#pragma unroll
-        for (int k = 0; k < PER; k++) {
-            myUnit[k] = s_unit[tid + k * THREADS];
-            myRank[k] = atomicAdd(&s_hist[myUnit[k]], 1);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int u = 0; u < U_COUNT; u++) {
-                s_off[u] = acc;
-                acc += s_hist[u];
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < PER; k++) s_perm[s_off[myUnit[k]] + myRank[k]] = (unsigned short)(tid + k * THREADS);
-        const int nActive = SLOTS - s_hist[U_IDLE];
-        __syncthreads();
-        if (nActive == 0) break;
-        // ---- sweep: one unit per active slot
+
+    volatile unsigned int *vhead = s_head, *vtail = s_tail;
+    volatile int *vidle = &s_idle, *vcur = &s_cur;
+#ifdef GLC_DEBUG_HANG
+    volatile int *dbg = A.debug ? A.debug + ((int64_t)blockIdx.x * (THREADS / 32) + (tid >> 5)) * 8 : nullptr;
+#define GLC_DBG(k, v) do { if (dbg && lane == 0) dbg[k] = (v); } while (0)
+#define GLC_DBG_LANE(k, v) do { if (dbg) dbg[k] = (v); } while (0)
+#else
+#define GLC_DBG(k, v) ((void)0)
+#define GLC_DBG_LANE(k, v) ((void)0)
+#endif
+    int warpLast = -1;
+    (void)warpLast;
 #pragma unroll 1
-        for (int c = warp; c * 32 < nActive; c += WARPS) {
-            const int p = c * 32 + lane;
-            if (p < nActive) {
-                const int s = s_perm[p];
-                const int64_t slot = base + s;
-                LaneMem M{&A, A.ws + slot * (WS_NVEC * NY), 1};
-                machine_step(slots[slot], M);
-                s_unit[s] = (unsigned char)slots[slot].unit;
+    for (int it = 0; it < A.budget; ++it) {
+        // ---- lane 0 reserves up to 32 entries of the block's CURRENT unit.  The whole block works on one unit
+        // at a time (its code, 10-30 KB, then lives in the SM's instruction cache) and moves on to the fullest
+        // queue when the current one cannot fill a warp any more.  No barrier: a warp that still holds a stale
+        // choice just pops from that queue once more.
+        int u = -1, take = 0;
+        unsigned int start = 0;
+        GLC_DBG(0, 1);
+        GLC_DBG(1, it);
+        if (lane == 0) {
+#pragma unroll 1
+            for (int attempt = 0; attempt < 4 && u < 0; attempt++) {
+                int cur = *vcur;
+                unsigned int n = vtail[cur] - vhead[cur];
+#ifdef GLC_POLICY_WARP
+                if (warpLast >= 0 && vtail[warpLast] - vhead[warpLast] >= 32u && vtail[warpLast] - vhead[warpLast] <= (unsigned int)SLOTS) {
+                    cur = warpLast;
+                    n = 32u;
+                }
+#endif
+                if (n < 32u) {
+                    int best = cur;
+                    unsigned int bestN = n;
+                    for (int q = 0; q < U_IDLE; q++) {
+                        const unsigned int m = vtail[q] - vhead[q];
+                        if (m > bestN && m <= (unsigned int)SLOTS) {
+                            bestN = m;
+                            best = q;
+                        }
+                    }
+                    if (best != cur) {
+                        *vcur = best;
+                        cur = best;
+                    }
+                }
+                const unsigned int old = vhead[cur];
+                n = vtail[cur] - old;
+                if (n == 0u || n > (unsigned int)SLOTS) continue;
+                const unsigned int t = n < 32u ? n : 32u;
+                if (atomicCAS(&s_head[cur], old, old + t) == old) {
+                    u = cur;
+                    start = old;
+                    take = (int)t;
+                }
             }
-            __syncwarp();
         }
-        __syncthreads();
+        // NB: every decision that steers the warp's control flow is taken by lane 0 and broadcast.  Letting each
+        // lane read the volatile idle counter itself dead-locked the block: the lanes of a warp are not guaranteed
+        // to execute that load at the same instant, so when the counter reached SLOTS between two of them part of
+        // the warp left the loop while the rest waited for it in the next __shfl_sync.
+        int allIdle = 0;
+        if (lane == 0 && u < 0) allIdle = (*vidle >= SLOTS) ? 1 : 0;
+        u = __shfl_sync(0xffffffffu, u, 0);
+        start = __shfl_sync(0xffffffffu, start, 0);
+        take = __shfl_sync(0xffffffffu, take, 0);
+        allIdle = __shfl_sync(0xffffffffu, allIdle, 0);
+        GLC_DBG(2, u);
+        GLC_DBG(3, (int)start);
+        GLC_DBG(4, take);
+        if (u < 0) {
+            GLC_DBG(0, 6);
+            GLC_DBG(5, allIdle);
+#ifdef GLC_WATCHDOG
+            if (lane == 0 && (it % 4000) == 3999)
+                printf("[watchdog] block %d warp %d it %d: nothing to pop, idle=%d cur=%d\n", blockIdx.x, tid >> 5, it, *vidle, *vcur);
+#endif
+            if (allIdle) break;  // every slot of the block is out of work
+            __nanosleep(256);
+            continue;
+        }
+        // ---- one unit per lane
+        if (lane < take) {
+            // Ring entries carry a 5-bit lap tag above the 11-bit slot id, so a consumer can tell "written for my
+            // lap" from "left over from the previous lap" without anybody ever resetting an entry.
+            const unsigned int pos = start + (unsigned int)lane;
+            const unsigned short tag = (unsigned short)(((pos / SLOTS) & 31u) << 11);
+            volatile unsigned short *entry = &s_q[u][pos & (SLOTS - 1)];
+            unsigned short e;
+            GLC_DBG_LANE(0, 2);
+            GLC_DBG_LANE(6, lane);
+            while (((e = *entry) & 0xf800u) != tag) __nanosleep(32);
+            GLC_DBG_LANE(0, 3);
+            GLC_DBG_LANE(6, lane);
+            GLC_DBG_LANE(7, (int)(e & 0x07ffu));  // the producer reserved it and is about to write it
+            const int s = (int)(e & 0x07ffu);
+            __threadfence_block();  // acquire: the producer's stores to the slot's continuation are visible
+            const int64_t slot = base + s;
+            const SlotRef S = slot_ref(slots, slot);
+            LaneMem M{&A, A.ws + slot * (WS_NVEC * NY), 1};
+            S.unit = u;  // the queue a slot sits in IS its pending unit
+            machine_step(S, M);
+            const int nu = S.unit;
+            __threadfence_block();  // release: continuation stores before the queue entry
+            if (nu == U_IDLE)
+                atomicAdd(&s_idle, 1);
+            else {
+                const unsigned int np = atomicAdd(&s_tail[nu], 1u);
+                s_q[nu][np & (SLOTS - 1)] = (unsigned short)((((np / SLOTS) & 31u) << 11) | (unsigned int)s);
+            }
+        }
+        GLC_DBG_LANE(0, 4);
+        __syncwarp();
+        GLC_DBG(0, 5);
+        warpLast = u;
     }
+    GLC_DBG(0, 9);
     __syncthreads();
     // ---- counters of this block's slots: warp-reduce then one atomic per warp per counter
     unsigned int vals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
     for (int k = 0; k < PER; k++) {
-        SlotState &own = slots[base + tid + k * THREADS];
+        const SlotRef own = slot_ref(slots, base + tid + k * THREADS);
         LaneState &L = own.L;
         vals[0] += L.nAcc;
         vals[1] += L.nRej;

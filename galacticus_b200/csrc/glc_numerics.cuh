@@ -28,13 +28,12 @@ struct RootOptions {
 GLC_DEVICE_INLINE double fsign1(double x) { return signbit(x) ? -1.0 : 1.0; }
 
 // Re-entrant form of rootFinder%find (Brent branch): the caller owns the loop.
-//   brent_begin(...)            initialise;
+//   brent_begin(...)            initialise;   (the RootOptions are passed to every call: compile-time constants)
 //   brent_advance(B) -> bool    run the state machine to the next abscissa B.x at which the function is needed
 //                               (false: nothing to evaluate -- finished, B.busy == 0, B.result/B.status are set);
 //   brent_feed(B, f(B.x))       digest the value.
 // status 0 = ok, 2 = could not bracket, 3 = bad bracket
 struct BrentState {
-    RootOptions o;
     double xLow, xHigh, fLow, fHigh;
     double a, b, c, d, e, fa, fb, fc, xl, xh, root, x, result;
     int state, iteration, status;
@@ -42,9 +41,8 @@ struct BrentState {
 };
 enum : int { ST_FLO, ST_FHI, ST_BRACKET, ST_EXP_UP, ST_EXP_DOWN, ST_BRENT };
 
-GLC_DEVICE_INLINE void brent_begin(BrentState &B, bool on, const RootOptions &o, double xLow, double xHigh, bool haveValues,
-                                   double fLow, double fHigh) {
-    B.o = o;
+GLC_DEVICE_INLINE void brent_begin(BrentState &B, bool on, double xLow, double xHigh, bool haveValues, double fLow,
+                                   double fHigh) {
     B.xLow = xLow;
     B.xHigh = xHigh;
     B.fLow = fLow;
@@ -58,7 +56,7 @@ GLC_DEVICE_INLINE void brent_begin(BrentState &B, bool on, const RootOptions &o,
     B.busy = on ? 1 : 0;
 }
 
-GLC_DEVICE_INLINE bool brent_advance(BrentState &B) {
+GLC_DEVICE_INLINE bool brent_advance(BrentState &B, const RootOptions &o) {
     double x = 0.0;
     bool evaluate = false;
     while (B.busy && !evaluate) {
@@ -74,11 +72,11 @@ GLC_DEVICE_INLINE bool brent_advance(BrentState &B) {
                     B.first = false;
                 }
                 if (fsign1(B.fLow) * fsign1(B.fHigh) > 0.0 && B.fLow != 0.0 && B.fHigh != 0.0) {
-                    B.lowerOk = B.o.signExpectDownward == SIGN_NEGATIVE   ? (B.fLow < 0.0)
-                              : B.o.signExpectDownward == SIGN_POSITIVE ? (B.fLow > 0.0)
+                    B.lowerOk = o.signExpectDownward == SIGN_NEGATIVE   ? (B.fLow < 0.0)
+                              : o.signExpectDownward == SIGN_POSITIVE ? (B.fLow > 0.0)
                                                                       : false;
-                    B.upperOk = B.o.signExpectUpward == SIGN_NEGATIVE   ? (B.fHigh < 0.0)
-                              : B.o.signExpectUpward == SIGN_POSITIVE ? (B.fHigh > 0.0)
+                    B.upperOk = o.signExpectUpward == SIGN_NEGATIVE   ? (B.fHigh < 0.0)
+                              : o.signExpectUpward == SIGN_POSITIVE ? (B.fHigh > 0.0)
                                                                     : false;
                     B.rangeChanged = false;
                     B.state = ST_EXP_UP;
@@ -101,10 +99,10 @@ GLC_DEVICE_INLINE bool brent_advance(BrentState &B) {
                 }
             } else if (B.state == ST_EXP_UP) {
                 bool move;
-                if (B.o.expandType == EXPAND_ADDITIVE)
-                    move = B.o.expandUpward > 0.0 && !B.upperOk;
-                else if (B.o.expandType == EXPAND_MULTIPLICATIVE)
-                    move = ((B.o.expandUpward > 1.0 && B.xHigh > 0.0) || (B.o.expandUpward < 1.0 && B.xHigh < 0.0)) && !B.upperOk;
+                if (o.expandType == EXPAND_ADDITIVE)
+                    move = o.expandUpward > 0.0 && !B.upperOk;
+                else if (o.expandType == EXPAND_MULTIPLICATIVE)
+                    move = ((o.expandUpward > 1.0 && B.xHigh > 0.0) || (o.expandUpward < 1.0 && B.xHigh < 0.0)) && !B.upperOk;
                 else
                     move = false;
                 if (move) {
@@ -112,7 +110,7 @@ GLC_DEVICE_INLINE bool brent_advance(BrentState &B) {
                         B.xLow = B.xHigh;
                         B.fLow = B.fHigh;
                     }
-                    B.xHigh = (B.o.expandType == EXPAND_ADDITIVE) ? B.xHigh + B.o.expandUpward : B.xHigh * B.o.expandUpward;
+                    B.xHigh = (o.expandType == EXPAND_ADDITIVE) ? B.xHigh + o.expandUpward : B.xHigh * o.expandUpward;
                     x = B.xHigh;
                     B.rangeChanged = true;
                 } else {
@@ -121,10 +119,10 @@ GLC_DEVICE_INLINE bool brent_advance(BrentState &B) {
                 }
             } else if (B.state == ST_EXP_DOWN) {
                 bool move;
-                if (B.o.expandType == EXPAND_ADDITIVE)
-                    move = B.o.expandDownward < 0.0 && !B.lowerOk;
-                else if (B.o.expandType == EXPAND_MULTIPLICATIVE)
-                    move = ((B.o.expandDownward < 1.0 && B.xLow > 0.0) || (B.o.expandDownward > 1.0 && B.xLow < 0.0)) && !B.lowerOk;
+                if (o.expandType == EXPAND_ADDITIVE)
+                    move = o.expandDownward < 0.0 && !B.lowerOk;
+                else if (o.expandType == EXPAND_MULTIPLICATIVE)
+                    move = ((o.expandDownward < 1.0 && B.xLow > 0.0) || (o.expandDownward > 1.0 && B.xLow < 0.0)) && !B.lowerOk;
                 else
                     move = false;
                 if (move) {
@@ -132,7 +130,7 @@ GLC_DEVICE_INLINE bool brent_advance(BrentState &B) {
                         B.xHigh = B.xLow;
                         B.fHigh = B.fLow;
                     }
-                    B.xLow = (B.o.expandType == EXPAND_ADDITIVE) ? B.xLow + B.o.expandDownward : B.xLow * B.o.expandDownward;
+                    B.xLow = (o.expandType == EXPAND_ADDITIVE) ? B.xLow + o.expandDownward : B.xLow * o.expandDownward;
                     x = B.xLow;
                     B.rangeChanged = true;
                 } else {
@@ -189,7 +187,7 @@ GLC_DEVICE_INLINE bool brent_advance(BrentState &B) {
                     if (B.iteration > 1) {
                         const double al = fabs(B.xl), au = fabs(B.xh);
                         const double minAbs = ((B.xl > 0.0 && B.xh > 0.0) || (B.xl < 0.0 && B.xh < 0.0)) ? fmin(al, au) : 0.0;
-                        if (fabs(B.xh - B.xl) < B.o.tolAbs + B.o.tolRel * minAbs) {
+                        if (fabs(B.xh - B.xl) < o.tolAbs + o.tolRel * minAbs) {
                             B.result = B.root;
                             B.busy = false;
                         }
@@ -240,7 +238,7 @@ GLC_DEVICE_INLINE bool brent_advance(BrentState &B) {
     return B.busy && evaluate;
 }
 
-GLC_DEVICE_INLINE void brent_feed(BrentState &B, double fx) {
+GLC_DEVICE_INLINE void brent_feed(BrentState &B, const RootOptions &o, double fx) {
             if (B.state == ST_FLO) {
                 B.fLow = fx;
                 B.state = ST_FHI;
@@ -268,7 +266,7 @@ GLC_DEVICE_INLINE void brent_feed(BrentState &B, double fx) {
                 if (B.iteration > 1) {
                     const double al = fabs(B.xl), au = fabs(B.xh);
                     const double minAbs = ((B.xl > 0.0 && B.xh > 0.0) || (B.xl < 0.0 && B.xh < 0.0)) ? fmin(al, au) : 0.0;
-                    if (fabs(B.xh - B.xl) < B.o.tolAbs + B.o.tolRel * minAbs) {
+                    if (fabs(B.xh - B.xl) < o.tolAbs + o.tolRel * minAbs) {
                         B.result = B.root;
                         B.busy = false;
                     }
@@ -288,9 +286,9 @@ template <class F>
 GLC_DEVICE_INLINE double root_find(F &&f, bool on, const RootOptions &o, double xLow, double xHigh,
                                             bool haveValues, double fLow, double fHigh, int &status) {
     BrentState B;
-    brent_begin(B, on, o, xLow, xHigh, haveValues, fLow, fHigh);
+    brent_begin(B, on, xLow, xHigh, haveValues, fLow, fHigh);
     while (GLC_ANY(B.busy != 0)) {
-        if (brent_advance(B)) brent_feed(B, f(B.x));  // ---- the single call site (straight-line integrands only)
+        if (brent_advance(B, o)) brent_feed(B, o, f(B.x));  // ---- the single call site (straight-line integrands only)
     }
     status = B.status;
     return B.result;

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import abi
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libglcb200.so")
+LIB_PATH = os.environ.get("GLC_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libglcb200.so")
 _LIB = None
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")

@@ -121,7 +121,29 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
     for (int64_t i = 0; i < n; i++)
         for (int p = 0; p < NPROP; p++) soa[(size_t)p * cap + i] = props[i * NPROP + p];
     std::vector<double> ws((size_t)WS_NVEC * NY * nslots);
-    std::vector<SlotState> slots(nslots);
+    std::vector<LaneState> sL(nslots);
+    std::vector<RhsState> sR(nslots);
+    std::vector<RootState> sRoot(nslots);
+    std::vector<double> sYt((size_t)nslots * NY);
+    std::vector<QagState> sQ(nslots);
+    std::vector<int> sUnit(nslots);
+    // device memory comes from cudaMalloc uninitialised: poison the continuations and the workspace with
+    // pseudo-random bytes so that any read-before-write in the machine shows up here as a mismatch or a hang
+    {
+        std::mt19937 g(987654321u);
+        auto poison = [&](void *ptr, size_t bytes) {
+            unsigned char *b = (unsigned char *)ptr;
+            for (size_t i = 0; i < bytes; i++) b[i] = (unsigned char)(g() & 0xff);
+        };
+        poison(sL.data(), sL.size() * sizeof(LaneState));
+        poison(sR.data(), sR.size() * sizeof(RhsState));
+        poison(sRoot.data(), sRoot.size() * sizeof(RootState));
+        poison(sYt.data(), sYt.size() * sizeof(double));
+        poison(sQ.data(), sQ.size() * sizeof(QagState));
+        poison(sUnit.data(), sUnit.size() * sizeof(int));
+        poison(ws.data(), ws.size() * sizeof(double));
+    }
+    SlotArrays slots{sL.data(), sR.data(), sRoot.data(), sYt.data(), sQ.data(), sUnit.data()};
     std::vector<int32_t> order;
     if (sort) {
         order.resize(n);
@@ -153,10 +175,11 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
     for (int s = 0; s < nslots; s++) perm[s] = s;
     for (;;) {
         for (int s = 0; s < nslots; s++) {
-            if (!A.resume) slot_reset(slots[s]);
-            if (slots[s].unit == U_IDLE) {
-                slots[s].L.phase = PH_FETCH;
-                slots[s].unit = U_RK;
+            const SlotRef S = slot_ref(slots, s);
+            if (!A.resume) slot_reset(S);
+            if (S.unit == U_IDLE) {
+                S.L.phase = PH_FETCH;
+                S.unit = U_RK;
             }
         }
         for (int it = 0; it < A.budget; ++it) {
@@ -165,12 +188,12 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
             for (int p = 0; p < nslots; p++) {
                 const int s = perm[p];
                 LaneMem M{&A, A.ws + (int64_t)s * (WS_NVEC * NY), 1};
-                any |= machine_step(slots[s], M);
+                any |= machine_step(slot_ref(slots, s), M);
             }
             if (!any) break;
         }
         for (int s = 0; s < nslots; s++) {
-            LaneState &L = slots[s].L;
+            LaneState &L = sL[s];
             hc[0] += L.nAcc;
             hc[1] += L.nRej;
             hc[2] += L.nRhs;
