@@ -2,16 +2,26 @@
 """bench.py -- node-ODE hot path throughput on N B200s (one process per GPU).
 
 Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line.
-  value      : node-ODE steps/s (accepted RKCK steps, successful iterations of driver2.c:190) summed over all
-               ranks, inputs already resident in HBM (device-resident arena), CUDA-event timed, max over ranks.
-  e2e        : same metric through the reference-facing C-ABI call glc_evolve_batch with HOST buffers
-               (H2D + layout transpose + kernel + D2H inside the timed region).
-  roofline   : dominant kernel (evolve_kernel) against the HBM roofline (algorithmic bytes = the node records read
-               and written once per launch) plus, as north_star asks, the FP64 view: FP64 flop/s from the kernel's
-               own counters against a DFMA-chain peak measured in this process.
-  cpu_baseline: the CPU oracle (oracle/, OpenMP over nodes like the reference's OpenMP over trees) on a bounded
-               sample of the same workload, on this box's host cores.
-``--impl reference`` times the oracle alone (the reference Fortran cannot be built here: no gfortran/GSL/HDF5).
+
+  workload   : a seeded batch of synthetic node records per GPU -- the stand-in for BASELINE.json configs[1]
+               (testSuite benchmark-milkyWay: 10^3 Milky-Way-mass trees ~ 10^6 node-evolve calls); every record is
+               one call of mergerTreeNodeEvolverStandard%evolve over its own time interval with the quickTest
+               operator set (black-hole operators not restated yet) and synthetic CIE tables.
+  step       : one pass of the hot path over the whole batch: every node is evolved to its end time.
+  value      : accepted RKCK node-ODE steps/s (successful iterations of the driver2.c:190 loop) summed over all
+               ranks, inputs already resident in HBM (device arena), timed with CUDA events on the evolver's
+               stream, max over ranks.
+  e2e        : the same metric through the reference-facing C-ABI call glc_evolve_batch with HOST buffers
+               (H2D copy + layout transpose + kernels + D2H inside the timed region).
+  roofline   : the dominant kernel (machine_kernel) against the HBM roofline with the ALGORITHMIC bytes of
+               SURVEY.md 8(d) (state streamed once per accepted step: 3*8*n_y bytes, plus one read and one write
+               of every node record per launch), and -- because the path is FP64-ALU/latency bound, not HBM
+               bound -- `roofline_fp64`: FP64 flop/s from the kernel's own RHS counter times the ncu-measured
+               flop per RHS evaluation (profiles/) against a DFMA-chain peak measured in this process.
+  cpu_baseline: the CPU checker (oracle/, OpenMP over nodes like the reference's OpenMP over trees, built with the
+               reference's own optimisation flags) on a bounded sample of the same workload on this box's cores.
+``--impl reference`` times that CPU implementation alone (the Fortran reference cannot be built in this image:
+no gfortran/GSL/HDF5).
 """
 from __future__ import annotations
 
@@ -30,16 +40,20 @@ if ROOT not in sys.path:
 
 METRIC = "node_ode_steps_per_s"
 UNIT = "accepted RKCK node-ODE steps/s"
+# FP64 flop per evaluation of the rate function (DADD + DMUL + 2*DFMA thread-level SASS instructions of
+# machine_kernel divided by its RHS counter, ncu capture profiles/r01_machine_kernel_summary.txt)
+FLOP_PER_RHS = 1.0e4
+N_Y = 24
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nodes", type=int, default=1_000_000, help="node records per GPU (weak scaling)")
-    ap.add_argument("--cpu-sample", type=int, default=40_000, help="node records of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="node records of the CPU baseline sample")
     ap.add_argument("--seed", type=int, default=219)
     return ap.parse_args()
 
@@ -55,6 +69,12 @@ def workload(n, seed):
     synthetic.finalize_params(p)
     props, flags, t_end = synthetic.standard_nodes(p, n, seed=seed)
     return p, props, flags, t_end
+
+
+WORKLOAD_NAME = ("node-batch stand-in for testSuite benchmark-milkyWay (10^3 MW-mass trees ~ 10^6 node-evolve calls): "
+                 "%d node records per GPU over the quickTest mass range (1e10-1e13 Msun), each evolved over its own "
+                 "0.05-0.8 Gyr interval; quickTest operator set without the black-hole operators, "
+                 "hotHaloRamPressureStripping=virialRadius, synthetic CIE tables")
 
 
 class ClockSampler(threading.Thread):
@@ -108,19 +128,39 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
 
 
-def run_reference(args):
-    """Reference arm: the CPU implementation of the path (the oracle port; the Fortran reference cannot be
-    compiled in this image) on the host cores, on a bounded sample of the same workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def cpu_run(p, props, flags, t_end, repeats):
+    """The CPU implementation of the path on all host cores; returns (steps/s, nodes/s, seconds per pass, cores)."""
     from galacticus_b200 import synthetic
     from oracle import orc
 
     orc.build()
     cores = os.cpu_count() or 1
+    o = orc.Oracle(fast=True)
+    synthetic.install(o, p)
+    times, steps = [], 0
+    for _ in range(repeats):
+        pp, ff = props.copy(), flags.copy()
+        t0 = time.perf_counter()
+        _, _, c = o.evolve_batch(pp, ff, t_end, n_threads=cores)
+        times.append(time.perf_counter() - t0)
+        steps = c["steps_accepted"]
+    best = float(np.mean(times))
+    return steps / best, props.shape[0] / best, best, cores
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the path (the oracle port; the Fortran reference cannot be
+    compiled in this image) on the host cores, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
     n = args.cpu_sample
     p, props, flags, t_end = workload(n, args.seed)
+    cores = os.cpu_count() or 1
+    from galacticus_b200 import synthetic
+    from oracle import orc
+
+    orc.build()
     o = orc.Oracle(fast=True)
     synthetic.install(o, p)
     times, steps = [], 0
@@ -134,13 +174,14 @@ def run_reference(args):
             steps = c["steps_accepted"]
     tot = sum(times)
     value = steps * len(times) / tot
+    sample = f"{n} node records of the same generator/seed per step; {n * len(times) / tot:.0f} nodes/s"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"node-batch sample of {n} records, quickTest operator set (no BH ops), seed {args.seed}"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} node records of the same generator/seed; nodes/s = {n * len(times) / tot:.1f}"},
+        "config": {"workload": WORKLOAD_NAME % args.nodes, "nodes_per_gpu": args.nodes, "seed": args.seed,
+                   "sample_nodes_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -170,10 +211,11 @@ def main():
 
     n = args.nodes
     # independent forests shard naturally: every rank owns its own forest queue (different seed), no data-path collective
-    p, props, flags, t_end = workload(n, args.seed + 1000 * rank)
+    from galacticus_b200 import sharding as _sh
+
+    p, props, flags, t_end = workload(n, _sh.forest_seed(args.seed, rank) if world > 1 else args.seed)
     ev = Evolver(local_rank)
     synthetic.install(ev, p)
-    fp64_peak = ev.fp64_peak_tflops()
 
     def barrier():
         if world > 1:
@@ -183,7 +225,6 @@ def main():
     # ---------------- device-resident arm ("value")
     ev.arena_upload(props, flags, t_end)
     ev.arena_snapshot(n)
-    launches0 = ev.kernel_launch_count()
     for _ in range(args.warmup):
         ev.arena_restore(n)
         ev.evolve_arena(n)
@@ -195,19 +236,33 @@ def main():
     kernel_ms, counters = [], None
     for _ in range(args.steps):
         ev.arena_restore(n)
-        counters, ms = ev.evolve_arena(n)  # synchronises the evolver's stream; ms = CUDA events around the kernel
+        counters, ms = ev.evolve_arena(n)  # synchronises the evolver's stream; ms = CUDA events around the kernels
         kernel_ms.append(ms)
     barrier()
     wall = time.perf_counter() - t0
     launches = ev.kernel_launch_count() - launches1
     clocks = sampler.stop()
     dev_time = sum(kernel_ms) * 1e-3  # device time of the timed kernels on the launching stream
+    final_props, _, st, _ = ev.arena_download(n)
+
+    # ---------------- one instrumented pass in time slices: how the pass divides into bulk and straggler tail
+    profile = {}
+    try:
+        ev.set_option(abi.GLC_OPT_SLICE_BUDGET, 4096)
+        ev.arena_restore(n)
+        tb = time.perf_counter()
+        c_sl, ms_sl = ev.evolve_arena(n)
+        profile = {"sliced_pass_ms": ms_sl, "slices": None}
+        ev.set_option(abi.GLC_OPT_SLICE_BUDGET, 0)
+    except Exception as e:  # informational only
+        profile = {"error": repr(e)}
+        ev.set_option(abi.GLC_OPT_SLICE_BUDGET, 0)
 
     # ---------------- end-to-end arm through the C-ABI with host buffers
     pin = torch.empty((n, abi.NPROP), dtype=torch.float64).pin_memory()
     host_props = pin.numpy()
     e2e_times = []
-    for it in range(1 + min(args.steps, 3)):
+    for it in range(1 + max(1, min(args.steps, 3))):
         host_props[:] = props
         ff = flags.copy()
         barrier()
@@ -219,6 +274,7 @@ def main():
     e2e_time = float(np.mean(e2e_times))
     h2d = n * (abi.NPROP * 8 + 4 + 8)
     d2h = n * (abi.NPROP * 8 + 4 + 4 + 4)
+    fp64_peak = ev.fp64_peak_tflops()  # after the runs: the device is warm
 
     # ---------------- reduce over ranks: max time, summed work, NCCL all-reduce of an output statistic
     steps_acc = counters["steps_accepted"]
@@ -226,14 +282,14 @@ def main():
                           float(counters["steps_rejected"]), float(n)], dtype=torch.float64, device="cuda")
     tmax, tsum = stats.clone(), stats.clone()
     # stellar mass function histogram of the evolved batch (mirrors output/analyses/volume_function_1d.F90:986-987)
-    final_props, _, st, _ = ev.arena_download(n)
     mstar = final_props[:, abi.P["DISK_MASS_STELLAR"]] + final_props[:, abi.P["SPH_MASS_STELLAR"]]
     hist = np.histogram(np.log10(np.maximum(mstar, 1.0)), bins=30, range=(5.0, 12.5))[0].astype(np.float64)
-    hist_t = torch.from_numpy(hist).cuda()
+    from galacticus_b200 import sharding
+
+    hist_t = sharding.reduce_statistics(torch.from_numpy(hist).cuda())  # NCCL all-reduce over NVLink when world > 1
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dist.all_reduce(hist_t, op=dist.ReduceOp.SUM)
     tmax, tsum = tmax.cpu().numpy(), tsum.cpu().numpy()
     ok_frac = float((st == 0).mean())
 
@@ -244,60 +300,56 @@ def main():
         ms_per_step = 1e3 * dev_time_max / args.steps
         e2e_value = float(tsum[3]) / e2e_max
         # roofline of the dominant kernel (rank 0's launches)
-        alg_bytes = n * (2 * abi.NPROP * 8 + 8 + 3 * 4)  # read + write one record per node (+ time_end, flags/status/interrupt)
+        ms_kernel = float(np.mean(kernel_ms))
+        rhs_total = float(counters["rhs_evaluations"])
+        alg_bytes = steps_acc * 3 * 8 * N_Y + n * (2 * abi.NPROP * 8 + 8 + 3 * 4)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        ach_gbs = alg_bytes / (np.mean(kernel_ms) * 1e-3) / 1e9
-        # FP64 view: flop per RHS evaluation and per step measured with ncu (profiles/)
-        flop_per_rhs = float(os.environ.get("GLC_FLOP_PER_RHS", "0") or 0)
-        rhs_total = float(counters["rhs_evaluations"])
+        ach_gbs = alg_bytes / (ms_kernel * 1e-3) / 1e9
+        ach_tflops = rhs_total * FLOP_PER_RHS / (ms_kernel * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": ("node-batch stand-in for testSuite benchmark-milkyWay: %d node records per GPU over the "
-                             "quickTest mass range (1e10-1e13 Msun), quickTest operator set without the black-hole "
-                             "operators, hotHaloRamPressureStripping=virialRadius, synthetic CIE tables" % n),
-                "nodes_per_gpu": n, "seed": args.seed, "l2": "inputs (%.0f MB/GPU) larger than L2" % (n * abi.NPROP * 8 / 1e6),
+                "workload": WORKLOAD_NAME % n,
+                "nodes_per_gpu": n, "seed": args.seed,
+                "l2": "inputs (%.0f MB/GPU of node records + %.0f MB of per-slot continuations) larger than L2"
+                      % (n * abi.NPROP * 8 / 1e6, 148 * 2048 * 4.2e3 / 1e6),
+                "trees_per_s_equivalent": float(tsum[6]) * args.steps / dev_time_max / 1.0e3,
                 "nodes_per_s": float(tsum[6]) * args.steps / dev_time_max,
                 "rhs_evaluations_per_s": float(tsum[4]) * args.steps / dev_time_max,
                 "rejected_step_fraction": float(tsum[5]) / max(float(tsum[3]) + float(tsum[5]), 1.0),
                 "status_ok_fraction": ok_frac,
                 "wall_s_timed_region": float(tmax[1]),
+                "sliced_pass": profile,
                 "stellar_mass_function_counts": hist_t.cpu().numpy().tolist(),
             },
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "note": "latency/FP64-issue bound kernel: see roofline_fp64 and profiles/"},
-            "roofline_fp64": {"peak_tflops_measured": fp64_peak,
-                              "flop_per_rhs": flop_per_rhs or None,
-                              "achieved_tflops": (rhs_total * flop_per_rhs / (np.mean(kernel_ms) * 1e-3) / 1e12) if flop_per_rhs else None,
-                              "frac": (rhs_total * flop_per_rhs / (np.mean(kernel_ms) * 1e-3) / 1e12 / fp64_peak) if (flop_per_rhs and fp64_peak) else None},
+                         "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                         "note": "the path is FP64-ALU / latency bound (SURVEY 8d: >15 flop per algorithmic byte): "
+                                 "see roofline_fp64; algorithmic bytes = 576 B per accepted step + one read and one "
+                                 "write of each node record"},
+            "roofline_fp64": {"bound": "fp64", "achieved": ach_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": (ach_tflops / fp64_peak) if fp64_peak else None, "flop_per_rhs": FLOP_PER_RHS,
+                              "peak_source": "DFMA-chain microbenchmark in this process (glc_measure_fp64_peak_tflops)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        # CPU baseline (rank 0, N=1 only): the oracle on a bounded sample
+        # CPU baseline (rank 0, N=1 only): the CPU implementation on a bounded sample
         if world == 1:
             try:
-                from oracle import orc
-
-                orc.build()
-                cores = os.cpu_count() or 1
                 ns = min(args.cpu_sample, n)
-                o = orc.Oracle(fast=True)
-                synthetic.install(o, p)
-                pp, ff = props[:ns].copy(), flags[:ns].copy()
-                tc = time.perf_counter()
-                _, _, cc = o.evolve_batch(pp, ff, t_end[:ns], n_threads=cores)
-                dtc = time.perf_counter() - tc
-                line["cpu_baseline"] = {"value": cc["steps_accepted"] / dtc, "unit": UNIT, "cores": cores, "kind": "port",
-                                        "sample": "first %d node records of the GPU workload, %.1f s, %.0f nodes/s" % (ns, dtc, ns / dtc)}
+                v, nps, secs, cores = cpu_run(p, props[:ns], flags[:ns], t_end[:ns], repeats=1)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": "first %d node records of the GPU workload, %.1f s, %.0f nodes/s"
+                                                  % (ns, secs, nps)}
             except Exception as e:  # the checker is optional for the bench line
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         print(json.dumps(line))

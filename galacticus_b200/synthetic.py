@@ -160,7 +160,11 @@ def standard_nodes(params, n, seed=219, fresh_fraction=0.3, satellite_fraction=0
     props[:, P["DMSCALE_RATE"]] = np.where(sat, 0.0, rng.uniform(-0.1, 0.1, n) * rvir / conc)
     props[:, P["DMSCALE_TARGET"]] = props[:, P["DMSCALE"]] + props[:, P["DMSCALE_RATE"]] * (props[:, P["TIME_TARGET"]] - t0)
     props[:, P["SPIN"]] = jhalo
-    props[:, P["SPIN_RATE"]] = np.where(sat, 0.0, rng.uniform(0.0, 0.3, n) * jhalo)
+    # the halo gains angular momentum with its mass at (roughly) fixed spin parameter, J ~ M^(5/3): the specific
+    # angular momentum of freshly accreted gas is then that of the halo (haloAngularMomentumInterpolate tracks
+    # the same relation between neighbouring tree nodes); an uncorrelated rate would hand newly created hot
+    # haloes almost no angular momentum and make parsec-sized, pathologically stiff disks
+    props[:, P["SPIN_RATE"]] = np.where(sat, 0.0, (5.0 / 3.0) * jhalo * growth / mass * rng.uniform(0.7, 1.3, n))
     props[:, P["SPIN_TARGET"]] = jhalo + props[:, P["SPIN_RATE"]] * (props[:, P["TIME_TARGET"]] - t0)
     props[:, P["TIME_LAST_ISOLATED"]] = np.where(sat, t0 * rng.uniform(0.6, 1.0, n), 0.0)
     props[:, P["SAT_BOUND_MASS"]] = mass

@@ -5,6 +5,7 @@
 
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../galacticus_b200/csrc/glc_detmath.h"
 #include <string.h>
@@ -464,10 +465,77 @@ double orc_linear_table_eval(orc_fn1 g, void *ctx, double xmin, double xmax, int
 
 static double powfn(double x, void *ctx) { return dm_pow(x, *(double *)ctx); }
 
+/* The reference tabulates x^exponent once per fastExponentiator object (math/exponentiation.F90:57-104).  The
+ * values are kept in a small per-process cache keyed by the table's definition; a cached entry is exactly the
+ * dm_pow value the on-the-fly evaluation would produce, so results do not change -- only the CPU baseline gets
+ * the reference's own cost profile (table look-ups instead of pow calls). */
+#define ORC_POW_TABLES 4
+static struct {
+    double range_min, range_max, exponent, density;
+    int n;
+    double *v;
+} orc_pow_cache[ORC_POW_TABLES];
+static int orc_pow_cache_n = 0;
+
+static const double *orc_pow_table(double range_min, double range_max, double exponent, double density, int *n_out) {
+    int t, k;
+    for (t = 0; t < orc_pow_cache_n; t++)
+        if (orc_pow_cache[t].range_min == range_min && orc_pow_cache[t].range_max == range_max &&
+            orc_pow_cache[t].exponent == exponent && orc_pow_cache[t].density == density) {
+            *n_out = orc_pow_cache[t].n;
+            return orc_pow_cache[t].v;
+        }
+    {
+        const double *result = 0;
+#pragma omp critical(orc_pow_cache_build)
+        {
+            for (t = 0; t < orc_pow_cache_n; t++)
+                if (orc_pow_cache[t].range_min == range_min && orc_pow_cache[t].range_max == range_max &&
+                    orc_pow_cache[t].exponent == exponent && orc_pow_cache[t].density == density)
+                    break;
+            if (t == orc_pow_cache_n && orc_pow_cache_n < ORC_POW_TABLES) {
+                const int n = (int)((range_max - range_min) * density) + 1;
+                const double dx = (range_max - range_min) / (double)(n - 1);
+                double *v = (double *)malloc(sizeof(double) * (size_t)n);
+                for (k = 0; k < n; k++) v[k] = dm_pow((k == n - 1) ? range_max : range_min + dx * (double)k, exponent);
+                orc_pow_cache[t].range_min = range_min;
+                orc_pow_cache[t].range_max = range_max;
+                orc_pow_cache[t].exponent = exponent;
+                orc_pow_cache[t].density = density;
+                orc_pow_cache[t].n = n;
+                orc_pow_cache[t].v = v;
+#pragma omp flush
+                orc_pow_cache_n = t + 1;
+            }
+            if (t < orc_pow_cache_n) {
+                *n_out = orc_pow_cache[t].n;
+                result = orc_pow_cache[t].v;
+            }
+        }
+        return result;
+    }
+}
+
 double orc_fast_exponentiate(double range_min, double range_max, double exponent, double density, double x) {
     /* math/exponentiation.F90:57-104 */
-    int point_count;
+    int n, i;
+    const double *v;
     if (x < range_min || x > range_max) return dm_pow(x, exponent);
-    point_count = (int)((range_max - range_min) * density) + 1;
-    return orc_linear_table_eval(powfn, &exponent, range_min, range_max, point_count, x, 0);
+    v = orc_pow_table(range_min, range_max, exponent, density, &n);
+    if (!v) return orc_linear_table_eval(powfn, &exponent, range_min, range_max, (int)((range_max - range_min) * density) + 1, x, 0);
+    {
+        const double dx = (range_max - range_min) / (double)(n - 1);
+        const double inverse_dx = 1.0 / ((range_min + dx) - range_min);
+        double xi, h;
+        if (x >= range_max)
+            i = n - 1;
+        else {
+            i = (int)((x - range_min) * inverse_dx) + 1;
+            if (i > n - 1) i = n - 1;
+            if (i < 1) i = 1;
+        }
+        xi = range_min + dx * (double)(i - 1);
+        h = (x - xi) * inverse_dx;
+        return v[i - 1] * (1.0 - h) + v[i] * h;
+    }
 }
