@@ -188,7 +188,11 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
             for (int p = 0; p < nslots; p++) {
                 const int s = perm[p];
                 LaneMem M{&A, A.ws + (int64_t)s * (WS_NVEC * NY), 1};
-                any |= machine_step(slot_ref(slots, s), M);
+                const SlotRef S = slot_ref(slots, s);
+                any |= machine_step(S, M);
+                // mimic the device's sticky mode on a pseudo-random subset of the steps
+                if ((rng() & 3u) == 0u)
+                    for (int k = 0; k < 64 && S.unit != U_IDLE && S.unit != U_RK; k++) machine_step(S, M);
             }
             if (!any) break;
         }
