@@ -61,6 +61,10 @@ struct glc_evolver {
     SlotArrays d_slots{};           // micro-task machine: per-slot continuations, split by access group
     int64_t nslots_machine = 0;
     int32_t use_machine = 1;        // standard model: 1 = micro-task machine, 0 = warp-synchronous evolve_kernel
+    int32_t drain_handover = 1;     // run-to-completion mode: finish the last nodes with drain_kernel
+    int64_t drain_threshold = 60000;  // hand over when fewer slots than this are still in flight
+    int32_t *d_held = nullptr;
+    int64_t held_cap = 0;
     int32_t *d_order = nullptr;     // queue order (component-sorted node ids)
     int *d_sort = nullptr;          // 2 x 64 bucket counters
     int64_t order_cap = 0;
@@ -282,7 +286,7 @@ static int launch_evolve(glc_evolver *ev, int n, unsigned long long *hc) {
     A.resume = 0;
     A.budget = ev->slice_budget > 0 ? ev->slice_budget : 0x7fffffff;
     GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
-    GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 8, ev->stream));
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 16, ev->stream));
     const double t_start = now_s();
     int nslice = 0;
     for (;;) {
@@ -371,53 +375,99 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc) {
     }
 #endif
     GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
-    GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 8, ev->stream));
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 16, ev->stream));
     const double t_start = now_s();
     int nslice = 0;
-    unsigned long long tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    A.hold = 0;
+    A.held = nullptr;
+    A.nheld = 0;
+    A.held_counter = nullptr;
+    A.slotL = nullptr;
+    A.slotYt = nullptr;
+    A.slotUnit = nullptr;
+    A.drainSparse = 0;
+    // Run-to-completion mode (no user time slices) is a hybrid: the machine works in internal slices while the node
+    // queue still refills its slots and for as long as enough slots stay in flight to fill warps; then the slots
+    // are brought to an RK boundary (hold slices) and handed to drain_kernel, which finishes their nodes with
+    // whole evaluations.  With a user slice budget the machine alone runs (resumable by construction).
+    const bool hybrid = ev->slice_budget <= 0 && ev->drain_handover;
+    if (hybrid) A.budget = 4096;
+    const unsigned long long drainBelow = (unsigned long long)ev->drain_threshold;
+    bool draining = false;
     for (;;) {
-        if (ev->slice_log > 1) fprintf(stderr, "[glc host] launching machine_kernel grid=%d budget=%d resume=%d n=%d\n", grid, A.budget, A.resume, n);
+        if (ev->slice_log > 1) fprintf(stderr, "[glc host] launching machine_kernel grid=%d budget=%d resume=%d hold=%d n=%d\n", grid, A.budget, A.resume, A.hold, n);
         machine_kernel<GLC_MTHREADS, GLC_MSLOTS><<<grid, GLC_MTHREADS, kMachineSmem, ev->stream>>>(A, ev->d_slots);
         ev->launches++;
         ev->slices++;
         GLC_CHECK(ev, cudaGetLastError());
-        if (ev->slice_log > 1) fprintf(stderr, "[glc host] launched; copying counters\n");
-#ifdef GLC_DEBUG_HANG
-        {
-            const double t0 = now_s();
-            bool dumped = false;
-            while (cudaStreamQuery(ev->stream) == cudaErrorNotReady) {
-                if (!dumped && now_s() - t0 > 8.0) {
-                    dumped = true;
-                    fprintf(stderr, "[glc hang] kernel still running after 8 s; per-warp progress (state it u start take idle lane slot):\n");
-                    for (int b = 0; b < grid; b++)
-                        for (int w = 0; w < GLC_MTHREADS / 32; w++) {
-                            const int *d = h_dbg + ((size_t)b * (GLC_MTHREADS / 32) + w) * 8;
-                            fprintf(stderr, "  block %d warp %2d: state %d it %d u %d start %d take %d idle %d lane %d slot %d\n", b, w,
-                                    d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
-                        }
-                }
-                if (now_s() - t0 > 20.0) {
-                    fprintf(stderr, "[glc hang] giving up\n");
-                    _exit(3);
-                }
-            }
-        }
-#endif
-        GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost,
+        GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 9, cudaMemcpyDeviceToHost,
                                       ev->stream));
-        if (ev->slice_log > 1) fprintf(stderr, "[glc host] counters copy issued: done=%llu\n", hc[6]);
-        if (ev->slice_budget <= 0) break;
+        if (ev->slice_budget <= 0 && !hybrid) break;
         GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
         if (ev->slice_log)
-            fprintf(stderr, "[glc slice %lld] t=%.3f ms done=%llu/%d rhs=%llu accepted=%llu parked=%llu\n",
-                    (long long)ev->slices, 1e3 * (now_s() - t_start), hc[6], n, hc[2], hc[0], hc[7]);
-        GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long), ev->stream));
+            fprintf(stderr, "[glc slice %lld] t=%.3f ms done=%llu/%d rhs=%llu accepted=%llu parked=%llu mid-evaluation=%llu%s\n",
+                    (long long)ev->slices, 1e3 * (now_s() - t_start), hc[6], n, hc[2], hc[0], hc[7], hc[8], draining ? " (hold)" : "");
+        const unsigned long long parked = hc[7], midEvaluation = hc[8];
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long) * 2, ev->stream));
         if (hc[6] >= (unsigned long long)n) break;
         if (ev->max_slices > 0 && ++nslice >= ev->max_slices) break;  // profiling aid: leaves the batch unfinished
         A.resume = 1;
+        if (hybrid) {
+            // every node has been handed out once done + parked covers the batch
+            const bool queueDry = hc[6] + parked >= (unsigned long long)n;
+            if (!draining && queueDry && parked < drainBelow) {
+                draining = true;
+                A.hold = 1;
+                A.budget = 512;
+            }
+            if (draining && midEvaluation == 0) {
+                // ---- hand the held slots to the drain kernel: dense passes (one node per lane, bounded number of
+                // evaluations) while there are more nodes than warps, then one node per warp to the end
+                if (!ev->d_held || ev->held_cap < ev->nslots_machine) {
+                    cudaFree(ev->d_held);
+                    ev->d_held = nullptr;
+                    GLC_CHECK(ev, cudaMalloc(&ev->d_held, sizeof(int32_t) * (ev->nslots_machine + 2)));
+                    ev->held_cap = ev->nslots_machine;
+                }
+                int *d_count = reinterpret_cast<int *>(ev->d_held + ev->nslots_machine);  // [0] list length, [1] cursor
+                int bps = 0;
+                GLC_CHECK(ev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, drain_kernel<ModelStandard>, kBlock, 0));
+                if (bps < 1) bps = 1;
+                const int nslotsActive = grid * GLC_MSLOTS;
+                const int warpsResident = ev->num_sms * bps * (kBlock / 32);
+                A.slotL = ev->d_slots.L;
+                A.slotYt = ev->d_slots.yt;
+                A.slotUnit = ev->d_slots.unit;
+                for (int pass = 0;; pass++) {
+                    GLC_CHECK(ev, cudaMemsetAsync(d_count, 0, sizeof(int) * 2, ev->stream));
+                    held_list_kernel<<<std::min((nslotsActive + 255) / 256, ev->num_sms * 8), 256, 0, ev->stream>>>(
+                        ev->d_slots.unit, nslotsActive, ev->d_held, d_count);
+                    int nheld = 0;
+                    GLC_CHECK(ev, cudaMemcpyAsync(&nheld, d_count, sizeof(int), cudaMemcpyDeviceToHost, ev->stream));
+                    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+                    if (nheld == 0) break;
+                    const bool sparse = nheld <= warpsResident;
+                    A.held = ev->d_held;
+                    A.nheld = nheld;
+                    A.held_counter = d_count + 1;
+                    A.drainSparse = sparse ? 1 : 0;
+                    A.budget = sparse ? 0x7fffffff : 384;
+                    int dgrid = sparse ? (nheld + kBlock / 32 - 1) / (kBlock / 32) : (nheld + kBlock - 1) / kBlock;
+                    dgrid = std::max(1, std::min(ev->num_sms * bps, dgrid));
+                    drain_kernel<ModelStandard><<<dgrid, kBlock, 0, ev->stream>>>(A);
+                    ev->launches += 2;
+                    GLC_CHECK(ev, cudaGetLastError());
+                    GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 9, cudaMemcpyDeviceToHost,
+                                                  ev->stream));
+                    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+                    if (ev->slice_log)
+                        fprintf(stderr, "[glc drain pass %d%s] t=%.3f ms held=%d done=%llu/%d rhs=%llu\n", pass,
+                                sparse ? " sparse" : "", 1e3 * (now_s() - t_start), nheld, hc[6], n, hc[2]);
+                }
+                break;
+            }
+        }
     }
-    (void)tot;
     GLC_CHECK(ev, cudaEventRecord(ev->ev1, ev->stream));
     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
     return 0;
@@ -458,11 +508,13 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_SLICE_LOG")) ev->slice_log = atoi(e);
     if (const char *e = getenv("GLC_MAX_SLICES")) ev->max_slices = atoi(e);
     if (const char *e = getenv("GLC_MACHINE")) ev->use_machine = atoi(e);
+    if (const char *e = getenv("GLC_DRAIN")) ev->drain_handover = atoi(e);
+    if (const char *e = getenv("GLC_DRAIN_BELOW")) ev->drain_threshold = atoll(e);
     cudaStreamCreateWithFlags(&ev->stream, cudaStreamNonBlocking);
     cudaEventCreate(&ev->ev0);
     cudaEventCreate(&ev->ev1);
     cudaMalloc(&ev->d_work, sizeof(int));
-    cudaMalloc(&ev->d_counters, sizeof(unsigned long long) * 8);
+    cudaMalloc(&ev->d_counters, sizeof(unsigned long long) * 16);
     if (cudaGetLastError() != cudaSuccess) {
         delete ev;
         return -5;
@@ -492,6 +544,7 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaFree(ev->d_ws);
     cudaFree(ev->d_work);
     cudaFree(ev->d_counters);
+    cudaFree(ev->d_held);
     cudaFree(ev->d_pow_ac);
     cudaFree(ev->d_pow_kmt);
     cudaFree(ev->d_lanes);
@@ -639,7 +692,7 @@ int glc_evolve_arena(glc_evolver *ev, int64_t n, glc_counters *counters) {
     cudaSetDevice(ev->device);
     int rc = upload_constants(ev);
     if (rc) return rc;
-    unsigned long long hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long hc[16] = {0};
     if (ev->params.model == GLC_MODEL_BOX)
         rc = launch_evolve<ModelBox>(ev, (int)n, hc);
     else if (ev->use_machine)

@@ -151,6 +151,15 @@ struct KernelArgs {
     int resume;                    // 0: first slice of a batch (lanes start empty), 1: resume parked lanes
     int budget;                    // heavy calls per lane in this slice
     volatile int *debug;           // GLC_DEBUG_HANG builds: host-mapped per-warp progress words (else null)
+    // drain hand-over (machine -> drain_kernel): see glc_api.cu launch_machine
+    int hold;                      // machine: slots that reach an RK boundary (U_RHS_BEGIN) are held, not re-queued
+    const int32_t *held;           // drain: list of held slot ids
+    int nheld;
+    int *held_counter;             // drain: cursor into `held`
+    struct LaneState *slotL;       // drain: the machine's per-slot lane states and stage inputs
+    double *slotYt;                // [nslots][NY]
+    int *slotUnit;                 // drain: pending-unit words (a finished slot is marked -1)
+    int drainSparse;               // drain: 1 = one node per warp (lane 0 only): the last nodes run at lone-lane speed
 };
 
 // Per-node context kept in registers while a node is resident in a thread.

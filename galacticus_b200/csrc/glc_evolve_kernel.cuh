@@ -530,7 +530,109 @@ GLC_UNROLL_RK
     return L.heavy != HV_NONE;
 }
 
+// Drain path.  Takes over the slots the micro-task machine (glc_machine.cuh) has parked at an RK boundary -- lane
+// state after lane_prepare, stage input yt ready, nothing of the evaluation started -- and finishes their nodes with
+// whole evaluations: one lane per node, the warp-synchronous rate function, 255 registers.  When few nodes are left
+// there is nothing to re-group, and running an evaluation straight through is ~5x cheaper than unit by unit.
+// One call = take the next held slot if this lane has none, then ONE iteration of it.  Returns false when the lane
+// is out of work.  `fresh` = the lane's state was just loaded (skip lane_prepare: it has already run).
+GLC_DEVICE_INLINE void drain_tally(LaneState &L, unsigned int (&tot)[7]) {
+    tot[0] += L.nAcc;
+    tot[1] += L.nRej;
+    tot[2] += L.nRhs;
+    tot[3] += L.nSeg;
+    tot[4] += L.nTrialFail;
+    tot[5] += L.nNodes;
+    tot[6] += L.nDone;
+    L.nAcc = L.nRej = L.nRhs = L.nSeg = L.nTrialFail = L.nNodes = L.nDone = 0;
+}
+
+template <class Model>
+GLC_DEVICE_INLINE bool drain_iterate(LaneState &L, LaneMem &M, const KernelArgs &A, double (&yt)[NY], bool &fresh,
+                                     int &slotHeld, unsigned int (&tot)[7], bool mayTake) {
+    double rate[NY];
+    if (slotHeld == -1 && mayTake) {
+        const int h = glc_atomic_add(A.held_counter, 1);
+        if (h < A.nheld) {
+            slotHeld = A.held[h];
+            L = A.slotL[slotHeld];
+            GLC_UNROLL_RK
+            for (int i = 0; i < NY; i++) yt[i] = A.slotYt[(int64_t)slotHeld * NY + i];
+            M.ws = A.ws + (int64_t)slotHeld * (WS_NVEC * NY);
+            M.wstride = 1;
+            fresh = true;
+        } else
+            slotHeld = -2;  // list exhausted
+    }
+    const bool have = slotHeld >= 0;
+    if (have && !fresh) lane_prepare<Model>(L, M, yt);
+    fresh = false;
+    GLC_UNROLL_RK
+    for (int i = 0; i < NY; i++) rate[i] = 0.0;
+    const bool on = have && (L.heavy == HV_RHS || L.heavy == HV_POST_EVOLVE);
+    GLC_SYNCWARP();
+    const int code = Model::rates(L.ctx, L.ts, yt, rate, L.heavy == HV_POST_EVOLVE, on);
+    if (have) {
+        lane_consume<Model>(L, M, yt, rate, code);
+        if (L.phase == PH_FETCH) {  // node written back; the node queue is empty in the drain: release the slot
+            drain_tally(L, tot);
+            if (A.slotUnit) A.slotUnit[slotHeld] = -1;
+            slotHeld = -1;
+        }
+    }
+    return slotHeld >= 0 || (slotHeld == -1 && mayTake);
+}
+
+// Parks a node the drain kernel could not finish within its budget: brings the lane to the next RK boundary (state
+// after lane_prepare, exactly what the machine parks) and stores it back into the slot.
+template <class Model>
+GLC_DEVICE_INLINE void drain_park(LaneState &L, LaneMem &M, const KernelArgs &A, double (&yt)[NY], bool fresh, int slotHeld,
+                                  unsigned int (&tot)[7]) {
+    if (slotHeld < 0) return;
+    double rate[NY];
+    if (!fresh) {
+        for (;;) {
+            lane_prepare<Model>(L, M, yt);
+            if (L.heavy != HV_FROZEN) break;
+            GLC_UNROLL_RK
+            for (int i = 0; i < NY; i++) rate[i] = 0.0;
+            lane_consume<Model>(L, M, yt, rate, GLC_INT_NONE);
+        }
+    }
+    drain_tally(L, tot);
+    if (L.heavy == HV_NONE) {
+        if (A.slotUnit) A.slotUnit[slotHeld] = -1;
+        return;
+    }
+    A.slotL[slotHeld] = L;
+    GLC_UNROLL_RK
+    for (int i = 0; i < NY; i++) A.slotYt[(int64_t)slotHeld * NY + i] = yt[i];
+}
+
 #if defined(__CUDACC__)
+template <class Model>
+__global__ void __launch_bounds__(GLC_BLOCK, GLC_MIN_BLOCKS) drain_kernel(KernelArgs A) {
+    LaneMem M{&A, A.ws, 1};
+    LaneState L;
+    lane_reset(L);
+    double yt[NY];
+    bool fresh = false;
+    int slotHeld = -1;
+    unsigned int tot[7] = {0, 0, 0, 0, 0, 0, 0};
+    const bool mayTake = !A.drainSparse || (threadIdx.x & 31) == 0;
+    for (int it = 0; it < A.budget; ++it) {
+        const bool active = drain_iterate<Model>(L, M, A, yt, fresh, slotHeld, tot, mayTake);
+        if (!__any_sync(0xffffffffu, active)) break;
+    }
+    drain_park<Model>(L, M, A, yt, fresh, slotHeld, tot);
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        unsigned int v = tot[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&A.counters[k], (unsigned long long)v);
+    }
+}
+
 template <class Model>
 __global__ void __launch_bounds__(GLC_BLOCK, GLC_MIN_BLOCKS) evolve_kernel(KernelArgs A) {
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -555,7 +555,10 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
             own.unit = U_RK;
         }
         const int u = own.unit;
-        s_q[u][atomicAdd(&s_tail[u], 1u) & (SLOTS - 1)] = (unsigned short)s;  // lap 0: tag 0
+        if (A.hold && u == U_RHS_BEGIN)
+            atomicAdd(&s_idle, 1);  // held at an RK boundary for the drain kernel: out of work as far as this block goes
+        else
+            s_q[u][atomicAdd(&s_tail[u], 1u) & (SLOTS - 1)] = (unsigned short)s;  // lap 0: tag 0
     }
     __syncthreads();
 
@@ -665,7 +668,7 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
             machine_step(S, M);
             const int nu = S.unit;
             __threadfence_block();  // release: continuation stores before the queue entry
-            if (nu == U_IDLE)
+            if (nu == U_IDLE || (A.hold && nu == U_RHS_BEGIN))
                 atomicAdd(&s_idle, 1);
             else {
                 const unsigned int np = atomicAdd(&s_tail[nu], 1u);
@@ -680,7 +683,7 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
     GLC_DBG(0, 9);
     __syncthreads();
     // ---- counters of this block's slots: warp-reduce then one atomic per warp per counter
-    unsigned int vals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned int vals[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
     for (int k = 0; k < PER; k++) {
         const SlotRef own = slot_ref(slots, base + tid + k * THREADS);
@@ -693,14 +696,21 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
         vals[5] += L.nNodes;
         vals[6] += L.nDone;
         vals[7] += own.unit != U_IDLE ? 1u : 0u;
+        vals[8] += (own.unit != U_IDLE && own.unit != U_RHS_BEGIN) ? 1u : 0u;
         L.nAcc = L.nRej = L.nRhs = L.nSeg = L.nTrialFail = L.nNodes = L.nDone = 0;
     }
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 9; k++) {
         unsigned int v = vals[k];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0 && v) atomicAdd(&A.counters[k], (unsigned long long)v);
     }
+}
+
+// compacts the ids of the slots held at an RK boundary into a list for drain_kernel
+__global__ void held_list_kernel(const int *__restrict__ unit, int nslots, int32_t *held, int *count) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += gridDim.x * blockDim.x)
+        if (unit[i] == U_RHS_BEGIN) held[atomicAdd(count, 1)] = i;
 }
 #endif
 

@@ -47,7 +47,8 @@ def lib() -> C.CDLL:
 class EmuEvolver:
     """Same calling convention as galacticus_b200.Evolver.evolve_batch, executed lane by lane on the host."""
 
-    def __init__(self, nslots: int = 64, budget: int = 0, sort: bool = True, machine: bool = True):
+    def __init__(self, nslots: int = 64, budget: int = 0, sort: bool = True, machine=True):
+        """machine: False = lane kernel logic, True/1 = micro-task machine, 2 = machine + drain hand-over."""
         self.L = lib()
         self.h = C.c_void_p(self.L.emu_create())
         self.nslots, self.budget, self.sort, self.machine = nslots, budget, sort, machine

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <random>
 #include <vector>
 
@@ -115,7 +116,8 @@ static void run(Emu *e, int64_t n, double *props, int32_t *flags, const double *
 // order in which the slots of a block are visited is shuffled (seeded) to mimic the device's regrouping, which
 // must not change any result.
 static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const double *time_end, int32_t *status,
-                        int32_t *interrupt, glc_counters *counters, int nslots, int budget, int sort, int64_t *slices) {
+                        int32_t *interrupt, glc_counters *counters, int nslots, int budget, int sort, int64_t *slices,
+                        bool handover) {
     const int64_t cap = n;
     std::vector<double> soa((size_t)NPROP * cap);
     for (int64_t i = 0; i < n; i++)
@@ -184,6 +186,7 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
         }
         for (int it = 0; it < A.budget; ++it) {
             bool any = false;
+            if (handover && work >= A.n && it >= 3) break;  // node queue dry: go to the drain hand-over below
             std::shuffle(perm.begin(), perm.end(), rng);
             for (int p = 0; p < nslots; p++) {
                 const int s = perm[p];
@@ -210,6 +213,76 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
         (*slices)++;
         if (hc[6] >= (unsigned long long)n) break;
         A.resume = 1;
+        if (handover && work >= A.n) {
+            // ---- hold: bring every active slot to an RK boundary, as the device's hold slices do
+            for (bool moved = true; moved;) {
+                moved = false;
+                for (int s = 0; s < nslots; s++) {
+                    const SlotRef S = slot_ref(slots, s);
+                    if (S.unit != U_IDLE && S.unit != U_RHS_BEGIN) {
+                        LaneMem M{&A, A.ws + (int64_t)s * (WS_NVEC * NY), 1};
+                        machine_step(S, M);
+                        moved = true;
+                    }
+                }
+            }
+            for (int s = 0; s < nslots; s++) {  // counters gathered so far
+                LaneState &L = sL[s];
+                hc[0] += L.nAcc; hc[1] += L.nRej; hc[2] += L.nRhs; hc[3] += L.nSeg; hc[4] += L.nTrialFail; hc[5] += L.nNodes; hc[6] += L.nDone;
+                L.nAcc = L.nRej = L.nRhs = L.nSeg = L.nTrialFail = L.nNodes = L.nDone = 0;
+            }
+            // ---- drain: the held slots are finished by whole evaluations (drain_iterate), 7 "lanes"
+            std::vector<int32_t> held;
+            for (int s = 0; s < nslots; s++)
+                if (sUnit[s] == U_RHS_BEGIN) held.push_back(s);
+            int cursor = 0;
+            A.held = held.data();
+            A.nheld = (int)held.size();
+            A.held_counter = &cursor;
+            A.slotL = sL.data();
+            A.slotYt = sYt.data();
+            A.slotUnit = sUnit.data();
+            A.drainSparse = 0;
+            const int nl = 7;
+            std::vector<LaneState> dl(nl);
+            std::vector<LaneMem> dm(nl, LaneMem{&A, A.ws, 1});
+            std::vector<std::array<double, NY>> dyt(nl);
+            std::vector<char> fresh(nl, 0);
+            std::vector<int> hs(nl, -1);
+            unsigned int tot[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (int l = 0; l < nl; l++) lane_reset(dl[l]);
+            // passes of a bounded number of evaluations: unfinished nodes are parked (drain_park) and picked up
+            // again by the next pass, as the device does
+            for (int pass = 0; !held.empty(); pass++) {
+                cursor = 0;
+                A.held = held.data();
+                A.nheld = (int)held.size();
+                for (int l = 0; l < nl; l++) {
+                    lane_reset(dl[l]);
+                    hs[l] = -1;
+                    fresh[l] = 0;
+                }
+                for (int it = 0; it < 5 + 3 * pass; it++) {
+                    bool any = false;
+                    for (int l = 0; l < nl; l++) {
+                        bool f = fresh[l] != 0;
+                        double(&y)[NY] = *reinterpret_cast<double(*)[NY]>(dyt[l].data());
+                        any |= drain_iterate<ModelStandard>(dl[l], dm[l], A, y, f, hs[l], tot, true);
+                        fresh[l] = f ? 1 : 0;
+                    }
+                    if (!any) break;
+                }
+                for (int l = 0; l < nl; l++) {
+                    double(&y)[NY] = *reinterpret_cast<double(*)[NY]>(dyt[l].data());
+                    drain_park<ModelStandard>(dl[l], dm[l], A, y, fresh[l] != 0, hs[l], tot);
+                }
+                held.clear();
+                for (int s = 0; s < nslots; s++)
+                    if (sUnit[s] == U_RHS_BEGIN) held.push_back(s);
+            }
+            for (int k = 0; k < 7; k++) hc[k] += tot[k];
+            break;
+        }
     }
     for (int64_t i = 0; i < n; i++)
         for (int p = 0; p < NPROP; p++) props[i * NPROP + p] = soa[(size_t)p * cap + i];
@@ -260,7 +333,7 @@ int emu_evolve_batch(void *h, int64_t n, double *props, int32_t *flags, const do
     if (e->params.model == GLC_MODEL_BOX)
         run<ModelBox>(e, n, props, flags, time_end, status, interrupt, counters, nslots, budget, sort, slices);
     else if (machine)
-        run_machine(e, n, props, flags, time_end, status, interrupt, counters, nslots, budget, sort, slices);
+        run_machine(e, n, props, flags, time_end, status, interrupt, counters, nslots, budget, sort, slices, machine == 2);
     else
         run<ModelStandard>(e, n, props, flags, time_end, status, interrupt, counters, nslots, budget, sort, slices);
     return 0;

@@ -11,8 +11,8 @@ from tests import cases, emu
 P = abi.P
 
 
-def _both(orc, p, nslots, budget, sort, tables=True):
-    e = emu.EmuEvolver(nslots, budget, sort)
+def _both(orc, p, nslots, budget, sort, tables=True, machine=True):
+    e = emu.EmuEvolver(nslots, budget, sort, machine)
     o = orc.Oracle()
     if tables:
         synthetic.install(e, p)
@@ -23,10 +23,16 @@ def _both(orc, p, nslots, budget, sort, tables=True):
     return e, o
 
 
-@pytest.mark.parametrize("nslots,budget,sort", [(64, 0, True), (96, 7, True), (33, 50, False)])
-def test_standard_lane_logic_is_bit_identical_to_oracle(oracle_lib, nslots, budget, sort):
+@pytest.mark.parametrize("nslots,budget,sort,machine", [
+    (64, 0, True, False),   # lane state machine + warp-synchronous rate function (evolve_kernel)
+    (96, 7, True, True),    # micro-task machine, time slices, shuffled slot order, sticky stepping
+    (33, 50, False, True),
+    (40, 0, True, 2),       # machine, then hold at RK boundaries and hand over to drain_iterate
+    (300, 9, False, 2),
+])
+def test_standard_lane_logic_is_bit_identical_to_oracle(oracle_lib, nslots, budget, sort, machine):
     p = cases.standard_params()
-    e, o = _both(oracle_lib, p, nslots, budget, sort)
+    e, o = _both(oracle_lib, p, nslots, budget, sort, machine=machine)
     props, flags, t_end = synthetic.standard_nodes(p, 1500, seed=103)
     pe, fe = props.copy(), flags.copy()
     po, fo = props.copy(), flags.copy()
@@ -37,7 +43,7 @@ def test_standard_lane_logic_is_bit_identical_to_oracle(oracle_lib, nslots, budg
     np.testing.assert_array_equal(fe, fo)
     assert ce == co  # integer bookkeeping: segments, accepted/rejected steps, RHS evaluations
     assert np.array_equal(pe, po), "records not bit-identical"
-    if budget:
+    if budget and machine != 2:
         assert e.slices > 1  # the time-slice / park / resume path was exercised
 
 
