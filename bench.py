@@ -42,7 +42,7 @@ METRIC = "node_ode_steps_per_s"
 UNIT = "accepted RKCK node-ODE steps/s"
 # FP64 flop per evaluation of the rate function (DADD + DMUL + 2*DFMA thread-level SASS instructions of
 # machine_kernel divided by its RHS counter, ncu capture profiles/r01_machine_kernel_summary.txt)
-FLOP_PER_RHS = 1.0e4
+FLOP_PER_RHS = 7.8e3
 N_Y = 24
 
 
@@ -330,8 +330,13 @@ def main():
                 "stellar_mass_function_counts": hist_t.cpu().numpy().tolist(),
             },
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None,
+                         # DRAM traffic of the dominant kernel: ncu --set full capture of one machine_kernel launch
+                         # (profiles/r01c_machine_kernel_bulk_slice.txt: 37.94 GB read+written for 3 100 520 RHS
+                         # evaluations = 12.2 kB per evaluation, continuation records streaming through L2), scaled to
+                         # this launch's evaluation count
+                         "traffic": 37.94e9 / 3100520.0 * rhs_total,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                         "kernel": "machine_kernel (+ its drain_kernel continuation)",
                          "note": "the path is FP64-ALU / latency bound (SURVEY 8d: >15 flop per algorithmic byte): "
                                  "see roofline_fp64; algorithmic bytes = 576 B per accepted step + one read and one "
                                  "write of each node record"},
