@@ -1,0 +1,52 @@
+"""Regenerates the committed golden vectors: seeded node batches and the records the CPU checker (oracle/, parity
+build: gcc -O2 -ffp-contract=off) evolves them to.  The reference itself cannot be run in this image (no Fortran
+toolchain), so these vectors pin OUR restatement against accidental change; the reference's own golden values
+(closedBox / leakyBox, testSuite/test-reproducibility.py:46-67) are asserted in tests/test_oracle_golden.py.
+
+usage: python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from galacticus_b200 import abi, synthetic  # noqa: E402
+from oracle import orc  # noqa: E402
+from tests import cases  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def run(name, p, props, flags, t_end, tables):
+    o = orc.Oracle()
+    if tables:
+        synthetic.install(o, p)
+    else:
+        o.set_params(p)
+    po, fo = props.copy(), flags.copy()
+    status, interrupt, c = o.evolve_batch(po, fo, t_end, n_threads=1)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), props_in=props, flags_in=flags, t_end=t_end, props_out=po,
+                        flags_out=fo, status=status, interrupt=interrupt,
+                        counters=np.array([c[k] for k in sorted(c)], dtype=np.int64), counter_names=np.array(sorted(c)))
+    print(name, props.shape, c)
+
+
+def main():
+    orc.build()
+    p = cases.standard_params()
+    props, flags, t_end = synthetic.standard_nodes(p, 96, seed=4242)
+    run("standard_96", p, props, flags, t_end, True)
+    from galacticus_b200.evolver import params_default
+
+    pb = params_default(abi.GLC_MODEL_BOX)
+    pb.box_timescaleStarFormation = 0.5
+    pb.box_fractionOutflow = 1.0
+    props, flags, t_end = cases.box_nodes(96, seed=4243, leaky=True)
+    run("box_leaky_96", pb, props, flags, t_end, False)
+
+
+if __name__ == "__main__":
+    main()

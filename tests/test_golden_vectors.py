@@ -1,0 +1,72 @@
+"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py): the CPU checker, the kernel
+source driven on the host (tests/emu) and -- on the GPU box -- the CUDA path through the C-ABI must all reproduce
+them bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from galacticus_b200 import abi, synthetic
+from tests import cases
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _case(name):
+    g = np.load(os.path.join(HERE, name + ".npz"))
+    if name.startswith("standard"):
+        p = cases.standard_params()
+        tables = True
+    else:
+        from galacticus_b200.evolver import params_default
+
+        p = params_default(abi.GLC_MODEL_BOX)
+        p.box_timescaleStarFormation = 0.5
+        p.box_fractionOutflow = 1.0
+        tables = False
+    return g, p, tables
+
+
+def _check(g, props, flags, status, interrupt, counters):
+    np.testing.assert_array_equal(status, g["status"])
+    np.testing.assert_array_equal(interrupt, g["interrupt"])
+    np.testing.assert_array_equal(flags, g["flags_out"])
+    assert np.array_equal(props, g["props_out"]), "records differ from the golden vector"
+    want = dict(zip([str(k) for k in g["counter_names"]], [int(v) for v in g["counters"]]))
+    assert counters == want
+
+
+@pytest.mark.parametrize("name", ["standard_96", "box_leaky_96"])
+def test_oracle_reproduces_golden(oracle_lib, name):
+    g, p, tables = _case(name)
+    o = oracle_lib.Oracle()
+    synthetic.install(o, p) if tables else o.set_params(p)
+    props, flags = g["props_in"].copy(), g["flags_in"].copy()
+    s, i, c = o.evolve_batch(props, flags, g["t_end"], n_threads=4)
+    _check(g, props, flags, s, i, c)
+
+
+@pytest.mark.parametrize("name", ["standard_96", "box_leaky_96"])
+def test_kernel_source_on_host_reproduces_golden(name):
+    from tests import emu
+
+    g, p, tables = _case(name)
+    e = emu.EmuEvolver(nslots=40, budget=11, sort=True, machine=2 if tables else True)
+    synthetic.install(e, p) if tables else e.set_params(p)
+    props, flags = g["props_in"].copy(), g["flags_in"].copy()
+    s, i, c = e.evolve_batch(props, flags, g["t_end"])
+    _check(g, props, flags, s, i, c)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["standard_96", "box_leaky_96"])
+def test_cuda_reproduces_golden(name):
+    from galacticus_b200.evolver import Evolver
+
+    g, p, tables = _case(name)
+    ev = Evolver(0)
+    synthetic.install(ev, p) if tables else ev.set_params(p)
+    props, flags = g["props_in"].copy(), g["flags_in"].copy()
+    s, i, c = ev.evolve_batch(props, flags, g["t_end"])
+    _check(g, props, flags, s, i, c)
+    ev.close()
