@@ -65,6 +65,13 @@ struct glc_evolver {
     int64_t drain_threshold = 60000;  // hand over when fewer slots than this are still in flight
     int32_t *d_held = nullptr;
     int64_t held_cap = 0;
+    // streaming session (glc_stream_*)
+    bool stream_active = false, stream_started = false;
+    int64_t stream_n = 0;           // tickets handed out so far = length of the node queue
+    unsigned char *d_collected = nullptr;
+    int64_t *d_collect_list = nullptr;
+    int64_t collected_cap = 0;
+    int64_t stream_collected = 0;
     int32_t *d_order = nullptr;     // queue order (component-sorted node ids)
     int *d_sort = nullptr;          // 2 x 64 bucket counters
     int64_t order_cap = 0;
@@ -96,6 +103,7 @@ static double now_s() {
 // host/staging layout is node-major [n][NPROP]; the arena is SoA [NPROP][cap].
 __global__ void aos_to_soa_kernel(const double *__restrict__ aos, double *__restrict__ soa, int n,
                                   int64_t cap) {
+    // (callers pass aos/soa already offset to the first node of the range)
     __shared__ double tile[64 * NPROP];
     const int node0 = blockIdx.x * 64;
     const int nn = min(64, n - node0);
@@ -323,13 +331,18 @@ static void free_slots(glc_evolver *ev) {
 }
 
 // One batch on the micro-task machine (standard model): same slice protocol as launch_evolve.
-static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc) {
+// mode 0: one batch, fresh queue, run to completion (hybrid) or in user time slices
+// mode 1: streaming -- ONE time slice of `streamBudget` pops over the (possibly grown) node queue
+// mode 2: streaming -- continue to completion (hybrid)
+static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mode = 0, int streamBudget = 0) {
     constexpr size_t kMachineSmem = sizeof(unsigned short) * (size_t)U_IDLE * GLC_MSLOTS;
     GLC_CHECK(ev, cudaFuncSetAttribute(machine_kernel<GLC_MTHREADS, GLC_MSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kMachineSmem));
     const int gridMax = ev->num_sms;  // one block per SM
     int grid = std::min(gridMax, (n + GLC_MSLOTS - 1) / GLC_MSLOTS);
     if (grid < 1) grid = 1;
+    if (mode != 0) grid = gridMax;  // the queue grows: every block takes part from the first slice on
+    const bool fresh = mode == 0 || !ev->stream_started;
     const int64_t need = (int64_t)gridMax * GLC_MSLOTS;
     if (need > ev->nslots_machine) {
         free_slots(ev);
@@ -344,7 +357,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc) {
     int rc = ensure_workspace(ev, (int)((need + kBlock - 1) / kBlock));
     if (rc) return rc;
     GLC_CHECK(ev, cudaEventRecord(ev->ev0, ev->stream));
-    const int sorted = build_queue_order(ev, n);
+    const int sorted = mode == 0 ? build_queue_order(ev, n) : 0;  // a growing queue is served in submission order
     if (sorted < 0) return sorted;
     KernelArgs A;
     A.props = ev->d_props;
@@ -360,8 +373,9 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc) {
     A.counters = ev->d_counters;
     A.order = sorted ? ev->d_order : nullptr;
     A.lanes = nullptr;
-    A.resume = 0;
+    A.resume = fresh ? 0 : 1;
     A.budget = ev->slice_budget > 0 ? ev->slice_budget : 0x7fffffff;
+    if (mode == 1) A.budget = streamBudget > 0 ? streamBudget : 4096;
     A.debug = nullptr;
 #ifdef GLC_DEBUG_HANG
     static int *h_dbg = nullptr;
@@ -374,8 +388,12 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc) {
         A.debug = d_dbg;
     }
 #endif
-    GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
-    GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 16, ev->stream));
+    if (fresh) {
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 16, ev->stream));
+    } else
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long) * 2, ev->stream));
+    if (mode != 0) ev->stream_started = true;
     const double t_start = now_s();
     int nslice = 0;
     A.hold = 0;
@@ -390,7 +408,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc) {
     // queue still refills its slots and for as long as enough slots stay in flight to fill warps; then the slots
     // are brought to an RK boundary (hold slices) and handed to drain_kernel, which finishes their nodes with
     // whole evaluations.  With a user slice budget the machine alone runs (resumable by construction).
-    const bool hybrid = ev->slice_budget <= 0 && ev->drain_handover;
+    const bool hybrid = mode != 1 && (ev->slice_budget <= 0 || mode == 2) && ev->drain_handover;
     if (hybrid) A.budget = 4096;
     const unsigned long long drainBelow = (unsigned long long)ev->drain_threshold;
     bool draining = false;
@@ -402,8 +420,9 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc) {
         GLC_CHECK(ev, cudaGetLastError());
         GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 9, cudaMemcpyDeviceToHost,
                                       ev->stream));
-        if (ev->slice_budget <= 0 && !hybrid) break;
+        if (mode != 1 && ev->slice_budget <= 0 && !hybrid) break;
         GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+        if (mode == 1) break;  // streaming: exactly one slice per call
         if (ev->slice_log)
             fprintf(stderr, "[glc slice %lld] t=%.3f ms done=%llu/%d rhs=%llu accepted=%llu parked=%llu mid-evaluation=%llu%s\n",
                     (long long)ev->slices, 1e3 * (now_s() - t_start), hc[6], n, hc[2], hc[0], hc[7], hc[8], draining ? " (hold)" : "");
@@ -545,6 +564,8 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaFree(ev->d_work);
     cudaFree(ev->d_counters);
     cudaFree(ev->d_held);
+    cudaFree(ev->d_collected);
+    cudaFree(ev->d_collect_list);
     cudaFree(ev->d_pow_ac);
     cudaFree(ev->d_pow_kmt);
     cudaFree(ev->d_lanes);
@@ -822,6 +843,176 @@ int glc_rhs_batch(glc_evolver *ev, int64_t n, double *props, const int32_t *flag
     GLC_CHECK(ev, cudaGetLastError());
     GLC_CHECK(ev, cudaMemcpyAsync(dydt, ev->d_dydt, sizeof(double) * NY * n, cudaMemcpyDeviceToHost, ev->stream));
     return glc_arena_download(ev, n, props, nullptr, nullptr, interrupt);
+}
+
+// ------------------------------------------------------------------ streaming interface
+// The production host (the batching tree evolver of INTEGRATION.md) never waits for a batch to drain: it submits
+// evolvable nodes as the tree walk produces them, lets the device run time slices, and collects finished nodes.
+// A ticket is the node's index in the arena; the arena capacity bounds the tickets of one session.
+int glc_stream_begin(glc_evolver *ev, int64_t capacity) {
+    if (!ev || capacity < 1 || capacity > 0x7fffffff) return -1;
+    if (!ev->params_set) return -9;
+    if (ev->params.model != GLC_MODEL_STANDARD || !ev->use_machine) {
+        ev->err = "streaming needs the micro-task machine (standard model)";
+        return -11;
+    }
+    cudaSetDevice(ev->device);
+    int rc = glc_arena_reserve(ev, capacity);
+    if (rc) return rc;
+    if (ev->collected_cap < ev->cap) {
+        cudaFree(ev->d_collected);
+        cudaFree(ev->d_collect_list);
+        ev->d_collected = nullptr;
+        ev->d_collect_list = nullptr;
+        GLC_CHECK(ev, cudaMalloc(&ev->d_collected, (size_t)ev->cap));
+        GLC_CHECK(ev, cudaMalloc(&ev->d_collect_list, sizeof(int64_t) * ((size_t)ev->cap + 1)));
+        ev->collected_cap = ev->cap;
+    }
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_collected, 0, (size_t)ev->cap, ev->stream));
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_status, 0xff, sizeof(int32_t) * (size_t)ev->cap, ev->stream));  // -1 = pending
+    rc = upload_constants(ev);
+    if (rc) return rc;
+    ev->stream_active = true;
+    ev->stream_started = false;
+    ev->stream_n = 0;
+    ev->stream_collected = 0;
+    return 0;
+}
+
+int glc_stream_submit(glc_evolver *ev, int64_t n, const double *props, const int32_t *flags, const double *time_end,
+                      int64_t *first_ticket) {
+    if (!ev || !ev->stream_active || n < 0 || !props || !flags || !time_end) return -1;
+    if (ev->stream_n + n > ev->cap) {
+        ev->err = "stream capacity exhausted";
+        return -12;
+    }
+    if (first_ticket) *first_ticket = ev->stream_n;
+    if (n == 0) return 0;
+    cudaSetDevice(ev->device);
+    const int64_t off = ev->stream_n;
+    GLC_CHECK(ev, cudaMemcpyAsync(ev->d_stage + off * NPROP, props, sizeof(double) * NPROP * n, cudaMemcpyHostToDevice, ev->stream));
+    GLC_CHECK(ev, cudaMemcpyAsync(ev->d_flags + off, flags, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ev->stream));
+    GLC_CHECK(ev, cudaMemcpyAsync(ev->d_time_end + off, time_end, sizeof(double) * n, cudaMemcpyHostToDevice, ev->stream));
+    aos_to_soa_kernel<<<(int)((n + 63) / 64), 256, 0, ev->stream>>>(ev->d_stage + off * NPROP, ev->d_props + off, (int)n, ev->cap);
+    ev->launches++;
+    GLC_CHECK(ev, cudaGetLastError());
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));  // the host buffers may be reused on return
+    ev->stream_n += n;
+    return 0;
+}
+
+int glc_stream_run(glc_evolver *ev, int32_t pops_per_warp, int64_t *n_finished_total, glc_counters *counters) {
+    if (!ev || !ev->stream_active) return -1;
+    cudaSetDevice(ev->device);
+    unsigned long long hc[16] = {0};
+    if (ev->stream_n > 0) {
+        int rc = launch_machine(ev, (int)ev->stream_n, hc, 1, pops_per_warp);
+        if (rc) return rc;
+    }
+    if (n_finished_total) *n_finished_total = (int64_t)hc[6];
+    if (counters) {
+        counters->steps_accepted = hc[0];
+        counters->steps_rejected = hc[1];
+        counters->rhs_evaluations = hc[2];
+        counters->segments = hc[3];
+        counters->trials_failed = hc[4];
+        counters->nodes = hc[5];
+    }
+    return 0;
+}
+
+int glc_stream_finish(glc_evolver *ev, glc_counters *counters) {
+    if (!ev || !ev->stream_active) return -1;
+    cudaSetDevice(ev->device);
+    unsigned long long hc[16] = {0};
+    if (ev->stream_n > 0) {
+        int rc = launch_machine(ev, (int)ev->stream_n, hc, 2, 0);
+        if (rc) return rc;
+    }
+    if (counters) {
+        counters->steps_accepted = hc[0];
+        counters->steps_rejected = hc[1];
+        counters->rhs_evaluations = hc[2];
+        counters->segments = hc[3];
+        counters->trials_failed = hc[4];
+        counters->nodes = hc[5];
+    }
+    return 0;
+}
+
+__global__ void collect_list_kernel(const int32_t *__restrict__ status, unsigned char *collected, int64_t n, int64_t maxNodes,
+                                    int64_t *list) {
+    // list[0] = count, list[1..] = tickets
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (status[i] >= 0 && !collected[i]) {
+            const unsigned long long k = atomicAdd(reinterpret_cast<unsigned long long *>(list), 1ull);
+            if ((int64_t)k < maxNodes) {
+                list[1 + k] = i;
+                collected[i] = 1;
+            }
+        }
+}
+__global__ void collect_gather_kernel(const double *__restrict__ soa, int64_t cap, const int64_t *__restrict__ list, int64_t m,
+                                      double *__restrict__ rows, const int32_t *__restrict__ flags,
+                                      const int32_t *__restrict__ status, const int32_t *__restrict__ interrupt,
+                                      int32_t *__restrict__ meta) {
+    // one warp per collected node: rows[k][NPROP] and meta[k][3] = {flags, status, interrupt}
+    const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= m) return;
+    const int64_t node = list[1 + k];
+    for (int p = lane; p < NPROP; p += 32) rows[k * NPROP + p] = soa[(int64_t)p * cap + node];
+    if (lane == 0) {
+        meta[3 * k + 0] = flags[node];
+        meta[3 * k + 1] = status[node];
+        meta[3 * k + 2] = interrupt[node];
+    }
+}
+
+int glc_stream_collect(glc_evolver *ev, int64_t max_nodes, int64_t *tickets, double *props, int32_t *flags, int32_t *status,
+                       int32_t *interrupt, int64_t *n_out) {
+    if (!ev || !ev->stream_active || max_nodes < 0 || !tickets || !props || !flags || !status || !interrupt || !n_out) return -1;
+    *n_out = 0;
+    if (max_nodes == 0 || ev->stream_n == 0) return 0;
+    cudaSetDevice(ev->device);
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_collect_list, 0, sizeof(int64_t), ev->stream));
+    const int grid = (int)std::min<int64_t>((ev->stream_n + 255) / 256, (int64_t)ev->num_sms * 16);
+    collect_list_kernel<<<grid, 256, 0, ev->stream>>>(ev->d_status, ev->d_collected, ev->stream_n, max_nodes, ev->d_collect_list);
+    int64_t count = 0;
+    GLC_CHECK(ev, cudaMemcpyAsync(&count, ev->d_collect_list, sizeof(int64_t), cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    const int64_t m = std::min(count, max_nodes);
+    ev->launches++;
+    if (m == 0) return 0;
+    // rows are staged in d_stage (node-major, sized for the whole arena); meta behind the ticket list
+    int32_t *d_meta = nullptr;
+    GLC_CHECK(ev, cudaMalloc(&d_meta, sizeof(int32_t) * 3 * (size_t)m));
+    collect_gather_kernel<<<(int)((m * 32 + 255) / 256), 256, 0, ev->stream>>>(ev->d_props, ev->cap, ev->d_collect_list, m, ev->d_stage,
+                                                                              ev->d_flags, ev->d_status, ev->d_interrupt, d_meta);
+    ev->launches++;
+    GLC_CHECK(ev, cudaGetLastError());
+    std::vector<int32_t> meta(3 * (size_t)m);
+    GLC_CHECK(ev, cudaMemcpyAsync(props, ev->d_stage, sizeof(double) * NPROP * m, cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaMemcpyAsync(tickets, ev->d_collect_list + 1, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaMemcpyAsync(meta.data(), d_meta, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    cudaFree(d_meta);
+    for (int64_t k = 0; k < m; k++) {
+        flags[k] = meta[3 * k + 0];
+        status[k] = meta[3 * k + 1];
+        interrupt[k] = meta[3 * k + 2];
+    }
+    ev->stream_collected += m;
+    *n_out = m;
+    return 0;
+}
+
+int glc_stream_end(glc_evolver *ev) {
+    if (!ev) return -1;
+    ev->stream_active = false;
+    ev->stream_started = false;
+    ev->stream_n = 0;
+    return 0;
 }
 
 int glc_histogram_accumulate(glc_evolver *ev, int64_t n, int32_t prop, double log10_min,

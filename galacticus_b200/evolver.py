@@ -68,6 +68,14 @@ def load_library() -> C.CDLL:
     L.glc_evolver_set_option.argtypes = [vp, C.c_int32, C.c_int64]
     L.glc_slice_count.restype = C.c_int64
     L.glc_slice_count.argtypes = [vp]
+    i64p = C.POINTER(C.c_int64)
+    L.glc_stream_begin.argtypes = [vp, C.c_int64]
+    L.glc_stream_submit.argtypes = [vp, C.c_int64, _dp, _ip, _dp, i64p]
+    L.glc_stream_run.argtypes = [vp, C.c_int32, i64p, C.POINTER(abi.glc_counters)]
+    L.glc_stream_collect.argtypes = [vp, C.c_int64, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), _dp, _ip, _ip,
+                                     _ip, i64p]
+    L.glc_stream_finish.argtypes = [vp, C.POINTER(abi.glc_counters)]
+    L.glc_stream_end.argtypes = [vp]
     L.glc_histogram_accumulate.argtypes = [vp, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int32, vp]
     if L.glc_abi_version() != abi.GLC_ABI_VERSION:
         raise GlcError("libglcb200.so ABI version does not match include/glc_b200.h")
@@ -182,6 +190,45 @@ class Evolver:
 
     def device_props_ptr(self) -> int:
         return int(self.L.glc_arena_device_props(self.h) or 0)
+
+    # ---- streaming session (glc_stream_*): submit / run time slices / collect finished nodes
+    def stream_begin(self, capacity: int) -> None:
+        self._check(self.L.glc_stream_begin(self.h, capacity), "glc_stream_begin")
+
+    def stream_submit(self, props, flags, time_end) -> int:
+        n = props.shape[0]
+        assert props.shape == (n, abi.NPROP) and props.dtype == np.float64 and props.flags.c_contiguous
+        first = C.c_int64(-1)
+        te = np.ascontiguousarray(time_end, dtype=np.float64)
+        self._check(self.L.glc_stream_submit(self.h, n, props, np.ascontiguousarray(flags, dtype=np.int32), te, C.byref(first)),
+                    "glc_stream_submit")
+        return int(first.value)
+
+    def stream_run(self, pops_per_warp: int = 0):
+        done = C.c_int64(0)
+        c = abi.glc_counters()
+        self._check(self.L.glc_stream_run(self.h, pops_per_warp, C.byref(done), C.byref(c)), "glc_stream_run")
+        return int(done.value), abi.counters_dict(c)
+
+    def stream_collect(self, max_nodes: int):
+        tickets = np.zeros(max_nodes, dtype=np.int64)
+        props = np.zeros((max_nodes, abi.NPROP), dtype=np.float64)
+        flags = np.zeros(max_nodes, dtype=np.int32)
+        status = np.zeros(max_nodes, dtype=np.int32)
+        interrupt = np.zeros(max_nodes, dtype=np.int32)
+        m = C.c_int64(0)
+        self._check(self.L.glc_stream_collect(self.h, max_nodes, tickets, props, flags, status, interrupt, C.byref(m)),
+                    "glc_stream_collect")
+        k = int(m.value)
+        return tickets[:k], props[:k], flags[:k], status[:k], interrupt[:k]
+
+    def stream_finish(self):
+        c = abi.glc_counters()
+        self._check(self.L.glc_stream_finish(self.h, C.byref(c)), "glc_stream_finish")
+        return abi.counters_dict(c)
+
+    def stream_end(self) -> None:
+        self._check(self.L.glc_stream_end(self.h), "glc_stream_end")
 
     def rhs_batch(self, props, flags):
         n = props.shape[0]

@@ -322,6 +322,27 @@ int64_t glc_kernel_launch_count(const glc_evolver *ev);
 double glc_measure_fp64_peak_tflops(glc_evolver *ev);
 void *glc_evolver_stream(glc_evolver *ev);
 
+/*
+ * Streaming interface: what the batching tree evolver uses in production so that the device never
+ * drains between batches.  replaces: the per-node call sequence of evolver/standard.F90:398-577 over a SET of forests.
+ *   glc_stream_begin    reserve an arena for `capacity` tickets and reset the node queue
+ *   glc_stream_submit   append n node records to the queue (host, node-major as in glc_evolve_batch); *first_ticket = ticket
+ *                       of the first one, the others follow consecutively
+ *   glc_stream_run      ONE time slice (pops_per_warp unit executions per warp, 0 = default 4096); returns the number of
+ *                       nodes finished so far and the accumulated counters
+ *   glc_stream_collect  up to max_nodes finished, not yet collected nodes: tickets, records, flags, status, interrupt
+ *   glc_stream_finish   run until every submitted node is finished (machine slices + drain hand-over)
+ *   glc_stream_end      close the session
+ */
+int glc_stream_begin(glc_evolver *ev, int64_t capacity);
+int glc_stream_submit(glc_evolver *ev, int64_t n, const double *props, const int32_t *flags, const double *time_end,
+                      int64_t *first_ticket);
+int glc_stream_run(glc_evolver *ev, int32_t pops_per_warp, int64_t *n_finished_total, glc_counters *counters);
+int glc_stream_collect(glc_evolver *ev, int64_t max_nodes, int64_t *tickets, double *props, int32_t *flags,
+                       int32_t *status, int32_t *interrupt, int64_t *n_out);
+int glc_stream_finish(glc_evolver *ev, glc_counters *counters);
+int glc_stream_end(glc_evolver *ev);
+
 /* one evaluation of the RHS (standardODEs) for each node, for unit-level parity tests:
  *   dydt [n][GLC_NY] host out; props/flags are not modified except radii warm starts. */
 int glc_rhs_batch(glc_evolver *ev, int64_t n, double *props, const int32_t *flags,
