@@ -139,3 +139,50 @@ def test_baryon_budget_full_size():
     assert (d < 1e-3).mean() > 0.9  # only nodes that hit the negative-mass clamps deviate
     for k in ("HH_MASS", "DISK_MASS_GAS", "DISK_MASS_STELLAR", "SPH_MASS_GAS", "SPH_MASS_STELLAR"):
         assert (props[:, P[k]] >= 0).all(), k
+
+
+def test_execution_options_do_not_change_results(oracle_lib):
+    """The three execution paths -- hybrid run-to-completion (machine slices + hold + drain kernel), the machine in
+    user time slices, and the warp-synchronous lane kernel -- and the queue order are scheduling choices only."""
+    from galacticus_b200.evolver import Evolver
+
+    p = cases.standard_params()
+    props, flags, t_end = synthetic.standard_nodes(p, 6000, seed=31337)
+    ref = None
+    for budget, sort, machine in [(0, 1, 1), (777, 1, 1), (0, 0, 1), (0, 1, 0), (333, 0, 0)]:
+        ev = Evolver(0)
+        synthetic.install(ev, p)
+        ev.set_option(abi.GLC_OPT_SLICE_BUDGET, budget)
+        ev.set_option(abi.GLC_OPT_SORT_QUEUE, sort)
+        ev.set_option(abi.GLC_OPT_MICROTASK_MACHINE, machine)
+        pg, fg = props.copy(), flags.copy()
+        s, i, c = ev.evolve_batch(pg, fg, t_end)
+        if budget:
+            assert ev.slice_count() > 1
+        out = (pg, fg, s, i, c)
+        if ref is None:
+            ref = out
+        else:
+            assert np.array_equal(out[0], ref[0]) and np.array_equal(out[1], ref[1])
+            assert np.array_equal(out[2], ref[2]) and np.array_equal(out[3], ref[3]) and out[4] == ref[4]
+        ev.close()
+
+
+def test_ragged_and_degenerate_nodes(oracle_lib):
+    """Edge cases of the reference's own tests: zero-length evolutions (timeStart == timeEnd), nodes without any
+    component, freshly created components, an empty batch."""
+    ev, o, p = make(oracle_lib)
+    props, flags, t_end = synthetic.standard_nodes(p, 1200, seed=4)
+    t_end[::5] = props[::5, P["TIME"]]  # zero-length intervals
+    flags[::7] = 0  # no components at all (the state is ignored, components are created by interrupts)
+    props[1::9, P["DISK_RADIUS"]] = 0.0  # cold structure solves
+    props[1::9, P["DISK_VELOCITY"]] = 0.0
+    pg, fg = props.copy(), flags.copy()
+    po, fo = props.copy(), flags.copy()
+    sg, ig, cg = ev.evolve_batch(pg, fg, t_end)
+    so, io, co = o.evolve_batch(po, fo, t_end, n_threads=8)
+    compare(pg, po, fg, fo, sg, so, ig, io, "ragged")
+    assert cg == co
+    z = np.zeros((0, abi.NPROP))
+    s0, i0, c0 = ev.evolve_batch(z, np.zeros(0, dtype=np.int32), np.zeros(0))
+    assert s0.size == 0 and c0["nodes"] == 0
