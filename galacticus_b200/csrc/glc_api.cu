@@ -63,6 +63,7 @@ struct glc_evolver {
     int32_t use_machine = 1;        // standard model: 1 = micro-task machine, 0 = warp-synchronous evolve_kernel
     int32_t drain_handover = 1;     // run-to-completion mode: finish the last nodes with drain_kernel
     int64_t drain_threshold = 60000;  // hand over when fewer slots than this are still in flight
+    int32_t drain_dense_budget = 384; // evaluations per lane in a dense drain pass
     int32_t *d_held = nullptr;
     int64_t held_cap = 0;
     // streaming session (glc_stream_*)
@@ -470,7 +471,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                     A.nheld = nheld;
                     A.held_counter = d_count + 1;
                     A.drainSparse = sparse ? 1 : 0;
-                    A.budget = sparse ? 0x7fffffff : 384;
+                    A.budget = sparse ? 0x7fffffff : ev->drain_dense_budget;
                     int dgrid = sparse ? (nheld + kBlock / 32 - 1) / (kBlock / 32) : (nheld + kBlock - 1) / kBlock;
                     dgrid = std::max(1, std::min(ev->num_sms * bps, dgrid));
                     drain_kernel<ModelStandard><<<dgrid, kBlock, 0, ev->stream>>>(A);
@@ -529,6 +530,7 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_MACHINE")) ev->use_machine = atoi(e);
     if (const char *e = getenv("GLC_DRAIN")) ev->drain_handover = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_BELOW")) ev->drain_threshold = atoll(e);
+    if (const char *e = getenv("GLC_DRAIN_DENSE_BUDGET")) ev->drain_dense_budget = atoi(e);
     cudaStreamCreateWithFlags(&ev->stream, cudaStreamNonBlocking);
     cudaEventCreate(&ev->ev0);
     cudaEventCreate(&ev->ev1);
@@ -610,6 +612,8 @@ int glc_evolver_set_params(glc_evolver *ev, const glc_params *params) {
         ev->tables.powAcN = (int)ac.size();
         ev->tables.powKmt = ev->d_pow_kmt;
         ev->tables.powKmtN = (int)kmt.size();
+        pow_table_spacing(1.0e-3, 1.0, (int)ac.size(), ev->tables.powAcDx, ev->tables.powAcInvDx);
+        pow_table_spacing(1.0, 1000.0, (int)kmt.size(), ev->tables.powKmtDx, ev->tables.powKmtInvDx);
         ev->pow_ac_exponent = params->adiabaticOmega;
     }
     ev->params = *params;

@@ -130,6 +130,7 @@ struct DeviceTables {
     // x^adiabaticOmega on [1e-3,1] (adiabatic_Gnedin2004.F90:664-687) and x^0.33 on [1,1000] (Krumholz2009.F90)
     const double *powAc, *powKmt;
     int powAcN, powKmtN;
+    double powAcDx, powAcInvDx, powKmtDx, powKmtInvDx;  // lattice spacing and its reciprocal, computed once on the host
 };
 
 struct LaneState;

@@ -322,7 +322,8 @@ struct ModelStandard {
     GLC_DEVICE_INLINE double ac_orbital_mean(const Work &w, double radius) {
         // sphericalAdiabaticGnedin2004RadiusOrbitalMean, adiabatic_Gnedin2004.F90:664-687
         return GLC_PARAMS.adiabaticA * w.rvir *
-               fast_exponentiate(GLC_TABLES.powAc, GLC_TABLES.powAcN, 1.0e-3, 1.0, GLC_PARAMS.adiabaticOmega, radius / w.rvir);
+               fast_exponentiate(GLC_TABLES.powAc, GLC_TABLES.powAcN, GLC_TABLES.powAcDx, GLC_TABLES.powAcInvDx, 1.0e-3, 1.0,
+                                 GLC_PARAMS.adiabaticOmega, radius / w.rvir);
     }
     GLC_DEVICE_INLINE double baryonic_mass_self(const NodeCtx &c, const double (&y)[NY]) {
         double m = 0.0;
@@ -572,7 +573,8 @@ struct ModelStandard {
         if (sgd <= 0.0)
             factor = 0.0;
         else
-            factor = fast_exponentiate(GLC_TABLES.powKmt, GLC_TABLES.powKmtN, 1.0, 1000.0, 0.33, (sgd < 1.0) ? 1.0 / sgd : sgd);
+            factor = fast_exponentiate(GLC_TABLES.powKmt, GLC_TABLES.powKmtN, GLC_TABLES.powKmtDx, GLC_TABLES.powKmtInvDx, 1.0,
+                                       1000.0, 0.33, (sgd < 1.0) ? 1.0 / sgd : sgd);
         return GLC_PARAMS.frequencyStarFormation * sg * factor * fh2;
     }
     // starFormationRateDisksIntgrtdSurfaceDensity::rate (rates/disks/integrated_surface_density.F90:131-190)

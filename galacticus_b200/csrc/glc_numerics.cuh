@@ -540,11 +540,11 @@ GLC_DEVICE_INLINE double linear_table_eval(G &&g, double xmin, double xmax, int 
 // fastExponentiator (math/exponentiation.F90:57-104): linear interpolation in a table of x^exponent with `density`
 // points per unit x on [rangeMin, rangeMax], exact pow outside.  `table` holds the n lattice values (built once on the
 // host by build_pow_table with the same dm_pow).
-GLC_DEVICE_INLINE double fast_exponentiate(const double *__restrict__ table, int n, double rangeMin, double rangeMax,
-                                           double exponent, double x) {
+GLC_DEVICE_INLINE double fast_exponentiate(const double *__restrict__ table, int n, double dx, double inverseDx,
+                                           double rangeMin, double rangeMax, double exponent, double x) {
+    // dx = (rangeMax - rangeMin) / (n - 1) and inverseDx = 1 / ((rangeMin + dx) - rangeMin) are table constants
+    // (pow_table_spacing, glc_tables_host.h): the same two IEEE divisions, done once instead of per call
     if (x < rangeMin || x > rangeMax) return dm_pow(x, exponent);
-    const double dx = (rangeMax - rangeMin) / (double)(n - 1);
-    const double inverseDx = 1.0 / ((rangeMin + dx) - rangeMin);
     int i;
     if (x >= rangeMax)
         i = n - 1;

@@ -62,6 +62,11 @@ inline std::vector<double> build_pow_table(double rangeMin, double rangeMax, dou
     return t;
 }
 
+inline void pow_table_spacing(double rangeMin, double rangeMax, int n, double &dx, double &inverseDx) {
+    dx = (rangeMax - rangeMin) / (double)(n - 1);
+    inverseDx = 1.0 / ((rangeMin + dx) - rangeMin);
+}
+
 inline void install_table(DeviceTables &T, int id, const PreparedTable &t, const DeviceTable2D &d) {
     if (id == GLC_TABLE_COOLING_FUNCTION) {
         T.cooling = d;

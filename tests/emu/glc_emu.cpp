@@ -310,6 +310,8 @@ void emu_set_params(void *h, const glc_params *p) {
         e->dt.powAcN = (int)e->powAc.size();
         e->dt.powKmt = e->powKmt.data();
         e->dt.powKmtN = (int)e->powKmt.size();
+        pow_table_spacing(1.0e-3, 1.0, e->dt.powAcN, e->dt.powAcDx, e->dt.powAcInvDx);
+        pow_table_spacing(1.0, 1000.0, e->dt.powKmtN, e->dt.powKmtDx, e->dt.powKmtInvDx);
     }
 }
 int emu_set_table(void *h, int id, int n0, int n1, const double *x0, const double *x1, const double *v) {
