@@ -65,7 +65,10 @@ struct glc_evolver {
     int64_t drain_threshold = 60000;  // hand over when fewer slots than this are still in flight
     int32_t drain_dense_budget = 384; // evaluations per lane in a dense drain pass
     int32_t *d_held = nullptr;
+    float *d_held_score = nullptr;
     int64_t held_cap = 0;
+    int32_t drain_express = 1;      // first drain pass: predicted-longest nodes one per warp on stream2
+    cudaStream_t stream2 = nullptr;
     // streaming session (glc_stream_*)
     bool stream_active = false, stream_started = false;
     int64_t stream_n = 0;           // tickets handed out so far = length of the node queue
@@ -446,7 +449,10 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                 if (!ev->d_held || ev->held_cap < ev->nslots_machine) {
                     cudaFree(ev->d_held);
                     ev->d_held = nullptr;
-                    GLC_CHECK(ev, cudaMalloc(&ev->d_held, sizeof(int32_t) * (ev->nslots_machine + 2)));
+                    GLC_CHECK(ev, cudaMalloc(&ev->d_held, sizeof(int32_t) * (ev->nslots_machine + 8)));
+                    cudaFree(ev->d_held_score);
+                    ev->d_held_score = nullptr;
+                    GLC_CHECK(ev, cudaMalloc(&ev->d_held_score, sizeof(float) * ev->nslots_machine));
                     ev->held_cap = ev->nslots_machine;
                 }
                 int *d_count = reinterpret_cast<int *>(ev->d_held + ev->nslots_machine);  // [0] list length, [1] cursor
@@ -459,13 +465,71 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                 A.slotYt = ev->d_slots.yt;
                 A.slotUnit = ev->d_slots.unit;
                 for (int pass = 0;; pass++) {
-                    GLC_CHECK(ev, cudaMemsetAsync(d_count, 0, sizeof(int) * 2, ev->stream));
+                    GLC_CHECK(ev, cudaMemsetAsync(d_count, 0, sizeof(int) * 4, ev->stream));
                     held_list_kernel<<<std::min((nslotsActive + 255) / 256, ev->num_sms * 8), 256, 0, ev->stream>>>(
-                        ev->d_slots.unit, nslotsActive, ev->d_held, d_count);
+                        ev->d_slots.unit, ev->d_slots.L, nslotsActive, ev->d_held, pass == 0 ? ev->d_held_score : nullptr, d_count);
                     int nheld = 0;
                     GLC_CHECK(ev, cudaMemcpyAsync(&nheld, d_count, sizeof(int), cudaMemcpyDeviceToHost, ev->stream));
                     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
                     if (nheld == 0) break;
+                    const int express = ev->num_sms * (kBlock / 32);  // one block per SM, one node per warp
+                    if (pass == 0 && ev->drain_express && nheld > 2 * express) {
+                        // ---- first pass: the nodes predicted to need the most steps are the critical path of the
+                        // whole batch.  They get a warp each (one block per SM, stream2) right away, while the other
+                        // block per SM works through the rest one node per lane.
+                        std::vector<int32_t> h_held(nheld);
+                        std::vector<float> h_score(nheld);
+                        GLC_CHECK(ev, cudaMemcpyAsync(h_held.data(), ev->d_held, sizeof(int32_t) * nheld, cudaMemcpyDeviceToHost, ev->stream));
+                        GLC_CHECK(ev, cudaMemcpyAsync(h_score.data(), ev->d_held_score, sizeof(float) * nheld, cudaMemcpyDeviceToHost, ev->stream));
+                        GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+                        std::vector<int> idx(nheld);
+                        for (int k = 0; k < nheld; k++) idx[k] = k;
+                        std::nth_element(idx.begin(), idx.begin() + express, idx.end(),
+                                         [&](int a, int b) { return h_score[a] > h_score[b]; });
+                        std::vector<int32_t> ordered(nheld);
+                        for (int k = 0; k < nheld; k++) ordered[k] = h_held[idx[k]];
+                        GLC_CHECK(ev, cudaMemcpyAsync(ev->d_held, ordered.data(), sizeof(int32_t) * nheld, cudaMemcpyHostToDevice, ev->stream));
+                        GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+                        KernelArgs X = A;  // express: the first `express` entries, one per warp, to completion
+                        X.held = ev->d_held;
+                        X.nheld = express;
+                        X.held_counter = d_count + 1;
+                        X.drainSparse = 1;
+                        X.budget = 0x7fffffff;
+                        drain_kernel<ModelStandard><<<ev->num_sms, kBlock, 0, ev->stream2>>>(X);
+                        KernelArgs D = A;  // dense: the rest, bounded passes until fewer nodes than warps are left
+                        D.held = ev->d_held + express;
+                        D.nheld = nheld - express;
+                        D.held_counter = d_count + 2;
+                        D.drainSparse = 0;
+                        D.budget = ev->drain_dense_budget;
+                        drain_kernel<ModelStandard><<<ev->num_sms, kBlock, 0, ev->stream>>>(D);
+                        ev->launches += 3;
+                        GLC_CHECK(ev, cudaGetLastError());
+                        GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+                        if (ev->slice_log)
+                            fprintf(stderr, "[glc drain pass 0 dense+express] dense part done t=%.3f ms held=%d express=%d\n",
+                                    1e3 * (now_s() - t_start), nheld, express);
+                        // further dense passes over what the dense part left, while the express kernel is still running
+                        for (int sub = 0; sub < 8; sub++) {
+                            GLC_CHECK(ev, cudaMemsetAsync(d_count + 2, 0, sizeof(int), ev->stream));
+                            GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+                            if (cudaStreamQuery(ev->stream2) != cudaErrorNotReady) break;
+                            // nodes parked by the dense part keep unit == U_RHS_BEGIN, finished ones are -1: re-run the
+                            // same list (finished entries are skipped by the kernel through their unit word)
+                            D.budget = ev->drain_dense_budget;
+                            drain_kernel<ModelStandard><<<ev->num_sms, kBlock, 0, ev->stream>>>(D);
+                            ev->launches++;
+                            GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+                        }
+                        GLC_CHECK(ev, cudaStreamSynchronize(ev->stream2));
+                        GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 9, cudaMemcpyDeviceToHost, ev->stream));
+                        GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+                        if (ev->slice_log)
+                            fprintf(stderr, "[glc drain pass 0 dense+express] t=%.3f ms done=%llu/%d rhs=%llu\n",
+                                    1e3 * (now_s() - t_start), hc[6], n, hc[2]);
+                        continue;
+                    }
                     const bool sparse = nheld <= warpsResident;
                     A.held = ev->d_held;
                     A.nheld = nheld;
@@ -531,7 +595,9 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_DRAIN")) ev->drain_handover = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_BELOW")) ev->drain_threshold = atoll(e);
     if (const char *e = getenv("GLC_DRAIN_DENSE_BUDGET")) ev->drain_dense_budget = atoi(e);
+    if (const char *e = getenv("GLC_DRAIN_EXPRESS")) ev->drain_express = atoi(e);
     cudaStreamCreateWithFlags(&ev->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ev->stream2, cudaStreamNonBlocking);
     cudaEventCreate(&ev->ev0);
     cudaEventCreate(&ev->ev1);
     cudaMalloc(&ev->d_work, sizeof(int));
@@ -577,6 +643,8 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaEventDestroy(ev->ev0);
     cudaEventDestroy(ev->ev1);
     cudaStreamDestroy(ev->stream);
+    cudaStreamDestroy(ev->stream2);
+    cudaFree(ev->d_held_score);
     delete ev;
     return 0;
 }

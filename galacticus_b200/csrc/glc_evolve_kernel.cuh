@@ -552,17 +552,23 @@ GLC_DEVICE_INLINE bool drain_iterate(LaneState &L, LaneMem &M, const KernelArgs 
                                      int &slotHeld, unsigned int (&tot)[7], bool mayTake) {
     double rate[NY];
     if (slotHeld == -1 && mayTake) {
-        const int h = glc_atomic_add(A.held_counter, 1);
-        if (h < A.nheld) {
-            slotHeld = A.held[h];
+        for (;;) {
+            const int h = glc_atomic_add(A.held_counter, 1);
+            if (h >= A.nheld) {
+                slotHeld = -2;  // list exhausted
+                break;
+            }
+            const int s = A.held[h];
+            if (A.slotUnit && A.slotUnit[s] < 0) continue;  // finished in an earlier pass over the same list
+            slotHeld = s;
             L = A.slotL[slotHeld];
             GLC_UNROLL_RK
             for (int i = 0; i < NY; i++) yt[i] = A.slotYt[(int64_t)slotHeld * NY + i];
             M.ws = A.ws + (int64_t)slotHeld * (WS_NVEC * NY);
             M.wstride = 1;
             fresh = true;
-        } else
-            slotHeld = -2;  // list exhausted
+            break;
+        }
     }
     const bool have = slotHeld >= 0;
     if (have && !fresh) lane_prepare<Model>(L, M, yt);

@@ -707,10 +707,19 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
     }
 }
 
-// compacts the ids of the slots held at an RK boundary into a list for drain_kernel
-__global__ void held_list_kernel(const int *__restrict__ unit, int nslots, int32_t *held, int *count) {
+// compacts the ids of the slots held at an RK boundary into a list for drain_kernel; score = predicted number of
+// remaining steps of the node, (t_end - t) / h with the controller's current step size
+__global__ void held_list_kernel(const int *__restrict__ unit, const LaneState *__restrict__ L, int nslots, int32_t *held,
+                                 float *score, int *count) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += gridDim.x * blockDim.x)
-        if (unit[i] == U_RHS_BEGIN) held[atomicAdd(count, 1)] = i;
+        if (unit[i] == U_RHS_BEGIN) {
+            const int k = atomicAdd(count, 1);
+            held[k] = i;
+            if (score) {
+                const double h = L[i].h, left = L[i].x1 - L[i].x;
+                score[k] = (L[i].heavy == HV_RHS && h > 0.0 && left > 0.0) ? (float)fmin(left / h, 1.0e30) : 0.0f;
+            }
+        }
 }
 #endif
 
