@@ -3,7 +3,7 @@ import csv, subprocess, sys, collections, re, os, glob, tempfile
 rep, kname = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 45
 tmp = tempfile.mkdtemp()
-subprocess.run("cd %s && cuobjdump -xelf all %s >/dev/null 2>&1" % (tmp, os.path.abspath("galacticus_b200/libglcb200.so")), shell=True)
+subprocess.run("cd %s && cuobjdump -xelf all %s >/dev/null 2>&1" % (tmp, os.path.abspath(os.environ.get("GLC_PROFILE_LIB", "galacticus_b200/libglcb200.so"))), shell=True)
 cub = [c for c in glob.glob(tmp + "/*.cubin") if "params" not in c][0]
 dis = subprocess.run(["nvdisasm", "--print-line-info", cub], capture_output=True, text=True).stdout.split("\n")
 start = None

@@ -2,7 +2,7 @@
 import csv, subprocess, sys, collections, re, os, glob, tempfile
 rep = sys.argv[1]
 tmp = tempfile.mkdtemp()
-subprocess.run("cd %s && cuobjdump -xelf all %s >/dev/null 2>&1" % (tmp, os.path.abspath("galacticus_b200/libglcb200.so")), shell=True)
+subprocess.run("cd %s && cuobjdump -xelf all %s >/dev/null 2>&1" % (tmp, os.path.abspath(os.environ.get("GLC_PROFILE_LIB", "galacticus_b200/libglcb200.so"))), shell=True)
 cub = [c for c in glob.glob(tmp + "/*.cubin") if "params" not in c][0]
 sym = subprocess.run(["readelf", "-sW", cub], capture_output=True, text=True).stdout
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
