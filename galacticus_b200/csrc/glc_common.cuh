@@ -126,6 +126,10 @@ struct DeviceTables {
     // exponential-disk rotation-curve factor, uniform in ln(half-radius)
     DeviceTable2D diskrc;
     double diskrc_lnx0, diskrc_inv_dlnx;
+    // ADAF tabulations (accretion_disks/ADAF.F90:394-447), uniform in ln(1-j): x0 = ln(1-j), v[n0][2] = {jet power per
+    // unit accretion rate, spin-up ratio}
+    DeviceTable2D adaf;
+    double adaf_inv_dlnx;
     // fastExponentiator tables (math/exponentiation.F90:57-104), tabulated once like the reference does:
     // x^adiabaticOmega on [1e-3,1] (adiabatic_Gnedin2004.F90:664-687) and x^0.33 on [1,1000] (Krumholz2009.F90)
     const double *powAc, *powKmt;

@@ -101,7 +101,7 @@ GLC_DEVICE_INLINE void slot_reset(const SlotRef &S) {
 GLC_DEVICE_INLINE void m_cool_decide(const SlotRef &S) {
     RhsState &R = S.R;
     R.coolOn = MS::cooling_on(S.L.ctx, S.yt, R.w, R.go != 0) ? 1 : 0;
-    R.radiusOn = MS::cooling_radius_on(R.w, R.coolOn != 0) ? 1 : 0;
+    R.radiusOn = MS::cooling_radius_on(S.L.ctx, S.yt, R.w, R.coolOn != 0, R.go != 0) ? 1 : 0;
     R.rinfall = 0.0;
     R.logSlopeT = 0.0;
     S.unit = R.radiusOn ? U_COOL_BEGIN : U_RK;

@@ -13,7 +13,7 @@
 // (glc_numerics.cuh).
 //
 // Documented deviations from quickTest.xml ("out of scope / next"):
-// hotHaloRamPressureStripping=virialRadius; black-hole operators gated off by operatorMask; direct
+// hotHaloRamPressureStripping=virialRadius; ADAF tabulations supplied by the host (GLC_TABLE_ADAF); direct
 // solve for the first-guess radius; per-solve reset of the oscillation history; beta = 2/3.
 #pragma once
 
@@ -682,6 +682,244 @@ struct ModelStandard {
         return (tau > 0.0) ? y[GLC_P_SPH_MASS_GAS] / tau : 0.0;
     }
 
+    // ---------------------------------------------------------------- black holes
+    // Everything here is straight-line arithmetic once the cooling radius is known (standardHotModeFraction).
+    struct Bh {
+        bool on;            // a black hole of positive mass exists and a black-hole consumer is enabled
+        double mass, spin;
+        double eIsco, lIsco;  // ISCO specific energy / angular momentum (gravitational units, prograde)
+        double eddington;
+        double accSph, accHot, acc;  // blackHoleAccretionRateStandard::rateAccretion
+    };
+    GLC_DEVICE_INLINE double ideal_gas_sound_speed(double temperature) {
+        // Ideal_Gas_Sound_Speed, thermodynamics/ideal_gases.F90:46-69 (primordial mean atomic mass)
+        return sqrt(5.0 * kBoltzmann * temperature / 3.0 / kMeanAtomicMassPrimordial / kAtomicMassUnit) / kKilo;
+    }
+    GLC_DEVICE_INLINE double bhl_radius(double mass, double temperature) {
+        // Bondi_Hoyle_Lyttleton_Accretion_Radius, accretion/Bondi_Hoyle_Lyttleton.F90:61-78
+        if (!(temperature > 0.0)) return DBL_MAX;
+        const double cs = ideal_gas_sound_speed(temperature);
+        return kGInternal * mass / (cs * cs);
+    }
+    GLC_DEVICE_INLINE double bhl_rate(double mass, double density, double velocity, double temperature, bool withRadius,
+                                      double radius) {
+        // Bondi_Hoyle_Lyttleton_Accretion_Rate, accretion/Bondi_Hoyle_Lyttleton.F90:34-59
+        const double cs = ideal_gas_sound_speed(temperature);
+        const double gm = kGInternal * mass;
+        if (withRadius)
+            return (kKilo * kGigaYear / kMegaParsec) * 4.0 * kPi * (radius * radius) * density *
+                   sqrt(cs * cs + velocity * velocity);
+        return (kKilo * kGigaYear / kMegaParsec) * 4.0 * kPi * (gm * gm) * density /
+               dm_pow(cs * cs + velocity * velocity, 1.5);
+    }
+    GLC_DEVICE_INLINE double bh_isco_radius(double j) {
+        // Black_Hole_ISCO_Radius_Spin (prograde), black_holes/fundamentals.F90:78-121; A1, A2 :553-573
+        const double third = 1.0 / 3.0;
+        const double a1 = 1.0 + dm_pow(1.0 - j * j, third) * (dm_pow(1.0 + j, third) + dm_pow(1.0 - j, third));
+        const double a2 = sqrt(3.0 * (j * j) + a1 * a1);
+        return 3.0 + a2 - sqrt((3.0 - a1) * (3.0 + a1 + 2.0 * a2));
+    }
+    GLC_DEVICE_INLINE double bh_isco_energy(double j, double r) {
+        // Black_Hole_ISCO_Specific_Energy_Spin, black_holes/fundamentals.F90:207-233
+        if (j >= 0.99999) return 0.5773502693 + 0.9164864242 * dm_pow(1.0 - j, 1.0 / 3.0);
+        return (r * r - 2.0 * r + j * sqrt(r)) / r / sqrt(r * r - 3.0 * r + 2.0 * j * sqrt(r));
+    }
+    GLC_DEVICE_INLINE double bh_isco_angular_momentum(double j, double r) {
+        // Black_Hole_ISCO_Specific_Angular_Momentum (gravitational units), black_holes/fundamentals.F90:235-282
+        if (j > 0.99999) return 1.154700538 + 1.832972849 * dm_pow(1.0 - j, 1.0 / 3.0);
+        return sqrt(r) * (r * r - 2.0 * j * sqrt(r) + j * j) / r / sqrt(r * r - 3.0 * r + 2.0 * j * sqrt(r));
+    }
+    GLC_DEVICE_INLINE double adaf_table(double spin, int column) {
+        // table1DLogarithmicLinear::interpolate, extrapolationTypeFix (objects/tables/_module.F90:1360-1405,1518-1533,
+        // 2505-2555) of the ADAF tabulations in 1-j (accretion_disks/ADAF.F90:394-447,481-523); 1-j <= 0 (where the
+        // reference would take the logarithm of a non-positive number) is treated as below the table
+        const DeviceTable2D &t = GLC_TABLES.adaf;
+        const double xinv = 1.0 - spin;
+        const double lx0 = GLC_LDG(t.x0), lxn = GLC_LDG(t.x0 + t.n0 - 1);
+        double xe = (xinv > 0.0) ? dm_log(xinv) : lx0;
+        if (xe < lx0) xe = lx0;
+        if (xe > lxn) xe = lxn;
+        int i;
+        if (xe >= lxn)
+            i = t.n0 - 2;
+        else {
+            i = (int)((xe - lx0) * GLC_TABLES.adaf_inv_dlnx);
+            i = max(min(i, t.n0 - 2), 0);
+        }
+        const double h = (xe - GLC_LDG(t.x0 + i)) * GLC_TABLES.adaf_inv_dlnx;
+        return GLC_LDG(t.v + 2 * i + column) * (1.0 - h) + GLC_LDG(t.v + 2 * (i + 1) + column) * h;
+    }
+    GLC_DEVICE_INLINE double disk_fraction_adaf(const Bh &b, double mdot) {
+        // switchedFractionADAF, accretion_disks/switched.F90:259-297
+        double f = 0.0;
+        if (!(b.eddington > 0.0 && mdot > 0.0)) return 0.0;
+        const double lm = dm_log(mdot / b.eddington);
+        if (GLC_PARAMS.accretionRateThinDiskMinimum > 0.0) {
+            const double arg = fmin(+(lm - dm_log(GLC_PARAMS.accretionRateThinDiskMinimum)) / GLC_PARAMS.accretionRateTransitionWidth, 60.0);
+            f = f + 1.0 / (1.0 + dm_exp(arg));
+        }
+        if (GLC_PARAMS.accretionRateThinDiskMaximum < DBL_MAX) {
+            const double arg = fmin(-(lm - dm_log(GLC_PARAMS.accretionRateThinDiskMaximum)) / GLC_PARAMS.accretionRateTransitionWidth, 60.0);
+            f = f + 1.0 / (1.0 + dm_exp(arg));
+        }
+        return f;
+    }
+    GLC_DEVICE_INLINE double disk_efficiency_radiative(const Bh &b, double mdot) {
+        // switchedEfficiencyRadiative :199-226 over shakuraSunyaevEfficiencyRadiative (Shakura_Sunyaev.F90:69-93) and
+        // adafEfficiencyRadiative (ADAF.F90:453-479) with switchedEfficiencyRadiativeScalingADAF :299-331
+        const double f = disk_fraction_adaf(b, mdot);
+        const double effThin = 1.0 - b.eIsco;
+        double effAdaf = GLC_PARAMS.adafEfficiencyRadiationTypeThinDisk ? effThin : GLC_PARAMS.adafEfficiencyRadiation;
+        if (GLC_PARAMS.scaleADAFRadiativeEfficiency) {
+            double scaling = 1.0;
+            if (b.eddington > 0.0 && mdot > 0.0) {
+                const double md = mdot / b.eddington;
+                if (GLC_PARAMS.accretionRateThinDiskMinimum > 0.0 && md < GLC_PARAMS.accretionRateThinDiskMinimum)
+                    scaling = md / GLC_PARAMS.accretionRateThinDiskMinimum;
+            }
+            effAdaf = effAdaf * scaling;
+        }
+        double eff = 0.0;
+        eff = eff + f * effAdaf;
+        eff = eff + (1.0 - f) * effThin;
+        return eff;
+    }
+    GLC_DEVICE_INLINE double disk_power_jet(const Bh &b, double mdot) {
+        // switchedPowerJet :228-242; shakuraSunyaevPowerJet (Shakura_Sunyaev.F90:95-155); adafPowerJet (ADAF.F90:481-499).
+        // 10**42.7 and 10**41.7 are compile-time constants of the reference.
+        const double normKerr = 5.011872336272756e+42 * kErgs * kGigaYear / kMassSolar / (kKilo * kKilo);
+        const double normSchw = 5.011872336272755e+41 * kErgs * kGigaYear / kMassSolar / (kKilo * kKilo);
+        const double f = disk_fraction_adaf(b, mdot);
+        double thin = 0.0;
+        if (mdot > 0.0) {
+            const double md = mdot / b.eddington, mb = b.mass / 1.0e9;
+            if (mb > 0.0 && md > 0.0) {
+                if (b.spin > 0.8)
+                    thin = normKerr * dm_pow(mb, 0.9) * dm_pow(md, 1.2) / 1.0 * (1.0 + 1.1 * b.spin + 0.29 * (b.spin * b.spin));
+                else
+                    thin = normSchw * dm_pow(mb, 0.9) * dm_pow(md, 1.2) / 1.0 * dm_exp(3.785 * b.spin);
+            }
+        }
+        const double adaf = mdot * adaf_table(b.spin, 0);
+        return (1.0 - f) * thin + f * adaf;
+    }
+    GLC_DEVICE_INLINE double disk_rate_spin_up(const Bh &b, double mdot) {
+        // switchedRateSpinUp :244-257; shakuraSunyaevRateSpinUp (Shakura_Sunyaev.F90:157-179); adafRateSpinUp (ADAF.F90:501-523)
+        const double f = disk_fraction_adaf(b, mdot);
+        double thin = 0.0;
+        if (mdot != 0.0) thin = (b.lIsco - 2.0 * b.spin * b.eIsco) * mdot / b.mass;
+        const double adaf = adaf_table(b.spin, 1) * mdot / b.mass;
+        return (1.0 - f) * thin + f * adaf;
+    }
+    GLC_DEVICE_INLINE double sph_gas_density(const NodeCtx &c, const double (&y)[NY], double radius) {
+        // node%massDistribution(spheroid, gaseous)%density: Hernquist profile inside a spherical scaler
+        // (spheroid/standard/bound_functions.Inc; mass_distributions/spherical/{scaler,Hernquist}.F90)
+        if (!has(c, GLC_F_HAS_SPHEROID)) return 0.0;
+        const double a = c.sphRadius;
+        const double m = fmax(0.0, y[GLC_P_SPH_MASS_GAS]);
+        if (a <= 0.0 || !(m > 0.0)) return 0.0;
+        const double x = radius * (1.0 / a);
+        return 0.5 / kPi / x / ((1.0 + x) * (1.0 + x) * (1.0 + x)) * m / (a * a * a);
+    }
+    GLC_DEVICE_INLINE bool bh_on(const NodeCtx &c, const double (&y)[NY], bool go) {
+        return go && has(c, GLC_F_HAS_BH) && y[GLC_P_BH_MASS] > 0.0 &&
+               (GLC_PARAMS.operatorMask & (GLC_OP_BLACK_HOLES_ACCRETION | GLC_OP_BLACK_HOLES_WINDS | GLC_OP_CGM_COOLING_HEATING));
+    }
+    // standardHotModeFraction (accretion_rates/standard.F90:442-466) asks for the cooling radius whenever the hot-halo
+    // density can be non-zero
+    GLC_DEVICE_INLINE bool bh_radius_on(const NodeCtx &c, const double (&y)[NY], const Work &w, bool go) {
+        return bh_on(c, y, go) && w.hhValid && GLC_PARAMS.bondiHoyleAccretionHotModeOnly;
+    }
+    GLC_DEVICE_INLINE void bh_accretion(const NodeCtx &c, const double (&y)[NY], const Work &w, bool go, double rcool, Bh &b) {
+        // blackHoleAccretionRateStandard::rateAccretion, black_holes/accretion_rates/standard.F90:221-440 (no nuclear
+        // star cluster; blackHoleBinarySeparationGrowthRate "zero" => velocityRelative = 0; radialPosition = 0 for the
+        // central black hole; cold mode not tracked)
+        const double densityGasMinimum = 1.0;
+        const double velocity = 0.0 * kMpcPerKmPerSToGyr;
+        b.on = bh_on(c, y, go);
+        b.mass = b.spin = b.eIsco = b.lIsco = b.eddington = b.accSph = b.accHot = b.acc = 0.0;
+        if (!b.on) return;
+        b.mass = y[GLC_P_BH_MASS];
+        b.spin = y[GLC_P_BH_SPIN];
+        // a trial RK stage can carry the spin out of the range in which the Kerr expressions of the reference are finite
+        // (j > 1: cube roots of negative numbers; j < ~-0.63: negative radicand in the ISCO energy of the prograde formula).
+        // The ISCO quantities are evaluated at the spin clamped to [-0.5, 1]; states reached by accepted steps are in
+        // [0, 0.9999] (post-step clamp), so this only replaces NaNs of rejected trial stages.
+        const double jk = fmax(fmin(b.spin, 1.0), -0.5);
+        const double riso = bh_isco_radius(jk);
+        b.eIsco = bh_isco_energy(jk, riso);
+        b.lIsco = bh_isco_angular_momentum(jk, riso);
+        // Black_Hole_Eddington_Accretion_Rate, fundamentals.F90:123-138
+        b.eddington = 4.0 * kPi * kGravitationalConstant * b.mass * kMassHydrogenAtom * kGigaYear / kThomsonCrossSection / kSpeedLight;
+        // spheroid
+        double rAcc = fmax(bhl_radius(b.mass, GLC_PARAMS.bondiHoyleAccretionTemperatureSpheroid), 0.0);
+        double rho = sph_gas_density(c, y, rAcc);
+        if (rho > densityGasMinimum) {
+            double lj = ideal_gas_sound_speed(GLC_PARAMS.bondiHoyleAccretionTemperatureSpheroid) / sqrt(kGInternal) / sqrt(rho);
+            lj = fmin(lj, c.sphRadius);
+            if (lj > rAcc) rho = sph_gas_density(c, y, lj);
+            b.accSph = fmax(GLC_PARAMS.bondiHoyleAccretionEnhancementSpheroid *
+                                bhl_rate(b.mass, rho, velocity, GLC_PARAMS.bondiHoyleAccretionTemperatureSpheroid, false, 0.0),
+                            0.0);
+            const double eff = disk_efficiency_radiative(b, b.accSph);
+            if (eff > 0.0) b.accSph = fmin(b.accSph, b.eddington / eff);
+        }
+        // hot halo
+        if (w.hhValid) {
+            const double tHot = w.tvir;  // hotHaloTemperatureProfile virial
+            double fHot = 1.0;
+            rAcc = bhl_radius(b.mass, tHot);
+            rAcc = fmin(rAcc, w.hhRouter);
+            if (GLC_PARAMS.bondiHoyleAccretionHotModeOnly) {
+                const double xf = rcool / w.rvir;
+                if (xf < 0.9)
+                    fHot = 1.0;
+                else if (xf > 1.0)
+                    fHot = 0.0;
+                else {
+                    const double x = (xf - 0.9) / (1.0 - 0.9);
+                    fHot = x * x * (2.0 * x - 3.0) + 1.0;
+                }
+            }
+            rho = fHot * hh_density(w, rAcc);
+            if (rho > densityGasMinimum) {
+                b.accHot = fmax(GLC_PARAMS.bondiHoyleAccretionEnhancementHotHalo * bhl_rate(b.mass, rho, velocity, tHot, true, rAcc), 0.0);
+                const double rateMax = fmax(y[GLC_P_HH_MASS] / (w.hhRouter / ideal_gas_sound_speed(tHot) * kMpcPerKmPerSToGyr), 0.0);
+                b.accHot = fmin(b.accHot, rateMax);
+                const double eff = disk_efficiency_radiative(b, b.accHot);
+                if (eff > 0.0) b.accHot = fmin(b.accHot, b.eddington / eff);
+            }
+        }
+        b.acc = b.accSph + b.accHot;
+    }
+    GLC_DEVICE_INLINE double bh_wind_power(const NodeCtx &c, const double (&y)[NY], const Bh &b) {
+        // blackHoleWindCiotti2009::power, black_holes/winds/Ciotti2009.F90:153-246
+        const double velocityWind = 1.0e4, temperatureISM = 1.0e4;
+        double eff = GLC_PARAMS.bhEfficiencyWind, coupled = 0.0;
+        if (GLC_PARAMS.bhEfficiencyWindScalesWithEfficiencyRadiative) eff = eff * disk_efficiency_radiative(b, b.acc);
+        if (b.acc <= 0.0 || eff <= 0.0) return 0.0;
+        const double mgas = has(c, GLC_F_HAS_SPHEROID) ? y[GLC_P_SPH_MASS_GAS] : 0.0;
+        if (mgas > 0.0) {
+            const double rs = c.sphRadius;
+            if (rs > 0.0) {
+                const double c2 = kSpeedLight * kSpeedLight;
+                const double pWind = eff * b.acc * kMassSolar / kGigaYear * c2 / 4.0 / kPi / velocityWind / kKilo / (rs * rs) /
+                                     (kMegaParsec * kMegaParsec);
+                const double pIsm = 3.0 / 4.0 / kPi * mgas * kMassSolar / (rs * rs * rs) / (kMegaParsec * kMegaParsec * kMegaParsec) /
+                                    kMassHydrogenAtom * 3.0 / 2.0 * kBoltzmann * temperatureISM;
+                const double x = pIsm / pWind - 0.50;
+                if (x <= 0.0)
+                    coupled = 0.0;
+                else if (x >= 1.0)
+                    coupled = 1.0;
+                else
+                    coupled = 3.0 * (x * x) - 2.0 * (x * x * x);
+            }
+        }
+        eff = eff * coupled;
+        return eff * b.acc * (kSpeedLight * kSpeedLight) / (kKilo * kKilo);
+    }
+
     // ---------------------------------------------------------------- scales (scaleSetTask hooks)
     GLC_DEVICE_INLINE void scales(const NodeCtx &c, const double (&y)[NY], double (&s)[NY]) {
         Work w;
@@ -720,7 +958,13 @@ struct ModelStandard {
             const double ss = has(c, GLC_F_IS_SATELLITE) ? sm : 1.0;
             s[GLC_P_HH_STRIPPED_MASS] = s[GLC_P_HH_STRIPPED_ABUND] = ss;
         }
-        if (has(c, GLC_F_HAS_BH)) s[GLC_P_BH_MASS] = s[GLC_P_BH_SPIN] = 1.0;
+        if (has(c, GLC_F_HAS_BH)) {
+            // Node_Component_Black_Hole_Standard_Scale_Set, black_hole/standard/_class.F90:193-257 (no nuclear star cluster)
+            double mstar = has(c, GLC_F_HAS_SPHEROID) ? y[GLC_P_SPH_MASS_STELLAR] : 0.0;
+            if (!(mstar > 0.0)) mstar = 0.0;
+            s[GLC_P_BH_MASS] = fmax(fmax(1.0, 1.0e-4 * mstar), y[GLC_P_BH_MASS]);
+            s[GLC_P_BH_SPIN] = 1.0;
+        }
     }
 
     GLC_DEVICE_INLINE void pre_evolve(NodeCtx &c, double (&y)[NY]) {
@@ -829,8 +1073,12 @@ struct ModelStandard {
                y[GLC_P_HH_MASS] > 0.0 && !(y[GLC_P_HH_ANGMOM] <= 0.0 || w.hhRouter <= 0.0);
     }
     // coolingRateWhiteFrenk1991::rate needs the cooling radius unless the halo is above the velocity cut-off
-    GLC_DEVICE_INLINE bool cooling_radius_on(const Work &w, bool coolOn) {
+    GLC_DEVICE_INLINE bool cooling_rate_needs_radius(const Work &w, bool coolOn) {
         return coolOn && !(w.vvir > GLC_PARAMS.coolingVelocityCutOff);
+    }
+    // ... and so does the hot-mode fraction of the black-hole accretion rate
+    GLC_DEVICE_INLINE bool cooling_radius_on(const NodeCtx &c, const double (&y)[NY], const Work &w, bool coolOn, bool go) {
+        return cooling_rate_needs_radius(w, coolOn) || bh_radius_on(c, y, w, go);
     }
 
     // Everything of the RHS that is straight-line once the nested solvers have delivered the disk star formation
@@ -843,6 +1091,7 @@ struct ModelStandard {
         const uint32_t ops = GLC_PARAMS.operatorMask;
         const bool hh = has(c, GLC_F_HAS_HOTHALO), hd = has(c, GLC_F_HAS_DISK), hs = has(c, GLC_F_HAS_SPHEROID);
         const bool sat = has(c, GLC_F_IS_SATELLITE);
+        const bool coolRadiusOn = cooling_rate_needs_radius(w, coolOn);  // radiusOn may also be set for the black hole
         // satelliteMassLoss (satellite/mass_loss/_class.F90:230-257; darkMatterHaloMassLossRate "zero")
         if (go && (ops & GLC_OP_SATELLITE_MASS_LOSS)) rate[GLC_P_SAT_BOUND_MASS] += sat ? 0.0 : c.massRate;
 
@@ -898,6 +1147,56 @@ struct ModelStandard {
             }
         }
 
+        // blackHolesSeed (black_holes/seed.F90:153-182, blackHoleSeeds fixed): create the seed by interrupt
+        if (go && (ops & GLC_OP_BLACK_HOLES_SEED) && !has(c, GLC_F_HAS_BH) && GLC_PARAMS.bhSeedMass > 0.0)
+            a.interrupt = GLC_INT_BH_CREATE;
+        Bh bh;
+        bh_accretion(c, y, w, go, radiusOn ? rinfallSolved : 0.0, bh);
+        // blackHolesAccretion (black_holes/accretion.F90:113-173)
+        if (bh.on && (ops & GLC_OP_BLACK_HOLES_ACCRETION) && bh.acc > 0.0) {
+            const double effRad = disk_efficiency_radiative(bh, bh.acc);
+            const double effJet = disk_power_jet(bh, bh.acc) / bh.acc / (kSpeedLight * kSpeedLight) / (kKilo * kKilo);
+            const double reduced = bh.acc * (1.0 - effRad - effJet);
+            const double spinUp = disk_rate_spin_up(bh, bh.acc);
+            rate[GLC_P_BH_MASS] += reduced;
+            // Node_Component_Spheroid_Standard_Mass_Gas_Sink_Rate, spheroid/standard/_class.F90:638-671
+            if (hs && -bh.accSph != 0.0) {
+                const double mg = y[GLC_P_SPH_MASS_GAS], ms = y[GLC_P_SPH_MASS_STELLAR], r = -bh.accSph;
+                if (mg > 0.0 && mg + ms > 0.0) {
+                    rate[GLC_P_SPH_MASS_GAS] += r;
+                    rate[GLC_P_SPH_ANGMOM] += (r / (mg + ms)) * y[GLC_P_SPH_ANGMOM];
+                    rate[GLC_P_SPH_ABUND_GAS] += (r / mg) * y[GLC_P_SPH_ABUND_GAS];
+                }
+            }
+            // Node_Component_Hot_Halo_Standard_Mass_Sink -> Hot_Gas_All_Rate, hot_halo/standard/_class.F90:749-800
+            if (hh && -bh.accHot != 0.0) {
+                const double mg = y[GLC_P_HH_MASS], r = -bh.accHot;
+                if (mg > 0.0) {
+                    rate[GLC_P_HH_MASS] += r;
+                    rate[GLC_P_HH_ANGMOM] += y[GLC_P_HH_ANGMOM] * (r / mg);
+                    rate[GLC_P_HH_ABUND] += y[GLC_P_HH_ABUND] * (r / mg);
+                }
+            }
+            rate[GLC_P_BH_SPIN] += spinUp;
+        }
+        // blackHolesWinds (black_holes/winds.F90:103-134) -> Node_Component_Spheroid_Standard_Energy_Gas_Input_Rate,
+        // spheroid/standard/_class.F90:673-725
+        if (bh.on && (ops & GLC_OP_BLACK_HOLES_WINDS)) {
+            const double power = bh_wind_power(c, y, bh);
+            if (power != 0.0 && hs) {
+                const double mg = y[GLC_P_SPH_MASS_GAS], ms = y[GLC_P_SPH_MASS_STELLAR], vs = c.sphVelocity;
+                if (mg > 0.0 && mg + ms > 0.0 && vs > 0.0) {
+                    const double out = GLC_PARAMS.spheroidEfficiencyEnergeticOutflow * power / (vs * vs);
+                    const double jout = (out / (mg + ms)) * y[GLC_P_SPH_ANGMOM];
+                    const double zout = (out / mg) * y[GLC_P_SPH_ABUND_GAS];
+                    rate[GLC_P_SPH_MASS_GAS] += -out;
+                    rate[GLC_P_SPH_ANGMOM] += -jout;
+                    rate[GLC_P_SPH_ABUND_GAS] += -zout;
+                    hh_outflowing(a, c, w, rate, out, jout, zout);
+                }
+            }
+        }
+
         // CGMAccretion (circumgalactic_medium/accretion.F90:517-593; accretion/halo/simple.F90:281-378,592-613)
         if (go && (ops & GLC_OP_CGM_ACCRETION)) {
             double rateHot = 0.0, rateFailed = 0.0, rateJ = 0.0;
@@ -935,7 +1234,7 @@ struct ModelStandard {
         // CGMCoolingHeating (cooling_heating.F90:216-381; component=disk, coolingFrom=currentNode)
         if (coolOn) {
             double cool = 0.0, rinfall = 0.0;
-            if (radiusOn) {
+            if (coolRadiusOn) {
                 rinfall = rinfallSolved;
                 if (rinfall >= w.hhRouter)
                     cool = y[GLC_P_HH_MASS] / w.tdyn;
@@ -951,7 +1250,9 @@ struct ModelStandard {
                     cool = 4.0 * kPi * rinfall * rinfall * hh_density(w, rinfall) * growth;
                 }
             }
-            const double heat = 0.0 / (w.vvir * w.vvir);  // circumgalacticMediumHeatingAGNFeedback: no black holes yet
+            // circumgalacticMediumHeatingAGNFeedback (circumgalactic_medium/heating/AGN_feedback.F90:103-126) over
+            // blackHoleCGMHeatingJetPower (black_holes/CGM_heating/jet_power.F90:120-138)
+            const double heat = (bh.on ? GLC_PARAMS.bhEfficiencyRadioMode * disk_power_jet(bh, bh.acc) : 0.0) / (w.vvir * w.vvir);
             if (heat > cool) {
                 if (GLC_PARAMS.excessHeatDrivesOutflow) {
                     const double out = fmin(heat - cool, GLC_PARAMS.rateMaximumExpulsion * y[GLC_P_HH_MASS] / w.tdyn);
@@ -1029,7 +1330,7 @@ struct ModelStandard {
         const bool dOn = disk_sfr_on(c, y, go);
         const double psiDisk = sfr_disk(c, y, bad, dOn);
         const bool coolOn = cooling_on(c, y, w, go);
-        const bool radiusOn = cooling_radius_on(w, coolOn);
+        const bool radiusOn = cooling_radius_on(c, y, w, coolOn, go);
         double logSlopeT = 0.0;
         if (radiusOn) cooling_prepare(y, w, logSlopeT);
         const double rinfallSolved = cooling_radius(y, w, bad, radiusOn);
@@ -1116,6 +1417,17 @@ struct ModelStandard {
             if (y[GLC_P_SPH_ANGMOM] < 0.0) {
                 const double j = c.sphRadius * c.sphVelocity / GLC_PARAMS.spheroidRatioAngularMomentumScaleRadius;
                 y[GLC_P_SPH_ANGMOM] = j * (y[GLC_P_SPH_MASS_GAS] + y[GLC_P_SPH_MASS_STELLAR]);
+                status = kGslContinue;
+            }
+        }
+        // Node_Component_Black_Hole_Standard_Post_Evolve, black_hole/standard/_class.F90:422-462
+        if (has(c, GLC_F_HAS_BH)) {
+            if (y[GLC_P_BH_SPIN] > 0.9999 || y[GLC_P_BH_SPIN] < 0.0) {
+                y[GLC_P_BH_SPIN] = fmax(fmin(y[GLC_P_BH_SPIN], 0.9999), 0.0);
+                status = kGslContinue;
+            }
+            if (y[GLC_P_BH_MASS] < 0.0) {
+                y[GLC_P_BH_MASS] = GLC_PARAMS.bhSeedMass;
                 status = kGslContinue;
             }
         }

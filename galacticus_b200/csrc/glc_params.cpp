@@ -83,6 +83,10 @@ extern "C" int glc_params_default(glc_params *P, int32_t model) {
     P->accretionRateThinDiskMinimum = 0.01;
     P->adafEfficiencyRadiation = 0.01;
     P->adafAdiabaticIndex = 1.444;
+    P->accretionRateTransitionWidth = 0.1;  /* accretion_disks/switched.F90:125-127 */
+    P->scaleADAFRadiativeEfficiency = 1;
+    P->bhEfficiencyWindScalesWithEfficiencyRadiative = 1;
+    P->adafEfficiencyRadiationTypeThinDisk = 1;
     P->operatorMask = GLC_OP_ALL;
     return 0;
 }

@@ -48,6 +48,12 @@ inline int prepare_table(int id, int n0, int n1, const double *x0, const double 
         if (n1 != 1) return -1;
         t.ln0 = dm_log(t.x0[0]);
         t.inv_dln = (double)(n0 - 1) / (dm_log(t.x0[n0 - 1]) - dm_log(t.x0[0]));
+    } else if (id == GLC_TABLE_ADAF) {
+        if (n1 != 2) return -1;
+        // table1DLogarithmicLinear keeps its abscissae as ln x (objects/tables/_module.F90:1451-1468)
+        for (auto &x : t.x0) x = dm_log(x);
+        t.ln0 = t.x0[0];
+        t.inv_dln = (double)(n0 - 1) / (t.x0[n0 - 1] - t.x0[0]);
     }
     return 0;
 }
@@ -94,6 +100,9 @@ inline void install_table(DeviceTables &T, int id, const PreparedTable &t, const
         T.diskrc = d;
         T.diskrc_lnx0 = t.ln0;
         T.diskrc_inv_dlnx = t.inv_dln;
+    } else if (id == GLC_TABLE_ADAF) {
+        T.adaf = d;
+        T.adaf_inv_dlnx = t.inv_dln;
     }
 }
 

@@ -99,12 +99,30 @@ def disk_rotation_curve_table(per_decade=100, x_min=1.0e-6, x_max=1.0e2):
     return x, None, f
 
 
+def adaf_table(count=10000, x_min=1.0e-6, x_max=1.0):
+    """GLC_TABLE_ADAF: the two tabulations the accretionDisksADAF constructor builds (accretion_disks/ADAF.F90:394-447)
+    on its lattice (table1DLogarithmicLinear in the inverse spin 1-j on [1e-6, 1], countTable = 10000 points).  The
+    Benson & Babul (2009) ADAF structure integrals that fill the reference's table are host-side, construction-time
+    work outside the hot path; this stand-in has the same shape and qualitative behaviour: a jet efficiency that
+    rises steeply towards j = 1 and is capped at efficiencyJetMaximum = 2, and a spin-up function that changes sign
+    at the equilibrium spin j ~ 0.93."""
+    x = np.exp(np.linspace(np.log(x_min), np.log(x_max), count))
+    x[0], x[-1] = x_min, x_max
+    j = 1.0 - x
+    speed_light_kms = 2.99792458e8 / 1.0e3
+    efficiency_jet = np.minimum(2.0, 0.002 + 0.1 * j**2 + 0.02 * j**2 / x**0.7)
+    power_jet = efficiency_jet * speed_light_kms**2
+    spin_up = 2.0 * (1.0 - j / 0.93)
+    return x, None, np.stack([power_jet, spin_up], axis=1)
+
+
 def standard_tables(params):
     return {
         abi.GLC_TABLE_COOLING_FUNCTION: cooling_function_table(),
         abi.GLC_TABLE_ELECTRON_FRACTION: electron_fraction_table(),
         abi.GLC_TABLE_HALO_MEAN_DENSITY: halo_mean_density_table(params),
         abi.GLC_TABLE_DISK_ROTATION_CURVE: disk_rotation_curve_table(),
+        abi.GLC_TABLE_ADAF: adaf_table(),
     }
 
 
@@ -131,8 +149,10 @@ def virial_radius(params, mass, t):
     return np.cbrt(3.0 * mass / (4.0 * np.pi * rho))
 
 
-def standard_nodes(params, n, seed=219, fresh_fraction=0.3, satellite_fraction=0.2):
-    """Seeded node records spanning the quickTest mass range (1e10..1e13 Msun) at 1..13 Gyr."""
+def standard_nodes(params, n, seed=219, fresh_fraction=0.3, satellite_fraction=0.2, black_hole_fraction=0.0):
+    """Seeded node records spanning the quickTest mass range (1e10..1e13 Msun) at 1..13 Gyr.  A fraction
+    black_hole_fraction of the nodes carries a black hole (drawn from a separate stream so that the other properties do
+    not depend on it); the others get their seed by the blackHolesSeed interrupt when that operator is enabled."""
     rng = np.random.default_rng(seed)
     cosmo = Cosmology(params)
     props = np.zeros((n, abi.NPROP))
@@ -218,4 +238,17 @@ def standard_nodes(params, n, seed=219, fresh_fraction=0.3, satellite_fraction=0
     props[:, P["SPH_RADIUS"]] = np.where(warm_s, rs, 0.0)
     props[:, P["SPH_VELOCITY"]] = np.where(warm_s, vvir * rng.uniform(0.8, 1.8, n), 0.0)
     flags[has_s] |= abi.GLC_F_HAS_SPHEROID
+
+    # black hole: masses from the seed (100 Msun) to 1e9.5 Msun, capped at 1 % of the halo's baryons so that all
+    # accretion regimes (ADAF / thin disk / Eddington-limited) occur; spins over [0, 0.9999]
+    if black_hole_fraction > 0.0:
+        rb = np.random.default_rng(seed + 100003)
+        has_b = rb.random(n) < black_hole_fraction
+        mb = np.minimum(10.0 ** rb.uniform(2.0, 9.5, n), 0.01 * fb * mass)
+        jb = rb.uniform(0.0, 0.998, n)
+        u = rb.random(n)
+        jb = np.where(u < 0.1, 0.0, np.where(u > 0.95, 0.9999, jb))
+        props[:, P["BH_MASS"]] = np.where(has_b, mb, 0.0)
+        props[:, P["BH_SPIN"]] = np.where(has_b, jb, 0.0)
+        flags[has_b] |= abi.GLC_F_HAS_BH
     return props, flags, t0 + dt

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GLC_ABI_VERSION 1
+#define GLC_ABI_VERSION 2
 
 /* ---------------------------------------------------------------------------------
  * Node record.  One row of GLC_NPROP doubles per node, node-major ("what
@@ -196,10 +196,13 @@ typedef struct glc_params {
     double bhEfficiencyWind, bhEfficiencyRadioMode;
     double accretionRateThinDiskMaximum, accretionRateThinDiskMinimum;
     double adafEfficiencyRadiation, adafAdiabaticIndex;
+    double accretionRateTransitionWidth;      /* accretionDisks switched [accretionRateTransitionWidth] (switched.F90:125-127) */
+    int32_t scaleADAFRadiativeEfficiency;     /* accretionDisks switched */
+    int32_t bhEfficiencyWindScalesWithEfficiencyRadiative; /* blackHoleWind ciotti2009 */
+    int32_t adafEfficiencyRadiationTypeThinDisk; /* accretionDisksADAF [efficiencyRadiationType]: 1 thinDisk, 0 fixed */
     /* operator enable mask (bit i = operator i of enum glc_operator); lets a host run
        reduced operator sets exactly as a reduced <nodeOperator value="multi"> would */
     uint32_t operatorMask;
-    uint32_t pad2;
 } glc_params;
 
 enum glc_operator {
@@ -238,6 +241,11 @@ enum glc_table {
        lattice of half-radii x = R/2R_d, 100 points per decade (table1DLogarithmicLinear,
        mass_distributions/cylindrical/exponential_disk.F90:675-733): x0 = half-radii[n0], n1 = 1. */
     GLC_TABLE_DISK_ROTATION_CURVE = 3,
+    /* ADAF tabulations built by the accretionDisksADAF constructor (accretion_disks/ADAF.F90:394-447):
+       table1DLogarithmicLinear in the "inverse spin" 1-j on [1e-6,1] (countTable = 10000 there), extrapolation
+       "fix" at both ends: x0 = (1-j)[n0] (log-uniform), n1 = 2: values[n0][0] = jet power per unit accretion
+       rate ((km/s)^2, adafTablePowerJet), values[n0][1] = spin-up to mass-growth ratio (adafTableRateSpinUp). */
+    GLC_TABLE_ADAF = 4,
     GLC_NTABLES
 };
 

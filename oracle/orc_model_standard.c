@@ -785,6 +785,256 @@ static double sfr_spheroid(const std_work *w) {
     return (tau > 0.0) ? w->p[GLC_P_SPH_MASS_GAS] / tau : 0.0;
 }
 
+/* ------------------------------------------------------------ black holes */
+typedef struct bh_state {
+    int on;          /* a black hole of positive mass exists */
+    double mass, spin;
+    double e_isco, l_isco; /* ISCO specific energy / angular momentum, gravitational units, prograde */
+    double eddington;
+    double acc_sph, acc_hot, acc; /* blackHoleAccretionRateStandard::rateAccretion */
+} bh_state;
+
+static double ideal_gas_sound_speed(double temperature) {
+    /* Ideal_Gas_Sound_Speed, thermodynamics/ideal_gases.F90:46-69 (primordial mean atomic mass) */
+    return sqrt(5.0 * ORC_BOLTZMANN * temperature / 3.0 / ORC_MEAN_ATOMIC_MASS_PRIMORDIAL / ORC_ATOMIC_MASS_UNIT) / ORC_KILO;
+}
+static double bhl_radius(double mass, double temperature) {
+    /* Bondi_Hoyle_Lyttleton_Accretion_Radius, accretion/Bondi_Hoyle_Lyttleton.F90:61-78 */
+    double cs;
+    if (!(temperature > 0.0)) return DBL_MAX;
+    cs = ideal_gas_sound_speed(temperature);
+    return ORC_G_INTERNAL * mass / (cs * cs);
+}
+static double bhl_rate(double mass, double density, double velocity, double temperature, int with_radius, double radius) {
+    /* Bondi_Hoyle_Lyttleton_Accretion_Rate, accretion/Bondi_Hoyle_Lyttleton.F90:34-59 */
+    const double cs = ideal_gas_sound_speed(temperature);
+    const double gm = ORC_G_INTERNAL * mass;
+    if (with_radius)
+        return (ORC_KILO * ORC_GIGAYEAR / ORC_MEGAPARSEC) * 4.0 * ORC_PI * (radius * radius) * density *
+               sqrt(cs * cs + velocity * velocity);
+    return (ORC_KILO * ORC_GIGAYEAR / ORC_MEGAPARSEC) * 4.0 * ORC_PI * (gm * gm) * density /
+           dm_pow(cs * cs + velocity * velocity, 1.5);
+}
+static double bh_isco_radius(double j) {
+    /* Black_Hole_ISCO_Radius_Spin (prograde), black_holes/fundamentals.F90:78-121; A1, A2 :553-573 */
+    const double third = 1.0 / 3.0;
+    double a1 = 1.0 + dm_pow(1.0 - j * j, third) * (dm_pow(1.0 + j, third) + dm_pow(1.0 - j, third));
+    double a2 = sqrt(3.0 * (j * j) + a1 * a1);
+    return 3.0 + a2 - sqrt((3.0 - a1) * (3.0 + a1 + 2.0 * a2));
+}
+static double bh_isco_energy(double j, double r) {
+    /* Black_Hole_ISCO_Specific_Energy_Spin, black_holes/fundamentals.F90:207-233 */
+    if (j >= 0.99999) return 0.5773502693 + 0.9164864242 * dm_pow(1.0 - j, 1.0 / 3.0);
+    return (r * r - 2.0 * r + j * sqrt(r)) / r / sqrt(r * r - 3.0 * r + 2.0 * j * sqrt(r));
+}
+static double bh_isco_angular_momentum(double j, double r) {
+    /* Black_Hole_ISCO_Specific_Angular_Momentum (gravitational units), black_holes/fundamentals.F90:235-282 */
+    if (j > 0.99999) return 1.154700538 + 1.832972849 * dm_pow(1.0 - j, 1.0 / 3.0);
+    return sqrt(r) * (r * r - 2.0 * j * sqrt(r) + j * j) / r / sqrt(r * r - 3.0 * r + 2.0 * j * sqrt(r));
+}
+static double adaf_table(const std_work *w, double spin, int column) {
+    /* table1DLogarithmicLinear::interpolate with extrapolationTypeFix (objects/tables/_module.F90:1360-1405,
+       1518-1533, 2505-2555) of the ADAF tabulations in 1-j (accretion_disks/ADAF.F90:394-447,481-523).
+       1-j <= 0 (the reference would take log of a non-positive number) is treated as below the table. */
+    const orc_table2d *t = &w->T->t[GLC_TABLE_ADAF];
+    const double xinv = 1.0 - spin;
+    const double lx0 = dm_log(t->x0[0]), lxn = dm_log(t->x0[t->n0 - 1]);
+    const double inv = (double)(t->n0 - 1) / (lxn - lx0);
+    double xe, h;
+    int i;
+    xe = (xinv > 0.0) ? dm_log(xinv) : lx0;
+    if (xe < lx0) xe = lx0;
+    if (xe > lxn) xe = lxn;
+    if (xe >= lxn)
+        i = t->n0 - 2;
+    else {
+        i = (int)((xe - lx0) * inv);
+        if (i > t->n0 - 2) i = t->n0 - 2;
+        if (i < 0) i = 0;
+    }
+    h = (xe - dm_log(t->x0[i])) * inv;
+    return t->v[2 * i + column] * (1.0 - h) + t->v[2 * (i + 1) + column] * h;
+}
+static double disk_fraction_adaf(const std_work *w, const bh_state *b, double mdot) {
+    /* switchedFractionADAF, accretion_disks/switched.F90:259-297 */
+    const glc_params *P = w->P;
+    double f = 0.0, lm, arg;
+    if (!(b->eddington > 0.0 && mdot > 0.0)) return 0.0;
+    lm = dm_log(mdot / b->eddington);
+    if (P->accretionRateThinDiskMinimum > 0.0) {
+        arg = fmin(+(lm - dm_log(P->accretionRateThinDiskMinimum)) / P->accretionRateTransitionWidth, 60.0);
+        f = f + 1.0 / (1.0 + dm_exp(arg));
+    }
+    if (P->accretionRateThinDiskMaximum < DBL_MAX) {
+        arg = fmin(-(lm - dm_log(P->accretionRateThinDiskMaximum)) / P->accretionRateTransitionWidth, 60.0);
+        f = f + 1.0 / (1.0 + dm_exp(arg));
+    }
+    return f;
+}
+static double disk_efficiency_radiative(const std_work *w, const bh_state *b, double mdot) {
+    /* switchedEfficiencyRadiative :199-226 over shakuraSunyaevEfficiencyRadiative (Shakura_Sunyaev.F90:69-93)
+       and adafEfficiencyRadiative (ADAF.F90:453-479) with switchedEfficiencyRadiativeScalingADAF :299-331 */
+    const glc_params *P = w->P;
+    const double f = disk_fraction_adaf(w, b, mdot);
+    const double eff_thin = 1.0 - b->e_isco;
+    double eff_adaf = P->adafEfficiencyRadiationTypeThinDisk ? eff_thin : P->adafEfficiencyRadiation;
+    double eff;
+    if (P->scaleADAFRadiativeEfficiency) {
+        double scaling = 1.0;
+        if (b->eddington > 0.0 && mdot > 0.0) {
+            const double md = mdot / b->eddington;
+            if (P->accretionRateThinDiskMinimum > 0.0 && md < P->accretionRateThinDiskMinimum)
+                scaling = md / P->accretionRateThinDiskMinimum;
+        }
+        eff_adaf = eff_adaf * scaling;
+    }
+    eff = 0.0;
+    eff = eff + f * eff_adaf;
+    eff = eff + (1.0 - f) * eff_thin;
+    return eff;
+}
+static double disk_power_jet(const std_work *w, const bh_state *b, double mdot) {
+    /* switchedPowerJet :228-242; shakuraSunyaevPowerJet (Shakura_Sunyaev.F90:95-155, Meier 2001);
+       adafPowerJet (ADAF.F90:481-499) */
+    /* (10**42.7, 10**41.7) * ergs * gigaYear / massSolar / kilo**2: compile-time constants of the reference */
+    const double norm_kerr = 5.011872336272756e+42 * ORC_ERGS * ORC_GIGAYEAR / ORC_MASS_SOLAR / (ORC_KILO * ORC_KILO);
+    const double norm_schw = 5.011872336272755e+41 * ORC_ERGS * ORC_GIGAYEAR / ORC_MASS_SOLAR / (ORC_KILO * ORC_KILO);
+    const double f = disk_fraction_adaf(w, b, mdot);
+    double thin = 0.0, adaf;
+    if (mdot > 0.0) {
+        const double md = mdot / b->eddington, mb = b->mass / 1.0e9;
+        if (mb > 0.0 && md > 0.0) {
+            if (b->spin > 0.8)
+                thin = norm_kerr * dm_pow(mb, 0.9) * dm_pow(md, 1.2) / 1.0 *
+                       (1.0 + 1.1 * b->spin + 0.29 * (b->spin * b->spin));
+            else
+                thin = norm_schw * dm_pow(mb, 0.9) * dm_pow(md, 1.2) / 1.0 * dm_exp(3.785 * b->spin);
+        }
+    }
+    adaf = mdot * adaf_table(w, b->spin, 0);
+    return (1.0 - f) * thin + f * adaf;
+}
+static double disk_rate_spin_up(const std_work *w, const bh_state *b, double mdot) {
+    /* switchedRateSpinUp :244-257; shakuraSunyaevRateSpinUp (Shakura_Sunyaev.F90:157-179); adafRateSpinUp (ADAF.F90:501-523) */
+    const double f = disk_fraction_adaf(w, b, mdot);
+    double thin = 0.0, adaf;
+    if (mdot != 0.0) thin = (b->l_isco - 2.0 * b->spin * b->e_isco) * mdot / b->mass;
+    adaf = adaf_table(w, b->spin, 1) * mdot / b->mass;
+    return (1.0 - f) * thin + f * adaf;
+}
+static double sph_gas_density(const std_work *w, double radius) {
+    /* node%massDistribution(spheroid, gaseous)%density: Hernquist profile inside a spherical scaler
+       (spheroid/standard/bound_functions.Inc: Node_Component_Spheroid_Standard_Mass_Distribution;
+       mass_distributions/spherical/{scaler,Hernquist}.F90) */
+    double a, m, x;
+    if (!has(w, GLC_F_HAS_SPHEROID)) return 0.0;
+    a = w->p[GLC_P_SPH_RADIUS];
+    m = fmax(0.0, w->p[GLC_P_SPH_MASS_GAS]);
+    if (a <= 0.0 || !(m > 0.0)) return 0.0;
+    x = radius * (1.0 / a);
+    return 0.5 / ORC_PI / x / ((1.0 + x) * (1.0 + x) * (1.0 + x)) * m / (a * a * a);
+}
+static void bh_accretion(std_work *w, bh_state *b) {
+    /* blackHoleAccretionRateStandard::rateAccretion, black_holes/accretion_rates/standard.F90:221-440
+       (no nuclear star cluster component, blackHoleBinarySeparationGrowthRate "zero" => velocityRelative = 0,
+       radialPosition = 0 for the central black hole, cold mode not tracked) */
+    const glc_params *P = w->P;
+    const double density_gas_minimum = 1.0;
+    const double velocity = 0.0 * ORC_MPC_PER_KMS_TO_GYR;
+    double r_acc, rho, riso, jk;
+    memset(b, 0, sizeof(*b));
+    if (!(P->operatorMask & (GLC_OP_BLACK_HOLES_ACCRETION | GLC_OP_BLACK_HOLES_WINDS | GLC_OP_CGM_COOLING_HEATING))) return;
+    if (!has(w, GLC_F_HAS_BH)) return;
+    b->mass = w->p[GLC_P_BH_MASS];
+    b->spin = w->p[GLC_P_BH_SPIN];
+    if (!(b->mass > 0.0)) return;
+    b->on = 1;
+    /* a trial RK stage can carry the spin out of the range in which the Kerr expressions of the reference are finite
+       (j > 1: cube roots of negative numbers; j < ~-0.63: negative radicand in the ISCO energy of the prograde formula).
+       The ISCO quantities are evaluated at the spin clamped to [-0.5, 1]; states reached by accepted steps are in
+       [0, 0.9999] (post-step clamp), so this only replaces NaNs of rejected trial stages. */
+    jk = fmax(fmin(b->spin, 1.0), -0.5);
+    riso = bh_isco_radius(jk);
+    b->e_isco = bh_isco_energy(jk, riso);
+    b->l_isco = bh_isco_angular_momentum(jk, riso);
+    /* Black_Hole_Eddington_Accretion_Rate, fundamentals.F90:123-138 */
+    b->eddington = 4.0 * ORC_PI * ORC_GRAVITATIONAL_CONSTANT * b->mass * ORC_MASS_HYDROGEN_ATOM * ORC_GIGAYEAR /
+                   ORC_THOMSON_CROSS_SECTION / ORC_SPEED_LIGHT;
+    /* spheroid */
+    r_acc = fmax(bhl_radius(b->mass, P->bondiHoyleAccretionTemperatureSpheroid), 0.0);
+    rho = sph_gas_density(w, r_acc);
+    if (rho > density_gas_minimum) {
+        double lj = ideal_gas_sound_speed(P->bondiHoyleAccretionTemperatureSpheroid) / sqrt(ORC_G_INTERNAL) / sqrt(rho);
+        double eff;
+        lj = fmin(lj, w->p[GLC_P_SPH_RADIUS]);
+        if (lj > r_acc) rho = sph_gas_density(w, lj);
+        b->acc_sph = fmax(P->bondiHoyleAccretionEnhancementSpheroid *
+                              bhl_rate(b->mass, rho, velocity, P->bondiHoyleAccretionTemperatureSpheroid, 0, 0.0),
+                          0.0);
+        eff = disk_efficiency_radiative(w, b, b->acc_sph);
+        if (eff > 0.0) b->acc_sph = fmin(b->acc_sph, b->eddington / eff);
+    }
+    /* hot halo */
+    halo_scales(w);
+    hh_profile(w);
+    if (w->hh_valid) {
+        const double t_hot = w->tvir; /* hotHaloTemperatureProfile virial */
+        double f_hot = 1.0;
+        r_acc = bhl_radius(b->mass, t_hot);
+        r_acc = fmin(r_acc, hh_outer_radius(w));
+        if (P->bondiHoyleAccretionHotModeOnly) {
+            const double xf = cooling_radius(w) / w->rvir;
+            if (xf < 0.9)
+                f_hot = 1.0;
+            else if (xf > 1.0)
+                f_hot = 0.0;
+            else {
+                const double x = (xf - 0.9) / (1.0 - 0.9);
+                f_hot = x * x * (2.0 * x - 3.0) + 1.0;
+            }
+        }
+        rho = f_hot * hh_density(w, r_acc);
+        if (rho > density_gas_minimum) {
+            double rate_max, eff;
+            b->acc_hot = fmax(P->bondiHoyleAccretionEnhancementHotHalo * bhl_rate(b->mass, rho, velocity, t_hot, 1, r_acc), 0.0);
+            rate_max = fmax(w->p[GLC_P_HH_MASS] / (hh_outer_radius(w) / ideal_gas_sound_speed(t_hot) * ORC_MPC_PER_KMS_TO_GYR), 0.0);
+            b->acc_hot = fmin(b->acc_hot, rate_max);
+            eff = disk_efficiency_radiative(w, b, b->acc_hot);
+            if (eff > 0.0) b->acc_hot = fmin(b->acc_hot, b->eddington / eff);
+        }
+    }
+    b->acc = b->acc_sph + b->acc_hot;
+}
+static double bh_wind_power(std_work *w, const bh_state *b) {
+    /* blackHoleWindCiotti2009::power, black_holes/winds/Ciotti2009.F90:153-246 */
+    const glc_params *P = w->P;
+    const double velocity_wind = 1.0e4, temperature_ism = 1.0e4;
+    double eff = P->bhEfficiencyWind, coupled = 0.0, mgas, rs;
+    if (P->bhEfficiencyWindScalesWithEfficiencyRadiative) eff = eff * disk_efficiency_radiative(w, b, b->acc);
+    if (b->acc <= 0.0 || eff <= 0.0) return 0.0;
+    mgas = has(w, GLC_F_HAS_SPHEROID) ? w->p[GLC_P_SPH_MASS_GAS] : 0.0;
+    if (mgas > 0.0) {
+        rs = w->p[GLC_P_SPH_RADIUS];
+        if (rs > 0.0) {
+            const double c2 = ORC_SPEED_LIGHT * ORC_SPEED_LIGHT;
+            double p_wind = eff * b->acc * ORC_MASS_SOLAR / ORC_GIGAYEAR * c2 / 4.0 / ORC_PI / velocity_wind / ORC_KILO /
+                            (rs * rs) / (ORC_MEGAPARSEC * ORC_MEGAPARSEC);
+            double p_ism = 3.0 / 4.0 / ORC_PI * mgas * ORC_MASS_SOLAR / (rs * rs * rs) /
+                           (ORC_MEGAPARSEC * ORC_MEGAPARSEC * ORC_MEGAPARSEC) / ORC_MASS_HYDROGEN_ATOM * 3.0 / 2.0 *
+                           ORC_BOLTZMANN * temperature_ism;
+            double x = p_ism / p_wind - 0.50;
+            if (x <= 0.0)
+                coupled = 0.0;
+            else if (x >= 1.0)
+                coupled = 1.0;
+            else
+                coupled = 3.0 * (x * x) - 2.0 * (x * x * x);
+        }
+    }
+    eff = eff * coupled;
+    return eff * b->acc * (ORC_SPEED_LIGHT * ORC_SPEED_LIGHT) / (ORC_KILO * ORC_KILO);
+}
+
 /* ------------------------------------------------------------ rate plumbing */
 typedef struct {
     double *rate;
@@ -991,7 +1241,11 @@ void orc_std_scales(orc_evolve_ctx *c, double *s) {
             s[GLC_P_HH_STRIPPED_MASS] = s[GLC_P_HH_STRIPPED_ABUND] = 1.0;
     }
     if (c->flags & GLC_F_HAS_BH) {
-        s[GLC_P_BH_MASS] = 1.0;
+        /* Node_Component_Black_Hole_Standard_Scale_Set, black_hole/standard/_class.F90:193-257 (no nuclear star
+           cluster: massStellar = spheroid stellar mass if positive, else 0) */
+        double mstar = (c->flags & GLC_F_HAS_SPHEROID) ? p[GLC_P_SPH_MASS_STELLAR] : 0.0;
+        if (!(mstar > 0.0)) mstar = 0.0;
+        s[GLC_P_BH_MASS] = fmax(fmax(1.0, 1.0e-4 * mstar), p[GLC_P_BH_MASS]);
         s[GLC_P_BH_SPIN] = 1.0;
     }
 }
@@ -1002,6 +1256,7 @@ int orc_std_rates(orc_evolve_ctx *c, double time, double *rate) {
     const glc_params *P = c->P;
     const double *p = c->p;
     double dlnrho_dt;
+    bh_state bh;
     work_init(&w, c, time);
     rcs.rate = rate;
     rcs.interrupt = GLC_INT_NONE;
@@ -1080,6 +1335,55 @@ int orc_std_rates(orc_evolve_ctx *c, double time, double *rate) {
         }
     }
 
+    /* blackHolesSeed: black_holes/seed.F90:153-182 (blackHoleSeeds fixed): create the seed by interrupt */
+    if ((P->operatorMask & GLC_OP_BLACK_HOLES_SEED) && !has(&w, GLC_F_HAS_BH) && P->bhSeedMass > 0.0)
+        rcs.interrupt = GLC_INT_BH_CREATE;
+    bh_accretion(&w, &bh);
+    /* blackHolesAccretion: black_holes/accretion.F90:113-173 */
+    if ((P->operatorMask & GLC_OP_BLACK_HOLES_ACCRETION) && has(&w, GLC_F_HAS_BH) && bh.on && bh.acc > 0.0) {
+        const double eff_rad = disk_efficiency_radiative(&w, &bh, bh.acc);
+        const double eff_jet = disk_power_jet(&w, &bh, bh.acc) / bh.acc / (ORC_SPEED_LIGHT * ORC_SPEED_LIGHT) / (ORC_KILO * ORC_KILO);
+        const double reduced = bh.acc * (1.0 - eff_rad - eff_jet);
+        const double spin_up = disk_rate_spin_up(&w, &bh, bh.acc);
+        rate[GLC_P_BH_MASS] += reduced;
+        /* Node_Component_Spheroid_Standard_Mass_Gas_Sink_Rate, spheroid/standard/_class.F90:638-671 */
+        if (has(&w, GLC_F_HAS_SPHEROID) && -bh.acc_sph != 0.0) {
+            const double mg = p[GLC_P_SPH_MASS_GAS], ms = p[GLC_P_SPH_MASS_STELLAR], r = -bh.acc_sph;
+            if (mg > 0.0 && mg + ms > 0.0) {
+                SP(GLC_P_SPH_MASS_GAS, r);
+                SP(GLC_P_SPH_ANGMOM, (r / (mg + ms)) * p[GLC_P_SPH_ANGMOM]);
+                SP(GLC_P_SPH_ABUND_GAS, (r / mg) * p[GLC_P_SPH_ABUND_GAS]);
+            }
+        }
+        /* Node_Component_Hot_Halo_Standard_Mass_Sink -> Hot_Gas_All_Rate, hot_halo/standard/_class.F90:749-800 */
+        if (has(&w, GLC_F_HAS_HOTHALO) && -bh.acc_hot != 0.0) {
+            const double mg = p[GLC_P_HH_MASS], r = -bh.acc_hot;
+            if (mg > 0.0) {
+                HH(GLC_P_HH_MASS, r);
+                HH(GLC_P_HH_ANGMOM, p[GLC_P_HH_ANGMOM] * (r / mg));
+                HH(GLC_P_HH_ABUND, p[GLC_P_HH_ABUND] * (r / mg));
+            }
+        }
+        rate[GLC_P_BH_SPIN] += spin_up;
+    }
+    /* blackHolesWinds: black_holes/winds.F90:103-134 -> Node_Component_Spheroid_Standard_Energy_Gas_Input_Rate,
+       spheroid/standard/_class.F90:673-725 */
+    if ((P->operatorMask & GLC_OP_BLACK_HOLES_WINDS) && has(&w, GLC_F_HAS_BH) && bh.on) {
+        const double power = bh_wind_power(&w, &bh);
+        if (power != 0.0 && has(&w, GLC_F_HAS_SPHEROID)) {
+            const double mg = p[GLC_P_SPH_MASS_GAS], ms = p[GLC_P_SPH_MASS_STELLAR], vs = p[GLC_P_SPH_VELOCITY];
+            if (mg > 0.0 && mg + ms > 0.0 && vs > 0.0) {
+                const double out = P->spheroidEfficiencyEnergeticOutflow * power / (vs * vs);
+                const double jout = (out / (mg + ms)) * p[GLC_P_SPH_ANGMOM];
+                const double zout = (out / mg) * p[GLC_P_SPH_ABUND_GAS];
+                SP(GLC_P_SPH_MASS_GAS, -out);
+                SP(GLC_P_SPH_ANGMOM, -jout);
+                SP(GLC_P_SPH_ABUND_GAS, -zout);
+                hh_outflowing(rc, out, jout, zout);
+            }
+        }
+    }
+
     /* CGMAccretion: circumgalactic_medium/accretion.F90:517-593 with accretionHaloSimple
        (accretion/halo/simple.F90:281-378,592-613); IGM metallicity zero */
     if (P->operatorMask & GLC_OP_CGM_ACCRETION) {
@@ -1120,7 +1424,9 @@ int orc_std_rates(orc_evolve_ctx *c, double time, double *rate) {
     if ((P->operatorMask & GLC_OP_CGM_COOLING_HEATING) && has(&w, GLC_F_HAS_HOTHALO) && p[GLC_P_HH_MASS] > 0.0 &&
         !(p[GLC_P_HH_ANGMOM] <= 0.0 || hh_outer_radius(&w) <= 0.0)) {
         double cool = cooling_rate(&w);
-        double heat = 0.0 / (w.vvir * w.vvir); /* circumgalacticMediumHeatingAGNFeedback: no black holes yet */
+        /* circumgalacticMediumHeatingAGNFeedback (circumgalactic_medium/heating/AGN_feedback.F90:103-126) over
+           blackHoleCGMHeatingJetPower (black_holes/CGM_heating/jet_power.F90:120-138) */
+        double heat = ((bh.on ? P->bhEfficiencyRadioMode * disk_power_jet(&w, &bh, bh.acc) : 0.0)) / (w.vvir * w.vvir);
         if (heat > cool) {
             if (P->excessHeatDrivesOutflow) {
                 double out = fmin(heat - cool, P->rateMaximumExpulsion * p[GLC_P_HH_MASS] / w.tdyn);
@@ -1251,6 +1557,17 @@ void orc_std_post_step(orc_evolve_ctx *c, int *status) {
             if (*status == ORC_GSL_SUCCESS) *status = ORC_GSL_CONTINUE;
         }
     }
+    /* Node_Component_Black_Hole_Standard_Post_Evolve, black_hole/standard/_class.F90:422-462 */
+    if (c->flags & GLC_F_HAS_BH) {
+        if (p[GLC_P_BH_SPIN] > 0.9999 || p[GLC_P_BH_SPIN] < 0.0) {
+            p[GLC_P_BH_SPIN] = fmax(fmin(p[GLC_P_BH_SPIN], 0.9999), 0.0);
+            if (*status == ORC_GSL_SUCCESS) *status = ORC_GSL_CONTINUE;
+        }
+        if (p[GLC_P_BH_MASS] < 0.0) {
+            p[GLC_P_BH_MASS] = c->P->bhSeedMass;
+            if (*status == ORC_GSL_SUCCESS) *status = ORC_GSL_CONTINUE;
+        }
+    }
 }
 
 void orc_std_post_evolve(orc_evolve_ctx *c) {
@@ -1293,4 +1610,21 @@ void orc_probe_node(const glc_params *P, const orc_tables *T, double *props, int
     out[13] = has(&w, GLC_F_HAS_HOTHALO) && props[GLC_P_HH_MASS] > 0 ? cooling_radius(&w) : 0.0;
     out[14] = sqrt(ORC_G_INTERNAL * out[7] / r0 + out[6]);
     out[15] = dm_log(out[14] / r0);
+}
+
+/* known-answer access to the black-hole helper functions (tests/test_oracle_black_holes.py):
+ * out[0..3] = ISCO radius, specific energy, specific angular momentum (gravitational units, prograde), Eddington
+ * accretion rate (Msun/Gyr); out[4] = Bondi-Hoyle-Lyttleton radius (Mpc) and out[5] = rate (Msun/Gyr) for unit
+ * density (1 Msun/Mpc^3) at `temperature`; out[6] = ideal-gas sound speed (km/s); out[7] = Jeans length at unit density */
+void orc_bh_probe(double mass, double spin, double temperature, double *out) {
+    const double r = bh_isco_radius(spin);
+    out[0] = r;
+    out[1] = bh_isco_energy(spin, r);
+    out[2] = bh_isco_angular_momentum(spin, r);
+    out[3] = 4.0 * ORC_PI * ORC_GRAVITATIONAL_CONSTANT * mass * ORC_MASS_HYDROGEN_ATOM * ORC_GIGAYEAR /
+             ORC_THOMSON_CROSS_SECTION / ORC_SPEED_LIGHT;
+    out[4] = bhl_radius(mass, temperature);
+    out[5] = bhl_rate(mass, 1.0, 0.0, temperature, 0, 0.0);
+    out[6] = ideal_gas_sound_speed(temperature);
+    out[7] = ideal_gas_sound_speed(temperature) / sqrt(ORC_G_INTERNAL) / sqrt(1.0);
 }

@@ -6,6 +6,8 @@
 #include "orc_node.h"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "../galacticus_b200/csrc/glc_detmath.h"
 #include <stdlib.h>
@@ -40,7 +42,14 @@ static int standard_odes(double time, const double *y, double *dydt, void *vctx)
     if (code == GLC_INT_NONE) {
         for (i = 0; i < c->n_active; i++) {
             dydt[i] = rate[c->active[i]];
-            if (!isfinite(dydt[i])) c->nonfinite = 1;
+            if (!isfinite(dydt[i])) {
+                if (getenv("ORC_DEBUG_NAN") && !c->nonfinite) {
+                    int k;
+                    fprintf(stderr, "[orc] non-finite rate of property %d at t=%.17g\n", c->active[i], time);
+                    for (k = 0; k < GLC_NPROP; k++) fprintf(stderr, "  p[%d]=%.17g rate=%g\n", k, c->p[k], k < GLC_NY ? rate[k] : 0.0);
+                }
+                c->nonfinite = 1;
+            }
         }
         return ORC_GSL_SUCCESS;
     }

@@ -85,7 +85,8 @@ def smoke_case(model_name):
 
 
 def standard_params(orc_or_none=None, with_black_holes=False):
-    """quickTest.xml operator set (black-hole operators gated until they are restated)."""
+    """quickTest.xml operator set; with_black_holes=False masks blackHolesSeed/Accretion/Winds (the reduced set the
+    first golden vectors were made with), True is the full <nodeOperator value="multi"> list of quickTest.xml."""
     from galacticus_b200 import synthetic
 
     if orc_or_none is not None:
@@ -98,6 +99,16 @@ def standard_params(orc_or_none=None, with_black_holes=False):
         p.operatorMask = abi.GLC_OP_ALL & ~(abi.GLC_OP_BLACK_HOLES_SEED | abi.GLC_OP_BLACK_HOLES_ACCRETION
                                             | abi.GLC_OP_BLACK_HOLES_WINDS)
     return synthetic.finalize_params(p)
+
+
+BH_FRACTION = 0.7  # share of the synthetic nodes that start with a black hole; the others get the seed by interrupt
+
+
+def standard_bh_nodes(p, n, seed, **kw):
+    """Node records for the full operator set: black-hole masses from the seed to 1e9.5 Msun, spins over [0, 0.9999]."""
+    from galacticus_b200 import synthetic
+
+    return synthetic.standard_nodes(p, n, seed=seed, black_hole_fraction=BH_FRACTION, **kw)
 
 
 def y_scale(props):

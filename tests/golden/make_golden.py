@@ -39,6 +39,10 @@ def main():
     p = cases.standard_params()
     props, flags, t_end = synthetic.standard_nodes(p, 96, seed=4242)
     run("standard_96", p, props, flags, t_end, True)
+    # full quickTest operator list (black-hole seed / accretion / winds, jet-power heating of the CGM)
+    p = cases.standard_params(with_black_holes=True)
+    props, flags, t_end = cases.standard_bh_nodes(p, 96, seed=4244)
+    run("standard_bh_96", p, props, flags, t_end, True)
     from galacticus_b200.evolver import params_default
 
     pb = params_default(abi.GLC_MODEL_BOX)

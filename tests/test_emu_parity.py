@@ -47,6 +47,47 @@ def test_standard_lane_logic_is_bit_identical_to_oracle(oracle_lib, nslots, budg
         assert e.slices > 1  # the time-slice / park / resume path was exercised
 
 
+@pytest.mark.parametrize("nslots,budget,sort,machine", [
+    (64, 0, True, False),
+    (96, 7, True, True),
+    (40, 0, True, 2),
+    (130, 13, False, 2),
+])
+def test_black_hole_chain_lane_logic_is_bit_identical_to_oracle(oracle_lib, nslots, budget, sort, machine):
+    """Full quickTest operator list: blackHolesSeed (creation interrupt), blackHolesAccretion (Bondi-Hoyle-Lyttleton rates
+    from spheroid gas and hot halo, switched thin-disk/ADAF efficiencies, spin-up), blackHolesWinds (Ciotti 2009) and the
+    jet-power heating term of CGMCoolingHeating -- SURVEY 8a a19."""
+    p = cases.standard_params(with_black_holes=True)
+    e, o = _both(oracle_lib, p, nslots, budget, sort, machine=machine)
+    props, flags, t_end = cases.standard_bh_nodes(p, 1500, seed=303)
+    pe, fe = props.copy(), flags.copy()
+    po, fo = props.copy(), flags.copy()
+    se, ie, ce = e.evolve_batch(pe, fe, t_end)
+    so, io, co = o.evolve_batch(po, fo, t_end, n_threads=8)
+    np.testing.assert_array_equal(se, so)
+    np.testing.assert_array_equal(ie, io)
+    np.testing.assert_array_equal(fe, fo)
+    assert ce == co
+    assert np.array_equal(pe, po), "records not bit-identical"
+    assert (so == 0).all() and ((fo & abi.GLC_F_HAS_BH) != 0).all()
+    grown = po[:, P["BH_MASS"]] > 1.01 * np.maximum(props[:, P["BH_MASS"]], 100.0)
+    assert grown.mean() > 0.05  # accretion did something
+
+
+def test_black_hole_seed_interrupt_returned_to_host(oracle_lib):
+    p = cases.standard_params(with_black_holes=True)
+    p.resolveInterruptsOnDevice = 0
+    e, o = _both(oracle_lib, p, 64, 11, True)
+    props, flags, t_end = cases.standard_bh_nodes(p, 500, seed=12)
+    pe, fe = props.copy(), flags.copy()
+    po, fo = props.copy(), flags.copy()
+    se, ie, ce = e.evolve_batch(pe, fe, t_end)
+    so, io, co = o.evolve_batch(po, fo, t_end, n_threads=8)
+    assert (io == abi.GLC_INT_BH_CREATE).any()
+    np.testing.assert_array_equal(ie, io)
+    assert ce == co and np.array_equal(pe, po)
+
+
 def test_standard_interrupts_returned_to_host(oracle_lib):
     p = cases.standard_params()
     p.resolveInterruptsOnDevice = 0

@@ -15,7 +15,7 @@ HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def _case(name):
     g = np.load(os.path.join(HERE, name + ".npz"))
     if name.startswith("standard"):
-        p = cases.standard_params()
+        p = cases.standard_params(with_black_holes="_bh_" in name)
         tables = True
     else:
         from galacticus_b200.evolver import params_default
@@ -36,7 +36,7 @@ def _check(g, props, flags, status, interrupt, counters):
     assert counters == want
 
 
-@pytest.mark.parametrize("name", ["standard_96", "box_leaky_96"])
+@pytest.mark.parametrize("name", ["standard_96", "standard_bh_96", "box_leaky_96"])
 def test_oracle_reproduces_golden(oracle_lib, name):
     g, p, tables = _case(name)
     o = oracle_lib.Oracle()
@@ -46,7 +46,7 @@ def test_oracle_reproduces_golden(oracle_lib, name):
     _check(g, props, flags, s, i, c)
 
 
-@pytest.mark.parametrize("name", ["standard_96", "box_leaky_96"])
+@pytest.mark.parametrize("name", ["standard_96", "standard_bh_96", "box_leaky_96"])
 def test_kernel_source_on_host_reproduces_golden(name):
     from tests import emu
 
@@ -59,7 +59,7 @@ def test_kernel_source_on_host_reproduces_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["standard_96", "box_leaky_96"])
+@pytest.mark.parametrize("name", ["standard_96", "standard_bh_96", "box_leaky_96"])
 def test_cuda_reproduces_golden(name):
     from galacticus_b200.evolver import Evolver
 

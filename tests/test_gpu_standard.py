@@ -10,10 +10,10 @@ P = abi.P
 RTOL = 1.0e-6  # north_star tolerance on per-galaxy properties
 
 
-def make(orc, **kw):
+def make(orc, with_black_holes=False, **kw):
     from galacticus_b200.evolver import Evolver
 
-    p = cases.standard_params()
+    p = cases.standard_params(with_black_holes=with_black_holes)
     for k, v in kw.items():
         setattr(p, k, v)
     ev = Evolver(0)
@@ -53,6 +53,63 @@ def test_rhs_parity(oracle_lib):
     assert np.array_equal(dg, do), f"dydt not bit-identical in {(dg != do).sum()} entries"
     for k in ("DISK_RADIUS", "DISK_VELOCITY", "SPH_RADIUS", "SPH_VELOCITY"):
         assert np.array_equal(pg[:, P[k]], po[:, P[k]]), k
+
+
+def test_rhs_parity_black_holes(oracle_lib):
+    """One evaluation with the full operator list (Bondi-Hoyle-Lyttleton accretion, switched thin-disk /
+    ADAF efficiencies and spin-up, Ciotti 2009 winds, jet-power heating, seed interrupt)."""
+    ev, o, p = make(oracle_lib, with_black_holes=True)
+    props, flags, _ = cases.standard_bh_nodes(p, 3000, seed=6, fresh_fraction=0.0)
+    dg, ig, pg = ev.rhs_batch(props, flags)
+    do = np.zeros_like(dg)
+    io = np.zeros_like(ig)
+    for i in range(props.shape[0]):
+        do[i], io[i], _ = o.rhs(props[i], flags[i])
+    np.testing.assert_array_equal(ig, io)
+    assert (io == abi.GLC_INT_BH_CREATE).any() and (do[:, P["BH_MASS"]] != 0).any()
+    assert np.array_equal(dg, do), f"dydt not bit-identical in {(dg != do).sum()} entries"
+
+
+@pytest.mark.parametrize("n", [37, 3000, 20000])
+def test_evolve_parity_black_holes(oracle_lib, n):
+    ev, o, p = make(oracle_lib, with_black_holes=True)
+    props, flags, t_end = cases.standard_bh_nodes(p, n, seed=200 + n)
+    pg, fg = props.copy(), flags.copy()
+    po, fo = props.copy(), flags.copy()
+    sg, ig, cg = ev.evolve_batch(pg, fg, t_end)
+    so, io, co = o.evolve_batch(po, fo, t_end, n_threads=8)
+    compare(pg, po, fg, fo, sg, so, ig, io, f"black holes n={n}")
+    assert cg == co
+    assert ((fg & abi.GLC_F_HAS_BH) != 0).all()
+
+
+def test_black_hole_seed_interrupt_returned_to_host(oracle_lib):
+    """resolveInterruptsOnDevice=0: blackHoleCreate comes back to the host, which seeds mass and spin
+    (black_holes/seed.F90:184-206) and re-submits; same result as the on-device resolution."""
+    ev, o, p = make(oracle_lib, with_black_holes=True, resolveInterruptsOnDevice=0)
+    ev2, _, _ = make(oracle_lib, with_black_holes=True)
+    props, flags, t_end = cases.standard_bh_nodes(p, 1200, seed=19)
+    p_ref, f_ref = props.copy(), flags.copy()
+    ev2.evolve_batch(p_ref, f_ref, t_end)
+    ph, fh = props.copy(), flags.copy()
+    pending = np.arange(props.shape[0])
+    rounds, saw = 0, False
+    while pending.size and rounds < 16:
+        sub_p, sub_f = ph[pending].copy(), fh[pending].copy()
+        s, i, _ = ev.evolve_batch(sub_p, sub_f, t_end[pending])
+        assert (s == 0).all()
+        saw |= bool((i == abi.GLC_INT_BH_CREATE).any())
+        for code, bit in ((abi.GLC_INT_HOTHALO_CREATE, abi.GLC_F_HAS_HOTHALO), (abi.GLC_INT_DISK_CREATE, abi.GLC_F_HAS_DISK),
+                          (abi.GLC_INT_SPHEROID_CREATE, abi.GLC_F_HAS_SPHEROID), (abi.GLC_INT_BH_CREATE, abi.GLC_F_HAS_BH)):
+            sub_f[i == code] |= bit
+        sub_p[i == abi.GLC_INT_BH_CREATE, P["BH_MASS"]] = p.bhSeedMass
+        sub_p[i == abi.GLC_INT_BH_CREATE, P["BH_SPIN"]] = p.bhSeedSpin
+        ph[pending], fh[pending] = sub_p, sub_f
+        pending = pending[(i != 0) & (sub_p[:, P["TIME"]] < t_end[pending])]
+        rounds += 1
+    assert saw and pending.size == 0
+    np.testing.assert_array_equal(fh, f_ref)
+    assert np.array_equal(ph[:, :abi.NY], p_ref[:, :abi.NY])
 
 
 @pytest.mark.parametrize("n", [1, 37, 3000, 20000])
