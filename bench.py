@@ -44,6 +44,7 @@ UNIT = "accepted RKCK node-ODE steps/s"
 # machine_kernel divided by its RHS counter, ncu capture profiles/r01_machine_kernel_summary.txt)
 FLOP_PER_RHS = 7.8e3
 N_Y = 24
+BLACK_HOLE_FRACTION = 0.7
 
 
 def parse():
@@ -62,19 +63,17 @@ def workload(n, seed):
     from galacticus_b200 import abi, synthetic
     from galacticus_b200.evolver import params_default
 
-    p = params_default(abi.GLC_MODEL_STANDARD)
-    # black-hole operators are not restated yet: run the same reduced operator set on both sides
-    p.operatorMask = abi.GLC_OP_ALL & ~(abi.GLC_OP_BLACK_HOLES_SEED | abi.GLC_OP_BLACK_HOLES_ACCRETION
-                                        | abi.GLC_OP_BLACK_HOLES_WINDS)
+    p = params_default(abi.GLC_MODEL_STANDARD)  # operatorMask = GLC_OP_ALL: the full nodeOperator list of quickTest.xml
     synthetic.finalize_params(p)
-    props, flags, t_end = synthetic.standard_nodes(p, n, seed=seed)
+    props, flags, t_end = synthetic.standard_nodes(p, n, seed=seed, black_hole_fraction=BLACK_HOLE_FRACTION)
     return p, props, flags, t_end
 
 
 WORKLOAD_NAME = ("node-batch stand-in for testSuite benchmark-milkyWay (10^3 MW-mass trees ~ 10^6 node-evolve calls): "
                  "%d node records per GPU over the quickTest mass range (1e10-1e13 Msun), each evolved over its own "
-                 "0.05-0.8 Gyr interval; quickTest operator set without the black-hole operators, "
-                 "hotHaloRamPressureStripping=virialRadius, synthetic CIE tables")
+                 "0.05-0.8 Gyr interval; full quickTest nodeOperator list (incl. black-hole seed/accretion/winds and "
+                 "jet-power CGM heating; 70 % of the nodes start with a black hole, the others are seeded by interrupt), "
+                 "hotHaloRamPressureStripping=virialRadius, synthetic CIE and ADAF tables")
 
 
 class ClockSampler(threading.Thread):
