@@ -72,7 +72,7 @@ def workload(n, seed):
 WORKLOAD_NAME = ("node-batch stand-in for testSuite benchmark-milkyWay (10^3 MW-mass trees ~ 10^6 node-evolve calls): "
                  "%d node records per GPU over the quickTest mass range (1e10-1e13 Msun), each evolved over its own "
                  "0.05-0.8 Gyr interval; full quickTest nodeOperator list (incl. black-hole seed/accretion/winds and "
-                 "jet-power CGM heating; 70 % of the nodes start with a black hole, the others are seeded by interrupt), "
+                 "jet-power CGM heating; 70 percent of the nodes start with a black hole, the others are seeded by interrupt), "
                  "hotHaloRamPressureStripping=virialRadius, synthetic CIE and ADAF tables")
 
 

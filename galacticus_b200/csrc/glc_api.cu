@@ -11,6 +11,7 @@
 
 #include "glc_common.cuh"
 #include "glc_tables_host.h"
+#include "host/glc_forest.hpp"
 
 #include "glc_evolve_kernel.cuh"
 #include "glc_model_box.cuh"
@@ -39,6 +40,7 @@ struct glc_evolver {
     bool params_set = false;
     DeviceTables tables{};
     HostTable host_tables[GLC_NTABLES];
+    glcf::HaloTable halo_host;  // host copy of GLC_TABLE_HALO_MEAN_DENSITY for the forest scheduler
     // arena
     int64_t cap = 0;
     double *d_props = nullptr;
@@ -711,6 +713,7 @@ int glc_evolver_set_table(glc_evolver *ev, int32_t id, int32_t n0, int32_t n1, c
     t.n0 = n0;
     t.n1 = n1;
     install_table(ev->tables, id, pt, DeviceTable2D{n0, n1, t.d_x0, t.d_x1, t.d_v});
+    if (id == GLC_TABLE_HALO_MEAN_DENSITY) ev->halo_host.set(n0, x0, values);
     return 0;
 }
 
@@ -1102,3 +1105,59 @@ int glc_histogram_accumulate(glc_evolver *ev, int64_t n, int32_t prop, double lo
 int glc_params_default(glc_params *P, int32_t model);  // defined in glc_params.cpp
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- forest interface (host/glc_forest.hpp)
+int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, const double *mass, const double *time,
+                      const double *scale_radius, const double *angular_momentum, double *records, int32_t *flags,
+                      int32_t *state, glc_forest_counters *forest_counters, glc_counters *counters) {
+    if (!ev || n_nodes < 1 || !parent || !mass || !time || !scale_radius || !angular_momentum || !records || !flags || !state)
+        return -1;
+    if (!ev->params_set || ev->params.model != GLC_MODEL_STANDARD || !ev->params.resolveInterruptsOnDevice) {
+        ev->err = "glc_forest_evolve needs the standard model with resolveInterruptsOnDevice = 1";
+        return -9;
+    }
+    if (ev->halo_host.n0 < 2) {
+        ev->err = "glc_forest_evolve needs GLC_TABLE_HALO_MEAN_DENSITY";
+        return -9;
+    }
+    for (int64_t i = 0; i < n_nodes; i++)
+        if (parent[i] >= n_nodes || parent[i] == i) return -1;
+    glcf::Forest F;
+    F.init(&ev->params, &ev->halo_host, n_nodes, parent, mass, time, scale_radius, angular_momentum, records, flags, state);
+    glc_counters total{};
+    std::vector<double> buf, tend;
+    std::vector<int32_t> bflags, status, interrupt;
+    auto evolve = [&](const std::vector<int32_t> &list, const std::vector<double> &te) -> int {
+        const int64_t m = (int64_t)list.size();
+        buf.resize((size_t)m * GLC_NPROP);
+        bflags.resize(m);
+        status.resize(m);
+        interrupt.resize(m);
+        for (int64_t k = 0; k < m; k++) {
+            memcpy(&buf[(size_t)k * GLC_NPROP], F.R(list[k]), sizeof(double) * GLC_NPROP);
+            bflags[k] = flags[list[k]];
+        }
+        glc_counters c{};
+        int rc = glc_evolve_batch(ev, m, buf.data(), bflags.data(), te.data(), status.data(), interrupt.data(), &c);
+        if (rc) return rc;
+        for (int64_t k = 0; k < m; k++) {
+            if (status[k] != GLC_STATUS_SUCCESS || interrupt[k] != GLC_INT_NONE) {
+                ev->err = "glc_forest_evolve: a node evolve did not complete (status / unresolved interrupt)";
+                return -10;
+            }
+            memcpy(F.R(list[k]), &buf[(size_t)k * GLC_NPROP], sizeof(double) * GLC_NPROP);
+            flags[list[k]] = bflags[k];
+        }
+        total.steps_accepted += c.steps_accepted;
+        total.steps_rejected += c.steps_rejected;
+        total.rhs_evaluations += c.rhs_evaluations;
+        total.segments += c.segments;
+        total.trials_failed += c.trials_failed;
+        total.nodes += c.nodes;
+        return 0;
+    };
+    const int rc = F.run(evolve);
+    if (forest_counters) *forest_counters = F.fc;
+    if (counters) *counters = total;
+    return rc;
+}

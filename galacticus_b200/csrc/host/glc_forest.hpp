@@ -1,0 +1,372 @@
+// glc_forest.hpp -- host side of the path: the batching tree evolver ("mergerTreeEvolverB200").
+//
+// replaces: the tree walk of mergerTreeEvolverStandard::evolve (source/merger_trees/evolver/standard.F90:291-635) over a
+// SET of forests, which hands one node at a time to mergerTreeNodeEvolver%evolve (:452).  Here every round gathers all
+// nodes that the reference's rules allow to move (standardNodeIsEvolvable :723-760, standardTimeEvolveTo :762-1035)
+// and evolves them in one call of the batched node evolver; promotions and node mergers (node_evolver/standard.F90:
+// 1241-1356) and the node-operator hooks that go with them are bookkeeping on the host.  Citations are relative to
+// /root/reference/source.
+//
+// The evolve call-back is a template parameter: the product (glc_forest.cpp) passes glc_evolve_batch (CUDA); the
+// CPU-only test harness (tests/emu, test infrastructure) passes the host-driven kernel source.
+//
+// Rules restated (and what is left out):
+//   * a node moves only when it has no children left (:741) and, if it is not a satellite, at most to its parent's time
+//     (:905-914); every call is also capped by mergerTreeEvolveTimestepSimple (evolve/timesteps/simple.F90:
+//     min(timeStepRelative/H(t), timeStepAbsolute)) and by the final time of its tree;
+//   * a satellite may not pass its host while the host still has a child (:927-941), otherwise it may lead the host by
+//     timeStepHost = min(timestepHostRelative/H(t_host), timestepHostAbsolute) (:942-968);
+//   * a host may not pass any of its satellites (:1003-1030);
+//   * a non-primary progenitor that reaches its parent's time becomes a satellite of the parent at once (standardMerge,
+//     mergerTreeNodeMergerSingleLevelHierarchy: its own satellites are re-hosted too); the primary progenitor is promoted
+//     when it has reached the parent's time and all its siblings have merged (:1241-1327);
+//   * hooks: nodeOperatorDMOInterpolate (dark_matter_only_mass/interpolate.F90:84-291), the scale-radius and
+//     angular-momentum interpolators (same scheme), nodeOperatorCGMAccretion nodeInitialize / nodePromote / nodesMerge
+//     (circumgalactic_medium/accretion.F90:144-426) with accretionHaloSimple.
+//   Satellites move before their hosts in every round (the reference's walk visits a node's satellites first), sums over
+//   satellites run in ascending node index.  Not restated: the "primary may not lead its siblings" cap (:984-1000; it only
+//   changes where the primary waits), satellite merging times / galaxy mergers (satellites live to the end of
+//   the tree), tree and node events.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../../include/glc_b200.h"
+#include "../glc_detmath.h"
+
+namespace glcf {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kGInternal = 6.673e-11 * 1.98892e30 / (1.0e3 * 1.0e3) / (1.0e6 * 3.08567758135e16);
+constexpr double kMpcPerKmPerSToGyr = (1.0e6 * 3.08567758135e16) / 1.0e3 / (1.0e9 * 3.15581497635456e7);
+
+enum NodeState : int32_t {
+    NS_PENDING = GLC_FOREST_NODE_PENDING,     // still has children (a future halo of the tree)
+    NS_ACTIVE = GLC_FOREST_NODE_ISOLATED,     // childless, not a satellite: being evolved towards its parent
+    NS_SATELLITE = GLC_FOREST_NODE_SATELLITE, // hosted by another node
+    NS_DONE = GLC_FOREST_NODE_PROMOTED        // promoted into its parent (destroyed)
+};
+
+struct HaloTable {  // GLC_TABLE_HALO_MEAN_DENSITY as uploaded (times, {rho_mean, dln rho/dt})
+    int n0 = 0;
+    std::vector<double> lnt, v;
+    double lnt0 = 0.0, inv_dlnt = 0.0;
+    void set(int n, const double *t, const double *values) {
+        n0 = n;
+        lnt.resize(n);
+        for (int i = 0; i < n; i++) lnt[i] = dm_log(t[i]);
+        v.assign(values, values + 2 * (size_t)n);
+        lnt0 = lnt[0];
+        inv_dlnt = (double)(n - 1) / (lnt[n - 1] - lnt[0]);
+    }
+    // virialDensityContrastDefinition: dark_matter_halos/scales/virial_density_contrast.F90:195-417 (same look-up as
+    // the device's halo_scales)
+    double virial_velocity(double mass, double time) const {
+        const double lt = dm_log(time);
+        const double x = (lt - lnt0) * inv_dlnt;
+        int i = (int)x;
+        if (lt < lnt0) i = 0;
+        i = std::max(std::min(i, n0 - 2), 0);
+        const double h = x - (double)i;
+        const double rho = v[2 * i] * (1.0 - h) + v[2 * (i + 1)] * h;
+        const double rvir = dm_cbrt(3.0 * mass / 4.0 / kPi / rho);
+        return sqrt(kGInternal * mass / rvir);
+    }
+};
+
+struct Forest {
+    const glc_params *P = nullptr;
+    const HaloTable *halo = nullptr;
+    int64_t n = 0;
+    const int32_t *parent = nullptr;
+    const double *mass = nullptr, *time = nullptr, *scale = nullptr, *angmom = nullptr;
+    double *rec = nullptr;     // [n][GLC_NPROP]
+    int32_t *flags = nullptr;  // [n]
+    int32_t *state = nullptr;  // [n] NodeState
+    std::vector<int32_t> first_child, sibling, host, children_left, root_of;
+    std::vector<std::vector<int32_t>> sats;  // ascending node index
+    std::vector<double> time_end;            // per node: final time of its tree
+    glc_forest_counters fc{};
+
+    double *R(int64_t i) const { return rec + i * GLC_NPROP; }
+
+    // cosmologyFunctionsMatterLambda in closed form (flat): H(t) = H0 sqrt(OL) coth(1.5 sqrt(OL) H0 t)
+    double expansion_timescale(double t) const {
+        const double OL = 1.0 - P->OmegaMatter;
+        const double H0 = P->HubbleConstant / kMpcPerKmPerSToGyr;
+        const double e = dm_exp(2.0 * (1.5 * sqrt(OL) * H0 * t));
+        return 1.0 / (H0 * sqrt(OL) * ((e + 1.0) / (e - 1.0)));
+    }
+    double timestep(double t) const {  // simple.F90 and evolver/standard.F90:945-958 (same numbers in quickTest.xml)
+        return std::min(0.1 * expansion_timescale(t), 1.0);
+    }
+    double failed_fraction(double m, double t) const {  // accretion/halo/simple.F90: simpleFailedFraction
+        return (t > P->timeReionization && halo->virial_velocity(m, t) < P->velocitySuppressionReionization) ? 1.0 : 0.0;
+    }
+    bool is_primary(int32_t i) const { return parent[i] >= 0 && first_child[parent[i]] == i; }
+    double node_time(int32_t i) const { return state[i] == NS_PENDING ? time[i] : R(i)[GLC_P_TIME]; }
+
+    // interpolation targets of node i towards `p` (its parent in the tree), nodeOperator{DMO,darkMatterProfileScale,
+    // haloAngularMomentum}Interpolate::nodeInitialize
+    void set_targets(int32_t i, double *r) const {
+        const int32_t p = parent[i];
+        r[GLC_P_MASS_TARGET] = mass[i];
+        r[GLC_P_MASS_RATE] = 0.0;
+        r[GLC_P_TIME_TARGET] = time[i];
+        r[GLC_P_DMSCALE_TARGET] = scale[i];
+        r[GLC_P_DMSCALE_RATE] = 0.0;
+        r[GLC_P_SPIN_TARGET] = angmom[i];
+        r[GLC_P_SPIN_RATE] = 0.0;
+        if (p < 0) return;
+        double unresolved = mass[p];
+        for (int32_t c = first_child[p]; c >= 0; c = sibling[c]) unresolved = unresolved - mass[c];
+        const double dt = time[p] - time[i];
+        r[GLC_P_TIME_TARGET] = time[p];
+        if (unresolved > 0.0) {
+            if (is_primary(i)) {
+                if (dt > 0.0) r[GLC_P_MASS_RATE] = unresolved / dt;
+                r[GLC_P_MASS_TARGET] = mass[i] + unresolved;
+            }
+        } else {
+            const double total = mass[p] - unresolved;
+            if (dt > 0.0) r[GLC_P_MASS_RATE] = (unresolved / dt) * (mass[i] / total);
+            r[GLC_P_MASS_TARGET] = mass[i] + unresolved * mass[i] / total;
+        }
+        if (is_primary(i) && dt > 0.0) {
+            r[GLC_P_DMSCALE_TARGET] = scale[p];
+            r[GLC_P_DMSCALE_RATE] = (scale[p] - scale[i]) / dt;
+            r[GLC_P_SPIN_TARGET] = angmom[p];
+            r[GLC_P_SPIN_RATE] = (angmom[p] - angmom[i]) / dt;
+        }
+    }
+
+    void init(const glc_params *params, const HaloTable *h, int64_t n_nodes, const int32_t *par, const double *m, const double *t,
+              const double *s, const double *j, double *records, int32_t *fl, int32_t *st) {
+        P = params; halo = h; n = n_nodes; parent = par; mass = m; time = t; scale = s; angmom = j;
+        rec = records; flags = fl; state = st;
+        first_child.assign(n, -1); sibling.assign(n, -1); host.assign(n, -1); children_left.assign(n, 0);
+        root_of.assign(n, -1); sats.assign(n, {}); time_end.assign(n, 0.0);
+        memset(&fc, 0, sizeof(fc));
+        // children ordered by descending mass (ties: ascending index); the first one is the primary progenitor
+        std::vector<int32_t> order(n);
+        for (int64_t i = 0; i < n; i++) order[i] = (int32_t)i;
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return mass[a] > mass[b]; });
+        for (auto it = order.rbegin(); it != order.rend(); ++it) {  // pushed at the front in reverse => descending lists
+            const int32_t i = *it;
+            const int32_t p = parent[i];
+            if (p < 0) continue;
+            sibling[i] = first_child[p];
+            first_child[p] = i;
+            children_left[p]++;
+        }
+        for (int64_t i = 0; i < n; i++) {
+            int32_t r = (int32_t)i;
+            while (parent[r] >= 0) r = parent[r];
+            root_of[i] = r;
+            time_end[i] = time[r];
+        }
+        memset(rec, 0, sizeof(double) * (size_t)n * GLC_NPROP);
+        const double fb = P->OmegaBaryon / P->OmegaMatter;
+        for (int64_t i = 0; i < n; i++) {
+            flags[i] = 0;
+            state[i] = children_left[i] > 0 ? NS_PENDING : NS_ACTIVE;
+            if (state[i] != NS_ACTIVE) continue;
+            fc.trees += parent[i] < 0 ? 1 : 0;
+            double *r = R(i);
+            r[GLC_P_TIME] = time[i];
+            r[GLC_P_TIME_STEP] = -1.0;
+            r[GLC_P_BASIC_MASS] = mass[i];
+            r[GLC_P_DMSCALE] = scale[i];
+            r[GLC_P_SPIN] = angmom[i];
+            r[GLC_P_SAT_BOUND_MASS] = mass[i];
+            set_targets((int32_t)i, r);
+            // nodeOperatorCGMAccretion::nodeInitialize (accretion.F90:144-200) for branch tips
+            const double failed = failed_fraction(mass[i], time[i]);
+            const double m_hot = fb * mass[i] * (1.0 - failed), m_failed = fb * mass[i] * failed;
+            if (m_hot > 0.0 || m_failed > 0.0) {
+                flags[i] |= GLC_F_HAS_HOTHALO;
+                r[GLC_P_HH_MASS] = m_hot;
+                r[GLC_P_HH_UNACCRETED_MASS] = m_failed;
+                r[GLC_P_HH_ANGMOM] = angmom[i] * m_hot / mass[i];
+            }
+        }
+        for (int64_t i = 0; i < n; i++)
+            if (parent[i] < 0 && children_left[i] > 0) fc.trees++;
+        fc.nodes = (uint64_t)n;
+    }
+
+    // standardTimeEvolveTo for a satellite (:916-982)
+    double satellite_limit(int32_t s) const {
+        const int32_t h = host[s];
+        const double tn = R(s)[GLC_P_TIME];
+        double to = std::min(time_end[s], tn + timestep(tn));
+        if (to == tn) return tn;
+        const double th = parent[h] >= 0 ? node_time(h) : std::max(node_time(h), tn);
+        double limit;
+        if (children_left[h] > 0)
+            limit = std::max(th, tn);
+        else
+            limit = std::max(th + timestep(th), tn);
+        return std::min(to, limit);
+    }
+    // ... for a childless, isolated node (:905-914, :1003-1030)
+    double isolated_limit(int32_t a) const {
+        const double tn = R(a)[GLC_P_TIME];
+        if (parent[a] < 0) return tn;  // standardNodeIsEvolvable: no parent
+        double to = std::min(time_end[a], tn + timestep(tn));
+        to = std::min(to, time[parent[a]]);
+        for (int32_t s : sats[a]) {
+            const double ts = R(s)[GLC_P_TIME];
+            if (ts < to) to = std::max(ts, tn);
+        }
+        return to;
+    }
+    double baryons(int32_t i) const {
+        const double *r = R(i);
+        double m = 0.0;
+        if (flags[i] & GLC_F_HAS_HOTHALO) m += r[GLC_P_HH_MASS] + r[GLC_P_HH_OUTFLOWED_MASS];
+        if (flags[i] & GLC_F_HAS_DISK) m += r[GLC_P_DISK_MASS_GAS] + r[GLC_P_DISK_MASS_STELLAR];
+        if (flags[i] & GLC_F_HAS_SPHEROID) m += r[GLC_P_SPH_MASS_GAS] + r[GLC_P_SPH_MASS_STELLAR];
+        if (flags[i] & GLC_F_HAS_BH) m += r[GLC_P_BH_MASS];
+        return m;
+    }
+    void add_satellite(int32_t h, int32_t s) {
+        host[s] = h;
+        sats[h].insert(std::lower_bound(sats[h].begin(), sats[h].end(), s), s);
+    }
+
+    // standardMerge (:1329-1356): node i (non-primary, at its parent's time) becomes a satellite of the parent
+    void merge(int32_t i) {
+        const int32_t p = parent[i];
+        double *r = R(i), *rp = R(p);
+        // nodeOperatorCGMAccretion::nodesMerge (accretion.F90:265-426): unaccreted gas goes to the parent, part of the
+        // parent's unaccreted reservoir is re-accreted into its hot phase.  Until its own promotion the parent's record
+        // only carries this pending hot-halo content.
+        if (flags[i] & GLC_F_HAS_HOTHALO) {
+            flags[p] |= GLC_F_HAS_HOTHALO;
+            rp[GLC_P_HH_UNACCRETED_MASS] = rp[GLC_P_HH_UNACCRETED_MASS] + r[GLC_P_HH_UNACCRETED_MASS];
+            r[GLC_P_HH_UNACCRETED_MASS] = 0.0;
+            rp[GLC_P_HH_UNACCRETED_ABUND] = rp[GLC_P_HH_UNACCRETED_ABUND] + r[GLC_P_HH_UNACCRETED_ABUND];
+            r[GLC_P_HH_UNACCRETED_ABUND] = 0.0;
+            const double fb = P->OmegaBaryon / P->OmegaMatter;
+            const double failed = failed_fraction(mass[p], time[p]);
+            const double acc_hot = fb * mass[p] * (1.0 - failed), acc = acc_hot, unacc = fb * mass[p] * failed;
+            if (acc_hot > 0.0) {
+                const double fraction = acc_hot / (acc + unacc);
+                const double re = rp[GLC_P_HH_UNACCRETED_MASS] * fraction * r[GLC_P_BASIC_MASS] / mass[p];
+                rp[GLC_P_HH_UNACCRETED_MASS] = rp[GLC_P_HH_UNACCRETED_MASS] - re;
+                rp[GLC_P_HH_MASS] = rp[GLC_P_HH_MASS] + re;
+                // accreted metals: zero (IGM metallicity zero) => nothing moves between the abundance reservoirs
+                rp[GLC_P_HH_ANGMOM] = rp[GLC_P_HH_ANGMOM] + re * angmom[p] / mass[p];
+            }
+        }
+        // dmoInterpolateNodesMerge (:277-291) and the scale / angular-momentum interpolators: growth stops
+        r[GLC_P_MASS_RATE] = 0.0;
+        r[GLC_P_MASS_TARGET] = r[GLC_P_BASIC_MASS];
+        r[GLC_P_DMSCALE_RATE] = 0.0;
+        r[GLC_P_DMSCALE_TARGET] = r[GLC_P_DMSCALE];
+        r[GLC_P_SPIN_RATE] = 0.0;
+        r[GLC_P_SPIN_TARGET] = r[GLC_P_SPIN];
+        r[GLC_P_TIME_LAST_ISOLATED] = r[GLC_P_TIME];
+        r[GLC_P_SAT_BOUND_MASS] = r[GLC_P_BASIC_MASS];
+        r[GLC_P_MASS_BARYONIC_SUBHALOS] = 0.0;
+        // mergerTreeNodeMergerSingleLevelHierarchy: the node and its own satellites all become satellites of the parent
+        flags[i] |= GLC_F_IS_SATELLITE;
+        state[i] = NS_SATELLITE;
+        add_satellite(p, i);
+        for (int32_t s : sats[i]) add_satellite(p, s);
+        sats[i].clear();
+        children_left[p]--;
+        fc.node_mergers++;
+    }
+    // standardPromote (:1241-1327): the primary progenitor i takes over its parent
+    void promote(int32_t i) {
+        const int32_t p = parent[i];
+        double *r = R(i), *rp = R(p);
+        // nodeOperatorCGMAccretion::nodePromote (accretion.F90:202-263): add the parent's pending hot halo
+        if (flags[p] & GLC_F_HAS_HOTHALO) {
+            if (!(flags[i] & GLC_F_HAS_HOTHALO)) flags[i] |= GLC_F_HAS_HOTHALO;
+            if (r[GLC_P_HH_MASS] <= 0.0) r[GLC_P_HH_MASS] = r[GLC_P_HH_ANGMOM] = r[GLC_P_HH_ABUND] = 0.0;
+            r[GLC_P_HH_UNACCRETED_MASS] = r[GLC_P_HH_UNACCRETED_MASS] + rp[GLC_P_HH_UNACCRETED_MASS];
+            r[GLC_P_HH_MASS] = r[GLC_P_HH_MASS] + rp[GLC_P_HH_MASS];
+            r[GLC_P_HH_ANGMOM] = r[GLC_P_HH_ANGMOM] + rp[GLC_P_HH_ANGMOM];
+            r[GLC_P_HH_UNACCRETED_ABUND] = r[GLC_P_HH_UNACCRETED_ABUND] + rp[GLC_P_HH_UNACCRETED_ABUND];
+            r[GLC_P_HH_ABUND] = r[GLC_P_HH_ABUND] + rp[GLC_P_HH_ABUND];
+        }
+        // moveComponentsTo(parent); dmoInterpolateNodePromote (:241-275): mass, target and rate of the parent
+        memcpy(rp, r, sizeof(double) * GLC_NPROP);
+        flags[p] = flags[i];
+        rp[GLC_P_BASIC_MASS] = mass[p];
+        rp[GLC_P_DMSCALE] = scale[p];
+        rp[GLC_P_SPIN] = angmom[p];
+        rp[GLC_P_SAT_BOUND_MASS] = mass[p];
+        set_targets(p, rp);
+        // satellites follow (standardPromote :1281-1303)
+        for (int32_t s : sats[i]) add_satellite(p, s);
+        sats[i].clear();
+        state[i] = NS_DONE;
+        state[p] = NS_ACTIVE;
+        children_left[p]--;
+        fc.promotions++;
+    }
+
+    // One pass over the forest.  evolve(idx, n_idx, time_end) evolves the listed nodes' records in place and returns 0.
+    template <class Evolve>
+    int run(Evolve &&evolve) {
+        std::vector<int32_t> list;
+        std::vector<double> tend;
+        for (;;) {
+            bool progressed = false;
+            // phase A: satellites
+            list.clear(); tend.clear();
+            for (int64_t s = 0; s < n; s++) {
+                if (state[s] != NS_SATELLITE) continue;
+                const double to = satellite_limit((int32_t)s);
+                if (to > R(s)[GLC_P_TIME]) { list.push_back((int32_t)s); tend.push_back(to); }
+            }
+            if (!list.empty()) {
+                if (int rc = evolve(list, tend)) return rc;
+                fc.evolve_calls += list.size();
+                progressed = true;
+            }
+            // phase B: isolated childless nodes
+            list.clear(); tend.clear();
+            for (int64_t a = 0; a < n; a++) {
+                if (state[a] != NS_ACTIVE) continue;
+                const double to = isolated_limit((int32_t)a);
+                if (to > R(a)[GLC_P_TIME]) {
+                    double sub = 0.0;
+                    for (int32_t s : sats[a]) sub += baryons(s);
+                    R(a)[GLC_P_MASS_BARYONIC_SUBHALOS] = sub;
+                    list.push_back((int32_t)a); tend.push_back(to);
+                }
+            }
+            if (!list.empty()) {
+                if (int rc = evolve(list, tend)) return rc;
+                fc.evolve_calls += list.size();
+                progressed = true;
+            }
+            // arrivals: node mergers first, then promotions (ascending node index)
+            for (int64_t i = 0; i < n; i++)
+                if (state[i] == NS_ACTIVE && parent[i] >= 0 && !is_primary((int32_t)i) && R(i)[GLC_P_TIME] == time[parent[i]]) {
+                    merge((int32_t)i);
+                    progressed = true;
+                }
+            for (int64_t i = 0; i < n; i++)
+                if (state[i] == NS_ACTIVE && parent[i] >= 0 && is_primary((int32_t)i) && R(i)[GLC_P_TIME] == time[parent[i]] &&
+                    children_left[parent[i]] == 1) {
+                    promote((int32_t)i);
+                    progressed = true;
+                }
+            fc.rounds++;
+            if (!progressed) break;
+        }
+        return 0;
+    }
+};
+
+}  // namespace glcf

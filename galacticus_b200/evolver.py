@@ -57,6 +57,8 @@ def load_library() -> C.CDLL:
     L.glc_evolver_stream.restype = vp
     L.glc_evolver_stream.argtypes = [vp]
     L.glc_rhs_batch.argtypes = [vp, C.c_int64, _dp, _ip, _dp, _ip]
+    L.glc_forest_evolve.argtypes = [vp, C.c_int64, _ip, _dp, _dp, _dp, _dp, _dp, _ip, _ip,
+                                    C.POINTER(abi.glc_forest_counters), C.POINTER(abi.glc_counters)]
     L.glc_arena_snapshot.argtypes = [vp, C.c_int64]
     L.glc_arena_restore.argtypes = [vp, C.c_int64]
     L.glc_arena_capacity.restype = C.c_int64
@@ -237,3 +239,17 @@ class Evolver:
         p = props.copy()
         self._check(self.L.glc_rhs_batch(self.h, n, p, flags, dydt, interrupt), "glc_rhs_batch")
         return dydt, interrupt, p
+
+    def forest_evolve(self, forest):
+        """Tree-level evolution of a set of forests (glc_forest_evolve: the batching tree evolver of INTEGRATION.md section 3).
+        forest: dict of flat arrays parent / mass / time / scale_radius / angular_momentum (synthetic.binary_split_forest).
+        Returns (records, flags, state, forest_counters, counters)."""
+        n = forest["parent"].shape[0]
+        rec = np.zeros((n, abi.NPROP))
+        flags = np.zeros(n, dtype=np.int32)
+        state = np.zeros(n, dtype=np.int32)
+        fc, c = abi.glc_forest_counters(), abi.glc_counters()
+        a = [np.ascontiguousarray(forest[k], dtype=np.float64) for k in ("mass", "time", "scale_radius", "angular_momentum")]
+        self._check(self.L.glc_forest_evolve(self.h, n, np.ascontiguousarray(forest["parent"], dtype=np.int32), a[0], a[1], a[2],
+                                             a[3], rec, flags, state, C.byref(fc), C.byref(c)), "glc_forest_evolve")
+        return rec, flags, state, abi.counters_dict(fc), abi.counters_dict(c)

@@ -252,3 +252,68 @@ def standard_nodes(params, n, seed=219, fresh_fraction=0.3, satellite_fraction=0
         props[:, P["BH_SPIN"]] = np.where(has_b, jb, 0.0)
         flags[has_b] |= abi.GLC_F_HAS_BH
     return props, flags, t0 + dt
+
+
+# ------------------------------------------------------------------ synthetic forests (inputs of glc_forest_evolve)
+def binary_split_forest(params, n_trees, mass_root, mass_resolution, seed=219, time_min=0.6, step=(0.04, 0.10),
+                        mass_root_max=None):
+    """Seeded binary-split merger trees as flat arrays (parent, mass, time, scale_radius, angular_momentum), roots at the
+    present day.  Stand-in for mergerTreeBuilderCole2000 (tree building stays on the host and is outside the hot path,
+    SURVEY 8d/8f): going back in time every halo takes a step dt = t U(step), loses a smoothly accreted fraction and, with
+    a probability that grows with M / m_res, splits off a secondary progenitor with mass ratio q drawn from
+    dn/dq ~ q^-1.5 above the resolution; node counts scale like M / m_res.  Built level by level (vectorised).
+    Roots have mass mass_root (or log-uniform in [mass_root, mass_root_max])."""
+    rng = np.random.default_rng(seed)
+    cosmo = Cosmology(params)
+    t0 = float(cosmo.time_of_redshift(0.0))
+    if mass_root_max is None:
+        m_root = np.full(n_trees, float(mass_root))
+    else:
+        m_root = 10.0 ** rng.uniform(np.log10(mass_root), np.log10(mass_root_max), n_trees)
+    parent = [np.full(n_trees, -1, dtype=np.int64)]
+    mass = [m_root]
+    time = [np.full(n_trees, t0)]
+    tree = [np.arange(n_trees)]
+    front_idx = np.arange(n_trees)
+    front_m, front_t, front_tree = m_root.copy(), np.full(n_trees, t0), np.arange(n_trees)
+    n_total = n_trees
+    while front_idx.size:
+        k = front_idx.size
+        dt = front_t * rng.uniform(step[0], step[1], k)
+        t_child = front_t - dt
+        alive = (t_child > time_min) & (front_m > mass_resolution)
+        smooth = rng.uniform(0.0, 0.04, k)
+        m_avail = front_m * (1.0 - smooth)
+        q_min = mass_resolution / np.maximum(m_avail, mass_resolution)
+        p_split = np.clip(0.25 + 0.12 * np.log10(np.maximum(front_m / mass_resolution, 1.0)), 0.0, 0.85)
+        split = alive & (rng.random(k) < p_split) & (q_min < 0.5)
+        u = rng.random(k)
+        qm = np.minimum(q_min, 0.5)
+        q = (qm ** -0.5 - u * (qm ** -0.5 - 0.5 ** -0.5)) ** -2.0  # dn/dq ~ q^-1.5 on [q_min, 0.5]
+        m1 = np.where(split, m_avail * (1.0 - q), m_avail)
+        m2 = m_avail * q
+        keep1 = alive & (m1 > mass_resolution)
+        keep2 = split & (m2 > mass_resolution) & keep1
+        n1, n2 = int(keep1.sum()), int(keep2.sum())
+        idx1 = n_total + np.arange(n1)
+        idx2 = n_total + n1 + np.arange(n2)
+        n_total += n1 + n2
+        parent += [front_idx[keep1], front_idx[keep2]]
+        mass += [m1[keep1], m2[keep2]]
+        time += [t_child[keep1], t_child[keep2]]
+        tree += [front_tree[keep1], front_tree[keep2]]
+        front_idx = np.concatenate([idx1, idx2])
+        front_m = np.concatenate([m1[keep1], m2[keep2]])
+        front_t = np.concatenate([t_child[keep1], t_child[keep2]])
+        front_tree = np.concatenate([front_tree[keep1], front_tree[keep2]])
+    parent = np.concatenate(parent).astype(np.int32)
+    mass = np.concatenate(mass)
+    time = np.concatenate(time)
+    tree = np.concatenate(tree).astype(np.int32)
+    lam = (0.04326 * np.exp(rng.normal(0.0, 0.5, n_trees)))[tree]
+    rvir = virial_radius(params, mass, time)
+    vvir = np.sqrt(G_INTERNAL * mass / rvir)
+    conc = np.clip(9.0 * (mass / 1.0e12) ** -0.1 * (time / t0) ** 0.7, 3.0, 20.0)
+    return {"parent": parent, "mass": mass, "time": time, "scale_radius": rvir / conc,
+            "angular_momentum": np.sqrt(2.0) * lam * mass * rvir * vvir, "tree": tree}
+

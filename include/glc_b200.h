@@ -361,6 +361,35 @@ int glc_rhs_batch(glc_evolver *ev, int64_t n, double *props, const int32_t *flag
 int glc_histogram_accumulate(glc_evolver *ev, int64_t n, int32_t prop, double log10_min,
                              double log10_max, int32_t n_bins, double *device_hist);
 
+/*
+ * Forest interface: the batching tree evolver ("mergerTreeEvolverB200").
+ * replaces: mergerTreeEvolverStandard::evolve (merger_trees/evolver/standard.F90:291-635) over a SET of forests -- the
+ *           evolvability test (:723-760), the timeEvolveTo limits (:762-1035), standardPromote / standardMerge
+ *           (node_evolver/standard.F90:1241-1356) and the node-operator hooks called there; every round all nodes
+ *           allowed to move are evolved by ONE batched call of the node evolver.
+ * Forests arrive as flat arrays (node i: parent index or -1 for a root, halo mass [Msun], cosmic time [Gyr], dark-matter
+ * scale radius [Mpc], halo angular momentum [Msun Mpc km/s]); the most massive progenitor of a node is its primary.
+ *   records [n][GLC_NPROP] host, out   final node records (valid where state is ISOLATED or SATELLITE)
+ *   flags   [n]            host, out   component bits
+ *   state   [n]            host, out   enum glc_forest_node_state
+ * Requires resolveInterruptsOnDevice = 1 and the GLC_TABLE_HALO_MEAN_DENSITY table.
+ */
+enum glc_forest_node_state {
+    GLC_FOREST_NODE_PENDING = 0,   /* still has progenitors (only before/during the run) */
+    GLC_FOREST_NODE_ISOLATED = 1,  /* alive, not a satellite (at the end: the root galaxies) */
+    GLC_FOREST_NODE_SATELLITE = 2, /* alive, hosted by another node */
+    GLC_FOREST_NODE_PROMOTED = 3   /* was promoted into its parent (treeNode destroyed, standardPromote) */
+};
+typedef struct glc_forest_counters {
+    uint64_t trees, nodes;
+    uint64_t rounds;       /* batched evolve rounds (satellites, then hosts) */
+    uint64_t evolve_calls; /* mergerTreeNodeEvolver%evolve calls the reference would have issued */
+    uint64_t promotions, node_mergers; /* integer bookkeeping: must match the reference exactly */
+} glc_forest_counters;
+int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, const double *mass, const double *time,
+                      const double *scale_radius, const double *angular_momentum, double *records, int32_t *flags,
+                      int32_t *state, glc_forest_counters *forest_counters, glc_counters *counters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,8 @@ def lib(fast: bool = False) -> C.CDLL:
                                        _ip, _ip, C.POINTER(abi.glc_counters), C.c_int]
         L.orc_rhs_node.argtypes = [C.POINTER(abi.glc_params), C.c_void_p, _dp, C.c_int, _dp,
                                    C.POINTER(C.c_int)]
+        L.orc_forest_evolve.argtypes = [C.POINTER(abi.glc_params), C.c_void_p, C.c_long, _ip, _dp, _dp, _dp, _dp, _dp, _ip, _ip,
+                                        C.POINTER(abi.glc_forest_counters), C.POINTER(abi.glc_counters), C.c_int]
         _LIBS[name] = L
     return _LIBS[name]
 
@@ -114,3 +116,17 @@ class Oracle:
         row = np.ascontiguousarray(props_row, dtype=np.float64).copy()
         self.L.orc_rhs_node(C.byref(self.params), self.T, row, int(flag), dydt, C.byref(code))
         return dydt, code.value, row
+
+    def forest_evolve(self, forest, n_threads: int = 1):
+        """Tree-level evolution (orc_tree.c): returns (records, flags, state, forest_counters, counters)."""
+        n = forest["parent"].shape[0]
+        rec = np.zeros((n, abi.NPROP))
+        flags = np.zeros(n, dtype=np.int32)
+        state = np.zeros(n, dtype=np.int32)
+        fc, c = abi.glc_forest_counters(), abi.glc_counters()
+        a = [np.ascontiguousarray(forest[k], dtype=np.float64) for k in ("mass", "time", "scale_radius", "angular_momentum")]
+        rc = self.L.orc_forest_evolve(C.byref(self.params), self.T, n, np.ascontiguousarray(forest["parent"], dtype=np.int32),
+                                      a[0], a[1], a[2], a[3], rec, flags, state, C.byref(fc), C.byref(c), n_threads)
+        assert rc == 0, rc
+        return rec, flags, state, abi.counters_dict(fc), abi.counters_dict(c)
+

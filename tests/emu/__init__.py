@@ -22,6 +22,7 @@ def build(force: bool = False) -> None:
     src = os.path.join(HERE, "glc_emu.cpp")
     csrc = os.path.join(ROOT, "galacticus_b200", "csrc")
     deps = [src, abi.HEADER] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    deps += [os.path.join(csrc, "host", f) for f in os.listdir(os.path.join(csrc, "host"))]
     if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return
     os.makedirs(os.path.dirname(SO), exist_ok=True)
@@ -40,6 +41,9 @@ def lib() -> C.CDLL:
         L.emu_set_table.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_void_p, _dp]
         L.emu_evolve_batch.argtypes = [C.c_void_p, C.c_int64, _dp, _ip, _dp, _ip, _ip, C.POINTER(abi.glc_counters),
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+        L.emu_forest_evolve.argtypes = [C.c_void_p, C.c_int64, _ip, _dp, _dp, _dp, _dp, _dp, _ip, _ip,
+                                        C.POINTER(abi.glc_forest_counters), C.POINTER(abi.glc_counters), C.c_int, C.c_int, C.c_int,
+                                        C.c_int]
         _LIB = L
     return _LIB
 
@@ -87,3 +91,18 @@ class EmuEvolver:
         assert rc == 0
         self.slices = s.value
         return status, interrupt, abi.counters_dict(c)
+
+    def forest_evolve(self, forest):
+        """The product's host scheduler (csrc/host/glc_forest.hpp) over the host-executed kernel source."""
+        n = forest["parent"].shape[0]
+        rec = np.zeros((n, abi.NPROP))
+        flags = np.zeros(n, dtype=np.int32)
+        state = np.zeros(n, dtype=np.int32)
+        fc, c = abi.glc_forest_counters(), abi.glc_counters()
+        a = [np.ascontiguousarray(forest[k], dtype=np.float64) for k in ("mass", "time", "scale_radius", "angular_momentum")]
+        rc = self.L.emu_forest_evolve(self.h, n, np.ascontiguousarray(forest["parent"], dtype=np.int32), a[0], a[1], a[2], a[3],
+                                      rec, flags, state, C.byref(fc), C.byref(c), self.nslots, self.budget, int(self.sort),
+                                      int(self.machine))
+        assert rc == 0, rc
+        return rec, flags, state, abi.counters_dict(fc), abi.counters_dict(c)
+

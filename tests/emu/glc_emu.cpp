@@ -26,7 +26,10 @@
 
 using namespace glc;
 
+#include "../../galacticus_b200/csrc/host/glc_forest.hpp"
+
 struct Emu {
+    glcf::HaloTable halo_host;
     glc_params params;
     PreparedTable tables[GLC_NTABLES];
     DeviceTables dt;
@@ -316,6 +319,7 @@ void emu_set_params(void *h, const glc_params *p) {
 }
 int emu_set_table(void *h, int id, int n0, int n1, const double *x0, const double *x1, const double *v) {
     Emu *e = (Emu *)h;
+    if (id == GLC_TABLE_HALO_MEAN_DENSITY) e->halo_host.set(n0, x0, v);
     if (prepare_table(id, n0, n1, x0, x1, v, e->tables[id]) != 0) return -1;
     PreparedTable &t = e->tables[id];
     install_table(e->dt, id, t, DeviceTable2D{n0, n1, t.x0.data(), t.x1.empty() ? nullptr : t.x1.data(), t.v.data()});
@@ -341,4 +345,48 @@ int emu_evolve_batch(void *h, int64_t n, double *props, int32_t *flags, const do
     return 0;
 }
 
+// the host scheduler of the product (host/glc_forest.hpp) driven with the host-executed kernel source as evolve call-back
+int emu_forest_evolve(void *h, int64_t n_nodes, const int32_t *parent, const double *mass, const double *time,
+                      const double *scale_radius, const double *angular_momentum, double *records, int32_t *flags,
+                      int32_t *state, glc_forest_counters *fc, glc_counters *counters, int nslots, int budget, int sort,
+                      int machine) {
+    Emu *e = (Emu *)h;
+    glcf::Forest F;
+    F.init(&e->params, &e->halo_host, n_nodes, parent, mass, time, scale_radius, angular_momentum, records, flags, state);
+    glc_counters total{};
+    std::vector<double> buf;
+    std::vector<int32_t> bflags, status, interrupt;
+    auto evolve = [&](const std::vector<int32_t> &list, const std::vector<double> &te) -> int {
+        const int64_t m = (int64_t)list.size();
+        buf.resize((size_t)m * GLC_NPROP);
+        bflags.resize(m);
+        status.resize(m);
+        interrupt.resize(m);
+        for (int64_t k = 0; k < m; k++) {
+            memcpy(&buf[(size_t)k * GLC_NPROP], F.R(list[k]), sizeof(double) * GLC_NPROP);
+            bflags[k] = flags[list[k]];
+        }
+        glc_counters c{};
+        int64_t slices = 0;
+        int rc = emu_evolve_batch(h, m, buf.data(), bflags.data(), te.data(), status.data(), interrupt.data(), &c, nslots, budget,
+                                  sort, machine, &slices);
+        if (rc) return rc;
+        for (int64_t k = 0; k < m; k++) {
+            if (status[k] != GLC_STATUS_SUCCESS || interrupt[k] != GLC_INT_NONE) return -10;
+            memcpy(F.R(list[k]), &buf[(size_t)k * GLC_NPROP], sizeof(double) * GLC_NPROP);
+            flags[list[k]] = bflags[k];
+        }
+        total.steps_accepted += c.steps_accepted;
+        total.steps_rejected += c.steps_rejected;
+        total.rhs_evaluations += c.rhs_evaluations;
+        total.segments += c.segments;
+        total.trials_failed += c.trials_failed;
+        total.nodes += c.nodes;
+        return 0;
+    };
+    const int rc = F.run(evolve);
+    if (fc) *fc = F.fc;
+    if (counters) *counters = total;
+    return rc;
+}
 }  // extern "C"
