@@ -63,6 +63,8 @@ struct glc_evolver {
     SlotArrays d_slots{};           // micro-task machine: per-slot continuations, split by access group
     int64_t nslots_machine = 0;
     int32_t use_machine = 1;        // standard model: 1 = micro-task machine, 0 = warp-synchronous evolve_kernel
+    int64_t machine_min_nodes = 0;  // batches smaller than this go to the warp-synchronous evolve_kernel (few nodes cannot fill
+                                    // the machine's per-unit queues); results are identical either way
     int32_t drain_handover = 1;     // run-to-completion mode: finish the last nodes with drain_kernel
     int64_t drain_threshold = 60000;  // hand over when fewer slots than this are still in flight
     int32_t drain_dense_budget = 384; // evaluations per lane in a dense drain pass
@@ -594,6 +596,7 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_SLICE_LOG")) ev->slice_log = atoi(e);
     if (const char *e = getenv("GLC_MAX_SLICES")) ev->max_slices = atoi(e);
     if (const char *e = getenv("GLC_MACHINE")) ev->use_machine = atoi(e);
+    if (const char *e = getenv("GLC_MACHINE_MIN_NODES")) ev->machine_min_nodes = atoll(e);
     if (const char *e = getenv("GLC_DRAIN")) ev->drain_handover = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_BELOW")) ev->drain_threshold = atoll(e);
     if (const char *e = getenv("GLC_DRAIN_DENSE_BUDGET")) ev->drain_dense_budget = atoi(e);
@@ -791,7 +794,7 @@ int glc_evolve_arena(glc_evolver *ev, int64_t n, glc_counters *counters) {
     unsigned long long hc[16] = {0};
     if (ev->params.model == GLC_MODEL_BOX)
         rc = launch_evolve<ModelBox>(ev, (int)n, hc);
-    else if (ev->use_machine)
+    else if (ev->use_machine && n >= ev->machine_min_nodes)
         rc = launch_machine(ev, (int)n, hc);
     else
         rc = launch_evolve<ModelStandard>(ev, (int)n, hc);
