@@ -40,11 +40,17 @@ if ROOT not in sys.path:
 
 METRIC = "node_ode_steps_per_s"
 UNIT = "accepted RKCK node-ODE steps/s"
-# FP64 flop per evaluation of the rate function (DADD + DMUL + 2*DFMA thread-level SASS instructions of
-# machine_kernel divided by its RHS counter, ncu capture profiles/r01_machine_kernel_summary.txt)
-FLOP_PER_RHS = 7.8e3
+# FP64 flop per evaluation of the rate function: DADD + DMUL + 2*DFMA thread-level SASS instructions of every
+# machine_kernel and drain_kernel launch of one whole pass (300 000 node records, full operator list) divided by the
+# pass's RHS counter: 2.217e11 / 13 693 801 (ncu, profiles/r01f_fp64_ops_whole_pass.txt).  The first bulk slice alone
+# gives 7.8e3 (cheap, disk-less nodes are queued first), the second 16.1e3.
+FLOP_PER_RHS = 16.2e3
+# DRAM bytes per evaluation: ncu --set full of the second bulk slice of machine_kernel (profiles/r01e_machine_kernel_bulk_slice.txt:
+# 74.28 GB read + 43.91 GB written for 7 702 358 evaluations)
+DRAM_BYTES_PER_RHS = (74.277716e9 + 43.909916e9) / 7702358.0
 N_Y = 24
 BLACK_HOLE_FRACTION = 0.7
+MW_ROOT_MASS, MW_RESOLUTION = 1.52e12, 1.0e9  # testSuite/parameters/benchmark_milkyWay.xml:30-42
 
 
 def parse():
@@ -56,6 +62,8 @@ def parse():
     ap.add_argument("--nodes", type=int, default=1_000_000, help="node records per GPU (weak scaling)")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="node records of the CPU baseline sample")
     ap.add_argument("--seed", type=int, default=219)
+    ap.add_argument("--trees", type=int, default=1000, help="Milky-Way-mass trees per GPU of the tree-level arm (0 = skip)")
+    ap.add_argument("--cpu-trees", type=int, default=64, help="trees of the CPU tree-walk sample")
     return ap.parse_args()
 
 
@@ -147,6 +155,21 @@ def cpu_run(p, props, flags, t_end, repeats):
     return steps / best, props.shape[0] / best, best, cores
 
 
+def cpu_forest(p, n_trees, seed, cores):
+    """The CPU checker's tree walk (oracle/orc_tree.c, OpenMP over trees) on a sample of the same trees."""
+    from galacticus_b200 import synthetic
+    from oracle import orc
+
+    sub = synthetic.binary_split_forest(p, n_trees, MW_ROOT_MASS, MW_RESOLUTION, seed=seed)
+    o = orc.Oracle(fast=True)
+    synthetic.install(o, p)
+    t0 = time.perf_counter()
+    _, _, _, fc, c = o.forest_evolve(sub, n_threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n_trees / dt, "unit": "merger trees/s", "trees": n_trees, "seconds": dt,
+            "node_ode_steps_per_s": c["steps_accepted"] / dt}
+
+
 def run_reference(args):
     """Reference arm: the CPU implementation of the path (the oracle port; the Fortran reference cannot be
     compiled in this image) on the host cores, each step a bounded sample of the same workload."""
@@ -184,6 +207,9 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.trees > 0 and args.cpu_trees > 0:
+        line["trees_per_s"] = cpu_forest(p, args.cpu_trees, args.seed, cores)
+        line["cpu_baseline"]["trees_per_s"] = line["trees_per_s"]
     print(json.dumps(line))
 
 
@@ -273,12 +299,29 @@ def main():
     e2e_time = float(np.mean(e2e_times))
     h2d = n * (abi.NPROP * 8 + 4 + 8)
     d2h = n * (abi.NPROP * 8 + 4 + 4 + 4)
+    # ---------------- tree-level arm: BASELINE configs[1], 10^3 Milky-Way-mass trees through glc_forest_evolve (trees/s)
+    forest_s, forest_info = 0.0, None
+    if args.trees > 0:
+        fseed = _sh.forest_seed(args.seed, rank) if world > 1 else args.seed
+        forest = synthetic.binary_split_forest(p, args.trees, MW_ROOT_MASS, MW_RESOLUTION, seed=fseed)
+        ev.forest_evolve(synthetic.binary_split_forest(p, 4, MW_ROOT_MASS, 1.0e10, seed=1))  # warm-up
+        barrier()
+        t1 = time.perf_counter()
+        _, _, fstate, ffc, fcnt = ev.forest_evolve(forest)
+        torch.cuda.synchronize()
+        forest_s = time.perf_counter() - t1
+        forest_info = {"trees_per_gpu": args.trees, "nodes_per_gpu": int(forest["parent"].shape[0]),
+                       "root_mass": MW_ROOT_MASS, "mass_resolution": MW_RESOLUTION,
+                       "rounds": ffc["rounds"], "evolve_calls": ffc["evolve_calls"], "promotions": ffc["promotions"],
+                       "node_mergers": ffc["node_mergers"], "node_ode_steps": fcnt["steps_accepted"],
+                       "galaxies_at_final_time": int((fstate != abi.GLC_FOREST_NODE_PROMOTED).sum())}
     fp64_peak = ev.fp64_peak_tflops()  # after the runs: the device is warm
 
     # ---------------- reduce over ranks: max time, summed work, NCCL all-reduce of an output statistic
     steps_acc = counters["steps_accepted"]
     stats = torch.tensor([dev_time, wall, e2e_time, float(steps_acc), float(counters["rhs_evaluations"]),
-                          float(counters["steps_rejected"]), float(n)], dtype=torch.float64, device="cuda")
+                          float(counters["steps_rejected"]), float(n), forest_s, float(args.trees),
+                          float(forest_info["node_ode_steps"]) if forest_info else 0.0], dtype=torch.float64, device="cuda")
     tmax, tsum = stats.clone(), stats.clone()
     # stellar mass function histogram of the evolved batch (mirrors output/analyses/volume_function_1d.F90:986-987)
     mstar = final_props[:, abi.P["DISK_MASS_STELLAR"]] + final_props[:, abi.P["SPH_MASS_STELLAR"]]
@@ -330,10 +373,9 @@ def main():
             },
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          # DRAM traffic of the dominant kernel: ncu --set full capture of one machine_kernel launch
-                         # (profiles/r01c_machine_kernel_bulk_slice.txt: 37.94 GB read+written for 3 100 520 RHS
-                         # evaluations = 12.2 kB per evaluation, continuation records streaming through L2), scaled to
-                         # this launch's evaluation count
-                         "traffic": 37.94e9 / 3100520.0 * rhs_total,
+                         # (15.3 kB per evaluation: continuation records streaming through L2), scaled to this pass's
+                         # evaluation count
+                         "traffic": DRAM_BYTES_PER_RHS * rhs_total,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
                          "kernel": "machine_kernel (+ its drain_kernel continuation)",
                          "note": "the path is FP64-ALU / latency bound (SURVEY 8d: >15 flop per algorithmic byte): "
@@ -343,6 +385,13 @@ def main():
                               "frac": (ach_tflops / fp64_peak) if fp64_peak else None, "flop_per_rhs": FLOP_PER_RHS,
                               "peak_source": "DFMA-chain microbenchmark in this process (glc_measure_fp64_peak_tflops)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            # the other half of BASELINE.json's metric ("trees/sec & node-ODE steps/sec"), end to end through the C-ABI
+            # (host scheduler + batched node evolver, host buffers): all ranks' trees / slowest rank's time
+            "trees_per_s": ({"value": float(tsum[8]) / float(tmax[7]), "unit": "merger trees/s",
+                             "node_ode_steps_per_s": float(tsum[9]) / float(tmax[7]), "seconds": float(tmax[7]),
+                             "workload": "Milky-Way-mass binary-split trees (root %.3g Msun, resolution %.3g Msun: the masses of "
+                                         "testSuite/parameters/benchmark_milkyWay.xml), quickTest physics" % (MW_ROOT_MASS, MW_RESOLUTION),
+                             **forest_info} if forest_info else None),
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -354,6 +403,8 @@ def main():
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                         "sample": "first %d node records of the GPU workload, %.1f s, %.0f nodes/s"
                                                   % (ns, secs, nps)}
+                if forest_info and args.cpu_trees > 0:
+                    line["cpu_baseline"]["trees_per_s"] = cpu_forest(p, args.cpu_trees, args.seed, cores)
             except Exception as e:  # the checker is optional for the bench line
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         print(json.dumps(line))

@@ -62,12 +62,13 @@ struct glc_evolver {
     LaneState *d_lanes = nullptr;   // parked lane states, one per resident lane
     SlotArrays d_slots{};           // micro-task machine: per-slot continuations, split by access group
     int64_t nslots_machine = 0;
-    int32_t use_machine = 1;        // standard model: 1 = micro-task machine, 0 = warp-synchronous evolve_kernel
-    int64_t machine_min_nodes = 0;  // batches smaller than this go to the warp-synchronous evolve_kernel (few nodes cannot fill
-                                    // the machine's per-unit queues); results are identical either way
+    int32_t use_machine = 2;        // standard model: 1 = micro-task machine, 0 = warp-synchronous evolve_kernel, 2 = by batch size
+    int64_t machine_min_nodes = -1; // use_machine == 2: batches smaller than this (default: drain_threshold) go to the
+                                    // warp-synchronous evolve_kernel -- too few nodes to fill the machine's per-unit queues, it would
+                                    // hand over to the drain after one slice on a few SMs anyway; results are identical either way
     int32_t drain_handover = 1;     // run-to-completion mode: finish the last nodes with drain_kernel
-    int64_t drain_threshold = 60000;  // hand over when fewer slots than this are still in flight
-    int32_t drain_dense_budget = 384; // evaluations per lane in a dense drain pass
+    int64_t drain_threshold = 120000; // hand over when fewer slots than this are still in flight (measured: profiles/r01f_knobs.txt)
+    int32_t drain_dense_budget = 1024; // evaluations per lane in a dense drain pass
     int32_t *d_held = nullptr;
     float *d_held_score = nullptr;
     int64_t held_cap = 0;
@@ -794,7 +795,8 @@ int glc_evolve_arena(glc_evolver *ev, int64_t n, glc_counters *counters) {
     unsigned long long hc[16] = {0};
     if (ev->params.model == GLC_MODEL_BOX)
         rc = launch_evolve<ModelBox>(ev, (int)n, hc);
-    else if (ev->use_machine && n >= ev->machine_min_nodes)
+    else if (ev->use_machine == 1 ||
+             (ev->use_machine == 2 && n >= (ev->machine_min_nodes >= 0 ? ev->machine_min_nodes : ev->drain_threshold)))
         rc = launch_machine(ev, (int)n, hc);
     else
         rc = launch_evolve<ModelStandard>(ev, (int)n, hc);
@@ -845,7 +847,7 @@ int glc_evolver_set_option(glc_evolver *ev, int32_t option, int64_t value) {
     switch (option) {
         case GLC_OPT_SLICE_BUDGET: ev->slice_budget = (int32_t)std::max<int64_t>(0, std::min<int64_t>(value, 0x7fffffff)); return 0;
         case GLC_OPT_SORT_QUEUE: ev->sort_queue = value ? 1 : 0; return 0;
-        case GLC_OPT_MICROTASK_MACHINE: ev->use_machine = value ? 1 : 0; return 0;
+        case GLC_OPT_MICROTASK_MACHINE: ev->use_machine = value == 2 ? 2 : (value ? 1 : 0); return 0;
         default: ev->err = "unknown option"; return -10;
     }
 }

@@ -59,13 +59,15 @@ def test_kernel_source_on_host_reproduces_golden(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("machine", [1, 2])  # micro-task machine + drain hand-over / kernel chosen by batch size
 @pytest.mark.parametrize("name", ["standard_96", "standard_bh_96", "box_leaky_96"])
-def test_cuda_reproduces_golden(name):
+def test_cuda_reproduces_golden(name, machine):
     from galacticus_b200.evolver import Evolver
 
     g, p, tables = _case(name)
     ev = Evolver(0)
     synthetic.install(ev, p) if tables else ev.set_params(p)
+    ev.set_option(abi.GLC_OPT_MICROTASK_MACHINE, machine)
     props, flags = g["props_in"].copy(), g["flags_in"].copy()
     s, i, c = ev.evolve_batch(props, flags, g["t_end"])
     _check(g, props, flags, s, i, c)

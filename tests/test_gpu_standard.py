@@ -10,7 +10,7 @@ P = abi.P
 RTOL = 1.0e-6  # north_star tolerance on per-galaxy properties
 
 
-def make(orc, with_black_holes=False, **kw):
+def make(orc, with_black_holes=False, machine=1, **kw):
     from galacticus_b200.evolver import Evolver
 
     p = cases.standard_params(with_black_holes=with_black_holes)
@@ -18,6 +18,7 @@ def make(orc, with_black_holes=False, **kw):
         setattr(p, k, v)
     ev = Evolver(0)
     synthetic.install(ev, p)
+    ev.set_option(abi.GLC_OPT_MICROTASK_MACHINE, machine)
     o = orc.Oracle()
     synthetic.install(o, p)
     return ev, o, p
@@ -126,6 +127,20 @@ def test_evolve_parity(oracle_lib, n):
     assert cg["steps_accepted"] == co["steps_accepted"]
     assert cg["steps_rejected"] == co["steps_rejected"]
     assert cg["rhs_evaluations"] == co["rhs_evaluations"]
+
+
+@pytest.mark.parametrize("n", [500, 150000])
+def test_evolve_parity_kernel_chosen_by_batch_size(oracle_lib, n):
+    """Default execution option: small batches run on the warp-synchronous kernel, large ones on the micro-task machine
+    with drain hand-over; either way the records equal the oracle's bit for bit."""
+    ev, o, p = make(oracle_lib, with_black_holes=True, machine=2)
+    props, flags, t_end = cases.standard_bh_nodes(p, n, seed=77 + n)
+    pg, fg = props.copy(), flags.copy()
+    po, fo = props.copy(), flags.copy()
+    sg, ig, cg = ev.evolve_batch(pg, fg, t_end)
+    so, io, co = o.evolve_batch(po, fo, t_end, n_threads=16)
+    compare(pg, po, fg, fo, sg, so, ig, io, f"auto n={n}")
+    assert cg == co
 
 
 def test_interrupts_returned_to_host(oracle_lib):
