@@ -313,7 +313,8 @@ def main():
         forest_info = {"trees_per_gpu": args.trees, "nodes_per_gpu": int(forest["parent"].shape[0]),
                        "root_mass": MW_ROOT_MASS, "mass_resolution": MW_RESOLUTION,
                        "rounds": ffc["rounds"], "evolve_calls": ffc["evolve_calls"], "promotions": ffc["promotions"],
-                       "node_mergers": ffc["node_mergers"], "node_ode_steps": fcnt["steps_accepted"],
+                       "node_mergers": ffc["node_mergers"], "failed_evolves": ffc["failed_evolves"],
+                       "node_ode_steps": fcnt["steps_accepted"],
                        "galaxies_at_final_time": int((fstate != abi.GLC_FOREST_NODE_PROMOTED).sum())}
     fp64_peak = ev.fp64_peak_tflops()  # after the runs: the device is warm
 

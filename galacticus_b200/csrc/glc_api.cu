@@ -1146,11 +1146,11 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
         int rc = glc_evolve_batch(ev, m, buf.data(), bflags.data(), te.data(), status.data(), interrupt.data(), &c);
         if (rc) return rc;
         for (int64_t k = 0; k < m; k++) {
-            if (status[k] != GLC_STATUS_SUCCESS || interrupt[k] != GLC_INT_NONE) {
-                ev->err = "glc_forest_evolve: a node evolve did not complete (status / unresolved interrupt)";
-                return -10;
-            }
             memcpy(F.R(list[k]), &buf[(size_t)k * GLC_NPROP], sizeof(double) * GLC_NPROP);
+            if (status[k] != GLC_STATUS_SUCCESS || interrupt[k] != GLC_INT_NONE) {
+                F.fc.failed_evolves++;
+                F.R(list[k])[GLC_P_TIME] = te[k];
+            }
             flags[list[k]] = bflags[k];
         }
         total.steps_accepted += c.steps_accepted;

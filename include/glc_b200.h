@@ -386,6 +386,8 @@ typedef struct glc_forest_counters {
     uint64_t rounds;       /* batched evolve rounds (satellites, then hosts) */
     uint64_t evolve_calls; /* mergerTreeNodeEvolver%evolve calls the reference would have issued */
     uint64_t promotions, node_mergers; /* integer bookkeeping: must match the reference exactly */
+    uint64_t failed_evolves; /* evolve calls that came back with a status other than success (the reference aborts the
+                                run there, standard.F90:697-722); the node is moved to its end time and the walk goes on */
 } glc_forest_counters;
 int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, const double *mass, const double *time,
                       const double *scale_radius, const double *angular_momentum, double *records, int32_t *flags,

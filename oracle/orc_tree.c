@@ -214,7 +214,12 @@ static int evolve_to(tree_ctx *c, int i, double to, glc_forest_counters *fc, glc
     C->trials_failed += local.trials_failed;
     C->nodes += local.nodes;
     fc->evolve_calls++;
-    return (status[0] == GLC_STATUS_SUCCESS && interrupt[0] == GLC_INT_NONE) ? 0 : -10;
+    if (!(status[0] == GLC_STATUS_SUCCESS && interrupt[0] == GLC_INT_NONE)) {
+        /* the reference aborts here (standard.F90:697-722); the checker and the product move the node on and count it */
+        fc->failed_evolves++;
+        R(c, i)[GLC_P_TIME] = to;
+    }
+    return 0;
 }
 
 /* visit node i of the walk: its satellites first, then the node itself; returns 1 if anything moved, <0 on error */
@@ -379,6 +384,7 @@ int orc_forest_evolve(const glc_params *P, const orc_tables *T, long n, const in
             {
                 if (err) rc = -10;
                 fc.evolve_calls += lfc.evolve_calls; fc.promotions += lfc.promotions; fc.node_mergers += lfc.node_mergers;
+                fc.failed_evolves += lfc.failed_evolves;
                 if (lfc.rounds > fc.rounds) fc.rounds = lfc.rounds;
                 C.steps_accepted += lC.steps_accepted; C.steps_rejected += lC.steps_rejected;
                 C.rhs_evaluations += lC.rhs_evaluations; C.segments += lC.segments; C.trials_failed += lC.trials_failed;

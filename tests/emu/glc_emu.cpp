@@ -372,8 +372,11 @@ int emu_forest_evolve(void *h, int64_t n_nodes, const int32_t *parent, const dou
                                   sort, machine, &slices);
         if (rc) return rc;
         for (int64_t k = 0; k < m; k++) {
-            if (status[k] != GLC_STATUS_SUCCESS || interrupt[k] != GLC_INT_NONE) return -10;
             memcpy(F.R(list[k]), &buf[(size_t)k * GLC_NPROP], sizeof(double) * GLC_NPROP);
+            if (status[k] != GLC_STATUS_SUCCESS || interrupt[k] != GLC_INT_NONE) {
+                F.fc.failed_evolves++;
+                F.R(list[k])[GLC_P_TIME] = te[k];
+            }
             flags[list[k]] = bflags[k];
         }
         total.steps_accepted += c.steps_accepted;
@@ -388,5 +391,23 @@ int emu_forest_evolve(void *h, int64_t n_nodes, const int32_t *parent, const dou
     if (fc) *fc = F.fc;
     if (counters) *counters = total;
     return rc;
+}
+// scheduler-only run (no evolution: every node just arrives at its end time): host-side cost and round structure
+int emu_forest_dryrun(void *h, int64_t n_nodes, const int32_t *parent, const double *mass, const double *time,
+                      const double *scale_radius, const double *angular_momentum, double *records, int32_t *flags,
+                      int32_t *state, glc_forest_counters *fc, int64_t *batch_sizes, int max_batches) {
+    Emu *e = (Emu *)h;
+    glcf::Forest F;
+    F.init(&e->params, &e->halo_host, n_nodes, parent, mass, time, scale_radius, angular_momentum, records, flags, state);
+    int nb = 0;
+    auto evolve = [&](const std::vector<int32_t> &list, const std::vector<double> &te) -> int {
+        if (nb < max_batches) batch_sizes[nb] = (int64_t)list.size();
+        nb++;
+        for (size_t k = 0; k < list.size(); k++) F.R(list[k])[GLC_P_TIME] = te[k];
+        return 0;
+    };
+    const int rc = F.run(evolve);
+    if (fc) *fc = F.fc;
+    return rc ? rc : nb;
 }
 }  // extern "C"

@@ -48,8 +48,9 @@ def test_scheduler_matches_reference_walk(oracle_lib, machine, nslots, budget):
     re, fe, se, fce, ce = e.forest_evolve(f)
     np.testing.assert_array_equal(se, so)
     np.testing.assert_array_equal(fe, fo)
-    for k in ("trees", "nodes", "evolve_calls", "promotions", "node_mergers"):
+    for k in ("trees", "nodes", "evolve_calls", "promotions", "node_mergers", "failed_evolves"):
         assert fce[k] == fco[k], k
+    assert fco["failed_evolves"] == 0
     assert ce == co  # segments, accepted / rejected steps, RHS evaluations
     alive = so != PROMOTED
     assert np.array_equal(re[alive], ro[alive]), "surviving node records not bit-identical"
@@ -107,7 +108,7 @@ def test_forest_evolve_cuda_matches_reference_walk(oracle_lib):
     rg, fg, sg, fcg, cg = ev.forest_evolve(f)
     np.testing.assert_array_equal(sg, so)
     np.testing.assert_array_equal(fg, fo)
-    for k in ("trees", "nodes", "evolve_calls", "promotions", "node_mergers"):
+    for k in ("trees", "nodes", "evolve_calls", "promotions", "node_mergers", "failed_evolves"):
         assert fcg[k] == fco[k], k
     assert cg == co
     alive = so != PROMOTED
