@@ -1130,6 +1130,7 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
     glcf::Forest F;
     F.init(&ev->params, &ev->halo_host, n_nodes, parent, mass, time, scale_radius, angular_momentum, records, flags, state);
     glc_counters total{};
+    const bool forest_log = getenv("GLC_FOREST_LOG") != nullptr;
     std::vector<double> buf, tend;
     std::vector<int32_t> bflags, status, interrupt;
     auto evolve = [&](const std::vector<int32_t> &list, const std::vector<double> &te) -> int {
@@ -1143,8 +1144,13 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
             bflags[k] = flags[list[k]];
         }
         glc_counters c{};
+        const double t_batch = now_s();
         int rc = glc_evolve_batch(ev, m, buf.data(), bflags.data(), te.data(), status.data(), interrupt.data(), &c);
         if (rc) return rc;
+        if (forest_log)
+            fprintf(stderr, "[glc forest] batch of %lld nodes: %.1f ms (kernels %.1f ms), %llu RHS evaluations, %llu accepted steps\n",
+                    (long long)m, 1e3 * (now_s() - t_batch), ev->last_ms, (unsigned long long)c.rhs_evaluations,
+                    (unsigned long long)c.steps_accepted);
         for (int64_t k = 0; k < m; k++) {
             memcpy(F.R(list[k]), &buf[(size_t)k * GLC_NPROP], sizeof(double) * GLC_NPROP);
             if (status[k] != GLC_STATUS_SUCCESS || interrupt[k] != GLC_INT_NONE) {

@@ -19,6 +19,7 @@
  * bulk-synchronous rounds; the per-node sequences of (state, end time) -- and therefore the results -- do not.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -214,6 +215,9 @@ static int evolve_to(tree_ctx *c, int i, double to, glc_forest_counters *fc, glc
     C->trials_failed += local.trials_failed;
     C->nodes += local.nodes;
     fc->evolve_calls++;
+    if (local.rhs_evaluations > 800 && getenv("ORC_DEBUG_LONG_CALLS"))
+        fprintf(stderr, "[orc_tree] node %d: %llu RHS evaluations in one evolve call (to t=%.6g, flags %d, M=%.4g)\n", i,
+                (unsigned long long)local.rhs_evaluations, to, c->flags[i], R(c, i)[GLC_P_BASIC_MASS]);
     if (!(status[0] == GLC_STATUS_SUCCESS && interrupt[0] == GLC_INT_NONE)) {
         /* the reference aborts here (standard.F90:697-722); the checker and the product move the node on and count it */
         fc->failed_evolves++;
