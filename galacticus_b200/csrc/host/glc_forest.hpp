@@ -90,6 +90,14 @@ struct Forest {
     std::vector<int32_t> first_child, sibling, host, children_left, root_of;
     std::vector<std::vector<int32_t>> sats;  // ascending node index
     std::vector<double> time_end;            // per node: final time of its tree
+    // work lists (so that a round costs O(nodes that can move), not O(all nodes)): childless isolated nodes, nodes that host
+    // satellites; entries that no longer qualify are dropped when the list is next walked
+    std::vector<int32_t> active_list, host_list, sib_rank;
+    std::vector<uint8_t> in_host_list;
+    // what cgmAccretionNodesMerge needs of a merged progenitor (see merge()): unaccreted mass / metals and halo mass at merger
+    std::vector<double> merged_unaccreted, merged_unaccreted_abund, merged_mass;
+    std::vector<uint8_t> merged_hot;
+    mutable double memo_t[2] = {-1.0, -1.0}, memo_v[2] = {0.0, 0.0};  // timestep memo, like timeHostPrevious (:945-958)
     glc_forest_counters fc{};
 
     double *R(int64_t i) const { return rec + i * GLC_NPROP; }
@@ -102,7 +110,13 @@ struct Forest {
         return 1.0 / (H0 * sqrt(OL) * ((e + 1.0) / (e - 1.0)));
     }
     double timestep(double t) const {  // simple.F90 and evolver/standard.F90:945-958 (same numbers in quickTest.xml)
-        return std::min(0.1 * expansion_timescale(t), 1.0);
+        if (t == memo_t[0]) return memo_v[0];
+        if (t == memo_t[1]) return memo_v[1];
+        memo_t[1] = memo_t[0];
+        memo_v[1] = memo_v[0];
+        memo_t[0] = t;
+        memo_v[0] = std::min(0.1 * expansion_timescale(t), 1.0);
+        return memo_v[0];
     }
     double failed_fraction(double m, double t) const {  // accretion/halo/simple.F90: simpleFailedFraction
         return (t > P->timeReionization && halo->virial_velocity(m, t) < P->velocitySuppressionReionization) ? 1.0 : 0.0;
@@ -150,6 +164,8 @@ struct Forest {
         rec = records; flags = fl; state = st;
         first_child.assign(n, -1); sibling.assign(n, -1); host.assign(n, -1); children_left.assign(n, 0);
         root_of.assign(n, -1); sats.assign(n, {}); time_end.assign(n, 0.0);
+        active_list.clear(); host_list.clear(); sib_rank.assign(n, 0); in_host_list.assign(n, 0);
+        merged_unaccreted.assign(n, 0.0); merged_unaccreted_abund.assign(n, 0.0); merged_mass.assign(n, 0.0); merged_hot.assign(n, 0);
         memset(&fc, 0, sizeof(fc));
         // children ordered by descending mass (ties: ascending index); the first one is the primary progenitor
         std::vector<int32_t> order(n);
@@ -163,11 +179,22 @@ struct Forest {
             first_child[p] = i;
             children_left[p]++;
         }
+        for (int64_t p = 0; p < n; p++) {
+            int32_t k = 0;
+            for (int32_t c = first_child[p]; c >= 0; c = sibling[c]) sib_rank[c] = k++;
+        }
         for (int64_t i = 0; i < n; i++) {
             int32_t r = (int32_t)i;
-            while (parent[r] >= 0) r = parent[r];
-            root_of[i] = r;
-            time_end[i] = time[r];
+            while (parent[r] >= 0 && root_of[r] < 0) r = parent[r];
+            const int32_t root = root_of[r] >= 0 ? root_of[r] : r;
+            for (int32_t q = (int32_t)i; q != r && root_of[q] < 0;) {  // path compression: every node is walked once
+                const int32_t nx = parent[q];
+                root_of[q] = root;
+                q = nx;
+            }
+            root_of[r] = root;
+            root_of[i] = root;
+            time_end[i] = time[root];
         }
         memset(rec, 0, sizeof(double) * (size_t)n * GLC_NPROP);
         const double fb = P->OmegaBaryon / P->OmegaMatter;
@@ -175,6 +202,7 @@ struct Forest {
             flags[i] = 0;
             state[i] = children_left[i] > 0 ? NS_PENDING : NS_ACTIVE;
             if (state[i] != NS_ACTIVE) continue;
+            active_list.push_back((int32_t)i);
             fc.trees += parent[i] < 0 ? 1 : 0;
             double *r = R(i);
             r[GLC_P_TIME] = time[i];
@@ -236,33 +264,30 @@ struct Forest {
     }
     void add_satellite(int32_t h, int32_t s) {
         host[s] = h;
+        if (!in_host_list[h]) {
+            in_host_list[h] = 1;
+            host_list.push_back(h);
+        }
         sats[h].insert(std::lower_bound(sats[h].begin(), sats[h].end(), s), s);
     }
 
     // standardMerge (:1329-1356): node i (non-primary, at its parent's time) becomes a satellite of the parent
     void merge(int32_t i) {
         const int32_t p = parent[i];
-        double *r = R(i), *rp = R(p);
+        double *r = R(i);
         // nodeOperatorCGMAccretion::nodesMerge (accretion.F90:265-426): unaccreted gas goes to the parent, part of the
-        // parent's unaccreted reservoir is re-accreted into its hot phase.  Until its own promotion the parent's record
-        // only carries this pending hot-halo content.
+        // parent's unaccreted reservoir is re-accreted into its hot phase.  The parent's side of this hook is order
+        // dependent (each merger sees what the previous ones left); the reference applies it in arrival order, which is a
+        // property of its walk.  Here the node's side happens now and the parent's side is applied at the parent's own
+        // promotion, in progenitor order (apply_merged_progenitors): the same result for every schedule, and identical to
+        // arrival order whenever a node has at most one non-primary progenitor.
         if (flags[i] & GLC_F_HAS_HOTHALO) {
-            flags[p] |= GLC_F_HAS_HOTHALO;
-            rp[GLC_P_HH_UNACCRETED_MASS] = rp[GLC_P_HH_UNACCRETED_MASS] + r[GLC_P_HH_UNACCRETED_MASS];
+            merged_hot[i] = 1;
+            merged_unaccreted[i] = r[GLC_P_HH_UNACCRETED_MASS];
+            merged_unaccreted_abund[i] = r[GLC_P_HH_UNACCRETED_ABUND];
+            merged_mass[i] = r[GLC_P_BASIC_MASS];
             r[GLC_P_HH_UNACCRETED_MASS] = 0.0;
-            rp[GLC_P_HH_UNACCRETED_ABUND] = rp[GLC_P_HH_UNACCRETED_ABUND] + r[GLC_P_HH_UNACCRETED_ABUND];
             r[GLC_P_HH_UNACCRETED_ABUND] = 0.0;
-            const double fb = P->OmegaBaryon / P->OmegaMatter;
-            const double failed = failed_fraction(mass[p], time[p]);
-            const double acc_hot = fb * mass[p] * (1.0 - failed), acc = acc_hot, unacc = fb * mass[p] * failed;
-            if (acc_hot > 0.0) {
-                const double fraction = acc_hot / (acc + unacc);
-                const double re = rp[GLC_P_HH_UNACCRETED_MASS] * fraction * r[GLC_P_BASIC_MASS] / mass[p];
-                rp[GLC_P_HH_UNACCRETED_MASS] = rp[GLC_P_HH_UNACCRETED_MASS] - re;
-                rp[GLC_P_HH_MASS] = rp[GLC_P_HH_MASS] + re;
-                // accreted metals: zero (IGM metallicity zero) => nothing moves between the abundance reservoirs
-                rp[GLC_P_HH_ANGMOM] = rp[GLC_P_HH_ANGMOM] + re * angmom[p] / mass[p];
-            }
         }
         // dmoInterpolateNodesMerge (:277-291) and the scale / angular-momentum interpolators: growth stops
         r[GLC_P_MASS_RATE] = 0.0;
@@ -283,10 +308,33 @@ struct Forest {
         children_left[p]--;
         fc.node_mergers++;
     }
+    // the parent's side of cgmAccretionNodesMerge (:281-362) for every merged progenitor of p, in progenitor order; until its
+    // own promotion the parent's record only carries this pending hot-halo content
+    void apply_merged_progenitors(int32_t p) {
+        double *rp = R(p);
+        const double fb = P->OmegaBaryon / P->OmegaMatter;
+        for (int32_t c = first_child[p]; c >= 0; c = sibling[c]) {
+            if (!merged_hot[c]) continue;
+            flags[p] |= GLC_F_HAS_HOTHALO;
+            rp[GLC_P_HH_UNACCRETED_MASS] = rp[GLC_P_HH_UNACCRETED_MASS] + merged_unaccreted[c];
+            rp[GLC_P_HH_UNACCRETED_ABUND] = rp[GLC_P_HH_UNACCRETED_ABUND] + merged_unaccreted_abund[c];
+            const double failed = failed_fraction(mass[p], time[p]);
+            const double acc_hot = fb * mass[p] * (1.0 - failed), acc = acc_hot, unacc = fb * mass[p] * failed;
+            if (acc_hot > 0.0) {
+                const double fraction = acc_hot / (acc + unacc);
+                const double re = rp[GLC_P_HH_UNACCRETED_MASS] * fraction * merged_mass[c] / mass[p];
+                rp[GLC_P_HH_UNACCRETED_MASS] = rp[GLC_P_HH_UNACCRETED_MASS] - re;
+                rp[GLC_P_HH_MASS] = rp[GLC_P_HH_MASS] + re;
+                // accreted metals: zero (IGM metallicity zero) => nothing moves between the abundance reservoirs
+                rp[GLC_P_HH_ANGMOM] = rp[GLC_P_HH_ANGMOM] + re * angmom[p] / mass[p];
+            }
+        }
+    }
     // standardPromote (:1241-1327): the primary progenitor i takes over its parent
     void promote(int32_t i) {
         const int32_t p = parent[i];
         double *r = R(i), *rp = R(p);
+        apply_merged_progenitors(p);
         // nodeOperatorCGMAccretion::nodePromote (accretion.F90:202-263): add the parent's pending hot halo
         if (flags[p] & GLC_F_HAS_HOTHALO) {
             if (!(flags[i] & GLC_F_HAS_HOTHALO)) flags[i] |= GLC_F_HAS_HOTHALO;
@@ -310,23 +358,33 @@ struct Forest {
         sats[i].clear();
         state[i] = NS_DONE;
         state[p] = NS_ACTIVE;
+        active_list.push_back(p);
         children_left[p]--;
         fc.promotions++;
     }
 
-    // One pass over the forest.  evolve(idx, n_idx, time_end) evolves the listed nodes' records in place and returns 0.
+    // Rounds over the forest.  evolve(idx, time_end) evolves the listed nodes' records in place and returns 0.
     template <class Evolve>
     int run(Evolve &&evolve) {
-        std::vector<int32_t> list;
+        std::vector<int32_t> list, arrived;
         std::vector<double> tend;
         for (;;) {
             bool progressed = false;
-            // phase A: satellites
+            // phase A: satellites, host by host (a host that still has a progenitor pins its satellites, :927-941)
             list.clear(); tend.clear();
-            for (int64_t s = 0; s < n; s++) {
-                if (state[s] != NS_SATELLITE) continue;
-                const double to = satellite_limit((int32_t)s);
-                if (to > R(s)[GLC_P_TIME]) { list.push_back((int32_t)s); tend.push_back(to); }
+            {
+                size_t keep = 0;
+                for (size_t k = 0; k < host_list.size(); k++) {
+                    const int32_t h = host_list[k];
+                    if (sats[h].empty()) { in_host_list[h] = 0; continue; }
+                    host_list[keep++] = h;
+                    if (children_left[h] > 0) continue;
+                    for (int32_t s : sats[h]) {
+                        const double to = satellite_limit(s);
+                        if (to > R(s)[GLC_P_TIME]) { list.push_back(s); tend.push_back(to); }
+                    }
+                }
+                host_list.resize(keep);
             }
             if (!list.empty()) {
                 if (int rc = evolve(list, tend)) return rc;
@@ -335,31 +393,43 @@ struct Forest {
             }
             // phase B: isolated childless nodes
             list.clear(); tend.clear();
-            for (int64_t a = 0; a < n; a++) {
-                if (state[a] != NS_ACTIVE) continue;
-                const double to = isolated_limit((int32_t)a);
-                if (to > R(a)[GLC_P_TIME]) {
-                    double sub = 0.0;
-                    for (int32_t s : sats[a]) sub += baryons(s);
-                    R(a)[GLC_P_MASS_BARYONIC_SUBHALOS] = sub;
-                    list.push_back((int32_t)a); tend.push_back(to);
+            {
+                size_t keep = 0;
+                for (size_t k = 0; k < active_list.size(); k++) {
+                    const int32_t a = active_list[k];
+                    if (state[a] != NS_ACTIVE) continue;
+                    active_list[keep++] = a;
+                    const double to = isolated_limit(a);
+                    if (to > R(a)[GLC_P_TIME]) {
+                        double sub = 0.0;
+                        for (int32_t s : sats[a]) sub += baryons(s);
+                        R(a)[GLC_P_MASS_BARYONIC_SUBHALOS] = sub;
+                        list.push_back(a); tend.push_back(to);
+                    }
                 }
+                active_list.resize(keep);
             }
             if (!list.empty()) {
                 if (int rc = evolve(list, tend)) return rc;
                 fc.evolve_calls += list.size();
                 progressed = true;
             }
-            // arrivals: node mergers first, then promotions (ascending node index)
-            for (int64_t i = 0; i < n; i++)
-                if (state[i] == NS_ACTIVE && parent[i] >= 0 && !is_primary((int32_t)i) && R(i)[GLC_P_TIME] == time[parent[i]]) {
-                    merge((int32_t)i);
+            // arrivals: node mergers first -- siblings of one parent in progenitor order, as the reference's walk meets
+            // them --, then promotions
+            arrived.clear();
+            for (int32_t i : active_list)
+                if (parent[i] >= 0 && R(i)[GLC_P_TIME] == time[parent[i]]) arrived.push_back(i);
+            std::sort(arrived.begin(), arrived.end(), [&](int32_t a, int32_t b) {
+                return parent[a] != parent[b] ? parent[a] < parent[b] : sib_rank[a] < sib_rank[b];
+            });
+            for (int32_t i : arrived)
+                if (!is_primary(i)) {
+                    merge(i);
                     progressed = true;
                 }
-            for (int64_t i = 0; i < n; i++)
-                if (state[i] == NS_ACTIVE && parent[i] >= 0 && is_primary((int32_t)i) && R(i)[GLC_P_TIME] == time[parent[i]] &&
-                    children_left[parent[i]] == 1) {
-                    promote((int32_t)i);
+            for (int32_t i : arrived)
+                if (is_primary(i) && children_left[parent[i]] == 1) {
+                    promote(i);
                     progressed = true;
                 }
             fc.rounds++;

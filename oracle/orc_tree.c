@@ -39,6 +39,9 @@ typedef struct tree_ctx {
     int *flags, *state;
     int *first_child, *sibling, *host, *children_left, *first_sat, *next_sat; /* satellite lists kept in ascending index */
     double *time_end;
+    /* what cgmAccretionNodesMerge needs of a merged progenitor: unaccreted mass / metals and halo mass at merger */
+    double *merged_unaccreted, *merged_unaccreted_abund, *merged_mass;
+    unsigned char *merged_hot;
 } tree_ctx;
 
 static double *R(const tree_ctx *c, long i) { return c->rec + i * GLC_NPROP; }
@@ -137,26 +140,44 @@ static double baryons(const tree_ctx *c, int i) {
     return m;
 }
 
-static void node_merge(tree_ctx *c, int i, glc_forest_counters *fc) {
-    /* standardMerge :1329-1356 + cgmAccretionNodesMerge :265-426 + dmoInterpolateNodesMerge :277-291 */
-    const int p = c->parent[i];
-    double *r = R(c, i), *rp = R(c, p);
-    if (c->flags[i] & GLC_F_HAS_HOTHALO) {
-        const double fb = c->P->OmegaBaryon / c->P->OmegaMatter;
-        const double failed = failed_fraction(c, c->mass[p], c->time[p]);
-        const double acc_hot = fb * c->mass[p] * (1.0 - failed), unacc = fb * c->mass[p] * failed;
+static void apply_merged_progenitors(tree_ctx *c, int p) {
+    /* the parent's side of cgmAccretionNodesMerge :281-362 for every merged progenitor, in progenitor order.  That side is
+       order dependent; the reference applies it in arrival order, a property of its walk.  Checker and product apply it at
+       the parent's own promotion in progenitor order: schedule independent, and identical to arrival order whenever a node
+       has at most one non-primary progenitor. */
+    double *rp = R(c, p);
+    const double fb = c->P->OmegaBaryon / c->P->OmegaMatter;
+    int k;
+    for (k = c->first_child[p]; k >= 0; k = c->sibling[k]) {
+        double failed, acc_hot, unacc;
+        if (!c->merged_hot[k]) continue;
         c->flags[p] |= GLC_F_HAS_HOTHALO;
-        rp[GLC_P_HH_UNACCRETED_MASS] = rp[GLC_P_HH_UNACCRETED_MASS] + r[GLC_P_HH_UNACCRETED_MASS];
-        r[GLC_P_HH_UNACCRETED_MASS] = 0.0;
-        rp[GLC_P_HH_UNACCRETED_ABUND] = rp[GLC_P_HH_UNACCRETED_ABUND] + r[GLC_P_HH_UNACCRETED_ABUND];
-        r[GLC_P_HH_UNACCRETED_ABUND] = 0.0;
+        rp[GLC_P_HH_UNACCRETED_MASS] = rp[GLC_P_HH_UNACCRETED_MASS] + c->merged_unaccreted[k];
+        rp[GLC_P_HH_UNACCRETED_ABUND] = rp[GLC_P_HH_UNACCRETED_ABUND] + c->merged_unaccreted_abund[k];
+        failed = failed_fraction(c, c->mass[p], c->time[p]);
+        acc_hot = fb * c->mass[p] * (1.0 - failed);
+        unacc = fb * c->mass[p] * failed;
         if (acc_hot > 0.0) {
             const double fraction = acc_hot / (acc_hot + unacc);
-            const double re = rp[GLC_P_HH_UNACCRETED_MASS] * fraction * r[GLC_P_BASIC_MASS] / c->mass[p];
+            const double re = rp[GLC_P_HH_UNACCRETED_MASS] * fraction * c->merged_mass[k] / c->mass[p];
             rp[GLC_P_HH_UNACCRETED_MASS] = rp[GLC_P_HH_UNACCRETED_MASS] - re;
             rp[GLC_P_HH_MASS] = rp[GLC_P_HH_MASS] + re;
             rp[GLC_P_HH_ANGMOM] = rp[GLC_P_HH_ANGMOM] + re * c->angmom[p] / c->mass[p];
         }
+    }
+}
+
+static void node_merge(tree_ctx *c, int i, glc_forest_counters *fc) {
+    /* standardMerge :1329-1356 + the node's side of cgmAccretionNodesMerge :265-280 + dmoInterpolateNodesMerge :277-291 */
+    const int p = c->parent[i];
+    double *r = R(c, i);
+    if (c->flags[i] & GLC_F_HAS_HOTHALO) {
+        c->merged_hot[i] = 1;
+        c->merged_unaccreted[i] = r[GLC_P_HH_UNACCRETED_MASS];
+        c->merged_unaccreted_abund[i] = r[GLC_P_HH_UNACCRETED_ABUND];
+        c->merged_mass[i] = r[GLC_P_BASIC_MASS];
+        r[GLC_P_HH_UNACCRETED_MASS] = 0.0;
+        r[GLC_P_HH_UNACCRETED_ABUND] = 0.0;
     }
     r[GLC_P_MASS_RATE] = 0.0;
     r[GLC_P_MASS_TARGET] = r[GLC_P_BASIC_MASS];
@@ -179,6 +200,7 @@ static void node_promote(tree_ctx *c, int i, glc_forest_counters *fc) {
     /* standardPromote :1241-1327 + cgmAccretionNodePromote :202-263 + dmoInterpolateNodePromote :241-275 */
     const int p = c->parent[i];
     double *r = R(c, i), *rp = R(c, p);
+    apply_merged_progenitors(c, p);
     if (c->flags[p] & GLC_F_HAS_HOTHALO) {
         c->flags[i] |= GLC_F_HAS_HOTHALO;
         if (r[GLC_P_HH_MASS] <= 0.0) r[GLC_P_HH_MASS] = r[GLC_P_HH_ANGMOM] = r[GLC_P_HH_ABUND] = 0.0;
@@ -293,6 +315,8 @@ int orc_forest_evolve(const glc_params *P, const orc_tables *T, long n, const in
     c.first_child = malloc(sizeof(int) * n); c.sibling = malloc(sizeof(int) * n); c.host = malloc(sizeof(int) * n);
     c.children_left = calloc(n, sizeof(int)); c.first_sat = malloc(sizeof(int) * n); c.next_sat = malloc(sizeof(int) * n);
     c.time_end = malloc(sizeof(double) * n);
+    c.merged_unaccreted = calloc(n, sizeof(double)); c.merged_unaccreted_abund = calloc(n, sizeof(double));
+    c.merged_mass = calloc(n, sizeof(double)); c.merged_hot = calloc(n, 1);
     order = malloc(sizeof(int) * n); root_of = malloc(sizeof(int) * n); post = malloc(sizeof(int) * n);
     for (i = 0; i < n; i++) c.first_child[i] = c.sibling[i] = c.host[i] = c.first_sat[i] = c.next_sat[i] = -1;
     /* progenitors ordered by descending mass: insertion sort of each node into its parent's list (ties: lower index first) */
@@ -400,6 +424,7 @@ int orc_forest_evolve(const glc_params *P, const orc_tables *T, long n, const in
     if (fc_out) *fc_out = fc;
     if (C_out) *C_out = C;
     free(c.first_child); free(c.sibling); free(c.host); free(c.children_left); free(c.first_sat); free(c.next_sat);
+    free(c.merged_unaccreted); free(c.merged_unaccreted_abund); free(c.merged_mass); free(c.merged_hot);
     free(c.time_end); free(order); free(root_of); free(post); free(roots); free(root_first);
     return rc;
 }

@@ -62,6 +62,34 @@ def test_scheduler_matches_reference_walk(oracle_lib, machine, nslots, budget):
     assert ((fo[so == SATELLITE] & abi.GLC_F_IS_SATELLITE) != 0).all() and ((fo[roots] & abi.GLC_F_IS_SATELLITE) == 0).all()
 
 
+def test_scheduler_matches_walk_on_trees_with_many_progenitors(oracle_lib):
+    """Nodes with three and more progenitors (N-body-like trees): several siblings can become satellites of one parent in
+    the same round; their hooks touch the parent's pending hot halo, so they must run in the walk's (progenitor) order."""
+    from tests import emu
+
+    p = cases.standard_params(with_black_holes=True)
+    f = _forest(p, n_trees=8, seed=29, resolution=1.5e10)
+    rng = np.random.default_rng(3)
+    parent = f["parent"].copy()
+    grand = np.where(parent >= 0, parent[np.maximum(parent, 0)], -1)
+    move = (grand >= 0) & (rng.random(parent.size) < 0.3)
+    parent[move] = grand[move]  # re-hang on the grandparent: still earlier than its new parent
+    f["parent"] = parent.astype(np.int32)
+    assert np.bincount(parent[parent >= 0]).max() >= 4
+    o = oracle_lib.Oracle()
+    synthetic.install(o, p)
+    ro, fo, so, fco, co = o.forest_evolve(f, n_threads=4)
+    e = emu.EmuEvolver(64, 0, True, 2)
+    synthetic.install(e, p)
+    re, fe, se, fce, ce = e.forest_evolve(f)
+    np.testing.assert_array_equal(se, so)
+    np.testing.assert_array_equal(fe, fo)
+    assert ce == co and {k: fce[k] for k in fce if k != "rounds"} == {k: fco[k] for k in fco if k != "rounds"}
+    alive = so != PROMOTED
+    assert np.array_equal(re[alive], ro[alive])
+    assert fco["promotions"] + fco["node_mergers"] == parent.size - (parent < 0).sum()
+
+
 def test_tree_level_invariants(oracle_lib):
     p = cases.standard_params(with_black_holes=True)
     f = _forest(p, n_trees=10, seed=11)
