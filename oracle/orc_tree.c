@@ -237,7 +237,7 @@ static int evolve_to(tree_ctx *c, int i, double to, glc_forest_counters *fc, glc
     C->trials_failed += local.trials_failed;
     C->nodes += local.nodes;
     fc->evolve_calls++;
-    if (local.rhs_evaluations > 800 && getenv("ORC_DEBUG_LONG_CALLS"))
+    if (local.rhs_evaluations > 20000 && getenv("ORC_DEBUG_LONG_CALLS"))
         fprintf(stderr, "[orc_tree] node %d: %llu RHS evaluations in one evolve call (to t=%.6g, flags %d, M=%.4g)\n", i,
                 (unsigned long long)local.rhs_evaluations, to, c->flags[i], R(c, i)[GLC_P_BASIC_MASS]);
     if (!(status[0] == GLC_STATUS_SUCCESS && interrupt[0] == GLC_INT_NONE)) {
