@@ -328,6 +328,49 @@ static int launch_evolve(glc_evolver *ev, int n, unsigned long long *hc) {
     return 0;
 }
 
+// Evolves the listed arena nodes to completion on the warp-synchronous kernel and ADDS its counters to those already in
+// d_counters (used by launch_machine to finish nodes the machine did not).
+static int launch_evolve_list(glc_evolver *ev, const std::vector<int32_t> &list, unsigned long long *hc) {
+    const int m = (int)list.size();
+    int blocksPerSm = 0;
+    GLC_CHECK(ev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, evolve_kernel<ModelStandard>, kBlock, 0));
+    if (blocksPerSm < 1) blocksPerSm = 1;
+    int grid = std::min(ev->num_sms * blocksPerSm, (m + kBlock - 1) / kBlock);
+    if (grid < 1) grid = 1;
+    int rc = ensure_workspace(ev, ev->num_sms * blocksPerSm);
+    if (rc) return rc;
+    if (m > ev->order_cap) {
+        cudaFree(ev->d_order);
+        ev->d_order = nullptr;
+        GLC_CHECK(ev, cudaMalloc(&ev->d_order, sizeof(int32_t) * (size_t)m));
+        ev->order_cap = m;
+    }
+    GLC_CHECK(ev, cudaMemcpyAsync(ev->d_order, list.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ev->stream));
+    KernelArgs A{};
+    A.props = ev->d_props;
+    A.flags = ev->d_flags;
+    A.time_end = ev->d_time_end;
+    A.status = ev->d_status;
+    A.interrupt = ev->d_interrupt;
+    A.cap = ev->cap;
+    A.n = m;
+    A.ws = ev->d_ws;
+    A.nslots = ev->nslots;
+    A.work_counter = ev->d_work;
+    A.counters = ev->d_counters;
+    A.order = ev->d_order;
+    A.lanes = ev->d_lanes;
+    A.resume = 0;
+    A.budget = 0x7fffffff;
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
+    evolve_kernel<ModelStandard><<<grid, kBlock, 0, ev->stream>>>(A);
+    ev->launches++;
+    GLC_CHECK(ev, cudaGetLastError());
+    GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    return 0;
+}
+
 static void free_slots(glc_evolver *ev) {
     cudaFree(ev->d_slots.L);
     cudaFree(ev->d_slots.R);
@@ -400,6 +443,8 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     if (fresh) {
         GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
         GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 16, ev->stream));
+        // status = -1 until a node is written back: lets the host find nodes the machine never finished (see "stalled")
+        if (mode == 0) GLC_CHECK(ev, cudaMemsetAsync(ev->d_status, 0xff, sizeof(int32_t) * (size_t)n, ev->stream));
     } else
         GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long) * 2, ev->stream));
     if (mode != 0) ev->stream_started = true;
@@ -421,6 +466,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     if (hybrid) A.budget = 4096;
     const unsigned long long drainBelow = (unsigned long long)ev->drain_threshold;
     bool draining = false;
+    int stalled = 0;
     for (;;) {
         if (ev->slice_log > 1) fprintf(stderr, "[glc host] launching machine_kernel grid=%d budget=%d resume=%d hold=%d n=%d\n", grid, A.budget, A.resume, A.hold, n);
         machine_kernel<GLC_MTHREADS, GLC_MSLOTS><<<grid, GLC_MTHREADS, kMachineSmem, ev->stream>>>(A, ev->d_slots);
@@ -440,6 +486,23 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
         if (hc[6] >= (unsigned long long)n) break;
         if (ev->max_slices > 0 && ++nslice >= ev->max_slices) break;  // profiling aid: leaves the batch unfinished
         A.resume = 1;
+        if (mode == 0 && hybrid && parked == 0 && midEvaluation == 0 && ++stalled >= 2) {
+            // Stalled: no slot holds a node, yet not every node of the batch has been written back.  Seen once on the device
+            // (r01l_forest_4000_slices: 132 of 551 585 nodes of one batch; the slices then repeated for ever) and not yet
+            // understood.  Finish the nodes that were never written back on the warp-synchronous kernel -- the arena still
+            // holds their untouched input records and the result of a node does not depend on the kernel that evolves it.
+            std::vector<int32_t> h_status((size_t)n), missing;
+            GLC_CHECK(ev, cudaMemcpyAsync(h_status.data(), ev->d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ev->stream));
+            GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+            for (int i = 0; i < n; i++)
+                if (h_status[i] == -1) missing.push_back(i);
+            fprintf(stderr, "[glc] machine stalled with %llu of %d nodes done; finishing %zu nodes on the lane kernel\n", hc[6], n,
+                    missing.size());
+            if (missing.empty()) break;
+            int rc2 = launch_evolve_list(ev, missing, hc);
+            if (rc2) return rc2;
+            break;
+        }
         if (hybrid) {
             // every node has been handed out once done + parked covers the batch
             const bool queueDry = hc[6] + parked >= (unsigned long long)n;
