@@ -26,6 +26,8 @@
 
 using namespace glc;
 
+#include <cstdio>
+#include <cstdlib>
 #include "../../galacticus_b200/csrc/host/glc_forest.hpp"
 
 struct Emu {
@@ -215,6 +217,16 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
         }
         (*slices)++;
         if (hc[6] >= (unsigned long long)n) break;
+        {
+            // stall guard: every slot idle although nodes are missing (would repeat empty slices for ever)
+            bool occupied = false;
+            for (int s = 0; s < nslots; s++) occupied |= (sUnit[s] != U_IDLE);
+            if (!occupied && work >= A.n) {
+                fprintf(stderr, "[emu] machine stalled: %llu of %lld nodes done, no slot occupied\n", hc[6], (long long)n);
+                for (int64_t i = 0; i < n; i++) status[i] = GLC_STATUS_FAIL;
+                break;
+            }
+        }
         A.resume = 1;
         if (handover && work >= A.n) {
             // ---- hold: bring every active slot to an RK boundary, as the device's hold slices do
@@ -368,9 +380,17 @@ int emu_forest_evolve(void *h, int64_t n_nodes, const int32_t *parent, const dou
         }
         glc_counters c{};
         int64_t slices = 0;
+        static int n_batches = 0;
+        if (const char *mb = getenv("EMU_FOREST_MAX_BATCHES")) {
+            if (n_batches >= atoi(mb)) return 1;
+            n_batches++;
+        }
         int rc = emu_evolve_batch(h, m, buf.data(), bflags.data(), te.data(), status.data(), interrupt.data(), &c, nslots, budget,
                                   sort, machine, &slices);
         if (rc) return rc;
+        if (getenv("EMU_FOREST_MAX_BATCHES"))
+            fprintf(stderr, "[emu forest] batch of %lld nodes: %llu RHS, %lld slices, nodes counted %llu\n", (long long)m,
+                    (unsigned long long)c.rhs_evaluations, (long long)slices, (unsigned long long)c.nodes);
         for (int64_t k = 0; k < m; k++) {
             memcpy(F.R(list[k]), &buf[(size_t)k * GLC_NPROP], sizeof(double) * GLC_NPROP);
             if (status[k] != GLC_STATUS_SUCCESS || interrupt[k] != GLC_INT_NONE) {
