@@ -50,6 +50,22 @@ def main():
     pb.box_fractionOutflow = 1.0
     props, flags, t_end = cases.box_nodes(96, seed=4243, leaky=True)
     run("box_leaky_96", pb, props, flags, t_end, False)
+    forest_golden()
+
+
+def forest_golden():
+    """Tree level: a small seeded forest and what the CPU checker's walk (oracle/orc_tree.c) makes of it."""
+    p = cases.standard_params(with_black_holes=True)
+    f = synthetic.binary_split_forest(p, 5, 3.0e11, 2.5e10, seed=4245, mass_root_max=1.5e12)
+    o = orc.Oracle()
+    synthetic.install(o, p)
+    rec, flags, state, fc, c = o.forest_evolve(f, n_threads=1)
+    np.savez_compressed(os.path.join(HERE, "forest_5.npz"), records=rec, flags=flags, state=state,
+                        forest_counters=np.array([fc[k] for k in sorted(fc) if k != "rounds"], dtype=np.int64),
+                        forest_counter_names=np.array([k for k in sorted(fc) if k != "rounds"]),
+                        counters=np.array([c[k] for k in sorted(c)], dtype=np.int64), counter_names=np.array(sorted(c)),
+                        **{"in_" + k: v for k, v in f.items()})
+    print("forest_5", rec.shape, fc, c)
 
 
 if __name__ == "__main__":

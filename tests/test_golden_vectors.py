@@ -72,3 +72,47 @@ def test_cuda_reproduces_golden(name, machine):
     s, i, c = ev.evolve_batch(props, flags, g["t_end"])
     _check(g, props, flags, s, i, c)
     ev.close()
+
+
+# ---------------------------------------------------------------- tree level
+def _forest_case():
+    g = np.load(os.path.join(HERE, "forest_5.npz"))
+    f = {k[3:]: g[k] for k in g.files if k.startswith("in_")}
+    return g, f, cases.standard_params(with_black_holes=True)
+
+
+def _check_forest(g, rec, flags, state, fc, c):
+    np.testing.assert_array_equal(state, g["state"])
+    np.testing.assert_array_equal(flags, g["flags"])
+    assert {str(k): int(v) for k, v in zip(g["forest_counter_names"], g["forest_counters"])} == {k: v for k, v in fc.items() if k != "rounds"}
+    assert {str(k): int(v) for k, v in zip(g["counter_names"], g["counters"])} == c
+    alive = g["state"] != abi.GLC_FOREST_NODE_PROMOTED
+    assert np.array_equal(rec[alive], g["records"][alive]), "surviving node records differ from the golden forest"
+
+
+def test_oracle_walk_reproduces_golden_forest(oracle_lib):
+    g, f, p = _forest_case()
+    o = oracle_lib.Oracle()
+    synthetic.install(o, p)
+    _check_forest(g, *o.forest_evolve(f, n_threads=3))
+
+
+def test_scheduler_on_host_reproduces_golden_forest():
+    from tests import emu
+
+    g, f, p = _forest_case()
+    e = emu.EmuEvolver(nslots=48, budget=13, sort=True, machine=2)
+    synthetic.install(e, p)
+    _check_forest(g, *e.forest_evolve(f))
+
+
+@pytest.mark.gpu
+def test_cuda_forest_reproduces_golden_forest():
+    from galacticus_b200.evolver import Evolver
+
+    g, f, p = _forest_case()
+    ev = Evolver(0)
+    synthetic.install(ev, p)
+    _check_forest(g, *ev.forest_evolve(f))
+    ev.close()
+
