@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 SRC=galacticus_b200/csrc
-OUT=galacticus_b200/libglcb200.so
+OUT=${GLC_OUT:-galacticus_b200/libglcb200.so}
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
   -Xcompiler -fPIC,-ffp-contract=off -shared ${GLC_FMAD:--fmad=false} ${GLC_NVCC_EXTRA} \

@@ -58,6 +58,7 @@ struct glc_evolver {
     int *d_work = nullptr;
     unsigned long long *d_counters = nullptr;
     double *d_pow_ac = nullptr, *d_pow_kmt = nullptr;  // fastExponentiator tables
+    double *d_nfw_jx = nullptr, *d_nfw_jv = nullptr;   // inverse tabulation of the NFW specific angular momentum
     double pow_ac_exponent = 0.0;
     LaneState *d_lanes = nullptr;   // parked lane states, one per resident lane
     SlotArrays d_slots{};           // micro-task machine: per-slot continuations, split by access group
@@ -91,6 +92,12 @@ struct glc_evolver {
     int64_t slices = 0;
     float last_ms = 0.f;
     std::string err;
+#ifdef GLC_LEDGER
+    // debug build: node-ownership ledger (see glc_evolve_kernel.cuh GLC_LEDGER_*)
+    int *d_ledger = nullptr, *d_slot_busy = nullptr;
+    unsigned long long *d_ledger_err = nullptr;
+    int64_t ledger_cap = 0;
+#endif
 };
 
 static double now_s() {
@@ -286,7 +293,7 @@ static int launch_evolve(glc_evolver *ev, int n, unsigned long long *hc) {
     GLC_CHECK(ev, cudaEventRecord(ev->ev0, ev->stream));
     const int sorted = build_queue_order(ev, n);
     if (sorted < 0) return sorted;
-    KernelArgs A;
+    KernelArgs A{};
     A.props = ev->d_props;
     A.flags = ev->d_flags;
     A.time_end = ev->d_time_end;
@@ -328,49 +335,6 @@ static int launch_evolve(glc_evolver *ev, int n, unsigned long long *hc) {
     return 0;
 }
 
-// Evolves the listed arena nodes to completion on the warp-synchronous kernel and ADDS its counters to those already in
-// d_counters (used by launch_machine to finish nodes the machine did not).
-static int launch_evolve_list(glc_evolver *ev, const std::vector<int32_t> &list, unsigned long long *hc) {
-    const int m = (int)list.size();
-    int blocksPerSm = 0;
-    GLC_CHECK(ev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, evolve_kernel<ModelStandard>, kBlock, 0));
-    if (blocksPerSm < 1) blocksPerSm = 1;
-    int grid = std::min(ev->num_sms * blocksPerSm, (m + kBlock - 1) / kBlock);
-    if (grid < 1) grid = 1;
-    int rc = ensure_workspace(ev, ev->num_sms * blocksPerSm);
-    if (rc) return rc;
-    if (m > ev->order_cap) {
-        cudaFree(ev->d_order);
-        ev->d_order = nullptr;
-        GLC_CHECK(ev, cudaMalloc(&ev->d_order, sizeof(int32_t) * (size_t)m));
-        ev->order_cap = m;
-    }
-    GLC_CHECK(ev, cudaMemcpyAsync(ev->d_order, list.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ev->stream));
-    KernelArgs A{};
-    A.props = ev->d_props;
-    A.flags = ev->d_flags;
-    A.time_end = ev->d_time_end;
-    A.status = ev->d_status;
-    A.interrupt = ev->d_interrupt;
-    A.cap = ev->cap;
-    A.n = m;
-    A.ws = ev->d_ws;
-    A.nslots = ev->nslots;
-    A.work_counter = ev->d_work;
-    A.counters = ev->d_counters;
-    A.order = ev->d_order;
-    A.lanes = ev->d_lanes;
-    A.resume = 0;
-    A.budget = 0x7fffffff;
-    GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
-    evolve_kernel<ModelStandard><<<grid, kBlock, 0, ev->stream>>>(A);
-    ev->launches++;
-    GLC_CHECK(ev, cudaGetLastError());
-    GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, ev->stream));
-    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
-    return 0;
-}
-
 static void free_slots(glc_evolver *ev) {
     cudaFree(ev->d_slots.L);
     cudaFree(ev->d_slots.R);
@@ -381,6 +345,58 @@ static void free_slots(glc_evolver *ev) {
     ev->d_slots = SlotArrays{};
     ev->nslots_machine = 0;
 }
+
+#ifdef GLC_LEDGER
+static int ledger_setup(glc_evolver *ev, int n, KernelArgs &A, bool fresh) {
+    if (n > ev->ledger_cap) {
+        cudaFree(ev->d_ledger);
+        ev->d_ledger = nullptr;
+        GLC_CHECK(ev, cudaMalloc(&ev->d_ledger, sizeof(int) * (size_t)n));
+        ev->ledger_cap = n;
+    }
+    if (!ev->d_slot_busy) GLC_CHECK(ev, cudaMalloc(&ev->d_slot_busy, sizeof(int) * (size_t)ev->nslots_machine));
+    if (!ev->d_ledger_err) GLC_CHECK(ev, cudaMalloc(&ev->d_ledger_err, sizeof(unsigned long long) * 8));
+    if (fresh) {
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_ledger, 0xff, sizeof(int) * (size_t)n, ev->stream));
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_slot_busy, 0, sizeof(int) * (size_t)ev->nslots_machine, ev->stream));
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_ledger_err, 0, sizeof(unsigned long long) * 8, ev->stream));
+    }
+    A.ledger = ev->d_ledger;
+    A.slotBusy = ev->d_slot_busy;
+    A.ledgerErr = ev->d_ledger_err;
+    return 0;
+}
+// prints what the ledger knows: violation counters, nodes never fetched, nodes fetched but never written back and the
+// state of the slots that took them
+static int ledger_report(glc_evolver *ev, int n, const char *tag) {
+    unsigned long long herr[8];
+    std::vector<int> led((size_t)n);
+    int work = 0;
+    GLC_CHECK(ev, cudaMemcpy(herr, ev->d_ledger_err, sizeof herr, cudaMemcpyDeviceToHost));
+    GLC_CHECK(ev, cudaMemcpy(led.data(), ev->d_ledger, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+    GLC_CHECK(ev, cudaMemcpy(&work, ev->d_work, sizeof(int), cudaMemcpyDeviceToHost));
+    long long never = 0, held = 0, done = 0;
+    std::vector<int> heldNodes;
+    for (int i = 0; i < n; i++) {
+        if (led[i] == -1) never++;
+        else if (led[i] == -2) done++;
+        else { held++; if (heldNodes.size() < 24) heldNodes.push_back(i); }
+    }
+    fprintf(stderr, "[glc ledger %s] n=%d work_counter=%d never-fetched=%lld held=%lld done=%lld | violations: double-fetch=%llu "
+                    "foreign-writeback=%llu two-lanes-in-slot=%llu wrong-queue=%llu\n",
+            tag, n, work, never, held, done, herr[0], herr[1], herr[2], herr[3]);
+    for (int node : heldNodes) {
+        const int slot = led[node] - 1;
+        LaneState L;
+        int unit = -99;
+        cudaMemcpy(&L, ev->d_slots.L + slot, sizeof(LaneState), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&unit, ev->d_slots.unit + slot, sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "   node %d held by slot %d (block %d): slot.unit=%d L.node=%d phase=%d heavy=%d stage=%d x=%.6g x1=%.6g h=%.3g\n",
+                node, slot, slot / GLC_MSLOTS, unit, L.node, L.phase, L.heavy, L.stage, L.x, L.x1, L.h);
+    }
+    return 0;
+}
+#endif
 
 // One batch on the micro-task machine (standard model): same slice protocol as launch_evolve.
 // mode 0: one batch, fresh queue, run to completion (hybrid) or in user time slices
@@ -411,7 +427,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     GLC_CHECK(ev, cudaEventRecord(ev->ev0, ev->stream));
     const int sorted = mode == 0 ? build_queue_order(ev, n) : 0;  // a growing queue is served in submission order
     if (sorted < 0) return sorted;
-    KernelArgs A;
+    KernelArgs A{};
     A.props = ev->d_props;
     A.flags = ev->d_flags;
     A.time_end = ev->d_time_end;
@@ -429,6 +445,12 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     A.budget = ev->slice_budget > 0 ? ev->slice_budget : 0x7fffffff;
     if (mode == 1) A.budget = streamBudget > 0 ? streamBudget : 4096;
     A.debug = nullptr;
+    A.ledger = nullptr;
+    A.slotBusy = nullptr;
+    A.ledgerErr = nullptr;
+#ifdef GLC_LEDGER
+    if (int rcl = ledger_setup(ev, n, A, fresh)) return rcl;
+#endif
 #ifdef GLC_DEBUG_HANG
     static int *h_dbg = nullptr;
     const int nDbg = gridMax * (GLC_MTHREADS / 32) * 8;
@@ -443,10 +465,10 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     if (fresh) {
         GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
         GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 16, ev->stream));
-        // status = -1 until a node is written back: lets the host find nodes the machine never finished (see "stalled")
-        if (mode == 0) GLC_CHECK(ev, cudaMemsetAsync(ev->d_status, 0xff, sizeof(int32_t) * (size_t)n, ev->stream));
+        // status = GLC_STATUS_PENDING (0x80808080) until a node is written back
+        if (mode == 0) GLC_CHECK(ev, cudaMemsetAsync(ev->d_status, 0x80, sizeof(int32_t) * (size_t)n, ev->stream));
     } else
-        GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long) * 2, ev->stream));
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long) * 3, ev->stream));
     if (mode != 0) ev->stream_started = true;
     const double t_start = now_s();
     int nslice = 0;
@@ -467,13 +489,14 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     const unsigned long long drainBelow = (unsigned long long)ev->drain_threshold;
     bool draining = false;
     int stalled = 0;
+    unsigned long long prevDone = ~0ull, prevRhs = ~0ull, prevParked = ~0ull;
     for (;;) {
         if (ev->slice_log > 1) fprintf(stderr, "[glc host] launching machine_kernel grid=%d budget=%d resume=%d hold=%d n=%d\n", grid, A.budget, A.resume, A.hold, n);
         machine_kernel<GLC_MTHREADS, GLC_MSLOTS><<<grid, GLC_MTHREADS, kMachineSmem, ev->stream>>>(A, ev->d_slots);
         ev->launches++;
         ev->slices++;
         GLC_CHECK(ev, cudaGetLastError());
-        GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 9, cudaMemcpyDeviceToHost,
+        GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 10, cudaMemcpyDeviceToHost,
                                       ev->stream));
         if (mode != 1 && ev->slice_budget <= 0 && !hybrid) break;
         GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
@@ -482,27 +505,30 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
             fprintf(stderr, "[glc slice %lld] t=%.3f ms done=%llu/%d rhs=%llu accepted=%llu parked=%llu mid-evaluation=%llu%s\n",
                     (long long)ev->slices, 1e3 * (now_s() - t_start), hc[6], n, hc[2], hc[0], hc[7], hc[8], draining ? " (hold)" : "");
         const unsigned long long parked = hc[7], midEvaluation = hc[8];
-        GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long) * 2, ev->stream));
+        GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long) * 3, ev->stream));
         if (hc[6] >= (unsigned long long)n) break;
         if (ev->max_slices > 0 && ++nslice >= ev->max_slices) break;  // profiling aid: leaves the batch unfinished
         A.resume = 1;
-        if (mode == 0 && hybrid && parked == 0 && midEvaluation == 0 && ++stalled >= 2) {
-            // Stalled: no slot holds a node, yet not every node of the batch has been written back.  Seen once on the device
-            // (r01l_forest_4000_slices: 132 of 551 585 nodes of one batch; the slices then repeated for ever) and not yet
-            // understood.  Finish the nodes that were never written back on the warp-synchronous kernel -- the arena still
-            // holds their untouched input records and the result of a node does not depend on the kernel that evolves it.
-            std::vector<int32_t> h_status((size_t)n), missing;
-            GLC_CHECK(ev, cudaMemcpyAsync(h_status.data(), ev->d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ev->stream));
-            GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
-            for (int i = 0; i < n; i++)
-                if (h_status[i] == -1) missing.push_back(i);
-            fprintf(stderr, "[glc] machine stalled with %llu of %d nodes done; finishing %zu nodes on the lane kernel\n", hc[6], n,
-                    missing.size());
-            if (missing.empty()) break;
-            int rc2 = launch_evolve_list(ev, missing, hc);
-            if (rc2) return rc2;
-            break;
-        }
+        // No-progress guard (every mode): a slice that executed no unit at all (hc[9]) and changed no counter cannot be
+        // followed by a better one.  Three in a row end the call with an error instead of repeating empty slices for ever (the reference finishes every tree or
+        // reports: tasks/evolve_forests/_class.F90:887-897).
+        if (hc[9] == 0 && hc[6] == prevDone && hc[2] == prevRhs && parked == prevParked) {
+            if (++stalled >= 3) {
+                char msg[256];
+                snprintf(msg, sizeof msg,
+                         "micro-task machine made no progress in 3 consecutive slices: %llu of %d nodes done, %llu slots occupied "
+                         "(%llu mid-evaluation)", hc[6], n, parked, midEvaluation);
+                ev->err = msg;
+#ifdef GLC_LEDGER
+                ledger_report(ev, n, "stalled");
+#endif
+                return GLC_ERR_STALLED;
+            }
+        } else
+            stalled = 0;
+        prevDone = hc[6];
+        prevRhs = hc[2];
+        prevParked = parked;
         if (hybrid) {
             // every node has been handed out once done + parked covers the batch
             const bool queueDry = hc[6] + parked >= (unsigned long long)n;
@@ -622,6 +648,20 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     }
     GLC_CHECK(ev, cudaEventRecord(ev->ev1, ev->stream));
     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+#ifdef GLC_LEDGER
+    {
+        unsigned long long herr[8];
+        GLC_CHECK(ev, cudaMemcpy(herr, ev->d_ledger_err, sizeof herr, cudaMemcpyDeviceToHost));
+        if (herr[0] | herr[1] | herr[2] | herr[3] || (mode != 1 && hc[6] != (unsigned long long)n) || ev->slice_log) ledger_report(ev, n, "end of call");
+    }
+#endif
+    // a call that runs to completion must have written back every node of the batch
+    if (mode != 1 && ev->max_slices <= 0 && hc[6] != (unsigned long long)n) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "micro-task machine returned with %llu of %d nodes written back", hc[6], n);
+        ev->err = msg;
+        return GLC_ERR_STALLED;
+    }
     return 0;
 }
 
@@ -705,6 +745,8 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaFree(ev->d_collect_list);
     cudaFree(ev->d_pow_ac);
     cudaFree(ev->d_pow_kmt);
+    cudaFree(ev->d_nfw_jx);
+    cudaFree(ev->d_nfw_jv);
     cudaFree(ev->d_lanes);
     free_slots(ev);
     cudaFree(ev->d_order);
@@ -752,6 +794,17 @@ int glc_evolver_set_params(glc_evolver *ev, const glc_params *params) {
         pow_table_spacing(1.0e-3, 1.0, (int)ac.size(), ev->tables.powAcDx, ev->tables.powAcInvDx);
         pow_table_spacing(1.0, 1000.0, (int)kmt.size(), ev->tables.powKmtDx, ev->tables.powKmtInvDx);
         ev->pow_ac_exponent = params->adiabaticOmega;
+    }
+    if (params->model == GLC_MODEL_STANDARD && !ev->d_nfw_jx) {
+        std::vector<double> xs, js;
+        build_nfw_j_table(xs, js);
+        GLC_CHECK(ev, cudaMalloc(&ev->d_nfw_jx, sizeof(double) * xs.size()));
+        GLC_CHECK(ev, cudaMalloc(&ev->d_nfw_jv, sizeof(double) * js.size()));
+        GLC_CHECK(ev, cudaMemcpy(ev->d_nfw_jx, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice));
+        GLC_CHECK(ev, cudaMemcpy(ev->d_nfw_jv, js.data(), sizeof(double) * js.size(), cudaMemcpyHostToDevice));
+        ev->tables.nfwJx = ev->d_nfw_jx;
+        ev->tables.nfwJv = ev->d_nfw_jv;
+        ev->tables.nfwJN = (int)xs.size();
     }
     ev->params = *params;
     ev->params_set = true;
@@ -1012,7 +1065,7 @@ int glc_stream_begin(glc_evolver *ev, int64_t capacity) {
         ev->collected_cap = ev->cap;
     }
     GLC_CHECK(ev, cudaMemsetAsync(ev->d_collected, 0, (size_t)ev->cap, ev->stream));
-    GLC_CHECK(ev, cudaMemsetAsync(ev->d_status, 0xff, sizeof(int32_t) * (size_t)ev->cap, ev->stream));  // -1 = pending
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_status, 0x80, sizeof(int32_t) * (size_t)ev->cap, ev->stream));  // GLC_STATUS_PENDING
     rc = upload_constants(ev);
     if (rc) return rc;
     ev->stream_active = true;
@@ -1087,7 +1140,7 @@ __global__ void collect_list_kernel(const int32_t *__restrict__ status, unsigned
                                     int64_t *list) {
     // list[0] = count, list[1..] = tickets
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        if (status[i] >= 0 && !collected[i]) {
+        if (status[i] != GLC_STATUS_PENDING && !collected[i]) {
             const unsigned long long k = atomicAdd(reinterpret_cast<unsigned long long *>(list), 1ull);
             if ((int64_t)k < maxNodes) {
                 list[1 + k] = i;

@@ -136,6 +136,10 @@ struct DeviceTables {
     const double *powAc, *powKmt;
     int powAcN, powKmtN;
     double powAcDx, powAcInvDx, powKmtDx, powKmtInvDx;  // lattice spacing and its reciprocal, computed once on the host
+    // inverse tabulation of the scale-free NFW specific angular momentum (NFW.F90:589-639; numerical/tabulations_inverse.F90):
+    // nfwJx[k] = 2^(k/30) on the octave lattice, nfwJv[k] = sqrt(4 pi m(x_k) x_k), built once on the host
+    const double *nfwJx, *nfwJv;
+    int nfwJN;
 };
 
 struct LaneState;
@@ -166,6 +170,10 @@ struct KernelArgs {
     double *slotYt;                // [nslots][NY]
     int *slotUnit;                 // drain: pending-unit words (a finished slot is marked -1)
     int drainSparse;               // drain: 1 = one node per warp (lane 0 only): the last nodes run at lone-lane speed
+    // GLC_LEDGER builds (debug): node-ownership ledger and per-slot execution flags, see glc_machine.cuh
+    int *ledger;                   // [n] -1 = never fetched, s+1 = held by slot s, -2 = written back
+    int *slotBusy;                 // [nslots] 1 while a lane executes a unit of the slot
+    unsigned long long *ledgerErr; // [8] violation counters
 };
 
 // Per-node context kept in registers while a node is resident in a thread.

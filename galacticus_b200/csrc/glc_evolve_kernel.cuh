@@ -43,6 +43,28 @@
 
 namespace glc {
 
+// GLC_LEDGER (debug builds of the machine): every node records which slot holds it from fetch to write-back; a second
+// fetch, a write-back by a slot that does not own the node, or a node left owned at the end of a batch are violations.
+#if defined(GLC_LEDGER) && defined(__CUDACC__)
+#define GLC_LEDGER_FETCH(A, M, node)                                                       \
+    do {                                                                                   \
+        if ((A).ledger) {                                                                  \
+            const int old__ = atomicExch(&(A).ledger[node], (M).dbgSlot + 1);              \
+            if (old__ != -1) atomicAdd(&(A).ledgerErr[0], 1ull);                           \
+        }                                                                                  \
+    } while (0)
+#define GLC_LEDGER_DONE(A, M, node)                                                        \
+    do {                                                                                   \
+        if ((A).ledger) {                                                                  \
+            const int old__ = atomicExch(&(A).ledger[node], -2);                           \
+            if (old__ != (M).dbgSlot + 1) atomicAdd(&(A).ledgerErr[1], 1ull);              \
+        }                                                                                  \
+    } while (0)
+#else
+#define GLC_LEDGER_FETCH(A, M, node) ((void)0)
+#define GLC_LEDGER_DONE(A, M, node) ((void)0)
+#endif
+
 // Cash-Karp tableau (Cash & Karp 1990). Row s = weights of k1..k6 used to build the input of
 // stage s (s=1..5 -> k2..k6; s=6 -> 5th-order solution); row 0 = error weights (5th-4th order).
 #define GLC_RK_B_INIT                                                                                    \
@@ -101,6 +123,7 @@ struct LaneMem {
     const KernelArgs *A;
     double *ws;       // this lane's / slot's first workspace word
     int64_t wstride;  // nslots: SoA over resident lanes (evolve_kernel); 1: one contiguous record per slot (machine)
+    int dbgSlot = -1; // GLC_LEDGER builds: id of the slot that runs this lane state
     GLC_DEVICE_METHOD double &W(int vec, int comp) const { return ws[((int64_t)vec * NY + comp) * wstride]; }
     GLC_DEVICE_METHOD double &AR(int prop, int node) const { return A->props[(int64_t)prop * A->cap + node]; }
 };
@@ -156,6 +179,7 @@ GLC_UNROLL_RK
     }
     A.status[node] = L.nodeStatus;
     A.interrupt[node] = code;
+    GLC_LEDGER_DONE(A, M, node);
     L.nDone++;
     L.phase = PH_FETCH;
 }
@@ -177,6 +201,7 @@ GLC_DEVICE_INLINE void lane_prepare(LaneState &L, const LaneMem &M, double (&yt)
                 return;
             }
             L.node = A.order ? A.order[q] : q;
+            GLC_LEDGER_FETCH(A, M, L.node);
             L.nNodes++;
             L.ctx.flags = A.flags[L.node];
             L.tEnd = A.time_end[L.node];
@@ -375,6 +400,7 @@ GLC_UNROLL_RK
                     // errorStatusUnderflow: node left at its saved values
                     A.status[L.node] = GLC_STATUS_UNDERFLOW;
                     A.interrupt[L.node] = GLC_INT_NONE;
+                    GLC_LEDGER_DONE(A, M, L.node);
                     L.nDone++;
                     L.phase = PH_FETCH;
                     continue;
@@ -566,6 +592,7 @@ GLC_DEVICE_INLINE bool drain_iterate(LaneState &L, LaneMem &M, const KernelArgs 
             for (int i = 0; i < NY; i++) yt[i] = A.slotYt[(int64_t)slotHeld * NY + i];
             M.ws = A.ws + (int64_t)slotHeld * (WS_NVEC * NY);
             M.wstride = 1;
+            M.dbgSlot = slotHeld;
             fresh = true;
             break;
         }

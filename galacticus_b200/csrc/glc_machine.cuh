@@ -33,7 +33,6 @@ enum Unit : int {
     U_STRUCT,       // structure solver: one (iteration, component) visit up to its root find
     U_ROOT_AC,      // Brent step + adiabatic-contraction function
     U_STRUCT_FIN,   // structure solver: digest the root, fixed-point update
-    U_ROOT_J,       // Brent step + specific-angular-momentum function (first-guess radius)
     U_SFR_BEGIN,    // Krumholz-McKee-Tumlinson set-up
     U_ROOT_TRUNC,   // Brent step + surface-density truncation function
     U_SFR_MID,      // after the truncation radius: second root find or the integration intervals
@@ -50,16 +49,16 @@ typedef ModelStandard MS;
 
 struct RhsState {
     Work w;
-    double nfwNorm, hist[4], fit;
-    double j, radius, lnj;
+    double hist[4], fit;
+    double j, radius;
     MS::AcProblem ac;
     MS::SfrProblem sfr;
     double lo[2], hi[2], total, psiDisk, rinfall, logSlopeT;
-    int count, comp, active, bad, structureOnly, go, dOn, coolOn, radiusOn, two, nIv, iv, guess, pad;
+    int count, comp, active, bad, structureOnly, go, dOn, coolOn, radiusOn, two, nIv, iv;
 };
 
 // Everything a root-find unit touches: the Brent state and the parameters of the function being solved.
-//   AC    p = {nfwNorm, rs, rvir, fi, fd, radius, bterm}      J     p = {nfwNorm, rs, lnj}
+//   AC    p = {dmoNorm, dmoScale, rvir, fi, fd, radius, bterm}
 //   TRUNC/CRIT p = {sigma0, rdisk, sigmaTrunc, xh}
 //   COOL  p = {coolXH, coolFHn, coolEfrac, coolLambda, tvir, coolTavail, hhRho0, hhRcore, hhRouter, hhValid}
 struct RootState {
@@ -155,14 +154,13 @@ GLC_DEVICE_INLINE void m_struct_next(const SlotRef &S) {
 template <int UNIT>
 GLC_DEVICE_INLINE RootOptions m_root_options() {
     return UNIT == U_ROOT_AC     ? MS::ac_root_options()
-           : UNIT == U_ROOT_J    ? MS::jroot_options()
            : UNIT == U_ROOT_COOL ? MS::cooling_root_options()
                                  : MS::sfr_root_options();
 }
 // unit that digests the finished root find of type UNIT
 template <int UNIT>
 GLC_DEVICE_INLINE int m_root_done_unit() {
-    return (UNIT == U_ROOT_AC || UNIT == U_ROOT_J) ? U_STRUCT_FIN
+    return (UNIT == U_ROOT_AC) ? U_STRUCT_FIN
            : UNIT == U_ROOT_TRUNC                  ? U_SFR_MID
            : UNIT == U_ROOT_CRIT                   ? U_SFR_MID2
                                                    : U_RK;
@@ -265,6 +263,7 @@ GLC_DEVICE_NOINLINE void unit_rhs_begin(const SlotRef S) {
     RhsState &R = S.R;
     NodeCtx &c = S.L.ctx;
     Work w;
+    GLC_COUNT(6);
     MS::work_clear(w);
     MS::halo_scales(c, S.L.ts, w);
     MS::hh_profile(c, S.yt, w);
@@ -273,7 +272,7 @@ GLC_DEVICE_NOINLINE void unit_rhs_begin(const SlotRef S) {
     R.bad = 0;
     R.hist[0] = R.hist[1] = R.hist[2] = R.hist[3] = -1.0;
     R.fit = 2.0 * GLC_PARAMS.structureSolutionTolerance;
-    R.nfwNorm = w.plausible ? MS::nfw_norm(c, w) : 0.0;
+    if (w.plausible) MS::dmo_prepare(c, w);
     R.w = w;
     if (!w.plausible) {
         m_after_struct(S);
@@ -295,24 +294,8 @@ GLC_DEVICE_NOINLINE void unit_struct(const SlotRef S) {
     double radius = 0.0, velocity = 0.0;
     R.active++;
     R.j = j;
-    R.guess = 0;
     if (R.count == 1) {
-        bool guess, needRoot;
-        MS::structure_first_pass(c, R.w, R.nfwNorm, comp, j, radius, velocity, guess, needRoot);
-        if (needRoot) {
-            if (j > 0.0) {
-                R.lnj = dm_log(j);
-                const double lnrv = dm_log(R.w.rvir);
-                R.guess = 1;
-                S.p[0] = R.nfwNorm;
-                S.p[1] = c.dmScale;
-                S.p[2] = R.lnj;
-                m_root_start<U_ROOT_J>(S, lnrv - 4.0, lnrv, false, 0.0, 0.0);
-                return;
-            }
-            radius = 0.0;  // nfw_radius_from_j of a non-positive j
-        }
-        if (guess) velocity = MS::structure_guess_velocity(c, R.nfwNorm, radius);
+        MS::structure_first_pass(c, R.w, comp, j, radius, velocity);
         MS::structure_store(c, comp, radius, velocity);
         R.comp++;
         m_struct_next(S);
@@ -329,11 +312,11 @@ GLC_DEVICE_NOINLINE void unit_struct(const SlotRef S) {
     P.fd = P.fi = P.bterm = 0.0;
     P.rup = P.rInit = radius;
     P.need = 0;
-    if (GLC_PARAMS.adiabaticContraction && !(radius <= 0.0)) MS::ac_setup(c, S.yt, R.w, R.nfwNorm, radius, P);
+    if (GLC_PARAMS.adiabaticContraction && !(radius <= 0.0)) MS::ac_setup(c, S.yt, R.w, radius, P);
     R.ac = P;
     if (P.need) {
-        S.p[0] = R.nfwNorm;
-        S.p[1] = c.dmScale;
+        S.p[0] = R.w.dmoNorm;
+        S.p[1] = R.w.dmoScale;
         S.p[2] = R.w.rvir;
         S.p[3] = P.fi;
         S.p[4] = P.fd;
@@ -347,23 +330,17 @@ GLC_DEVICE_NOINLINE void unit_struct(const SlotRef S) {
     }
 }
 
-// digest the root of a structure visit: first-guess radius, or the contracted dark-matter mass and the
-// fixed-point update
+// digest the root of a structure visit: the contracted dark-matter mass and the fixed-point update
 GLC_DEVICE_NOINLINE void unit_struct_fin(const SlotRef S) {
     RhsState &R = S.R;
     NodeCtx &c = S.L.ctx;
     const int comp = R.comp;
-    double radius, velocity;
-    if (R.guess) {
-        radius = (S.B.status != 0) ? R.w.rvir : dm_exp(S.B.result);
-        velocity = MS::structure_guess_velocity(c, R.nfwNorm, radius);
-    } else {
-        const double rs = c.dmScale;
+    double radius = R.radius, velocity;
+    {
         const double fDm = 1.0 - GLC_PARAMS.OmegaBaryon / GLC_PARAMS.OmegaMatter;
-        radius = R.radius;
         double mdm;
         if (!GLC_PARAMS.adiabaticContraction)
-            mdm = MS::nfw_mass(R.nfwNorm, rs, radius);
+            mdm = MS::dmo_mass(R.w.dmoNorm, R.w.dmoScale, radius);
         else if (radius <= 0.0)
             mdm = 0.0;
         else {
@@ -372,7 +349,7 @@ GLC_DEVICE_NOINLINE void unit_struct_fin(const SlotRef S) {
                 rInit = S.B.result;
                 if (S.B.status != 0) R.bad = 1;
             }
-            mdm = fDm * MS::nfw_mass(R.nfwNorm, rs, rInit);
+            mdm = fDm * MS::dmo_mass(R.w.dmoNorm, R.w.dmoScale, rInit);
         }
         MS::structure_update(c, S.yt, R.w, R.j, mdm, R.count, R.hist[2 * comp], R.hist[2 * comp + 1], R.fit, R.bad, radius,
                              velocity);
@@ -398,14 +375,13 @@ GLC_DEVICE_NOINLINE void unit_root(const SlotRef S) {
         P.fd = S.p[4];
         P.bterm = S.p[6];
         fx = MS::ac_function(S.p[0], S.p[1], w, P, S.p[5], x);
-    } else if (UNIT == U_ROOT_J) {
-        fx = MS::jroot_function(S.p[0], S.p[1], S.p[2], x);
     } else if (UNIT == U_ROOT_TRUNC || UNIT == U_ROOT_CRIT) {
         MS::Kmt k;
         k.sigma0 = S.p[0];
         k.rdisk = S.p[1];
         k.sigmaTrunc = S.p[2];
         k.xh = S.p[3];
+        GLC_COUNT(4);
         fx = (UNIT == U_ROOT_TRUNC) ? MS::sfr_trunc_function(k, x) : MS::sfr_crit_function(k, x);
     } else {
         GLC_COUNT(3);
@@ -452,6 +428,7 @@ GLC_DEVICE_NOINLINE void unit_sfr_mid2(const SlotRef S) {
 GLC_DEVICE_NOINLINE void unit_qag(const SlotRef S) {
     RhsState &R = S.R;
     const MS::Kmt k = R.sfr.k;
+    GLC_COUNT(7);
     qag_pass(S.Q, [&](double r) {
         GLC_COUNT(2);
         return MS::sfr_integrand(k, r);
@@ -504,7 +481,6 @@ GLC_DEVICE_INLINE bool machine_step(const SlotRef &S, const LaneMem &M) {
         case U_STRUCT: unit_struct(S); break;
         case U_STRUCT_FIN: unit_struct_fin(S); break;
         case U_ROOT_AC: unit_root<U_ROOT_AC>(S); break;
-        case U_ROOT_J: unit_root<U_ROOT_J>(S); break;
         case U_ROOT_TRUNC: unit_root<U_ROOT_TRUNC>(S); break;
         case U_ROOT_CRIT: unit_root<U_ROOT_CRIT>(S); break;
         case U_ROOT_COOL: unit_root<U_ROOT_COOL>(S); break;
@@ -574,6 +550,7 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
 #endif
     int warpLast = -1;
     (void)warpLast;
+    unsigned int unitsDone = 0;  // unit executions of this warp in this slice (lane 0's copy is reported)
 #pragma unroll 1
     for (int it = 0; it < A.budget; ++it) {
         // ---- lane 0 reserves up to 32 entries of the block's CURRENT unit.  The whole block works on one unit
@@ -664,9 +641,17 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
             const int64_t slot = base + s;
             const SlotRef S = slot_ref(slots, slot);
             LaneMem M{&A, A.ws + slot * (WS_NVEC * NY), 1};
+#ifdef GLC_LEDGER
+            M.dbgSlot = (int)slot;
+            if (A.slotBusy && atomicExch(&A.slotBusy[slot], 1) != 0) atomicAdd(&A.ledgerErr[2], 1ull);  // two lanes in one slot
+            if (A.slotBusy && S.unit != u && !(u == U_RK && S.unit == U_IDLE)) atomicAdd(&A.ledgerErr[3], 1ull);  // wrong queue
+#endif
             S.unit = u;  // the queue a slot sits in IS its pending unit
             machine_step(S, M);
             const int nu = S.unit;
+#ifdef GLC_LEDGER
+            if (A.slotBusy) atomicExch(&A.slotBusy[slot], 0);
+#endif
             __threadfence_block();  // release: continuation stores before the queue entry
             if (nu == U_IDLE || (A.hold && nu == U_RHS_BEGIN))
                 atomicAdd(&s_idle, 1);
@@ -679,6 +664,7 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
         __syncwarp();
         GLC_DBG(0, 5);
         warpLast = u;
+        unitsDone += (unsigned int)take;
     }
     GLC_DBG(0, 9);
     __syncthreads();
@@ -705,6 +691,7 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0 && v) atomicAdd(&A.counters[k], (unsigned long long)v);
     }
+    if (lane == 0 && unitsDone) atomicAdd(&A.counters[9], (unsigned long long)unitsDone);
 }
 
 // compacts the ids of the slots held at an RK boundary into a list for drain_kernel; score = predicted number of

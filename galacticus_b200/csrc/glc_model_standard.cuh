@@ -13,8 +13,7 @@
 // (glc_numerics.cuh).
 //
 // Documented deviations from quickTest.xml ("out of scope / next"):
-// hotHaloRamPressureStripping=virialRadius; ADAF tabulations supplied by the host (GLC_TABLE_ADAF); direct
-// solve for the first-guess radius; per-solve reset of the oscillation history; beta = 2/3.
+// hotHaloRamPressureStripping=virialRadius; ADAF tabulations supplied by the host (GLC_TABLE_ADAF); beta = 2/3.
 #pragma once
 
 #include "glc_common.cuh"
@@ -31,6 +30,8 @@ struct Work {
     // cooling: CIE table values at the node's (T_vir, Z_hot), looked up once per RHS call
     double coolLambda, coolEfrac, coolXH, coolFHn, coolTavail;
     bool plausible, solvable;
+    // dark-matter-only profile (darkMatterProfileDMO): M(<r) = dmoNorm * m(r / dmoScale), see dmo_prepare
+    double dmoNorm, dmoScale;
 };
 
 GLC_DEVICE_INLINE double mass_to_fraction(double ab, double mass) {
@@ -311,13 +312,54 @@ struct ModelStandard {
         if (x >= 1.0e-6) return dm_log(1.0 + x) - x / (1.0 + x);
         return x * x * (0.5 + x * (-2.0 / 3.0 + x * (0.75 + x * (-0.8))));
     }
-    // NFW M(<r) = nfwNorm * m(r/rs), nfwNorm = M_vir / m(c)  (NFW.F90:254-255,444-464)
-    GLC_DEVICE_INLINE double nfw_norm(const NodeCtx &c, const Work &w) {
-        const double conc = w.rvir / c.dmScale;
-        return c.basicMass / (dm_log(1.0 + conc) - conc / (1.0 + conc));
+    // darkMatterProfileDMO.  NFW (mass_distributions/spherical/NFW.F90:254-255,444-464): M(<r) = norm * m(r / r_s) with
+    // norm = M_vir / m(c); isothermal (mass_distributions/spherical/isothermal.F90:150-205,287-302; mass = M_vir,
+    // lengthReference = r_vir): M(<r) = 4 pi rho_n L^2 r.
+    GLC_DEVICE_INLINE bool dmo_isothermal() { return GLC_PARAMS.darkMatterProfileDMO == GLC_DMO_ISOTHERMAL; }
+    GLC_DEVICE_INLINE void dmo_prepare(const NodeCtx &c, Work &w) {
+        if (dmo_isothermal()) {
+            const double L = w.rvir;
+            const double rhoN = c.basicMass / 4.0 / kPi / (L * L * L);
+            w.dmoNorm = 4.0 * kPi * rhoN * (L * L);
+            w.dmoScale = L;
+        } else {
+            const double conc = w.rvir / c.dmScale;
+            w.dmoNorm = c.basicMass / (dm_log(1.0 + conc) - conc / (1.0 + conc));
+            w.dmoScale = c.dmScale;
+        }
     }
-    GLC_DEVICE_INLINE double nfw_mass(double nfwNorm, double rs, double radius) {
-        return nfwNorm * nfw_mass_scale_free(radius / rs);
+    GLC_DEVICE_INLINE double dmo_mass(double norm, double scale, double radius) {
+        if (dmo_isothermal()) return norm * radius;
+        return norm * nfw_mass_scale_free(radius / scale);
+    }
+    // massDistribution_%rotationCurve(radius) of the dark-matter-only profile
+    GLC_DEVICE_INLINE double dmo_rotation_curve(const Work &w, double radius) {
+        if (dmo_isothermal()) return sqrt(kGInternal * w.dmoNorm);  // velocityRotation, isothermal.F90:196-204
+        return (radius > 0.0) ? sqrt(kGInternal * dmo_mass(w.dmoNorm, w.dmoScale, radius) / radius) : 0.0;
+    }
+    // massDistribution_%radiusFromSpecificAngularMomentum(j).  NFW.F90:589-625: inverse tabulation of the scale-free
+    // specific angular momentum sqrt(4 pi m(x) x) on the octave lattice x_k = 2^(k/30), linear interpolation of x in j
+    // (numerical/tabulations_inverse.F90:202-245); the lattice is tabulated once on the host over 2^-40 .. 2^40 (the
+    // reference grows it octave by octave on demand; values on a pinned lattice do not depend on its extent).
+    // isothermal.F90:350-370: r = j / sqrt(4 pi rho_n L^2) / sqrt(G).
+    GLC_DEVICE_INLINE double dmo_radius_from_j(const NodeCtx &c, const Work &w, double j) {
+        if (!(j > 0.0)) return 0.0;
+        if (dmo_isothermal()) return j / sqrt(w.dmoNorm) / sqrt(kGInternal);
+        const double rs = c.dmScale, conc = w.rvir / rs;
+        const double rhoN = c.basicMass / 4.0 / kPi / (rs * rs * rs) / (dm_log(1.0 + conc) - conc / (1.0 + conc));
+        const double jsf = j / sqrt(kGInternal * rhoN) / (rs * rs);
+        const double *__restrict__ xs = GLC_TABLES.nfwJx, *__restrict__ js = GLC_TABLES.nfwJv;
+        int lo = 0, hi = GLC_TABLES.nfwJN - 1;
+        while (hi > lo + 1) {
+            const int mid = (hi + lo) >> 1;
+            if (GLC_LDG(js + mid) > jsf)
+                hi = mid;
+            else
+                lo = mid;
+        }
+        const double x = GLC_LDG(xs + lo) + (jsf - GLC_LDG(js + lo)) / (GLC_LDG(js + lo + 1) - GLC_LDG(js + lo)) *
+                                                (GLC_LDG(xs + lo + 1) - GLC_LDG(xs + lo));
+        return x * rs;
     }
     GLC_DEVICE_INLINE double ac_orbital_mean(const Work &w, double radius) {
         // sphericalAdiabaticGnedin2004RadiusOrbitalMean, adiabatic_Gnedin2004.F90:664-687
@@ -339,14 +381,13 @@ struct ModelStandard {
         double fd, fi, bterm, rup, rInit;
         int need;  // 1: r_i must be found by the root finder on [radius, rup]; 0: rInit is final
     };
-    GLC_DEVICE_INLINE double ac_function(double nfwNorm, double rs, const Work &w, const AcProblem &P, double radius,
+    GLC_DEVICE_INLINE double ac_function(double dmoNorm, double dmoScale, const Work &w, const AcProblem &P, double radius,
                                          double ri) {
-        return nfw_mass(nfwNorm, rs, ac_orbital_mean(w, ri)) * (P.fi * ri - P.fd * radius) - P.bterm;
+        return dmo_mass(dmoNorm, dmoScale, ac_orbital_mean(w, ri)) * (P.fi * ri - P.fd * radius) - P.bterm;
     }
     // set-up for a shell inside the virial radius (radius > 0)
-    GLC_DEVICE_INLINE void ac_setup(const NodeCtx &c, const double (&y)[NY], const Work &w, double nfwNorm, double radius,
-                                    AcProblem &P) {
-        const double rs = c.dmScale;
+    GLC_DEVICE_INLINE void ac_setup(const NodeCtx &c, const double (&y)[NY], const Work &w, double radius, AcProblem &P) {
+        const double nfwNorm = w.dmoNorm, rs = w.dmoScale;
         const double fDm = 1.0 - GLC_PARAMS.OmegaBaryon / GLC_PARAMS.OmegaMatter;
         P.fd = P.fi = P.bterm = 0.0;
         P.rup = radius;
@@ -360,7 +401,7 @@ struct ModelStandard {
         P.fi = fmin(fDm + mTot / c.basicMass, 1.0);
         const double rmean = ac_orbital_mean(w, radius);
         P.bterm = baryonic_vc2(c, y, w, rmean) * rmean * radius / kGInternal;
-        const double menc = nfw_mass(nfwNorm, rs, rmean);
+        const double menc = dmo_mass(nfwNorm, rs, rmean);
         if (menc > 0.0) P.rup = fmax((P.bterm / menc + P.fd * radius) / P.fi, radius);
         // the reference first tests solver(r_vir) < 0 (:463-466)
         const double fVir = ac_function(nfwNorm, rs, w, P, radius, w.rvir);
@@ -372,18 +413,18 @@ struct ModelStandard {
     GLC_DEVICE_INLINE RootOptions ac_root_options() {
         return RootOptions{0.0, 1.0e-2, EXPAND_MULTIPLICATIVE, 1.1, 0.9, SIGN_POSITIVE, SIGN_NEGATIVE};
     }
-    GLC_DEVICE_INLINE double dark_matter_mass_enclosed(const NodeCtx &c, const double (&y)[NY], const Work &w,
-                                                       double nfwNorm, double radius, int &bad, bool on) {
+    GLC_DEVICE_INLINE double dark_matter_mass_enclosed(const NodeCtx &c, const double (&y)[NY], const Work &w, double radius,
+                                                       int &bad, bool on) {
         // [warp-synchronous]
-        const double rs = c.dmScale;
+        const double nfwNorm = w.dmoNorm, rs = w.dmoScale;
         const double fDm = 1.0 - GLC_PARAMS.OmegaBaryon / GLC_PARAMS.OmegaMatter;
-        if (!GLC_PARAMS.adiabaticContraction) return on ? nfw_mass(nfwNorm, rs, radius) : 0.0;
+        if (!GLC_PARAMS.adiabaticContraction) return on ? dmo_mass(nfwNorm, rs, radius) : 0.0;
         const bool live = on && !(radius <= 0.0);
         AcProblem P;
         P.fd = P.fi = P.bterm = 0.0;
         P.rup = P.rInit = radius;
         P.need = 0;
-        if (live) ac_setup(c, y, w, nfwNorm, radius, P);
+        if (live) ac_setup(c, y, w, radius, P);
         const RootOptions o = ac_root_options();
         int st = 0;
         const double root = root_find([&](double ri) {
@@ -395,27 +436,7 @@ struct ModelStandard {
             P.rInit = root;
             if (st != 0) bad = 1;
         }
-        return live ? fDm * nfw_mass(nfwNorm, rs, P.rInit) : 0.0;
-    }
-    // stands in for nfwRadiusFromSpecificAngularMomentum (NFW.F90:589-625): solve j = sqrt(G M(<r) r) in ln r
-    GLC_DEVICE_INLINE double jroot_function(double nfwNorm, double rs, double lnj, double lr) {
-        const double r = dm_exp(lr);
-        return 0.5 * dm_log(kGInternal * nfw_mass(nfwNorm, rs, r) * r) - lnj;
-    }
-    GLC_DEVICE_INLINE RootOptions jroot_options() {
-        return RootOptions{1.0e-12, 0.0, EXPAND_ADDITIVE, 2.0, -2.0, SIGN_POSITIVE, SIGN_NEGATIVE};
-    }
-    GLC_DEVICE_INLINE double nfw_radius_from_j(const NodeCtx &c, const Work &w, double nfwNorm, double j, bool on) {
-        // [warp-synchronous]
-        const bool live = on && (j > 0.0);
-        const double lnj = live ? dm_log(j) : 0.0, rs = c.dmScale;
-        const double lnrv = live ? dm_log(w.rvir) : 0.0;
-        const RootOptions o = jroot_options();
-        int st;
-        const double lnr = root_find([&](double lr) { return jroot_function(nfwNorm, rs, lnj, lr); }, live, o, lnrv - 4.0,
-                                     lnrv, false, 0.0, 0.0, st);
-        if (!live) return 0.0;
-        return (st != 0) ? w.rvir : dm_exp(lnr);
+        return live ? fDm * dmo_mass(nfwNorm, rs, P.rInit) : 0.0;
     }
     GLC_DEVICE_INLINE void plausibility(const NodeCtx &c, const double (&y)[NY], double time, Work &w) {
         // basic/standard/_class.F90:105-123; disk/standard/_class.F90:999-1049; spheroid/standard/_class.F90:1249-1296
@@ -451,24 +472,21 @@ struct ModelStandard {
     // The pieces of one (iteration, component) visit, shared by the warp-synchronous solver below and by the
     // micro-task machine (glc_machine.cuh).
     //   first pass (:356-404): previous solution, else a first guess from the dark-matter-only rotation curve
-    GLC_DEVICE_INLINE void structure_first_pass(const NodeCtx &c, const Work &w, double nfwNorm, int comp, double j,
-                                                double &radius, double &velocity, bool &guess, bool &needRoot) {
-        guess = needRoot = false;
-        velocity = 0.0;
+    GLC_DEVICE_INLINE void structure_first_pass(const NodeCtx &c, const Work &w, int comp, double j, double &radius,
+                                                double &velocity) {
         radius = comp == 0 ? c.diskRadius : c.sphRadius;
         if (radius <= 0.0) {
-            const double radiusLarge = 1.0e10;
-            const double jmax = sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radiusLarge) / radiusLarge) * radiusLarge;
-            guess = true;
+            const double radiusLarge = 1.0e10;  // galactic_structure/options.F90
+            const double jmax = dmo_rotation_curve(w, radiusLarge) * radiusLarge;
             if (jmax < j)
                 radius = w.rvir;
             else
-                needRoot = true;
+                radius = dmo_radius_from_j(c, w, j);
+            velocity = dmo_rotation_curve(w, radius);
         } else
             velocity = comp == 0 ? c.diskVelocity : c.sphVelocity;
-    }
-    GLC_DEVICE_INLINE double structure_guess_velocity(const NodeCtx &c, double nfwNorm, double radius) {
-        return (radius > 0.0) ? sqrt(kGInternal * nfw_mass(nfwNorm, c.dmScale, radius) / radius) : 0.0;
+        if (GLC_PARAMS.structureVelocityMaximumFactor > 0.0)
+            velocity = fmin(velocity, GLC_PARAMS.structureVelocityMaximumFactor * w.vvir);
     }
     //   later passes (:406-481): one fixed-point update in the current potential, with the oscillation breaker
     GLC_DEVICE_INLINE void structure_update(const NodeCtx &c, const double (&y)[NY], const Work &w, double j, double mdm,
@@ -477,6 +495,8 @@ struct ModelStandard {
         const double vdm2 = kGInternal * mdm / radius;
         const double vb2 = GLC_PARAMS.includeBaryonGravity ? baryonic_vc2(c, y, w, radius) : 0.0;
         velocity = sqrt(vdm2 + vb2);
+        if (GLC_PARAMS.structureVelocityMaximumFactor > 0.0)
+            velocity = fmin(velocity, GLC_PARAMS.structureVelocityMaximumFactor * w.vvir);  // equilibrium.F90:429-433
         const double radiusNew = (radius > 0.0) ? sqrt(j / velocity * radius) : j / velocity;
         if (count > 10 && h0 >= 0.0 && h1 >= 0.0 && (h1 - h0) * (h0 - radius) < 0.0) {
             switch (count % 4) {
@@ -509,7 +529,8 @@ struct ModelStandard {
         if (on) plausibility(c, y, time, w);
         const double tolerance = GLC_PARAMS.structureSolutionTolerance;
         bool looping = on && w.plausible;
-        const double nfwNorm = looping ? nfw_norm(c, w) : 0.0;
+        w.dmoNorm = w.dmoScale = 0.0;
+        if (looping) dmo_prepare(c, w);
         double hist00 = -1.0, hist01 = -1.0, hist10 = -1.0, hist11 = -1.0;
         double fit = 2.0 * tolerance;
         int count = 0;
@@ -527,16 +548,10 @@ struct ModelStandard {
                 double radius = 0.0, velocity = 0.0;
                 if (compOn) active++;
                 const bool first = compOn && count == 1;
-                bool guess = false, needRoot = false;
-                if (first) structure_first_pass(c, w, nfwNorm, comp, j, radius, velocity, guess, needRoot);
-                const double rGuess = nfw_radius_from_j(c, w, nfwNorm, j, needRoot);
-                if (guess) {
-                    if (needRoot) radius = rGuess;
-                    velocity = structure_guess_velocity(c, nfwNorm, radius);
-                }
+                if (first) structure_first_pass(c, w, comp, j, radius, velocity);
                 const bool later = compOn && count > 1 && !(j <= 0.0);
                 if (later) radius = comp == 0 ? c.diskRadius : c.sphRadius;
-                const double mdm = dark_matter_mass_enclosed(c, y, w, nfwNorm, radius, bad, later);
+                const double mdm = dark_matter_mass_enclosed(c, y, w, radius, bad, later);
                 if (later)
                     structure_update(c, y, w, j, mdm, count, comp == 0 ? hist00 : hist10, comp == 0 ? hist01 : hist11, fit,
                                      bad, radius, velocity);
@@ -1061,6 +1076,7 @@ struct ModelStandard {
         w.hhValid = false;
         w.coolLambda = w.coolEfrac = w.coolXH = w.coolFHn = w.coolTavail = 0.0;
         w.plausible = w.solvable = false;
+        w.dmoNorm = w.dmoScale = 0.0;
     }
     // which of the nested solvers an evaluation needs (operator gates of nodeOperatorMulti)
     GLC_DEVICE_INLINE bool disk_sfr_on(const NodeCtx &c, const double (&y)[NY], bool go) {

@@ -88,5 +88,12 @@ extern "C" int glc_params_default(glc_params *P, int32_t model) {
     P->bhEfficiencyWindScalesWithEfficiencyRadiative = 1;
     P->adafEfficiencyRadiationTypeThinDisk = 1;
     P->operatorMask = GLC_OP_ALL;
+    P->darkMatterProfileDMO = GLC_DMO_NFW;        // quickTest.xml:88
+    P->structureVelocityMaximumFactor = 0.0;      // equilibrium.F90:124-128
+    P->timestepHostRelative = 0.1;                // quickTest.xml:297-300
+    P->timestepHostAbsolute = 1.0;
+    P->timestepSimpleRelative = 0.1;              // merger_trees/evolve/timesteps/simple.F90 defaults
+    P->timestepSimpleAbsolute = 1.0;
+    P->wallClockMaximumSeconds = 0.0;
     return 0;
 }

@@ -68,6 +68,34 @@ inline std::vector<double> build_pow_table(double rangeMin, double rangeMax, dou
     return t;
 }
 
+// Inverse tabulation used by nfwRadiusFromSpecificAngularMomentum (mass_distributions/spherical/NFW.F90:589-639): abscissae on
+// the absolute octave lattice x_k = 2^(k/30) (countRadiiPerOctave = 30, NFW.F90:94; numerical/ranges.F90 Lattice_Value),
+// values sqrt(massEnclosedScaleFree(x) x) with the 4 pi of NFW.F90:568-570.  The reference grows the lattice octave by octave
+// until it brackets the request; 80 octaves about unity cover every physical case and, the lattice being absolute, hold the
+// very points the reference would compute.
+constexpr int kNfwJPointsPerOctave = 30, kNfwJOctaves = 40;
+inline void build_nfw_j_table(std::vector<double> &xs, std::vector<double> &js) {
+    const int n = 2 * kNfwJOctaves * kNfwJPointsPerOctave + 1;
+    const double ln2 = 0.69314718055994530942, pi = 3.14159265358979323846;
+    xs.resize(n);
+    js.resize(n);
+    for (int i = 0; i < n; i++) {
+        const int k = i - kNfwJOctaves * kNfwJPointsPerOctave;
+        const double x = (k % kNfwJPointsPerOctave == 0) ? dm_scale2(1.0, k / kNfwJPointsPerOctave)
+                                                         : dm_exp(((double)k / (double)kNfwJPointsPerOctave) * ln2);
+        double m;
+        if (x == 1.0)
+            m = dm_log(2.0) - 0.5;
+        else if (x >= 1.0e-6)
+            m = dm_log(1.0 + x) - x / (1.0 + x);
+        else
+            m = x * x * (0.5 + x * (-2.0 / 3.0 + x * (0.75 + x * (-0.8))));
+        m = 4.0 * pi * m;
+        xs[i] = x;
+        js[i] = sqrt(m * x);
+    }
+}
+
 inline void pow_table_spacing(double rangeMin, double rangeMax, int n, double &dx, double &inverseDx) {
     dx = (rangeMax - rangeMin) / (double)(n - 1);
     inverseDx = 1.0 / ((rangeMin + dx) - rangeMin);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GLC_ABI_VERSION 2
+#define GLC_ABI_VERSION 3
 
 /* ---------------------------------------------------------------------------------
  * Node record.  One row of GLC_NPROP doubles per node, node-major ("what
@@ -104,13 +104,30 @@ enum glc_flag {
                                      radius by the pre-evolve task (hot_halo/standard/_class.F90:871-891) */
 };
 
-/* per-node status: errorStatus* of source/error/_module.F90 as used at
- * node_evolver/standard.F90:392-393,697-720 */
+/* per-node status.  Numerically EQUAL to the reference's errorStatus* constants (source/error/_module.F90:66-75, which
+ * copy the GSL error codes of gsl_errno.h) as used at node_evolver/standard.F90:392-393,697-720, so that the Fortran shim
+ * hands them to the tree evolver unchanged; library-specific codes are above 1024 like the reference's own additions. */
 enum glc_status {
-    GLC_STATUS_SUCCESS   = 0,
-    GLC_STATUS_FAIL      = 1,
-    GLC_STATUS_UNDERFLOW = 2, /* errorStatusUnderflow: 8 trials exhausted (standard.F90:707-722) */
-    GLC_STATUS_NONFINITE = 3  /* device flagged NaN/Inf where the reference would trap (-ffpe-trap) */
+    GLC_STATUS_SUCCESS   = 0,    /* errorStatusSuccess   = GSL_SUCCESS                                          */
+    GLC_STATUS_FAIL      = -1,   /* errorStatusFail      = GSL_FAILURE                                          */
+    GLC_STATUS_UNDERFLOW = 15,   /* errorStatusUnderflow = GSL_EUNDRFLW: 8 trials exhausted (standard.F90:707-722) */
+    GLC_STATUS_XCPU      = 1025, /* errorStatusXCPU: systemClockMaximum exceeded (standard.F90:694-705,861-867)  */
+    GLC_STATUS_NONFINITE = 1027, /* device flagged NaN/Inf where the reference would trap (-ffpe-trap, Makefile:100) */
+    GLC_STATUS_PENDING   = -2139062144 /* 0x80808080: not evolved (yet) -- streaming sessions, and nodes of a batch call
+                                    that returned an error */
+};
+
+/* return codes of the entry points: 0 = success, otherwise negative.  -1..-12: argument / state errors (see
+ * glc_last_error), <= -1000: -(cudaError_t) - 1000. */
+enum glc_error {
+    GLC_ERR_STALLED        = -20, /* the device made no progress on a batch (a defect, never expected): nothing was lost,
+                                     the nodes not evolved keep GLC_STATUS_PENDING */
+    GLC_ERR_BUSY           = -21, /* batch call while a streaming session is active, or stream call out of sequence */
+    GLC_ERR_BAD_FOREST     = -22, /* parent array is not a forest (index out of range or a cycle) */
+    GLC_ERR_EVOLVE_FAILED  = -23, /* glc_forest_evolve: a node evolve came back with a status other than success; the
+                                     reference aborts the run or drops the tree there (tasks/evolve_forests/_class.F90:887-897) */
+    GLC_ERR_DEADLOCK       = -24  /* glc_forest_evolve: trees not at their final time although no node can move
+                                     (merger_trees/evolver/standard.F90:606-625) */
 };
 
 /* interrupt codes = which functionInterrupt the host must call
@@ -203,7 +220,25 @@ typedef struct glc_params {
     /* operator enable mask (bit i = operator i of enum glc_operator); lets a host run
        reduced operator sets exactly as a reduced <nodeOperator value="multi"> would */
     uint32_t operatorMask;
+    /* darkMatterProfileDMO: the dark-matter-only profile under the contraction (enum glc_dmo_profile) */
+    int32_t darkMatterProfileDMO;
+    /* galacticStructureSolverEquilibrium [velocityMaximumFactor] (equilibrium.F90:124-128): 0 = no cap */
+    double structureVelocityMaximumFactor;
+    /* tree level (glc_forest_evolve): mergerTreeEvolverStandard [timestepHostRelative/Absolute]
+       (merger_trees/evolver/standard.F90:942-968) and mergerTreeEvolveTimestepSimple [timeStepRelative/Absolute]
+       (merger_trees/evolve/timesteps/simple.F90) */
+    double timestepHostRelative, timestepHostAbsolute;
+    double timestepSimpleRelative, timestepSimpleAbsolute;
+    /* systemClockMaximum of mergerTreeNodeEvolver%evolve (node_evolver/standard.F90:694-705,861-867) as a wall-clock
+       budget in seconds for ONE batched call (0 = none): nodes not finished when it expires come back with
+       GLC_STATUS_XCPU (errorStatusXCPU) */
+    double wallClockMaximumSeconds;
 } glc_params;
+
+enum glc_dmo_profile {
+    GLC_DMO_NFW = 0,        /* darkMatterProfileDMO value="NFW" (quickTest.xml:88) */
+    GLC_DMO_ISOTHERMAL = 1  /* value="isothermal" (testSuite/parameters/reproducibility/adiabaticContraction.xml) */
+};
 
 enum glc_operator {
     GLC_OP_STAR_FORMATION_DISKS      = 1u << 0,

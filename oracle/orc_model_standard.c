@@ -437,15 +437,33 @@ static double nfw_mass_scale_free(double x) {
     if (x >= 1.0e-6) return dm_log(1.0 + x) - x / (1.0 + x);
     return x * x * (0.5 + x * (-2.0 / 3.0 + x * (0.75 + x * (-0.8))));
 }
+static int dmo_isothermal(const std_work *w) { return w->P->darkMatterProfileDMO == GLC_DMO_ISOTHERMAL; }
 static double nfw_mass_enclosed(std_work *w, double radius) {
-    /* nfwMassEnclosedBySphere :444-464 with normalisation :254-255 */
-    /* M(<r) = [M_vir / m(c)] m(r/r_s): the 4 pi rho_0 r_s^3 of :254-255,458-460 folded into one factor */
+    /* darkMatterProfileDMO%get(node)%massEnclosedBySphere.
+       NFW: nfwMassEnclosedBySphere :444-464 with normalisation :254-255: M(<r) = [M_vir / m(c)] m(r/r_s) (the
+       4 pi rho_0 r_s^3 of :254-255,458-460 folded into one factor);
+       isothermal (mass_distributions/spherical/isothermal.F90:150-205,287-302; mass = M_vir, lengthReference = r_vir):
+       M(<r) = 4 pi rho_n L^2 r */
     double rs = w->p[GLC_P_DMSCALE]; /* current scale radius */
     double conc, norm;
     halo_scales(w);
+    if (dmo_isothermal(w)) {
+        const double L = w->rvir;
+        const double rho_n = w->p[GLC_P_BASIC_MASS] / 4.0 / ORC_PI / (L * L * L);
+        return (4.0 * ORC_PI * rho_n * (L * L)) * radius;
+    }
     conc = w->rvir / rs;
     norm = w->p[GLC_P_BASIC_MASS] / (dm_log(1.0 + conc) - conc / (1.0 + conc));
     return norm * nfw_mass_scale_free(radius / rs);
+}
+static double dmo_rotation_curve(std_work *w, double radius) {
+    /* massDistribution_%rotationCurve: isothermal.F90:196-204,431-442 (velocityRotation); NFW: sqrt(G M(<r)/r) */
+    if (dmo_isothermal(w)) {
+        const double L = (halo_scales(w), w->rvir);
+        const double rho_n = w->p[GLC_P_BASIC_MASS] / 4.0 / ORC_PI / (L * L * L);
+        return sqrt(ORC_G_INTERNAL * (4.0 * ORC_PI * rho_n * (L * L)));
+    }
+    return (radius > 0.0) ? sqrt(ORC_G_INTERNAL * nfw_mass_enclosed(w, radius) / radius) : 0.0;
 }
 
 static double ac_orbital_mean(std_work *w, double radius) {
@@ -512,28 +530,57 @@ static double dark_matter_mass_enclosed(std_work *w, double radius) {
     return f_dm * nfw_mass_enclosed(w, r_init);
 }
 
-static double nfw_j_root(double lnr, void *vw) {
-    std_work *w = (std_work *)vw;
-    double r = dm_exp(lnr);
-    return 0.5 * dm_log(ORC_G_INTERNAL * nfw_mass_enclosed(w, r) * r) - w->ac_bterm; /* ac_bterm = ln j here */
+/* inverse tabulation of the scale-free NFW specific angular momentum on the octave lattice x_k = 2^(k/30)
+   (NFW.F90:94,589-639; numerical/tabulations_inverse.F90:143-245; numerical/ranges.F90 Lattice_Value), tabulated once over
+   2^-40 .. 2^40: the lattice is absolute, so these are the points the reference computes, whatever extent it has grown to */
+#define NFWJ_PER_OCTAVE 30
+#define NFWJ_OCTAVES 40
+#define NFWJ_N (2 * NFWJ_OCTAVES * NFWJ_PER_OCTAVE + 1)
+static double nfwj_x[NFWJ_N], nfwj_v[NFWJ_N];
+static int nfwj_built = 0;
+static void nfwj_build(void) {
+    int i;
+#pragma omp critical(orc_nfwj_build)
+    if (!nfwj_built) {
+        for (i = 0; i < NFWJ_N; i++) {
+            const int k = i - NFWJ_OCTAVES * NFWJ_PER_OCTAVE;
+            const double x = (k % NFWJ_PER_OCTAVE == 0) ? dm_scale2(1.0, k / NFWJ_PER_OCTAVE)
+                                                        : dm_exp(((double)k / (double)NFWJ_PER_OCTAVE) * 0.69314718055994530942);
+            nfwj_x[i] = x;
+            nfwj_v[i] = sqrt(4.0 * ORC_PI * nfw_mass_scale_free(x) * x);
+        }
+        nfwj_built = 1;
+    }
 }
 static double nfw_radius_from_j(std_work *w, double j) {
-    /* stands in for nfwRadiusFromSpecificAngularMomentum (NFW.F90:589-625): solve j = sqrt(G M(<r) r) */
-    orc_root_finder rf;
-    int st;
-    double lnr, save = w->ac_bterm;
+    /* massDistribution_%radiusFromSpecificAngularMomentum: nfwRadiusFromSpecificAngularMomentum (NFW.F90:589-625),
+       isothermalRadiusFromSpecificAngularMomentum (isothermal.F90:350-370) */
+    double rs, conc, rho_n, jsf, x;
+    int lo, hi;
     if (!(j > 0.0)) return 0.0;
-    w->ac_bterm = dm_log(j);
-    orc_root_init(&rf, nfw_j_root, w, 1.0e-12, 0.0);
-    rf.expand_type = ORC_EXPAND_ADDITIVE;
-    rf.expand_upward = 2.0;
-    rf.expand_downward = -2.0;
-    rf.sign_expect_upward = ORC_SIGN_POSITIVE;
-    rf.sign_expect_downward = ORC_SIGN_NEGATIVE;
-    lnr = orc_root_find(&rf, dm_log(w->rvir) - 4.0, dm_log(w->rvir), 0, 0, 0, &st);
-    w->ac_bterm = save;
-    if (st != 0) return w->rvir;
-    return dm_exp(lnr);
+    halo_scales(w);
+    if (dmo_isothermal(w)) {
+        const double L = w->rvir;
+        const double rn = w->p[GLC_P_BASIC_MASS] / 4.0 / ORC_PI / (L * L * L);
+        return j / sqrt(4.0 * ORC_PI * rn * (L * L)) / sqrt(ORC_G_INTERNAL);
+    }
+    if (!nfwj_built) nfwj_build();
+    rs = w->p[GLC_P_DMSCALE];
+    conc = w->rvir / rs;
+    rho_n = w->p[GLC_P_BASIC_MASS] / 4.0 / ORC_PI / (rs * rs * rs) / (dm_log(1.0 + conc) - conc / (1.0 + conc));
+    jsf = j / sqrt(ORC_G_INTERNAL * rho_n) / (rs * rs);
+    lo = 0;
+    hi = NFWJ_N - 1;
+    while (hi > lo + 1) {
+        const int mid = (hi + lo) >> 1;
+        if (nfwj_v[mid] > jsf)
+            hi = mid;
+        else
+            lo = mid;
+    }
+    /* gsl_interp_linear: y_lo + (x - x_lo) / dx * dy */
+    x = nfwj_x[lo] + (jsf - nfwj_v[lo]) / (nfwj_v[lo + 1] - nfwj_v[lo]) * (nfwj_x[lo + 1] - nfwj_x[lo]);
+    return x * rs;
 }
 
 static void plausibility(std_work *w) {
@@ -583,6 +630,10 @@ static double component_j(const std_work *w, int comp) {
 static void structure_solve(std_work *w) {
     /* galacticStructureSolverEquilibrium::solve, galactic_structure/radius_solver/equilibrium.F90:243-506 */
     const int iteration_maximum = 100;
+    /* radiusHistory is a saved, thread-private array in the reference (:329) and is NOT reset between solves (the reset at
+       :455 sits in the branch that only runs for countIterations >= 2).  That persistence is unobservable: an entry is read
+       only when countIterations > 10 (:456-459), and by then iterations 2..10 of THIS solve have overwritten both entries
+       of every active component (:477-478) -- so starting each solve from -1 gives the reference's results exactly */
     double history[2][2] = {{-1.0, -1.0}, {-1.0, -1.0}};
     double fit;
     int count = 0, comp;
@@ -604,14 +655,16 @@ static void structure_solve(std_work *w) {
                 radius = w->p[pr];
                 if (radius <= 0.0) {
                     /* :358-376: guess from the dark-matter-only profile */
-                    double jmax = sqrt(ORC_G_INTERNAL * nfw_mass_enclosed(w, 1.0e10) / 1.0e10) * 1.0e10;
+                    double jmax = dmo_rotation_curve(w, 1.0e10) * 1.0e10;
                     if (jmax < j)
                         radius = w->rvir;
                     else
                         radius = nfw_radius_from_j(w, j);
-                    velocity = (radius > 0.0) ? sqrt(ORC_G_INTERNAL * nfw_mass_enclosed(w, radius) / radius) : 0.0;
+                    velocity = dmo_rotation_curve(w, radius);
                 } else
                     velocity = w->p[pv];
+                if (w->P->structureVelocityMaximumFactor > 0.0) /* :376,380 */
+                    velocity = fmin(velocity, w->P->structureVelocityMaximumFactor * w->vvir);
             } else {
                 double mdm, vdm2, vb2, radius_new;
                 if (j <= 0.0) continue;
@@ -620,6 +673,8 @@ static void structure_solve(std_work *w) {
                 vdm2 = ORC_G_INTERNAL * mdm / radius;
                 vb2 = w->P->includeBaryonGravity ? baryonic_vc2(w, radius) : 0.0;
                 velocity = sqrt(vdm2 + vb2);
+                if (w->P->structureVelocityMaximumFactor > 0.0) /* :429-433 */
+                    velocity = fmin(velocity, w->P->structureVelocityMaximumFactor * w->vvir);
                 radius_new = (radius > 0.0) ? sqrt(j / velocity * radius) : j / velocity;
                 if (count > 10 && history[comp][0] >= 0.0 && history[comp][1] >= 0.0 &&
                     (history[comp][1] - history[comp][0]) * (history[comp][0] - radius) < 0.0) {

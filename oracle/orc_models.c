@@ -164,6 +164,13 @@ void orc_params_default(glc_params *P, int model) {
     P->bhEfficiencyWindScalesWithEfficiencyRadiative = 1;
     P->adafEfficiencyRadiationTypeThinDisk = 1;
     P->operatorMask = GLC_OP_ALL;
+    P->darkMatterProfileDMO = GLC_DMO_NFW;   /* quickTest.xml:88 */
+    P->structureVelocityMaximumFactor = 0.0; /* equilibrium.F90:124-128 */
+    P->timestepHostRelative = 0.1;           /* quickTest.xml:297-300 */
+    P->timestepHostAbsolute = 1.0;
+    P->timestepSimpleRelative = 0.1;         /* merger_trees/evolve/timesteps/simple.F90 */
+    P->timestepSimpleAbsolute = 1.0;
+    P->wallClockMaximumSeconds = 0.0;
 }
 
 /* ---- tables -------------------------------------------------------------------------- */

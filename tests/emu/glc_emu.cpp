@@ -35,7 +35,7 @@ struct Emu {
     glc_params params;
     PreparedTable tables[GLC_NTABLES];
     DeviceTables dt;
-    std::vector<double> powAc, powKmt;
+    std::vector<double> powAc, powKmt, nfwJx, nfwJv;
 };
 
 template <class Model>
@@ -313,6 +313,16 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
 
 extern "C" {
 
+#ifdef GLC_EMU_COUNTERS
+// profiling aid: evaluation counts of the nested solvers (GLC_COUNT sites)
+void emu_get_counts(long long *out) {
+    for (int k = 0; k < 8; k++) out[k] = g_emu_count[k];
+}
+void emu_reset_counts(void) {
+    for (int k = 0; k < 8; k++) g_emu_count[k] = 0;
+}
+#endif
+
 void *emu_create(void) { return new Emu(); }
 void emu_destroy(void *h) { delete (Emu *)h; }
 void emu_set_params(void *h, const glc_params *p) {
@@ -327,6 +337,10 @@ void emu_set_params(void *h, const glc_params *p) {
         e->dt.powKmtN = (int)e->powKmt.size();
         pow_table_spacing(1.0e-3, 1.0, e->dt.powAcN, e->dt.powAcDx, e->dt.powAcInvDx);
         pow_table_spacing(1.0, 1000.0, e->dt.powKmtN, e->dt.powKmtDx, e->dt.powKmtInvDx);
+        build_nfw_j_table(e->nfwJx, e->nfwJv);
+        e->dt.nfwJx = e->nfwJx.data();
+        e->dt.nfwJv = e->nfwJv.data();
+        e->dt.nfwJN = (int)e->nfwJx.size();
     }
 }
 int emu_set_table(void *h, int id, int n0, int n1, const double *x0, const double *x1, const double *v) {
