@@ -385,15 +385,64 @@ static int ledger_report(glc_evolver *ev, int n, const char *tag) {
     fprintf(stderr, "[glc ledger %s] n=%d work_counter=%d never-fetched=%lld held=%lld done=%lld | violations: double-fetch=%llu "
                     "foreign-writeback=%llu two-lanes-in-slot=%llu wrong-queue=%llu\n",
             tag, n, work, never, held, done, herr[0], herr[1], herr[2], herr[3]);
+    FILE *dump = nullptr;
+    if (const char *path = getenv("GLC_LEDGER_DUMP")) dump = fopen(path, "wb");
+    if (dump) {
+        const int sizes[8] = {(int)heldNodes.size(), (int)sizeof(LaneState), (int)sizeof(RhsState), (int)sizeof(RootState),
+                              (int)sizeof(QagState), NY, WS_NVEC * NY, NPROP};
+        fwrite(sizes, sizeof(int), 8, dump);
+    }
     for (int node : heldNodes) {
         const int slot = led[node] - 1;
         LaneState L;
-        int unit = -99;
+        RhsState R;
+        RootState root;
+        QagState Q;
+        double yt[NY], ws[WS_NVEC * NY], rec[NPROP], tEnd = 0.0;
+        int unit = -99, flags = 0;
         cudaMemcpy(&L, ev->d_slots.L + slot, sizeof(LaneState), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&R, ev->d_slots.R + slot, sizeof(RhsState), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&root, ev->d_slots.root + slot, sizeof(RootState), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&Q, ev->d_slots.Q + slot, sizeof(QagState), cudaMemcpyDeviceToHost);
+        cudaMemcpy(yt, ev->d_slots.yt + (int64_t)slot * NY, sizeof yt, cudaMemcpyDeviceToHost);
+        cudaMemcpy(ws, ev->d_ws + (int64_t)slot * (WS_NVEC * NY), sizeof ws, cudaMemcpyDeviceToHost);
         cudaMemcpy(&unit, ev->d_slots.unit + slot, sizeof(int), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "   node %d held by slot %d (block %d): slot.unit=%d L.node=%d phase=%d heavy=%d stage=%d x=%.6g x1=%.6g h=%.3g\n",
-                node, slot, slot / GLC_MSLOTS, unit, L.node, L.phase, L.heavy, L.stage, L.x, L.x1, L.h);
+        cudaMemcpy(&flags, ev->d_flags + node, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&tEnd, ev->d_time_end + node, sizeof(double), cudaMemcpyDeviceToHost);
+        for (int p = 0; p < NPROP; p++) cudaMemcpy(&rec[p], ev->d_props + (int64_t)p * ev->cap + node, sizeof(double), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "   node %d held by slot %d (block %d): slot.unit=%d L.node=%d phase=%d heavy=%d stage=%d trial=%d x=%.9g x1=%.9g h=%.3g "
+                        "tEnd=%.9g flags=0x%x | R.count=%d comp=%d active=%d fit=%.3g bad=%d | B.state=%d it=%d busy=%d x=%.6g xLow=%.6g xHigh=%.6g "
+                        "fLow=%.3g fHigh=%.3g | Q.busy=%d size=%d it=%d\n",
+                node, slot, slot / GLC_MSLOTS, unit, L.node, L.phase, L.heavy, L.stage, L.trial, L.x, L.x1, L.h, tEnd, flags, R.count, R.comp,
+                R.active, R.fit, R.bad, root.B.state, root.B.iteration, root.B.busy, root.B.x, root.B.xLow, root.B.xHigh, root.B.fLow,
+                root.B.fHigh, Q.busy, Q.size, Q.iteration);
+        if (dump) {
+            fwrite(&node, sizeof(int), 1, dump);
+            fwrite(&slot, sizeof(int), 1, dump);
+            fwrite(&unit, sizeof(int), 1, dump);
+            fwrite(&flags, sizeof(int), 1, dump);
+            fwrite(&tEnd, sizeof(double), 1, dump);
+            fwrite(&L, sizeof L, 1, dump);
+            fwrite(&R, sizeof R, 1, dump);
+            fwrite(&root, sizeof root, 1, dump);
+            fwrite(&Q, sizeof Q, 1, dump);
+            fwrite(yt, sizeof yt, 1, dump);
+            fwrite(ws, sizeof ws, 1, dump);
+            fwrite(rec, sizeof rec, 1, dump);
+        }
     }
+    if (dump) fclose(dump);
+    int shown = 0;
+    for (int i = 0; i < n && shown < 16; i++)
+        if (led[i] == -1) {
+            int flags = 0;
+            double t = 0.0, tEnd = 0.0;
+            cudaMemcpy(&flags, ev->d_flags + i, sizeof(int), cudaMemcpyDeviceToHost);
+            cudaMemcpy(&tEnd, ev->d_time_end + i, sizeof(double), cudaMemcpyDeviceToHost);
+            cudaMemcpy(&t, ev->d_props + (int64_t)GLC_P_TIME * ev->cap + i, sizeof(double), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "   node %d never fetched: flags=0x%x time=%.9g tEnd=%.9g\n", i, flags, t, tEnd);
+            shown++;
+        }
     return 0;
 }
 #endif
@@ -403,7 +452,7 @@ static int ledger_report(glc_evolver *ev, int n, const char *tag) {
 // mode 1: streaming -- ONE time slice of `streamBudget` pops over the (possibly grown) node queue
 // mode 2: streaming -- continue to completion (hybrid)
 static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mode = 0, int streamBudget = 0) {
-    constexpr size_t kMachineSmem = sizeof(unsigned short) * (size_t)U_IDLE * GLC_MSLOTS;
+    constexpr size_t kMachineSmem = sizeof(unsigned int) * (size_t)U_IDLE * GLC_MSLOTS;
     GLC_CHECK(ev, cudaFuncSetAttribute(machine_kernel<GLC_MTHREADS, GLC_MSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kMachineSmem));
     const int gridMax = ev->num_sms;  // one block per SM
@@ -489,21 +538,28 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     const unsigned long long drainBelow = (unsigned long long)ev->drain_threshold;
     bool draining = false;
     int stalled = 0;
-    unsigned long long prevDone = ~0ull, prevRhs = ~0ull, prevParked = ~0ull;
+    unsigned long long prevDone = ~0ull, prevRhs = ~0ull, prevParked = ~0ull, unitsSinceProgress = 0;
     for (;;) {
         if (ev->slice_log > 1) fprintf(stderr, "[glc host] launching machine_kernel grid=%d budget=%d resume=%d hold=%d n=%d\n", grid, A.budget, A.resume, A.hold, n);
         machine_kernel<GLC_MTHREADS, GLC_MSLOTS><<<grid, GLC_MTHREADS, kMachineSmem, ev->stream>>>(A, ev->d_slots);
         ev->launches++;
         ev->slices++;
         GLC_CHECK(ev, cudaGetLastError());
-        GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 10, cudaMemcpyDeviceToHost,
+        GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 11, cudaMemcpyDeviceToHost,
                                       ev->stream));
         if (mode != 1 && ev->slice_budget <= 0 && !hybrid) break;
         GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+        if (hc[10] != 0) {
+            ev->err = "micro-task machine: a queue wait timed out inside the kernel (protocol violation)";
+#ifdef GLC_LEDGER
+            ledger_report(ev, n, "queue time-out");
+#endif
+            return GLC_ERR_STALLED;
+        }
         if (mode == 1) break;  // streaming: exactly one slice per call
         if (ev->slice_log)
-            fprintf(stderr, "[glc slice %lld] t=%.3f ms done=%llu/%d rhs=%llu accepted=%llu parked=%llu mid-evaluation=%llu%s\n",
-                    (long long)ev->slices, 1e3 * (now_s() - t_start), hc[6], n, hc[2], hc[0], hc[7], hc[8], draining ? " (hold)" : "");
+            fprintf(stderr, "[glc slice %lld] t=%.3f ms done=%llu/%d fetched=%llu rhs=%llu accepted=%llu parked=%llu mid-evaluation=%llu units=%llu%s\n",
+                    (long long)ev->slices, 1e3 * (now_s() - t_start), hc[6], n, hc[5], hc[2], hc[0], hc[7], hc[8], hc[9], draining ? " (hold)" : "");
         const unsigned long long parked = hc[7], midEvaluation = hc[8];
         GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters + 7, 0, sizeof(unsigned long long) * 3, ev->stream));
         if (hc[6] >= (unsigned long long)n) break;
@@ -526,6 +582,23 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
             }
         } else
             stalled = 0;
+        // ... and so does a long run of slices that execute units without finishing a single evaluation or node: the nested
+        // solvers of one evaluation are bounded (100 structure iterations, 1000 Brent steps, 24 quadrature intervals)
+        if (hc[6] == prevDone && hc[2] == prevRhs) {
+            unitsSinceProgress += hc[9];
+            if (unitsSinceProgress > 400000ull * std::max<unsigned long long>(parked, 1ull) && mode != 1) {
+                char msg[256];
+                snprintf(msg, sizeof msg,
+                         "micro-task machine: %llu slots executed %llu units without finishing an evaluation "
+                         "(%llu of %d nodes done)", parked, unitsSinceProgress, hc[6], n);
+                ev->err = msg;
+#ifdef GLC_LEDGER
+                ledger_report(ev, n, "livelock");
+#endif
+                return GLC_ERR_STALLED;
+            }
+        } else
+            unitsSinceProgress = 0;
         prevDone = hc[6];
         prevRhs = hc[2];
         prevParked = parked;
@@ -655,6 +728,10 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
         if (herr[0] | herr[1] | herr[2] | herr[3] || (mode != 1 && hc[6] != (unsigned long long)n) || ev->slice_log) ledger_report(ev, n, "end of call");
     }
 #endif
+    if (hc[10] != 0) {
+        ev->err = "micro-task machine: a queue wait timed out inside the kernel (protocol violation)";
+        return GLC_ERR_STALLED;
+    }
     // a call that runs to completion must have written back every node of the batch
     if (mode != 1 && ev->max_slices <= 0 && hc[6] != (unsigned long long)n) {
         char msg[160];
@@ -1011,6 +1088,13 @@ int glc_evolve_batch(glc_evolver *ev, int64_t n, double *props, int32_t *flags, 
     int rc = glc_arena_upload(ev, n, props, flags, time_end);
     if (rc) return rc;
     rc = glc_evolve_arena(ev, n, counters);
+    if (rc == GLC_ERR_STALLED) {
+        // nothing was lost: hand back what was evolved; the others carry GLC_STATUS_PENDING and their input records
+        const std::string why = ev->err;
+        glc_arena_download(ev, n, props, flags, status, interrupt);
+        ev->err = why;
+        return rc;
+    }
     if (rc) return rc;
     return glc_arena_download(ev, n, props, flags, status, interrupt);
 }
@@ -1241,8 +1325,34 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
         ev->err = "glc_forest_evolve needs GLC_TABLE_HALO_MEAN_DENSITY";
         return -9;
     }
-    for (int64_t i = 0; i < n_nodes; i++)
-        if (parent[i] >= n_nodes || parent[i] == i) return -1;
+    if (n_nodes > 0x7fffffff) {
+        ev->err = "glc_forest_evolve: more than 2^31-1 nodes in one call";
+        return GLC_ERR_BAD_FOREST;
+    }
+    {
+        // the parent array must describe a forest: indices in [-1, n), no cycles (every walk towards a root ends)
+        std::vector<int32_t> mark((size_t)n_nodes, 0);  // 0 = unseen, k > 0 = reached in walk k, -1 = known to end at a root
+        for (int64_t i = 0; i < n_nodes; i++) {
+            if (parent[i] < -1 || parent[i] >= n_nodes) {
+                ev->err = "glc_forest_evolve: parent index out of range";
+                return GLC_ERR_BAD_FOREST;
+            }
+        }
+        for (int64_t i = 0; i < n_nodes; i++) {
+            if (mark[i] != 0) continue;
+            const int32_t walk = (int32_t)(i % 0x7ffffffe) + 1;
+            int64_t q = i;
+            while (q >= 0 && mark[q] == 0) {
+                mark[q] = walk;
+                q = parent[q];
+            }
+            if (q >= 0 && mark[q] == walk) {
+                ev->err = "glc_forest_evolve: the parent array contains a cycle";
+                return GLC_ERR_BAD_FOREST;
+            }
+            for (q = i; q >= 0 && mark[q] == walk; q = parent[q]) mark[q] = -1;
+        }
+    }
     glcf::Forest F;
     F.init(&ev->params, &ev->halo_host, n_nodes, parent, mass, time, scale_radius, angular_momentum, records, flags, state);
     glc_counters total{};
@@ -1261,7 +1371,32 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
         }
         glc_counters c{};
         const double t_batch = now_s();
+        static int n_batches = 0;
+        if (const char *mb = getenv("GLC_FOREST_MAX_BATCHES"))  // debugging aid: stop after that many batched calls
+            if (n_batches++ >= atoi(mb)) return GLC_ERR_BUSY;
+        std::vector<double> input;
+        const char *dumpPath = getenv("GLC_DUMP_PENDING");
+        if (dumpPath) input = buf;
         int rc = glc_evolve_batch(ev, m, buf.data(), bflags.data(), te.data(), status.data(), interrupt.data(), &c);
+        if (rc && dumpPath) {
+            // debugging aid: the input records of the nodes that did not come back
+            if (FILE *f = fopen(dumpPath, "wb")) {
+                int64_t cnt = 0;
+                for (int64_t k = 0; k < m; k++) cnt += status[k] != GLC_STATUS_SUCCESS;
+                const int64_t head[3] = {cnt, GLC_NPROP, m};
+                fwrite(head, sizeof(int64_t), 3, f);
+                for (int64_t k = 0; k < m; k++)
+                    if (status[k] != GLC_STATUS_SUCCESS) {
+                        const int64_t kk = k;
+                        fwrite(&kk, sizeof(int64_t), 1, f);
+                        fwrite(&status[k], sizeof(int32_t), 1, f);
+                        fwrite(&flags[list[k]], sizeof(int32_t), 1, f);
+                        fwrite(&te[k], sizeof(double), 1, f);
+                        fwrite(&input[(size_t)k * GLC_NPROP], sizeof(double), GLC_NPROP, f);
+                    }
+                fclose(f);
+            }
+        }
         if (rc) return rc;
         if (forest_log)
             fprintf(stderr, "[glc forest] batch of %lld nodes: %.1f ms (kernels %.1f ms), %llu RHS evaluations, %llu accepted steps\n",
@@ -1270,6 +1405,9 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
         for (int64_t k = 0; k < m; k++) {
             memcpy(F.R(list[k]), &buf[(size_t)k * GLC_NPROP], sizeof(double) * GLC_NPROP);
             if (status[k] != GLC_STATUS_SUCCESS || interrupt[k] != GLC_INT_NONE) {
+                // The reference aborts the run here or, with tolerateFailures, drops the tree (tasks/evolve_forests/
+                // _class.F90:887-897).  The walk goes on with the node moved to its end time so that the other trees finish;
+                // the call then returns GLC_WARN_EVOLVE_FAILED and the count is in failed_evolves.
                 F.fc.failed_evolves++;
                 F.R(list[k])[GLC_P_TIME] = te[k];
             }
@@ -1283,8 +1421,18 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
         total.nodes += c.nodes;
         return 0;
     };
-    const int rc = F.run(evolve);
+    int rc = F.run(evolve);
     if (forest_counters) *forest_counters = F.fc;
     if (counters) *counters = total;
+    if (rc == 0 && !F.all_roots_finished()) {
+        // no node can move although a tree has not reached its final time: the reference's deadlock report
+        // (merger_trees/evolver/standard.F90:606-625)
+        ev->err = "glc_forest_evolve: deadlock -- trees not at their final time although no node can be evolved";
+        return GLC_ERR_DEADLOCK;
+    }
+    if (rc == 0 && F.fc.failed_evolves > 0) {
+        ev->err = "glc_forest_evolve: node evolves came back with a status other than success (see failed_evolves)";
+        return GLC_WARN_EVOLVE_FAILED;
+    }
     return rc;
 }

@@ -503,22 +503,38 @@ GLC_DEVICE_INLINE bool machine_step(const SlotRef &S, const LaneMem &M) {
 // a cold-started structure solve) delays only its own slots.  All per-slot state lives in HBM/L2 (SlotArrays +
 // the RK stage vectors); the queues are rebuilt from the slots' pending-unit words at the start of every time
 // slice, so parking costs nothing.
+//
+// Queue protocol (bounded multi-producer / multi-consumer ring, one per unit).  A cell is one 32-bit word
+//     (lap << 12) | (full << 11) | slot            lap = (position / SLOTS) mod 2^20
+// and goes  empty(lap) -> full(lap) -> empty(lap + 1).  A producer takes a position with atomicAdd on the tail, WAITS until
+// the cell is empty for its lap (i.e. until the consumer of the position one lap earlier has read it) and writes it; a
+// consumer (lane 0 reserves up to 32 positions with a CAS on the head) waits until its cell is full for its lap, reads
+// the slot id and immediately marks the cell empty for the next lap.  Round 1 used 16-bit cells with a 5-bit lap tag and
+// producers that did not wait: a consumer that was slow between reserving and reading could be lapped (its cell
+// overwritten: the slot was lost), and because the tag repeats every 32 laps it then took another slot's entry (the slot
+// ran on two lanes at once).  Seen on the device as nodes that never finish and as corrupted lane states in batches with
+// very fast turnover (profiles/r02_ledger_*.txt); the GLC_LEDGER build (node-ownership ledger + per-slot busy flags)
+// proves the absence of both with this protocol.  All spins are bounded: a time-out sets the block's abort flag and the
+// host returns GLC_ERR_STALLED.
+constexpr unsigned int kCellFull = 1u << 11, kCellSlotMask = 0x7ffu, kLapMask = 0xfffffu;
+constexpr unsigned int kSpinLimit = 1u << 24;  // x ~64 ns
+
 template <int THREADS, int SLOTS>
 __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotArrays slots) {
     static_assert((SLOTS & (SLOTS - 1)) == 0 && SLOTS <= 2048, "SLOTS must be a power of two <= 2048 (11-bit ids)");
     constexpr int PER = SLOTS / THREADS;
-    constexpr unsigned short EMPTY = 0xf800u;  // lap tag 31: never the tag of lap 0
-    extern __shared__ unsigned short s_qdyn[];  // [U_IDLE][SLOTS] ring buffers (dynamic: > 48 KB)
-    unsigned short(*s_q)[SLOTS] = reinterpret_cast<unsigned short(*)[SLOTS]>(s_qdyn);
+    extern __shared__ unsigned int s_qdyn[];  // [U_IDLE][SLOTS] ring cells (dynamic: > 48 KB)
+    unsigned int(*s_q)[SLOTS] = reinterpret_cast<unsigned int(*)[SLOTS]>(s_qdyn);
     __shared__ unsigned int s_head[U_IDLE], s_tail[U_IDLE];
-    __shared__ int s_idle, s_cur;
+    __shared__ int s_idle, s_cur, s_abort;
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t base = (int64_t)blockIdx.x * SLOTS;
-    for (int i = tid; i < U_IDLE * SLOTS; i += THREADS) s_qdyn[i] = EMPTY;
+    for (int i = tid; i < U_IDLE * SLOTS; i += THREADS) s_qdyn[i] = 0u;  // empty, lap 0
     if (tid < U_IDLE) s_head[tid] = s_tail[tid] = 0u;
     if (tid == 0) {
         s_idle = 0;
         s_cur = U_RK;
+        s_abort = 0;
     }
     __syncthreads();
 #pragma unroll 1
@@ -530,16 +546,20 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
             own.L.phase = PH_FETCH;
             own.unit = U_RK;
         }
-        const int u = own.unit;
+        int u = own.unit;
+        if (u < 0 || u > U_IDLE) {  // finished by the drain kernel (-1) in an earlier hand-over: free, like U_IDLE
+            own.L.phase = PH_FETCH;
+            own.unit = u = U_RK;
+        }
         if (A.hold && u == U_RHS_BEGIN)
             atomicAdd(&s_idle, 1);  // held at an RK boundary for the drain kernel: out of work as far as this block goes
         else
-            s_q[u][atomicAdd(&s_tail[u], 1u) & (SLOTS - 1)] = (unsigned short)s;  // lap 0: tag 0
+            s_q[u][atomicAdd(&s_tail[u], 1u) & (SLOTS - 1)] = kCellFull | (unsigned int)s;  // lap 0, full
     }
     __syncthreads();
 
     volatile unsigned int *vhead = s_head, *vtail = s_tail;
-    volatile int *vidle = &s_idle, *vcur = &s_cur;
+    volatile int *vidle = &s_idle, *vcur = &s_cur, *vabort = &s_abort;
 #ifdef GLC_DEBUG_HANG
     volatile int *dbg = A.debug ? A.debug + ((int64_t)blockIdx.x * (THREADS / 32) + (tid >> 5)) * 8 : nullptr;
 #define GLC_DBG(k, v) do { if (dbg && lane == 0) dbg[k] = (v); } while (0)
@@ -604,6 +624,7 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
         // the warp left the loop while the rest waited for it in the next __shfl_sync.
         int allIdle = 0;
         if (lane == 0 && u < 0) allIdle = (*vidle >= SLOTS) ? 1 : 0;
+        if (lane == 0 && *vabort) allIdle = 2;  // a queue time-out somewhere in the block: leave
         u = __shfl_sync(0xffffffffu, u, 0);
         start = __shfl_sync(0xffffffffu, start, 0);
         take = __shfl_sync(0xffffffffu, take, 0);
@@ -611,6 +632,7 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
         GLC_DBG(2, u);
         GLC_DBG(3, (int)start);
         GLC_DBG(4, take);
+        if (allIdle == 2) break;
         if (u < 0) {
             GLC_DBG(0, 6);
             GLC_DBG(5, allIdle);
@@ -624,19 +646,26 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
         }
         // ---- one unit per lane
         if (lane < take) {
-            // Ring entries carry a 5-bit lap tag above the 11-bit slot id, so a consumer can tell "written for my
-            // lap" from "left over from the previous lap" without anybody ever resetting an entry.
             const unsigned int pos = start + (unsigned int)lane;
-            const unsigned short tag = (unsigned short)(((pos / SLOTS) & 31u) << 11);
-            volatile unsigned short *entry = &s_q[u][pos & (SLOTS - 1)];
-            unsigned short e;
+            const unsigned int lap = (pos / SLOTS) & kLapMask;
+            volatile unsigned int *entry = &s_q[u][pos & (SLOTS - 1)];
+            const unsigned int want = (lap << 1) | 1u;  // full, my lap
+            unsigned int e, spins = 0;
             GLC_DBG_LANE(0, 2);
             GLC_DBG_LANE(6, lane);
-            while (((e = *entry) & 0xf800u) != tag) __nanosleep(32);
+            while (((e = *entry) >> 11) != want) {  // the producer has taken the position and is about to write it
+                if (++spins > kSpinLimit) break;
+                __nanosleep(32);
+            }
+            if (spins > kSpinLimit) {
+                *vabort = 1;
+                atomicAdd(&A.counters[10], 1ull);
+            } else {
+            *entry = ((lap + 1u) & kLapMask) << 12;  // empty for the next lap: the producer one lap on may write
             GLC_DBG_LANE(0, 3);
             GLC_DBG_LANE(6, lane);
-            GLC_DBG_LANE(7, (int)(e & 0x07ffu));  // the producer reserved it and is about to write it
-            const int s = (int)(e & 0x07ffu);
+            GLC_DBG_LANE(7, (int)(e & kCellSlotMask));
+            const int s = (int)(e & kCellSlotMask);
             __threadfence_block();  // acquire: the producer's stores to the slot's continuation are visible
             const int64_t slot = base + s;
             const SlotRef S = slot_ref(slots, slot);
@@ -653,11 +682,26 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
             if (A.slotBusy) atomicExch(&A.slotBusy[slot], 0);
 #endif
             __threadfence_block();  // release: continuation stores before the queue entry
-            if (nu == U_IDLE || (A.hold && nu == U_RHS_BEGIN))
+            if (nu < 0 || nu > U_IDLE) {  // not a unit: the continuation is corrupt -- never index a queue with it
+                *vabort = 1;
+                atomicAdd(&A.counters[10], 1ull);
+            } else if (nu == U_IDLE || (A.hold && nu == U_RHS_BEGIN))
                 atomicAdd(&s_idle, 1);
             else {
                 const unsigned int np = atomicAdd(&s_tail[nu], 1u);
-                s_q[nu][np & (SLOTS - 1)] = (unsigned short)((((np / SLOTS) & 31u) << 11) | (unsigned int)s);
+                const unsigned int plap = (np / SLOTS) & kLapMask;
+                volatile unsigned int *cell = &s_q[nu][np & (SLOTS - 1)];
+                unsigned int pspins = 0;
+                while (*cell != (plap << 12)) {  // the consumer one lap back has not read its entry yet
+                    if (++pspins > kSpinLimit) break;
+                    __nanosleep(32);
+                }
+                if (pspins > kSpinLimit) {
+                    *vabort = 1;
+                    atomicAdd(&A.counters[10], 1ull);
+                }
+                *cell = (plap << 12) | kCellFull | (unsigned int)s;
+            }
             }
         }
         GLC_DBG_LANE(0, 4);

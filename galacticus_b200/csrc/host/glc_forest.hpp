@@ -363,6 +363,13 @@ struct Forest {
         fc.promotions++;
     }
 
+    // every root at the final time of its tree (else the walk stopped with nodes that cannot move: a deadlock)
+    bool all_roots_finished() const {
+        for (int64_t i = 0; i < n; i++)
+            if (parent[i] < 0 && !(state[i] == NS_ACTIVE && R(i)[GLC_P_TIME] == time[i])) return false;
+        return true;
+    }
+
     // Rounds over the forest.  evolve(idx, time_end) evolves the listed nodes' records in place and returns 0.
     template <class Evolve>
     int run(Evolve &&evolve) {

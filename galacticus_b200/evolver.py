@@ -117,7 +117,12 @@ class Evolver:
             pass
 
     def _check(self, rc: int, what: str):
-        if rc != 0:
+        if rc > 0:  # completed with a warning (GLC_WARN_*): the outputs are valid, the caller inspects the counters
+            import warnings
+
+            msg = self.L.glc_last_error(self.h)
+            warnings.warn(f"{what}: {msg.decode() if msg else rc}")
+        elif rc != 0:
             msg = self.L.glc_last_error(self.h)
             raise GlcError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
 

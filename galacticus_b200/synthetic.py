@@ -317,3 +317,76 @@ def binary_split_forest(params, n_trees, mass_root, mass_resolution, seed=219, t
     return {"parent": parent, "mass": mass, "time": time, "scale_radius": rvir / conc,
             "angular_momentum": np.sqrt(2.0) * lam * mass * rvir * vvir, "tree": tree}
 
+
+
+# ------------------------------------------------------------------ spherical collapse (host-side table input)
+def spherical_collapse_virial_density_contrast(params, t):
+    """Virial density contrast (relative to the mean matter density at time t [Gyr]) of the spherical collapse model
+    for collisionless matter plus a cosmological constant: what virialDensityContrastSphericalCollapseClsnlssMttrCsmlgclCnstnt
+    tabulates (structure_formation/spherical_collapse/solver/collisionlessMatter_cosmologicalConstant.F90:348-497,
+    520-640).  For each epoch: find the perturbation amplitude epsilon whose collapse time -- twice the time to
+    turnaround, the integral of sqrt(r / (Om + eps r + OL r^3)) in units of the epochal Hubble time with the analytic
+    correction near turnaround -- equals t; the turnaround radius solves Om/r + eps + OL r^2 = 0; the ratio of virial
+    to turnaround radius solves the cubic energy equation 2 eta x^3 - (2 + eta) x + 1 = 0 with eta = 2 (OL/Om) r_ta^3
+    (Lahav et al. 1991); Delta = 1 / (x r_ta)^3.  Host-side input generation for GLC_TABLE_HALO_MEAN_DENSITY: the
+    reference builds the same table once at start-up, outside the hot path."""
+    from scipy import integrate, optimize
+
+    cosmo = Cosmology(params)
+    t = np.atleast_1d(np.asarray(t, dtype=float))
+    out = np.empty_like(t)
+    for i, ti in enumerate(t):
+        a = float(cosmo.expansion_factor(ti))
+        e2 = cosmo.Om / a**3 + cosmo.OL
+        om, ol = cosmo.Om / a**3 / e2, cosmo.OL / e2
+        hubble = float(cosmo.hubble(a))  # 1/Gyr
+
+        def radius_max(eps):
+            lo, hi = -om / eps, (om / ol / 2.0) ** (1.0 / 3.0)
+            f = lambda r: om / r + eps + ol * r * r
+            if f(hi) > 0.0:
+                return hi
+            if f(lo) < 0.0:
+                return lo
+            return optimize.brentq(f, lo, hi, xtol=1.0e-300, rtol=1.0e-12)
+
+        def time_collapse(eps):
+            rta = radius_max(eps)
+            ru = (1.0 - 1.0e-4) * rta
+
+            def integrand(r):
+                s = om + eps * r + ol * r**3
+                return np.sqrt(r / s) if s > 0.0 else 0.0
+
+            tt = integrate.quad(integrand, 0.0, ru, epsrel=1.0e-9, limit=400)[0] / hubble
+            tt -= 2.0 * np.sqrt(om / ru + eps + ol * ru**2) / (2.0 * ol * ru - om / ru**2) / hubble
+            return 2.0 * tt
+
+        eps_max = -((27.0 / 4.0 * ol * om**2) ** (1.0 / 3.0))
+        lo, hi = -10.0, eps_max * (1.0 + 1.0e-9)
+        while time_collapse(lo) > ti:  # more negative = collapses earlier
+            lo *= 2.0
+        eps = optimize.brentq(lambda e: time_collapse(e) - ti, lo, hi, xtol=1.0e-300, rtol=1.0e-10)
+        rta = radius_max(eps)
+        eta = 2.0 * (ol / om) * rta**3
+        roots = np.roots([2.0 * eta, 0.0, -(2.0 + eta), 1.0])
+        x = min(float(r.real) for r in roots if abs(r.imag) < 1.0e-9 and 0.0 < r.real < 1.0)
+        out[i] = 1.0 / (x * rta) ** 3
+    return out
+
+
+def spherical_collapse_mean_density_table(params, t_min=0.01, t_max=30.0, per_decade=100):
+    """GLC_TABLE_HALO_MEAN_DENSITY with the spherical-collapse contrast instead of the Bryan & Norman fit (the layout of
+    halo_mean_density_table): mean matter density x Delta_vir(t), and its logarithmic time derivative."""
+    cosmo = Cosmology(params)
+    n = int(np.ceil(np.log10(t_max / t_min) * per_decade)) + 1
+    t = t_min * 10.0 ** (np.arange(n) / per_decade)
+
+    def rho(tt):
+        a = cosmo.expansion_factor(tt)
+        return spherical_collapse_virial_density_contrast(params, tt) * cosmo.Om * cosmo.rho_crit0 / a**3
+
+    r = rho(t)
+    eps = 1.0e-4
+    dln = (np.log(rho(t * (1 + eps))) - np.log(rho(t * (1 - eps)))) / (2 * eps * t)
+    return t, None, np.stack([r, dln], axis=1)

@@ -34,7 +34,8 @@ extern "C" {
  * treeNode%serializeValues would write", python/Galacticus/Build/Components/
  * TreeNodes/ODESolver.py:95-138, extended by the analytic / non-evolved properties
  * the RHS reads).  Component class order and property order follow the generated
- * serialization (alphabetical component classes, XML property order).
+ * serialization (component classes in the order of the generated treeNodeSerializeValuesToArray, XML property order;
+ * checked against the output of the reference generators by tests/test_layout.py).
  * ------------------------------------------------------------------------------- */
 enum glc_prop {
     /* --- numerically integrated properties (the ODE state vector y) ------------- */
@@ -117,15 +118,16 @@ enum glc_status {
                                     that returned an error */
 };
 
-/* return codes of the entry points: 0 = success, otherwise negative.  -1..-12: argument / state errors (see
+/* return codes of the entry points: 0 = success, negative = error (positive: completed with a warning).  -1..-12: argument / state errors (see
  * glc_last_error), <= -1000: -(cudaError_t) - 1000. */
 enum glc_error {
     GLC_ERR_STALLED        = -20, /* the device made no progress on a batch (a defect, never expected): nothing was lost,
                                      the nodes not evolved keep GLC_STATUS_PENDING */
     GLC_ERR_BUSY           = -21, /* batch call while a streaming session is active, or stream call out of sequence */
     GLC_ERR_BAD_FOREST     = -22, /* parent array is not a forest (index out of range or a cycle) */
-    GLC_ERR_EVOLVE_FAILED  = -23, /* glc_forest_evolve: a node evolve came back with a status other than success; the
-                                     reference aborts the run or drops the tree there (tasks/evolve_forests/_class.F90:887-897) */
+    GLC_WARN_EVOLVE_FAILED = 1,   /* glc_forest_evolve completed, but failed_evolves node evolves came back with a status other
+                                     than success (the reference aborts the run or, with tolerateFailures, drops the tree there:
+                                     tasks/evolve_forests/_class.F90:887-897); the only positive return code */
     GLC_ERR_DEADLOCK       = -24  /* glc_forest_evolve: trees not at their final time although no node can move
                                      (merger_trees/evolver/standard.F90:606-625) */
 };

@@ -1667,6 +1667,31 @@ void orc_probe_node(const glc_params *P, const orc_tables *T, double *props, int
     out[15] = dm_log(out[14] / r0);
 }
 
+/* rotation curve at `radius` as nodePropertyExtractorRotationCurve reports it for the radius specifiers of
+ * testSuite/parameters/reproducibility/adiabaticContraction.xml: out[0] = all components / all mass, out[1] = dark halo /
+ * dark (the contracted profile), out[2] = baryonic; km/s; out[3] = r_vir, out[4] = V_vir */
+void orc_rotation_curve_probe(const glc_params *P, const orc_tables *T, double *props, int flags, double radius, double *out) {
+    orc_evolve_ctx c;
+    std_work w;
+    double vdm2, vb2;
+    memset(&c, 0, sizeof(c));
+    c.P = P;
+    c.T = T;
+    c.p = props;
+    c.flags = flags;
+    orc_std_solve_analytics(&c, props[GLC_P_TIME]);
+    work_init(&w, &c, props[GLC_P_TIME]);
+    halo_scales(&w);
+    hh_profile(&w);
+    vdm2 = ORC_G_INTERNAL * dark_matter_mass_enclosed(&w, radius) / radius;
+    vb2 = baryonic_vc2(&w, radius);
+    out[0] = sqrt(vdm2 + vb2);
+    out[1] = sqrt(vdm2);
+    out[2] = sqrt(vb2);
+    out[3] = w.rvir;
+    out[4] = w.vvir;
+}
+
 /* known-answer access to the black-hole helper functions (tests/test_oracle_black_holes.py):
  * out[0..3] = ISCO radius, specific energy, specific angular momentum (gravitational units, prograde), Eddington
  * accretion rate (Msun/Gyr); out[4] = Bondi-Hoyle-Lyttleton radius (Mpc) and out[5] = rate (Msun/Gyr) for unit

@@ -426,6 +426,68 @@ int emu_forest_evolve(void *h, int64_t n_nodes, const int32_t *parent, const dou
     if (counters) *counters = total;
     return rc;
 }
+// Debugging aid: replays slots dumped by a GLC_LEDGER build of the product (GLC_LEDGER_DUMP=file) on the host, one unit at a
+// time, printing the unit sequence -- to see on the CPU what a slot that never finishes on the device is doing.
+int emu_replay_slots(void *h, const char *path, int max_steps, int verbose) {
+    Emu *e = (Emu *)h;
+    c_params = e->params;
+    c_tables = e->dt;
+    FILE *f = fopen(path, "rb");
+    if (!f) return -1;
+    int sizes[8];
+    if (fread(sizes, sizeof(int), 8, f) != 8) return -2;
+    if (sizes[1] != (int)sizeof(LaneState) || sizes[2] != (int)sizeof(RhsState) || sizes[3] != (int)sizeof(RootState) ||
+        sizes[4] != (int)sizeof(QagState) || sizes[5] != NY || sizes[6] != WS_NVEC * NY || sizes[7] != NPROP) {
+        fprintf(stderr, "[emu replay] struct sizes differ: file %d %d %d %d, here %zu %zu %zu %zu\n", sizes[1], sizes[2], sizes[3], sizes[4],
+                sizeof(LaneState), sizeof(RhsState), sizeof(RootState), sizeof(QagState));
+        return -3;
+    }
+    for (int k = 0; k < sizes[0]; k++) {
+        int node, slot, unit, flags;
+        double tEnd, yt[NY], ws[WS_NVEC * NY], rec[NPROP];
+        LaneState L;
+        RhsState R;
+        RootState root;
+        QagState Q;
+        size_t ok = fread(&node, sizeof(int), 1, f) + fread(&slot, sizeof(int), 1, f) + fread(&unit, sizeof(int), 1, f) +
+                    fread(&flags, sizeof(int), 1, f) + fread(&tEnd, sizeof(double), 1, f) + fread(&L, sizeof L, 1, f) +
+                    fread(&R, sizeof R, 1, f) + fread(&root, sizeof root, 1, f) + fread(&Q, sizeof Q, 1, f) + fread(yt, sizeof yt, 1, f) +
+                    fread(ws, sizeof ws, 1, f) + fread(rec, sizeof rec, 1, f);
+        if (ok != 12) break;
+        int32_t aflags = flags, status = 0, interrupt = 0;
+        int work = 1;
+        unsigned long long hc[16] = {0};
+        KernelArgs A{};
+        A.props = rec;  // cap = 1: the record is the arena
+        A.flags = &aflags;
+        A.time_end = &tEnd;
+        A.status = &status;
+        A.interrupt = &interrupt;
+        A.cap = 1;
+        A.n = 1;
+        A.ws = ws;
+        A.nslots = 1;
+        A.work_counter = &work;
+        A.counters = hc;
+        L.node = 0;
+        SlotArrays slots{&L, &R, &root, yt, &Q, &unit};
+        const SlotRef S = slot_ref(slots, 0);
+        LaneMem M{&A, ws, 1};
+        fprintf(stderr, "[emu replay] node %d slot %d unit %d phase %d heavy %d stage %d: ", node, slot, unit, L.phase, L.heavy, L.stage);
+        int step = 0;
+        unsigned int rhs0 = L.nRhs;
+        for (; step < max_steps && S.unit != U_IDLE; step++) {
+            if (verbose) fprintf(stderr, "%d ", S.unit);
+            machine_step(S, M);
+            if (L.nDone) break;
+        }
+        fprintf(stderr, "-> %d steps, unit %d, nDone %u, rhs +%u, B.state %d it %d busy %d x %.9g | R.count %d comp %d fit %.3g\n", step, S.unit,
+                L.nDone, L.nRhs - rhs0, root.B.state, root.B.iteration, root.B.busy, root.B.x, R.count, R.comp, R.fit);
+    }
+    fclose(f);
+    return 0;
+}
+
 // scheduler-only run (no evolution: every node just arrives at its end time): host-side cost and round structure
 int emu_forest_dryrun(void *h, int64_t n_nodes, const int32_t *parent, const double *mass, const double *time,
                       const double *scale_radius, const double *angular_momentum, double *records, int32_t *flags,
