@@ -91,6 +91,11 @@ struct glc_evolver {
     int32_t max_slices = 0;
     int64_t slices = 0;
     float last_ms = 0.f;
+    // phases of the last hybrid machine batch (glc_last_phase_stats): device ms and rate-function evaluations of the machine slices and
+    // of the drain passes
+    cudaEvent_t ev_mid = nullptr;
+    double phase_ms[2] = {0.0, 0.0}, phase_rhs[2] = {0.0, 0.0}, phase_steps[2] = {0.0, 0.0}, phase_nodes[2] = {0.0, 0.0};
+    bool phase_split = false;
     std::string err;
 #ifdef GLC_LEDGER
     // debug build: node-ownership ledger (see glc_evolve_kernel.cuh GLC_LEDGER_*)
@@ -98,6 +103,26 @@ struct glc_evolver {
     unsigned long long *d_ledger_err = nullptr;
     int64_t ledger_cap = 0;
 #endif
+};
+
+// page-locked host staging (std::vector interface): H2D / D2H copies of the forest batches run at PCIe/NVLink-C2C speed
+// instead of going through the driver's pageable bounce buffers
+template <class T>
+struct PinnedAllocator {
+    typedef T value_type;
+    PinnedAllocator() = default;
+    template <class U>
+    PinnedAllocator(const PinnedAllocator<U> &) {}
+    T *allocate(size_t n) {
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, n * sizeof(T), cudaHostAllocDefault) != cudaSuccess) throw std::bad_alloc();
+        return static_cast<T *>(p);
+    }
+    void deallocate(T *p, size_t) { cudaFreeHost(p); }
+    template <class U>
+    bool operator==(const PinnedAllocator<U> &) const { return true; }
+    template <class U>
+    bool operator!=(const PinnedAllocator<U> &) const { return false; }
 };
 
 static double now_s() {
@@ -521,6 +546,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     if (mode != 0) ev->stream_started = true;
     const double t_start = now_s();
     int nslice = 0;
+    ev->phase_split = false;
     A.hold = 0;
     A.held = nullptr;
     A.nheld = 0;
@@ -611,6 +637,11 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                 A.budget = 512;
             }
             if (draining && midEvaluation == 0) {
+                GLC_CHECK(ev, cudaEventRecord(ev->ev_mid, ev->stream));  // end of the machine phase
+                ev->phase_split = true;
+                ev->phase_rhs[0] = (double)hc[2];
+                ev->phase_steps[0] = (double)hc[0];
+                ev->phase_nodes[0] = (double)hc[6];
                 // ---- hand the held slots to the drain kernel: dense passes (one node per lane, bounded number of
                 // evaluations) while there are more nodes than warps, then one node per warp to the end
                 if (!ev->d_held || ev->held_cap < ev->nslots_machine) {
@@ -721,6 +752,27 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     }
     GLC_CHECK(ev, cudaEventRecord(ev->ev1, ev->stream));
     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    {
+        float total = 0.f, first = 0.f;
+        cudaEventElapsedTime(&total, ev->ev0, ev->ev1);
+        if (ev->phase_split) {
+            cudaEventElapsedTime(&first, ev->ev0, ev->ev_mid);
+            ev->phase_ms[0] = first;
+            ev->phase_ms[1] = total - first;
+            ev->phase_rhs[1] = (double)hc[2] - ev->phase_rhs[0];
+            ev->phase_steps[1] = (double)hc[0] - ev->phase_steps[0];
+            ev->phase_nodes[1] = (double)hc[6] - ev->phase_nodes[0];
+        } else {
+            ev->phase_ms[0] = total;
+            ev->phase_ms[1] = 0.0;
+            ev->phase_rhs[0] = (double)hc[2];
+            ev->phase_rhs[1] = 0.0;
+            ev->phase_steps[0] = (double)hc[0];
+            ev->phase_steps[1] = 0.0;
+            ev->phase_nodes[0] = (double)hc[6];
+            ev->phase_nodes[1] = 0.0;
+        }
+    }
 #ifdef GLC_LEDGER
     {
         unsigned long long herr[8];
@@ -786,6 +838,7 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     cudaStreamCreateWithFlags(&ev->stream2, cudaStreamNonBlocking);
     cudaEventCreate(&ev->ev0);
     cudaEventCreate(&ev->ev1);
+    cudaEventCreate(&ev->ev_mid);
     cudaMalloc(&ev->d_work, sizeof(int));
     cudaMalloc(&ev->d_counters, sizeof(unsigned long long) * 16);
     if (cudaGetLastError() != cudaSuccess) {
@@ -830,6 +883,7 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaFree(ev->d_sort);
     cudaEventDestroy(ev->ev0);
     cudaEventDestroy(ev->ev1);
+    cudaEventDestroy(ev->ev_mid);
     cudaStreamDestroy(ev->stream);
     cudaStreamDestroy(ev->stream2);
     cudaFree(ev->d_held_score);
@@ -883,6 +937,8 @@ int glc_evolver_set_params(glc_evolver *ev, const glc_params *params) {
         ev->tables.nfwJv = ev->d_nfw_jv;
         ev->tables.nfwJN = (int)xs.size();
     }
+    ev->tables.lnThinDiskMin = params->accretionRateThinDiskMinimum > 0.0 ? dm_log(params->accretionRateThinDiskMinimum) : 0.0;
+    ev->tables.lnThinDiskMax = params->accretionRateThinDiskMaximum > 0.0 ? dm_log(params->accretionRateThinDiskMaximum) : 0.0;
     ev->params = *params;
     ev->params_set = true;
     return 0;
@@ -1074,6 +1130,18 @@ double glc_measure_fp64_peak_tflops(glc_evolver *ev) {
 }
 
 float glc_last_kernel_ms(const glc_evolver *ev) { return ev ? ev->last_ms : 0.f; }
+int glc_last_phase_stats(const glc_evolver *ev, double *out6) {
+    if (!ev || !out6) return -1;
+    out6[6] = ev->phase_nodes[0];
+    out6[7] = ev->phase_nodes[1];
+    out6[0] = ev->phase_ms[0];
+    out6[1] = ev->phase_ms[1];
+    out6[2] = ev->phase_rhs[0];
+    out6[3] = ev->phase_rhs[1];
+    out6[4] = ev->phase_steps[0];
+    out6[5] = ev->phase_steps[1];
+    return 0;
+}
 void *glc_arena_device_props(glc_evolver *ev) { return ev ? (void *)ev->d_props : nullptr; }
 void *glc_evolver_stream(glc_evolver *ev) { return ev ? (void *)ev->stream : nullptr; }
 
@@ -1357,11 +1425,21 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
     F.init(&ev->params, &ev->halo_host, n_nodes, parent, mass, time, scale_radius, angular_momentum, records, flags, state);
     glc_counters total{};
     const bool forest_log = getenv("GLC_FOREST_LOG") != nullptr;
-    std::vector<double> buf, tend;
-    std::vector<int32_t> bflags, status, interrupt;
-    auto evolve = [&](const std::vector<int32_t> &list, const std::vector<double> &te) -> int {
+    std::vector<double, PinnedAllocator<double>> buf, tpin;
+    std::vector<int32_t, PinnedAllocator<int32_t>> bflags, status, interrupt;
+    auto evolve = [&](const std::vector<int32_t> &list, const std::vector<double> &te_in) -> int {
         const int64_t m = (int64_t)list.size();
+        if ((size_t)m * GLC_NPROP > buf.capacity()) {  // grow geometrically: page-locking is expensive
+            const size_t cap = std::max<size_t>((size_t)m + (size_t)m / 4, 1024);
+            buf.reserve(cap * GLC_NPROP);
+            tpin.reserve(cap);
+            bflags.reserve(cap);
+            status.reserve(cap);
+            interrupt.reserve(cap);
+        }
         buf.resize((size_t)m * GLC_NPROP);
+        tpin.assign(te_in.begin(), te_in.end());
+        const auto &te = tpin;
         bflags.resize(m);
         status.resize(m);
         interrupt.resize(m);
@@ -1376,7 +1454,7 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
             if (n_batches++ >= atoi(mb)) return GLC_ERR_BUSY;
         std::vector<double> input;
         const char *dumpPath = getenv("GLC_DUMP_PENDING");
-        if (dumpPath) input = buf;
+        if (dumpPath) input.assign(buf.begin(), buf.end());
         int rc = glc_evolve_batch(ev, m, buf.data(), bflags.data(), te.data(), status.data(), interrupt.data(), &c);
         if (rc && dumpPath) {
             // debugging aid: the input records of the nodes that did not come back

@@ -140,6 +140,9 @@ struct DeviceTables {
     // nfwJx[k] = 2^(k/30) on the octave lattice, nfwJv[k] = sqrt(4 pi m(x_k) x_k), built once on the host
     const double *nfwJx, *nfwJv;
     int nfwJN;
+    // constructor-time constants of accretionDisksSwitched (switched.F90:259-297 takes these logarithms at every call; they
+    // are pure functions of the parameters): ln(accretionRateThinDiskMinimum), ln(accretionRateThinDiskMaximum)
+    double lnThinDiskMin, lnThinDiskMax;
 };
 
 struct LaneState;

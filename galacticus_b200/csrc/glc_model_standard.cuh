@@ -705,6 +705,11 @@ struct ModelStandard {
         double eIsco, lIsco;  // ISCO specific energy / angular momentum (gravitational units, prograde)
         double eddington;
         double accSph, accHot, acc;  // blackHoleAccretionRateStandard::rateAccretion
+        // one-entry memos keyed on the exact accretion rate (the operators ask for the same quantities at the same rate
+        // several times per evaluation: accretion, winds, CGM heating); the functions are pure, so a hit returns the very
+        // bits a fresh evaluation would
+        double fKey, fVal, effKey, effVal, jetKey, jetVal;
+        int fOk, effOk, jetOk;
     };
     GLC_DEVICE_INLINE double ideal_gas_sound_speed(double temperature) {
         // Ideal_Gas_Sound_Speed, thermodynamics/ideal_gases.F90:46-69 (primordial mean atomic mass)
@@ -764,24 +769,29 @@ struct ModelStandard {
         const double h = (xe - GLC_LDG(t.x0 + i)) * GLC_TABLES.adaf_inv_dlnx;
         return GLC_LDG(t.v + 2 * i + column) * (1.0 - h) + GLC_LDG(t.v + 2 * (i + 1) + column) * h;
     }
-    GLC_DEVICE_INLINE double disk_fraction_adaf(const Bh &b, double mdot) {
+    GLC_DEVICE_INLINE double disk_fraction_adaf(Bh &b, double mdot) {
         // switchedFractionADAF, accretion_disks/switched.F90:259-297
         double f = 0.0;
         if (!(b.eddington > 0.0 && mdot > 0.0)) return 0.0;
+        if (b.fOk && mdot == b.fKey) return b.fVal;
         const double lm = dm_log(mdot / b.eddington);
         if (GLC_PARAMS.accretionRateThinDiskMinimum > 0.0) {
-            const double arg = fmin(+(lm - dm_log(GLC_PARAMS.accretionRateThinDiskMinimum)) / GLC_PARAMS.accretionRateTransitionWidth, 60.0);
+            const double arg = fmin(+(lm - GLC_TABLES.lnThinDiskMin) / GLC_PARAMS.accretionRateTransitionWidth, 60.0);
             f = f + 1.0 / (1.0 + dm_exp(arg));
         }
         if (GLC_PARAMS.accretionRateThinDiskMaximum < DBL_MAX) {
-            const double arg = fmin(-(lm - dm_log(GLC_PARAMS.accretionRateThinDiskMaximum)) / GLC_PARAMS.accretionRateTransitionWidth, 60.0);
+            const double arg = fmin(-(lm - GLC_TABLES.lnThinDiskMax) / GLC_PARAMS.accretionRateTransitionWidth, 60.0);
             f = f + 1.0 / (1.0 + dm_exp(arg));
         }
+        b.fKey = mdot;
+        b.fVal = f;
+        b.fOk = 1;
         return f;
     }
-    GLC_DEVICE_INLINE double disk_efficiency_radiative(const Bh &b, double mdot) {
+    GLC_DEVICE_INLINE double disk_efficiency_radiative(Bh &b, double mdot) {
         // switchedEfficiencyRadiative :199-226 over shakuraSunyaevEfficiencyRadiative (Shakura_Sunyaev.F90:69-93) and
         // adafEfficiencyRadiative (ADAF.F90:453-479) with switchedEfficiencyRadiativeScalingADAF :299-331
+        if (b.effOk && mdot == b.effKey) return b.effVal;
         const double f = disk_fraction_adaf(b, mdot);
         const double effThin = 1.0 - b.eIsco;
         double effAdaf = GLC_PARAMS.adafEfficiencyRadiationTypeThinDisk ? effThin : GLC_PARAMS.adafEfficiencyRadiation;
@@ -797,13 +807,17 @@ struct ModelStandard {
         double eff = 0.0;
         eff = eff + f * effAdaf;
         eff = eff + (1.0 - f) * effThin;
+        b.effKey = mdot;
+        b.effVal = eff;
+        b.effOk = 1;
         return eff;
     }
-    GLC_DEVICE_INLINE double disk_power_jet(const Bh &b, double mdot) {
+    GLC_DEVICE_INLINE double disk_power_jet(Bh &b, double mdot) {
         // switchedPowerJet :228-242; shakuraSunyaevPowerJet (Shakura_Sunyaev.F90:95-155); adafPowerJet (ADAF.F90:481-499).
         // 10**42.7 and 10**41.7 are compile-time constants of the reference.
         const double normKerr = 5.011872336272756e+42 * kErgs * kGigaYear / kMassSolar / (kKilo * kKilo);
         const double normSchw = 5.011872336272755e+41 * kErgs * kGigaYear / kMassSolar / (kKilo * kKilo);
+        if (b.jetOk && mdot == b.jetKey) return b.jetVal;
         const double f = disk_fraction_adaf(b, mdot);
         double thin = 0.0;
         if (mdot > 0.0) {
@@ -816,9 +830,13 @@ struct ModelStandard {
             }
         }
         const double adaf = mdot * adaf_table(b.spin, 0);
-        return (1.0 - f) * thin + f * adaf;
+        const double power = (1.0 - f) * thin + f * adaf;
+        b.jetKey = mdot;
+        b.jetVal = power;
+        b.jetOk = 1;
+        return power;
     }
-    GLC_DEVICE_INLINE double disk_rate_spin_up(const Bh &b, double mdot) {
+    GLC_DEVICE_INLINE double disk_rate_spin_up(Bh &b, double mdot) {
         // switchedRateSpinUp :244-257; shakuraSunyaevRateSpinUp (Shakura_Sunyaev.F90:157-179); adafRateSpinUp (ADAF.F90:501-523)
         const double f = disk_fraction_adaf(b, mdot);
         double thin = 0.0;
@@ -853,6 +871,8 @@ struct ModelStandard {
         const double velocity = 0.0 * kMpcPerKmPerSToGyr;
         b.on = bh_on(c, y, go);
         b.mass = b.spin = b.eIsco = b.lIsco = b.eddington = b.accSph = b.accHot = b.acc = 0.0;
+        b.fKey = b.fVal = b.effKey = b.effVal = b.jetKey = b.jetVal = 0.0;
+        b.fOk = b.effOk = b.jetOk = 0;
         if (!b.on) return;
         b.mass = y[GLC_P_BH_MASS];
         b.spin = y[GLC_P_BH_SPIN];
@@ -907,7 +927,7 @@ struct ModelStandard {
         }
         b.acc = b.accSph + b.accHot;
     }
-    GLC_DEVICE_INLINE double bh_wind_power(const NodeCtx &c, const double (&y)[NY], const Bh &b) {
+    GLC_DEVICE_INLINE double bh_wind_power(const NodeCtx &c, const double (&y)[NY], Bh &b) {
         // blackHoleWindCiotti2009::power, black_holes/winds/Ciotti2009.F90:153-246
         const double velocityWind = 1.0e4, temperatureISM = 1.0e4;
         double eff = GLC_PARAMS.bhEfficiencyWind, coupled = 0.0;

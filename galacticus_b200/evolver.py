@@ -52,6 +52,7 @@ def load_library() -> C.CDLL:
     L.glc_evolve_arena.argtypes = [vp, C.c_int64, C.POINTER(abi.glc_counters)]
     L.glc_last_kernel_ms.restype = C.c_float
     L.glc_last_kernel_ms.argtypes = [vp]
+    L.glc_last_phase_stats.argtypes = [vp, _dp]
     L.glc_arena_device_props.restype = vp
     L.glc_arena_device_props.argtypes = [vp]
     L.glc_evolver_stream.restype = vp
@@ -165,6 +166,13 @@ class Evolver:
         c = abi.glc_counters()
         self._check(self.L.glc_evolve_arena(self.h, n, C.byref(c)), "glc_evolve_arena")
         return abi.counters_dict(c), float(self.L.glc_last_kernel_ms(self.h))
+
+    def last_phase_stats(self):
+        """{machine_ms, drain_ms, machine_rhs, drain_rhs, machine_steps, drain_steps} of the last machine batch."""
+        out = np.zeros(8)
+        self._check(self.L.glc_last_phase_stats(self.h, out), "glc_last_phase_stats")
+        return dict(zip(("machine_ms", "drain_ms", "machine_rhs", "drain_rhs", "machine_steps", "drain_steps", "machine_nodes",
+                         "drain_nodes"), out.tolist()))
 
     def arena_download(self, n: int):
         props = np.zeros((n, abi.NPROP), dtype=np.float64)

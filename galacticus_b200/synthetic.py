@@ -266,7 +266,10 @@ def binary_split_forest(params, n_trees, mass_root, mass_resolution, seed=219, t
     rng = np.random.default_rng(seed)
     cosmo = Cosmology(params)
     t0 = float(cosmo.time_of_redshift(0.0))
-    if mass_root_max is None:
+    if np.ndim(mass_root) == 1:  # one root mass per tree (e.g. drawn from a halo mass function)
+        m_root = np.asarray(mass_root, dtype=float).copy()
+        assert m_root.shape[0] == n_trees
+    elif mass_root_max is None:
         m_root = np.full(n_trees, float(mass_root))
     else:
         m_root = 10.0 ** rng.uniform(np.log10(mass_root), np.log10(mass_root_max), n_trees)
@@ -317,6 +320,36 @@ def binary_split_forest(params, n_trees, mass_root, mass_resolution, seed=219, t
     return {"parent": parent, "mass": mass, "time": time, "scale_radius": rvir / conc,
             "angular_momentum": np.sqrt(2.0) * lam * mass * rvir * vvir, "tree": tree}
 
+
+
+def forest_subset(forest, n_trees):
+    """The first n_trees trees of a forest (trees are independent: a sample of the SAME trees for the CPU baseline)."""
+    keep = forest["tree"] < n_trees
+    new_index = np.cumsum(keep) - 1
+    parent = forest["parent"][keep]
+    parent = np.where(parent >= 0, new_index[np.maximum(parent, 0)], -1).astype(np.int32)
+    out = {k: v[keep] for k, v in forest.items() if k != "parent"}
+    out["parent"] = parent
+    return out
+
+
+def mass_function_roots(n_trees, mass_min=1.0e10, mass_max=1.0e14, slope=-0.9, mass_star=1.0e14, seed=219):
+    """Root masses of a Monte Carlo volume (BASELINE.json configs[3]): dn/dlnM ~ M^slope exp(-M/M*) on
+    [mass_min, mass_max], a Tinker et al. (2008)-like shape, by inverse-transform sampling on a fine lattice in ln M."""
+    rng = np.random.default_rng(seed)
+    lnm = np.linspace(np.log(mass_min), np.log(mass_max), 4097)
+    m = np.exp(lnm)
+    pdf = m**slope * np.exp(-m / mass_star)
+    cdf = np.concatenate([[0.0], np.cumsum(0.5 * (pdf[1:] + pdf[:-1]) * np.diff(lnm))])
+    cdf /= cdf[-1]
+    return np.exp(np.interp(rng.random(n_trees), cdf, lnm))
+
+
+def mass_function_forest(params, n_trees, mass_resolution=5.0e9, seed=219, **kw):
+    """configs[3]: halo-mass-function-sampled Monte Carlo trees at the quickTest mass resolution (mergerTreeMassResolution
+    fixed, default 5e9 Msun: merger_trees/construct/build/mass_resolution/fixed.F90:61-64)."""
+    roots = mass_function_roots(n_trees, seed=seed, **kw)
+    return binary_split_forest(params, n_trees, roots, mass_resolution, seed=seed + 1)
 
 
 # ------------------------------------------------------------------ spherical collapse (host-side table input)

@@ -346,6 +346,10 @@ int glc_arena_snapshot(glc_evolver *ev, int64_t n);
 int glc_arena_restore(glc_evolver *ev, int64_t n);
 /* duration (ms, CUDA events on the evolver's stream) of the last glc_evolve_arena kernel */
 float glc_last_kernel_ms(const glc_evolver *ev);
+/* how the last micro-task-machine batch divided into its two kernels (measurement aid): out8 = {device ms of the
+ * machine_kernel slices, device ms of the drain_kernel passes, rate-function evaluations of each, accepted steps of each,
+ * nodes written back by each} */
+int glc_last_phase_stats(const glc_evolver *ev, double *out8);
 /* raw device pointers for zero-copy interop (e.g. torch.distributed/NCCL reductions) */
 void *glc_arena_device_props(glc_evolver *ev);
 int64_t glc_arena_capacity(const glc_evolver *ev);

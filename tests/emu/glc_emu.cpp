@@ -337,6 +337,8 @@ void emu_set_params(void *h, const glc_params *p) {
         e->dt.powKmtN = (int)e->powKmt.size();
         pow_table_spacing(1.0e-3, 1.0, e->dt.powAcN, e->dt.powAcDx, e->dt.powAcInvDx);
         pow_table_spacing(1.0, 1000.0, e->dt.powKmtN, e->dt.powKmtDx, e->dt.powKmtInvDx);
+        e->dt.lnThinDiskMin = p->accretionRateThinDiskMinimum > 0.0 ? dm_log(p->accretionRateThinDiskMinimum) : 0.0;
+        e->dt.lnThinDiskMax = p->accretionRateThinDiskMaximum > 0.0 ? dm_log(p->accretionRateThinDiskMaximum) : 0.0;
         build_nfw_j_table(e->nfwJx, e->nfwJv);
         e->dt.nfwJx = e->nfwJx.data();
         e->dt.nfwJv = e->nfwJv.data();
