@@ -59,17 +59,26 @@ def _parse_struct(src: str, name: str):
         parts = decl.split(None, 1)
         ctype = _CTYPES[parts[0]]
         for var in parts[1].split(","):
-            fields.append((var.strip(), ctype))
+            var = var.strip()
+            m2 = re.match(r"(\w+)\[(\w+)\]$", var)
+            if m2:  # fixed-size array member: the bound is a #define or an enumerator
+                bound = m2.group(2)
+                nelem = int(bound) if bound.isdigit() else (ENUMS.get(bound) or _DEFINES[bound])
+                fields.append((m2.group(1), ctype * nelem))
+            else:
+                fields.append((var, ctype))
     return type(name, (C.Structure,), {"_fields_": fields})
 
 
 _SRC = _strip_comments(open(HEADER).read())
+_DEFINES = {k: int(v) for k, v in re.findall(r"#define\s+(\w+)\s+(\d+)\s*$", _SRC, flags=re.M)}
 ENUMS = _parse_enums(_SRC)
 globals().update(ENUMS)
 
 glc_params = _parse_struct(_SRC, "glc_params")
 glc_counters = _parse_struct(_SRC, "glc_counters")
 glc_forest_counters = _parse_struct(_SRC, "glc_forest_counters")
+glc_profile = _parse_struct(_SRC, "glc_profile")
 
 GLC_ABI_VERSION = int(re.search(r"#define\s+GLC_ABI_VERSION\s+(\d+)", _SRC).group(1))
 NPROP = ENUMS["GLC_NPROP"]
@@ -85,3 +94,14 @@ DECLARED_FUNCTIONS = sorted(set(re.findall(r"\b(glc_\w+)\s*\(", _SRC)))
 
 def counters_dict(c: "glc_counters") -> dict[str, int]:
     return {name: int(getattr(c, name)) for name, _ in c._fields_}
+
+
+def profile_dict(pr: "glc_profile") -> dict:
+    import numpy as np
+
+    n = int(pr.n_bins)
+    out = {"n_bins": n, "time_step_smallest": float(pr.time_step_smallest), "property_hits_unknown": int(pr.property_hits_unknown)}
+    for name in ("time_step", "time_step_count", "evaluation_count", "time_step_count_interrupted", "evaluation_count_interrupted"):
+        out[name] = np.array(list(getattr(pr, name))[:n])
+    out["property_hits"] = np.array(list(pr.property_hits))
+    return out

@@ -59,6 +59,7 @@ struct glc_evolver {
     unsigned long long *d_counters = nullptr;
     double *d_pow_ac = nullptr, *d_pow_kmt = nullptr;  // fastExponentiator tables
     double *d_nfw_jx = nullptr, *d_nfw_jv = nullptr;   // inverse tabulation of the NFW specific angular momentum
+    unsigned long long *d_profile = nullptr;           // mergerTreeEvolveProfilerSimple accumulators (profileOdeEvolver)
     double pow_ac_exponent = 0.0;
     LaneState *d_lanes = nullptr;   // parked lane states, one per resident lane
     SlotArrays d_slots{};           // micro-task machine: per-slot continuations, split by access group
@@ -242,6 +243,16 @@ __global__ void histogram_kernel(const double *__restrict__ v, int n, double lo,
     if (b >= 0 && b < nb) atomicAdd(&hist[b], 1.0);
 }
 
+// systemClockMaximum (node_evolver/standard.F90:694-705,861-867): nodes that were not finished when the wall-clock budget of
+// the batched call ran out come back with errorStatusXCPU
+__global__ void mark_xcpu_kernel(int32_t *status, int32_t *interrupt, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && status[i] == GLC_STATUS_PENDING) {
+        status[i] = GLC_STATUS_XCPU;
+        interrupt[i] = GLC_INT_NONE;
+    }
+}
+
 // ---------------------------------------------------------------------------- queue order
 // Nodes are handed to lanes in an order sorted by component set, so that the lanes of a warp -- which
 // fetch consecutive queue entries -- mostly run the same branches of the rate function.  Bucket order:
@@ -333,9 +344,12 @@ static int launch_evolve(glc_evolver *ev, int n, unsigned long long *hc) {
     A.order = sorted ? ev->d_order : nullptr;
     A.lanes = ev->d_lanes;
     A.resume = 0;
-    A.budget = ev->slice_budget > 0 ? ev->slice_budget : 0x7fffffff;
+    const double wallMax = ev->params.wallClockMaximumSeconds;
+    const int budget = ev->slice_budget > 0 ? ev->slice_budget : (wallMax > 0.0 ? 256 : 0);  // the guard needs time slices
+    A.budget = budget > 0 ? budget : 0x7fffffff;
     GLC_CHECK(ev, cudaMemsetAsync(ev->d_work, 0, sizeof(int), ev->stream));
     GLC_CHECK(ev, cudaMemsetAsync(ev->d_counters, 0, sizeof(unsigned long long) * 16, ev->stream));
+    if (wallMax > 0.0) GLC_CHECK(ev, cudaMemsetAsync(ev->d_status, 0x80, sizeof(int32_t) * (size_t)n, ev->stream));
     const double t_start = now_s();
     int nslice = 0;
     for (;;) {
@@ -345,8 +359,13 @@ static int launch_evolve(glc_evolver *ev, int n, unsigned long long *hc) {
         GLC_CHECK(ev, cudaGetLastError());
         GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost,
                                       ev->stream));
-        if (ev->slice_budget <= 0) break;
+        if (budget <= 0) break;
         GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+        if (wallMax > 0.0 && now_s() - t_start > wallMax && hc[6] < (unsigned long long)n) {
+            mark_xcpu_kernel<<<(n + 255) / 256, 256, 0, ev->stream>>>(ev->d_status, ev->d_interrupt, n);
+            ev->launches++;
+            break;
+        }
         if (ev->slice_log)
             fprintf(stderr, "[glc slice %lld] t=%.3f ms done=%llu/%d rhs=%llu accepted=%llu parked=%llu\n",
                     (long long)ev->slices, 1e3 * (now_s() - t_start), hc[6], n, hc[2], hc[0], hc[7]);
@@ -564,6 +583,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     const unsigned long long drainBelow = (unsigned long long)ev->drain_threshold;
     bool draining = false;
     int stalled = 0;
+    bool xcpu = false;
     unsigned long long prevDone = ~0ull, prevRhs = ~0ull, prevParked = ~0ull, unitsSinceProgress = 0;
     for (;;) {
         if (ev->slice_log > 1) fprintf(stderr, "[glc host] launching machine_kernel grid=%d budget=%d resume=%d hold=%d n=%d\n", grid, A.budget, A.resume, A.hold, n);
@@ -583,6 +603,13 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
             return GLC_ERR_STALLED;
         }
         if (mode == 1) break;  // streaming: exactly one slice per call
+        if (mode == 0 && ev->params.wallClockMaximumSeconds > 0.0 && now_s() - t_start > ev->params.wallClockMaximumSeconds &&
+            hc[6] < (unsigned long long)n) {
+            mark_xcpu_kernel<<<(n + 255) / 256, 256, 0, ev->stream>>>(ev->d_status, ev->d_interrupt, n);
+            ev->launches++;
+            xcpu = true;
+            break;
+        }
         if (ev->slice_log)
             fprintf(stderr, "[glc slice %lld] t=%.3f ms done=%llu/%d fetched=%llu rhs=%llu accepted=%llu parked=%llu mid-evaluation=%llu units=%llu%s\n",
                     (long long)ev->slices, 1e3 * (now_s() - t_start), hc[6], n, hc[5], hc[2], hc[0], hc[7], hc[8], hc[9], draining ? " (hold)" : "");
@@ -785,7 +812,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
         return GLC_ERR_STALLED;
     }
     // a call that runs to completion must have written back every node of the batch
-    if (mode != 1 && ev->max_slices <= 0 && hc[6] != (unsigned long long)n) {
+    if (mode != 1 && ev->max_slices <= 0 && !xcpu && hc[6] != (unsigned long long)n) {
         char msg[160];
         snprintf(msg, sizeof msg, "micro-task machine returned with %llu of %d nodes written back", hc[6], n);
         ev->err = msg;
@@ -877,6 +904,7 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaFree(ev->d_pow_kmt);
     cudaFree(ev->d_nfw_jx);
     cudaFree(ev->d_nfw_jv);
+    cudaFree(ev->d_profile);
     cudaFree(ev->d_lanes);
     free_slots(ev);
     cudaFree(ev->d_order);
@@ -936,6 +964,22 @@ int glc_evolver_set_params(glc_evolver *ev, const glc_params *params) {
         ev->tables.nfwJx = ev->d_nfw_jx;
         ev->tables.nfwJv = ev->d_nfw_jv;
         ev->tables.nfwJN = (int)xs.size();
+    }
+    ev->tables.profile = nullptr;
+    ev->tables.profBins = 0;
+    if (params->profileOdeEvolver) {
+        if (!(params->profilerTimeStepMinimum > 0.0) || !(params->profilerTimeStepMaximum > params->profilerTimeStepMinimum) ||
+            params->profilerTimeStepPointsPerDecade < 1) {
+            ev->err = "profileOdeEvolver needs 0 < profilerTimeStepMinimum < profilerTimeStepMaximum and profilerTimeStepPointsPerDecade >= 1";
+            return -8;
+        }
+        if (!ev->d_profile) {
+            GLC_CHECK(ev, cudaMalloc(&ev->d_profile, sizeof(unsigned long long) * kProfWords));
+            GLC_CHECK(ev, cudaMemset(ev->d_profile, 0, sizeof(unsigned long long) * kProfWords));
+            GLC_CHECK(ev, cudaMemset(ev->d_profile + kProfSmallest, 0x7f, sizeof(unsigned long long)));  // "huge": no step yet
+        }
+        ev->tables.profBins = build_profile_edges(*params, ev->tables.profEdges);
+        ev->tables.profile = ev->d_profile;
     }
     ev->tables.lnThinDiskMin = params->accretionRateThinDiskMinimum > 0.0 ? dm_log(params->accretionRateThinDiskMinimum) : 0.0;
     ev->tables.lnThinDiskMax = params->accretionRateThinDiskMaximum > 0.0 ? dm_log(params->accretionRateThinDiskMaximum) : 0.0;
@@ -1372,6 +1416,41 @@ int glc_histogram_accumulate(glc_evolver *ev, int64_t n, int32_t prop, double lo
         ev->d_props + (int64_t)prop * ev->cap, (int)n, log10_min, log10_max, n_bins, device_hist);
     GLC_CHECK(ev, cudaGetLastError());
     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    return 0;
+}
+
+int glc_profiler_reset(glc_evolver *ev) {
+    if (!ev) return -1;
+    if (!ev->d_profile) return 0;
+    cudaSetDevice(ev->device);
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_profile, 0, sizeof(unsigned long long) * kProfWords, ev->stream));
+    GLC_CHECK(ev, cudaMemsetAsync(ev->d_profile + kProfSmallest, 0x7f, sizeof(unsigned long long), ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    return 0;
+}
+
+int glc_profiler_read(glc_evolver *ev, glc_profile *out) {
+    if (!ev || !out) return -1;
+    memset(out, 0, sizeof(*out));
+    if (!ev->d_profile || !ev->params.profileOdeEvolver) {
+        ev->err = "profileOdeEvolver is not set";
+        return -9;
+    }
+    cudaSetDevice(ev->device);
+    unsigned long long h[kProfWords];
+    GLC_CHECK(ev, cudaMemcpyAsync(h, ev->d_profile, sizeof h, cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    out->n_bins = ev->tables.profBins;
+    for (int i = 0; i < GLC_PROFILE_BINS; i++) {
+        out->time_step[i] = ev->tables.profEdges[i];
+        out->time_step_count[i] = h[0 * GLC_PROFILE_BINS + i];
+        out->evaluation_count[i] = h[1 * GLC_PROFILE_BINS + i];
+        out->time_step_count_interrupted[i] = h[2 * GLC_PROFILE_BINS + i];
+        out->evaluation_count_interrupted[i] = h[3 * GLC_PROFILE_BINS + i];
+    }
+    for (int i = 0; i < GLC_NY; i++) out->property_hits[i] = h[kProfHits + i];
+    out->property_hits_unknown = h[kProfUnknown];
+    memcpy(&out->time_step_smallest, &h[kProfSmallest], sizeof(double));
     return 0;
 }
 

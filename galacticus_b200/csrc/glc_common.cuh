@@ -24,6 +24,8 @@
 #define GLC_ANY(p) __any_sync(0xffffffffu, (p))
 #define GLC_COUNT(k) ((void)0)
 #define GLC_SYNCWARP() __syncwarp()
+// smallest positive double: positive IEEE doubles order like their bit patterns
+#define glc_atomic_min_positive_double(p, v) atomicMin((p), (unsigned long long)__double_as_longlong(v))
 #ifndef GLC_BLOCK
 #define GLC_BLOCK 128
 #endif
@@ -39,6 +41,7 @@
 #endif
 #else
 #include <math.h>
+#include <string.h>
 #include <algorithm>
 #define GLC_DEVICE_INLINE static inline
 #define GLC_DEVICE_METHOD inline
@@ -64,6 +67,11 @@ static inline T glc_atomic_add(T *p, T v) {
     T o = *p;
     *p = o + v;
     return o;
+}
+static inline void glc_atomic_min_positive_double(unsigned long long *p, double v) {
+    unsigned long long b;
+    memcpy(&b, &v, sizeof b);
+    if (b < *p) *p = b;
 }
 using std::max;
 using std::min;
@@ -143,7 +151,15 @@ struct DeviceTables {
     // constructor-time constants of accretionDisksSwitched (switched.F90:259-297 takes these logarithms at every call; they
     // are pure functions of the parameters): ln(accretionRateThinDiskMinimum), ln(accretionRateThinDiskMaximum)
     double lnThinDiskMin, lnThinDiskMax;
+    // mergerTreeEvolveProfilerSimple: bin edges of the step-size histogram (Make_Range logarithmic, simple.F90:147) and the
+    // device accumulators [time_step_count | evaluation_count | ..._interrupted | ..._interrupted][bins], then
+    // property_hits[NY], hits "unknown", smallest step (bits of a positive double); null = profiling off
+    double profEdges[GLC_PROFILE_BINS];
+    int profBins;
+    unsigned long long *profile;
 };
+constexpr int kProfHits = 4 * GLC_PROFILE_BINS, kProfUnknown = kProfHits + GLC_NY, kProfSmallest = kProfUnknown + 1,
+              kProfWords = kProfSmallest + 1;
 
 struct LaneState;
 

@@ -22,7 +22,11 @@
 #define GLC_HD __host__ __device__ __forceinline__
 /* the big kernels call exp/log/pow/atan/cbrt as real functions: inlining their polynomial kernels at every
    call site blew the evolve kernel up to 665 KB of SASS and made it instruction-fetch bound */
+#ifdef GLC_INLINE_MATH
+#define GLC_HD_BIG __host__ __device__ __forceinline__
+#else
 #define GLC_HD_BIG __host__ __device__ __noinline__
+#endif
 #else
 #define GLC_HD static inline
 #define GLC_HD_BIG static inline

@@ -96,6 +96,10 @@ struct LaneState {
     int interruptFound, interruptCode, count, inApply, outWritten, yslot, kslot, trial, finalStep;
     int segmentsThisNode, nodeStatus, solveFailed, forbiddenNegatives;
     unsigned int nAcc, nRej, nRhs, nSeg, nTrialFail, nNodes, nDone, pad;
+    // profileOdeEvolver: largest scaled error of the attempt and the property that has it (standardStepErrorAnalyzer
+    // :1210-1219), evolve_apply calls since the last successful one (countEvaluationsToSuccess)
+    double profErrMax;
+    int limiting, evalsToSuccess;
 };
 
 GLC_DEVICE_INLINE void lane_reset(LaneState &L) {
@@ -266,6 +270,7 @@ GLC_UNROLL_RK
             L.interruptCode = GLC_INT_NONE;
             L.trial = 0;
             L.solveFailed = 0;
+            L.evalsToSuccess = 0;
             L.x = L.timeStartSaved;
             L.phase = (L.timeStartSaved != L.tEnd && L.mask != 0u) ? PH_TRIAL : PH_SOLVE_DONE;
         }
@@ -305,6 +310,8 @@ GLC_UNROLL_RK
                 L.finalStep = 0;
             }
             L.rmax = DBL_MIN;
+            L.profErrMax = 0.0;
+            L.limiting = -1;
             L.forbiddenNegatives = 0;
             L.stage = needK1 ? 0 : 1;
             L.phase = PH_STAGE;
@@ -354,6 +361,10 @@ GLC_UNROLL_RK
                         const double D0 = epsRel * fabs(ynew) + epsAbs * M.W(WS_SCALE, i);
                         const double r = fabs(yerr) / fabs(D0);
                         rmax = fmax(r, rmax);
+                        if (GLC_TABLES.profile && r > L.profErrMax) {  // scaledError > scaledErrorMaximum: the first maximum wins
+                            L.profErrMax = r;
+                            L.limiting = i;
+                        }
                         if (nonNeg && prop_is_non_negative(i) && ynew < 0.0) forbidden = 1;
                     }
                 }
@@ -466,6 +477,7 @@ GLC_UNROLL_RK
         // of t0 here; if it is beyond the interrupt time the solver restarts from the initial state.
         L.x1 = L.timeInterruptFirst;
         L.inApply = 0;
+        L.evalsToSuccess++;  // the analyzer sees the interrupted evolve_apply call too (status /= success: counted, :1205-1207)
         if (L.x > L.x1) {
 GLC_UNROLL_RK
             for (int i = 0; i < NY; i++) M.W(WS_YA, i) = M.AR(i, L.node);
@@ -511,7 +523,8 @@ GLC_UNROLL_RK
             L.phase = PH_ATTEMPT;
             return;
         }
-        // GSL_FAILURE: step-size underflow
+        // GSL_FAILURE: step-size underflow (the analyzer counts the call and returns, :1205-1207)
+        L.evalsToSuccess++;
         L.h = L.h0;
         L.inApply = 0;
         L.solveFailed = 1;
@@ -520,6 +533,30 @@ GLC_UNROLL_RK
         return;
     }
     // ---- accepted
+    if (GLC_TABLES.profile) {
+        // standardStepErrorAnalyzer (:1187-1239) -> mergerTreeEvolveProfilerSimple::profile (simple.F90:250-304); the step
+        // handed to it is evolve's last_step (driver2.c:195-198)
+        unsigned long long *P = GLC_TABLES.profile;
+        const int nb = GLC_TABLES.profBins;
+        int lo = 0, hi = nb - 1;  // gsl_interp_bsearch over the bin edges
+        while (hi > lo + 1) {
+            const int mid = (hi + lo) >> 1;
+            if (GLC_TABLES.profEdges[mid] > hOld)
+                hi = mid;
+            else
+                lo = mid;
+        }
+        const unsigned long long evals = (unsigned long long)L.evalsToSuccess + 1ull;
+        glc_atomic_add(&P[0 * GLC_PROFILE_BINS + lo], 1ull);
+        glc_atomic_add(&P[1 * GLC_PROFILE_BINS + lo], evals);
+        if (L.interruptFound) {
+            glc_atomic_add(&P[2 * GLC_PROFILE_BINS + lo], 1ull);
+            glc_atomic_add(&P[3 * GLC_PROFILE_BINS + lo], evals);
+        }
+        glc_atomic_add(&P[(L.limiting >= 0) ? kProfHits + L.limiting : kProfUnknown], 1ull);
+        glc_atomic_min_positive_double(&P[kProfSmallest], hOld);
+        L.evalsToSuccess = 0;
+    }
     if (!L.finalStep) L.h = L.h0;
     L.yslot ^= 1;
     L.inApply = 0;

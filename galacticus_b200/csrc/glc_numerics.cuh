@@ -325,6 +325,10 @@ GLC_DEVICE_INLINE double rescale_error(double err, double resultAbs, double resu
     return err;
 }
 
+#ifndef GLC_QAG_UNROLL
+#define GLC_QAG_UNROLL 1
+#endif
+constexpr int kQagUnroll = GLC_QAG_UNROLL;
 constexpr int kQagLimitDevice = 24;  // intervals kept per thread; the reference allows 1000 and aborts beyond
 
 // Re-entrant form of gsl_integration_qag(key = GAUSS15): the caller owns the loop.
@@ -364,7 +368,11 @@ GLC_DEVICE_INLINE void qag_pass(QagState &Q, F &&f) {
         const double center = 0.5 * (Q.ia + Q.ib);
         const double halfLength = 0.5 * (Q.ib - Q.ia);
         const double absHalfLength = fabs(halfLength);
-#pragma unroll 1
+        // the 15 abscissae are independent: unrolling by GLC_QAG_UNROLL interleaves their dependency chains (a lone lane is
+        // bound by the latency of dependent FP64 instructions, not by issue slots)
+#if defined(__CUDACC__)
+#pragma unroll kQagUnroll
+#endif
         for (int j = 0; j < 15; j++) {
             double x;
             if (j == 0)

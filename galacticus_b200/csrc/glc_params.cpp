@@ -95,5 +95,9 @@ extern "C" int glc_params_default(glc_params *P, int32_t model) {
     P->timestepSimpleRelative = 0.1;              // merger_trees/evolve/timesteps/simple.F90 defaults
     P->timestepSimpleAbsolute = 1.0;
     P->wallClockMaximumSeconds = 0.0;
+    P->profileOdeEvolver = 0;                     // node_evolver/standard.F90:249-253
+    P->profilerTimeStepPointsPerDecade = 3;       // merger_trees/evolve/profiler/simple.F90:84-104
+    P->profilerTimeStepMinimum = 1.0e-6;
+    P->profilerTimeStepMaximum = 1.0e+1;
     return 0;
 }

@@ -96,6 +96,18 @@ inline void build_nfw_j_table(std::vector<double> &xs, std::vector<double> &js) 
     }
 }
 
+// bin edges of mergerTreeEvolveProfilerSimple (simple.F90:128-147): Make_Range(min, max, n, logarithmic) with
+// n = int(log10(max / min) * pointsPerDecade) + 1, i.e. exp of a linear range of the logarithms
+inline int build_profile_edges(const glc_params &P, double *edges) {
+    int n = (int)(log10(P.profilerTimeStepMaximum / P.profilerTimeStepMinimum) * (double)P.profilerTimeStepPointsPerDecade) + 1;
+    if (n < 2) n = 2;
+    if (n > GLC_PROFILE_BINS) n = GLC_PROFILE_BINS;
+    const double l0 = dm_log(P.profilerTimeStepMinimum), l1 = dm_log(P.profilerTimeStepMaximum);
+    for (int i = 0; i < n; i++) edges[i] = dm_exp(l0 + (l1 - l0) * (double)i / (double)(n - 1));
+    for (int i = n; i < GLC_PROFILE_BINS; i++) edges[i] = 0.0;
+    return n;
+}
+
 inline void pow_table_spacing(double rangeMin, double rangeMax, int n, double &dx, double &inverseDx) {
     dx = (rangeMax - rangeMin) / (double)(n - 1);
     inverseDx = 1.0 / ((rangeMin + dx) - rangeMin);

@@ -52,7 +52,11 @@ def load_library() -> C.CDLL:
     L.glc_evolve_arena.argtypes = [vp, C.c_int64, C.POINTER(abi.glc_counters)]
     L.glc_last_kernel_ms.restype = C.c_float
     L.glc_last_kernel_ms.argtypes = [vp]
-    L.glc_last_phase_stats.argtypes = [vp, _dp]
+    if hasattr(L, "glc_profiler_read"):
+        L.glc_profiler_read.argtypes = [vp, C.POINTER(abi.glc_profile)]
+        L.glc_profiler_reset.argtypes = [vp]
+    if hasattr(L, "glc_last_phase_stats"):  # (absent from older builds kept for regression experiments)
+        L.glc_last_phase_stats.argtypes = [vp, _dp]
     L.glc_arena_device_props.restype = vp
     L.glc_arena_device_props.argtypes = [vp]
     L.glc_evolver_stream.restype = vp
@@ -166,6 +170,15 @@ class Evolver:
         c = abi.glc_counters()
         self._check(self.L.glc_evolve_arena(self.h, n, C.byref(c)), "glc_evolve_arena")
         return abi.counters_dict(c), float(self.L.glc_last_kernel_ms(self.h))
+
+    def profiler_read(self):
+        """mergerTreeEvolveProfilerSimple accumulators (profileOdeEvolver must be set) as a dict of numpy arrays."""
+        pr = abi.glc_profile()
+        self._check(self.L.glc_profiler_read(self.h, C.byref(pr)), "glc_profiler_read")
+        return abi.profile_dict(pr)
+
+    def profiler_reset(self) -> None:
+        self._check(self.L.glc_profiler_reset(self.h), "glc_profiler_reset")
 
     def last_phase_stats(self):
         """{machine_ms, drain_ms, machine_rhs, drain_rhs, machine_steps, drain_steps} of the last machine batch."""

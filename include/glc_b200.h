@@ -235,6 +235,12 @@ typedef struct glc_params {
        budget in seconds for ONE batched call (0 = none): nodes not finished when it expires come back with
        GLC_STATUS_XCPU (errorStatusXCPU) */
     double wallClockMaximumSeconds;
+    /* mergerTreeNodeEvolverStandard [profileOdeEvolver] (node_evolver/standard.F90:249-253): feed every successful step to the
+       profiler (standardStepErrorAnalyzer :1187-1239 -> mergerTreeEvolveProfilerSimple, merger_trees/evolve/profiler/
+       simple.F90 [timeStepMinimum, timeStepMaximum, timeStepPointsPerDecade]); read back with glc_profiler_read */
+    int32_t profileOdeEvolver;
+    int32_t profilerTimeStepPointsPerDecade;
+    double profilerTimeStepMinimum, profilerTimeStepMaximum;
 } glc_params;
 
 enum glc_dmo_profile {
@@ -294,6 +300,21 @@ typedef struct glc_counters {
     uint64_t trials_failed;  /* trialCount increments (standard.F90:686-692) */
     uint64_t nodes;
 } glc_counters;
+
+/* what mergerTreeEvolveProfilerSimple accumulates (merger_trees/evolve/profiler/simple.F90:250-304): per bin of the step
+ * size (bin i holds time_step[i] <= h < time_step[i+1], searchArray) the number of successful steps and of solver
+ * evaluations (evolve_apply calls up to and including the successful one), the same for steps taken after an interrupt
+ * was found, the number of steps limited by each property (propertyHits; index = enum glc_prop) and the smallest step */
+#define GLC_PROFILE_BINS 32
+typedef struct glc_profile {
+    int32_t n_bins, pad;
+    double time_step[GLC_PROFILE_BINS];
+    uint64_t time_step_count[GLC_PROFILE_BINS], evaluation_count[GLC_PROFILE_BINS];
+    uint64_t time_step_count_interrupted[GLC_PROFILE_BINS], evaluation_count_interrupted[GLC_PROFILE_BINS];
+    uint64_t property_hits[GLC_NY];
+    uint64_t property_hits_unknown; /* steps with zero error in every property ("unknown") */
+    double time_step_smallest;
+} glc_profile;
 
 typedef struct glc_evolver glc_evolver; /* opaque; owns device arena, tables, stream */
 
@@ -392,6 +413,11 @@ int glc_stream_collect(glc_evolver *ev, int64_t max_nodes, int64_t *tickets, dou
                        int32_t *status, int32_t *interrupt, int64_t *n_out);
 int glc_stream_finish(glc_evolver *ev, glc_counters *counters);
 int glc_stream_end(glc_evolver *ev);
+
+/* replaces: mergerTreeEvolveProfiler (the metaData/evolverProfiler output of a profileOdeEvolver=true run).  Accumulates over
+ * all batches since the last reset. */
+int glc_profiler_read(glc_evolver *ev, glc_profile *out);
+int glc_profiler_reset(glc_evolver *ev);
 
 /* one evaluation of the RHS (standardODEs) for each node, for unit-level parity tests:
  *   dydt [n][GLC_NY] host out; props/flags are not modified except radii warm starts. */

@@ -56,6 +56,10 @@ def lib(fast: bool = False) -> C.CDLL:
                                    C.POINTER(C.c_int)]
         L.orc_forest_evolve.argtypes = [C.POINTER(abi.glc_params), C.c_void_p, C.c_long, _ip, _dp, _dp, _dp, _dp, _dp, _ip, _ip,
                                         C.POINTER(abi.glc_forest_counters), C.POINTER(abi.glc_counters), C.c_int]
+        L.orc_profiler_reset.restype = None
+        L.orc_profiler_reset.argtypes = [C.POINTER(abi.glc_params)]
+        L.orc_profiler_read.restype = None
+        L.orc_profiler_read.argtypes = [C.POINTER(abi.glc_profile)]
         _LIBS[name] = L
     return _LIBS[name]
 
@@ -109,6 +113,14 @@ class Oracle:
                                      interrupt, C.byref(c), n_threads)
         assert rc == 0
         return status, interrupt, abi.counters_dict(c)
+
+    def profiler_reset(self):
+        self.L.orc_profiler_reset(C.byref(self.params))
+
+    def profiler_read(self):
+        pr = abi.glc_profile()
+        self.L.orc_profiler_read(C.byref(pr))
+        return abi.profile_dict(pr)
 
     def rhs(self, props_row, flag):
         dydt = np.zeros(abi.NY, dtype=np.float64)

@@ -1692,6 +1692,48 @@ void orc_rotation_curve_probe(const glc_params *P, const orc_tables *T, double *
     out[4] = w.vvir;
 }
 
+/* known-answer access to the mass distributions the path uses (tests/test_oracle_mass_distributions.py pins them to
+ * source/tests/mass_distributions.F90): beta profile (beta = 2/3) of total `mass` inside `router` with core radius `rcore`:
+ * out[0] = M(<radius), out[1] = rho(radius), out[2], out[3] = the scale-free radial moments m = 2, 3 from 0 to radius/rcore
+ * (radialMomentTwoThirds), out[4] = rho_0; Hernquist sphere of unit mass and scale length: out[5] = M(<radius) via the
+ * rotation-curve term of baryonic_vc2 (V^2 r / G); out[6] = NFW scale-free enclosed mass m(radius). */
+void orc_mass_distribution_probe(const glc_params *P, double mass, double rcore, double router, double radius, double *out) {
+    orc_evolve_ctx c;
+    std_work w;
+    double props[GLC_NPROP];
+    memset(&c, 0, sizeof(c));
+    memset(props, 0, sizeof(props));
+    c.P = P;
+    c.p = props;
+    c.flags = GLC_F_HAS_HOTHALO | GLC_F_HAS_SPHEROID;
+    work_init(&w, &c, 1.0);
+    /* fill the memoised profile directly (hh_profile would derive the radii from the halo scales) */
+    w.halo_done = 1;
+    w.hh_done = 1;
+    w.hh_valid = 1;
+    w.hh_router = router;
+    w.hh_rcore = rcore;
+    w.hh_mass = mass;
+    {
+        const double r = router / rcore;
+        const double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - dm_atan(r));
+        w.hh_rho0 = mass / 4.0 / ORC_PI / (rcore * rcore * rcore) * nf;
+    }
+    out[0] = hh_mass_enclosed(&w, radius);
+    out[1] = hh_density(&w, radius);
+    out[2] = hh_radial_moment23(2, radius / rcore);
+    out[3] = hh_radial_moment23(3, radius / rcore);
+    out[4] = w.hh_rho0;
+    /* Hernquist: unit mass in stars, unit scale length, no disk, no hot halo contribution */
+    props[GLC_P_SPH_MASS_STELLAR] = 1.0;
+    props[GLC_P_SPH_RADIUS] = 1.0;
+    c.flags = GLC_F_HAS_SPHEROID;
+    work_init(&w, &c, 1.0);
+    w.halo_done = 1;
+    out[5] = baryonic_vc2(&w, radius) * radius / ORC_G_INTERNAL;
+    out[6] = nfw_mass_scale_free(radius);
+}
+
 /* known-answer access to the black-hole helper functions (tests/test_oracle_black_holes.py):
  * out[0..3] = ISCO radius, specific energy, specific angular momentum (gravitational units, prograde), Eddington
  * accretion rate (Msun/Gyr); out[4] = Bondi-Hoyle-Lyttleton radius (Mpc) and out[5] = rate (Msun/Gyr) for unit

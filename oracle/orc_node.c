@@ -5,6 +5,7 @@
  */
 #include "orc_node.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -76,6 +77,71 @@ static void standard_post_step(double time, double *y, int *status, void *vctx) 
     if (*status == ORC_GSL_CONTINUE) *status = ORC_GSL_SUCCESS;
 }
 
+/* ---- profiling: standardStepErrorAnalyzer (standard.F90:1187-1239) -> mergerTreeEvolveProfilerSimple::profile
+ * (merger_trees/evolve/profiler/simple.F90:250-304) */
+static glc_profile g_profile;
+void orc_profiler_reset(const glc_params *P) {
+    int i, n;
+    double l0, l1;
+    memset(&g_profile, 0, sizeof(g_profile));
+    /* simple.F90:128-147: Make_Range(min, max, n, logarithmic), n = int(log10(max / min) * pointsPerDecade) + 1 */
+    n = (int)(log10(P->profilerTimeStepMaximum / P->profilerTimeStepMinimum) * (double)P->profilerTimeStepPointsPerDecade) + 1;
+    if (n < 2) n = 2;
+    if (n > GLC_PROFILE_BINS) n = GLC_PROFILE_BINS;
+    l0 = dm_log(P->profilerTimeStepMinimum);
+    l1 = dm_log(P->profilerTimeStepMaximum);
+    for (i = 0; i < n; i++) g_profile.time_step[i] = dm_exp(l0 + (l1 - l0) * (double)i / (double)(n - 1));
+    g_profile.n_bins = n;
+    g_profile.time_step_smallest = DBL_MAX;
+}
+void orc_profiler_read(glc_profile *out) { *out = g_profile; }
+
+static void standard_step_error_analyzer(double time, double time_end, const double *y, const double *yerr, double time_step,
+                                         int step_status, void *vctx) {
+    orc_evolve_ctx *c = (orc_evolve_ctx *)vctx;
+    double scaled_error_maximum = 0.0;
+    int i, limiting = -1, lo, hi;
+    (void)time;
+    (void)time_end;
+    c->evals_to_success++;
+    if (step_status != ORC_GSL_SUCCESS) return;
+    for (i = 0; i < c->n_active; i++) {
+        const double scale = c->P->odeToleranceAbsolute * c->scale[i] + c->P->odeToleranceRelative * fabs(y[i]);
+        const double scaled_error = fabs(yerr[i]) / scale;
+        if (scaled_error > scaled_error_maximum) {
+            scaled_error_maximum = scaled_error;
+            limiting = c->active[i];
+        }
+    }
+    /* searchArray = gsl_interp_bsearch over the bin edges */
+    lo = 0;
+    hi = g_profile.n_bins - 1;
+    while (hi > lo + 1) {
+        const int mid = (hi + lo) >> 1;
+        if (g_profile.time_step[mid] > time_step)
+            hi = mid;
+        else
+            lo = mid;
+    }
+#ifdef _OPENMP
+#pragma omp critical(orc_profile)
+#endif
+    {
+        g_profile.time_step_count[lo] += 1;
+        g_profile.evaluation_count[lo] += c->evals_to_success;
+        if (c->interrupt_first_found) {
+            g_profile.time_step_count_interrupted[lo] += 1;
+            g_profile.evaluation_count_interrupted[lo] += c->evals_to_success;
+        }
+        if (limiting >= 0)
+            g_profile.property_hits[limiting] += 1;
+        else
+            g_profile.property_hits_unknown += 1;
+        if (time_step < g_profile.time_step_smallest) g_profile.time_step_smallest = time_step;
+    }
+    c->evals_to_success = 0;
+}
+
 static int is_non_negative_prop(int prop) {
     /* isNonNegative="true" attributes of the component definitions; only the satellite
        bound mass (satellite/standard.F90:46-49) is not flagged */
@@ -122,6 +188,9 @@ int orc_evolve_node_segment(const glc_params *P, const orc_tables *T, double *pr
         ode_status = ORC_GSL_FAILURE;
         orc_ode_init(&solver, (size_t)c.n_active, standard_odes, &c, P->odeToleranceAbsolute,
                      P->odeToleranceRelative, scale, nonneg, standard_post_step);
+        c.scale = scale;
+        c.evals_to_success = 0;
+        if (P->profileOdeEvolver) solver.analyzer = standard_step_error_analyzer; /* errorAnalyzer, :633 */
         while (trial_count < TRIAL_COUNT_MAXIMUM &&
                !(ode_status == ORC_GSL_SUCCESS || ode_status == ORC_GSL_EBADFUNC)) {
             if (P->reuseODEStepSize)

@@ -50,6 +50,8 @@ typedef struct orc_evolve_ctx {
     int interrupt_first_code;
     orc_ode_solver *solver;
     int nonfinite;
+    const double *scale;          /* by y index: propertyScalesActive */
+    unsigned long evals_to_success; /* countEvaluationsToSuccess (per call here; an object member in the reference) */
 } orc_evolve_ctx;
 
 /* one standardEvolve call: evolves the record to time_end or the first interrupt.
@@ -71,6 +73,10 @@ int orc_rhs_node(const glc_params *P, const orc_tables *T, double *props, int fl
                  int *interrupt);
 
 void orc_params_default(glc_params *P, int model);
+
+/* mergerTreeEvolveProfilerSimple fed by standardStepErrorAnalyzer when P->profileOdeEvolver (process-wide accumulators) */
+void orc_profiler_reset(const glc_params *P);
+void orc_profiler_read(glc_profile *out);
 
 /* model hooks (orc_model_box.c, orc_model_standard.c) */
 int orc_model_active_list(const orc_evolve_ctx *c, int *active);

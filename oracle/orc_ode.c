@@ -236,6 +236,7 @@ int orc_driver2_apply(orc_ode_solver *s, double *t, double t1, double *y) {
     if (sign * (t1 - *t) < 0.0) return ORC_GSL_EINVAL;
     while (sign * (t1 - *t) > 0.0) {
         int st = orc_evolve_apply(s, t, t1, &s->h, y);
+        if (s->analyzer != NULL) s->analyzer(*t, t1, y, s->yerr, s->last_step, st, s->ctx); /* driver2.c:195-198 */
         if (st != ORC_GSL_SUCCESS) return st;
         if (s->post_step != NULL) {
             int ps = ORC_GSL_SUCCESS;

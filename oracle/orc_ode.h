@@ -49,6 +49,9 @@ typedef int (*orc_rhs_fn)(double t, const double *y, double *dydt, void *ctx);
 /* postStep(t, y, &status): may edit y; status != 0 forces an evolve reset (driver2.c:206-217). */
 typedef void (*orc_poststep_fn)(double t, double *y, int *status, void *ctx);
 
+/* stepAnalyzer(t, t1, y, yerr, last_step, status): driver2.c:195-198 */
+typedef void (*orc_analyzer_fn)(double t, double t1, const double *y, const double *yerr, double h, int status, void *ctx);
+
 typedef struct {
     /* system */
     size_t dim;
@@ -72,6 +75,7 @@ typedef struct {
     unsigned long n;
     /* odeSolver-level */
     orc_poststep_fn post_step;
+    orc_analyzer_fn analyzer; /* NULL unless profileOdeEvolver */
     double interrupted_at_x; /* module variable interruptedAtX (ODE_Solver_Error_Codes) */
     /* statistics (not in the reference; used for the metric "node-ODE steps") */
     unsigned long n_steps_accepted, n_steps_rejected, n_rhs;

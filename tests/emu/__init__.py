@@ -44,6 +44,7 @@ def lib() -> C.CDLL:
         L.emu_forest_evolve.argtypes = [C.c_void_p, C.c_int64, _ip, _dp, _dp, _dp, _dp, _dp, _ip, _ip,
                                         C.POINTER(abi.glc_forest_counters), C.POINTER(abi.glc_counters), C.c_int, C.c_int, C.c_int,
                                         C.c_int]
+        L.emu_profiler_read.argtypes = [C.c_void_p, C.POINTER(abi.glc_profile)]
         _LIB = L
     return _LIB
 
@@ -91,6 +92,11 @@ class EmuEvolver:
         assert rc == 0
         self.slices = s.value
         return status, interrupt, abi.counters_dict(c)
+
+    def profiler_read(self):
+        pr = abi.glc_profile()
+        assert self.L.emu_profiler_read(self.h, C.byref(pr)) == 0
+        return abi.profile_dict(pr)
 
     def forest_evolve(self, forest):
         """The product's host scheduler (csrc/host/glc_forest.hpp) over the host-executed kernel source."""

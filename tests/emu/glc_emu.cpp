@@ -36,6 +36,7 @@ struct Emu {
     PreparedTable tables[GLC_NTABLES];
     DeviceTables dt;
     std::vector<double> powAc, powKmt, nfwJx, nfwJv;
+    std::vector<unsigned long long> profile;
 };
 
 template <class Model>
@@ -339,6 +340,14 @@ void emu_set_params(void *h, const glc_params *p) {
         pow_table_spacing(1.0, 1000.0, e->dt.powKmtN, e->dt.powKmtDx, e->dt.powKmtInvDx);
         e->dt.lnThinDiskMin = p->accretionRateThinDiskMinimum > 0.0 ? dm_log(p->accretionRateThinDiskMinimum) : 0.0;
         e->dt.lnThinDiskMax = p->accretionRateThinDiskMaximum > 0.0 ? dm_log(p->accretionRateThinDiskMaximum) : 0.0;
+        e->dt.profile = nullptr;
+        e->dt.profBins = 0;
+        if (p->profileOdeEvolver) {
+            e->profile.assign(kProfWords, 0ull);
+            e->profile[kProfSmallest] = 0x7f7f7f7f7f7f7f7full;
+            e->dt.profBins = build_profile_edges(*p, e->dt.profEdges);
+            e->dt.profile = e->profile.data();
+        }
         build_nfw_j_table(e->nfwJx, e->nfwJv);
         e->dt.nfwJx = e->nfwJx.data();
         e->dt.nfwJv = e->nfwJv.data();
@@ -428,6 +437,25 @@ int emu_forest_evolve(void *h, int64_t n_nodes, const int32_t *parent, const dou
     if (counters) *counters = total;
     return rc;
 }
+int emu_profiler_read(void *h, glc_profile *out) {
+    Emu *e = (Emu *)h;
+    memset(out, 0, sizeof(*out));
+    if (e->profile.empty()) return -9;
+    const unsigned long long *P = e->profile.data();
+    out->n_bins = e->dt.profBins;
+    for (int i = 0; i < GLC_PROFILE_BINS; i++) {
+        out->time_step[i] = e->dt.profEdges[i];
+        out->time_step_count[i] = P[0 * GLC_PROFILE_BINS + i];
+        out->evaluation_count[i] = P[1 * GLC_PROFILE_BINS + i];
+        out->time_step_count_interrupted[i] = P[2 * GLC_PROFILE_BINS + i];
+        out->evaluation_count_interrupted[i] = P[3 * GLC_PROFILE_BINS + i];
+    }
+    for (int i = 0; i < GLC_NY; i++) out->property_hits[i] = P[kProfHits + i];
+    out->property_hits_unknown = P[kProfUnknown];
+    memcpy(&out->time_step_smallest, &P[kProfSmallest], sizeof(double));
+    return 0;
+}
+
 // Debugging aid: replays slots dumped by a GLC_LEDGER build of the product (GLC_LEDGER_DUMP=file) on the host, one unit at a
 // time, printing the unit sequence -- to see on the CPU what a slot that never finishes on the device is doing.
 int emu_replay_slots(void *h, const char *path, int max_steps, int verbose) {

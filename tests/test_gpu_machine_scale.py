@@ -66,3 +66,35 @@ def test_fast_turnover_batch_600k(oracle_lib):
 def test_fast_turnover_batch_user_slices(oracle_lib):
     """The same regime in user time slices (no drain hand-over: the machine alone runs every node to its end)."""
     _run(oracle_lib, 330_000, seed=4001, budget=2048)
+
+
+def test_forest_4000_trees(oracle_lib):
+    """The case that exposed the defect: 4000 Milky-Way-mass trees (6.9 million nodes) through glc_forest_evolve.  In round 1
+    the third machine batch of this forest (551 585 nodes) lost 132 nodes and never finished.  Every tree must reach its
+    final time with no failed evolve, and -- trees being independent -- the records of the first trees must equal the
+    checker's depth-first walk over those trees alone, bit for bit."""
+    import os
+
+    from galacticus_b200.evolver import Evolver
+
+    p = cases.standard_params(with_black_holes=True)
+    forest = synthetic.binary_split_forest(p, 4000, 1.52e12, 1.0e9, seed=219)
+    ev = Evolver(0)
+    synthetic.install(ev, p)
+    rec, flags, state, fc, c = ev.forest_evolve(forest)
+    ev.close()
+    assert fc["failed_evolves"] == 0 and fc["trees"] == 4000
+    roots = forest["parent"] < 0
+    assert (state[roots] == abi.GLC_FOREST_NODE_ISOLATED).all()
+    assert (rec[roots, P["TIME"]] == forest["time"][roots]).all()
+    n_sub = 120
+    sub = synthetic.forest_subset(forest, n_sub)
+    o = oracle_lib.Oracle(fast=False)
+    synthetic.install(o, p)
+    ro, fo, so, fco, co = o.forest_evolve(sub, n_threads=os.cpu_count() or 1)
+    keep = forest["tree"] < n_sub
+    np.testing.assert_array_equal(state[keep], so)
+    np.testing.assert_array_equal(flags[keep], fo)
+    alive = so != abi.GLC_FOREST_NODE_PROMOTED
+    bad = np.argwhere(rec[keep][alive] != ro[alive])
+    assert bad.size == 0, f"{len(bad)} record entries of the first {n_sub} trees differ from the checker"
