@@ -68,3 +68,28 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read().lower()
                 assert "oracle" not in src and "liborc" not in src, f"{f} references the oracle"
+
+
+def test_fortran_interface_matches_header():
+    """integration/B200_interface.F90 (the ISO_C_BINDING module of INTEGRATION.md) is generated from include/glc_b200.h:
+    the committed file must be what the generator produces now, every struct field of the C-ABI must appear in its bind(c)
+    type in header order, and the per-node status codes must be the reference's errorStatus* values
+    (source/error/_module.F90:66-75 = GSL error codes)."""
+    import importlib.util
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_fortran_interface", os.path.join(root, "scripts", "gen_fortran_interface.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    committed = open(os.path.join(root, "integration", "B200_interface.F90")).read()
+    assert committed == gen.generate(), "run scripts/gen_fortran_interface.py"
+    block = re.search(r"type, bind\(c\) :: glcParams(.*?)end type glcParams", committed, flags=re.S).group(1)
+    fields = re.findall(r"::\s*(\w+)", block)
+    assert fields == [name for name, _ in abi.glc_params._fields_]
+    assert abi.GLC_STATUS_SUCCESS == 0 and abi.GLC_STATUS_FAIL == -1 and abi.GLC_STATUS_UNDERFLOW == 15
+    assert abi.GLC_STATUS_XCPU == 1025
+    for f in ("node_evolver_B200.F90", "evolver_B200.F90"):
+        src = open(os.path.join(root, "integration", f)).read()
+        for call in re.findall(r"\b(glc_\w+)\s*\(", src):
+            assert call in abi.DECLARED_FUNCTIONS, f"{f} calls {call}, which include/glc_b200.h does not declare"
