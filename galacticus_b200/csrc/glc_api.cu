@@ -81,6 +81,10 @@ struct glc_evolver {
     int64_t stream_n = 0;           // tickets handed out so far = length of the node queue
     unsigned char *d_collected = nullptr;
     int64_t *d_collect_list = nullptr;
+    int32_t *d_collect_meta = nullptr;   // [cap][3] flags, status, interrupt of the collected nodes
+    int32_t *h_collect_meta = nullptr;   // pinned
+    int64_t collect_meta_cap = 0;
+    int32_t forest_schedule = 1;         // glc_forest_evolve: 1 = asynchronous groups over the streaming machine, 0 = bulk-synchronous rounds
     int64_t collected_cap = 0;
     int64_t stream_collected = 0;
     int32_t *d_order = nullptr;     // queue order (component-sorted node ids)
@@ -900,6 +904,8 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaFree(ev->d_held);
     cudaFree(ev->d_collected);
     cudaFree(ev->d_collect_list);
+    cudaFree(ev->d_collect_meta);
+    cudaFreeHost(ev->h_collect_meta);
     cudaFree(ev->d_pow_ac);
     cudaFree(ev->d_pow_kmt);
     cudaFree(ev->d_nfw_jx);
@@ -1141,6 +1147,7 @@ int glc_evolver_set_option(glc_evolver *ev, int32_t option, int64_t value) {
         case GLC_OPT_SLICE_BUDGET: ev->slice_budget = (int32_t)std::max<int64_t>(0, std::min<int64_t>(value, 0x7fffffff)); return 0;
         case GLC_OPT_SORT_QUEUE: ev->sort_queue = value ? 1 : 0; return 0;
         case GLC_OPT_MICROTASK_MACHINE: ev->use_machine = value == 2 ? 2 : (value ? 1 : 0); return 0;
+        case GLC_OPT_FOREST_SCHEDULE: ev->forest_schedule = value ? 1 : 0; return 0;
         default: ev->err = "unknown option"; return -10;
     }
 }
@@ -1376,19 +1383,26 @@ int glc_stream_collect(glc_evolver *ev, int64_t max_nodes, int64_t *tickets, dou
     const int64_t m = std::min(count, max_nodes);
     ev->launches++;
     if (m == 0) return 0;
-    // rows are staged in d_stage (node-major, sized for the whole arena); meta behind the ticket list
-    int32_t *d_meta = nullptr;
-    GLC_CHECK(ev, cudaMalloc(&d_meta, sizeof(int32_t) * 3 * (size_t)m));
+    // rows are staged in d_stage (node-major, sized for the whole arena); meta in a buffer that grows geometrically
+    if (m > ev->collect_meta_cap) {
+        cudaFree(ev->d_collect_meta);
+        cudaFreeHost(ev->h_collect_meta);
+        ev->d_collect_meta = ev->h_collect_meta = nullptr;
+        const int64_t want = std::max<int64_t>(2 * m, 1 << 16);
+        GLC_CHECK(ev, cudaMalloc(&ev->d_collect_meta, sizeof(int32_t) * 3 * (size_t)want));
+        GLC_CHECK(ev, cudaHostAlloc(&ev->h_collect_meta, sizeof(int32_t) * 3 * (size_t)want, cudaHostAllocDefault));
+        ev->collect_meta_cap = want;
+    }
+    int32_t *d_meta = ev->d_collect_meta;
     collect_gather_kernel<<<(int)((m * 32 + 255) / 256), 256, 0, ev->stream>>>(ev->d_props, ev->cap, ev->d_collect_list, m, ev->d_stage,
                                                                               ev->d_flags, ev->d_status, ev->d_interrupt, d_meta);
     ev->launches++;
     GLC_CHECK(ev, cudaGetLastError());
-    std::vector<int32_t> meta(3 * (size_t)m);
+    int32_t *meta = ev->h_collect_meta;
     GLC_CHECK(ev, cudaMemcpyAsync(props, ev->d_stage, sizeof(double) * NPROP * m, cudaMemcpyDeviceToHost, ev->stream));
     GLC_CHECK(ev, cudaMemcpyAsync(tickets, ev->d_collect_list + 1, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, ev->stream));
-    GLC_CHECK(ev, cudaMemcpyAsync(meta.data(), d_meta, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaMemcpyAsync(meta, d_meta, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost, ev->stream));
     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
-    cudaFree(d_meta);
     for (int64_t k = 0; k < m; k++) {
         flags[k] = meta[3 * k + 0];
         status[k] = meta[3 * k + 1];
@@ -1578,7 +1592,154 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
         total.nodes += c.nodes;
         return 0;
     };
-    int rc = F.run(evolve);
+    int rc;
+    const char *envAsync = getenv("GLC_FOREST_ASYNC");
+    const bool asynchronous = (envAsync ? atoi(envAsync) != 0 : ev->forest_schedule != 0) && ev->use_machine != 0 && !ev->stream_active;
+    if (asynchronous) {
+        // ---- asynchronous groups over the streaming machine (Forest::run_async): the device never drains between batches
+        struct StreamEngine {
+            glc_evolver *ev;
+            glcf::Forest &F;
+            glc_counters &total;
+            bool log;
+            int64_t capacity = 0, inflight = 0, submitted = 0, collected = 0;
+            std::vector<int32_t> ticket_node;  // ticket of the current session -> node
+            std::vector<int32_t> q_nodes;
+            std::vector<double, PinnedAllocator<double>> q_props, q_tend, c_props;
+            std::vector<int32_t, PinnedAllocator<int32_t>> q_flags, c_flags, c_status, c_interrupt;
+            std::vector<int64_t, PinnedAllocator<int64_t>> c_tickets;
+            glc_counters session{};
+            double t0 = now_s(), t_run = 0.0, t_collect = 0.0, t_submit = 0.0;
+            int64_t polls = 0;
+            StreamEngine(glc_evolver *e, glcf::Forest &f, glc_counters &t, bool l) : ev(e), F(f), total(t), log(l) {}
+            int begin() {
+                // tickets are arena rows: room for several evolve calls per node; a full arena restarts the session (finish,
+                // collect, begin) -- see flush()
+                const int64_t want = std::min<int64_t>(std::max<int64_t>(8 * F.n + 65536, 1 << 20), 48ll << 20);
+                capacity = want;
+                ticket_node.clear();
+                submitted = collected = 0;
+                memset(&session, 0, sizeof(session));
+                return glc_stream_begin(ev, capacity);
+            }
+            void submit(int32_t node, double tend) {
+                q_nodes.push_back(node);
+                q_tend.push_back(tend);
+                inflight++;
+            }
+            int64_t in_flight() const { return inflight; }
+            void add_session() {
+                total.steps_accepted += session.steps_accepted;
+                total.steps_rejected += session.steps_rejected;
+                total.rhs_evaluations += session.rhs_evaluations;
+                total.segments += session.segments;
+                total.trials_failed += session.trials_failed;
+                total.nodes += session.nodes;
+            }
+            int collect(std::vector<int32_t> &done, std::vector<int32_t> &st, std::vector<int32_t> &in) {
+                const int64_t outstanding = submitted - collected;
+                if (outstanding <= 0) return 0;
+                if ((int64_t)c_tickets.size() < outstanding) {
+                    const size_t cap = (size_t)std::max<int64_t>(2 * outstanding, 1 << 16);
+                    c_tickets.resize(cap);
+                    c_props.resize(cap * GLC_NPROP);
+                    c_flags.resize(cap);
+                    c_status.resize(cap);
+                    c_interrupt.resize(cap);
+                }
+                int64_t nout = 0;
+                int rc = glc_stream_collect(ev, outstanding, c_tickets.data(), c_props.data(), c_flags.data(), c_status.data(),
+                                            c_interrupt.data(), &nout);
+                if (rc) return rc;
+                for (int64_t k = 0; k < nout; k++) {
+                    const int32_t node = ticket_node[(size_t)c_tickets[k]];
+                    memcpy(F.R(node), &c_props[(size_t)k * GLC_NPROP], sizeof(double) * GLC_NPROP);
+                    F.flags[node] = c_flags[k];
+                    done.push_back(node);
+                    st.push_back(c_status[k]);
+                    in.push_back(c_interrupt[k]);
+                }
+                collected += nout;
+                inflight -= nout;
+                return 0;
+            }
+            int flush() {
+                const int64_t m = (int64_t)q_nodes.size();
+                if (m == 0) return 0;
+                const double t = now_s();
+                if (submitted + m > capacity) {
+                    // arena full: run everything in flight to completion, hand it back at the next poll, start a new session
+                    restart = true;
+                    return 0;
+                }
+                q_props.resize((size_t)m * GLC_NPROP);
+                q_flags.resize(m);
+                for (int64_t k = 0; k < m; k++) {
+                    memcpy(&q_props[(size_t)k * GLC_NPROP], F.R(q_nodes[k]), sizeof(double) * GLC_NPROP);
+                    q_flags[k] = F.flags[q_nodes[k]];
+                    ticket_node.push_back(q_nodes[k]);
+                }
+                int64_t first = 0;
+                int rc = glc_stream_submit(ev, m, q_props.data(), q_flags.data(), q_tend.data(), &first);
+                if (rc) return rc;
+                submitted += m;
+                q_nodes.clear();
+                q_tend.clear();
+                t_submit += now_s() - t;
+                return 0;
+            }
+            bool restart = false;
+            int poll(std::vector<int32_t> &done, std::vector<int32_t> &st, std::vector<int32_t> &in) {
+                polls++;
+                if (restart) {
+                    int rc = glc_stream_finish(ev, &session);
+                    if (rc) return rc;
+                    rc = collect(done, st, in);
+                    if (rc) return rc;
+                    add_session();
+                    glc_stream_end(ev);
+                    rc = begin();
+                    if (rc) return rc;
+                    restart = false;
+                    return flush();  // the held-back submissions open the new session
+                }
+                for (int64_t idle = 0;; idle++) {
+                    if (idle > 200000) {
+                        ev->err = "glc_forest_evolve: 200 000 device time slices without a finished node";
+                        return GLC_ERR_STALLED;
+                    }
+                    // one time slice; shorter slices when few nodes are in flight, so that finished nodes are seen early
+                    const int64_t live = submitted - collected;
+                    const int budget = live > 200000 ? 4096 : (live > 20000 ? 1024 : 256);
+                    int64_t nfin = 0;
+                    double t = now_s();
+                    int rc = glc_stream_run(ev, budget, &nfin, &session);
+                    if (rc) return rc;
+                    t_run += now_s() - t;
+                    t = now_s();
+                    if (nfin > collected) {
+                        rc = collect(done, st, in);
+                        if (rc) return rc;
+                    }
+                    t_collect += now_s() - t;
+                    if (!done.empty()) return 0;
+                }
+            }
+            int end() {
+                add_session();
+                if (log)
+                    fprintf(stderr, "[glc forest async] %lld polls, %.2f s in device slices, %.2f s collecting, %.2f s submitting, %.2f s total\n",
+                            (long long)polls, t_run, t_collect, t_submit, now_s() - t0);
+                return glc_stream_end(ev);
+            }
+        };
+        StreamEngine E(ev, F, total, forest_log);
+        rc = E.begin();
+        if (rc == 0) rc = F.run_async(E);
+        const int rc2 = E.end();
+        if (rc == 0) rc = rc2;
+    } else
+        rc = F.run(evolve);
     if (forest_counters) *forest_counters = F.fc;
     if (counters) *counters = total;
     if (rc == 0 && !F.all_roots_finished()) {

@@ -513,7 +513,7 @@ GLC_DEVICE_INLINE bool machine_step(const SlotRef &S, const LaneMem &M) {
 // producers that did not wait: a consumer that was slow between reserving and reading could be lapped (its cell
 // overwritten: the slot was lost), and because the tag repeats every 32 laps it then took another slot's entry (the slot
 // ran on two lanes at once).  Seen on the device as nodes that never finish and as corrupted lane states in batches with
-// very fast turnover (profiles/r02_ledger_*.txt); the GLC_LEDGER build (node-ownership ledger + per-slot busy flags)
+// very fast turnover (profiles/r02a_ledger_4000_trees_round1_queues.txt); the GLC_LEDGER build (node-ownership ledger + per-slot busy flags)
 // proves the absence of both with this protocol.  All spins are bounded: a time-out sets the block's abort flag and the
 // host returns GLC_ERR_STALLED.
 constexpr unsigned int kCellFull = 1u << 11, kCellSlotMask = 0x7ffu, kLapMask = 0xfffffu;

@@ -444,6 +444,128 @@ struct Forest {
         }
         return 0;
     }
+    // ------------------------------------------------------------------------------------------ asynchronous schedule
+    // The rounds of run() end with a barrier: every batched call lasts as long as the chain of its slowest node (one node
+    // advances at ~4 000 rate-function evaluations per second on a GPU lane), whichever tree that node belongs to.  The rules
+    // above couple a node only to its own GROUP -- an isolated, childless host and the satellites it carries -- between
+    // arrival events, and arrivals are schedule independent by construction (a parent's time is fixed by the tree; the
+    // parent's side of the merger hooks is applied at its promotion in progenitor order).  run_async() therefore lets every
+    // group cycle on its own through the SAME two phases as a round of run() -- (A) its satellites that may move, all
+    // together; (B) the host itself; then the arrival test -- and only waits for the nodes of that group.  Every node sees the
+    // sequence of (state, end time) it sees under run() and under the reference's walk, so the results are bit-identical;
+    // what changes is that a slow node delays its own group, not the forest.
+    //
+    // Engine: submit(node, t_end) queues a node whose record is in R(node); flush() hands the queue to the device; poll(done,
+    // status, interrupt) makes the device work and returns nodes that have finished (records and flags written back in
+    // place); in_flight() = submitted and not yet returned.
+    template <class Engine>
+    int run_async(Engine &E) {
+        enum : uint8_t { NEED_A = 0, IN_A = 1, NEED_B = 2, IN_B = 3, AFTER_B = 4 };
+        std::vector<uint8_t> phase((size_t)n, (uint8_t)NEED_A), queued((size_t)n, 0);
+        std::vector<int32_t> pending((size_t)n, 0), group_of((size_t)n, -1), ready, done, dstatus, dinterrupt;
+        std::vector<double> tsub((size_t)n, 0.0);
+        auto wake = [&](int32_t h) {
+            if (!queued[h]) {
+                queued[h] = 1;
+                ready.push_back(h);
+            }
+        };
+        for (int32_t a : active_list) wake(a);
+        // a primary progenitor that has arrived takes over its parent once all its siblings have merged
+        auto try_promote = [&](int32_t p) {
+            const int32_t c = first_child[p];
+            if (c >= 0 && children_left[p] == 1 && state[c] == NS_ACTIVE && pending[c] == 0 && R(c)[GLC_P_TIME] == time[p]) {
+                promote(c);
+                phase[p] = NEED_A;
+                wake(p);
+            }
+        };
+        for (;;) {
+            for (size_t k = 0; k < ready.size(); k++) {  // (grows while it is walked: promotions wake the parent)
+                const int32_t h = ready[k];
+                queued[h] = 0;
+                if (state[h] != NS_ACTIVE || pending[h] > 0) continue;
+                for (int tries = 0; tries < 3; tries++) {
+                    if (phase[h] == AFTER_B) {
+                        // arrival at the parent: node merger at once, promotion when the siblings are gone
+                        const int32_t p = parent[h];
+                        if (p >= 0 && R(h)[GLC_P_TIME] == time[p]) {
+                            if (!is_primary(h)) {
+                                merge(h);
+                                try_promote(p);
+                            } else
+                                try_promote(p);
+                            break;  // merged, promoted, or waiting for its siblings
+                        }
+                        phase[h] = NEED_A;
+                    }
+                    if (phase[h] == NEED_A) {
+                        int32_t cnt = 0;
+                        for (int32_t s : sats[h]) {
+                            const double to = satellite_limit(s);
+                            if (to > R(s)[GLC_P_TIME]) {
+                                E.submit(s, to);
+                                tsub[s] = to;
+                                group_of[s] = h;
+                                cnt++;
+                            }
+                        }
+                        if (cnt) {
+                            pending[h] = cnt;
+                            phase[h] = IN_A;
+                            fc.evolve_calls += (uint64_t)cnt;
+                            break;
+                        }
+                        phase[h] = NEED_B;
+                    }
+                    if (phase[h] == NEED_B) {
+                        const double to = isolated_limit(h);
+                        if (to > R(h)[GLC_P_TIME]) {
+                            double sub = 0.0;
+                            for (int32_t s : sats[h]) sub += baryons(s);
+                            R(h)[GLC_P_MASS_BARYONIC_SUBHALOS] = sub;
+                            E.submit(h, to);
+                            tsub[h] = to;
+                            group_of[h] = h;
+                            pending[h] = 1;
+                            phase[h] = IN_B;
+                            fc.evolve_calls++;
+                            break;
+                        }
+                        phase[h] = AFTER_B;  // cannot move: perhaps it stands at its parent's time already
+                        if (tries >= 1) {
+                            // neither its satellites nor the host can move: the arrival test, then sleep until an event (a
+                            // promotion into this node) wakes the group
+                            const int32_t p = parent[h];
+                            if (p >= 0 && R(h)[GLC_P_TIME] == time[p]) continue;
+                            phase[h] = NEED_A;
+                            break;
+                        }
+                    }
+                }
+            }
+            ready.clear();
+            if (E.in_flight() == 0) break;
+            if (int rc = E.flush()) return rc;
+            done.clear();
+            dstatus.clear();
+            dinterrupt.clear();
+            if (int rc = E.poll(done, dstatus, dinterrupt)) return rc;
+            fc.rounds++;
+            for (size_t k = 0; k < done.size(); k++) {
+                const int32_t x = done[k], g = group_of[x];
+                if (dstatus[k] != GLC_STATUS_SUCCESS || dinterrupt[k] != GLC_INT_NONE) {
+                    fc.failed_evolves++;
+                    R(x)[GLC_P_TIME] = tsub[x];
+                }
+                if (--pending[g] == 0) {
+                    phase[g] = (phase[g] == IN_A) ? (uint8_t)NEED_B : (uint8_t)AFTER_B;
+                    wake(g);
+                }
+            }
+        }
+        return 0;
+    }
 };
 
 }  // namespace glcf

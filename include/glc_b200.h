@@ -379,9 +379,12 @@ enum glc_option {
     GLC_OPT_SLICE_BUDGET = 0, /* rate-function evaluations per lane per kernel launch (time slice); lanes park
                                  their solver state in HBM between slices.  0 = one launch runs to completion */
     GLC_OPT_SORT_QUEUE = 1,   /* 1 (default): hand nodes to lanes in component-sorted order */
-    GLC_OPT_MICROTASK_MACHINE = 2 /* standard model: 1 = micro-task machine kernel (units of the rate function re-grouped
+    GLC_OPT_MICROTASK_MACHINE = 2, /* standard model: 1 = micro-task machine kernel (units of the rate function re-grouped
                                  across lanes every iteration), 0 = warp-synchronous kernel, 2 (default) = machine for
                                  batches large enough to fill its queues, warp-synchronous kernel for small ones */
+    GLC_OPT_FOREST_SCHEDULE = 3  /* glc_forest_evolve: 1 (default) = asynchronous -- every host-and-satellites group cycles
+                                 on its own over the streaming machine, a slow node delays only its group; 0 = bulk-
+                                 synchronous rounds, one batched call per phase.  Same results bit for bit. */
 };
 int glc_evolver_set_option(glc_evolver *ev, int32_t option, int64_t value);
 /* number of time slices (evolve-kernel launches) so far */

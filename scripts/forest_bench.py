@@ -22,7 +22,10 @@ from galacticus_b200 import abi, synthetic  # noqa: E402
 from galacticus_b200.evolver import Evolver  # noqa: E402
 
 p, _, _, _ = bench.workload(8, 219)
-f = synthetic.binary_split_forest(p, n_trees, 1.52e12, 1.0e9, seed=219)
+if os.environ.get("FOREST_KIND", "mw") == "volume":  # configs[3]: mass-function-sampled roots at the quickTest resolution
+    f = synthetic.mass_function_forest(p, n_trees, 5.0e9, seed=219)
+else:
+    f = synthetic.binary_split_forest(p, n_trees, 1.52e12, 1.0e9, seed=219)
 ev = Evolver(0)
 synthetic.install(ev, p)
 warm = synthetic.binary_split_forest(p, 4, 1.52e12, 1.0e10, seed=1)

@@ -44,6 +44,9 @@ def lib() -> C.CDLL:
         L.emu_forest_evolve.argtypes = [C.c_void_p, C.c_int64, _ip, _dp, _dp, _dp, _dp, _dp, _ip, _ip,
                                         C.POINTER(abi.glc_forest_counters), C.POINTER(abi.glc_counters), C.c_int, C.c_int, C.c_int,
                                         C.c_int]
+        L.emu_forest_evolve_async.argtypes = [C.c_void_p, C.c_int64, _ip, _dp, _dp, _dp, _dp, _dp, _ip, _ip,
+                                              C.POINTER(abi.glc_forest_counters), C.POINTER(abi.glc_counters), C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_int]
         L.emu_profiler_read.argtypes = [C.c_void_p, C.POINTER(abi.glc_profile)]
         _LIB = L
     return _LIB
@@ -98,17 +101,23 @@ class EmuEvolver:
         assert self.L.emu_profiler_read(self.h, C.byref(pr)) == 0
         return abi.profile_dict(pr)
 
-    def forest_evolve(self, forest):
-        """The product's host scheduler (csrc/host/glc_forest.hpp) over the host-executed kernel source."""
+    def forest_evolve(self, forest, asynchronous=False, straggle=0):
+        """The product's host scheduler (csrc/host/glc_forest.hpp) over the host-executed kernel source: the bulk-synchronous
+        rounds, or (asynchronous) the per-group schedule with finished nodes reported up to `straggle` polls late."""
         n = forest["parent"].shape[0]
         rec = np.zeros((n, abi.NPROP))
         flags = np.zeros(n, dtype=np.int32)
         state = np.zeros(n, dtype=np.int32)
         fc, c = abi.glc_forest_counters(), abi.glc_counters()
         a = [np.ascontiguousarray(forest[k], dtype=np.float64) for k in ("mass", "time", "scale_radius", "angular_momentum")]
-        rc = self.L.emu_forest_evolve(self.h, n, np.ascontiguousarray(forest["parent"], dtype=np.int32), a[0], a[1], a[2], a[3],
-                                      rec, flags, state, C.byref(fc), C.byref(c), self.nslots, self.budget, int(self.sort),
-                                      int(self.machine))
+        if asynchronous:
+            rc = self.L.emu_forest_evolve_async(self.h, n, np.ascontiguousarray(forest["parent"], dtype=np.int32), a[0], a[1], a[2],
+                                                a[3], rec, flags, state, C.byref(fc), C.byref(c), self.nslots, self.budget,
+                                                int(self.sort), int(self.machine), int(straggle))
+        else:
+            rc = self.L.emu_forest_evolve(self.h, n, np.ascontiguousarray(forest["parent"], dtype=np.int32), a[0], a[1], a[2], a[3],
+                                          rec, flags, state, C.byref(fc), C.byref(c), self.nslots, self.budget, int(self.sort),
+                                          int(self.machine))
         assert rc == 0, rc
         return rec, flags, state, abi.counters_dict(fc), abi.counters_dict(c)
 

@@ -537,3 +537,76 @@ int emu_forest_dryrun(void *h, int64_t n_nodes, const int32_t *parent, const dou
     return rc ? rc : nb;
 }
 }  // extern "C"
+
+// The asynchronous scheduler (Forest::run_async) over the host-executed kernel source.  The engine evolves what it is given at
+// once but, to exercise the schedule independence the product relies on, reports finished nodes late and out of order: each
+// finished node is held back for a pseudo-random number of polls (`straggle` > 0) -- results must not depend on it.
+struct EmuAsyncEngine {
+    void *h;
+    glcf::Forest &F;
+    int nslots, budget, sort, machine, straggle;
+    std::vector<int32_t> q_nodes;
+    std::vector<double> q_tend;
+    struct Held { int32_t node, status, interrupt; int polls; };
+    std::vector<Held> held;
+    glc_counters total{};
+    std::mt19937 rng{20240607u};
+    int64_t inflight = 0;
+    EmuAsyncEngine(void *h_, glcf::Forest &F_, int ns, int b, int so, int m, int st) : h(h_), F(F_), nslots(ns), budget(b), sort(so), machine(m), straggle(st) {}
+    void submit(int32_t node, double tend) { q_nodes.push_back(node); q_tend.push_back(tend); inflight++; }
+    int64_t in_flight() const { return inflight; }
+    int flush() {
+        const int64_t m = (int64_t)q_nodes.size();
+        if (m == 0) return 0;
+        std::vector<double> buf((size_t)m * GLC_NPROP);
+        std::vector<int32_t> bflags(m), status(m), interrupt(m);
+        for (int64_t k = 0; k < m; k++) {
+            memcpy(&buf[(size_t)k * GLC_NPROP], F.R(q_nodes[k]), sizeof(double) * GLC_NPROP);
+            bflags[k] = F.flags[q_nodes[k]];
+        }
+        glc_counters c{};
+        int64_t slices = 0;
+        int rc = emu_evolve_batch(h, m, buf.data(), bflags.data(), q_tend.data(), status.data(), interrupt.data(), &c, nslots, budget, sort, machine, &slices);
+        if (rc) return rc;
+        for (int64_t k = 0; k < m; k++) {
+            memcpy(F.R(q_nodes[k]), &buf[(size_t)k * GLC_NPROP], sizeof(double) * GLC_NPROP);
+            F.flags[q_nodes[k]] = bflags[k];
+            held.push_back(Held{q_nodes[k], status[k], interrupt[k], straggle > 0 ? (int)(rng() % (unsigned)(straggle + 1)) : 0});
+        }
+        total.steps_accepted += c.steps_accepted; total.steps_rejected += c.steps_rejected; total.rhs_evaluations += c.rhs_evaluations;
+        total.segments += c.segments; total.trials_failed += c.trials_failed; total.nodes += c.nodes;
+        q_nodes.clear();
+        q_tend.clear();
+        return 0;
+    }
+    int poll(std::vector<int32_t> &done, std::vector<int32_t> &st, std::vector<int32_t> &in) {
+        for (;;) {
+            size_t keep = 0;
+            for (size_t k = 0; k < held.size(); k++) {
+                if (held[k].polls <= 0) {
+                    done.push_back(held[k].node); st.push_back(held[k].status); in.push_back(held[k].interrupt);
+                    inflight--;
+                } else {
+                    held[k].polls--;
+                    held[keep++] = held[k];
+                }
+            }
+            held.resize(keep);
+            if (!done.empty() || held.empty()) return 0;
+        }
+    }
+};
+
+extern "C" int emu_forest_evolve_async(void *h, int64_t n_nodes, const int32_t *parent, const double *mass, const double *time,
+                                       const double *scale_radius, const double *angular_momentum, double *records, int32_t *flags,
+                                       int32_t *state, glc_forest_counters *fc, glc_counters *counters, int nslots, int budget, int sort,
+                                       int machine, int straggle) {
+    Emu *e = (Emu *)h;
+    glcf::Forest F;
+    F.init(&e->params, &e->halo_host, n_nodes, parent, mass, time, scale_radius, angular_momentum, records, flags, state);
+    EmuAsyncEngine E(h, F, nslots, budget, sort, machine, straggle);
+    const int rc = F.run_async(E);
+    if (fc) *fc = F.fc;
+    if (counters) *counters = E.total;
+    return rc;
+}

@@ -143,3 +143,76 @@ def test_forest_evolve_cuda_matches_reference_walk(oracle_lib):
     assert np.array_equal(rg[alive], ro[alive]), "surviving node records not bit-identical"
     _check_bookkeeping(f, sg, fcg)
     ev.close()
+
+
+@pytest.mark.parametrize("straggle", [0, 3, 11])
+def test_asynchronous_schedule_matches_reference_walk(oracle_lib, straggle):
+    """Forest::run_async: every group (a host and its satellites) cycles on its own and finished nodes come back late and out
+    of order (`straggle` polls); integer bookkeeping and surviving records must still equal the reference walk's."""
+    from tests import emu
+
+    p = cases.standard_params(with_black_holes=True)
+    f = _forest(p, n_trees=7, seed=13)
+    o = oracle_lib.Oracle()
+    synthetic.install(o, p)
+    ro, fo, so, fco, co = o.forest_evolve(f, n_threads=4)
+    e = emu.EmuEvolver(64, 0, True, 2)
+    synthetic.install(e, p)
+    re, fe, se, fce, ce = e.forest_evolve(f, asynchronous=True, straggle=straggle)
+    np.testing.assert_array_equal(se, so)
+    np.testing.assert_array_equal(fe, fo)
+    for k in ("trees", "nodes", "evolve_calls", "promotions", "node_mergers", "failed_evolves"):
+        assert fce[k] == fco[k], k
+    assert ce == co
+    alive = so != PROMOTED
+    assert np.array_equal(re[alive], ro[alive]), "surviving node records not bit-identical"
+    _check_bookkeeping(f, se, fce)
+
+
+def test_asynchronous_schedule_many_progenitors(oracle_lib):
+    from tests import emu
+
+    p = cases.standard_params(with_black_holes=True)
+    f = _forest(p, n_trees=8, seed=29, resolution=1.5e10)
+    rng = np.random.default_rng(3)
+    parent = f["parent"].copy()
+    grand = np.where(parent >= 0, parent[np.maximum(parent, 0)], -1)
+    move = (grand >= 0) & (rng.random(parent.size) < 0.3)
+    parent[move] = grand[move]
+    f["parent"] = parent.astype(np.int32)
+    o = oracle_lib.Oracle()
+    synthetic.install(o, p)
+    ro, fo, so, fco, co = o.forest_evolve(f, n_threads=4)
+    e = emu.EmuEvolver(64, 0, True, 2)
+    synthetic.install(e, p)
+    re, fe, se, fce, ce = e.forest_evolve(f, asynchronous=True, straggle=5)
+    np.testing.assert_array_equal(se, so)
+    assert ce == co and {k: fce[k] for k in fce if k != "rounds"} == {k: fco[k] for k in fco if k != "rounds"}
+    alive = so != PROMOTED
+    assert np.array_equal(re[alive], ro[alive])
+
+
+@pytest.mark.gpu
+def test_forest_schedules_agree_on_gpu(oracle_lib):
+    """glc_forest_evolve under both schedules (GLC_OPT_FOREST_SCHEDULE: asynchronous groups over the streaming machine, the
+    default, and bulk-synchronous rounds) against the checker's walk: identical bookkeeping, bit-identical records."""
+    from galacticus_b200.evolver import Evolver
+
+    p = cases.standard_params(with_black_holes=True)
+    f = _forest(p, n_trees=60, seed=31, resolution=8.0e9)
+    o = oracle_lib.Oracle()
+    synthetic.install(o, p)
+    ro, fo, so, fco, co = o.forest_evolve(f, n_threads=16)
+    alive = so != PROMOTED
+    for schedule in (1, 0):
+        ev = Evolver(0)
+        synthetic.install(ev, p)
+        ev.set_option(abi.GLC_OPT_FOREST_SCHEDULE, schedule)
+        rg, fg, sg, fcg, cg = ev.forest_evolve(f)
+        ev.close()
+        np.testing.assert_array_equal(sg, so)
+        np.testing.assert_array_equal(fg, fo)
+        for k in ("trees", "nodes", "evolve_calls", "promotions", "node_mergers", "failed_evolves"):
+            assert fcg[k] == fco[k], (schedule, k)
+        assert cg == co, schedule
+        assert np.array_equal(rg[alive], ro[alive]), f"schedule {schedule}: surviving node records not bit-identical"

@@ -4,8 +4,10 @@ Round 1's unit queues could be lapped: ring cells carried a 5-bit lap tag and pr
 the position one lap back.  In batches with very fast turnover (hundreds of thousands of nodes that finish within a few
 units, as in every batch of a large forest) a consumer that was slow between reserving and reading its cell lost its
 slot (the node never finished) and, 32 laps later, took another slot's entry (the slot then ran on two lanes at once and
-its lane state was corrupted): profiles/r02a_ledger_4000_trees.txt.  These tests run such batches through the machine
-and demand the checker's results bit for bit for EVERY node."""
+its lane state was corrupted): profiles/r02a_ledger_4000_trees_round1_queues.txt.  test_forest_4000_trees is the reproducer
+(the round-1 library never finishes its third machine batch); the two batch tests put the machine in the same regime -- they
+happen to pass on the round-1 protocol too, lapping needs the timing of that forest -- and demand the checker's results bit for
+bit for EVERY node."""
 import numpy as np
 import pytest
 
