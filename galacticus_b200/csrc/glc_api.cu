@@ -78,12 +78,17 @@ struct glc_evolver {
     cudaStream_t stream2 = nullptr;
     // streaming session (glc_stream_*)
     bool stream_active = false, stream_started = false;
+    bool stream_lane_mode = false;  // streaming, adaptive ticks: every occupied slot stands at an RK boundary (lane passes)
+    int64_t stream_live = 0;        // occupied slots after the last tick
     int64_t stream_n = 0;           // tickets handed out so far = length of the node queue
     unsigned char *d_collected = nullptr;
     int64_t *d_collect_list = nullptr;
     int32_t *d_collect_meta = nullptr;   // [cap][3] flags, status, interrupt of the collected nodes
     int32_t *h_collect_meta = nullptr;   // pinned
     int64_t collect_meta_cap = 0;
+    int32_t stream_sparse_budget = 32, stream_dense_budget = 12;  // evaluations per lane in one lane pass of a streaming tick
+    int32_t l2_persist = 0;              // GLC_L2_PERSIST=1: pin the machine's RootState array in L2 (experiment)
+    bool l2_window_set = false;
     int32_t forest_schedule = 1;         // glc_forest_evolve: 1 = asynchronous groups over the streaming machine, 0 = bulk-synchronous rounds
     int64_t collected_cap = 0;
     int64_t stream_collected = 0;
@@ -499,7 +504,7 @@ static int ledger_report(glc_evolver *ev, int n, const char *tag) {
 // mode 0: one batch, fresh queue, run to completion (hybrid) or in user time slices
 // mode 1: streaming -- ONE time slice of `streamBudget` pops over the (possibly grown) node queue
 // mode 2: streaming -- continue to completion (hybrid)
-static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mode = 0, int streamBudget = 0) {
+static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mode = 0, int streamBudget = 0, int streamHold = 0) {
     constexpr size_t kMachineSmem = sizeof(unsigned int) * (size_t)U_IDLE * GLC_MSLOTS;
     GLC_CHECK(ev, cudaFuncSetAttribute(machine_kernel<GLC_MTHREADS, GLC_MSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kMachineSmem));
@@ -521,6 +526,25 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     }
     int rc = ensure_workspace(ev, (int)((need + kBlock - 1) / kBlock));
     if (rc) return rc;
+    if (ev->l2_persist && !ev->l2_window_set) {
+        // The root-find units (a quarter of the warp-state samples, 43 % of them waiting for memory) touch one 256-byte
+        // RootState per slot: 78 MB for 303 104 slots, which fits the 126 MB L2 if nothing else evicts it.  Pin it.
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, ev->device);
+        const size_t bytes = sizeof(RootState) * (size_t)ev->nslots_machine;
+        const size_t setAside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes);
+        if (setAside > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside) == cudaSuccess) {
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = ev->d_slots.root;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setAside / (double)attr.accessPolicyWindow.num_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(ev->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+        cudaGetLastError();
+        ev->l2_window_set = true;
+    }
     GLC_CHECK(ev, cudaEventRecord(ev->ev0, ev->stream));
     const int sorted = mode == 0 ? build_queue_order(ev, n) : 0;  // a growing queue is served in submission order
     if (sorted < 0) return sorted;
@@ -570,7 +594,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     const double t_start = now_s();
     int nslice = 0;
     ev->phase_split = false;
-    A.hold = 0;
+    A.hold = (mode == 1) ? streamHold : 0;
     A.held = nullptr;
     A.nheld = 0;
     A.held_counter = nullptr;
@@ -696,7 +720,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                 for (int pass = 0;; pass++) {
                     GLC_CHECK(ev, cudaMemsetAsync(d_count, 0, sizeof(int) * 4, ev->stream));
                     held_list_kernel<<<std::min((nslotsActive + 255) / 256, ev->num_sms * 8), 256, 0, ev->stream>>>(
-                        ev->d_slots.unit, ev->d_slots.L, nslotsActive, ev->d_held, pass == 0 ? ev->d_held_score : nullptr, d_count);
+                        ev->d_slots.unit, ev->d_slots.L, nslotsActive, ev->d_held, pass == 0 ? ev->d_held_score : nullptr, d_count, 0);
                     int nheld = 0;
                     GLC_CHECK(ev, cudaMemcpyAsync(&nheld, d_count, sizeof(int), cudaMemcpyDeviceToHost, ev->stream));
                     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
@@ -825,6 +849,111 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     return 0;
 }
 
+// ---------------------------------------------------------------------------- streaming: adaptive time slices
+// glc_stream_run(pops_per_warp = 0).  The machine is a throughput engine: a slot advances at (block throughput) / (slots in
+// flight), and a lone slot at ~1 ms per evaluation (every unit is a cold piece of code plus a queue round trip).  A streaming
+// host (the asynchronous tree scheduler) mostly has few nodes in flight and waits for the slowest of them, so a tick is
+//   * a machine slice while the node queue plus the occupied slots would fill the machine (>= drain_threshold), else
+//   * a LANE PASS: every occupied slot is brought to an RK boundary once (hold slices), then drain_kernel -- whole
+//     evaluations, one node per lane, or one per WARP when there are fewer nodes than resident warps -- runs all of them for a
+//     bounded number of evaluations, fetching queued nodes into free slots as it goes (drainRefill), and parks what is left.
+// Both engines work on the same slots; a node's result does not depend on which engine advances it.
+static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
+    const int64_t need = (int64_t)ev->num_sms * GLC_MSLOTS;
+    if (need > ev->nslots_machine || !ev->stream_started) {
+        // first tick of a session: a one-pop machine slice allocates the slot arrays (first use) and resets every slot, the
+        // queue cursor and the counters
+        int rc = launch_machine(ev, n, hc, 1, 1, 0);
+        if (rc) return rc;
+        ev->stream_lane_mode = false;
+        ev->stream_live = (int64_t)hc[7];
+    }
+    int work = 0;
+    GLC_CHECK(ev, cudaMemcpyAsync(&work, ev->d_work, sizeof(int), cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    const int64_t queued = std::max<int64_t>(0, (int64_t)n - (int64_t)std::min(work, n));
+    const int64_t big = ev->drain_threshold;
+    if (!ev->stream_lane_mode) {
+        if (queued + ev->stream_live >= big) {
+            int rc = launch_machine(ev, n, hc, 1, 4096, 0);
+            ev->stream_live = (int64_t)hc[7];
+            return rc;
+        }
+        // few nodes: bring every occupied slot to an RK boundary (slots mid-evaluation finish their evaluation)
+        for (int k = 0; k < 64; k++) {
+            int rc = launch_machine(ev, n, hc, 1, 512, 1);
+            if (rc) return rc;
+            if (hc[8] == 0) break;
+        }
+        ev->stream_live = (int64_t)hc[7];
+        ev->stream_lane_mode = true;
+    } else if (queued >= big) {
+        ev->stream_lane_mode = false;  // a large submission: back to the machine (parked slots are re-queued by their unit words)
+        int rc = launch_machine(ev, n, hc, 1, 4096, 0);
+        ev->stream_live = (int64_t)hc[7];
+        return rc;
+    }
+    // ---- lane pass
+    if (!ev->d_held || ev->held_cap < ev->nslots_machine) {
+        cudaFree(ev->d_held);
+        ev->d_held = nullptr;
+        GLC_CHECK(ev, cudaMalloc(&ev->d_held, sizeof(int32_t) * (ev->nslots_machine + 8)));
+        cudaFree(ev->d_held_score);
+        ev->d_held_score = nullptr;
+        GLC_CHECK(ev, cudaMalloc(&ev->d_held_score, sizeof(float) * ev->nslots_machine));
+        ev->held_cap = ev->nslots_machine;
+    }
+    int *d_count = reinterpret_cast<int *>(ev->d_held + ev->nslots_machine);  // [0] list length, [1] cursor, [3] free slots seen
+    int bps = 0;
+    GLC_CHECK(ev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, drain_kernel<ModelStandard>, kBlock, 0));
+    if (bps < 1) bps = 1;
+    const int nslotsAll = (int)ev->nslots_machine;
+    const int warpsResident = ev->num_sms * bps * (kBlock / 32);
+    GLC_CHECK(ev, cudaMemsetAsync(d_count, 0, sizeof(int) * 4, ev->stream));
+    held_list_kernel<<<std::min((nslotsAll + 255) / 256, ev->num_sms * 8), 256, 0, ev->stream>>>(
+        ev->d_slots.unit, ev->d_slots.L, nslotsAll, ev->d_held, nullptr, d_count, (int)std::min<int64_t>(queued, nslotsAll));
+    int nlist = 0;
+    GLC_CHECK(ev, cudaMemcpyAsync(&nlist, d_count, sizeof(int), cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    ev->launches++;
+    if (nlist > 0) {
+        KernelArgs A{};
+        A.props = ev->d_props;
+        A.flags = ev->d_flags;
+        A.time_end = ev->d_time_end;
+        A.status = ev->d_status;
+        A.interrupt = ev->d_interrupt;
+        A.cap = ev->cap;
+        A.n = n;
+        A.ws = ev->d_ws;
+        A.nslots = ev->nslots;
+        A.work_counter = ev->d_work;
+        A.counters = ev->d_counters;
+        A.order = nullptr;
+        A.resume = 1;
+        A.slotL = ev->d_slots.L;
+        A.slotYt = ev->d_slots.yt;
+        A.slotUnit = ev->d_slots.unit;
+        A.held = ev->d_held;
+        A.nheld = nlist;
+        A.held_counter = d_count + 1;
+        A.drainRefill = 1;
+        const bool sparse = nlist <= warpsResident;
+        A.drainSparse = sparse ? 1 : 0;
+        A.budget = sparse ? ev->stream_sparse_budget : ev->stream_dense_budget;
+        int dgrid = sparse ? (nlist + kBlock / 32 - 1) / (kBlock / 32) : (nlist + kBlock - 1) / kBlock;
+        dgrid = std::max(1, std::min(ev->num_sms * bps, dgrid));
+        drain_kernel<ModelStandard><<<dgrid, kBlock, 0, ev->stream>>>(A);
+        ev->launches++;
+        ev->slices++;
+        GLC_CHECK(ev, cudaGetLastError());
+    }
+    GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 11, cudaMemcpyDeviceToHost, ev->stream));
+    GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+    ev->stream_live = nlist;  // upper bound until the next listing
+    return 0;
+}
+
 static int upload_constants(glc_evolver *ev) {
     GLC_CHECK(ev, cudaMemcpyToSymbolAsync(c_params, &ev->params, sizeof(glc_params), 0,
                                           cudaMemcpyHostToDevice, ev->stream));
@@ -865,6 +994,9 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_DRAIN_BELOW")) ev->drain_threshold = atoll(e);
     if (const char *e = getenv("GLC_DRAIN_DENSE_BUDGET")) ev->drain_dense_budget = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_EXPRESS")) ev->drain_express = atoi(e);
+    if (const char *e = getenv("GLC_L2_PERSIST")) ev->l2_persist = atoi(e);
+    if (const char *e = getenv("GLC_STREAM_SPARSE_BUDGET")) ev->stream_sparse_budget = atoi(e);
+    if (const char *e = getenv("GLC_STREAM_DENSE_BUDGET")) ev->stream_dense_budget = atoi(e);
     cudaStreamCreateWithFlags(&ev->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ev->stream2, cudaStreamNonBlocking);
     cudaEventCreate(&ev->ev0);
@@ -1047,6 +1179,10 @@ int glc_arena_reserve(glc_evolver *ev, int64_t capacity) {
 int glc_arena_upload(glc_evolver *ev, int64_t n, const double *props, const int32_t *flags,
                      const double *time_end) {
     if (!ev || n < 0 || !props || !flags || !time_end) return -1;
+    if (ev->stream_active) {
+        ev->err = "arena upload during a streaming session (the session owns the arena): call glc_stream_end first";
+        return GLC_ERR_BUSY;
+    }
     if (n == 0) return 0;
     cudaSetDevice(ev->device);
     int rc = glc_arena_reserve(ev, n);
@@ -1080,6 +1216,14 @@ int glc_arena_download(glc_evolver *ev, int64_t n, double *props, int32_t *flags
 
 int glc_evolve_arena(glc_evolver *ev, int64_t n, glc_counters *counters) {
     if (!ev || n < 0 || n > ev->cap) return -1;
+    if (n > 0x7fffffff) {
+        ev->err = "more than 2^31-1 nodes in one batch";
+        return -1;
+    }
+    if (ev->stream_active) {
+        ev->err = "batch call during a streaming session (the session owns the arena): call glc_stream_end first";
+        return GLC_ERR_BUSY;
+    }
     if (!ev->params_set) {
         ev->err = "glc_evolver_set_params has not been called";
         return -9;
@@ -1273,6 +1417,8 @@ int glc_stream_begin(glc_evolver *ev, int64_t capacity) {
     if (rc) return rc;
     ev->stream_active = true;
     ev->stream_started = false;
+    ev->stream_lane_mode = false;
+    ev->stream_live = 0;
     ev->stream_n = 0;
     ev->stream_collected = 0;
     return 0;
@@ -1305,8 +1451,13 @@ int glc_stream_run(glc_evolver *ev, int32_t pops_per_warp, int64_t *n_finished_t
     cudaSetDevice(ev->device);
     unsigned long long hc[16] = {0};
     if (ev->stream_n > 0) {
-        int rc = launch_machine(ev, (int)ev->stream_n, hc, 1, pops_per_warp);
+        // pops_per_warp > 0: one machine slice of that budget; 0: an adaptive tick (machine slice or lane pass, stream_tick)
+        int rc = pops_per_warp > 0 ? launch_machine(ev, (int)ev->stream_n, hc, 1, pops_per_warp) : stream_tick(ev, (int)ev->stream_n, hc);
         if (rc) return rc;
+        if (pops_per_warp > 0) {
+            ev->stream_lane_mode = false;
+            ev->stream_live = (int64_t)hc[7];
+        }
     }
     if (n_finished_total) *n_finished_total = (int64_t)hc[6];
     if (counters) {
@@ -1709,11 +1860,9 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
                         return GLC_ERR_STALLED;
                     }
                     // one time slice; shorter slices when few nodes are in flight, so that finished nodes are seen early
-                    const int64_t live = submitted - collected;
-                    const int budget = live > 200000 ? 4096 : (live > 20000 ? 1024 : 256);
                     int64_t nfin = 0;
                     double t = now_s();
-                    int rc = glc_stream_run(ev, budget, &nfin, &session);
+                    int rc = glc_stream_run(ev, 0, &nfin, &session);  // adaptive tick: machine slice or lane pass
                     if (rc) return rc;
                     t_run += now_s() - t;
                     t = now_s();

@@ -189,6 +189,9 @@ struct KernelArgs {
     double *slotYt;                // [nslots][NY]
     int *slotUnit;                 // drain: pending-unit words (a finished slot is marked -1)
     int drainSparse;               // drain: 1 = one node per warp (lane 0 only): the last nodes run at lone-lane speed
+    int drainRefill;               // drain, streaming sessions: a lane whose node is done fetches the next one from the node
+                                   // queue into the same slot (list entries with kHeldFresh set are free slots that start
+                                   // with a fetch)
     // GLC_LEDGER builds (debug): node-ownership ledger and per-slot execution flags, see glc_machine.cuh
     int *ledger;                   // [n] -1 = never fetched, s+1 = held by slot s, -2 = written back
     int *slotBusy;                 // [nslots] 1 while a lane executes a unit of the slot
@@ -210,6 +213,11 @@ struct NodeCtx {
     double massBaryonicSubhalos;  // frozen input, see GLC_P_MASS_BARYONIC_SUBHALOS
     int numericsFailed;           // a nested solver (Brent/QAG) failed where the reference would abort
 };
+
+// drain hand-over list: bit 30 of an entry marks a FREE slot handed to the drain kernel to fetch queued nodes into
+constexpr int32_t kHeldFresh = 1 << 30;
+// pending-unit word of a slot parked at an RK boundary (== U_RHS_BEGIN of glc_machine.cuh, checked there)
+constexpr int kUnitRhsBegin = 1;
 
 // single translation unit (glc_api.cu): defined here
 __constant__ glc_params c_params;

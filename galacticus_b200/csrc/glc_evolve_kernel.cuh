@@ -621,21 +621,36 @@ GLC_DEVICE_INLINE bool drain_iterate(LaneState &L, LaneMem &M, const KernelArgs 
                 slotHeld = -2;  // list exhausted
                 break;
             }
-            const int s = A.held[h];
+            const int entry = A.held[h];
+            const int s = entry & ~kHeldFresh;
+            M.ws = A.ws + (int64_t)s * (WS_NVEC * NY);
+            M.wstride = 1;
+            M.dbgSlot = s;
+            if (entry & kHeldFresh) {  // a free slot: start with a fetch from the node queue (streaming sessions)
+                slotHeld = s;
+                lane_reset(L);
+                fresh = false;
+                break;
+            }
             if (A.slotUnit && A.slotUnit[s] < 0) continue;  // finished in an earlier pass over the same list
             slotHeld = s;
             L = A.slotL[slotHeld];
             GLC_UNROLL_RK
             for (int i = 0; i < NY; i++) yt[i] = A.slotYt[(int64_t)slotHeld * NY + i];
-            M.ws = A.ws + (int64_t)slotHeld * (WS_NVEC * NY);
-            M.wstride = 1;
-            M.dbgSlot = slotHeld;
             fresh = true;
             break;
         }
     }
-    const bool have = slotHeld >= 0;
-    if (have && !fresh) lane_prepare<Model>(L, M, yt);
+    bool have = slotHeld >= 0;
+    if (have && !fresh) {
+        lane_prepare<Model>(L, M, yt);
+        if (L.heavy == HV_NONE) {  // the fetch found the node queue empty: release the slot
+            drain_tally(L, tot);
+            if (A.slotUnit) A.slotUnit[slotHeld] = -1;
+            slotHeld = -1;
+            have = false;
+        }
+    }
     fresh = false;
     GLC_UNROLL_RK
     for (int i = 0; i < NY; i++) rate[i] = 0.0;
@@ -644,11 +659,12 @@ GLC_DEVICE_INLINE bool drain_iterate(LaneState &L, LaneMem &M, const KernelArgs 
     const int code = Model::rates(L.ctx, L.ts, yt, rate, L.heavy == HV_POST_EVOLVE, on);
     if (have) {
         lane_consume<Model>(L, M, yt, rate, code);
-        if (L.phase == PH_FETCH) {  // node written back; the node queue is empty in the drain: release the slot
+        if (L.phase == PH_FETCH && !A.drainRefill) {  // node written back; no refill in the drain of a batch: release the slot
             drain_tally(L, tot);
             if (A.slotUnit) A.slotUnit[slotHeld] = -1;
             slotHeld = -1;
         }
+        // (with refill the next lane_prepare fetches the next queued node into this slot, or releases it above)
     }
     return slotHeld >= 0 || (slotHeld == -1 && mayTake);
 }
@@ -677,6 +693,7 @@ GLC_DEVICE_INLINE void drain_park(LaneState &L, LaneMem &M, const KernelArgs &A,
     A.slotL[slotHeld] = L;
     GLC_UNROLL_RK
     for (int i = 0; i < NY; i++) A.slotYt[(int64_t)slotHeld * NY + i] = yt[i];
+    if (A.slotUnit) A.slotUnit[slotHeld] = kUnitRhsBegin;  // (a free slot that fetched a node is now an occupied one)
 }
 
 #if defined(__CUDACC__)

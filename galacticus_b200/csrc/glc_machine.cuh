@@ -45,6 +45,8 @@ enum Unit : int {
     U_COUNT
 };
 
+static_assert(U_RHS_BEGIN == kUnitRhsBegin, "kUnitRhsBegin (glc_common.cuh) must equal U_RHS_BEGIN");
+
 typedef ModelStandard MS;
 
 struct RhsState {
@@ -739,18 +741,27 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
 }
 
 // compacts the ids of the slots held at an RK boundary into a list for drain_kernel; score = predicted number of
-// remaining steps of the node, (t_end - t) / h with the controller's current step size
+// remaining steps of the node, (t_end - t) / h with the controller's current step size.  Streaming sessions also list up to
+// `wantFree` free slots (entries tagged kHeldFresh, counted in count[3]) into which the drain kernel fetches queued nodes.
 __global__ void held_list_kernel(const int *__restrict__ unit, const LaneState *__restrict__ L, int nslots, int32_t *held,
-                                 float *score, int *count) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += gridDim.x * blockDim.x)
-        if (unit[i] == U_RHS_BEGIN) {
+                                 float *score, int *count, int wantFree) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += gridDim.x * blockDim.x) {
+        const int u = unit[i];
+        if (u == U_RHS_BEGIN) {
             const int k = atomicAdd(count, 1);
             held[k] = i;
             if (score) {
                 const double h = L[i].h, left = L[i].x1 - L[i].x;
                 score[k] = (L[i].heavy == HV_RHS && h > 0.0 && left > 0.0) ? (float)fmin(left / h, 1.0e30) : 0.0f;
             }
+        } else if (wantFree > 0 && (u == U_IDLE || u < 0)) {
+            if (atomicAdd(count + 3, 1) < wantFree) {
+                const int k = atomicAdd(count, 1);
+                held[k] = i | kHeldFresh;
+                if (score) score[k] = 0.0f;
+            }
         }
+    }
 }
 #endif
 
