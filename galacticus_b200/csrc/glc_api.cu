@@ -75,6 +75,8 @@ struct glc_evolver {
     float *d_held_score = nullptr;
     int64_t held_cap = 0;
     int32_t drain_express = 1;      // first drain pass: predicted-longest nodes one per warp on stream2
+    int32_t drain_spread = 1;       // drain / lane passes: spread the nodes over all resident warps (KernelArgs::drainLanes); 0 = one per
+                                    // warp when they fit, else 32 per warp (round-2 behaviour before the measurement in profiles/r02k)
     cudaStream_t stream2 = nullptr;
     // streaming session (glc_stream_*)
     bool stream_active = false, stream_started = false;
@@ -87,6 +89,10 @@ struct glc_evolver {
     int32_t *h_collect_meta = nullptr;   // pinned
     int64_t collect_meta_cap = 0;
     int32_t stream_sparse_budget = 32, stream_dense_budget = 12;  // evaluations per lane in one lane pass of a streaming tick
+    int64_t stream_machine_above = -1;   // adaptive ticks: machine slice when queued + occupied >= this (default: drain_threshold)
+    // tick statistics of the session (forest log): machine slices / lane passes, their device-side wall time, nodes in flight
+    int64_t tick_machine = 0, tick_lane = 0, tick_hold = 0;
+    double tick_machine_s = 0.0, tick_lane_s = 0.0, tick_live_sum = 0.0, tick_lanes_sum = 0.0;
     int32_t l2_persist = 0;              // GLC_L2_PERSIST=1: pin the machine's RootState array in L2 (experiment)
     bool l2_window_set = false;
     int32_t forest_schedule = 1;         // glc_forest_evolve: 1 = asynchronous groups over the streaming machine, 0 = bulk-synchronous rounds
@@ -505,7 +511,14 @@ static int ledger_report(glc_evolver *ev, int n, const char *tag) {
 // mode 1: streaming -- ONE time slice of `streamBudget` pops over the (possibly grown) node queue
 // mode 2: streaming -- continue to completion (hybrid)
 static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mode = 0, int streamBudget = 0, int streamHold = 0) {
-    constexpr size_t kMachineSmem = sizeof(unsigned int) * (size_t)U_IDLE * GLC_MSLOTS;
+    size_t kMachineSmem = sizeof(unsigned int) * (size_t)U_IDLE * GLC_MSLOTS;
+#if GLC_MACHINE_STAGED_POW
+    kMachineSmem += sizeof(double) * (size_t)ev->tables.powAcN;  // the x^omega table staged behind the queues
+    if (kMachineSmem > 227u * 1024u) {
+        ev->err = "micro-task machine: unit queues + staged exponentiation table exceed 227 KB of shared memory";
+        return -9;
+    }
+#endif
     GLC_CHECK(ev, cudaFuncSetAttribute(machine_kernel<GLC_MTHREADS, GLC_MSLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kMachineSmem));
     const int gridMax = ev->num_sms;  // one block per SM
@@ -601,7 +614,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     A.slotL = nullptr;
     A.slotYt = nullptr;
     A.slotUnit = nullptr;
-    A.drainSparse = 0;
+    A.drainLanes = 0;
     // Run-to-completion mode (no user time slices) is a hybrid: the machine works in internal slices while the node
     // queue still refills its slots and for as long as enough slots stay in flight to fill warps; then the slots
     // are brought to an RK boundary (hold slices) and handed to drain_kernel, which finishes their nodes with
@@ -630,7 +643,12 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
 #endif
             return GLC_ERR_STALLED;
         }
-        if (mode == 1) break;  // streaming: exactly one slice per call
+        if (mode == 1) {  // streaming: exactly one slice per call
+            if (ev->slice_log)
+                fprintf(stderr, "[glc stream slice] budget=%d hold=%d n=%d done=%llu fetched=%llu rhs=%llu parked=%llu mid-evaluation=%llu units=%llu\n",
+                        A.budget, A.hold, n, hc[6], hc[5], hc[2], hc[7], hc[8], hc[9]);
+            break;
+        }
         if (mode == 0 && ev->params.wallClockMaximumSeconds > 0.0 && now_s() - t_start > ev->params.wallClockMaximumSeconds &&
             hc[6] < (unsigned long long)n) {
             mark_xcpu_kernel<<<(n + 255) / 256, 256, 0, ev->stream>>>(ev->d_status, ev->d_interrupt, n);
@@ -747,14 +765,14 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                         X.held = ev->d_held;
                         X.nheld = express;
                         X.held_counter = d_count + 1;
-                        X.drainSparse = 1;
+                        X.drainLanes = 1;
                         X.budget = 0x7fffffff;
                         drain_kernel<ModelStandard><<<ev->num_sms, kBlock, 0, ev->stream2>>>(X);
                         KernelArgs D = A;  // dense: the rest, bounded passes until fewer nodes than warps are left
                         D.held = ev->d_held + express;
                         D.nheld = nheld - express;
                         D.held_counter = d_count + 2;
-                        D.drainSparse = 0;
+                        D.drainLanes = 0;
                         D.budget = ev->drain_dense_budget;
                         drain_kernel<ModelStandard><<<ev->num_sms, kBlock, 0, ev->stream>>>(D);
                         ev->launches += 3;
@@ -783,13 +801,17 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                                     1e3 * (now_s() - t_start), hc[6], n, hc[2]);
                         continue;
                     }
-                    const bool sparse = nheld <= warpsResident;
+                    // the nodes of a pass are spread over all resident warps (KernelArgs::drainLanes)
+                    const int lanes = ev->drain_spread ? std::min(32, (nheld + warpsResident - 1) / warpsResident)
+                                                       : (nheld <= warpsResident ? 1 : 32);
+                    const bool sparse = lanes == 1;
                     A.held = ev->d_held;
                     A.nheld = nheld;
                     A.held_counter = d_count + 1;
-                    A.drainSparse = sparse ? 1 : 0;
+                    A.drainLanes = lanes >= 32 ? 0 : lanes;
                     A.budget = sparse ? 0x7fffffff : ev->drain_dense_budget;
-                    int dgrid = sparse ? (nheld + kBlock / 32 - 1) / (kBlock / 32) : (nheld + kBlock - 1) / kBlock;
+                    const int perBlock = lanes * (kBlock / 32);
+                    int dgrid = (nheld + perBlock - 1) / perBlock;
                     dgrid = std::max(1, std::min(ev->num_sms * bps, dgrid));
                     drain_kernel<ModelStandard><<<dgrid, kBlock, 0, ev->stream>>>(A);
                     ev->launches += 2;
@@ -798,8 +820,8 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                                                   ev->stream));
                     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
                     if (ev->slice_log)
-                        fprintf(stderr, "[glc drain pass %d%s] t=%.3f ms held=%d done=%llu/%d rhs=%llu\n", pass,
-                                sparse ? " sparse" : "", 1e3 * (now_s() - t_start), nheld, hc[6], n, hc[2]);
+                        fprintf(stderr, "[glc drain pass %d, %d node(s) per warp] t=%.3f ms held=%d done=%llu/%d rhs=%llu\n", pass,
+                                lanes, 1e3 * (now_s() - t_start), nheld, hc[6], n, hc[2]);
                 }
                 break;
             }
@@ -872,25 +894,32 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
     GLC_CHECK(ev, cudaMemcpyAsync(&work, ev->d_work, sizeof(int), cudaMemcpyDeviceToHost, ev->stream));
     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
     const int64_t queued = std::max<int64_t>(0, (int64_t)n - (int64_t)std::min(work, n));
-    const int64_t big = ev->drain_threshold;
+    const int64_t big = ev->stream_machine_above >= 0 ? ev->stream_machine_above : ev->drain_threshold;
+    const double t_tick = now_s();
+    ev->tick_live_sum += (double)(queued + ev->stream_live);
     if (!ev->stream_lane_mode) {
         if (queued + ev->stream_live >= big) {
             int rc = launch_machine(ev, n, hc, 1, 4096, 0);
             ev->stream_live = (int64_t)hc[7];
+            ev->tick_machine++;
+            ev->tick_machine_s += now_s() - t_tick;
             return rc;
         }
         // few nodes: bring every occupied slot to an RK boundary (slots mid-evaluation finish their evaluation)
         for (int k = 0; k < 64; k++) {
             int rc = launch_machine(ev, n, hc, 1, 512, 1);
+            ev->tick_hold++;
             if (rc) return rc;
             if (hc[8] == 0) break;
         }
         ev->stream_live = (int64_t)hc[7];
         ev->stream_lane_mode = true;
-    } else if (queued >= big) {
-        ev->stream_lane_mode = false;  // a large submission: back to the machine (parked slots are re-queued by their unit words)
+    } else if (queued + ev->stream_live >= big) {
+        ev->stream_lane_mode = false;  // many nodes again: back to the machine (parked slots are re-queued by their unit words)
         int rc = launch_machine(ev, n, hc, 1, 4096, 0);
         ev->stream_live = (int64_t)hc[7];
+        ev->tick_machine++;
+        ev->tick_machine_s += now_s() - t_tick;
         return rc;
     }
     // ---- lane pass
@@ -938,11 +967,15 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
         A.nheld = nlist;
         A.held_counter = d_count + 1;
         A.drainRefill = 1;
-        const bool sparse = nlist <= warpsResident;
-        A.drainSparse = sparse ? 1 : 0;
-        A.budget = sparse ? ev->stream_sparse_budget : ev->stream_dense_budget;
-        int dgrid = sparse ? (nlist + kBlock / 32 - 1) / (kBlock / 32) : (nlist + kBlock - 1) / kBlock;
+        // spread over all resident warps: a node advances faster the fewer nodes share its warp; the evaluation budget of
+        // the pass shrinks with the number of nodes per warp so that a tick stays a few milliseconds long
+        const int lanes = ev->drain_spread ? std::min(32, (nlist + warpsResident - 1) / warpsResident) : (nlist <= warpsResident ? 1 : 32);
+        A.drainLanes = lanes >= 32 ? 0 : lanes;
+        A.budget = ev->stream_sparse_budget - (int)((long long)(ev->stream_sparse_budget - ev->stream_dense_budget) * (lanes - 1) / 31);
+        const int perBlock = lanes * (kBlock / 32);
+        int dgrid = (nlist + perBlock - 1) / perBlock;
         dgrid = std::max(1, std::min(ev->num_sms * bps, dgrid));
+        ev->tick_lanes_sum += lanes;
         drain_kernel<ModelStandard><<<dgrid, kBlock, 0, ev->stream>>>(A);
         ev->launches++;
         ev->slices++;
@@ -951,6 +984,11 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
     GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 11, cudaMemcpyDeviceToHost, ev->stream));
     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
     ev->stream_live = nlist;  // upper bound until the next listing
+    ev->tick_lane++;
+    ev->tick_lane_s += now_s() - t_tick;
+    if (ev->slice_log)
+        fprintf(stderr, "[glc stream tick: lane pass] n=%d queued=%lld listed=%d fetched=%llu done=%llu rhs=%llu\n", n, (long long)queued,
+                nlist, hc[5], hc[6], hc[2]);
     return 0;
 }
 
@@ -994,9 +1032,11 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_DRAIN_BELOW")) ev->drain_threshold = atoll(e);
     if (const char *e = getenv("GLC_DRAIN_DENSE_BUDGET")) ev->drain_dense_budget = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_EXPRESS")) ev->drain_express = atoi(e);
+    if (const char *e = getenv("GLC_DRAIN_SPREAD")) ev->drain_spread = atoi(e);
     if (const char *e = getenv("GLC_L2_PERSIST")) ev->l2_persist = atoi(e);
     if (const char *e = getenv("GLC_STREAM_SPARSE_BUDGET")) ev->stream_sparse_budget = atoi(e);
     if (const char *e = getenv("GLC_STREAM_DENSE_BUDGET")) ev->stream_dense_budget = atoi(e);
+    if (const char *e = getenv("GLC_STREAM_MACHINE_ABOVE")) ev->stream_machine_above = atoll(e);
     cudaStreamCreateWithFlags(&ev->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ev->stream2, cudaStreamNonBlocking);
     cudaEventCreate(&ev->ev0);
@@ -1876,9 +1916,15 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
             }
             int end() {
                 add_session();
-                if (log)
+                if (log) {
                     fprintf(stderr, "[glc forest async] %lld polls, %.2f s in device slices, %.2f s collecting, %.2f s submitting, %.2f s total\n",
                             (long long)polls, t_run, t_collect, t_submit, now_s() - t0);
+                    const int64_t ticks = ev->tick_machine + ev->tick_lane;
+                    fprintf(stderr, "[glc forest async] ticks: %lld machine slices (%.2f s), %lld lane passes (%.2f s, mean %.1f nodes per warp), %lld hold slices; mean nodes queued or in flight per tick %.0f\n",
+                            (long long)ev->tick_machine, ev->tick_machine_s, (long long)ev->tick_lane, ev->tick_lane_s,
+                            ev->tick_lane ? ev->tick_lanes_sum / (double)ev->tick_lane : 0.0, (long long)ev->tick_hold,
+                            ticks ? ev->tick_live_sum / (double)ticks : 0.0);
+                }
                 return glc_stream_end(ev);
             }
         };

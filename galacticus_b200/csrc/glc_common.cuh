@@ -188,7 +188,10 @@ struct KernelArgs {
     struct LaneState *slotL;       // drain: the machine's per-slot lane states and stage inputs
     double *slotYt;                // [nslots][NY]
     int *slotUnit;                 // drain: pending-unit words (a finished slot is marked -1)
-    int drainSparse;               // drain: 1 = one node per warp (lane 0 only): the last nodes run at lone-lane speed
+    int drainLanes;                // drain: lanes per warp that take nodes (0 or >= 32: all of them).  A warp serialises the divergent
+                                   // evaluations of its lanes, so a node advances fastest alone in its warp (1: lone-lane speed, ~0.2 ms
+                                   // per evaluation against ~0.7 ms with 32 nodes per warp); the host spreads the nodes of a pass
+                                   // over all resident warps: lanes = ceil(nodes / resident warps)
     int drainRefill;               // drain, streaming sessions: a lane whose node is done fetches the next one from the node
                                    // queue into the same slot (list entries with kHeldFresh set are free slots that start
                                    // with a fetch)

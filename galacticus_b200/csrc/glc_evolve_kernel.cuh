@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(GLC_BLOCK, GLC_MIN_BLOCKS) drain_kernel(Kernel
     bool fresh = false;
     int slotHeld = -1;
     unsigned int tot[7] = {0, 0, 0, 0, 0, 0, 0};
-    const bool mayTake = !A.drainSparse || (threadIdx.x & 31) == 0;
+    const bool mayTake = A.drainLanes <= 0 || (int)(threadIdx.x & 31) < A.drainLanes;
     for (int it = 0; it < A.budget; ++it) {
         const bool active = drain_iterate<Model>(L, M, A, yt, fresh, slotHeld, tot, mayTake);
         if (!__any_sync(0xffffffffu, active)) break;

@@ -49,6 +49,27 @@ static_assert(U_RHS_BEGIN == kUnitRhsBegin, "kUnitRhsBegin (glc_common.cuh) must
 
 typedef ModelStandard MS;
 
+#ifndef GLC_ROOT_STEPS
+#define GLC_ROOT_STEPS 1
+#endif
+
+// The x^omega table of the adiabatic-contraction function (fastExponentiator, 9 991 doubles = 80 KB) is looked up once per
+// Brent step of the most frequent unit.  Through the read-only global path those look-ups were 11 % of the long-scoreboard
+// samples of a bulk slice (profiles/r02i: the continuation records stream through L1 and evict the table, so most look-ups
+// go to L2).  machine_kernel therefore stages the table in shared memory behind its unit queues (104 KB + 80 KB of 227 KB).
+#if defined(__CUDACC__)
+extern __shared__ unsigned int s_qdyn[];  // machine_kernel's dynamic shared memory: [U_IDLE][SLOTS] ring cells, then the table
+#endif
+#if defined(__CUDACC__) && !defined(GLC_NO_STAGED_POW)
+#define GLC_MACHINE_STAGED_POW 1
+GLC_DEVICE_INLINE const double *machine_pow_ac() {
+    return reinterpret_cast<const double *>(s_qdyn + (size_t)U_IDLE * GLC_MSLOTS);  // (13 x 2048 x 4 bytes: 8-byte aligned)
+}
+#else
+#define GLC_MACHINE_STAGED_POW 0
+GLC_DEVICE_INLINE const double *machine_pow_ac() { return GLC_TABLES.powAc; }
+#endif
+
 struct RhsState {
     Work w;
     double hist[4], fit;
@@ -226,10 +247,18 @@ GLC_DEVICE_INLINE void m_sfr_after_trunc(const SlotRef &S, double rTrunc, int st
 }
 
 // ---------------------------------------------------------------- the units
+// Every unit returns the slot's NEXT unit.  Inside a unit the pending-unit word is a local (GLC_UNIT_ENTER rebinds the slot
+// view to it), so the transitions above never touch the word in HBM: the kernel read it back right after the unit had stored
+// it, and that load-after-store was the largest single memory stall of a bulk slice (8 % of the long-scoreboard samples,
+// profiles/r02i).  The caller stores the returned value.
+#define GLC_UNIT_ENTER(S0, SELF) \
+    int unit__ = (SELF);         \
+    const SlotRef S { (S0).L, (S0).R, (S0).B, (S0).p, (S0).yt, (S0).Q, unit__ }
 // U_RK: rates_accumulate of the evaluation whose nested solvers have just finished, lane_consume (store the
 // stage derivative; at the end of an attempt: controller, accept/reject, post-step), lane_prepare (next stage
 // input, or epilogue/fetch/prologue).
-GLC_DEVICE_NOINLINE void unit_rk(const SlotRef S, const LaneMem M) {
+GLC_DEVICE_NOINLINE int unit_rk(const SlotRef S0, const LaneMem M) {
+    GLC_UNIT_ENTER(S0, U_RK);
     LaneState L = S.L;
     double yt[NY], rate[NY];
     int code = GLC_INT_NONE;
@@ -254,14 +283,16 @@ GLC_DEVICE_NOINLINE void unit_rk(const SlotRef S, const LaneMem M) {
     S.L = L;
     if (L.heavy == HV_NONE) {
         S.unit = U_IDLE;
-        return;
+        return unit__;
     }
 #pragma unroll 1
     for (int i = 0; i < NY; i++) S.yt[i] = yt[i];
     S.unit = U_RHS_BEGIN;
+    return unit__;
 }
 
-GLC_DEVICE_NOINLINE void unit_rhs_begin(const SlotRef S) {
+GLC_DEVICE_NOINLINE int unit_rhs_begin(const SlotRef S0) {
+    GLC_UNIT_ENTER(S0, U_RHS_BEGIN);
     RhsState &R = S.R;
     NodeCtx &c = S.L.ctx;
     Work w;
@@ -278,17 +309,19 @@ GLC_DEVICE_NOINLINE void unit_rhs_begin(const SlotRef S) {
     R.w = w;
     if (!w.plausible) {
         m_after_struct(S);
-        return;
+        return unit__;
     }
     R.count = 1;
     GLC_COUNT(1);
     R.active = 0;
     R.comp = 0;
     m_struct_next(S);
+    return unit__;
 }
 
 // one (iteration, component) visit of the structure solver, up to the point where a root is needed
-GLC_DEVICE_NOINLINE void unit_struct(const SlotRef S) {
+GLC_DEVICE_NOINLINE int unit_struct(const SlotRef S0) {
+    GLC_UNIT_ENTER(S0, U_STRUCT);
     RhsState &R = S.R;
     NodeCtx &c = S.L.ctx;
     const int comp = R.comp;
@@ -301,12 +334,12 @@ GLC_DEVICE_NOINLINE void unit_struct(const SlotRef S) {
         MS::structure_store(c, comp, radius, velocity);
         R.comp++;
         m_struct_next(S);
-        return;
+        return unit__;
     }
     if (j <= 0.0) {
         R.comp++;
         m_struct_next(S);
-        return;
+        return unit__;
     }
     radius = comp == 0 ? c.diskRadius : c.sphRadius;
     R.radius = radius;
@@ -314,7 +347,8 @@ GLC_DEVICE_NOINLINE void unit_struct(const SlotRef S) {
     P.fd = P.fi = P.bterm = 0.0;
     P.rup = P.rInit = radius;
     P.need = 0;
-    if (GLC_PARAMS.adiabaticContraction && !(radius <= 0.0)) MS::ac_setup(c, S.yt, R.w, radius, P);
+    if (GLC_PARAMS.adiabaticContraction && !(radius <= 0.0))
+        MS::ac_setup<GLC_MACHINE_STAGED_POW != 0>(c, S.yt, R.w, radius, P, machine_pow_ac());
     R.ac = P;
     if (P.need) {
         S.p[0] = R.w.dmoNorm;
@@ -330,10 +364,12 @@ GLC_DEVICE_NOINLINE void unit_struct(const SlotRef S) {
         S.B.status = 0;
         S.unit = U_STRUCT_FIN;
     }
+    return unit__;
 }
 
 // digest the root of a structure visit: the contracted dark-matter mass and the fixed-point update
-GLC_DEVICE_NOINLINE void unit_struct_fin(const SlotRef S) {
+GLC_DEVICE_NOINLINE int unit_struct_fin(const SlotRef S0) {
+    GLC_UNIT_ENTER(S0, U_STRUCT_FIN);
     RhsState &R = S.R;
     NodeCtx &c = S.L.ctx;
     const int comp = R.comp;
@@ -359,13 +395,18 @@ GLC_DEVICE_NOINLINE void unit_struct_fin(const SlotRef S) {
     MS::structure_store(c, comp, radius, velocity);
     R.comp++;
     m_struct_next(S);
+    return unit__;
 }
 
 // One Brent step: evaluate the function at the pending abscissa, digest it, advance to the next abscissa.
 // Touches only the slot's RootState record.
 template <int UNIT>
-GLC_DEVICE_NOINLINE void unit_root(const SlotRef S) {
+GLC_DEVICE_NOINLINE int unit_root(const SlotRef S0) {
+    GLC_UNIT_ENTER(S0, UNIT);
     BrentState B = S.B;
+    const RootOptions o = m_root_options<UNIT>();
+#pragma unroll 1
+    for (int step = 0;; step++) {
     const double x = B.x;
     double fx;
     if (UNIT == U_ROOT_AC) {
@@ -376,7 +417,7 @@ GLC_DEVICE_NOINLINE void unit_root(const SlotRef S) {
         P.fi = S.p[3];
         P.fd = S.p[4];
         P.bterm = S.p[6];
-        fx = MS::ac_function(S.p[0], S.p[1], w, P, S.p[5], x);
+        fx = MS::ac_function<GLC_MACHINE_STAGED_POW != 0>(S.p[0], S.p[1], w, P, S.p[5], x, machine_pow_ac());
     } else if (UNIT == U_ROOT_TRUNC || UNIT == U_ROOT_CRIT) {
         MS::Kmt k;
         k.sigma0 = S.p[0];
@@ -400,34 +441,47 @@ GLC_DEVICE_NOINLINE void unit_root(const SlotRef S) {
         w.hhValid = S.p[9] != 0.0;
         fx = MS::cooling_function(w, x);
     }
-    const RootOptions o = m_root_options<UNIT>();
     brent_feed(B, o, fx);
     brent_advance(B, o);
+    // GLC_ROOT_STEPS Brent steps per unit execution while the lane's root find is still busy: the continuation stays in
+    // registers between them (a unit execution costs a queue round trip plus the load and store of the RootState record)
+    if (!B.busy || step + 1 >= GLC_ROOT_STEPS) break;
+    }
     S.B = B;
     if (!B.busy) m_root_finish<UNIT>(S);
+    return unit__;
 }
 
-GLC_DEVICE_NOINLINE void unit_sfr_begin(const SlotRef S) {
+GLC_DEVICE_NOINLINE int unit_sfr_begin(const SlotRef S0) {
+    GLC_UNIT_ENTER(S0, U_SFR_BEGIN);
     RhsState &R = S.R;
     MS::sfr_setup(S.L.ctx, S.yt, true, R.sfr);
     if (!R.sfr.live) {
         R.psiDisk = 0.0;
         m_cool_decide(S);
-        return;
+        return unit__;
     }
     if (R.sfr.needRmax) {
         m_sfr_root_params(S);
         m_root_start<U_ROOT_TRUNC>(S, 0.0, R.sfr.rOut, false, 0.0, 0.0);
     } else
         m_sfr_after_trunc(S, 0.0, 0);
+    return unit__;
 }
-GLC_DEVICE_NOINLINE void unit_sfr_mid(const SlotRef S) { m_sfr_after_trunc(S, S.B.result, S.B.status); }
-GLC_DEVICE_NOINLINE void unit_sfr_mid2(const SlotRef S) {
+GLC_DEVICE_NOINLINE int unit_sfr_mid(const SlotRef S0) {
+    GLC_UNIT_ENTER(S0, U_SFR_MID);
+    m_sfr_after_trunc(S, S.B.result, S.B.status);
+    return unit__;
+}
+GLC_DEVICE_NOINLINE int unit_sfr_mid2(const SlotRef S0) {
+    GLC_UNIT_ENTER(S0, U_SFR_MID2);
     if (S.B.status != 0) S.R.bad = 1;
     m_sfr_intervals(S, S.B.result);
+    return unit__;
 }
 
-GLC_DEVICE_NOINLINE void unit_qag(const SlotRef S) {
+GLC_DEVICE_NOINLINE int unit_qag(const SlotRef S0) {
+    GLC_UNIT_ENTER(S0, U_QAG);
     RhsState &R = S.R;
     const MS::Kmt k = R.sfr.k;
     GLC_COUNT(7);
@@ -435,20 +489,22 @@ GLC_DEVICE_NOINLINE void unit_qag(const SlotRef S) {
         GLC_COUNT(2);
         return MS::sfr_integrand(k, r);
     });
-    if (S.Q.busy) return;
+    if (S.Q.busy) return unit__;
     const double v = qag_finish(S.Q);
     R.total += v;
     if (S.Q.status == 11) R.bad = 1;
     R.iv++;
     if (R.iv < R.nIv) {
         m_qag_start(S);
-        return;
+        return unit__;
     }
     R.psiDisk = 2.0 * kPi * R.total;
     m_cool_decide(S);
+    return unit__;
 }
 
-GLC_DEVICE_NOINLINE void unit_cool_begin(const SlotRef S) {
+GLC_DEVICE_NOINLINE int unit_cool_begin(const SlotRef S0) {
+    GLC_UNIT_ENTER(S0, U_COOL_BEGIN);
     RhsState &R = S.R;
     Work w = R.w;
     double logSlopeT = 0.0, rootOuter, rootZero, result;
@@ -473,26 +529,33 @@ GLC_DEVICE_NOINLINE void unit_cool_begin(const SlotRef S) {
         R.rinfall = result;
         S.unit = U_RK;
     }
+    return unit__;
 }
 
-// One unit of one slot.  Returns false when the slot is idle.
-GLC_DEVICE_INLINE bool machine_step(const SlotRef &S, const LaneMem &M) {
-    switch (S.unit) {
-        case U_RK: unit_rk(S, M); break;
-        case U_RHS_BEGIN: unit_rhs_begin(S); break;
-        case U_STRUCT: unit_struct(S); break;
-        case U_STRUCT_FIN: unit_struct_fin(S); break;
-        case U_ROOT_AC: unit_root<U_ROOT_AC>(S); break;
-        case U_ROOT_TRUNC: unit_root<U_ROOT_TRUNC>(S); break;
-        case U_ROOT_CRIT: unit_root<U_ROOT_CRIT>(S); break;
-        case U_ROOT_COOL: unit_root<U_ROOT_COOL>(S); break;
-        case U_SFR_BEGIN: unit_sfr_begin(S); break;
-        case U_SFR_MID: unit_sfr_mid(S); break;
-        case U_SFR_MID2: unit_sfr_mid2(S); break;
-        case U_QAG: unit_qag(S); break;
-        case U_COOL_BEGIN: unit_cool_begin(S); break;
-        default: return false;
+// One unit (`u`) of one slot.  Returns the slot's next unit, -1 when `u` is not an executable unit (idle slot).
+GLC_DEVICE_INLINE int machine_dispatch(const SlotRef &S, const LaneMem &M, int u) {
+    switch (u) {
+        case U_RK: return unit_rk(S, M);
+        case U_RHS_BEGIN: return unit_rhs_begin(S);
+        case U_STRUCT: return unit_struct(S);
+        case U_STRUCT_FIN: return unit_struct_fin(S);
+        case U_ROOT_AC: return unit_root<U_ROOT_AC>(S);
+        case U_ROOT_TRUNC: return unit_root<U_ROOT_TRUNC>(S);
+        case U_ROOT_CRIT: return unit_root<U_ROOT_CRIT>(S);
+        case U_ROOT_COOL: return unit_root<U_ROOT_COOL>(S);
+        case U_SFR_BEGIN: return unit_sfr_begin(S);
+        case U_SFR_MID: return unit_sfr_mid(S);
+        case U_SFR_MID2: return unit_sfr_mid2(S);
+        case U_QAG: return unit_qag(S);
+        case U_COOL_BEGIN: return unit_cool_begin(S);
+        default: return -1;
     }
+}
+// ... of the unit the slot's pending-unit word names (host-driven machine, tests/emu).  Returns false when the slot is idle.
+GLC_DEVICE_INLINE bool machine_step(const SlotRef &S, const LaneMem &M) {
+    const int nu = machine_dispatch(S, M, S.unit);
+    if (nu < 0) return false;
+    S.unit = nu;
     return true;
 }
 
@@ -525,13 +588,20 @@ template <int THREADS, int SLOTS>
 __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotArrays slots) {
     static_assert((SLOTS & (SLOTS - 1)) == 0 && SLOTS <= 2048, "SLOTS must be a power of two <= 2048 (11-bit ids)");
     constexpr int PER = SLOTS / THREADS;
-    extern __shared__ unsigned int s_qdyn[];  // [U_IDLE][SLOTS] ring cells (dynamic: > 48 KB)
+    static_assert(SLOTS == GLC_MSLOTS, "machine_pow_ac() places the staged table behind U_IDLE x GLC_MSLOTS ring cells");
+    // s_qdyn: [U_IDLE][SLOTS] ring cells (dynamic: > 48 KB), then the staged x^omega table
     unsigned int(*s_q)[SLOTS] = reinterpret_cast<unsigned int(*)[SLOTS]>(s_qdyn);
     __shared__ unsigned int s_head[U_IDLE], s_tail[U_IDLE];
     __shared__ int s_idle, s_cur, s_abort;
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t base = (int64_t)blockIdx.x * SLOTS;
     for (int i = tid; i < U_IDLE * SLOTS; i += THREADS) s_qdyn[i] = 0u;  // empty, lap 0
+#if GLC_MACHINE_STAGED_POW
+    {
+        double *tab = reinterpret_cast<double *>(s_qdyn + (size_t)U_IDLE * SLOTS);
+        for (int i = tid; i < GLC_TABLES.powAcN; i += THREADS) tab[i] = GLC_LDG(GLC_TABLES.powAc + i);
+    }
+#endif
     if (tid < U_IDLE) s_head[tid] = s_tail[tid] = 0u;
     if (tid == 0) {
         s_idle = 0;
@@ -549,9 +619,12 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
             own.unit = U_RK;
         }
         int u = own.unit;
-        if (u < 0 || u > U_IDLE) {  // finished by the drain kernel (-1) in an earlier hand-over: free, like U_IDLE
-            own.L.phase = PH_FETCH;
-            own.unit = u = U_RK;
+        if (u < 0 || u > U_IDLE) {
+            // finished by the drain kernel (-1) in an earlier hand-over: free.  The lane state in memory is the STALE copy the
+            // drain kernel loaded (heavy == HV_RHS: unit_rk would digest an evaluation that never ran and evolve the old node
+            // again), so the slot is reset completely, not just re-armed like an idle one
+            slot_reset(own);
+            u = U_RK;
         }
         if (A.hold && u == U_RHS_BEGIN)
             atomicAdd(&s_idle, 1);  // held at an RK boundary for the drain kernel: out of work as far as this block goes
@@ -677,9 +750,8 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
             if (A.slotBusy && atomicExch(&A.slotBusy[slot], 1) != 0) atomicAdd(&A.ledgerErr[2], 1ull);  // two lanes in one slot
             if (A.slotBusy && S.unit != u && !(u == U_RK && S.unit == U_IDLE)) atomicAdd(&A.ledgerErr[3], 1ull);  // wrong queue
 #endif
-            S.unit = u;  // the queue a slot sits in IS its pending unit
-            machine_step(S, M);
-            const int nu = S.unit;
+            const int nu = machine_dispatch(S, M, u);  // the queue a slot sits in IS its pending unit
+            S.unit = nu;
 #ifdef GLC_LEDGER
             if (A.slotBusy) atomicExch(&A.slotBusy[slot], 0);
 #endif

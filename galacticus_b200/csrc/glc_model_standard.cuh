@@ -361,10 +361,13 @@ struct ModelStandard {
                                                 (GLC_LDG(xs + lo + 1) - GLC_LDG(xs + lo));
         return x * rs;
     }
-    GLC_DEVICE_INLINE double ac_orbital_mean(const Work &w, double radius) {
+    // `powAc`: where the caller keeps the x^omega table (the micro-task machine stages it in shared memory; same values)
+    // (kStaged: the table pointer is not a global-memory address -- plain loads instead of the read-only path)
+    template <bool kStaged = false>
+    GLC_DEVICE_INLINE double ac_orbital_mean(const Work &w, double radius, const double *__restrict__ powAc = GLC_TABLES.powAc) {
         // sphericalAdiabaticGnedin2004RadiusOrbitalMean, adiabatic_Gnedin2004.F90:664-687
         return GLC_PARAMS.adiabaticA * w.rvir *
-               fast_exponentiate(GLC_TABLES.powAc, GLC_TABLES.powAcN, GLC_TABLES.powAcDx, GLC_TABLES.powAcInvDx, 1.0e-3, 1.0,
+               fast_exponentiate<kStaged>(powAc, GLC_TABLES.powAcN, GLC_TABLES.powAcDx, GLC_TABLES.powAcInvDx, 1.0e-3, 1.0,
                                  GLC_PARAMS.adiabaticOmega, radius / w.rvir);
     }
     GLC_DEVICE_INLINE double baryonic_mass_self(const NodeCtx &c, const double (&y)[NY]) {
@@ -381,12 +384,15 @@ struct ModelStandard {
         double fd, fi, bterm, rup, rInit;
         int need;  // 1: r_i must be found by the root finder on [radius, rup]; 0: rInit is final
     };
+    template <bool kStaged = false>
     GLC_DEVICE_INLINE double ac_function(double dmoNorm, double dmoScale, const Work &w, const AcProblem &P, double radius,
-                                         double ri) {
-        return dmo_mass(dmoNorm, dmoScale, ac_orbital_mean(w, ri)) * (P.fi * ri - P.fd * radius) - P.bterm;
+                                         double ri, const double *__restrict__ powAc = GLC_TABLES.powAc) {
+        return dmo_mass(dmoNorm, dmoScale, ac_orbital_mean<kStaged>(w, ri, powAc)) * (P.fi * ri - P.fd * radius) - P.bterm;
     }
     // set-up for a shell inside the virial radius (radius > 0)
-    GLC_DEVICE_INLINE void ac_setup(const NodeCtx &c, const double (&y)[NY], const Work &w, double radius, AcProblem &P) {
+    template <bool kStaged = false>
+    GLC_DEVICE_INLINE void ac_setup(const NodeCtx &c, const double (&y)[NY], const Work &w, double radius, AcProblem &P,
+                                    const double *__restrict__ powAc = GLC_TABLES.powAc) {
         const double nfwNorm = w.dmoNorm, rs = w.dmoScale;
         const double fDm = 1.0 - GLC_PARAMS.OmegaBaryon / GLC_PARAMS.OmegaMatter;
         P.fd = P.fi = P.bterm = 0.0;
@@ -399,12 +405,12 @@ struct ModelStandard {
         const double mTot = fmax(mSelfRaw + c.massBaryonicSubhalos, 0.0);
         P.fd = fmin(fDm + (mTot - mSelf) / c.basicMass, 1.0);
         P.fi = fmin(fDm + mTot / c.basicMass, 1.0);
-        const double rmean = ac_orbital_mean(w, radius);
+        const double rmean = ac_orbital_mean<kStaged>(w, radius, powAc);
         P.bterm = baryonic_vc2(c, y, w, rmean) * rmean * radius / kGInternal;
         const double menc = dmo_mass(nfwNorm, rs, rmean);
         if (menc > 0.0) P.rup = fmax((P.bterm / menc + P.fd * radius) / P.fi, radius);
         // the reference first tests solver(r_vir) < 0 (:463-466)
-        const double fVir = ac_function(nfwNorm, rs, w, P, radius, w.rvir);
+        const double fVir = ac_function<kStaged>(nfwNorm, rs, w, P, radius, w.rvir, powAc);
         if (fVir < 0.0)
             P.rInit = w.rvir;
         else

@@ -548,6 +548,7 @@ GLC_DEVICE_INLINE double linear_table_eval(G &&g, double xmin, double xmax, int 
 // fastExponentiator (math/exponentiation.F90:57-104): linear interpolation in a table of x^exponent with `density`
 // points per unit x on [rangeMin, rangeMax], exact pow outside.  `table` holds the n lattice values (built once on the
 // host by build_pow_table with the same dm_pow).
+template <bool kStaged = false>
 GLC_DEVICE_INLINE double fast_exponentiate(const double *__restrict__ table, int n, double dx, double inverseDx,
                                            double rangeMin, double rangeMax, double exponent, double x) {
     // dx = (rangeMax - rangeMin) / (n - 1) and inverseDx = 1 / ((rangeMin + dx) - rangeMin) are table constants
@@ -560,6 +561,7 @@ GLC_DEVICE_INLINE double fast_exponentiate(const double *__restrict__ table, int
         i = max(min((int)((x - rangeMin) * inverseDx) + 1, n - 1), 1);
     const double xi = rangeMin + dx * (double)(i - 1);
     const double h = (x - xi) * inverseDx;
+    if (kStaged) return table[i - 1] * (1.0 - h) + table[i] * h;  // a staged copy (shared memory): not the read-only global path
     return GLC_LDG(table + i - 1) * (1.0 - h) + GLC_LDG(table + i) * h;
 }
 

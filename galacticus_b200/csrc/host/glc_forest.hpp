@@ -97,7 +97,7 @@ struct Forest {
     // what cgmAccretionNodesMerge needs of a merged progenitor (see merge()): unaccreted mass / metals and halo mass at merger
     std::vector<double> merged_unaccreted, merged_unaccreted_abund, merged_mass;
     std::vector<uint8_t> merged_hot;
-    mutable double memo_t[2] = {-1.0, -1.0}, memo_v[2] = {0.0, 0.0};  // timestep memo, like timeHostPrevious (:945-958)
+    mutable double memo_t[2][2] = {{-1.0, -1.0}, {-1.0, -1.0}}, memo_v[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // timestep memos
     glc_forest_counters fc{};
 
     double *R(int64_t i) const { return rec + i * GLC_NPROP; }
@@ -109,15 +109,21 @@ struct Forest {
         const double e = dm_exp(2.0 * (1.5 * sqrt(OL) * H0 * t));
         return 1.0 / (H0 * sqrt(OL) * ((e + 1.0) / (e - 1.0)));
     }
-    double timestep(double t) const {  // simple.F90 and evolver/standard.F90:945-958 (same numbers in quickTest.xml)
-        if (t == memo_t[0]) return memo_v[0];
-        if (t == memo_t[1]) return memo_v[1];
-        memo_t[1] = memo_t[0];
-        memo_v[1] = memo_v[0];
-        memo_t[0] = t;
-        memo_v[0] = std::min(0.1 * expansion_timescale(t), 1.0);
-        return memo_v[0];
+    // mergerTreeEvolveTimestepSimple (evolve/timesteps/simple.F90: min(timeStepRelative / H(t), timeStepAbsolute)) and the host
+    // timestep of mergerTreeEvolverStandard (evolver/standard.F90:942-968, same form with timestepHostRelative/Absolute; a
+    // non-positive relative value switches the expansion timescale off, :951-954); each memoised like timeHostPrevious (:945-958)
+    double timestep_of(double t, double relative, double absolute, int which) const {
+        double *mt = memo_t[which], *mv = memo_v[which];
+        if (t == mt[0]) return mv[0];
+        if (t == mt[1]) return mv[1];
+        mt[1] = mt[0];
+        mv[1] = mv[0];
+        mt[0] = t;
+        mv[0] = relative > 0.0 ? std::min(relative * expansion_timescale(t), absolute) : absolute;
+        return mv[0];
     }
+    double timestep(double t) const { return timestep_of(t, P->timestepSimpleRelative, P->timestepSimpleAbsolute, 0); }
+    double timestep_host(double t) const { return timestep_of(t, P->timestepHostRelative, P->timestepHostAbsolute, 1); }
     double failed_fraction(double m, double t) const {  // accretion/halo/simple.F90: simpleFailedFraction
         return (t > P->timeReionization && halo->virial_velocity(m, t) < P->velocitySuppressionReionization) ? 1.0 : 0.0;
     }
@@ -238,7 +244,7 @@ struct Forest {
         if (children_left[h] > 0)
             limit = std::max(th, tn);
         else
-            limit = std::max(th + timestep(th), tn);
+            limit = std::max(th + timestep_host(th), tn);
         return std::min(to, limit);
     }
     // ... for a childless, isolated node (:905-914, :1003-1030)

@@ -54,8 +54,15 @@ static double expansion_timescale(const tree_ctx *c, double t) {
     return 1.0 / (H0 * sqrt(OL) * ((e + 1.0) / (e - 1.0)));
 }
 static double timestep(const tree_ctx *c, double t) {
-    /* simple.F90: min(timeStepRelative / H, timeStepAbsolute); evolver/standard.F90:945-958 with the same numbers */
-    return fmin(0.1 * expansion_timescale(c, t), 1.0);
+    /* mergerTreeEvolveTimestepSimple, evolve/timesteps/simple.F90: min(timeStepRelative / H, timeStepAbsolute) */
+    return c->P->timestepSimpleRelative > 0.0 ? fmin(c->P->timestepSimpleRelative * expansion_timescale(c, t), c->P->timestepSimpleAbsolute)
+                                              : c->P->timestepSimpleAbsolute;
+}
+static double timestep_host(const tree_ctx *c, double t) {
+    /* evolver/standard.F90:942-968: min(timestepHostRelative / H, timestepHostAbsolute); the absolute value alone when the
+       relative one is not positive (:951-954) */
+    return c->P->timestepHostRelative > 0.0 ? fmin(c->P->timestepHostRelative * expansion_timescale(c, t), c->P->timestepHostAbsolute)
+                                            : c->P->timestepHostAbsolute;
 }
 static double virial_velocity(const tree_ctx *c, double m, double t) {
     /* virial_density_contrast.F90:195-417 through the tabulated mean halo density */
@@ -258,7 +265,7 @@ static int visit(tree_ctx *c, int i, glc_forest_counters *fc, glc_counters *C) {
         double to = fmin(c->time_end[s], tn + timestep(c, tn)), th, limit;
         if (to == tn) continue;
         th = c->parent[i] >= 0 ? node_time(c, i) : fmax(node_time(c, i), tn);
-        limit = c->children_left[i] > 0 ? fmax(th, tn) : fmax(th + timestep(c, th), tn);
+        limit = c->children_left[i] > 0 ? fmax(th, tn) : fmax(th + timestep_host(c, th), tn);
         to = fmin(to, limit);
         if (to > tn) {
             if (evolve_to(c, s, to, fc, C)) return -10;

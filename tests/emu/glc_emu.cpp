@@ -258,7 +258,7 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
             A.slotL = sL.data();
             A.slotYt = sYt.data();
             A.slotUnit = sUnit.data();
-            A.drainSparse = 0;
+            A.drainLanes = 0;
             const int nl = 7;
             std::vector<LaneState> dl(nl);
             std::vector<LaneMem> dm(nl, LaneMem{&A, A.ws, 1});
