@@ -71,10 +71,12 @@ struct glc_evolver {
     int32_t drain_handover = 1;     // run-to-completion mode: finish the last nodes with drain_kernel
     int64_t drain_threshold = 120000; // hand over when fewer slots than this are still in flight (measured: profiles/r01f_knobs.txt)
     int32_t drain_dense_budget = 1024; // evaluations per lane in a dense drain pass
+    int32_t hybrid_budget = 4096;      // pops per warp of one internal machine slice in run-to-completion mode
     int32_t *d_held = nullptr;
     float *d_held_score = nullptr;
     int64_t held_cap = 0;
     int32_t drain_express = 1;      // first drain pass: predicted-longest nodes one per warp on stream2
+    float drain_age_weight = 0.0f;  // express selection: score = predicted remaining steps (0) or 6 x that + weight x evaluations so far
     int32_t drain_spread = 1;       // drain / lane passes: spread the nodes over all resident warps (KernelArgs::drainLanes); 0 = one per
                                     // warp when they fit, else 32 per warp (round-2 behaviour before the measurement in profiles/r02k)
     cudaStream_t stream2 = nullptr;
@@ -89,10 +91,18 @@ struct glc_evolver {
     int32_t *h_collect_meta = nullptr;   // pinned
     int64_t collect_meta_cap = 0;
     int32_t stream_sparse_budget = 32, stream_dense_budget = 12;  // evaluations per lane in one lane pass of a streaming tick
+    int32_t stream_spread = 0;           // lane passes: spread the nodes over all warps (measured slower on forests: profiles/r02k)
+    int32_t stream_sort = 0;             // lane passes with more nodes than warps: list sorted by kind of node (component set)
+    int32_t stream_express = 0;          // lane passes with more nodes than warps: nodes whose score (evaluations spent so far +
+                                         // 6 x predicted remaining steps) reaches this get a warp each; 0 = off
+    int32_t stream_express_budget = 48;  // evaluations of an express warp per tick
+    std::vector<int32_t> h_held, h_ordered;
+    std::vector<float> h_score;
+    std::vector<int> h_idx;
     int64_t stream_machine_above = -1;   // adaptive ticks: machine slice when queued + occupied >= this (default: drain_threshold)
     // tick statistics of the session (forest log): machine slices / lane passes, their device-side wall time, nodes in flight
     int64_t tick_machine = 0, tick_lane = 0, tick_hold = 0;
-    double tick_machine_s = 0.0, tick_lane_s = 0.0, tick_live_sum = 0.0, tick_lanes_sum = 0.0;
+    double tick_machine_s = 0.0, tick_lane_s = 0.0, tick_live_sum = 0.0, tick_lanes_sum = 0.0, tick_express_sum = 0.0;
     int32_t l2_persist = 0;              // GLC_L2_PERSIST=1: pin the machine's RootState array in L2 (experiment)
     bool l2_window_set = false;
     int32_t forest_schedule = 1;         // glc_forest_evolve: 1 = asynchronous groups over the streaming machine, 0 = bulk-synchronous rounds
@@ -620,7 +630,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
     // are brought to an RK boundary (hold slices) and handed to drain_kernel, which finishes their nodes with
     // whole evaluations.  With a user slice budget the machine alone runs (resumable by construction).
     const bool hybrid = mode != 1 && (ev->slice_budget <= 0 || mode == 2) && ev->drain_handover;
-    if (hybrid) A.budget = 4096;
+    if (hybrid) A.budget = ev->hybrid_budget;
     const unsigned long long drainBelow = (unsigned long long)ev->drain_threshold;
     bool draining = false;
     int stalled = 0;
@@ -738,7 +748,8 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                 for (int pass = 0;; pass++) {
                     GLC_CHECK(ev, cudaMemsetAsync(d_count, 0, sizeof(int) * 4, ev->stream));
                     held_list_kernel<<<std::min((nslotsActive + 255) / 256, ev->num_sms * 8), 256, 0, ev->stream>>>(
-                        ev->d_slots.unit, ev->d_slots.L, nslotsActive, ev->d_held, pass == 0 ? ev->d_held_score : nullptr, d_count, 0);
+                        ev->d_slots.unit, ev->d_slots.L, nslotsActive, ev->d_held, pass == 0 ? ev->d_held_score : nullptr, d_count, 0,
+                        ev->drain_age_weight);
                     int nheld = 0;
                     GLC_CHECK(ev, cudaMemcpyAsync(&nheld, d_count, sizeof(int), cudaMemcpyDeviceToHost, ev->stream));
                     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
@@ -939,8 +950,11 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
     const int nslotsAll = (int)ev->nslots_machine;
     const int warpsResident = ev->num_sms * bps * (kBlock / 32);
     GLC_CHECK(ev, cudaMemsetAsync(d_count, 0, sizeof(int) * 4, ev->stream));
+    const bool wantExpress = ev->stream_express > 0;
+    const bool wantSort = !wantExpress && ev->stream_sort > 0;
     held_list_kernel<<<std::min((nslotsAll + 255) / 256, ev->num_sms * 8), 256, 0, ev->stream>>>(
-        ev->d_slots.unit, ev->d_slots.L, nslotsAll, ev->d_held, nullptr, d_count, (int)std::min<int64_t>(queued, nslotsAll));
+        ev->d_slots.unit, ev->d_slots.L, nslotsAll, ev->d_held, (wantExpress || wantSort) ? ev->d_held_score : nullptr, d_count,
+        (int)std::min<int64_t>(queued, nslotsAll), wantExpress ? 1.0f : (wantSort ? -1.0f : 0.0f));
     int nlist = 0;
     GLC_CHECK(ev, cudaMemcpyAsync(&nlist, d_count, sizeof(int), cudaMemcpyDeviceToHost, ev->stream));
     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
@@ -967,19 +981,94 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
         A.nheld = nlist;
         A.held_counter = d_count + 1;
         A.drainRefill = 1;
-        // spread over all resident warps: a node advances faster the fewer nodes share its warp; the evaluation budget of
-        // the pass shrinks with the number of nodes per warp so that a tick stays a few milliseconds long
-        const int lanes = ev->drain_spread ? std::min(32, (nlist + warpsResident - 1) / warpsResident) : (nlist <= warpsResident ? 1 : 32);
+        if (wantSort && nlist > warpsResident) {
+            // ---- more nodes than warps: the lanes of a warp share one instruction stream, so nodes of the same kind (same
+            // component set: queue_bucket) are put next to each other -- a warp of hot-halo-only nodes is done after one or
+            // two evaluations and leaves, a warp of disk + spheroid + black-hole nodes iterates its nested solvers together
+            std::vector<int32_t> &h_held = ev->h_held;
+            std::vector<float> &h_score = ev->h_score;
+            h_held.resize(nlist);
+            h_score.resize(nlist);
+            GLC_CHECK(ev, cudaMemcpyAsync(h_held.data(), ev->d_held, sizeof(int32_t) * nlist, cudaMemcpyDeviceToHost, ev->stream));
+            GLC_CHECK(ev, cudaMemcpyAsync(h_score.data(), ev->d_held_score, sizeof(float) * nlist, cudaMemcpyDeviceToHost, ev->stream));
+            GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+            int start[66] = {0};
+            for (int k = 0; k < nlist; k++) start[std::min(64, std::max(0, (int)h_score[k])) + 1]++;
+            for (int b = 0; b < 65; b++) start[b + 1] += start[b];
+            std::vector<int32_t> &ordered = ev->h_ordered;
+            ordered.resize(nlist);
+            for (int k = 0; k < nlist; k++) ordered[start[std::min(64, std::max(0, (int)h_score[k]))]++] = h_held[k];
+            GLC_CHECK(ev, cudaMemcpyAsync(ev->d_held, ordered.data(), sizeof(int32_t) * nlist, cudaMemcpyHostToDevice, ev->stream));
+            GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+        }
+        int nexpress = 0;
+        const int expressCap = ev->num_sms * (kBlock / 32) * std::max(1, bps - 1);  // all but one block per SM, one node per warp
+        if (wantExpress && nlist > warpsResident) {
+            // ---- more nodes than warps.  The tree scheduler waits for the SLOWEST node of a group, and a node alone in its warp
+            // advances ~4x faster than one of 32 (a warp serialises the divergent evaluations of its lanes).  The nodes that
+            // have run longest / have the most steps left (held_list_kernel's score) therefore get a warp each (express kernel,
+            // stream2) while the rest shares the remaining block per SM one node per lane.
+            std::vector<int32_t> &h_held = ev->h_held;
+            std::vector<float> &h_score = ev->h_score;
+            h_held.resize(nlist);
+            h_score.resize(nlist);
+            GLC_CHECK(ev, cudaMemcpyAsync(h_held.data(), ev->d_held, sizeof(int32_t) * nlist, cudaMemcpyDeviceToHost, ev->stream));
+            GLC_CHECK(ev, cudaMemcpyAsync(h_score.data(), ev->d_held_score, sizeof(float) * nlist, cudaMemcpyDeviceToHost, ev->stream));
+            GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+            std::vector<int> &idx = ev->h_idx;
+            idx.resize(nlist);
+            for (int k = 0; k < nlist; k++) idx[k] = k;
+            nexpress = std::min(expressCap, nlist);
+            std::nth_element(idx.begin(), idx.begin() + nexpress, idx.end(), [&](int a, int b) { return h_score[a] > h_score[b]; });
+            // only nodes that have actually been running qualify (fresh slots and just-fetched nodes score 0)
+            int keep = 0;
+            std::vector<int32_t> &ordered = ev->h_ordered;
+            ordered.resize(nlist);
+            for (int k = 0; k < nexpress; k++)
+                if (h_score[idx[k]] >= (float)ev->stream_express) ordered[keep++] = h_held[idx[k]];
+            int tail = keep;
+            for (int k = 0; k < nexpress; k++)
+                if (!(h_score[idx[k]] >= (float)ev->stream_express)) ordered[tail++] = h_held[idx[k]];
+            for (int k = nexpress; k < nlist; k++) ordered[tail++] = h_held[idx[k]];
+            nexpress = keep;
+            if (nexpress > 0) {
+                GLC_CHECK(ev, cudaMemcpyAsync(ev->d_held, ordered.data(), sizeof(int32_t) * nlist, cudaMemcpyHostToDevice, ev->stream));
+                GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
+                KernelArgs X = A;
+                X.nheld = nexpress;
+                X.held_counter = d_count + 2;
+                X.drainLanes = 1;
+                X.drainRefill = 0;  // an express warp is done when its node is
+                X.budget = ev->stream_express_budget;
+                drain_kernel<ModelStandard><<<(nexpress + kBlock / 32 - 1) / (kBlock / 32), kBlock, 0, ev->stream2>>>(X);
+                ev->launches++;
+                A.held = ev->d_held + nexpress;
+                A.nheld = nlist - nexpress;
+            }
+        }
+        // spread over the resident warps the express kernel leaves: a node advances faster the fewer nodes share its warp; the
+        // evaluation budget of the pass shrinks with the number of nodes per warp so that a tick stays a few milliseconds long
+        const int warpsFree = std::max(kBlock / 32, warpsResident - (nexpress + kBlock / 32 - 1) / (kBlock / 32) * (kBlock / 32));
+        // stream_spread: 0 = one node per warp when they fit, else 32 per warp on as few blocks as needed; 1 = over all resident
+        // warps; 2 = over one block per SM (a second block per SM only when 32 nodes per warp do not suffice)
+        const int warpsOne = ev->num_sms * (kBlock / 32);
+        int lanes = A.nheld <= warpsFree ? 1 : 32;
+        if (ev->stream_spread == 1) lanes = std::min(32, (A.nheld + warpsFree - 1) / warpsFree);
+        if (ev->stream_spread == 2 && A.nheld > warpsFree) lanes = std::min(32, (A.nheld + warpsOne - 1) / warpsOne);
         A.drainLanes = lanes >= 32 ? 0 : lanes;
         A.budget = ev->stream_sparse_budget - (int)((long long)(ev->stream_sparse_budget - ev->stream_dense_budget) * (lanes - 1) / 31);
         const int perBlock = lanes * (kBlock / 32);
-        int dgrid = (nlist + perBlock - 1) / perBlock;
-        dgrid = std::max(1, std::min(ev->num_sms * bps, dgrid));
+        int dgrid = (A.nheld + perBlock - 1) / perBlock;
+        dgrid = std::max(1, std::min(warpsFree / (kBlock / 32), dgrid));
         ev->tick_lanes_sum += lanes;
-        drain_kernel<ModelStandard><<<dgrid, kBlock, 0, ev->stream>>>(A);
-        ev->launches++;
+        ev->tick_express_sum += nexpress;
+        if (A.nheld > 0) {
+            drain_kernel<ModelStandard><<<dgrid, kBlock, 0, ev->stream>>>(A);
+            ev->launches++;
+        }
         ev->slices++;
         GLC_CHECK(ev, cudaGetLastError());
+        if (nexpress > 0) GLC_CHECK(ev, cudaStreamSynchronize(ev->stream2));
     }
     GLC_CHECK(ev, cudaMemcpyAsync(hc, ev->d_counters, sizeof(unsigned long long) * 11, cudaMemcpyDeviceToHost, ev->stream));
     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
@@ -1031,12 +1120,18 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_DRAIN")) ev->drain_handover = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_BELOW")) ev->drain_threshold = atoll(e);
     if (const char *e = getenv("GLC_DRAIN_DENSE_BUDGET")) ev->drain_dense_budget = atoi(e);
+    if (const char *e = getenv("GLC_HYBRID_BUDGET")) ev->hybrid_budget = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_EXPRESS")) ev->drain_express = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_SPREAD")) ev->drain_spread = atoi(e);
+    if (const char *e = getenv("GLC_DRAIN_AGE_WEIGHT")) ev->drain_age_weight = (float)atof(e);
     if (const char *e = getenv("GLC_L2_PERSIST")) ev->l2_persist = atoi(e);
     if (const char *e = getenv("GLC_STREAM_SPARSE_BUDGET")) ev->stream_sparse_budget = atoi(e);
     if (const char *e = getenv("GLC_STREAM_DENSE_BUDGET")) ev->stream_dense_budget = atoi(e);
     if (const char *e = getenv("GLC_STREAM_MACHINE_ABOVE")) ev->stream_machine_above = atoll(e);
+    if (const char *e = getenv("GLC_STREAM_EXPRESS")) ev->stream_express = atoi(e);
+    if (const char *e = getenv("GLC_STREAM_SPREAD")) ev->stream_spread = atoi(e);
+    if (const char *e = getenv("GLC_STREAM_SORT")) ev->stream_sort = atoi(e);
+    if (const char *e = getenv("GLC_STREAM_EXPRESS_BUDGET")) ev->stream_express_budget = atoi(e);
     cudaStreamCreateWithFlags(&ev->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ev->stream2, cudaStreamNonBlocking);
     cudaEventCreate(&ev->ev0);
@@ -1920,9 +2015,10 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
                     fprintf(stderr, "[glc forest async] %lld polls, %.2f s in device slices, %.2f s collecting, %.2f s submitting, %.2f s total\n",
                             (long long)polls, t_run, t_collect, t_submit, now_s() - t0);
                     const int64_t ticks = ev->tick_machine + ev->tick_lane;
-                    fprintf(stderr, "[glc forest async] ticks: %lld machine slices (%.2f s), %lld lane passes (%.2f s, mean %.1f nodes per warp), %lld hold slices; mean nodes queued or in flight per tick %.0f\n",
+                    fprintf(stderr, "[glc forest async] ticks: %lld machine slices (%.2f s), %lld lane passes (%.2f s, mean %.1f nodes per warp, %.0f express warps), %lld hold slices; mean nodes queued or in flight per tick %.0f\n",
                             (long long)ev->tick_machine, ev->tick_machine_s, (long long)ev->tick_lane, ev->tick_lane_s,
-                            ev->tick_lane ? ev->tick_lanes_sum / (double)ev->tick_lane : 0.0, (long long)ev->tick_hold,
+                            ev->tick_lane ? ev->tick_lanes_sum / (double)ev->tick_lane : 0.0,
+                            ev->tick_lane ? ev->tick_express_sum / (double)ev->tick_lane : 0.0, (long long)ev->tick_hold,
                             ticks ? ev->tick_live_sum / (double)ticks : 0.0);
                 }
                 return glc_stream_end(ev);

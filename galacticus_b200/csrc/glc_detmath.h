@@ -4,10 +4,14 @@
  * WHY: the reference's RHS nests loose-tolerance iterative solvers (Brent at 1e-2, a fixed-point
  * structure solve at 1e-2, adaptive quadrature at 1e-3).  Their discrete decisions (accept / stop /
  * bisect) flip on last-bit differences, so two implementations that differ only in the rounding of
- * exp/log/pow drift apart at the 1e-3 level on a fraction of nodes.  Built only from IEEE-754 basic
- * operations (+ - * / and bit manipulation; no FMA -- compile with -fmad=false / -ffp-contract=off),
- * these functions return identical bits on the GPU and on the host, which lets the parity tests
- * assert bit-exact agreement between the CUDA path and the CPU checker.
+ * exp/log/pow drift apart at the 1e-3 level on a fraction of nodes.  Built only from correctly rounded
+ * IEEE-754 operations (+ - * / fma and bit manipulation), these functions return identical bits on the
+ * GPU and on the host, which lets the parity tests assert bit-exact agreement between the CUDA path
+ * and the CPU checker.  Fused multiply-adds are EXPLICIT (DM_FMA: fma() is correctly rounded on both
+ * sides -- DFMA on the device, vfmadd on the host with -mfma, glibc's exact fma otherwise); the compilers'
+ * own contraction stays off (-fmad=false / -ffp-contract=off) because each would fuse different pairs.
+ * The polynomial kernels are where a GPU lane spends a quarter of its instructions (profiles/r02c):
+ * fused, a Horner/Estrin step is one dependent instruction instead of two.
  *
  * Accuracy (checked against numpy/glibc in tests/test_detmath.py): exp, log, atan <= 2 ulp;
  * cbrt <= 1 ulp; pow(x,y) relative error <= ~(2 + |y ln x|) ulp.
@@ -36,6 +40,12 @@ typedef union {
     double d;
     unsigned long long u;
 } glc_dm_bits;
+
+#if defined(__CUDACC__)
+#define DM_FMA(a, b, c) fma((a), (b), (c))
+#else
+#define DM_FMA(a, b, c) __builtin_fma((a), (b), (c))
+#endif
 
 GLC_HD double dm_from_bits(unsigned long long u) {
     glc_dm_bits b;
@@ -88,21 +98,21 @@ GLC_HD_BIG double dm_log(double x) {
     s = (m - 1.0) / (m + 1.0);
     z = s * s;
     /* 2 atanh(s) = 2 s (1 + z/3 + z^2/5 + ...): the series without its leading 1, p = z Q(z) with Q of degree 11,
-       evaluated as four interleaved Horner chains in z^4 (Estrin): the same 24 flops as a single Horner chain but a
-       dependency chain of 10 instead of 24 -- these functions run latency-bound on a GPU lane */
+       evaluated as four interleaved Horner chains in z^4 (Estrin) with fused steps: a dependency chain of 7 fused
+       operations instead of 24 -- these functions run latency-bound on a GPU lane */
     {
         const double z2 = z * z, z4 = z2 * z2;
-        const double q0 = ((1.0 / 19.0) * z4 + 1.0 / 11.0) * z4 + 1.0 / 3.0;
-        const double q1 = ((1.0 / 21.0) * z4 + 1.0 / 13.0) * z4 + 1.0 / 5.0;
-        const double q2 = ((1.0 / 23.0) * z4 + 1.0 / 15.0) * z4 + 1.0 / 7.0;
-        const double q3 = ((1.0 / 25.0) * z4 + 1.0 / 17.0) * z4 + 1.0 / 9.0;
-        p = z * ((q0 + z * q1) + z2 * (q2 + z * q3));
+        const double q0 = DM_FMA(DM_FMA(1.0 / 19.0, z4, 1.0 / 11.0), z4, 1.0 / 3.0);
+        const double q1 = DM_FMA(DM_FMA(1.0 / 21.0, z4, 1.0 / 13.0), z4, 1.0 / 5.0);
+        const double q2 = DM_FMA(DM_FMA(1.0 / 23.0, z4, 1.0 / 15.0), z4, 1.0 / 7.0);
+        const double q3 = DM_FMA(DM_FMA(1.0 / 25.0, z4, 1.0 / 17.0), z4, 1.0 / 9.0);
+        p = z * DM_FMA(z2, DM_FMA(z, q3, q2), DM_FMA(z, q1, q0));
     }
     {
         const double two_s = 2.0 * s;
         const double de = (double)e;
         /* log = e ln2_hi + (2s + (2s*p + e ln2_lo)) */
-        return de * ln2_hi + (two_s + (two_s * p + de * ln2_lo));
+        return DM_FMA(de, ln2_hi, two_s + DM_FMA(two_s, p, de * ln2_lo));
     }
 }
 
@@ -117,21 +127,21 @@ GLC_HD_BIG double dm_exp(double x) {
     fk = x * inv_ln2;
     k = (int)(fk + (fk < 0.0 ? -0.5 : 0.5));
     fk = (double)k;
-    r = (x - fk * ln2_hi) - fk * ln2_lo;
+    r = DM_FMA(-fk, ln2_lo, DM_FMA(-fk, ln2_hi, x));
     /* Taylor series of e^r, |r| <= 0.3466, degree 14: e^r = 1 + r (1 + r (1/2 + r Q(r))), Q of degree 11 evaluated
        as four interleaved Horner chains in r^4 (Estrin; dependency chain 16 instead of 30), the three leading terms
        by Horner so that their rounding is as before */
     {
         const double r2 = r * r, r4 = r2 * r2;
-        const double q0 = ((1.0 / 39916800.0) * r4 + 1.0 / 5040.0) * r4 + 1.0 / 6.0;
-        const double q1 = ((1.0 / 479001600.0) * r4 + 1.0 / 40320.0) * r4 + 1.0 / 24.0;
-        const double q2 = ((1.0 / 6227020800.0) * r4 + 1.0 / 362880.0) * r4 + 1.0 / 120.0;
-        const double q3 = ((1.0 / 87178291200.0) * r4 + 1.0 / 3628800.0) * r4 + 1.0 / 720.0;
-        p = (q0 + r * q1) + r2 * (q2 + r * q3);
+        const double q0 = DM_FMA(DM_FMA(1.0 / 39916800.0, r4, 1.0 / 5040.0), r4, 1.0 / 6.0);
+        const double q1 = DM_FMA(DM_FMA(1.0 / 479001600.0, r4, 1.0 / 40320.0), r4, 1.0 / 24.0);
+        const double q2 = DM_FMA(DM_FMA(1.0 / 6227020800.0, r4, 1.0 / 362880.0), r4, 1.0 / 120.0);
+        const double q3 = DM_FMA(DM_FMA(1.0 / 87178291200.0, r4, 1.0 / 3628800.0), r4, 1.0 / 720.0);
+        p = DM_FMA(r2, DM_FMA(r, q3, q2), DM_FMA(r, q1, q0));
     }
-    p = p * r + 0.5;
-    p = p * r + 1.0;
-    p = p * r + 1.0;
+    p = DM_FMA(p, r, 0.5);
+    p = DM_FMA(p, r, 1.0);
+    p = DM_FMA(p, r, 1.0);
     return dm_scale2(p, k);
 }
 
@@ -187,15 +197,15 @@ GLC_HD_BIG double dm_atan(double x) {
     }
     z = ax * ax;
     w = z * z;
-    s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
-    s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+    s1 = z * DM_FMA(w, DM_FMA(w, DM_FMA(w, DM_FMA(w, DM_FMA(w, aT10, aT8), aT6), aT4), aT2), aT0);
+    s2 = w * DM_FMA(w, DM_FMA(w, DM_FMA(w, DM_FMA(w, aT9, aT7), aT5), aT3), aT1);
     if (id < 0) {
-        res = ax - ax * (s1 + s2);
+        res = DM_FMA(-ax, s1 + s2, ax);
         return neg ? -res : res;
     }
     hi = (id == 0) ? atanhi0 : (id == 1) ? atanhi1 : (id == 2) ? atanhi2 : atanhi3;
     lo = (id == 0) ? atanlo0 : (id == 1) ? atanlo1 : (id == 2) ? atanlo2 : atanlo3;
-    res = hi - ((ax * (s1 + s2) - lo) - ax);
+    res = hi - (DM_FMA(ax, s1 + s2, -lo) - ax);
     return neg ? -res : res;
 }
 
@@ -208,8 +218,8 @@ GLC_HD_BIG double dm_cbrt(double x) {
     if (dm_to_bits(a) == 0x7ff0000000000000ULL) return x;
     t = dm_exp(dm_log(a) / 3.0);
     /* two Newton steps on t^3 = a */
-    t = t - (t * t * t - a) / (3.0 * t * t);
-    t = t - (t * t * t - a) / (3.0 * t * t);
+    t = t - DM_FMA(t * t, t, -a) / (3.0 * t * t);
+    t = t - DM_FMA(t * t, t, -a) / (3.0 * t * t);
     return neg ? -t : t;
 }
 

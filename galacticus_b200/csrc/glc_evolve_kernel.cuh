@@ -95,7 +95,8 @@ struct LaneState {
     uint32_t mask;
     int interruptFound, interruptCode, count, inApply, outWritten, yslot, kslot, trial, finalStep;
     int segmentsThisNode, nodeStatus, solveFailed, forbiddenNegatives;
-    unsigned int nAcc, nRej, nRhs, nSeg, nTrialFail, nNodes, nDone, pad;
+    unsigned int nAcc, nRej, nRhs, nSeg, nTrialFail, nNodes, nDone;
+    unsigned int age;  // rate-function evaluations spent on the current node so far (scheduling hint only: oldest nodes first)
     // profileOdeEvolver: largest scaled error of the attempt and the property that has it (standardStepErrorAnalyzer
     // :1210-1219), evolve_apply calls since the last successful one (countEvaluationsToSuccess)
     double profErrMax;
@@ -207,6 +208,7 @@ GLC_DEVICE_INLINE void lane_prepare(LaneState &L, const LaneMem &M, double (&yt)
             L.node = A.order ? A.order[q] : q;
             GLC_LEDGER_FETCH(A, M, L.node);
             L.nNodes++;
+            L.age = 0;
             L.ctx.flags = A.flags[L.node];
             L.tEnd = A.time_end[L.node];
             L.segmentsThisNode = 0;
@@ -374,6 +376,7 @@ GLC_UNROLL_RK
             // ---- standardODEs, part 1
             Model::solve_analytics(L.ctx, L.ts);
             L.nRhs++;  // every call of the derivatives function counts (also the frozen ones past an interrupt)
+            L.age++;
             if (L.interruptFound && L.ts >= L.timeInterruptFirst) {
                 Model::solve_analytics(L.ctx, L.timeInterruptFirst);
                 L.heavy = HV_FROZEN;

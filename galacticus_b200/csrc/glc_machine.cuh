@@ -50,17 +50,19 @@ static_assert(U_RHS_BEGIN == kUnitRhsBegin, "kUnitRhsBegin (glc_common.cuh) must
 typedef ModelStandard MS;
 
 #ifndef GLC_ROOT_STEPS
-#define GLC_ROOT_STEPS 1
+#define GLC_ROOT_STEPS 2  // Brent steps per execution of a root-find unit (measured: 1 -> 2 = -2...-4 % on the 10^6-node pass, 4 = +1 %)
 #endif
 
 // The x^omega table of the adiabatic-contraction function (fastExponentiator, 9 991 doubles = 80 KB) is looked up once per
 // Brent step of the most frequent unit.  Through the read-only global path those look-ups were 11 % of the long-scoreboard
 // samples of a bulk slice (profiles/r02i: the continuation records stream through L1 and evict the table, so most look-ups
-// go to L2).  machine_kernel therefore stages the table in shared memory behind its unit queues (104 KB + 80 KB of 227 KB).
+// go to L2).  With -DGLC_STAGED_POW machine_kernel stages the table in shared memory behind its unit queues (104 KB + 80 KB
+// of 227 KB).  Measured (profiles/r02j_machine_variants.txt): no gain -- the carve-out takes the same 80 KB away from L1, and
+// with two warps per scheduler a warp that no longer waits here waits at its next dependent instruction -- so it is OFF.
 #if defined(__CUDACC__)
 extern __shared__ unsigned int s_qdyn[];  // machine_kernel's dynamic shared memory: [U_IDLE][SLOTS] ring cells, then the table
 #endif
-#if defined(__CUDACC__) && !defined(GLC_NO_STAGED_POW)
+#if defined(__CUDACC__) && defined(GLC_STAGED_POW)
 #define GLC_MACHINE_STAGED_POW 1
 GLC_DEVICE_INLINE const double *machine_pow_ac() {
     return reinterpret_cast<const double *>(s_qdyn + (size_t)U_IDLE * GLC_MSLOTS);  // (13 x 2048 x 4 bytes: 8-byte aligned)
@@ -816,7 +818,7 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
 // remaining steps of the node, (t_end - t) / h with the controller's current step size.  Streaming sessions also list up to
 // `wantFree` free slots (entries tagged kHeldFresh, counted in count[3]) into which the drain kernel fetches queued nodes.
 __global__ void held_list_kernel(const int *__restrict__ unit, const LaneState *__restrict__ L, int nslots, int32_t *held,
-                                 float *score, int *count, int wantFree) {
+                                 float *score, int *count, int wantFree, float ageWeight = 0.0f) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += gridDim.x * blockDim.x) {
         const int u = unit[i];
         if (u == U_RHS_BEGIN) {
@@ -824,13 +826,18 @@ __global__ void held_list_kernel(const int *__restrict__ unit, const LaneState *
             held[k] = i;
             if (score) {
                 const double h = L[i].h, left = L[i].x1 - L[i].x;
-                score[k] = (L[i].heavy == HV_RHS && h > 0.0 && left > 0.0) ? (float)fmin(left / h, 1.0e30) : 0.0f;
+                const float steps = (L[i].heavy == HV_RHS && h > 0.0 && left > 0.0) ? (float)fmin(left / h, 1.0e30) : 0.0f;
+                // ageWeight > 0 (streaming ticks): evaluations already spent on the node count too -- step sizes collapse late,
+                // and a node that has been running for long is the best predictor of a node that will go on running
+                score[k] = ageWeight > 0.0f ? 6.0f * steps + ageWeight * (float)L[i].age : steps;
+                // ageWeight < 0: the component-set bucket of the node (queue_bucket), for lists sorted by kind of node
+                if (ageWeight < 0.0f) score[k] = (float)queue_bucket(L[i].ctx.flags);
             }
         } else if (wantFree > 0 && (u == U_IDLE || u < 0)) {
             if (atomicAdd(count + 3, 1) < wantFree) {
                 const int k = atomicAdd(count, 1);
                 held[k] = i | kHeldFresh;
-                if (score) score[k] = 0.0f;
+                if (score) score[k] = ageWeight < 0.0f ? 64.0f : 0.0f;
             }
         }
     }

@@ -26,7 +26,7 @@ def build(force: bool = False) -> None:
     if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return
     os.makedirs(os.path.dirname(SO), exist_ok=True)
-    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unused",
+    subprocess.run(["g++", "-std=c++17", "-O2", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unused",
                     "-Wno-unknown-pragmas", "-o", SO, src], check=True)
 
 

@@ -610,3 +610,63 @@ extern "C" int emu_forest_evolve_async(void *h, int64_t n_nodes, const int32_t *
     if (counters) *counters = E.total;
     return rc;
 }
+
+// Scheduling analysis (scripts/forest_critical_path.py): the asynchronous scheduler over a VIRTUAL clock with unlimited lanes.
+// Every submitted node starts at once and lasts (its rate-function evaluations) x 1 time unit; poll() returns the node that
+// finishes first.  The makespan is the critical path of the forest in evaluations -- the time the device would need with
+// infinitely many lone lanes, in units of the lone-lane time per evaluation -- and (total evaluations) / makespan is the mean
+// number of nodes the schedule can keep in flight.
+struct EmuClockEngine {
+    void *h;
+    glcf::Forest &F;
+    struct Ev { double finish; int32_t node, status, interrupt; };
+    std::vector<Ev> heap;  // min-heap on finish
+    double now = 0.0, total = 0.0, overhead;
+    int64_t inflight = 0, evolves = 0;
+    EmuClockEngine(void *h_, glcf::Forest &F_, double ov) : h(h_), F(F_), overhead(ov) {}
+    static bool later(const Ev &a, const Ev &b) { return a.finish > b.finish; }
+    void submit(int32_t node, double tend) {
+        double buf[GLC_NPROP];
+        memcpy(buf, F.R(node), sizeof buf);
+        int32_t fl = F.flags[node], st = 0, in = 0;
+        glc_counters c{};
+        int64_t slices = 0;
+        emu_evolve_batch(h, 1, buf, &fl, &tend, &st, &in, &c, 1, 0, 0, 0, &slices);
+        memcpy(F.R(node), buf, sizeof buf);
+        F.flags[node] = fl;
+        heap.push_back(Ev{now + overhead + (double)c.rhs_evaluations, node, st, in});
+        std::push_heap(heap.begin(), heap.end(), later);
+        total += (double)c.rhs_evaluations;
+        inflight++;
+        evolves++;
+    }
+    int64_t in_flight() const { return inflight; }
+    int flush() { return 0; }
+    int poll(std::vector<int32_t> &done, std::vector<int32_t> &st, std::vector<int32_t> &in) {
+        if (heap.empty()) return 0;
+        const double t = heap.front().finish;
+        while (!heap.empty() && heap.front().finish <= t) {
+            std::pop_heap(heap.begin(), heap.end(), later);
+            const Ev e = heap.back();
+            heap.pop_back();
+            done.push_back(e.node); st.push_back(e.status); in.push_back(e.interrupt);
+            inflight--;
+        }
+        now = t;
+        return 0;
+    }
+};
+
+extern "C" int emu_forest_critical_path(void *h, int64_t n_nodes, const int32_t *parent, const double *mass, const double *time,
+                                        const double *scale_radius, const double *angular_momentum, double *records, int32_t *flags,
+                                        int32_t *state, double overhead, double *out3) {
+    Emu *e = (Emu *)h;
+    glcf::Forest F;
+    F.init(&e->params, &e->halo_host, n_nodes, parent, mass, time, scale_radius, angular_momentum, records, flags, state);
+    EmuClockEngine E(h, F, overhead);
+    const int rc = F.run_async(E);
+    out3[0] = E.now;            // makespan = critical path, in evaluations
+    out3[1] = E.total;          // all evaluations
+    out3[2] = (double)E.evolves;
+    return rc;
+}
