@@ -79,6 +79,7 @@ glc_params = _parse_struct(_SRC, "glc_params")
 glc_counters = _parse_struct(_SRC, "glc_counters")
 glc_forest_counters = _parse_struct(_SRC, "glc_forest_counters")
 glc_profile = _parse_struct(_SRC, "glc_profile")
+glc_error_report = _parse_struct(_SRC, "glc_error_report")
 
 GLC_ABI_VERSION = int(re.search(r"#define\s+GLC_ABI_VERSION\s+(\d+)", _SRC).group(1))
 NPROP = ENUMS["GLC_NPROP"]

@@ -241,6 +241,83 @@ __global__ void rhs_kernel(KernelArgs A, double *dydt) {
     AR(GLC_P_BASIC_MASS) = ctx.basicMass;
 }
 
+// standardErrorHandler's table for ONE node (glc_error_report_node): one warp, lane 0 carries the node (the rate function is
+// warp-synchronous).  State = the record after the pre-evolve hooks; dy/dt = the evaluation at the node's time (k1); yError =
+// the embedded error of one Cash-Karp step of size h (rkck.c: h * sum ec_i k_i), with the stage inputs built as
+// lane_prepare builds them.  out: [7][NY] = y, dydt, scale, tolerance, error, error_scaled, active; then the interrupt code.
+template <class Model>
+__global__ void error_report_kernel(KernelArgs A, double h, double *out) {
+    const bool on = threadIdx.x == 0;
+    auto AR = [&](int prop) -> double & { return A.props[(int64_t)prop * A.cap]; };
+    NodeCtx ctx;
+    double y0[NY], yt[NY], rate[NY], s[NY], k[6][NY];
+    for (int i = 0; i < NY; i++) {
+        y0[i] = AR(i);
+        s[i] = 0.0;
+    }
+    ctx.flags = A.flags[0];
+    ctx.massTarget = AR(GLC_P_MASS_TARGET);
+    ctx.massRate = AR(GLC_P_MASS_RATE);
+    ctx.timeTarget = AR(GLC_P_TIME_TARGET);
+    ctx.scaleTarget = AR(GLC_P_DMSCALE_TARGET);
+    ctx.scaleRate = AR(GLC_P_DMSCALE_RATE);
+    ctx.spinTarget = AR(GLC_P_SPIN_TARGET);
+    ctx.spinRate = AR(GLC_P_SPIN_RATE);
+    ctx.timeLastIsolated = AR(GLC_P_TIME_LAST_ISOLATED);
+    ctx.diskRadius = AR(GLC_P_DISK_RADIUS);
+    ctx.diskVelocity = AR(GLC_P_DISK_VELOCITY);
+    ctx.sphRadius = AR(GLC_P_SPH_RADIUS);
+    ctx.sphVelocity = AR(GLC_P_SPH_VELOCITY);
+    ctx.basicMass = AR(GLC_P_BASIC_MASS);
+    ctx.dmScale = AR(GLC_P_DMSCALE);
+    ctx.spinJ = AR(GLC_P_SPIN);
+    ctx.massBaryonicSubhalos = AR(GLC_P_MASS_BARYONIC_SUBHALOS);
+    ctx.numericsFailed = 0;
+    const double t0 = AR(GLC_P_TIME);
+    ctx.timeNode = t0;
+    Model::pre_evolve(ctx, y0);
+    const uint32_t mask = Model::active_mask(ctx.flags);
+    Model::scales(ctx, y0, s);
+    int codeFirst = GLC_INT_NONE;
+#pragma unroll 1
+    for (int stage = 0; stage < 6; stage++) {
+        const double ts = t0 + c_rk_a[stage] * h;
+        if (stage == 0) {
+            for (int i = 0; i < NY; i++) yt[i] = y0[i];
+        } else if (stage == 1) {
+            const double b10 = c_rk_b[1][0];
+            for (int i = 0; i < NY; i++) yt[i] = y0[i] + b10 * h * k[0][i];
+        } else {
+            for (int i = 0; i < NY; i++) {
+                double acc = c_rk_b[stage][0] * k[0][i];
+                for (int j = 1; j < stage; j++) acc += c_rk_b[stage][j] * k[j][i];
+                yt[i] = y0[i] + h * acc;
+            }
+        }
+        for (int i = 0; i < NY; i++) rate[i] = 0.0;
+        Model::solve_analytics(ctx, ts);
+        const int code = Model::rates(ctx, ts, yt, rate, false, on);
+        if (stage == 0) codeFirst = code;
+        for (int i = 0; i < NY; i++) k[stage][i] = ((mask & (1u << i)) && code == GLC_INT_NONE) ? rate[i] : 0.0;
+    }
+    if (!on) return;
+    const double epsAbs = GLC_PARAMS.odeToleranceAbsolute, epsRel = GLC_PARAMS.odeToleranceRelative;
+    for (int i = 0; i < NY; i++) {
+        const bool active = (mask & (1u << i)) != 0;
+        const double yerr = h * (c_rk_b[0][0] * k[0][i] + c_rk_b[0][2] * k[2][i] + c_rk_b[0][3] * k[3][i] + c_rk_b[0][4] * k[4][i] +
+                                 c_rk_b[0][5] * k[5][i]);
+        const double tol = epsRel * fabs(y0[i]) + epsAbs * s[i];
+        out[0 * NY + i] = active ? y0[i] : 0.0;
+        out[1 * NY + i] = active ? k[0][i] : 0.0;
+        out[2 * NY + i] = active ? s[i] : 0.0;
+        out[3 * NY + i] = active ? tol : 0.0;
+        out[4 * NY + i] = active ? yerr : 0.0;
+        out[5 * NY + i] = active ? fabs(yerr) / tol : 0.0;
+        out[6 * NY + i] = active ? 1.0 : 0.0;
+    }
+    out[7 * NY] = (double)codeFirst;
+}
+
 // FP64 FMA-chain microbenchmark (16 independent chains per thread): the measured FP64 roofline denominator
 __global__ void fp64_peak_kernel(double *out, int iters) {
     double a[16];
@@ -1495,6 +1572,55 @@ int glc_evolve_batch(glc_evolver *ev, int64_t n, double *props, int32_t *flags, 
     }
     if (rc) return rc;
     return glc_arena_download(ev, n, props, flags, status, interrupt);
+}
+
+int glc_error_report_node(glc_evolver *ev, const double *record, int32_t flags, double time_step, glc_error_report *out) {
+    if (!ev || !record || !out) return -1;
+    if (!ev->params_set) return -9;
+    if (ev->stream_active) {
+        ev->err = "glc_error_report_node: a streaming session owns the arena";
+        return GLC_ERR_BUSY;
+    }
+    cudaSetDevice(ev->device);
+    std::vector<double> row(record, record + NPROP);
+    const double te = 0.0;
+    int rc = glc_arena_upload(ev, 1, row.data(), &flags, &te);
+    if (rc) return rc;
+    if (!ev->d_dydt) GLC_CHECK(ev, cudaMalloc(&ev->d_dydt, sizeof(double) * NY * ev->cap));
+    rc = upload_constants(ev);
+    if (rc) return rc;
+    double *d_out = nullptr;
+    GLC_CHECK(ev, cudaMalloc(&d_out, sizeof(double) * (7 * NY + 1)));
+    KernelArgs A{};
+    A.props = ev->d_props;
+    A.flags = ev->d_flags;
+    A.cap = ev->cap;
+    A.n = 1;
+    if (ev->params.model == GLC_MODEL_BOX)
+        error_report_kernel<ModelBox><<<1, 32, 0, ev->stream>>>(A, time_step, d_out);
+    else
+        error_report_kernel<ModelStandard><<<1, 32, 0, ev->stream>>>(A, time_step, d_out);
+    ev->launches++;
+    double h[7 * NY + 1];
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, ev->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ev->stream);
+    cudaFree(d_out);
+    GLC_CHECK(ev, e);
+    memset(out, 0, sizeof(*out));
+    out->time = record[GLC_P_TIME];
+    out->time_step = time_step;
+    for (int i = 0; i < NY; i++) {
+        out->y[i] = h[0 * NY + i];
+        out->dydt[i] = h[1 * NY + i];
+        out->scale[i] = h[2 * NY + i];
+        out->tolerance[i] = h[3 * NY + i];
+        out->error[i] = h[4 * NY + i];
+        out->error_scaled[i] = h[5 * NY + i];
+        out->active[i] = h[6 * NY + i] != 0.0 ? 1 : 0;
+    }
+    out->interrupt = (int32_t)h[7 * NY];
+    return 0;
 }
 
 int glc_rhs_batch(glc_evolver *ev, int64_t n, double *props, const int32_t *flags, double *dydt,

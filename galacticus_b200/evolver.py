@@ -177,6 +177,19 @@ class Evolver:
         self._check(self.L.glc_profiler_read(self.h, C.byref(pr)), "glc_profiler_read")
         return abi.profile_dict(pr)
 
+    def error_report_node(self, record, flag, time_step):
+        """standardErrorHandler's "ODE system parameters" table for one node (glc_error_report_node) as a dict of [NY] arrays."""
+        rep = abi.glc_error_report()
+        row = np.ascontiguousarray(record, dtype=np.float64)
+        self.L.glc_error_report_node.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(np.float64), C.c_int32, C.c_double,
+                                                 C.POINTER(abi.glc_error_report)]
+        self.L.glc_error_report_node.restype = C.c_int
+        self._check(self.L.glc_error_report_node(self.h, row, int(flag), float(time_step), C.byref(rep)), "glc_error_report_node")
+        f = lambda a: np.array(a[:], dtype=np.float64)  # noqa: E731
+        return {"y": f(rep.y), "dydt": f(rep.dydt), "scale": f(rep.scale), "tolerance": f(rep.tolerance), "error": f(rep.error),
+                "error_scaled": f(rep.error_scaled), "active": np.array(rep.active[:], dtype=np.int32), "interrupt": int(rep.interrupt),
+                "time": float(rep.time), "time_step": float(rep.time_step)}
+
     def profiler_reset(self) -> None:
         self._check(self.L.glc_profiler_reset(self.h), "glc_profiler_reset")
 

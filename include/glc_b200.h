@@ -422,6 +422,22 @@ int glc_stream_end(glc_evolver *ev);
 int glc_profiler_read(glc_evolver *ev, glc_profile *out);
 int glc_profiler_reset(glc_evolver *ev);
 
+/* replaces: standardErrorHandler (node_evolver/standard.F90:1063-1140) with standardODEStepTolerances (:1142-1158): the
+ * "ODE system parameters" table the reference prints for a node whose evolution failed on its last trial (the node comes
+ * back with GLC_STATUS_UNDERFLOW at its saved values).  Per property: y, dy/dt at the node's time (standardODEs), yScale
+ * (propertyScalesActive), yTolerance = odeToleranceRelative |y| + odeToleranceAbsolute yScale, yError and
+ * |yError| / yTolerance.  The reference reads yError from the failed solver (solver_%errors); the batched solver keeps no
+ * state of a failed node, so yError is the embedded Cash-Karp error estimate of ONE step of size time_step from the
+ * node's state after the pre-evolve hooks (pass the step to be diagnosed, e.g. the record's GLC_P_TIME_STEP).
+ * active[i] = 0 for properties that are not part of the node's ODE system (their other entries are 0). */
+typedef struct glc_error_report {
+    double time, time_step;
+    int32_t active[GLC_NY];
+    double y[GLC_NY], dydt[GLC_NY], scale[GLC_NY], tolerance[GLC_NY], error[GLC_NY], error_scaled[GLC_NY];
+    int32_t interrupt, pad; /* functionInterrupt raised by the evaluation at the node's time (enum glc_interrupt), if any */
+} glc_error_report;
+int glc_error_report_node(glc_evolver *ev, const double *record, int32_t flags, double time_step, glc_error_report *out);
+
 /* one evaluation of the RHS (standardODEs) for each node, for unit-level parity tests:
  *   dydt [n][GLC_NY] host out; props/flags are not modified except radii warm starts. */
 int glc_rhs_batch(glc_evolver *ev, int64_t n, double *props, const int32_t *flags,

@@ -275,6 +275,9 @@ contains
        call b200NodeScatter(self,nodes(i)%node,props(:,i),flags(i))
        ! glc_status values ARE the errorStatus* codes (source/error/_module.F90:66-75): no translation.
        status     (i)=int(statusDevice(i))
+       ! A node that failed on its last trial comes back at its saved values: print what standardErrorHandler prints
+       ! (node_evolver/standard.F90:1063-1140).
+       if (statusDevice(i) == GLC_STATUS_UNDERFLOW) call b200ErrorReport(self,nodes(i)%node,props(:,i),flags(i))
        interrupted(i)=interruptDevice(i) /= GLC_INT_NONE
        select case (interruptDevice(i))
        case (GLC_INT_NONE           )
@@ -291,6 +294,55 @@ contains
     end do
     return
   end subroutine b200EvolveBatch
+
+  subroutine b200ErrorReport(self,node,record,flags)
+    !!{RST
+    The "ODE system parameters" table of ``standardErrorHandler`` (``node_evolver/standard.F90:1063-1140``) for a node
+    whose evolution failed, from ``glc_error_report_node``.
+    !!}
+    use :: Display           , only : displayIndent, displayMessage, displayUnindent
+    use :: ISO_Varying_String, only : varying_string, assignment(=), operator(//)
+    use :: Galacticus_Nodes  , only : propertyTypeActive
+    implicit none
+    class           (mergerTreeNodeEvolverB200), intent(inout)               :: self
+    type            (treeNode                 ), intent(inout)               :: node
+    real            (c_double                 ), intent(in   ), dimension(:) :: record
+    integer         (c_int32_t                ), intent(in   )               :: flags
+    type            (glcErrorReport           )                              :: report
+    type            (varying_string           )                              :: message
+    character       (len=12                   )                              :: label
+    integer                                                                  :: i, j, statusCall
+
+    statusCall=glc_error_report_node(self%evolver,record,flags,record(GLC_P_TIME_STEP+1),report)
+    if (statusCall /= 0) return
+    call node%serializeASCII()
+    write (label,'(e12.6)') report%time
+    message="time, timeStep = "//label
+    write (label,'(e12.6)') report%time_step
+    message=message//", "//label
+    call displayMessage(message)
+    call displayIndent('ODE system parameters')
+    call displayMessage(' : y            : dy/dt        : yScale       : yError       : yErrorScaled')
+    j=0
+    do i=1,GLC_NY
+       if (report%active(i) == 0) cycle
+       j=j+1
+       message=node%nameFromIndex(j,propertyTypeActive)
+       write (label,'(e12.6)') report%y           (i)
+       message=message//" : "//label
+       write (label,'(e12.6)') report%dydt        (i)
+       message=message//" : "//label
+       write (label,'(e12.6)') report%scale       (i)
+       message=message//" : "//label
+       write (label,'(e12.6)') report%error       (i)
+       message=message//" : "//label
+       write (label,'(e12.6)') report%error_scaled(i)
+       message=message//" : "//label
+       call displayMessage(message)
+    end do
+    call displayUnindent('done')
+    return
+  end subroutine b200ErrorReport
 
   subroutine b200NodeGather(self,node,record,flags)
     !!{RST

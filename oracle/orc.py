@@ -122,6 +122,20 @@ class Oracle:
         self.L.orc_profiler_read(C.byref(pr))
         return abi.profile_dict(pr)
 
+    def error_report(self, record, flag, time_step):
+        """standardErrorHandler's table (orc_error_report): dict of [NY] arrays y, dydt, scale, tolerance, error, error_scaled,
+        active, and the interrupt code of the evaluation at the node's time."""
+        out = np.zeros(7 * abi.NY, dtype=np.float64)
+        code = C.c_int(0)
+        row = np.ascontiguousarray(record, dtype=np.float64).copy()
+        self.L.orc_error_report.argtypes = [C.POINTER(abi.glc_params), C.c_void_p, np.ctypeslib.ndpointer(np.float64), C.c_int,
+                                            C.c_double, np.ctypeslib.ndpointer(np.float64), C.POINTER(C.c_int)]
+        self.L.orc_error_report.restype = C.c_int
+        self.L.orc_error_report(C.byref(self.params), self.T, row, int(flag), float(time_step), out, C.byref(code))
+        o = out.reshape(7, abi.NY)
+        return {"y": o[0], "dydt": o[1], "scale": o[2], "tolerance": o[3], "error": o[4], "error_scaled": o[5],
+                "active": o[6].astype(np.int32), "interrupt": code.value}
+
     def rhs(self, props_row, flag):
         dydt = np.zeros(abi.NY, dtype=np.float64)
         code = C.c_int(0)

@@ -318,3 +318,60 @@ int orc_rhs_node(const glc_params *P, const orc_tables *T, double *props, int fl
     *interrupt = orc_model_rates(&c, props[GLC_P_TIME], dydt);
     return 0;
 }
+
+/* standardErrorHandler (node_evolver/standard.F90:1063-1140) + standardODEStepTolerances (:1142-1158): the "ODE system
+   parameters" table of a node, restated for glc_error_report_node: y, dy/dt at the node's time, yScale, yTolerance, and as
+   yError the embedded error of one Cash-Karp step of size h from the node's state after the pre-evolve hooks (the reference
+   reads the failed solver's own estimate; a batch interface has no such state).  out7: [7][GLC_NY] = y, dydt, scale,
+   tolerance, error, error_scaled, active. */
+int orc_error_report(const glc_params *P, const orc_tables *T, const double *record, int flags, double h, double *out7,
+                     int *interrupt) {
+    orc_evolve_ctx c;
+    orc_ode_solver solver;
+    double props[GLC_NPROP], y[GLC_NY], y0[GLC_NY], scale[GLC_NY], scale_by_prop[GLC_NY], yerr[GLC_NY], k1[GLC_NY], out[GLC_NY];
+    int nonneg[GLC_NY];
+    int i, st;
+    memcpy(props, record, sizeof props);
+    memset(&c, 0, sizeof(c));
+    c.P = P;
+    c.T = T;
+    c.p = props;
+    c.flags = flags;
+    c.solver = &solver;
+    *interrupt = GLC_INT_NONE;
+    orc_model_pre_evolve(&c);
+    c.n_active = orc_model_active_list(&c, c.active);
+    for (i = 0; i < c.n_active; i++) {
+        y[i] = props[c.active[i]];
+        y0[i] = y[i];
+        nonneg[i] = 0;
+    }
+    for (i = 0; i < GLC_NY; i++) scale_by_prop[i] = 0.0;
+    orc_model_scales(&c, scale_by_prop);
+    for (i = 0; i < c.n_active; i++) scale[i] = scale_by_prop[c.active[i]];
+    orc_ode_init(&solver, (size_t)c.n_active, standard_odes, &c, P->odeToleranceAbsolute, P->odeToleranceRelative, scale, nonneg,
+                 standard_post_step);
+    c.scale = scale;
+    for (i = 0; i < 7 * GLC_NY; i++) out7[i] = 0.0;
+    st = standard_odes(props[GLC_P_TIME], y, k1, &c);
+    if (st == ORC_GSL_EBADFUNC) *interrupt = c.interrupt_first_code;
+    /* one embedded step; a frozen system past an interrupt gives zero rates, as on the device */
+    for (i = 0; i < c.n_active; i++) {
+        y[i] = y0[i];
+        yerr[i] = 0.0;
+    }
+    (void)out;
+    orc_rkck_apply(&solver, record[GLC_P_TIME], h, y, yerr, k1, NULL);
+    for (i = 0; i < c.n_active; i++) {
+        const int pidx = c.active[i];
+        const double tol = P->odeToleranceRelative * fabs(y0[i]) + P->odeToleranceAbsolute * scale[i];
+        out7[0 * GLC_NY + pidx] = y0[i];
+        out7[1 * GLC_NY + pidx] = k1[i];
+        out7[2 * GLC_NY + pidx] = scale[i];
+        out7[3 * GLC_NY + pidx] = tol;
+        out7[4 * GLC_NY + pidx] = yerr[i];
+        out7[5 * GLC_NY + pidx] = fabs(yerr[i]) / tol;
+        out7[6 * GLC_NY + pidx] = 1.0;
+    }
+    return 0;
+}

@@ -69,6 +69,8 @@ int orc_evolve_batch(const glc_params *P, const orc_tables *T, long n, double *p
 void orc_apply_interrupt(const glc_params *P, double *props, int *flags, int code);
 
 /* one RHS evaluation (standardODEs) at the record's own time; dydt[GLC_NY] indexed by property */
+int orc_error_report(const glc_params *P, const orc_tables *T, const double *record, int flags, double h, double *out7,
+                     int *interrupt);
 int orc_rhs_node(const glc_params *P, const orc_tables *T, double *props, int flags, double *dydt,
                  int *interrupt);
 
