@@ -49,8 +49,11 @@ UNIT = "accepted RKCK node-ODE steps/s"
 # machine_kernel and drain_kernel launch of one whole pass divided by the pass's RHS counter (ncu,
 # profiles/r01f_fp64_ops_whole_pass.txt: 2.217e11 / 13 693 801).
 FLOP_PER_RHS = 16.2e3
-# DRAM bytes per evaluation, ncu --set full of one bulk slice of machine_kernel (profiles/)
-DRAM_BYTES_PER_RHS = (74.277716e9 + 43.909916e9) / 7702358.0
+# DRAM bytes per evaluation from the ncu --set full captures of the final round-2 build: machine_kernel = second bulk slice
+# (profiles/r02r_machine_kernel_bulk_slice.txt: 45.68 + 24.09 GB over the slice's 5 665 006 evaluations); drain_kernel = the
+# last, one-node-per-warp pass (profiles/r02r_drain_kernel_lone_lane_pass.txt: 1.77 MB over ~2.5e4 evaluations -- the drain
+# works out of L1/L2)
+DRAM_BYTES_PER_RHS = {"machine_kernel": (45.677725e9 + 24.085883e9) / 5665006.0, "drain_kernel": (1.673216e6 + 0.096e6) / 2.5e4}
 N_Y = 24
 BLACK_HOLE_FRACTION = 0.7
 MW_ROOT_MASS, MW_RESOLUTION = 1.52e12, 1.0e9  # testSuite/parameters/benchmark_milkyWay.xml:30-42
@@ -402,6 +405,7 @@ def main():
             kernels[name] = {"ms_per_pass": ms_k, "share_of_pass": ms_k / (ph["machine_ms"] + ph["drain_ms"]),
                              "rhs_evaluations": ph[key + "_rhs"], "accepted_steps": ph[key + "_steps"], "nodes_finished": ph[key + "_nodes"],
                              "rhs_per_s": ph[key + "_rhs"] / (ms_k * 1e-3),
+                             "traffic": DRAM_BYTES_PER_RHS.get(name, 0.0) * ph[key + "_rhs"],
                              "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak},
                              "fp64": {"achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (tfl / fp64_peak) if fp64_peak else None}}
         dominant = max(kernels, key=lambda k: kernels[k]["ms_per_pass"]) if kernels else "machine_kernel"
@@ -431,7 +435,7 @@ def main():
             },
             "roofline": {"bound": "hbm", "achieved": dk["hbm"]["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": dk["hbm"]["frac"],
                          # DRAM traffic of that kernel: ncu --set full capture (bytes per evaluation, profiles/) x its evaluations
-                         "traffic": DRAM_BYTES_PER_RHS * dk["rhs_evaluations"],
+                         "traffic": DRAM_BYTES_PER_RHS.get(dominant, 0.0) * dk["rhs_evaluations"],
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
                          "kernel": dominant,
                          "note": "the path is FP64-ALU / latency bound (SURVEY 8d: >15 flop per algorithmic byte): see roofline_fp64 "

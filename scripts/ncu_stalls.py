@@ -17,7 +17,7 @@ for l in sym.splitlines():
         funcs.append((int(f[1], 16), int(f[2], 0), f[6], f[7]))
 base = int(data[0][col["Address"]], 16)
 # the kernel entry symbol has value 0 in its section; choose section of the symbol whose name contains 'machine_kernel' or 'evolve_kernel'
-target = "machine_kernel" if "machine" in kname else "evolve_kernel"
+target = "machine_kernel" if "machine" in kname else ("drain_kernel" if "drain" in kname else "evolve_kernel")
 for v, sz, sec, name in funcs:
     if target in name and ("ModelStandard" in name or "machine" in name): ksec = sec
 regions = sorted([(v, sz, name) for v, sz, sec, name in funcs if sec == ksec])
