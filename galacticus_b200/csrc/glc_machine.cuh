@@ -561,6 +561,27 @@ GLC_DEVICE_INLINE bool machine_step(const SlotRef &S, const LaneMem &M) {
     return true;
 }
 
+// Start of a time slice: the pending unit of a slot, after re-arming what must be re-armed.  Shared by machine_kernel and
+// the host-driven machine of tests/emu (the stale-slot defect of round 2 lived in exactly this code).
+//   * first slice of a batch / session: every slot is reset;
+//   * idle slot: back to the node queue, which may have grown since the last slice;
+//   * not a unit (-1): the slot was finished by drain_kernel in an earlier hand-over and is free.  The lane state in memory is
+//     the STALE copy the drain kernel loaded (heavy == HV_RHS: unit_rk would digest an evaluation that never ran and evolve
+//     the old node a second time), so the slot is reset completely, not just re-armed like an idle one.
+GLC_DEVICE_INLINE int machine_rearm(const SlotRef &own, bool resume) {
+    if (!resume) slot_reset(own);
+    if (own.unit == U_IDLE) {
+        own.L.phase = PH_FETCH;
+        own.unit = U_RK;
+    }
+    int u = own.unit;
+    if (u < 0 || u > U_IDLE) {
+        slot_reset(own);
+        u = U_RK;
+    }
+    return u;
+}
+
 #if defined(__CUDACC__)
 // Persistent time-sliced kernel.  One block per SM owns SLOTS slots.  Scheduling is barrier-free: the block keeps
 // one ring-buffer queue per unit type in shared memory; a warp pops up to 32 slots that all wait for the SAME unit
@@ -615,19 +636,7 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
     for (int k = 0; k < PER; k++) {
         const int s = tid + k * THREADS;
         const SlotRef own = slot_ref(slots, base + s);
-        if (!A.resume) slot_reset(own);
-        if (own.unit == U_IDLE) {  // the queue may have grown since the last slice
-            own.L.phase = PH_FETCH;
-            own.unit = U_RK;
-        }
-        int u = own.unit;
-        if (u < 0 || u > U_IDLE) {
-            // finished by the drain kernel (-1) in an earlier hand-over: free.  The lane state in memory is the STALE copy the
-            // drain kernel loaded (heavy == HV_RHS: unit_rk would digest an evaluation that never ran and evolve the old node
-            // again), so the slot is reset completely, not just re-armed like an idle one
-            slot_reset(own);
-            u = U_RK;
-        }
+        const int u = machine_rearm(own, A.resume != 0);
         if (A.hold && u == U_RHS_BEGIN)
             atomicAdd(&s_idle, 1);  // held at an RK boundary for the drain kernel: out of work as far as this block goes
         else

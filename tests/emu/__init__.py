@@ -96,6 +96,22 @@ class EmuEvolver:
         self.slices = s.value
         return status, interrupt, abi.counters_dict(c)
 
+    def stream_session(self, props, flags, time_end, chunk, pattern, lane_budget=6, machine_budget=5):
+        """A streaming session with adaptive ticks on the host (emu_stream_session): nodes submitted in chunks, after each chunk
+        the ticks of `pattern` ('M' = machine slice, 'L' = lane pass with refill), finished by the machine.  Returns
+        (rc, status, interrupt, counters); rc 0 = every node written back exactly once."""
+        n = props.shape[0]
+        status = np.zeros(n, dtype=np.int32)
+        interrupt = np.zeros(n, dtype=np.int32)
+        c = abi.glc_counters()
+        te = np.ascontiguousarray(time_end, dtype=np.float64)
+        self.L.emu_stream_session.argtypes = [C.c_void_p, C.c_int64, _dp, _ip, _dp, _ip, _ip, C.POINTER(abi.glc_counters),
+                                              C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int]
+        self.L.emu_stream_session.restype = C.c_int
+        rc = self.L.emu_stream_session(self.h, n, props, flags, te, status, interrupt, C.byref(c), self.nslots, int(chunk),
+                                       pattern.encode(), int(lane_budget), int(machine_budget))
+        return rc, status, interrupt, abi.counters_dict(c)
+
     def profiler_read(self):
         pr = abi.glc_profile()
         assert self.L.emu_profiler_read(self.h, C.byref(pr)) == 0

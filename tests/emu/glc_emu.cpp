@@ -184,11 +184,7 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
     for (;;) {
         for (int s = 0; s < nslots; s++) {
             const SlotRef S = slot_ref(slots, s);
-            if (!A.resume) slot_reset(S);
-            if (S.unit == U_IDLE) {
-                S.L.phase = PH_FETCH;
-                S.unit = U_RK;
-            }
+            S.unit = machine_rearm(S, A.resume != 0);  // the kernel's own slice-start code
         }
         for (int it = 0; it < A.budget; ++it) {
             bool any = false;
@@ -312,6 +308,176 @@ static void run_machine(Emu *e, int64_t n, double *props, int32_t *flags, const 
     }
 }
 
+// A streaming session as the product's adaptive ticks run it (glc_api.cu stream_tick), on the host: nodes are submitted in
+// chunks; a tick is a machine slice ('M': a few unit executions per slot) or a lane pass ('L': every occupied slot is brought
+// to an RK boundary, then drain lanes take the held slots AND free slots for queued nodes -- drainRefill -- run a bounded
+// number of evaluations and park); the session is finished by the machine.  Exercises what the batch path never does: slots
+// that go machine -> drain -> machine, slots released by the drain (stale lane state), refill from a growing queue.
+static int run_stream_session(Emu *e, int64_t n, double *props, int32_t *flags, const double *time_end, int32_t *status,
+                              int32_t *interrupt, glc_counters *counters, int nslots, int chunk, const char *pattern, int lane_budget,
+                              int machine_budget) {
+    const int64_t cap = n;
+    std::vector<double> soa((size_t)NPROP * cap);
+    for (int64_t i = 0; i < n; i++)
+        for (int p = 0; p < NPROP; p++) soa[(size_t)p * cap + i] = props[i * NPROP + p];
+    std::vector<double> ws((size_t)WS_NVEC * NY * nslots);
+    std::vector<LaneState> sL(nslots);
+    std::vector<RhsState> sR(nslots);
+    std::vector<RootState> sRoot(nslots);
+    std::vector<double> sYt((size_t)nslots * NY);
+    std::vector<QagState> sQ(nslots);
+    std::vector<int> sUnit(nslots);
+    {
+        std::mt19937 g(424242u);
+        auto poison = [&](void *ptr, size_t bytes) {
+            unsigned char *b = (unsigned char *)ptr;
+            for (size_t i = 0; i < bytes; i++) b[i] = (unsigned char)(g() & 0xff);
+        };
+        poison(sL.data(), sL.size() * sizeof(LaneState));
+        poison(sR.data(), sR.size() * sizeof(RhsState));
+        poison(sRoot.data(), sRoot.size() * sizeof(RootState));
+        poison(sYt.data(), sYt.size() * sizeof(double));
+        poison(sQ.data(), sQ.size() * sizeof(QagState));
+        poison(sUnit.data(), sUnit.size() * sizeof(int));
+        poison(ws.data(), ws.size() * sizeof(double));
+    }
+    SlotArrays slots{sL.data(), sR.data(), sRoot.data(), sYt.data(), sQ.data(), sUnit.data()};
+    for (int64_t i = 0; i < n; i++) status[i] = GLC_STATUS_PENDING;
+    int work = 0;
+    unsigned long long hc[8] = {0};
+    KernelArgs A{};
+    A.props = soa.data();
+    A.flags = flags;
+    A.time_end = time_end;
+    A.status = status;
+    A.interrupt = interrupt;
+    A.cap = cap;
+    A.n = 0;
+    A.ws = ws.data();
+    A.nslots = nslots;
+    A.work_counter = &work;
+    A.counters = hc;
+    A.order = nullptr;
+    A.resume = 0;
+    A.slotL = sL.data();
+    A.slotYt = sYt.data();
+    A.slotUnit = sUnit.data();
+    std::mt19937 rng(777);
+    std::vector<int> perm(nslots);
+    for (int s = 0; s < nslots; s++) perm[s] = s;
+    auto tally_slots = [&]() {
+        for (int s = 0; s < nslots; s++) {
+            LaneState &L = sL[s];
+            hc[0] += L.nAcc; hc[1] += L.nRej; hc[2] += L.nRhs; hc[3] += L.nSeg; hc[4] += L.nTrialFail; hc[5] += L.nNodes; hc[6] += L.nDone;
+            L.nAcc = L.nRej = L.nRhs = L.nSeg = L.nTrialFail = L.nNodes = L.nDone = 0;
+        }
+    };
+    // one machine time slice: `budget` unit executions per slot at most; hold = slots stop at the next RK boundary
+    auto machine_slice = [&](int budget, bool hold) {
+        for (int s = 0; s < nslots; s++) {
+            const SlotRef S = slot_ref(slots, s);
+            S.unit = machine_rearm(S, A.resume != 0);
+        }
+        for (int it = 0; it < budget; ++it) {
+            bool any = false;
+            std::shuffle(perm.begin(), perm.end(), rng);
+            for (int p = 0; p < nslots; p++) {
+                const int s = perm[p];
+                const SlotRef S = slot_ref(slots, s);
+                if (hold && S.unit == U_RHS_BEGIN) continue;
+                LaneMem M{&A, A.ws + (int64_t)s * (WS_NVEC * NY), 1};
+                any |= machine_step(S, M);
+            }
+            if (!any) break;
+        }
+        tally_slots();
+        A.resume = 1;
+    };
+    bool laneMode = false;  // every occupied slot stands at an RK boundary (the previous tick was a lane pass)
+    auto lane_pass = [&]() {
+        // entering lane mode: hold slices bring every occupied slot to an RK boundary (idle slots fetch queued nodes on the
+        // way, as on the device); in lane mode newly submitted nodes are fetched by the drain lanes into free slots
+        for (int guard = 0; !laneMode && guard < 100000; guard++) {
+            machine_slice(1, true);
+            bool mid = false;
+            for (int s = 0; s < nslots; s++) mid |= (sUnit[s] >= 0 && sUnit[s] != U_IDLE && sUnit[s] != U_RHS_BEGIN);
+            if (!mid) break;
+        }
+        laneMode = true;
+        const int queued = std::max(0, A.n - std::min(work, A.n));
+        std::vector<int32_t> held;
+        int fresh = 0;
+        for (int s = 0; s < nslots; s++) {
+            if (sUnit[s] == U_RHS_BEGIN)
+                held.push_back(s);
+            else if ((sUnit[s] == U_IDLE || sUnit[s] < 0) && fresh < queued) {
+                held.push_back(s | kHeldFresh);
+                fresh++;
+            }
+        }
+        if (held.empty()) return;
+        std::shuffle(held.begin(), held.end(), rng);
+        int cursor = 0;
+        A.held = held.data();
+        A.nheld = (int)held.size();
+        A.held_counter = &cursor;
+        A.drainRefill = 1;
+        A.drainLanes = 0;
+        const int nl = 9;
+        std::vector<LaneState> dl(nl);
+        std::vector<LaneMem> dm(nl, LaneMem{&A, A.ws, 1});
+        std::vector<std::array<double, NY>> dyt(nl);
+        std::vector<char> fr(nl, 0);
+        std::vector<int> hs(nl, -1);
+        unsigned int tot[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int l = 0; l < nl; l++) lane_reset(dl[l]);
+        for (int it = 0; it < lane_budget; it++) {
+            bool any = false;
+            for (int l = 0; l < nl; l++) {
+                bool f = fr[l] != 0;
+                double(&y)[NY] = *reinterpret_cast<double(*)[NY]>(dyt[l].data());
+                any |= drain_iterate<ModelStandard>(dl[l], dm[l], A, y, f, hs[l], tot, true);
+                fr[l] = f ? 1 : 0;
+            }
+            if (!any) break;
+        }
+        for (int l = 0; l < nl; l++) {
+            double(&y)[NY] = *reinterpret_cast<double(*)[NY]>(dyt[l].data());
+            drain_park<ModelStandard>(dl[l], dm[l], A, y, fr[l] != 0, hs[l], tot);
+        }
+        for (int k = 0; k < 7; k++) hc[k] += tot[k];
+        A.drainRefill = 0;
+    };
+    for (int64_t first = 0; first < n; first += chunk) {
+        A.n = (int)std::min<int64_t>(n, first + chunk);
+        for (const char *t = pattern; *t; t++) {
+            if (*t == 'M') {
+                machine_slice(machine_budget, false);
+                laneMode = false;
+            } else
+                lane_pass();
+        }
+    }
+    // finish on the machine alone
+    for (int guard = 0; guard < 1000000 && hc[6] < (unsigned long long)n; guard++) machine_slice(64, false);
+    machine_slice(64, false);  // one more slice: a ghost (a stale lane state taken for a live one) would write its node back again
+    for (int64_t i = 0; i < n; i++)
+        for (int p = 0; p < NPROP; p++) props[i * NPROP + p] = soa[(size_t)p * cap + i];
+    if (counters) {
+        counters->steps_accepted = hc[0];
+        counters->steps_rejected = hc[1];
+        counters->rhs_evaluations = hc[2];
+        counters->segments = hc[3];
+        counters->trials_failed = hc[4];
+        counters->nodes = hc[5];
+    }
+    if (hc[6] != (unsigned long long)n) return hc[6] > (unsigned long long)n ? 2 : 1;  // nodes written back twice / lost
+    // every node is done: a slot that is still occupied is evolving a GHOST (a stale lane state taken for a live one)
+    for (int s = 0; s < nslots; s++)
+        if (sUnit[s] >= 0 && sUnit[s] != U_IDLE) return 3;
+    return 0;
+}
+
 extern "C" {
 
 #ifdef GLC_EMU_COUNTERS
@@ -380,6 +546,16 @@ int emu_evolve_batch(void *h, int64_t n, double *props, int32_t *flags, const do
     else
         run<ModelStandard>(e, n, props, flags, time_end, status, interrupt, counters, nslots, budget, sort, slices);
     return 0;
+}
+
+int emu_stream_session(void *h, int64_t n, double *props, int32_t *flags, const double *time_end, int32_t *status,
+                       int32_t *interrupt, glc_counters *counters, int nslots, int chunk, const char *pattern, int lane_budget,
+                       int machine_budget) {
+    Emu *e = (Emu *)h;
+    c_params = e->params;
+    c_tables = e->dt;
+    return run_stream_session(e, n, props, flags, time_end, status, interrupt, counters, nslots, chunk, pattern, lane_budget,
+                              machine_budget);
 }
 
 // the host scheduler of the product (host/glc_forest.hpp) driven with the host-executed kernel source as evolve call-back

@@ -121,3 +121,31 @@ def test_box_lane_logic_is_bit_identical_to_oracle(oracle_lib, leaky):
     so, io, co = o.evolve_batch(po, fo, t_end, n_threads=8)
     np.testing.assert_array_equal(se, so)
     assert ce == co and np.array_equal(pe, po) and np.array_equal(fe, fo)
+
+
+@pytest.mark.parametrize("pattern,chunk,lane_budget", [("LL", 16, 120), ("MLL", 16, 120), ("LML", 16, 80), ("LLLL", 40, 30), ("MMM", 40, 6)])
+def test_stream_session_matches_oracle(oracle_lib, pattern, chunk, lane_budget):
+    """The adaptive ticks of a streaming session (glc_api.cu stream_tick) on the host: slots go machine -> drain -> machine, the
+    drain lanes refill from a queue that grows between ticks and take free slots for newly submitted nodes, slots released by
+    the drain are re-armed by the machine's own slice-start code (machine_rearm).  Every node must be written back exactly once
+    and bit-identical to the checker.  (The stale-slot defect of round 2 -- a released slot re-evolved its old node when the
+    machine took over -- fails this test with "written back twice".)"""
+    from oracle import orc
+    from tests import emu
+
+    p = cases.standard_params(orc, with_black_holes=True)
+    props, flags, t_end = cases.standard_bh_nodes(p, 240, seed=31)
+    o = orc.Oracle()
+    synthetic.install(o, p)
+    po, fo = props.copy(), flags.copy()
+    so, io, co = o.evolve_batch(po, fo, t_end)
+    e = emu.EmuEvolver(nslots=24, machine=True)
+    synthetic.install(e, p)
+    pe, fe = props.copy(), flags.copy()
+    rc, se, ie, ce = e.stream_session(pe, fe, t_end, chunk=chunk, pattern=pattern, lane_budget=lane_budget)
+    assert rc == 0, "nodes lost (1), written back twice (2) or a stale slot taken for a live one (3): %d" % rc
+    np.testing.assert_array_equal(se, so)
+    np.testing.assert_array_equal(ie, io)
+    np.testing.assert_array_equal(fe, fo)
+    assert np.array_equal(pe, po), "streamed records differ from the checker"
+    assert ce == co
