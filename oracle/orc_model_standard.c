@@ -1750,3 +1750,29 @@ void orc_bh_probe(double mass, double spin, double temperature, double *out) {
     out[6] = ideal_gas_sound_speed(temperature);
     out[7] = ideal_gas_sound_speed(temperature) / sqrt(ORC_G_INTERNAL) / sqrt(1.0);
 }
+
+/* known answers of source/tests/dark_matter_profiles.F90:73-410 for the NFW profile ("Zhao1996 (1,3,1)" and NFW groups hold the
+ * same vectors): a halo of `mass` at `time` with concentration `conc`; out[0] = M(<x r_s) / M_vir, out[1] = the radius, in units
+ * of r_s, that massDistribution_%radiusFromSpecificAngularMomentum returns for j = sqrt(G M(<r) r) (the inverse tabulation of
+ * NFW.F90:589-639: recovers x to 2e-4 in the reference's test) */
+void orc_nfw_probe(const glc_params *P, const orc_tables *T, double mass, double time, double conc, double x, double *out) {
+    orc_evolve_ctx c;
+    std_work w;
+    double props[GLC_NPROP], rs, r, m;
+    memset(&c, 0, sizeof(c));
+    memset(props, 0, sizeof(props));
+    c.P = P;
+    c.T = T;
+    c.p = props;
+    props[GLC_P_BASIC_MASS] = mass;
+    props[GLC_P_TIME] = time;
+    props[GLC_P_DMSCALE] = 1.0;
+    work_init(&w, &c, time);
+    halo_scales(&w);
+    rs = w.rvir / conc;
+    props[GLC_P_DMSCALE] = rs;
+    r = x * rs;
+    m = nfw_mass_enclosed(&w, r);
+    out[0] = m / mass;
+    out[1] = nfw_radius_from_j(&w, sqrt(ORC_G_INTERNAL * m * r)) / rs;
+}

@@ -53,3 +53,27 @@ def test_nfw_scale_free_mass(oracle_lib):
     assert abs(probe(oracle_lib, 1.0, 1.0, 1.0, 1.0)[6] - (np.log(2.0) - 0.5)) < 1.0e-15
     a, b = probe(oracle_lib, 1.0, 1.0, 1.0, 0.999999e-6)[6], probe(oracle_lib, 1.0, 1.0, 1.0, 1.000001e-6)[6]
     assert abs(a / b - (0.999999 / 1.000001) ** 2) < 1.0e-3  # the closed form loses ~4 digits to cancellation there
+
+
+def test_nfw_known_answers_of_the_reference(oracle_lib):
+    """source/tests/dark_matter_profiles.F90:60-73,301-362: NFW halo of concentration 8 at z = 0; enclosed mass fractions at
+    r / r_s = 1/8 ... 8 (relTol 1e-6) and the radius recovered from the specific angular momentum of a circular orbit (relTol
+    2e-4: the inverse tabulation of NFW.F90:589-639 that gives the structure solver its first guess)."""
+    from galacticus_b200 import synthetic
+
+    orc = oracle_lib
+    p = orc.params_default(abi.GLC_MODEL_STANDARD)
+    o = orc.Oracle()
+    synthetic.install(o, p)
+    L = orc.lib()
+    L.orc_nfw_probe.restype = None
+    L.orc_nfw_probe.argtypes = [C.POINTER(abi.glc_params), C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                np.ctypeslib.ndpointer(np.float64)]
+    radius = [0.125, 0.25, 0.5, 1.0, 2.0, 4.0, 8.0]
+    mass_expected = [5.099550982355504e-3, 1.768930674181593e-2, 5.513246746363203e-2, 1.476281525188409e-1,
+                     3.301489257042704e-1, 6.186775455118112e-1, 1.000000000000000e+0]
+    out = np.zeros(2)
+    for x, m in zip(radius, mass_expected):
+        L.orc_nfw_probe(C.byref(o.params), o.T, 1.0e12, 13.8, 8.0, x, out)
+        assert abs(out[0] / m - 1.0) < 1.0e-6, (x, out[0], m)
+        assert abs(out[1] / x - 1.0) < 2.0e-4, (x, out[1])
