@@ -79,6 +79,7 @@ using std::min;
 
 #include "../../include/glc_b200.h"
 #include "glc_detmath.h"
+#include "glc_specfun.h"
 
 namespace glc {
 

@@ -13,7 +13,7 @@
 // (glc_numerics.cuh).
 //
 // Documented deviations from quickTest.xml ("out of scope / next"):
-// hotHaloRamPressureStripping=virialRadius; ADAF tabulations supplied by the host (GLC_TABLE_ADAF); beta = 2/3.
+// hotHaloRamPressureStripping=virialRadius; ADAF tabulations supplied by the host (GLC_TABLE_ADAF).
 #pragma once
 
 #include "glc_common.cuh"
@@ -136,7 +136,13 @@ struct ModelStandard {
         w.tvir = 0.5 * kAtomicMassUnit * kMeanAtomicMassPrimordial * ((kKilo * w.vvir) * (kKilo * w.vvir)) / kBoltzmann;
     }
 
-    // ---------------------------------------------------------------- hot halo beta profile (beta = 2/3)
+    // ---------------------------------------------------------------- hot halo beta profile
+    // betaIsTwoThirds = Values_Agree(beta, 2/3, relTol = 1e-3) (beta_profile.F90:214) selects the closed forms; any other beta
+    // goes through I_m(x) = x^(m+1)/(m+1) 2F1((m+1)/2, 3 beta/2; (m+3)/2; -x^2) (glc_specfun.h)
+    GLC_DEVICE_INLINE bool beta_is_two_thirds() {
+        const double b = GLC_PARAMS.hotHaloBeta, t = 2.0 / 3.0;
+        return fabs(b - t) <= 1.0e-3 * 0.5 * (fabs(b) + fabs(t));
+    }
     GLC_DEVICE_INLINE double hh_outer_radius(const Work &w, const double (&y)[NY]) {
         // Node_Component_Hot_Halo_Standard_Outer_Radius, hot_halo/standard/_class.F90:430-450
         return fmax(fmin(y[GLC_P_HH_OUTER_RADIUS], w.rvir), GLC_PARAMS.hotHaloScaleRadiusRelative * w.rvir);
@@ -151,8 +157,11 @@ struct ModelStandard {
         w.hhRho0 = 0.0;
         if (!w.hhValid) return;
         const double r = w.hhRouter / w.hhRcore;
-        const double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - dm_atan(r));
-        w.hhRho0 = mass / 4.0 / kPi / (w.hhRcore * w.hhRcore * w.hhRcore) * nf;
+        if (beta_is_two_thirds()) {
+            const double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - dm_atan(r));
+            w.hhRho0 = mass / 4.0 / kPi / (w.hhRcore * w.hhRcore * w.hhRcore) * nf;
+        } else  // :258: 3 M / (4 pi r_outer^3) / 2F1(3/2, 3 beta/2; 5/2; -r^2), with r^3/3 2F1(...) = I_2(r) (glc_specfun.h)
+            w.hhRho0 = mass / 4.0 / kPi / (w.hhRcore * w.hhRcore * w.hhRcore) / dm_beta_moment(2, r, GLC_PARAMS.hotHaloBeta);
     }
     GLC_DEVICE_INLINE double hh_density(const Work &w, double radius) {
         if (!w.hhValid || radius > w.hhRouter) return 0.0;
@@ -164,6 +173,7 @@ struct ModelStandard {
         if (radius > w.hhRouter) radius = w.hhRouter;
         const double x = radius / w.hhRcore;
         const double rc3 = w.hhRcore * w.hhRcore * w.hhRcore;
+        if (!beta_is_two_thirds()) return 4.0 * kPi * w.hhRho0 * dm_beta_moment(2, x, GLC_PARAMS.hotHaloBeta) * rc3;  // :425-436
         if (x < 1.0e-6)
             return 4.0 * kPi * w.hhRho0 * rc3 * (x * x * x) * (1.0 / 3.0 + x * x * (-1.0 / 5.0 + x * x * (1.0 / 7.0)));
         return 4.0 * kPi * w.hhRho0 * (x - dm_atan(x)) * rc3;
@@ -1314,8 +1324,11 @@ struct ModelStandard {
                 double jSpecific = 0.0;
                 if (rinfall > 0.0) {
                     const double x = w.hhRouter / w.hhRcore;
-                    const double m2 = (x < 1.0e-6) ? x * x * x * (1.0 / 3.0 - x * x / 5.0) : x - dm_atan(x);
-                    const double m3 = (x < 1.0e-6) ? x * x * x * x * (1.0 / 4.0 - x * x / 6.0) : 0.5 * (x * x - dm_log(1.0 + x * x));
+                    const bool b23 = beta_is_two_thirds();  // else the moments through 2F1 (:600-612) = I_m(x)
+                    const double m2 = !b23 ? dm_beta_moment(2, x, GLC_PARAMS.hotHaloBeta)
+                                           : ((x < 1.0e-6) ? x * x * x * (1.0 / 3.0 - x * x / 5.0) : x - dm_atan(x));
+                    const double m3 = !b23 ? dm_beta_moment(3, x, GLC_PARAMS.hotHaloBeta)
+                                           : ((x < 1.0e-6) ? x * x * x * x * (1.0 / 4.0 - x * x / 6.0) : 0.5 * (x * x - dm_log(1.0 + x * x)));
                     const double rc = w.hhRcore;
                     const double norm = (m2 * w.hhRho0 * (rc * rc * rc)) / (m3 * w.hhRho0 * (rc * rc * rc * rc));
                     jSpecific = norm * (y[GLC_P_HH_ANGMOM] / y[GLC_P_HH_MASS]) * rinfall;

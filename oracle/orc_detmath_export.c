@@ -2,6 +2,7 @@
  * (galacticus_b200/csrc/glc_detmath.h) to the tests so their accuracy can be checked against libm. */
 #include <math.h>
 #include "../galacticus_b200/csrc/glc_detmath.h"
+#include "../galacticus_b200/csrc/glc_specfun.h"
 void orc_dm_eval(int which, long n, const double *x, const double *y, double *out) {
     long i;
     for (i = 0; i < n; i++) {
@@ -13,4 +14,10 @@ void orc_dm_eval(int which, long n, const double *x, const double *y, double *ou
         default: out[i] = dm_cbrt(x[i]); break;
         }
     }
+}
+
+/* I_m(x; beta) of glc_specfun.h for tests/test_specfun.py */
+void orc_dm_beta_moment(int m, long n, const double *x, double beta, double *out) {
+    long i;
+    for (i = 0; i < n; i++) out[i] = dm_beta_moment(m, x[i], beta);
 }

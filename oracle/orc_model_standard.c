@@ -26,6 +26,7 @@
 #include <math.h>
 
 #include "../galacticus_b200/csrc/glc_detmath.h"
+#include "../galacticus_b200/csrc/glc_specfun.h"
 #include <string.h>
 
 #include "orc_constants.h"
@@ -128,6 +129,7 @@ static double rvir_growth_rate(std_work *w, double dlnrho_dt) {
 }
 
 /* ------------------------------------------------------------ hot halo beta profile */
+static int beta_is_two_thirds(const std_work *w);
 static double hh_outer_radius(std_work *w) {
     /* Node_Component_Hot_Halo_Standard_Outer_Radius, hot_halo/standard/_class.F90:430-450 */
     halo_scales(w);
@@ -147,10 +149,19 @@ static void hh_profile(std_work *w) {
     w->hh_valid = !(w->hh_router <= 0.0 || w->hh_mass <= 0.0);
     if (!w->hh_valid) return;
     r = w->hh_router / w->hh_rcore;
-    {
+    if (beta_is_two_thirds(w)) {
         double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - dm_atan(r));
         w->hh_rho0 = w->hh_mass / 4.0 / ORC_PI / (w->hh_rcore * w->hh_rcore * w->hh_rcore) * nf;
+    } else {
+        /* :258: rho_0 = 3 M / (4 pi r_outer^3) / 2F1(3/2, 3 beta/2; 5/2; -r^2), with r^3/3 2F1(...) = I_2(r) (glc_specfun.h) */
+        w->hh_rho0 = w->hh_mass / 4.0 / ORC_PI / (w->hh_rcore * w->hh_rcore * w->hh_rcore) / dm_beta_moment(2, r, w->P->hotHaloBeta);
     }
+}
+static int beta_is_two_thirds(const std_work *w) {
+    /* betaIsTwoThirds = Values_Agree(beta, 2/3, relTol = 1e-3), beta_profile.F90:214 (numerical/comparison.F90: |a - b| <=
+       relTol * (|a| + |b|) / 2) */
+    const double b = w->P->hotHaloBeta, t = 2.0 / 3.0;
+    return fabs(b - t) <= 1.0e-3 * 0.5 * (fabs(b) + fabs(t));
 }
 static double hh_density(std_work *w, double radius) {
     /* betaProfileDensity :303-320 (truncateAtOuterRadius) */
@@ -168,6 +179,8 @@ static double hh_mass_enclosed(std_work *w, double radius) {
     if (!w->hh_valid) return 0.0;
     if (radius > w->hh_router) radius = w->hh_router;
     x = radius / w->hh_rcore;
+    if (!beta_is_two_thirds(w)) /* :425-436: 4 pi rho_0 r^3 / 3 * 2F1(3/2, 3 beta/2; 5/2; -x^2) = 4 pi rho_0 r_c^3 I_2(x) */
+        return 4.0 * ORC_PI * w->hh_rho0 * dm_beta_moment(2, x, w->P->hotHaloBeta) * (w->hh_rcore * w->hh_rcore * w->hh_rcore);
     if (x < 1.0e-6)
         return 4.0 * ORC_PI * w->hh_rho0 * (w->hh_rcore * w->hh_rcore * w->hh_rcore) * (x * x * x) *
                (1.0 / 3.0 + x * x * (-1.0 / 5.0 + x * x * (1.0 / 7.0)));
@@ -372,8 +385,10 @@ static double cooling_specific_angular_momentum(std_work *w, double radius) {
     /* densityRadialMoment(m) = I_m(x) rho0 rc^(1+m): ratio m=2 / m=3 */
     {
         const double rc = w->hh_rcore;
-        norm = (hh_radial_moment23(2, x) * w->hh_rho0 * (rc * rc * rc)) /
-               (hh_radial_moment23(3, x) * w->hh_rho0 * (rc * rc * rc * rc));
+        /* general beta: the same moments through 2F1 (:600-612) = I_m(x) of glc_specfun.h */
+        const double m2 = beta_is_two_thirds(w) ? hh_radial_moment23(2, x) : dm_beta_moment(2, x, w->P->hotHaloBeta);
+        const double m3 = beta_is_two_thirds(w) ? hh_radial_moment23(3, x) : dm_beta_moment(3, x, w->P->hotHaloBeta);
+        norm = (m2 * w->hh_rho0 * (rc * rc * rc)) / (m3 * w->hh_rho0 * (rc * rc * rc * rc));
     }
     return norm * jmean * radius;
 }
@@ -1718,11 +1733,12 @@ void orc_mass_distribution_probe(const glc_params *P, double mass, double rcore,
         const double r = router / rcore;
         const double nf = (r < 1.0e-6) ? 3.0 / (r * r * r) + 9.0 / 5.0 / r - 36.0 * r / 175.0 : 1.0 / (r - dm_atan(r));
         w.hh_rho0 = mass / 4.0 / ORC_PI / (rcore * rcore * rcore) * nf;
+        if (!beta_is_two_thirds(&w)) w.hh_rho0 = mass / 4.0 / ORC_PI / (rcore * rcore * rcore) / dm_beta_moment(2, r, P->hotHaloBeta);
     }
     out[0] = hh_mass_enclosed(&w, radius);
     out[1] = hh_density(&w, radius);
-    out[2] = hh_radial_moment23(2, radius / rcore);
-    out[3] = hh_radial_moment23(3, radius / rcore);
+    out[2] = beta_is_two_thirds(&w) ? hh_radial_moment23(2, radius / rcore) : dm_beta_moment(2, radius / rcore, P->hotHaloBeta);
+    out[3] = beta_is_two_thirds(&w) ? hh_radial_moment23(3, radius / rcore) : dm_beta_moment(3, radius / rcore, P->hotHaloBeta);
     out[4] = w.hh_rho0;
     /* Hernquist: unit mass in stars, unit scale length, no disk, no hot halo contribution */
     props[GLC_P_SPH_MASS_STELLAR] = 1.0;
