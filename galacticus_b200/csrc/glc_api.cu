@@ -70,13 +70,16 @@ struct glc_evolver {
                                     // hand over to the drain after one slice on a few SMs anyway; results are identical either way
     int32_t drain_handover = 1;     // run-to-completion mode: finish the last nodes with drain_kernel
     int64_t drain_threshold = 120000; // hand over when fewer slots than this are still in flight (measured: profiles/r01f_knobs.txt)
-    int32_t drain_dense_budget = 1024; // evaluations per lane in a dense drain pass
+    int32_t drain_dense_budget = 0x3fffffff; // evaluations per lane in a dense drain pass.  Unbounded since round 2: once the list is
+                                       // exhausted a long node is left alone in its warp and runs at lone-lane speed, which beats parking it
+                                       // after 1024 evaluations and re-listing it (10^6-node pass 1941 -> 1808 ms, profiles/r02w)
     int32_t hybrid_budget = 4096;      // pops per warp of one internal machine slice in run-to-completion mode
     int32_t *d_held = nullptr;
     float *d_held_score = nullptr;
     int64_t held_cap = 0;
     int32_t drain_express = 1;      // first drain pass: predicted-longest nodes one per warp on stream2
     float drain_age_weight = 0.0f;  // express selection: score = predicted remaining steps (0) or 6 x that + weight x evaluations so far
+    int32_t drain_lanes_max = 32;   // most nodes per warp in a drain pass (fewer: less divergence per warp, more passes over the list)
     int32_t drain_spread = 1;       // drain / lane passes: spread the nodes over all resident warps (KernelArgs::drainLanes); 0 = one per
                                     // warp when they fit, else 32 per warp (round-2 behaviour before the measurement in profiles/r02k)
     cudaStream_t stream2 = nullptr;
@@ -890,8 +893,8 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                         continue;
                     }
                     // the nodes of a pass are spread over all resident warps (KernelArgs::drainLanes)
-                    const int lanes = ev->drain_spread ? std::min(32, (nheld + warpsResident - 1) / warpsResident)
-                                                       : (nheld <= warpsResident ? 1 : 32);
+                    const int lanes = ev->drain_spread ? std::min(ev->drain_lanes_max, (nheld + warpsResident - 1) / warpsResident)
+                                                       : (nheld <= warpsResident ? 1 : ev->drain_lanes_max);
                     const bool sparse = lanes == 1;
                     A.held = ev->d_held;
                     A.nheld = nheld;
@@ -1200,6 +1203,7 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_HYBRID_BUDGET")) ev->hybrid_budget = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_EXPRESS")) ev->drain_express = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_SPREAD")) ev->drain_spread = atoi(e);
+    if (const char *e = getenv("GLC_DRAIN_LANES_MAX")) ev->drain_lanes_max = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("GLC_DRAIN_AGE_WEIGHT")) ev->drain_age_weight = (float)atof(e);
     if (const char *e = getenv("GLC_L2_PERSIST")) ev->l2_persist = atoi(e);
     if (const char *e = getenv("GLC_STREAM_SPARSE_BUDGET")) ev->stream_sparse_budget = atoi(e);
