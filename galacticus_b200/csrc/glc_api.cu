@@ -99,6 +99,11 @@ struct glc_evolver {
     int32_t stream_express = 0;          // lane passes with more nodes than warps: nodes whose score (evaluations spent so far +
                                          // 6 x predicted remaining steps) reaches this get a warp each; 0 = off
     int32_t stream_express_budget = 48;  // evaluations of an express warp per tick
+    int32_t stream_priority_express = 0; // > 0: that many of the highest-PRIORITY nodes (glc_forest_evolve: halo mass, i.e. the main
+                                         // branches every tree waits for) get a warp each in lane passes with more nodes than warps.
+                                         // Measured (profiles/r02k): 200 = no change, 592 / 1000 = 18 % slower; off
+    float *d_stream_priority = nullptr;  // [cap] per ticket
+    int64_t stream_priority_cap = 0;
     std::vector<int32_t> h_held, h_ordered;
     std::vector<float> h_score;
     std::vector<int> h_idx;
@@ -1030,11 +1035,12 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
     const int nslotsAll = (int)ev->nslots_machine;
     const int warpsResident = ev->num_sms * bps * (kBlock / 32);
     GLC_CHECK(ev, cudaMemsetAsync(d_count, 0, sizeof(int) * 4, ev->stream));
-    const bool wantExpress = ev->stream_express > 0;
+    const bool wantPriority = ev->stream_priority_express > 0 && ev->d_stream_priority != nullptr;
+    const bool wantExpress = ev->stream_express > 0 || wantPriority;
     const bool wantSort = !wantExpress && ev->stream_sort > 0;
     held_list_kernel<<<std::min((nslotsAll + 255) / 256, ev->num_sms * 8), 256, 0, ev->stream>>>(
         ev->d_slots.unit, ev->d_slots.L, nslotsAll, ev->d_held, (wantExpress || wantSort) ? ev->d_held_score : nullptr, d_count,
-        (int)std::min<int64_t>(queued, nslotsAll), wantExpress ? 1.0f : (wantSort ? -1.0f : 0.0f));
+        (int)std::min<int64_t>(queued, nslotsAll), wantExpress ? 1.0f : (wantSort ? -1.0f : 0.0f), wantPriority ? ev->d_stream_priority : nullptr);
     int nlist = 0;
     GLC_CHECK(ev, cudaMemcpyAsync(&nlist, d_count, sizeof(int), cudaMemcpyDeviceToHost, ev->stream));
     GLC_CHECK(ev, cudaStreamSynchronize(ev->stream));
@@ -1098,17 +1104,18 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
             std::vector<int> &idx = ev->h_idx;
             idx.resize(nlist);
             for (int k = 0; k < nlist; k++) idx[k] = k;
-            nexpress = std::min(expressCap, nlist);
+            nexpress = std::min(wantPriority ? std::min(expressCap, ev->stream_priority_express) : expressCap, nlist);
+            const float expressMin = wantPriority ? 1.0e-30f : (float)ev->stream_express;  // (fresh slots carry priority 0)
             std::nth_element(idx.begin(), idx.begin() + nexpress, idx.end(), [&](int a, int b) { return h_score[a] > h_score[b]; });
             // only nodes that have actually been running qualify (fresh slots and just-fetched nodes score 0)
             int keep = 0;
             std::vector<int32_t> &ordered = ev->h_ordered;
             ordered.resize(nlist);
             for (int k = 0; k < nexpress; k++)
-                if (h_score[idx[k]] >= (float)ev->stream_express) ordered[keep++] = h_held[idx[k]];
+                if (h_score[idx[k]] >= expressMin) ordered[keep++] = h_held[idx[k]];
             int tail = keep;
             for (int k = 0; k < nexpress; k++)
-                if (!(h_score[idx[k]] >= (float)ev->stream_express)) ordered[tail++] = h_held[idx[k]];
+                if (!(h_score[idx[k]] >= expressMin)) ordered[tail++] = h_held[idx[k]];
             for (int k = nexpress; k < nlist; k++) ordered[tail++] = h_held[idx[k]];
             nexpress = keep;
             if (nexpress > 0) {
@@ -1213,6 +1220,7 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_STREAM_SPREAD")) ev->stream_spread = atoi(e);
     if (const char *e = getenv("GLC_STREAM_SORT")) ev->stream_sort = atoi(e);
     if (const char *e = getenv("GLC_STREAM_EXPRESS_BUDGET")) ev->stream_express_budget = atoi(e);
+    if (const char *e = getenv("GLC_STREAM_PRIORITY_EXPRESS")) ev->stream_priority_express = atoi(e);
     cudaStreamCreateWithFlags(&ev->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ev->stream2, cudaStreamNonBlocking);
     cudaEventCreate(&ev->ev0);
@@ -1269,6 +1277,7 @@ int glc_evolver_destroy(glc_evolver *ev) {
     cudaStreamDestroy(ev->stream);
     cudaStreamDestroy(ev->stream2);
     cudaFree(ev->d_held_score);
+    cudaFree(ev->d_stream_priority);
     delete ev;
     return 0;
 }
@@ -2024,6 +2033,7 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
             std::vector<double, PinnedAllocator<double>> q_props, q_tend, c_props;
             std::vector<int32_t, PinnedAllocator<int32_t>> q_flags, c_flags, c_status, c_interrupt;
             std::vector<int64_t, PinnedAllocator<int64_t>> c_tickets;
+            std::vector<float> q_prio;
             glc_counters session{};
             double t0 = now_s(), t_run = 0.0, t_collect = 0.0, t_submit = 0.0;
             int64_t polls = 0;
@@ -2098,6 +2108,19 @@ int glc_forest_evolve(glc_evolver *ev, int64_t n_nodes, const int32_t *parent, c
                 int64_t first = 0;
                 int rc = glc_stream_submit(ev, m, q_props.data(), q_flags.data(), q_tend.data(), &first);
                 if (rc) return rc;
+                if (ev->stream_priority_express > 0) {
+                    // priority of a ticket = the halo mass of its node: the main branches are what every tree waits for
+                    if (ev->stream_priority_cap < ev->cap) {
+                        cudaFree(ev->d_stream_priority);
+                        ev->d_stream_priority = nullptr;
+                        if (cudaMalloc(&ev->d_stream_priority, sizeof(float) * (size_t)ev->cap) != cudaSuccess) return -2;
+                        ev->stream_priority_cap = ev->cap;
+                    }
+                    q_prio.resize(m);
+                    for (int64_t k = 0; k < m; k++) q_prio[k] = (float)F.R(q_nodes[k])[GLC_P_BASIC_MASS];
+                    if (cudaMemcpyAsync(ev->d_stream_priority + first, q_prio.data(), sizeof(float) * m, cudaMemcpyHostToDevice, ev->stream) != cudaSuccess) return -2;
+                    cudaStreamSynchronize(ev->stream);
+                }
                 submitted += m;
                 q_nodes.clear();
                 q_tend.clear();

@@ -827,7 +827,7 @@ __global__ void __launch_bounds__(THREADS, 1) machine_kernel(KernelArgs A, SlotA
 // remaining steps of the node, (t_end - t) / h with the controller's current step size.  Streaming sessions also list up to
 // `wantFree` free slots (entries tagged kHeldFresh, counted in count[3]) into which the drain kernel fetches queued nodes.
 __global__ void held_list_kernel(const int *__restrict__ unit, const LaneState *__restrict__ L, int nslots, int32_t *held,
-                                 float *score, int *count, int wantFree, float ageWeight = 0.0f) {
+                                 float *score, int *count, int wantFree, float ageWeight = 0.0f, const float *priority = nullptr) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += gridDim.x * blockDim.x) {
         const int u = unit[i];
         if (u == U_RHS_BEGIN) {
@@ -841,6 +841,8 @@ __global__ void held_list_kernel(const int *__restrict__ unit, const LaneState *
                 score[k] = ageWeight > 0.0f ? 6.0f * steps + ageWeight * (float)L[i].age : steps;
                 // ageWeight < 0: the component-set bucket of the node (queue_bucket), for lists sorted by kind of node
                 if (ageWeight < 0.0f) score[k] = (float)queue_bucket(L[i].ctx.flags);
+                // priority given by the submitter (the tree scheduler knows which nodes its trees wait for): per ticket = arena row
+                if (priority) score[k] = (L[i].node >= 0) ? priority[L[i].node] : 0.0f;
             }
         } else if (wantFree > 0 && (u == U_IDLE || u < 0)) {
             if (atomicAdd(count + 3, 1) < wantFree) {

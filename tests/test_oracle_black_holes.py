@@ -134,3 +134,54 @@ def test_jet_heating_offsets_cooling(oracle_lib):
     ok = (c0 == 0) & (c1 == 0) & ((flags & abi.GLC_F_HAS_DISK) != 0)
     assert (d1[ok, P["DISK_MASS_GAS"]] <= d0[ok, P["DISK_MASS_GAS"]]).all()
     assert (d1[ok, P["DISK_MASS_GAS"]] < d0[ok, P["DISK_MASS_GAS"]]).any()
+
+
+def test_adaf_jet_power_known_answers():
+    """source/tests/accretion_disks.F90:37-66: jet power efficiency of an ADAF (pureADAF energy, exponential field enhancement,
+    fitted viscosity, adiabatic index 1.444, efficiencyJetMaximum 2) at six spins, relTol 1e-3 -- the reference's own known
+    answers for the construction-time tabulation the device interpolates (GLC_TABLE_ADAF), restated in galacticus_b200/adaf.py."""
+    from galacticus_b200 import adaf
+
+    disk = adaf.ADAF(energy="pureADAF", field="exponential", viscosity="fit", adiabatic_index=1.444, efficiency_jet_maximum=2.0)
+    spin = [0.0, 0.2, 0.4, 0.6, 0.8, 0.95]
+    expected = [2.993e-3, 3.916e-3, 6.571e-3, 1.564e-2, 5.246e-2, 4.119e-1]
+    for j, e in zip(spin, expected):
+        assert abs(disk.jet_efficiency(j) / e - 1.0) < 1.0e-3, (j, disk.jet_efficiency(j), e)
+    # Kerr-metric helpers against the reference's black_hole_fundamentals unit test (:41-50)
+    assert abs(adaf.isco_radius(0.0) - 6.0) < 1e-6 and abs(adaf.isco_radius(1.0) - 1.0) < 1e-6
+    assert abs(adaf.horizon_radius(0.0) - 2.0) < 1e-6 and abs(adaf.horizon_radius(1.0) - 1.0) < 1e-6
+    # the spin-up function changes sign at the equilibrium spin of Benson & Babul (2009), j ~ 0.92
+    assert disk.spin_up(0.90) > 0.0 > disk.spin_up(0.93)
+
+
+def test_path_runs_on_the_restated_adaf_tabulation(oracle_lib):
+    """The restated tabulation uploaded as GLC_TABLE_ADAF: the kernel source reproduces the checker bit for bit on it too
+    (black holes of at least 1e5 Msun: the spin equation of seed-mass holes is stiff with this table, see synthetic.adaf_table)."""
+    from galacticus_b200 import adaf
+    from tests import cases, emu
+
+    p = cases.standard_params(oracle_lib, with_black_holes=True)
+    props, flags, t_end = cases.standard_bh_nodes(p, 160, seed=23)
+    keep = ((flags & abi.GLC_F_HAS_BH) != 0) & (props[:, P["BH_MASS"]] >= 1.0e5) & (props[:, P["BH_SPIN"]] < 0.99)
+    props, flags, t_end = np.ascontiguousarray(props[keep]), np.ascontiguousarray(flags[keep]), np.ascontiguousarray(t_end[keep])
+    assert props.shape[0] >= 20
+    x, _, v = adaf.adaf_tabulations(count=2000)
+    o = oracle_lib.Oracle()
+    synthetic.install(o, p)
+    o.set_table(abi.GLC_TABLE_ADAF, x, None, v)
+    po, fo = props.copy(), flags.copy()
+    so, io, co = o.evolve_batch(po, fo, t_end)
+    assert (so == 0).all()
+    e = emu.EmuEvolver(nslots=32, machine=True)
+    synthetic.install(e, p)
+    e.set_table(abi.GLC_TABLE_ADAF, x, None, v)
+    pe, fe = props.copy(), flags.copy()
+    se, ie, ce = e.evolve_batch(pe, fe, t_end)
+    np.testing.assert_array_equal(se, so)
+    assert np.array_equal(pe, po) and ce == co
+    # and it is a different model from the stand-in: black-hole spins end elsewhere
+    o2 = oracle_lib.Oracle()
+    synthetic.install(o2, p)
+    q = props.copy()
+    o2.evolve_batch(q, flags.copy(), t_end)
+    assert not np.array_equal(q[:, P["BH_SPIN"]], po[:, P["BH_SPIN"]])
