@@ -9,7 +9,7 @@ reference codes them, the Kerr-metric factors of source/black_holes/fundamentals
 from the black hole (static limit) and from the disk (ISCO) (:548-672).
 
 Pinned by the reference's own unit test source/tests/accretion_disks.F90:37-66 (jet power efficiency at six spins to 1e-3):
-tests/test_oracle_black_holes.py::test_adaf_jet_power_known_answers.
+the black-hole known-answer tests under tests/ (test_adaf_jet_power_known_answers).
 """
 import math
 
