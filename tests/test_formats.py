@@ -126,3 +126,42 @@ def test_malformed_documents_are_rejected():
         formats.read_fully_specified(LEAKY_DOC.replace("<parent>2</parent>", "<parent>7</parent>"))
     with pytest.raises(formats.TreeFormatError, match="no root"):
         formats.read_fully_specified(LEAKY_DOC.replace("<parent>-1</parent>", "<parent>1</parent>"))
+
+
+def test_document_forest_through_the_tree_walk(oracle_lib):
+    """A forest written in the reference's tree format and read back evolves, through the checker's tree walk, to exactly
+    what the original arrays evolve to (the reader re-indexes the nodes; the trees are the same)."""
+    p = cases.standard_params(with_black_holes=True)
+    f = synthetic.binary_split_forest(p, 3, 1.0e12, 5.0e10, seed=5)
+    doc = formats.read_fully_specified(formats.write_fully_specified(f))
+    o = oracle_lib.Oracle()
+    synthetic.install(o, p)
+    ra, fa, sa, fca, ca = o.forest_evolve(f, n_threads=2)
+    rb, fb, sb, fcb, cb = o.forest_evolve(doc["forest"], n_threads=2)
+    order = doc["index"] - 1
+    assert fca == fcb and ca == cb
+    np.testing.assert_array_equal(sb, sa[order])
+    np.testing.assert_array_equal(fb, fa[order])
+    assert np.array_equal(rb, ra[order])
+
+
+@pytest.mark.gpu
+def test_document_forest_on_the_device(oracle_lib):
+    """The same document through glc_forest_evolve: the device evolves the trees read from XML to the checker's records."""
+    from galacticus_b200.evolver import Evolver
+
+    p = cases.standard_params(with_black_holes=True)
+    f = synthetic.binary_split_forest(p, 6, 1.0e12, 2.0e10, seed=9)
+    doc = formats.read_fully_specified(formats.write_fully_specified(f))
+    o = oracle_lib.Oracle()
+    synthetic.install(o, p)
+    ro, fo, so, fco, co = o.forest_evolve(doc["forest"], n_threads=8)
+    ev = Evolver(0)
+    synthetic.install(ev, p)
+    rg, fg, sg, fcg, cg = ev.forest_evolve(doc["forest"])
+    np.testing.assert_array_equal(sg, so)
+    np.testing.assert_array_equal(fg, fo)
+    assert cg == co
+    alive = so != abi.GLC_FOREST_NODE_PROMOTED
+    assert np.array_equal(rg[alive], ro[alive])
+    ev.close()
