@@ -79,6 +79,7 @@ struct glc_evolver {
     int64_t held_cap = 0;
     int32_t drain_express = 1;      // first drain pass: predicted-longest nodes one per warp on stream2
     float drain_age_weight = 0.0f;  // express selection: score = predicted remaining steps (0) or 6 x that + weight x evaluations so far
+    int32_t drain_block_sync = 0;   // dense drain / lane passes: the warps of a block start every evaluation together (KernelArgs)
     int32_t drain_lanes_max = 32;   // most nodes per warp in a drain pass (fewer: less divergence per warp, more passes over the list)
     int32_t drain_spread = 1;       // drain / lane passes: spread the nodes over all resident warps (KernelArgs::drainLanes); 0 = one per
                                     // warp when they fit, else 32 per warp (round-2 behaviour before the measurement in profiles/r02k)
@@ -107,6 +108,7 @@ struct glc_evolver {
     std::vector<int32_t> h_held, h_ordered;
     std::vector<float> h_score;
     std::vector<int> h_idx;
+    int32_t stream_machine_budget = 4096; // pops per warp of a machine slice used as a streaming tick
     int64_t stream_machine_above = -1;   // adaptive ticks: machine slice when queued + occupied >= this (default: drain_threshold)
     // tick statistics of the session (forest log): machine slices / lane passes, their device-side wall time, nodes in flight
     int64_t tick_machine = 0, tick_lane = 0, tick_hold = 0;
@@ -210,6 +212,7 @@ __global__ void rhs_kernel(KernelArgs A, double *dydt) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = gid < A.n;
     const int node = on ? gid : A.n - 1;
+    glc_vote_init(0);
     auto AR = [&](int prop) -> double & { return A.props[(int64_t)prop * A.cap + node]; };
     NodeCtx ctx;
     double y[NY], rate[NY];
@@ -256,6 +259,7 @@ __global__ void rhs_kernel(KernelArgs A, double *dydt) {
 template <class Model>
 __global__ void error_report_kernel(KernelArgs A, double h, double *out) {
     const bool on = threadIdx.x == 0;
+    glc_vote_init(0);
     auto AR = [&](int prop) -> double & { return A.props[(int64_t)prop * A.cap]; };
     NodeCtx ctx;
     double y0[NY], yt[NY], rate[NY], s[NY], k[6][NY];
@@ -869,6 +873,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                         D.nheld = nheld - express;
                         D.held_counter = d_count + 2;
                         D.drainLanes = 0;
+                        D.drainBlockSync = ev->drain_block_sync;
                         D.budget = ev->drain_dense_budget;
                         drain_kernel<ModelStandard><<<ev->num_sms, kBlock, 0, ev->stream>>>(D);
                         ev->launches += 3;
@@ -905,6 +910,7 @@ static int launch_machine(glc_evolver *ev, int n, unsigned long long *hc, int mo
                     A.nheld = nheld;
                     A.held_counter = d_count + 1;
                     A.drainLanes = lanes >= 32 ? 0 : lanes;
+                    A.drainBlockSync = (lanes > 1) ? ev->drain_block_sync : 0;
                     A.budget = sparse ? 0x7fffffff : ev->drain_dense_budget;
                     const int perBlock = lanes * (kBlock / 32);
                     int dgrid = (nheld + perBlock - 1) / perBlock;
@@ -995,7 +1001,7 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
     ev->tick_live_sum += (double)(queued + ev->stream_live);
     if (!ev->stream_lane_mode) {
         if (queued + ev->stream_live >= big) {
-            int rc = launch_machine(ev, n, hc, 1, 4096, 0);
+            int rc = launch_machine(ev, n, hc, 1, ev->stream_machine_budget, 0);
             ev->stream_live = (int64_t)hc[7];
             ev->tick_machine++;
             ev->tick_machine_s += now_s() - t_tick;
@@ -1012,7 +1018,7 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
         ev->stream_lane_mode = true;
     } else if (queued + ev->stream_live >= big) {
         ev->stream_lane_mode = false;  // many nodes again: back to the machine (parked slots are re-queued by their unit words)
-        int rc = launch_machine(ev, n, hc, 1, 4096, 0);
+        int rc = launch_machine(ev, n, hc, 1, ev->stream_machine_budget, 0);
         ev->stream_live = (int64_t)hc[7];
         ev->tick_machine++;
         ev->tick_machine_s += now_s() - t_tick;
@@ -1143,6 +1149,7 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
         if (ev->stream_spread == 1) lanes = std::min(32, (A.nheld + warpsFree - 1) / warpsFree);
         if (ev->stream_spread == 2 && A.nheld > warpsFree) lanes = std::min(32, (A.nheld + warpsOne - 1) / warpsOne);
         A.drainLanes = lanes >= 32 ? 0 : lanes;
+        A.drainBlockSync = (lanes > 1) ? ev->drain_block_sync : 0;
         A.budget = ev->stream_sparse_budget - (int)((long long)(ev->stream_sparse_budget - ev->stream_dense_budget) * (lanes - 1) / 31);
         const int perBlock = lanes * (kBlock / 32);
         int dgrid = (A.nheld + perBlock - 1) / perBlock;
@@ -1210,12 +1217,14 @@ int glc_evolver_create(glc_evolver **out, int32_t device_ordinal) {
     if (const char *e = getenv("GLC_HYBRID_BUDGET")) ev->hybrid_budget = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_EXPRESS")) ev->drain_express = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_SPREAD")) ev->drain_spread = atoi(e);
+    if (const char *e = getenv("GLC_DRAIN_BLOCK_SYNC")) ev->drain_block_sync = atoi(e);
     if (const char *e = getenv("GLC_DRAIN_LANES_MAX")) ev->drain_lanes_max = std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("GLC_DRAIN_AGE_WEIGHT")) ev->drain_age_weight = (float)atof(e);
     if (const char *e = getenv("GLC_L2_PERSIST")) ev->l2_persist = atoi(e);
     if (const char *e = getenv("GLC_STREAM_SPARSE_BUDGET")) ev->stream_sparse_budget = atoi(e);
     if (const char *e = getenv("GLC_STREAM_DENSE_BUDGET")) ev->stream_dense_budget = atoi(e);
     if (const char *e = getenv("GLC_STREAM_MACHINE_ABOVE")) ev->stream_machine_above = atoll(e);
+    if (const char *e = getenv("GLC_STREAM_MACHINE_BUDGET")) ev->stream_machine_budget = atoi(e);
     if (const char *e = getenv("GLC_STREAM_EXPRESS")) ev->stream_express = atoi(e);
     if (const char *e = getenv("GLC_STREAM_SPREAD")) ev->stream_spread = atoi(e);
     if (const char *e = getenv("GLC_STREAM_SORT")) ev->stream_sort = atoi(e);

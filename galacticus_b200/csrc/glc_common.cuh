@@ -21,7 +21,21 @@
 #define GLC_PARAMS c_params
 #define GLC_TABLES c_tables
 #define glc_atomic_add(p, v) atomicAdd((p), (v))
-#define GLC_ANY(p) __any_sync(0xffffffffu, (p))
+// Vote level of the running kernel (block-uniform, set by glc_vote_init at the top of every kernel that calls the
+// warp-synchronous rate function).  0/1: the data-dependent loops vote per warp.  2: the rate function also puts a block
+// barrier between its phases.  3: the loops vote per BLOCK, so the warps of a block walk through an evaluation in step
+// and share the instruction stream (drain_kernel only -- it is instruction-fetch bound, profiles/r02ac; every thread
+// of the block must then call the rate function the same number of times).
+__shared__ int s_glcVoteLevel;
+static __device__ __forceinline__ void glc_vote_init(int level) {
+    if (threadIdx.x == 0) s_glcVoteLevel = level;
+    __syncthreads();
+}
+static __device__ __forceinline__ bool glc_any(bool p) {
+    return s_glcVoteLevel >= 3 ? __syncthreads_or(p ? 1 : 0) != 0 : __any_sync(0xffffffffu, p) != 0;
+}
+#define GLC_ANY(p) glc_any(p)
+#define GLC_PHASE_SYNC() do { if (s_glcVoteLevel >= 2) __syncthreads(); } while (0)
 #define GLC_COUNT(k) ((void)0)
 #define GLC_SYNCWARP() __syncwarp()
 // smallest positive double: positive IEEE doubles order like their bit patterns
@@ -55,6 +69,7 @@
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
 #define GLC_ANY(p) (p)
+#define GLC_PHASE_SYNC() ((void)0)
 #ifdef GLC_EMU_COUNTERS
 static long long g_emu_count[8];
 #define GLC_COUNT(k) (g_emu_count[k]++)
@@ -193,6 +208,10 @@ struct KernelArgs {
                                    // evaluations of its lanes, so a node advances fastest alone in its warp (1: lone-lane speed, ~0.2 ms
                                    // per evaluation against ~0.7 ms with 32 nodes per warp); the host spreads the nodes of a pass
                                    // over all resident warps: lanes = ceil(nodes / resident warps)
+    int drainBlockSync;            // drain: 1 = the warps of a block start every evaluation together (__syncthreads_or at the top of
+                                   // the loop).  The dense pass is bound by instruction fetch (profiles/r02ac: no_instruction 12.8
+                                   // stall cycles per issue, 340 KB of SASS); warps that walk the rate function side by side share
+                                   // what one of them has fetched
     int drainRefill;               // drain, streaming sessions: a lane whose node is done fetches the next one from the node
                                    // queue into the same slot (list entries with kHeldFresh set are free slots that start
                                    // with a fetch)

@@ -710,9 +710,13 @@ __global__ void __launch_bounds__(GLC_BLOCK, GLC_MIN_BLOCKS) drain_kernel(Kernel
     int slotHeld = -1;
     unsigned int tot[7] = {0, 0, 0, 0, 0, 0, 0};
     const bool mayTake = A.drainLanes <= 0 || (int)(threadIdx.x & 31) < A.drainLanes;
+    glc_vote_init(A.drainBlockSync);
     for (int it = 0; it < A.budget; ++it) {
         const bool active = drain_iterate<Model>(L, M, A, yt, fresh, slotHeld, tot, mayTake);
-        if (!__any_sync(0xffffffffu, active)) break;
+        if (A.drainBlockSync) {
+            if (!__syncthreads_or(active ? 1 : 0)) break;  // block-uniform: every thread takes part in every barrier
+        } else if (!__any_sync(0xffffffffu, active))
+            break;
     }
     drain_park<Model>(L, M, A, yt, fresh, slotHeld, tot);
 #pragma unroll
@@ -734,6 +738,7 @@ __global__ void __launch_bounds__(GLC_BLOCK, GLC_MIN_BLOCKS) evolve_kernel(Kerne
         lane_reset(L);
     L.nAcc = L.nRej = L.nRhs = L.nSeg = L.nTrialFail = L.nNodes = L.nDone = 0;
     if (L.phase == PH_IDLE) L.phase = PH_FETCH;  // the queue may have grown since the last slice
+    glc_vote_init(0);
 
     for (int it = 0; it < A.budget; ++it) {
         // All 32 lanes stay in this loop until the whole warp is out of work; the vote is a reconvergence

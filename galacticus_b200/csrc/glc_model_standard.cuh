@@ -1381,14 +1381,17 @@ struct ModelStandard {
         }
         // <eventHook preDerivative>: galactic structure solve (standard.F90:1045)
         structure_solve(c, y, time, w, bad, on);
+        GLC_PHASE_SYNC();
         const bool go = on && !structureOnly && w.solvable;
         const bool dOn = disk_sfr_on(c, y, go);
         const double psiDisk = sfr_disk(c, y, bad, dOn);
+        GLC_PHASE_SYNC();
         const bool coolOn = cooling_on(c, y, w, go);
         const bool radiusOn = cooling_radius_on(c, y, w, coolOn, go);
         double logSlopeT = 0.0;
         if (radiusOn) cooling_prepare(y, w, logSlopeT);
         const double rinfallSolved = cooling_radius(y, w, bad, radiusOn);
+        GLC_PHASE_SYNC();
         return rates_accumulate(c, time, y, rate, w, go, dOn, psiDisk, coolOn, radiusOn, rinfallSolved, logSlopeT, bad);
     }
 

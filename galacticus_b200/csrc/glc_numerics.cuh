@@ -56,7 +56,13 @@ GLC_DEVICE_INLINE void brent_begin(BrentState &B, bool on, double xLow, double x
     B.busy = on ? 1 : 0;
 }
 
-GLC_DEVICE_INLINE bool brent_advance(BrentState &B, const RootOptions &o) {
+// GLC_NOINLINE_BRENT (experiment, profiles/r02ad): one copy of the Brent state machine per kernel instead of one per root problem
+#ifdef GLC_NOINLINE_BRENT
+#define GLC_DEVICE_BRENT GLC_DEVICE_NOINLINE
+#else
+#define GLC_DEVICE_BRENT GLC_DEVICE_INLINE
+#endif
+GLC_DEVICE_BRENT bool brent_advance(BrentState &B, const RootOptions &o) {
     double x = 0.0;
     bool evaluate = false;
     while (B.busy && !evaluate) {
@@ -238,7 +244,7 @@ GLC_DEVICE_INLINE bool brent_advance(BrentState &B, const RootOptions &o) {
     return B.busy && evaluate;
 }
 
-GLC_DEVICE_INLINE void brent_feed(BrentState &B, const RootOptions &o, double fx) {
+GLC_DEVICE_BRENT void brent_feed(BrentState &B, const RootOptions &o, double fx) {
             if (B.state == ST_FLO) {
                 B.fLow = fx;
                 B.state = ST_FHI;
