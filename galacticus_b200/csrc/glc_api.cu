@@ -79,7 +79,9 @@ struct glc_evolver {
     int64_t held_cap = 0;
     int32_t drain_express = 1;      // first drain pass: predicted-longest nodes one per warp on stream2
     float drain_age_weight = 0.0f;  // express selection: score = predicted remaining steps (0) or 6 x that + weight x evaluations so far
-    int32_t drain_block_sync = 0;   // dense drain / lane passes: the warps of a block start every evaluation together (KernelArgs)
+    int32_t drain_block_sync = 2;   // vote level of dense drain / lane passes (glc_common.cuh): the warps of a block start every evaluation
+                                    // together and meet again between the phases of the rate function -- the kernel is instruction-fetch
+                                    // bound (profiles/r02ac): dense drain 1105 -> 1000 ms at level 2 (profiles/r02ag); 1 and 3 gain less
     int32_t drain_lanes_max = 32;   // most nodes per warp in a drain pass (fewer: less divergence per warp, more passes over the list)
     int32_t drain_spread = 1;       // drain / lane passes: spread the nodes over all resident warps (KernelArgs::drainLanes); 0 = one per
                                     // warp when they fit, else 32 per warp (round-2 behaviour before the measurement in profiles/r02k)

@@ -23,18 +23,20 @@
 #define glc_atomic_add(p, v) atomicAdd((p), (v))
 // Vote level of the running kernel (block-uniform, set by glc_vote_init at the top of every kernel that calls the
 // warp-synchronous rate function).  0/1: the data-dependent loops vote per warp.  2: the rate function also puts a block
-// barrier between its phases.  3: the loops vote per BLOCK, so the warps of a block walk through an evaluation in step
-// and share the instruction stream (drain_kernel only -- it is instruction-fetch bound, profiles/r02ac; every thread
-// of the block must then call the rate function the same number of times).
+// barrier between its phases.  3: the fixed-point loop of the structure solve votes per BLOCK (one barrier per pass).
+// The point: the warps of a block walk through an evaluation in step and share the instruction stream (drain_kernel
+// only -- it is instruction-fetch bound, profiles/r02ac; every thread of the block must then call the rate function the
+// same number of times).  (Every loop voting per block, Brent and QAG included, was slower than no block vote at all.)
 __shared__ int s_glcVoteLevel;
 static __device__ __forceinline__ void glc_vote_init(int level) {
     if (threadIdx.x == 0) s_glcVoteLevel = level;
     __syncthreads();
 }
-static __device__ __forceinline__ bool glc_any(bool p) {
+static __device__ __forceinline__ bool glc_any_outer(bool p) {
     return s_glcVoteLevel >= 3 ? __syncthreads_or(p ? 1 : 0) != 0 : __any_sync(0xffffffffu, p) != 0;
 }
-#define GLC_ANY(p) glc_any(p)
+#define GLC_ANY(p) __any_sync(0xffffffffu, (p))
+#define GLC_ANY_OUTER(p) glc_any_outer(p)
 #define GLC_PHASE_SYNC() do { if (s_glcVoteLevel >= 2) __syncthreads(); } while (0)
 #define GLC_COUNT(k) ((void)0)
 #define GLC_SYNCWARP() __syncwarp()
@@ -69,6 +71,7 @@ static __device__ __forceinline__ bool glc_any(bool p) {
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
 #define GLC_ANY(p) (p)
+#define GLC_ANY_OUTER(p) (p)
 #define GLC_PHASE_SYNC() ((void)0)
 #ifdef GLC_EMU_COUNTERS
 static long long g_emu_count[8];

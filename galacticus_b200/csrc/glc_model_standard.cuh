@@ -550,7 +550,7 @@ struct ModelStandard {
         double hist00 = -1.0, hist01 = -1.0, hist10 = -1.0, hist11 = -1.0;
         double fit = 2.0 * tolerance;
         int count = 0;
-        while (GLC_ANY(looping)) {
+        while (GLC_ANY_OUTER(looping)) {
             int active = 0;
             if (looping) {
                 GLC_COUNT(1);
@@ -690,12 +690,18 @@ struct ModelStandard {
 #pragma unroll 1
         for (int i = 0; i < 2; i++) {
             const bool ion = S.live && i < nIv;
+#if defined(__CUDACC__) && !defined(GLC_NO_COOP_QAG)
+            const double v = qag15_coop(
+                k, [](const Kmt &kk, double r) { return sfr_integrand(kk, r); }, ion, lo[i], hi[i], 1.0e-12,
+                GLC_PARAMS.sfrIntegrationTolerance, st);
+#else
             const double v = qag15(
                 [&](double r) {
                     GLC_COUNT(2);
                     return sfr_integrand(k, r);
                 },
                 ion, lo[i], hi[i], 1.0e-12, GLC_PARAMS.sfrIntegrationTolerance, st);
+#endif
             if (ion) {
                 total += v;
                 if (st == 11) bad = 1;

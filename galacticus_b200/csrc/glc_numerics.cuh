@@ -365,31 +365,20 @@ GLC_DEVICE_INLINE void qag_begin(QagState &Q, bool on, double a, double b, doubl
     Q.summed = 0;
 }
 
-template <class F>
-GLC_DEVICE_INLINE void qag_pass(QagState &Q, F &&f) {
-    // ---- qk15 on (Q.ia, Q.ib): one call site of f
+// abscissa j of the 15-point rule in the order the values are taken: the centre, then the pairs centre -/+ halfLength x_k
+GLC_DEVICE_INLINE double qag_abscissa(double center, double halfLength, int j) {
+    if (j == 0) return center;
+    const int k = c_qk_order[(j - 1) >> 1];
+    const double absc = halfLength * c_xgk[k];
+    return ((j - 1) & 1) ? center + absc : center - absc;
+}
+
+// second half of a pass: qk15's sums over the 15 values fv[] taken on (Q.ia, Q.ib), then qag's bookkeeping
+GLC_DEVICE_INLINE void qag_digest(QagState &Q, const double (&fv)[15]) {
     double result, abserr, resabs, resasc;
     {
-        double fv[15];
-        const double center = 0.5 * (Q.ia + Q.ib);
         const double halfLength = 0.5 * (Q.ib - Q.ia);
         const double absHalfLength = fabs(halfLength);
-        // the 15 abscissae are independent: unrolling by GLC_QAG_UNROLL interleaves their dependency chains (a lone lane is
-        // bound by the latency of dependent FP64 instructions, not by issue slots)
-#if defined(__CUDACC__)
-#pragma unroll kQagUnroll
-#endif
-        for (int j = 0; j < 15; j++) {
-            double x;
-            if (j == 0)
-                x = center;
-            else {
-                const int k = c_qk_order[(j - 1) >> 1];
-                const double absc = halfLength * c_xgk[k];
-                x = ((j - 1) & 1) ? center + absc : center - absc;
-            }
-            fv[j] = f(x);
-        }
         const double fCenter = fv[0];
         double resultGauss = fCenter * c_wg[3];
         double resultKronrod = fCenter * c_wgk[7];
@@ -507,6 +496,21 @@ GLC_DEVICE_INLINE void qag_pass(QagState &Q, F &&f) {
     }
 }
 
+// one pass by one lane: the 15 values one after the other (the micro-task machine's QAG unit, the CPU build)
+template <class F>
+GLC_DEVICE_INLINE void qag_pass(QagState &Q, F &&f) {
+    double fv[15];
+    const double center = 0.5 * (Q.ia + Q.ib);
+    const double halfLength = 0.5 * (Q.ib - Q.ia);
+    // the 15 abscissae are independent: unrolling by GLC_QAG_UNROLL interleaves their dependency chains (a lone lane is
+    // bound by the latency of dependent FP64 instructions, not by issue slots)
+#if defined(__CUDACC__)
+#pragma unroll kQagUnroll
+#endif
+    for (int j = 0; j < 15; j++) fv[j] = f(qag_abscissa(center, halfLength, j));
+    qag_digest(Q, fv);
+}
+
 GLC_DEVICE_INLINE double qag_finish(QagState &Q) {
     if (Q.summed) {
         double sum = 0;
@@ -529,6 +533,68 @@ GLC_DEVICE_INLINE double qag15(F &&f, bool on, double a, double b, double epsabs
     status = Q.status;
     return r;
 }
+
+#if defined(__CUDACC__)
+// The same integral with the 15 values of a pass taken by 15 LANES at once.  In the warp-synchronous kernels few lanes of a
+// warp are inside an integral at the same time (4 of 32 in a dense drain pass, 1 in a lone-lane pass, profiles/r02ac), and
+// the values are independent: two busy lanes ("owners") are served per round, lanes 0-14 take the first owner's abscissae
+// and lanes 16-30 the second's, with the owner's problem (params: plain doubles; centre, half length) fetched by shuffles
+// and the values shuffled back in rule order.  Every value is computed by the same instructions from the same inputs and
+// summed in the same order by its owner (qag_digest), so the result is bit-identical to qag15; with more than kQagCoopMax
+// busy lanes the rounds would outnumber the 15 sequential evaluations and the warp takes the plain pass.
+constexpr int kQagCoopMax = 16;
+template <class T>
+GLC_DEVICE_INLINE T shfl_words(const T &v, int src) {
+    static_assert(sizeof(T) % sizeof(double) == 0, "plain doubles only");
+    T out;
+    const double *in = reinterpret_cast<const double *>(&v);
+    double *o = reinterpret_cast<double *>(&out);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / sizeof(double)); i++) o[i] = __shfl_sync(0xffffffffu, in[i], src);
+    return out;
+}
+template <class P, class F>
+GLC_DEVICE_INLINE double qag15_coop(const P &params, F &&f, bool on, double a, double b, double epsabs, double epsrel,
+                                    int &status) {
+    QagState Q;
+    qag_begin(Q, on, a, b, epsabs, epsrel);
+    const int lane = threadIdx.x & 31, group = lane >> 4, j = lane & 15;
+    for (;;) {
+        unsigned int busy = __ballot_sync(0xffffffffu, Q.busy != 0);
+        if (!busy) break;
+        if (__popc(busy) > kQagCoopMax) {
+            if (Q.busy) qag_pass(Q, [&](double x) { return f(params, x); });
+            continue;
+        }
+        double fv[15];
+        const double center = 0.5 * (Q.ia + Q.ib);
+        const double halfLength = 0.5 * (Q.ib - Q.ia);
+        while (busy) {  // (warp-uniform)
+            const int owner0 = __ffs(busy) - 1;
+            busy &= busy - 1;
+            const int owner1 = busy ? __ffs(busy) - 1 : -1;
+            busy &= busy - 1;  // (0 stays 0)
+            const int owner = group == 0 ? owner0 : owner1;
+            const int src = owner < 0 ? lane : owner;
+            const P p = shfl_words(params, src);
+            const double c = __shfl_sync(0xffffffffu, center, src), h = __shfl_sync(0xffffffffu, halfLength, src);
+            double v = 0.0;
+            if (owner >= 0 && j < 15) v = f(p, qag_abscissa(c, h, j));
+            const int base = lane == owner1 ? 16 : 0;
+            const bool mine = lane == owner0 || lane == owner1;
+#pragma unroll
+            for (int k = 0; k < 15; k++) {
+                const double t = __shfl_sync(0xffffffffu, v, base + k);
+                if (mine) fv[k] = t;
+            }
+        }
+        if (Q.busy) qag_digest(Q, fv);
+    }
+    const double r = qag_finish(Q);
+    status = Q.status;
+    return r;
+}
+#endif
 
 // value of a table1DLinearLinear with n points on [xmin,xmax] populated by g (evaluated on the fly)
 template <class G>
