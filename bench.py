@@ -49,11 +49,11 @@ UNIT = "accepted RKCK node-ODE steps/s"
 # machine_kernel and drain_kernel launch of one whole pass divided by the pass's RHS counter (ncu,
 # profiles/r01f_fp64_ops_whole_pass.txt: 2.217e11 / 13 693 801).
 FLOP_PER_RHS = 16.2e3
-# DRAM bytes per evaluation from the ncu --set full captures of the final round-2 build: machine_kernel = second bulk slice
+# DRAM bytes per evaluation from the ncu --set full captures of the round-2 build: machine_kernel = second bulk slice
 # (profiles/r02r_machine_kernel_bulk_slice.txt: 45.68 + 24.09 GB over the slice's 5 665 006 evaluations); drain_kernel = the
-# last, one-node-per-warp pass (profiles/r02r_drain_kernel_lone_lane_pass.txt: 1.77 MB over ~2.5e4 evaluations -- the drain
-# works out of L1/L2)
-DRAM_BYTES_PER_RHS = {"machine_kernel": (45.677725e9 + 24.085883e9) / 5665006.0, "drain_kernel": (1.673216e6 + 0.096e6) / 2.5e4}
+# dense pass, which is where the drain spends its time (profiles/r02aj_drain_kernel_dense_pass_coop_qag.txt: 0.67 + 1.84 GB over
+# the pass's ~4.46e6 evaluations; the last, one-node-per-warp passes work out of L1/L2: 71 B per evaluation, r02r)
+DRAM_BYTES_PER_RHS = {"machine_kernel": (45.677725e9 + 24.085883e9) / 5665006.0, "drain_kernel": (0.666549e9 + 1.837163e9) / 4.46e6}
 N_Y = 24
 BLACK_HOLE_FRACTION = 0.7
 MW_ROOT_MASS, MW_RESOLUTION = 1.52e12, 1.0e9  # testSuite/parameters/benchmark_milkyWay.xml:30-42
