@@ -97,7 +97,10 @@ struct glc_evolver {
     int32_t *h_collect_meta = nullptr;   // pinned
     int64_t collect_meta_cap = 0;
     int32_t stream_sparse_budget = 32, stream_dense_budget = 12;  // evaluations per lane in one lane pass of a streaming tick
-    int32_t stream_spread = 0;           // lane passes: spread the nodes over all warps (measured slower on forests: profiles/r02k)
+    int32_t stream_spread = 2;           // lane passes with more nodes than warps: 0 = 32 nodes per warp on as few blocks as needed, 1 = spread
+                                         // over all resident warps, 2 = over one block per SM (a second block per SM only when 32 per warp do not
+                                         // suffice).  2 since the GK15 pass is shared by lanes (thin warps got cheaper): 1000-tree forest 20.6-21.3 ->
+                                         // 19.9 s, volume forest 16.2 -> 14.7 s (gpu_r2aw.sh); 1 is as slow as 0 (8 warps per SM on 8 code paths)
     int32_t stream_sort = 0;             // lane passes with more nodes than warps: list sorted by kind of node (component set)
     int32_t stream_express = 0;          // lane passes with more nodes than warps: nodes whose score (evaluations spent so far +
                                          // 6 x predicted remaining steps) reaches this get a warp each; 0 = off
