@@ -1148,11 +1148,12 @@ static int stream_tick(glc_evolver *ev, int n, unsigned long long *hc) {
         // evaluation budget of the pass shrinks with the number of nodes per warp so that a tick stays a few milliseconds long
         const int warpsFree = std::max(kBlock / 32, warpsResident - (nexpress + kBlock / 32 - 1) / (kBlock / 32) * (kBlock / 32));
         // stream_spread: 0 = one node per warp when they fit, else 32 per warp on as few blocks as needed; 1 = over all resident
-        // warps; 2 = over one block per SM (a second block per SM only when 32 nodes per warp do not suffice)
+        // warps; 2 = over one block per SM as soon as there are more nodes than that block has warps (a second block per SM only
+        // when 32 nodes per warp do not suffice)
         const int warpsOne = ev->num_sms * (kBlock / 32);
         int lanes = A.nheld <= warpsFree ? 1 : 32;
         if (ev->stream_spread == 1) lanes = std::min(32, (A.nheld + warpsFree - 1) / warpsFree);
-        if (ev->stream_spread == 2 && A.nheld > warpsFree) lanes = std::min(32, (A.nheld + warpsOne - 1) / warpsOne);
+        if (ev->stream_spread == 2 && A.nheld > warpsOne) lanes = std::min(32, (A.nheld + warpsOne - 1) / warpsOne);
         A.drainLanes = lanes >= 32 ? 0 : lanes;
         A.drainBlockSync = (lanes > 1) ? ev->drain_block_sync : 0;
         A.budget = ev->stream_sparse_budget - (int)((long long)(ev->stream_sparse_budget - ev->stream_dense_budget) * (lanes - 1) / 31);
