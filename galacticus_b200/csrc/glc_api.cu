@@ -77,7 +77,10 @@ struct glc_evolver {
     int32_t *d_held = nullptr;
     float *d_held_score = nullptr;
     int64_t held_cap = 0;
-    int32_t drain_express = 1;      // first drain pass: predicted-longest nodes one per warp on stream2
+    int32_t drain_express = 0;      // 1 = first drain pass: the predicted-longest nodes one per warp on stream2 beside a dense launch on the
+                                    // other block per SM.  Off since the GK15 pass is shared by lanes: the express launch is over after 121 ms
+                                    // (profiles/r02aq: the nodes that end the pass are not the predicted ones) and meanwhile halves the lanes of
+                                    // the dense launch; 10^6-node pass 1588-1642 ms without it, 1623-1715 with it (gpu_r2bc.sh, alternating)
     float drain_age_weight = 0.0f;  // express selection: score = predicted remaining steps (0) or 6 x that + weight x evaluations so far
     int32_t drain_block_sync = 2;   // vote level of dense drain / lane passes (glc_common.cuh): the warps of a block start every evaluation
                                     // together and meet again between the phases of the rate function -- the kernel is instruction-fetch
