@@ -31,23 +31,32 @@ def fast_turnover_batch(p, n, seed, trivial_fraction=0.9):
     return props, flags, t_end
 
 
-def _run(oracle_lib, n, seed, budget=0):
+def _run(oracle_lib, n, seed, budget=0, env=None, trivial_fraction=0.9):
+    import os
+
     from galacticus_b200.evolver import Evolver
 
     p = cases.standard_params(with_black_holes=True)
-    ev = Evolver(0)
+    saved = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        ev = Evolver(0)  # (the execution knobs are read when the evolver is created)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     synthetic.install(ev, p)
     ev.set_option(abi.GLC_OPT_MICROTASK_MACHINE, 1)
     if budget:
         ev.set_option(abi.GLC_OPT_SLICE_BUDGET, budget)
     o = oracle_lib.Oracle(fast=False)
     synthetic.install(o, p)
-    props, flags, t_end = fast_turnover_batch(p, n, seed)
+    props, flags, t_end = fast_turnover_batch(p, n, seed, trivial_fraction)
     pg, fg = props.copy(), flags.copy()
     po, fo = props.copy(), flags.copy()
     sg, ig, cg = ev.evolve_batch(pg, fg, t_end)
-    import os
-
     so, io, co = o.evolve_batch(po, fo, t_end, n_threads=os.cpu_count() or 1)
     ev.close()
     assert cg["nodes"] == n, "every node is fetched exactly once"
@@ -63,6 +72,12 @@ def _run(oracle_lib, n, seed, budget=0):
 def test_fast_turnover_batch_600k(oracle_lib):
     """600 000 nodes, 90 per cent of which finish within a few units: the regime in which round 1 lost nodes."""
     _run(oracle_lib, 600_000, seed=4000)
+
+
+def test_hand_over_with_express_launch(oracle_lib):
+    """The hand-over variant that is no longer the default (glc_evolver::drain_express): the held nodes with the most predicted
+    steps one per warp on a second stream beside a dense launch on the other block per SM, then dense passes over what is left."""
+    _run(oracle_lib, 300_000, seed=4003, trivial_fraction=0.5, env={"GLC_DRAIN_EXPRESS": "1"})
 
 
 def test_fast_turnover_batch_user_slices(oracle_lib):
